@@ -1,0 +1,309 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+Pure-Python restatement of automerge-classic's *encode* side, used to build small binary changes from
+the JSON change objects the reference's tests use (fixtures only; never on the product path, never
+timed).  Independent of the C++ restatement in codec.hpp/columnar.hpp so that the two cross-check
+each other through the golden bytes of the reference's tests.
+
+Follows (paths relative to /root/reference):
+  backend/encoding.js:57-286     Encoder (LEB128)
+  backend/encoding.js:558-783    RLEEncoder (as canonical batch encoder)
+  backend/encoding.js:932-998    DeltaEncoder
+  backend/encoding.js:1061-1135  BooleanEncoder
+  backend/columnar.js:133-170    parseAllOpIds
+  backend/columnar.js:176-292    encodeObjectId / encodeOperationKey / encodeOperationAction / encodeValue
+  backend/columnar.js:370-436    encodeOps
+  backend/columnar.js:446-475    expandMultiOps
+  backend/columnar.js:659-686    encodeContainer
+  backend/columnar.js:710-739    encodeChange
+  src/common.js:22-28            parseOpId
+"""
+import hashlib
+import re
+import struct
+import zlib
+
+MAGIC = bytes([0x85, 0x6f, 0x4a, 0x83])
+ACTIONS = ['makeMap', 'set', 'makeList', 'del', 'makeText', 'inc', 'makeTable', 'link']
+VT = dict(NULL=0, FALSE=1, TRUE=2, LEB128_UINT=3, LEB128_INT=4, IEEE754=5, UTF8=6, BYTES=7, COUNTER=8, TIMESTAMP=9)
+MAX_SAFE = 2 ** 53 - 1
+DEFLATE_MIN_SIZE = 256
+
+
+def uleb(v):
+    if v < 0 or v > MAX_SAFE:
+        raise ValueError('number out of range')
+    out = bytearray()
+    while True:
+        b = v & 0x7f
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def sleb(v):
+    if v < -MAX_SAFE or v > MAX_SAFE:
+        raise ValueError('number out of range')
+    out = bytearray()
+    while True:
+        b = v & 0x7f
+        v >>= 7
+        if (v == 0 and not b & 0x40) or (v == -1 and b & 0x40):
+            out.append(b)
+            return bytes(out)
+        out.append(b | 0x80)
+
+
+def prefixed(b):
+    return uleb(len(b)) + b
+
+
+def hex_bytes(h):
+    if not re.fullmatch(r'([0-9a-f][0-9a-f])*', h):
+        raise ValueError('value is not hexadecimal')
+    return bytes.fromhex(h)
+
+
+def rle_encode(values, kind):
+    """kind: 'uint' | 'int' | 'utf8'; values may contain None."""
+    def raw(v):
+        if kind == 'uint':
+            return uleb(v)
+        if kind == 'int':
+            return sleb(v)
+        return prefixed(v.encode('utf-8'))
+    if all(v is None for v in values):
+        return b''
+    runs = []
+    for v in values:
+        if runs and runs[-1][0] == v and type(runs[-1][0]) is type(v):
+            runs[-1][1] += 1
+        else:
+            runs.append([v, 1])
+    out = bytearray()
+    lit = []
+
+    def flush():
+        if lit:
+            out.extend(sleb(-len(lit)))
+            for x in lit:
+                out.extend(raw(x))
+            lit.clear()
+    for v, n in runs:
+        if v is None:
+            flush()
+            out.extend(sleb(0))
+            out.extend(uleb(n))
+        elif n >= 2:
+            flush()
+            out.extend(sleb(n))
+            out.extend(raw(v))
+        else:
+            lit.append(v)
+    flush()
+    return bytes(out)
+
+
+def delta_encode(values):
+    out, last = [], 0
+    for v in values:
+        if v is None:
+            out.append(None)
+        else:
+            out.append(v - last)
+            last = v
+    return rle_encode(out, 'int')
+
+
+def bool_encode(values):
+    out = bytearray()
+    last, count = False, 0
+    for v in values:
+        if v == last:
+            count += 1
+        else:
+            out.extend(uleb(count))
+            last, count = v, 1
+    if count > 0:
+        out.extend(uleb(count))
+    return bytes(out)
+
+
+def parse_op_id(s):
+    m = re.fullmatch(r'(\d+)@(.*)', s or '')
+    if not m:
+        raise ValueError('Not a valid opId: %s' % s)
+    return int(m.group(1)), m.group(2)
+
+
+def expand_multi_ops(ops, start_op, actor):
+    op_num, out = start_op, []
+    for op in ops:
+        if op.get('action') == 'set' and 'values' in op and op.get('insert'):
+            if op.get('pred'):
+                raise ValueError('multi-insert pred must be empty')
+            last = op['elemId']
+            for value in op['values']:
+                o = {'action': 'set', 'obj': op['obj'], 'elemId': last, 'value': value, 'pred': [], 'insert': True}
+                if 'datatype' in op:
+                    o['datatype'] = op['datatype']
+                out.append(o)
+                last = '%d@%s' % (op_num, actor)
+                op_num += 1
+        elif op.get('action') == 'del' and op.get('multiOp', 0) > 1:
+            if len(op['pred']) != 1:
+                raise ValueError('multiOp deletion must have exactly one pred')
+            ec, ea = parse_op_id(op['elemId'])
+            pc, pa = parse_op_id(op['pred'][0])
+            for i in range(op['multiOp']):
+                out.append({'action': 'del', 'obj': op['obj'], 'elemId': '%d@%s' % (ec + i, ea), 'pred': ['%d@%s' % (pc + i, pa)]})
+                op_num += 1
+        else:
+            out.append(op)
+            op_num += 1
+    return out
+
+
+def encode_value(op, val_len, val_raw):
+    action, value = op.get('action'), op.get('value')
+    if action not in ('set', 'inc') or value is None:
+        val_len.append(VT['NULL'])
+    elif value is False:
+        val_len.append(VT['FALSE'])
+    elif value is True:
+        val_len.append(VT['TRUE'])
+    elif isinstance(value, str):
+        b = value.encode('utf-8')
+        val_raw.extend(b)
+        val_len.append(len(b) << 4 | VT['UTF8'])
+    elif isinstance(value, (bytes, bytearray)):
+        dt = op.get('datatype')
+        tag = dt if isinstance(dt, int) and 10 <= dt <= 15 else VT['BYTES']
+        val_raw.extend(value)
+        val_len.append(len(value) << 4 | tag)
+    elif isinstance(value, (int, float)):
+        dt = op.get('datatype')
+        if dt == 'counter':
+            tag, b = VT['COUNTER'], sleb(int(value))
+        elif dt == 'timestamp':
+            tag, b = VT['TIMESTAMP'], sleb(int(value))
+        elif dt == 'uint':
+            tag, b = VT['LEB128_UINT'], uleb(int(value))
+        elif dt == 'int':
+            tag, b = VT['LEB128_INT'], sleb(int(value))
+        elif dt == 'float64':
+            tag, b = VT['IEEE754'], struct.pack('<d', float(value))
+        elif float(value).is_integer() and abs(value) <= MAX_SAFE and not (isinstance(value, float) and dt == 'float64'):
+            tag, b = VT['LEB128_INT'], sleb(int(value))
+        else:
+            tag, b = VT['IEEE754'], struct.pack('<d', float(value))
+        val_raw.extend(b)
+        val_len.append(len(b) << 4 | tag)
+    else:
+        raise ValueError('Unsupported value in operation: %r' % (value,))
+
+
+def encode_change_raw(change, compress=True):
+    """Returns (bytes, hash_hex). `change` is the JSON form used throughout the reference's tests."""
+    actor = change['actor']
+    ops = expand_multi_ops(change['ops'], change['startOp'], actor)
+    # parseAllOpIds(single=True): actor table = [author] + sorted(other actors)
+    actors = {actor}
+    parsed = []
+    for op in ops:
+        p = dict(op)
+        p['_obj'] = None if op['obj'] == '_root' else parse_op_id(op['obj'])
+        elem = op.get('elemId')
+        p['_elem'] = elem if (elem is None or elem == '_head') else parse_op_id(elem)
+        p['_child'] = parse_op_id(op['child']) if op.get('child') else None
+        p['_pred'] = [parse_op_id(x) for x in op.get('pred', [])]
+        for ref in [p['_obj'], p['_elem'] if isinstance(p['_elem'], tuple) else None, p['_child']] + p['_pred']:
+            if ref:
+                actors.add(ref[1])
+        parsed.append(p)
+    actor_ids = [actor] + sorted(a for a in actors if a != actor)
+    num = {a: i for i, a in enumerate(actor_ids)}
+
+    cols = {k: [] for k in ['objActor', 'objCtr', 'keyActor', 'keyCtr', 'keyStr', 'insert', 'action', 'valLen',
+                            'chldActor', 'chldCtr', 'predNum', 'predActor', 'predCtr']}
+    val_raw = bytearray()
+    for p in parsed:
+        if p['_obj'] is None:
+            cols['objActor'].append(None); cols['objCtr'].append(None)
+        else:
+            if p['_obj'][0] <= 0:
+                raise ValueError('Unexpected objectId reference')
+            cols['objActor'].append(num[p['_obj'][1]]); cols['objCtr'].append(p['_obj'][0])
+        if p.get('key'):
+            cols['keyActor'].append(None); cols['keyCtr'].append(None); cols['keyStr'].append(p['key'])
+        elif p['_elem'] == '_head' and p.get('insert'):
+            cols['keyActor'].append(None); cols['keyCtr'].append(0); cols['keyStr'].append(None)
+        elif isinstance(p['_elem'], tuple) and p['_elem'][0] > 0:
+            cols['keyActor'].append(num[p['_elem'][1]]); cols['keyCtr'].append(p['_elem'][0]); cols['keyStr'].append(None)
+        else:
+            raise ValueError('Unexpected operation key: %r' % (p,))
+        cols['insert'].append(bool(p.get('insert')))
+        a = p['action']
+        if a in ACTIONS:
+            cols['action'].append(ACTIONS.index(a))
+        elif isinstance(a, int):
+            cols['action'].append(a)
+        else:
+            raise ValueError('Unexpected operation action: %r' % (a,))
+        encode_value(p, cols['valLen'], val_raw)
+        if p['_child'] and p['_child'][0]:
+            cols['chldActor'].append(num[p['_child'][1]]); cols['chldCtr'].append(p['_child'][0])
+        else:
+            cols['chldActor'].append(None); cols['chldCtr'].append(None)
+        preds = sorted(p['_pred'])   # compareParsedOpIds: counter, then actorId string
+        cols['predNum'].append(len(preds))
+        for c, a_ in preds:
+            cols['predActor'].append(num[a_]); cols['predCtr'].append(c)
+
+    column_list = [
+        (0x01, rle_encode(cols['objActor'], 'uint')), (0x02, rle_encode(cols['objCtr'], 'uint')),
+        (0x11, rle_encode(cols['keyActor'], 'uint')), (0x13, delta_encode(cols['keyCtr'])),
+        (0x15, rle_encode(cols['keyStr'], 'utf8')), (0x34, bool_encode(cols['insert'])),
+        (0x42, rle_encode(cols['action'], 'uint')), (0x56, rle_encode(cols['valLen'], 'uint')),
+        (0x57, bytes(val_raw)), (0x61, rle_encode(cols['chldActor'], 'uint')), (0x63, delta_encode(cols['chldCtr'])),
+        (0x70, rle_encode(cols['predNum'], 'uint')), (0x71, rle_encode(cols['predActor'], 'uint')),
+        (0x73, delta_encode(cols['predCtr']))]
+
+    body = bytearray()
+    deps = sorted(change.get('deps', []))
+    body += uleb(len(deps))
+    for d in deps:
+        body += hex_bytes(d)
+    body += prefixed(hex_bytes(actor)) + uleb(change['seq']) + uleb(change['startOp']) + sleb(change.get('time', 0))
+    body += prefixed((change.get('message') or '').encode('utf-8'))
+    body += uleb(len(actor_ids) - 1)
+    for a in actor_ids[1:]:
+        body += prefixed(hex_bytes(a))
+    nonempty = [(cid, buf) for cid, buf in column_list if len(buf) > 0]
+    body += uleb(len(nonempty))
+    for cid, buf in nonempty:
+        body += uleb(cid) + uleb(len(buf))
+    for cid, buf in column_list:
+        body += buf
+    if change.get('extraBytes'):
+        body += bytes(change['extraBytes'])
+
+    header = bytes([1]) + uleb(len(body))
+    digest = hashlib.sha256(header + bytes(body)).digest()
+    raw = MAGIC + digest[:4] + header + bytes(body)
+    if compress and len(raw) >= DEFLATE_MIN_SIZE:
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp = co.compress(bytes(body)) + co.flush()
+        raw = MAGIC + digest[:4] + bytes([2]) + uleb(len(comp)) + comp
+    return raw, digest.hex()
+
+
+def encode_change(change, compress=True):
+    return encode_change_raw(change, compress)[0]
+
+
+def change_hash(change):
+    return encode_change_raw(change, False)[1]
