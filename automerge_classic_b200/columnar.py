@@ -1,9 +1,11 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY.
+"""Host-side mirror of the reference's change *encoder* (backend/columnar.js encodeChange).
 
-Pure-Python restatement of automerge-classic's *encode* side, used to build small binary changes from
-the JSON change objects the reference's tests use (fixtures only; never on the product path, never
-timed).  Independent of the C++ restatement in codec.hpp/columnar.hpp so that the two cross-check
-each other through the golden bytes of the reference's tests.
+The reference keeps `encodeChange` in host JavaScript even with a native backend plugged in:
+`Backend.applyLocalChange` (backend/backend.js:54-91) encodes the frontend's change request on the
+host and then calls `applyChanges` with the binary change.  This module is that host-side encoder
+for the Python mirror of the Backend facade (automerge_classic_b200/backend.py); it is also what the
+fixture extractor (tools/jsfixtures/extract.py) uses to turn the reference tests' JSON changes into
+bytes.  It is pinned byte-for-byte by the annotated golden change of test/columnar_test.js:8-37.
 
 Follows (paths relative to /root/reference):
   backend/encoding.js:57-286     Encoder (LEB128)

@@ -140,6 +140,30 @@ class OracleDoc:
         _check(lib().orc_get_heads(self.h, C.byref(out), C.byref(err)), err.value)
         return json.loads(_take_str(out))
 
+    def clock(self):
+        out, err = C.c_void_p(), C.c_void_p()
+        _check(lib().orc_clock_json(self.h, C.byref(out), C.byref(err)), err.value)
+        return json.loads(_take_str(out))
+
+    def max_op(self):
+        v = C.c_int64()
+        lib().orc_max_op(self.h, C.byref(v))
+        return v.value
+
+    def hash_by_actor(self, actor, index):
+        out, err = C.c_void_p(), C.c_void_p()
+        _check(lib().orc_hash_by_actor(self.h, actor.encode(), C.c_int64(index), C.byref(out), C.byref(err)), err.value)
+        return _take_str(out) or None
+
+    def get_change_by_hash(self, hash_):
+        out, n, err = C.c_void_p(), C.c_size_t(), C.c_void_p()
+        _check(lib().orc_get_change_by_hash(self.h, hash_.encode(), C.byref(out), C.byref(n), C.byref(err)), err.value)
+        if not out.value:
+            return None
+        b = C.string_at(out, n.value)
+        lib().orc_free_mem(out)
+        return b
+
     def get_changes(self, have_deps):
         out, n, err = C.c_void_p(), C.c_size_t(), C.c_void_p()
         _check(lib().orc_get_changes(self.h, ''.join(have_deps).encode(), C.byref(out), C.byref(n), C.byref(err)), err.value)

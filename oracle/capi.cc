@@ -143,6 +143,25 @@ int orc_get_missing_deps(void* d, const char* heads_hex, char** out_json, char**
         *out_json = dupStr(jsonStrList(((BackendDoc*)d)->getMissingDeps(hs))); return 0;)
 }
 
+int orc_clock_json(void* d, char** out_json, char** err) {
+  GUARD(BackendDoc* doc = (BackendDoc*)d; std::string out = "{"; bool first = true;
+        for (auto& kv : doc->clock) { if (!first) out += ","; first = false; jsonStr(out, kv.first); out += ":" + std::to_string(kv.second); }
+        out += "}"; *out_json = dupStr(out); return 0;)
+}
+// backend.js:34-45 hashByActor: returns "" when unknown
+int orc_hash_by_actor(void* d, const char* actor_hex, int64_t index, char** out, char** err) {
+  GUARD(BackendDoc* doc = (BackendDoc*)d; doc->requireHashGraph(); auto it = doc->hashesByActor.find(actor_hex);
+        std::string h; if (it != doc->hashesByActor.end() && index >= 0 && index < (int64_t)it->second.size()) h = it->second[index];
+        *out = dupStr(h); return 0;)
+}
+// new.js:1999-2002; *len = (size_t)-1 when the hash is unknown (undefined)
+int orc_get_change_by_hash(void* d, const char* hash_hex, uint8_t** out, size_t* len, char** err) {
+  GUARD(BackendDoc* doc = (BackendDoc*)d; doc->requireHashGraph(); auto it = doc->changeIndexByHash.find(hash_hex);
+        if (it == doc->changeIndexByHash.end() || it->second < 0 || it->second >= (int64_t)doc->changes.size()) { *out = nullptr; *len = (size_t)-1; return 0; }
+        const std::string& c = doc->changes[it->second]; *out = (uint8_t*)malloc(c.size() + 1); memcpy(*out, c.data(), c.size()); *len = c.size(); return 0;)
+}
+int orc_max_op(void* d, int64_t* out) { *out = ((BackendDoc*)d)->maxOp; return 0; }
+
 // Blocks: encoded doc columns + metadata, as the reference's tests inspect them (checkColumns,
 // test/new_backend_test.js:7-22)
 int orc_blocks_json(void* d, char** out_json, char** err) {
