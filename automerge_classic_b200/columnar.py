@@ -149,6 +149,10 @@ def expand_multi_ops(ops, start_op, actor):
                 raise ValueError('multi-insert pred must be empty')
             last = op['elemId']
             for value in op['values']:
+                dt = op.get('datatype')
+                ok = (isinstance(value, (str, bool)) or value is None) if dt is None else (isinstance(value, (int, float)) and not isinstance(value, bool))
+                if not ok:
+                    raise ValueError('Decode failed: bad value/datatype association (%s,%s)' % (value, dt))
                 o = {'action': 'set', 'obj': op['obj'], 'elemId': last, 'value': value, 'pred': [], 'insert': True}
                 if 'datatype' in op:
                     o['datatype'] = op['datatype']
@@ -309,3 +313,269 @@ def encode_change(change, compress=True):
 
 def change_hash(change):
     return encode_change_raw(change, False)[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# Decode side (host mirror of decodeChange; used by tests and by callers that want JSON changes).
+# Follows backend/encoding.js:293-534 (Decoder), :789-920 (RLEDecoder), :1004-1051 (DeltaDecoder),
+# :1141-1207 (BooleanDecoder); backend/columnar.js:300-361 (decodeValue, decodeValueColumns),
+# :483-523 (decodeOps, checkSortedOpIds), :577-607 (decodeColumns), :609-652, :688-708, :741-776.
+
+class DecodeError(ValueError):
+    """The reference throws RangeError for all of these."""
+
+
+class _Dec:
+    def __init__(self, buf):
+        self.buf, self.off = bytes(buf), 0
+
+    @property
+    def done(self):
+        return self.off == len(self.buf)
+
+    def uleb(self, limit=MAX_SAFE):
+        result, shift = 0, 0
+        while self.off < len(self.buf):
+            b = self.buf[self.off]
+            if shift == 63 and b & 0xfe:
+                raise DecodeError('number out of range')
+            result |= (b & 0x7f) << shift
+            shift += 7
+            self.off += 1
+            if not b & 0x80:
+                if result > limit:
+                    raise DecodeError('number out of range')
+                return result
+        raise DecodeError('buffer ended with incomplete number')
+
+    def sleb(self):
+        result, shift = 0, 0
+        while self.off < len(self.buf):
+            b = self.buf[self.off]
+            if shift == 63 and b not in (0, 0x7f):
+                raise DecodeError('number out of range')
+            result |= (b & 0x7f) << shift
+            shift += 7
+            self.off += 1
+            if not b & 0x80:
+                if b & 0x40:
+                    result -= 1 << shift
+                if result < -MAX_SAFE or result > MAX_SAFE:
+                    raise DecodeError('number out of range')
+                return result
+        raise DecodeError('buffer ended with incomplete number')
+
+    def raw(self, n):
+        if self.off + n > len(self.buf):
+            raise DecodeError('subarray exceeds buffer size')
+        self.off += n
+        return self.buf[self.off - n:self.off]
+
+    def prefixed(self):
+        return self.raw(self.uleb())
+
+
+def rle_decode(buf, kind):
+    d, out, state, last = _Dec(buf), [], None, object()
+    def raw():
+        if kind == 'uint':
+            return d.uleb()
+        if kind == 'int':
+            return d.sleb()
+        return d.prefixed().decode('utf-8', 'replace')
+    while not d.done:
+        count = d.sleb()
+        if count > 1:
+            v = raw()
+            if state in ('rep', 'lit') and v == last:
+                raise DecodeError('Successive repetitions with the same value are not allowed')
+            state, last = 'rep', v
+            out.extend([v] * count)
+        elif count == 1:
+            raise DecodeError('Repetition count of 1 is not allowed, use a literal instead')
+        elif count < 0:
+            if state == 'lit':
+                raise DecodeError('Successive literals are not allowed')
+            state = 'lit'
+            for _ in range(-count):
+                v = raw()
+                if v == last:
+                    raise DecodeError('Repetition of values is not allowed in literal')
+                last = v
+                out.append(v)
+        else:
+            if state == 'nulls':
+                raise DecodeError('Successive null runs are not allowed')
+            n = d.uleb()
+            if n == 0:
+                raise DecodeError('Zero-length null runs are not allowed')
+            state, last = 'nulls', None
+            out.extend([None] * n)
+    return out
+
+
+def delta_decode(buf):
+    out, acc = [], 0
+    for v in rle_decode(buf, 'int'):
+        if v is None:
+            out.append(None)
+        else:
+            acc += v
+            out.append(acc)
+    return out
+
+
+def bool_decode(buf):
+    d, out, val, first = _Dec(buf), [], True, True
+    while not d.done:
+        n = d.uleb()
+        val = not val
+        if n == 0 and not first:
+            raise DecodeError('Zero-length runs are not allowed')
+        first = False
+        out.extend([val] * n)
+    return out
+
+
+def decode_value(size_tag, raw):
+    tag = size_tag % 16
+    if size_tag == VT['NULL']:
+        return None, None
+    if size_tag == VT['FALSE']:
+        return False, None
+    if size_tag == VT['TRUE']:
+        return True, None
+    if tag == VT['UTF8']:
+        return raw.decode('utf-8', 'replace'), None
+    if tag == VT['LEB128_UINT']:
+        return _Dec(raw).uleb(), 'uint'
+    if tag == VT['LEB128_INT']:
+        return _Dec(raw).sleb(), 'int'
+    if tag == VT['IEEE754']:
+        if len(raw) != 8:
+            raise DecodeError('Invalid length for floating point number: %d' % len(raw))
+        return struct.unpack('<d', raw)[0], 'float64'
+    if tag == VT['COUNTER']:
+        return _Dec(raw).sleb(), 'counter'
+    if tag == VT['TIMESTAMP']:
+        return _Dec(raw).sleb(), 'timestamp'
+    return bytes(raw), tag
+
+
+def split_container(buf):
+    """columnar.js:688-708 -> (chunk_type, body, hash_hex); verifies magic + checksum."""
+    buf = bytes(buf)
+    d = _Dec(buf)
+    if d.raw(4) != MAGIC:
+        raise DecodeError('Data does not begin with magic bytes 85 6f 4a 83')
+    expected = d.raw(4)
+    start = d.off
+    chunk_type = d.raw(1)[0]
+    body = d.raw(d.uleb())
+    digest = hashlib.sha256(buf[start:d.off]).digest()
+    if digest[:4] != expected:
+        raise DecodeError('checksum does not match data')
+    return chunk_type, body, digest.hex(), d.off
+
+
+def inflate_change(buf):
+    buf = bytes(buf)
+    if len(buf) > 8 and buf[8] == 2:
+        d = _Dec(buf[9:])
+        comp = d.raw(d.uleb())
+        body = zlib.decompress(comp, -15)
+        return buf[:8] + bytes([1]) + uleb(len(body)) + body
+    return buf
+
+
+def _check_sorted(ids):
+    last = None
+    for cur in ids:
+        if last is not None and not (last[0] < cur[0] or (last[0] == cur[0] and last[1] < cur[1])):
+            raise DecodeError('operation IDs are not in ascending order')
+        last = cur
+
+
+def decode_change(buf):
+    """columnar.js:770-776 decodeChange: binary change -> JSON change (with `hash`)."""
+    buf = inflate_change(buf)
+    chunk_type, body, hash_hex, end = split_container(buf)
+    if end != len(buf):
+        raise DecodeError('Encoded change has trailing data')
+    if chunk_type != 1:
+        raise DecodeError('Unexpected chunk type: %d' % chunk_type)
+    d = _Dec(body)
+    deps = [d.raw(32).hex() for _ in range(d.uleb())]
+    actor = d.prefixed().hex()
+    change = {'actor': actor, 'seq': d.uleb(), 'startOp': d.uleb(), 'time': d.sleb(),
+              'message': d.prefixed().decode('utf-8', 'replace'), 'deps': deps}
+    actor_ids = [actor] + [d.prefixed().hex() for _ in range(d.uleb())]
+    infos, last_id = [], -1
+    for _ in range(d.uleb()):
+        cid, ln = d.uleb(), d.uleb()
+        if last_id >= 0 and (cid & ~8) <= (last_id & ~8):
+            raise DecodeError('Columns must be in ascending order')
+        last_id = cid
+        infos.append((cid, ln))
+    cols = {}
+    for cid, ln in infos:
+        if cid & 8:
+            raise DecodeError('change must not contain deflated columns')
+        cols[cid] = d.raw(ln)
+    if not d.done:
+        change['extraBytes'] = d.raw(len(d.buf) - d.off)
+
+    def col(cid, kind):
+        b = cols.get(cid, b'')
+        return bool_decode(b) if kind == 'bool' else (delta_decode(b) if kind == 'delta' else rle_decode(b, kind))
+    action = col(0x42, 'uint')
+    n = len(action)
+    for cid, b in cols.items():   # the row count is the longest column (decodeColumns: any column not done)
+        if cid not in (0x57, 0x71, 0x73) and cid in (0x01, 0x02, 0x11, 0x13, 0x15, 0x34, 0x56, 0x61, 0x63, 0x70):
+            kind = 'bool' if cid == 0x34 else ('delta' if cid & 7 == 3 else ('utf8' if cid & 7 == 5 else 'uint'))
+            n = max(n, len(col(cid, kind)))
+
+    def padded(values, fill=None):
+        return values + [fill] * (n - len(values))
+    obj_actor, obj_ctr = padded(col(0x01, 'uint')), padded(col(0x02, 'uint'))
+    key_actor, key_ctr, key_str = padded(col(0x11, 'uint')), padded(col(0x13, 'delta')), padded(col(0x15, 'utf8'))
+    insert, action, val_len = padded(col(0x34, 'bool'), False), padded(action), padded(col(0x56, 'uint'))
+    chld_actor, chld_ctr = padded(col(0x61, 'uint')), padded(col(0x63, 'delta'))
+    pred_num, pred_actor, pred_ctr = padded(col(0x70, 'uint')), col(0x71, 'uint'), col(0x73, 'delta')
+    raw = _Dec(cols.get(0x57, b''))
+
+    def actor_of(i):
+        if i is None:
+            return None
+        if i >= len(actor_ids):
+            raise DecodeError('No actor index %d' % i)
+        return actor_ids[i]
+    ops, pi = [], 0
+    for i in range(n):
+        obj = '_root' if obj_ctr[i] is None else '%d@%s' % (obj_ctr[i], actor_of(obj_actor[i]))
+        act = ACTIONS[action[i]] if action[i] is not None and action[i] < len(ACTIONS) else action[i]
+        if key_str[i]:
+            op = {'obj': obj, 'key': key_str[i], 'action': act}
+        else:
+            op = {'obj': obj, 'elemId': '_head' if key_ctr[i] == 0 else '%s@%s' % (key_ctr[i], actor_of(key_actor[i])), 'action': act}
+        op['insert'] = bool(insert[i])
+        size_tag = val_len[i] if val_len[i] is not None else 0
+        value, datatype = decode_value(size_tag, raw.raw(size_tag >> 4))
+        if act in ('set', 'inc'):
+            op['value'] = value
+            if datatype:
+                op['datatype'] = datatype
+        if bool(chld_ctr[i]) != bool(chld_actor[i] is not None and actor_of(chld_actor[i])):
+            raise DecodeError('Mismatched child columns: %s and %s' % (chld_ctr[i], chld_actor[i]))
+        if chld_ctr[i] is not None:
+            op['child'] = '%d@%s' % (chld_ctr[i], actor_of(chld_actor[i]))
+        k = pred_num[i] or 0
+        preds = [(pred_ctr[pi + j] if pi + j < len(pred_ctr) else None,
+                  actor_of(pred_actor[pi + j]) if pi + j < len(pred_actor) else None) for j in range(k)]
+        pi += k
+        _check_sorted(preds)
+        op['pred'] = ['%s@%s' % p for p in preds]
+        ops.append(op)
+    change['ops'] = ops
+    change['hash'] = hash_hex
+    return change

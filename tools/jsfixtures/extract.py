@@ -29,7 +29,7 @@ sys.path.insert(0, HERE)
 
 import jsmini  # noqa: E402
 from jsmini import JSError, JSThrow, undefined  # noqa: E402
-from automerge_classic_b200.columnar import encode_change, change_hash  # noqa: E402
+from automerge_classic_b200.columnar import encode_change, change_hash, decode_change, DecodeError  # noqa: E402
 from automerge_classic_b200.backend import Backend, RangeError as FacadeRangeError  # noqa: E402
 import oracle  # noqa: E402
 from oracle import OracleDoc, OracleError  # noqa: E402
@@ -158,6 +158,9 @@ def run_engine(step, fn):
         step['error'] = e.message
         raise JSError(e.kind, e.message)
     except FacadeRangeError as e:
+        step['error'] = str(e)
+        raise JSError('RangeError', str(e))
+    except ValueError as e:
         step['error'] = str(e)
         raise JSError('RangeError', str(e))
     except (TypeError, RuntimeError) as e:
@@ -377,17 +380,29 @@ def to_plain(v):
 
 # ---------------------------------------------------------------- assertions & misc host functions
 def js_encode_change(change):
-    return encode_change(to_plain(change))
+    try:
+        return encode_change(to_plain(change))
+    except ValueError as e:
+        raise JSError('RangeError', str(e))
 
 
 def js_hash(change):
     return change_hash(to_plain(change))
 
 
-def js_decode_change(buf):
-    d = oracle.decode_change(bytes(jsmini.unwrap(buf)))
-    return {'hash': d['hash'], 'actor': d['actor'], 'seq': d['seq'], 'startOp': d['startOp'], 'time': d['time'],
-            'message': d['message'], 'deps': d['deps']}
+def js_decode_change(buf, *_):
+    try:
+        return decode_change(bytes(jsmini.unwrap(buf)))
+    except DecodeError as e:
+        raise JSError('RangeError', str(e))
+
+
+class JSDate:
+    def __init__(self, ms=None):
+        self.ms = 1600000000000 if ms is None else int(jsmini.unwrap(ms))
+
+    def getTime(self):
+        return self.ms
 
 
 def record_assert(kind, actual, expected, ok):
@@ -600,7 +615,7 @@ def make_globals():
         'Number': {'MAX_SAFE_INTEGER': 2 ** 53 - 1, 'MIN_SAFE_INTEGER': -(2 ** 53 - 1)},
         'JSON': {'stringify': lambda v: json.dumps(to_json(v))},
         'checkColumns': check_columns, 'hash': js_hash,
-        'console': {'log': lambda *a: undefined},
+        'console': {'log': lambda *a: undefined}, 'Date': JSDate,
     }
     return g
 
