@@ -1,0 +1,202 @@
+// amgpu — B200-native bulk change-replay engine: common device/host plumbing.
+//
+// Every per-item kernel of the engine is a functor with `void operator()(size_t i) const`, launched
+// through foreach<F>() as a grid-stride CUDA kernel (k_foreach<F>; the functor name shows up in ncu).
+// Grids are sized in multiples of the SM count (148 on B200) times resident CTAs per SM.
+//
+// AMG_EMU: a *development and host-logic test aid only*. In this build container there is no GPU, so
+// the same functors can be compiled with g++ (-DAMG_EMU) and run as a serial loop to debug the
+// pipeline's logic before spending GPU time. The emulation library is built under tests/_emu/, is
+// only loaded by explicitly named "emu" tests, and is never built into or reachable from the
+// product library (libamgpu.so), which is always compiled by nvcc and fails loudly without a GPU.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifdef AMG_EMU
+#define HD inline
+#define DEV inline
+#else
+#include <cuda_runtime.h>
+#define HD __host__ __device__ __forceinline__
+#define DEV __device__ __forceinline__
+#endif
+
+namespace amg {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+enum ErrCode {
+  AMG_OK = 0, AMG_ERR_RANGE = 1, AMG_ERR_TYPE = 2, AMG_ERR_INTERNAL = 3, AMG_ERR_UNSUPPORTED = 4, AMG_ERR_CUDA = 5, AMG_ERR_FROZEN = 6
+};
+
+#ifndef AMG_EMU
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw amg::Error(amg::AMG_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); } while (0)
+#endif
+
+struct Ctx {
+#ifndef AMG_EMU
+  cudaStream_t stream = nullptr;
+#endif
+  int device = 0;
+  int numSMs = 148;
+  uint64_t launches = 0;   // kernels launched (gpu_launches in bench.py)
+};
+
+// ---------------------------------------------------------------- device buffers
+inline void* dev_alloc(size_t bytes) {
+#ifdef AMG_EMU
+  return malloc(bytes ? bytes : 1);
+#else
+  void* p = nullptr; CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1)); return p;
+#endif
+}
+inline void dev_free(void* p) {
+#ifdef AMG_EMU
+  free(p);
+#else
+  if (p) cudaFree(p);
+#endif
+}
+inline void dev_memset(Ctx& c, void* p, int v, size_t bytes) {
+  if (!bytes) return;
+#ifdef AMG_EMU
+  memset(p, v, bytes);
+#else
+  CUDA_CHECK(cudaMemsetAsync(p, v, bytes, c.stream));
+#endif
+}
+inline void h2d(Ctx& c, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+#ifdef AMG_EMU
+  memcpy(dst, src, bytes);
+#else
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream));
+#endif
+}
+inline void d2h(Ctx& c, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+#ifdef AMG_EMU
+  memcpy(dst, src, bytes);
+#else
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
+#endif
+}
+inline void d2d(Ctx& c, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+#ifdef AMG_EMU
+  memmove(dst, src, bytes);
+#else
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c.stream));
+#endif
+}
+inline void sync(Ctx& c) {
+#ifndef AMG_EMU
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+#endif
+}
+
+// Growable device array. Growth keeps the old contents (needed for persistent state).
+template <class T> struct DBuf {
+  T* p = nullptr; size_t cap = 0;
+  DBuf() {}
+  DBuf(const DBuf&) = delete; DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { dev_free(p); }
+  void ensure(Ctx& c, size_t n, size_t keep = 0) {
+    if (n <= cap) return;
+    size_t ncap = n + n / 4 + 64;
+    T* np_ = (T*)dev_alloc(ncap * sizeof(T));
+    if (keep) { d2d(c, np_, p, keep * sizeof(T)); sync(c); }
+    dev_free(p); p = np_; cap = ncap;
+  }
+  T* get() { return p; }
+};
+
+// Pinned host staging buffer
+template <class T> struct HBuf {
+  T* p = nullptr; size_t cap = 0;
+  HBuf() {}
+  HBuf(const HBuf&) = delete; HBuf& operator=(const HBuf&) = delete;
+  ~HBuf() { release(); }
+  void release() {
+#ifdef AMG_EMU
+    free(p);
+#else
+    if (p) cudaFreeHost(p);
+#endif
+    p = nullptr; cap = 0;
+  }
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    size_t ncap = n + n / 4 + 64; T* np_;
+#ifdef AMG_EMU
+    np_ = (T*)malloc(ncap * sizeof(T));
+#else
+    CUDA_CHECK(cudaMallocHost((void**)&np_, ncap * sizeof(T)));
+#endif
+    if (p && cap) memcpy(np_, p, cap * sizeof(T));
+    release(); p = np_; cap = ncap;
+  }
+};
+
+// ---------------------------------------------------------------- kernel launch
+#ifndef AMG_EMU
+template <class F> __global__ void __launch_bounds__(256) k_foreach(size_t n, F f) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) f(i);
+}
+#endif
+
+template <class F> inline void foreach(Ctx& c, size_t n, const F& f) {
+  if (n == 0) return;
+#ifdef AMG_EMU
+  for (size_t i = 0; i < n; i++) f(i);
+#else
+  const int block = 256;
+  size_t want = (n + block - 1) / block;
+  size_t maxGrid = (size_t)c.numSMs * 8;   // 8 resident CTAs of 256 threads per SM
+  int grid = (int)(want < maxGrid ? want : maxGrid);
+  k_foreach<F><<<grid, block, 0, c.stream>>>(n, f);
+  CUDA_CHECK(cudaGetLastError());
+#endif
+  c.launches++;
+}
+
+// ---------------------------------------------------------------- atomics (serial in EMU)
+#ifdef AMG_EMU
+template <class T> inline T atomic_add(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomic_min(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> inline T atomic_max(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T atomic_or(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> inline T atomic_cas(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
+#else
+DEV uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+DEV int atomic_add(int* p, int v) { return atomicAdd(p, v); }
+DEV unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+DEV uint32_t atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
+DEV unsigned long long atomic_min(unsigned long long* p, unsigned long long v) { return atomicMin(p, v); }
+DEV uint32_t atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
+DEV unsigned long long atomic_max(unsigned long long* p, unsigned long long v) { return atomicMax(p, v); }
+DEV uint32_t atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+DEV unsigned long long atomic_cas(unsigned long long* p, unsigned long long cmp, unsigned long long v) { return atomicCAS(p, cmp, v); }
+DEV uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
+#endif
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+typedef uint8_t u8;
+
+HD u64 mix64(u64 x) {   // splitmix64 finaliser: hash for open-addressing tables
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 27; x *= 0x94d049bb133111ebULL; x ^= x >> 31; return x;
+}
+HD int bits_for(u64 maxValue) { int b = 0; while (maxValue) { b++; maxValue >>= 1; } return b ? b : 1; }
+inline size_t pow2_at_least(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
+
+}  // namespace amg

@@ -1,0 +1,413 @@
+// amgpu — kernels #1: columnar change decode.
+//
+// Replaces (reference paths relative to /root/reference):
+//   backend/columnar.js:688-708  decodeContainerHeader (magic, SHA-256 over [type|len|body], checksum)   -> ShaKernel
+//   backend/columnar.js:635-652  decodeChangeHeader, :609-624 decodeColumnInfo, :741-765 decodeChangeColumns -> ParseKernel
+//   backend/encoding.js:341-488  LEB128 readers, :789-920 RLEDecoder, :1004-1051 DeltaDecoder,
+//   backend/encoding.js:1141-1207 BooleanDecoder, backend/new.js:570-610 readOperation               -> DecodeColumnKernel
+//   backend/new.js:678-724       readNextChangeOp (opId assignment, reference validation)             -> FinalizeOpsKernel
+//
+// Layout: all change bytes of a call sit back to back in one device arena (u8). ParseKernel writes a
+// ChangeMeta per change plus a column directory in structure-of-arrays form ([column][change]);
+// DecodeColumnKernel runs one thread per (column, change) — adjacent threads handle adjacent changes
+// of the same column, so directory reads and row writes are coalesced for the many-small-changes
+// regime, and large changes get 14-way column parallelism. Rows are raw u32 columns (SoA); the
+// finalize kernel packs them into 64-bit ids with document-global actor numbers.
+#pragma once
+#include "common.cuh"
+
+namespace amg {
+
+static const u32 NULL32 = 0xffffffffu;
+static const int NCOLS = 14;   // known change columns, in this order:
+enum ColIx { CX_OBJ_ACTOR = 0, CX_OBJ_CTR, CX_KEY_ACTOR, CX_KEY_CTR, CX_KEY_STR, CX_INSERT, CX_ACTION, CX_VAL_LEN, CX_VAL_RAW,
+             CX_CHLD_ACTOR, CX_CHLD_CTR, CX_PRED_NUM, CX_PRED_ACTOR, CX_PRED_CTR };
+HD int col_index_of(u32 columnId) {
+  switch (columnId) {
+    case 0x01: return CX_OBJ_ACTOR; case 0x02: return CX_OBJ_CTR; case 0x11: return CX_KEY_ACTOR; case 0x13: return CX_KEY_CTR;
+    case 0x15: return CX_KEY_STR; case 0x34: return CX_INSERT; case 0x42: return CX_ACTION; case 0x56: return CX_VAL_LEN;
+    case 0x57: return CX_VAL_RAW; case 0x61: return CX_CHLD_ACTOR; case 0x63: return CX_CHLD_CTR; case 0x70: return CX_PRED_NUM;
+    case 0x71: return CX_PRED_ACTOR; case 0x73: return CX_PRED_CTR; default: return -1;
+  }
+}
+
+// error codes raised by kernels (ordered by the reference's check order where it matters)
+enum KErr {
+  KE_NONE = 0, KE_MAGIC, KE_CHECKSUM, KE_TRAILING, KE_CHUNK_TYPE, KE_TRUNCATED, KE_NUM_RANGE, KE_COL_ORDER, KE_COL_DEFLATE,
+  KE_RLE_REP1, KE_RLE_SUCC_REP, KE_RLE_SUCC_LIT, KE_RLE_SUCC_NULL, KE_RLE_ZERO_NULL, KE_RLE_LIT_REP, KE_BOOL_ZERO,
+  KE_OBJ_MISMATCH, KE_KEY_MISMATCH, KE_ACTOR_INDEX, KE_TOO_LARGE, KE_UNKNOWN_ACTOR, KE_PRED_MISSING, KE_REF_ELEM, KE_DUP_OPID,
+  KE_UNSUPPORTED_OP, KE_LAMPORT, KE_HASH_COLLISION, KE_LIST_ELEM, KE_PRED_ORDER
+};
+// error word: (code << 32 | item index); the smallest item index wins so that the error reported is
+// the one the sequential reference would hit first within a phase.
+HD void raise(u64* errWord, u32 code, u64 item) {
+  u64 w = ((u64)(item & 0xffffffffu) << 8) | code;   // ordered by item, then code
+#ifdef AMG_EMU
+  if (*errWord == 0 || w < *errWord) *errWord = w;
+#else
+#ifdef __CUDA_ARCH__
+  unsigned long long old = *errWord;
+  while (old == 0 || w < old) { unsigned long long prev = atomicCAS(errWord, old, w); if (prev == old) break; old = prev; }
+#endif
+#endif
+}
+
+struct ChangeMeta {
+  u32 off, len;            // absolute arena offset / length of the (inflated) change
+  u32 depsOff, nDeps;      // first dependency hash (32 bytes each)
+  u32 actorOff, actorLen;  // author actor id bytes
+  u32 msgOff, msgLen;
+  u32 otherOff, nOther;    // other-actor table entries (len-prefixed), after the count
+  u32 extraOff, extraLen;  // trailing bytes
+  u32 nOps, nPreds;
+  u64 seq, startOp; long long time;
+};
+
+// ---------------------------------------------------------------- byte-level readers
+struct ByteReader {
+  const u8* base; u32 pos, end; u32 err;
+  HD ByteReader(const u8* b, u32 p, u32 e) : base(b), pos(p), end(e), err(0) {}
+  HD bool done() const { return pos >= end; }
+  // encoding.js:416-441 readUint64 + :389-395 53-bit range check
+  HD u64 uleb() {
+    u64 result = 0; int shift = 0;
+    while (pos < end) {
+      u8 b = base[pos];
+      if (shift == 63 && (b & 0xfe)) { err = KE_NUM_RANGE; return 0; }
+      result |= (u64)(b & 0x7f) << shift; shift += 7; pos++;
+      if (!(b & 0x80)) { if (result > ((1ULL << 53) - 1)) err = KE_NUM_RANGE; return result; }
+    }
+    err = KE_TRUNCATED; return 0;
+  }
+  // encoding.js:450-488 readInt64 + :402-408
+  HD long long sleb() {
+    u64 result = 0; int shift = 0;
+    while (pos < end) {
+      u8 b = base[pos];
+      if (shift == 63 && b != 0 && b != 0x7f) { err = KE_NUM_RANGE; return 0; }
+      result |= (u64)(b & 0x7f) << shift; shift += 7; pos++;
+      if (!(b & 0x80)) {
+        if ((b & 0x40) && shift < 64) result |= ~0ULL << shift;
+        long long v = (long long)result;
+        if (v < -((1LL << 53) - 1) || v > ((1LL << 53) - 1)) err = KE_NUM_RANGE;
+        return v;
+      }
+    }
+    err = KE_TRUNCATED; return 0;
+  }
+  HD void skip(u64 n) { if ((u64)pos + n > end) { err = KE_TRUNCATED; pos = end; } else pos += (u32)n; }
+};
+
+// RLE record walker (encoding.js:789-920) over numeric (uint / int) or utf8 columns. One value at a time.
+struct RleReader {
+  ByteReader r; int type;   // 0 uint, 1 int, 2 utf8
+  long long count; int state;   // 0 none, 1 repetition, 2 literal, 3 nulls
+  long long lastNum; u32 lastOff, lastLen; bool haveLast; bool lastNull;
+  HD RleReader(const u8* b, u32 p, u32 e, int t) : r(b, p, e), type(t), count(0), state(0), lastNum(0), lastOff(0), lastLen(0), haveLast(false), lastNull(false) {}
+  HD bool done() const { return count == 0 && r.done(); }
+  HD bool strEq(u32 offA, u32 lenA, u32 offB, u32 lenB) const {
+    if (lenA != lenB) return false;
+    for (u32 i = 0; i < lenA; i++) if (r.base[offA + i] != r.base[offB + i]) return false;
+    return true;
+  }
+  HD void readRaw(long long& num, u32& off, u32& len) {
+    if (type == 0) num = (long long)r.uleb();
+    else if (type == 1) num = r.sleb();
+    else { u64 l = r.uleb(); off = r.pos; len = (u32)l; r.skip(l); }
+  }
+  HD bool sameAsLast(long long num, u32 off, u32 len) const {
+    if (!haveLast || lastNull) return false;
+    return type == 2 ? strEq(off, len, lastOff, lastLen) : num == lastNum;
+  }
+  // returns false for null; value in num (numeric) or off/len (utf8)
+  HD bool next(long long& num, u32& off, u32& len) {
+    if (done()) return false;
+    if (count == 0) {   // readRecord
+      count = r.sleb();
+      if (r.err) return false;
+      if (count > 1) {
+        long long n = 0; u32 o = 0, l = 0; readRaw(n, o, l);
+        if ((state == 1 || state == 2) && sameAsLast(n, o, l)) r.err = KE_RLE_SUCC_REP;
+        state = 1; lastNum = n; lastOff = o; lastLen = l; haveLast = true; lastNull = false;
+      } else if (count == 1) { r.err = KE_RLE_REP1; return false; }
+      else if (count < 0) { count = -count; if (state == 2) r.err = KE_RLE_SUCC_LIT; state = 2; }
+      else {
+        if (state == 3) r.err = KE_RLE_SUCC_NULL;
+        count = (long long)r.uleb();
+        if (count == 0) { r.err = KE_RLE_ZERO_NULL; return false; }
+        state = 3; haveLast = true; lastNull = true;
+      }
+    }
+    count -= 1;
+    if (state == 2) {
+      long long n = 0; u32 o = 0, l = 0; readRaw(n, o, l);
+      if (sameAsLast(n, o, l)) r.err = KE_RLE_LIT_REP;
+      lastNum = n; lastOff = o; lastLen = l; haveLast = true; lastNull = false;
+      num = n; off = o; len = l; return true;
+    }
+    if (state == 3) return false;
+    num = lastNum; off = lastOff; len = lastLen; return true;
+  }
+};
+
+// ---------------------------------------------------------------- SHA-256 (FIPS 180-4), one thread per change
+struct ShaConsts { u32 k[64]; };
+#ifndef AMG_EMU
+__constant__ ShaConsts c_sha;
+#endif
+static const u32 SHA_K[64] = {
+  0x428a2f98,0x71374491,0xb5c0fbcf,0xe9b5dba5,0x3956c25b,0x59f111f1,0x923f82a4,0xab1c5ed5,0xd807aa98,0x12835b01,0x243185be,0x550c7dc3,
+  0x72be5d74,0x80deb1fe,0x9bdc06a7,0xc19bf174,0xe49b69c1,0xefbe4786,0x0fc19dc6,0x240ca1cc,0x2de92c6f,0x4a7484aa,0x5cb0a9dc,0x76f988da,
+  0x983e5152,0xa831c66d,0xb00327c8,0xbf597fc7,0xc6e00bf3,0xd5a79147,0x06ca6351,0x14292967,0x27b70a85,0x2e1b2138,0x4d2c6dfc,0x53380d13,
+  0x650a7354,0x766a0abb,0x81c2c92e,0x92722c85,0xa2bfe8a1,0xa81a664b,0xc24b8b70,0xc76c51a3,0xd192e819,0xd6990624,0xf40e3585,0x106aa070,
+  0x19a4c116,0x1e376c08,0x2748774c,0x34b0bcb5,0x391c0cb3,0x4ed8aa4a,0x5b9cca4f,0x682e6ff3,0x748f82ee,0x78a5636f,0x84c87814,0x8cc70208,
+  0x90befffa,0xa4506ceb,0xbef9a3f7,0xc67178f2};
+
+HD u32 rotr32(u32 x, int n) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(x, x, n);
+#else
+  return (x >> n) | (x << (32 - n));
+#endif
+}
+// big-endian 32-bit load at an arbitrary byte address (two aligned loads + funnel shift on device)
+HD u32 load_be32(const u8* p) {
+#if defined(__CUDA_ARCH__)
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const u32* w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+  const u32 sh = (u32)(a & 3) * 8;
+  const u32 lo = w[0], hi = sh ? w[1] : 0;
+  return __byte_perm(__funnelshift_r(lo, hi, sh), 0, 0x0123);
+#else
+  return (u32)p[0] << 24 | (u32)p[1] << 16 | (u32)p[2] << 8 | p[3];
+#endif
+}
+HD void sha256_compress(u32* h, u32* w, const u32* K) {
+  u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll 16
+  for (int i = 0; i < 64; i++) {
+    u32 wi;
+    if (i < 16) wi = w[i];
+    else {
+      const u32 w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+      const u32 s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3), s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+      wi = w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+    }
+    const u32 t1 = hh + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + wi;
+    const u32 t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+  }
+  h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+// hashes arena[off+8 .. off+len) of every change; writes 32-byte digests; checks magic + checksum
+struct ShaKernel {
+  const u8* arena; const u32* chOff; const u32* chLen; u8* hashOut /* [n][32] */; u64* errWord; const u32* Kdev;
+  HD void operator()(size_t c) const {
+    const u8* p = arena + chOff[c]; const u32 len = chLen[c];
+    if (len < 10 || p[0] != 0x85 || p[1] != 0x6f || p[2] != 0x4a || p[3] != 0x83) { raise(errWord, KE_MAGIC, c); return; }
+#if defined(__CUDA_ARCH__)
+    const u32* K = c_sha.k;
+#else
+    const u32* K = SHA_K;
+#endif
+    u32 h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    const u8* m = p + 8; const u32 mlen = len - 8;
+    u32 w[16]; u32 done = 0;
+    while (done + 64 <= mlen) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) w[i] = load_be32(m + done + 4 * i);
+      sha256_compress(h, w, K); done += 64;
+    }
+    // tail: remaining bytes + 0x80 + zero pad + 64-bit bit length
+    const u32 rem = mlen - done;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      u32 v = 0;
+      for (int b = 0; b < 4; b++) {
+        const u32 ix = 4 * i + b; u32 byte = 0;
+        if (ix < rem) byte = m[done + ix]; else if (ix == rem) byte = 0x80;
+        v = (v << 8) | byte;
+      }
+      w[i] = v;
+    }
+    if (rem >= 56) {
+      sha256_compress(h, w, K);
+#pragma unroll
+      for (int i = 0; i < 16; i++) w[i] = 0;
+    }
+    w[14] = (u32)(((u64)mlen * 8) >> 32); w[15] = (u32)((u64)mlen * 8);
+    sha256_compress(h, w, K);
+    u8* out = hashOut + c * 32;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }
+    if (out[0] != p[4] || out[1] != p[5] || out[2] != p[6] || out[3] != p[7]) raise(errWord, KE_CHECKSUM, c);
+  }
+};
+
+// ---------------------------------------------------------------- header / column directory parse, one thread per change
+struct ParseKernel {
+  const u8* arena; const u32* chOff; const u32* chLen; size_t numChanges;
+  ChangeMeta* meta; u32* colOff /* [NCOLS][numChanges] */; u32* colLen; u32* nOpsOut; u32* nPredsOut; u32* nDepsOut; u32* nActorsOut; u64* errWord;
+  HD void operator()(size_t c) const {
+    const u32 off = chOff[c], len = chLen[c];
+    ChangeMeta m; memset(&m, 0, sizeof(m)); m.off = off; m.len = len;
+    for (int k = 0; k < NCOLS; k++) { colOff[(size_t)k * numChanges + c] = 0; colLen[(size_t)k * numChanges + c] = 0; }
+    nOpsOut[c] = 0; nPredsOut[c] = 0; nDepsOut[c] = 0; nActorsOut[c] = 1;
+    ByteReader r(arena, off + 8, off + len);
+    const u32 chunkType = r.done() ? 0xff : arena[r.pos]; r.pos++;
+    const u64 chunkLen = r.uleb();
+    if (r.err) { raise(errWord, r.err, c); meta[c] = m; return; }
+    if ((u64)r.pos + chunkLen > (u64)off + len) { raise(errWord, KE_TRUNCATED, c); meta[c] = m; return; }
+    if ((u64)r.pos + chunkLen != (u64)off + len) { raise(errWord, KE_TRAILING, c); meta[c] = m; return; }
+    if (chunkType != 1) { raise(errWord, KE_CHUNK_TYPE, c); meta[c] = m; return; }
+    // decodeChangeHeader
+    const u64 nDeps = r.uleb(); m.depsOff = r.pos; m.nDeps = (u32)nDeps; r.skip(nDeps * 32);
+    const u64 actorLen = r.uleb(); m.actorOff = r.pos; m.actorLen = (u32)actorLen; r.skip(actorLen);
+    m.seq = r.uleb(); m.startOp = r.uleb(); m.time = r.sleb();
+    const u64 msgLen = r.uleb(); m.msgOff = r.pos; m.msgLen = (u32)msgLen; r.skip(msgLen);
+    const u64 nOther = r.uleb(); m.otherOff = r.pos; m.nOther = (u32)nOther;
+    for (u64 i = 0; i < nOther && !r.err; i++) { u64 l = r.uleb(); r.skip(l); }
+    // decodeColumnInfo
+    const u64 nCols = r.uleb();
+    if (r.err) { raise(errWord, r.err, c); meta[c] = m; return; }
+    const u32 dirPos = r.pos; long long lastId = -1; u64 total = 0;
+    for (u64 i = 0; i < nCols && !r.err; i++) {
+      const u64 id = r.uleb(), l = r.uleb();
+      if (lastId >= 0 && ((u32)id & ~8u) <= ((u32)lastId & ~8u)) { raise(errWord, KE_COL_ORDER, c); meta[c] = m; return; }
+      if (id & 8) { raise(errWord, KE_COL_DEFLATE, c); meta[c] = m; return; }
+      lastId = (long long)id; total += l;
+    }
+    if (r.err) { raise(errWord, r.err, c); meta[c] = m; return; }
+    u32 dataPos = r.pos;
+    if ((u64)dataPos + total > (u64)off + len) { raise(errWord, KE_TRUNCATED, c); meta[c] = m; return; }
+    ByteReader d(arena, dirPos, dataPos);
+    for (u64 i = 0; i < nCols; i++) {
+      const u64 id = d.uleb(), l = d.uleb();
+      const int ix = col_index_of((u32)id);
+      if (ix >= 0) { colOff[(size_t)ix * numChanges + c] = dataPos; colLen[(size_t)ix * numChanges + c] = (u32)l; }
+      dataPos += (u32)l;
+    }
+    m.extraOff = dataPos; m.extraLen = off + len - dataPos;
+    // count ops (values of the action column) and preds (sum of the predNum column)
+    u32 nOps = 0; u64 nPreds = 0; u32 kerr = 0;
+    {
+      RleReader a(arena, colOff[(size_t)CX_ACTION * numChanges + c], colOff[(size_t)CX_ACTION * numChanges + c] + colLen[(size_t)CX_ACTION * numChanges + c], 0);
+      // record-level count: no need to touch every value of a repetition / null run
+      while (!a.done() && !a.r.err) {
+        long long n; u32 o, l; a.next(n, o, l);
+        u64 adv = 1;
+        if (a.state != 2 && a.count > 0) { adv += (u64)a.count; a.count = 0; }
+        nOps += (u32)adv;
+      }
+      kerr = a.r.err;
+    }
+    if (!kerr) {
+      RleReader pn(arena, colOff[(size_t)CX_PRED_NUM * numChanges + c], colOff[(size_t)CX_PRED_NUM * numChanges + c] + colLen[(size_t)CX_PRED_NUM * numChanges + c], 0);
+      u32 seen = 0;
+      while (!pn.done() && !pn.r.err && seen < nOps) {
+        long long n = 0; u32 o, l; const bool nn = pn.next(n, o, l);
+        u64 adv = 1;
+        if (pn.state != 2 && pn.count > 0) { adv += (u64)pn.count; if (seen + adv > nOps) adv = nOps - seen; pn.count -= (long long)(adv - 1); }
+        if (nn) nPreds += (u64)n * adv;
+        seen += (u32)adv;
+      }
+      kerr = pn.r.err;
+    }
+    if (kerr) { raise(errWord, kerr, c); meta[c] = m; return; }
+    if (nPreds > 0x7fffffffULL) { raise(errWord, KE_TOO_LARGE, c); meta[c] = m; return; }
+    m.nOps = nOps; m.nPreds = (u32)nPreds;
+    meta[c] = m; nOpsOut[c] = nOps; nPredsOut[c] = (u32)nPreds; nDepsOut[c] = m.nDeps; nActorsOut[c] = 1 + m.nOther;
+  }
+};
+
+// ---------------------------------------------------------------- column expansion, one thread per (column, change)
+struct RawRows {   // SoA, one entry per op of the batch (raw change-local values; NULL32 = null)
+  u32 *objActor, *objCtr, *keyActor, *keyCtr, *keyStrOff, *keyStrLen, *insert, *action, *valLen, *valOff, *predNum, *predOff;
+  u32 *predActor, *predCtr;   // one entry per pred of the batch
+};
+
+struct DecodeColumnKernel {
+  const u8* arena; size_t numChanges; const ChangeMeta* meta; const u32* colOff; const u32* colLen;
+  const u32* opBase /* exclusive scan of nOps */; const u32* predBase; const u8* applied /* per change: decode only if 1 */;
+  RawRows rows; u64* errWord;
+  HD void operator()(size_t t) const {
+    const int col = (int)(t / numChanges); const size_t c = t % numChanges;
+    if (!applied[c]) return;
+    const u32 nOps = meta[c].nOps; if (nOps == 0) return;
+    const u32 base = opBase[c], cOff = colOff[(size_t)col * numChanges + c], cEnd = cOff + colLen[(size_t)col * numChanges + c];
+    u32 kerr = 0;
+    switch (col) {
+      case CX_OBJ_ACTOR: case CX_OBJ_CTR: case CX_KEY_ACTOR: case CX_ACTION: case CX_VAL_LEN: case CX_PRED_NUM: {
+        u32* out = col == CX_OBJ_ACTOR ? rows.objActor : col == CX_OBJ_CTR ? rows.objCtr : col == CX_KEY_ACTOR ? rows.keyActor
+                 : col == CX_ACTION ? rows.action : col == CX_VAL_LEN ? rows.valLen : rows.predNum;
+        RleReader r(arena, cOff, cEnd, 0);
+        u32 running = 0;   // VAL_LEN: byte offset into valRaw; PRED_NUM: pred offset
+        const u32 rawBase = col == CX_VAL_LEN ? colOff[(size_t)CX_VAL_RAW * numChanges + c] : (col == CX_PRED_NUM ? predBase[c] : 0);
+        for (u32 i = 0; i < nOps; i++) {
+          long long n = 0; u32 o, l; const bool nn = r.next(n, o, l);
+          if (nn && (u64)n > 0xfffffffeULL) kerr = KE_TOO_LARGE;
+          out[base + i] = nn ? (u32)n : NULL32;
+          if (col == CX_VAL_LEN) { rows.valOff[base + i] = rawBase + running; running += nn ? (u32)((u64)n >> 4) : 0; }
+          if (col == CX_PRED_NUM) { rows.predOff[base + i] = rawBase + running; running += nn ? (u32)n : 0; if (!nn) out[base + i] = 0; }
+        }
+        if (col == CX_VAL_LEN && running > colLen[(size_t)CX_VAL_RAW * numChanges + c]) kerr = KE_TRUNCATED;
+        if (!kerr) kerr = r.r.err;
+        break;
+      }
+      case CX_KEY_CTR: {
+        RleReader r(arena, cOff, cEnd, 1); long long acc = 0;
+        for (u32 i = 0; i < nOps; i++) {
+          long long n = 0; u32 o, l; const bool nn = r.next(n, o, l);
+          if (nn) { acc += n; if (acc < 0 || acc > 0xfffffffeLL) kerr = KE_TOO_LARGE; }
+          rows.keyCtr[base + i] = nn ? (u32)acc : NULL32;
+        }
+        if (!kerr) kerr = r.r.err;
+        break;
+      }
+      case CX_KEY_STR: {
+        RleReader r(arena, cOff, cEnd, 2);
+        for (u32 i = 0; i < nOps; i++) {
+          long long n; u32 o = 0, l = 0; const bool nn = r.next(n, o, l);
+          rows.keyStrOff[base + i] = nn ? o : 0; rows.keyStrLen[base + i] = nn ? l : NULL32;
+        }
+        kerr = r.r.err;
+        break;
+      }
+      case CX_INSERT: {   // BooleanDecoder encoding.js:1141-1207
+        ByteReader r(arena, cOff, cEnd); bool val = true, first = true; u64 count = 0;
+        for (u32 i = 0; i < nOps; i++) {
+          bool v = false;
+          if (!(count == 0 && r.done())) {
+            while (count == 0) {
+              count = r.uleb(); val = !val;
+              if (r.err) break;
+              if (count == 0 && !first) { kerr = KE_BOOL_ZERO; break; }
+              first = false;
+            }
+            if (r.err || kerr) break;
+            count--; v = val;
+          }
+          rows.insert[base + i] = v ? 1u : 0u;
+        }
+        if (!kerr) kerr = r.err;
+        break;
+      }
+      case CX_PRED_ACTOR: case CX_PRED_CTR: {
+        const u32 nPreds = meta[c].nPreds, pb = predBase[c];
+        RleReader r(arena, cOff, cEnd, col == CX_PRED_CTR ? 1 : 0); long long acc = 0;
+        for (u32 j = 0; j < nPreds; j++) {
+          long long n = 0; u32 o, l; const bool nn = r.next(n, o, l);
+          if (col == CX_PRED_CTR) { if (nn) { acc += n; if (acc < 0 || acc > 0xfffffffeLL) kerr = KE_TOO_LARGE; } rows.predCtr[pb + j] = nn ? (u32)acc : NULL32; }
+          else { if (nn && (u64)n > 0xfffffffeULL) kerr = KE_TOO_LARGE; rows.predActor[pb + j] = nn ? (u32)n : NULL32; }
+        }
+        if (!kerr) kerr = r.r.err;
+        break;
+      }
+      default: break;   // VAL_RAW is referenced in place; chld* columns are not needed by the op set
+    }
+    if (kerr) raise(errWord, kerr, c);
+  }
+};
+
+}  // namespace amg

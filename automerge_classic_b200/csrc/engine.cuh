@@ -1,0 +1,197 @@
+// amgpu — host orchestration of the change-replay pipeline (one Engine = one backend document).
+//
+// Mirrors class BackendDoc (reference backend/new.js:1694-2069): applyChanges (:1797-1879) and
+// getPatch (:2060-2068) run as sequences of CUDA kernels over device-resident state:
+//   arena   : every applied / queued change's bytes back to back (values and keys are referenced in place)
+//   hashes  : SHA-256 of every applied change                      (gate)
+//   doc     : document rows in document order, SoA, + succ CSR      (op set)
+//   actors  : byte-string table of actor ids -> document actor index
+// An applyChanges call is atomic (reference :1793-1795): all kernels write into scratch buffers; the
+// persistent state is swapped in only after the last error check passed.
+#pragma once
+#include <algorithm>
+#include <array>
+#include <map>
+#include <thread>
+#include <zlib.h>
+#include "patch.cuh"
+#include "prims.cuh"
+
+namespace amg {
+
+struct DocBufs {
+  DBuf<u64> id, obj, key; DBuf<u32> keyStrOff, keyStrLen, flags, valLen, valOff, time;
+  void ensure(Ctx& c, size_t n, size_t keep = 0) {
+    id.ensure(c, n, keep); obj.ensure(c, n, keep); key.ensure(c, n, keep); keyStrOff.ensure(c, n, keep); keyStrLen.ensure(c, n, keep);
+    flags.ensure(c, n, keep); valLen.ensure(c, n, keep); valOff.ensure(c, n, keep); time.ensure(c, n, keep);
+  }
+  DocRows view() { return DocRows{id.p, obj.p, key.p, keyStrOff.p, keyStrLen.p, flags.p, valLen.p, valOff.p, time.p}; }
+  void swap(DocBufs& o) {
+    std::swap(id.p, o.id.p); std::swap(id.cap, o.id.cap); std::swap(obj.p, o.obj.p); std::swap(obj.cap, o.obj.cap); std::swap(key.p, o.key.p); std::swap(key.cap, o.key.cap);
+    std::swap(keyStrOff.p, o.keyStrOff.p); std::swap(keyStrOff.cap, o.keyStrOff.cap); std::swap(keyStrLen.p, o.keyStrLen.p); std::swap(keyStrLen.cap, o.keyStrLen.cap);
+    std::swap(flags.p, o.flags.p); std::swap(flags.cap, o.flags.cap); std::swap(valLen.p, o.valLen.p); std::swap(valLen.cap, o.valLen.cap);
+    std::swap(valOff.p, o.valOff.p); std::swap(valOff.cap, o.valOff.cap); std::swap(time.p, o.time.p); std::swap(time.cap, o.time.cap);
+  }
+};
+
+struct PatchOut {   // flat patch (see include/amgpu.h for the byte layout produced by serialize())
+  u64 maxOp = 0, pendingChanges = 0; bool hasActorSeq = false; std::string actor; u64 seq = 0;
+  std::vector<std::pair<u32, u64>> clock; std::vector<std::array<u8, 32>> deps;
+  std::vector<PropRec> props; std::vector<EditRec> edits; std::vector<u64> editElem;
+  std::vector<std::string> actors;
+  std::vector<u8> bytes;
+};
+
+struct HostChange { u32 off, len; bool deflated; };
+
+inline std::string hex_of(const u8* p, size_t n) { static const char* d = "0123456789abcdef"; std::string s; for (size_t i = 0; i < n; i++) { s.push_back(d[p[i] >> 4]); s.push_back(d[p[i] & 15]); } return s; }
+
+class Engine {
+ public:
+  Ctx ctx;
+  // ---- persistent device state
+  DBuf<u8> arena; size_t arenaLen = 0; std::vector<u8> hostArena;   // host mirror (values / keys / changes are read from it)
+  DBuf<u8> hashes; size_t numApplied = 0;
+  DocBufs doc; size_t numRows = 0; DBuf<u32> succOff; DBuf<u64> succ; size_t numSucc = 0;
+  DBuf<ActorSlot> actorSlots; size_t actorCap = 0;
+  DBuf<u32> actorRank;
+  // ---- persistent host state
+  std::vector<std::string> actorIds;   // raw bytes, index = document actor number
+  std::vector<u64> clock;              // per actor number
+  std::vector<std::array<u8, 32>> heads; std::vector<u32> headIdx;   // heads (sorted by hash) and their application indices
+  std::vector<std::pair<u32, u32>> actorRep;   // arena (offset, length) of each actor's id bytes
+  std::vector<HostChange> changes;     // applied, in application order
+  std::vector<std::array<u8, 32>> changeHashes;   // host copy of applied hashes (filled lazily)
+  std::map<u32, std::string> deflatedOriginal;    // applied change index -> original compressed bytes
+  std::vector<HostChange> queue; std::vector<std::string> queueOriginal;   // not yet causally ready
+  u64 maxOp = 0;
+  float lastPhaseMs[8] = {0};
+  // ---- scratch (grow-only)
+  DBuf<u32> chOff, chLen, nOps, nPreds, nDeps, nActors, colOff, colLen, depBase, depIdx, primary, pass, flagWord, appRank, opBase, predBase, timeBase, amapBase, amap, authorSlot, newSlots;
+  DBuf<u8> applied; DBuf<ChangeMeta> meta; DBuf<u64> errWord; DBuf<u32> hashTable;
+  DBuf<u32> r_objActor, r_objCtr, r_keyActor, r_keyCtr, r_keyStrOff, r_keyStrLen, r_insert, r_action, r_valLen, r_valOff, r_predNum, r_predOff, r_predActor, r_predCtr;
+  DBuf<u64> o_id, o_obj, o_key, o_predId; DBuf<u32> o_keyStrOff, o_keyStrLen, o_flags, o_valLen, o_valOff, o_predOff, o_predNum, o_change, o_time;
+  DBuf<u32> isRow, rowSlot, rowOfOp; DocBufs work, sorted;
+  DBuf<u64> idKeys; DBuf<u32> idVals; DBuf<u32> objRow, elemRow, parentRow, keySlot, repList, repCount, listPos, perm, pos;
+  DBuf<KeySlot> keySlots; DBuf<u64> sortKeys; DBuf<u32> sortVals; SortTemp sortTmp; ScanTemp scanTmp;
+  DBuf<u32> eNext, eNext2, eRank, eRank2, insItems;
+  DBuf<u64> pairKey, pairSucc, newSucc; DBuf<u32> pairIdx, pairPos, pairTime, succCnt, newSuccCnt, newSuccOff, firstNewSucc;
+  DBuf<u32> elemPos, keyRankAt, objPos, head, headScan, groupOf, groupRows, groupVisible, groupFirst, groupTouched, groupLinked, objTouchedAt, linkDone, emit, marker, slot;
+  DBuf<u32> isObjHead, objIdx, objStart, elemVis, elemVisScan, rowEmit, firstVis, state, nItems, itemBase, qIndex, zero, wzero, zscan, wscan, editObjKey;
+  DBuf<DomItem> items, items2; DBuf<PropRec> propOut; DBuf<EditRec> editOut, editOut2; DBuf<u64> editElem, editElem2;
+  DBuf<u32> seqSlot, actorCnt, actorBaseD, clockD, changeActor; DBuf<u8> hashTmp;
+
+  explicit Engine(int device) {
+    ctx.device = device;
+#ifndef AMG_EMU
+    int count = 0; cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) throw Error(AMG_ERR_CUDA, "amgpu: no CUDA device available (this library has no CPU fallback)");
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device)); ctx.numSMs = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+    ShaConsts k; memcpy(k.k, SHA_K, sizeof(SHA_K)); CUDA_CHECK(cudaMemcpyToSymbol(c_sha, &k, sizeof(k)));
+#endif
+    errWord.ensure(ctx, 4); flagWord.ensure(ctx, 16);
+    actorCap = 64; actorSlots.ensure(ctx, actorCap); resetActorSlots(0, actorCap);
+    succOff.ensure(ctx, 1); dev_memset(ctx, succOff.p, 0, 4);
+  }
+  ~Engine() {
+#ifndef AMG_EMU
+    if (ctx.stream) cudaStreamDestroy(ctx.stream);
+#endif
+  }
+
+  // (re)builds the device actor table from the host's actor list (after growth, rollback or commit)
+  void rebuildActorTable() {
+    std::vector<ActorSlot> t(actorCap); for (auto& s : t) { s.hash = 0; s.first = ~0ULL; s.actorNum = EMPTY32; s.repOff = 0; s.repLen = 0; s.pad = 0; }
+    for (size_t a = 0; a < actorIds.size(); a++) {
+      const u64 h = fnv1a64((const u8*)actorIds[a].data(), (u32)actorIds[a].size()); u64 s = mix64(h) & (actorCap - 1);
+      while (t[s].hash != 0) s = (s + 1) & (actorCap - 1);
+      t[s].hash = h; t[s].first = 0; t[s].actorNum = (u32)a; t[s].repOff = actorRep[a].first; t[s].repLen = actorRep[a].second;
+    }
+    h2d(ctx, actorSlots.p, t.data(), actorCap * sizeof(ActorSlot)); sync(ctx);
+  }
+  void resetActorSlots(size_t from, size_t to) {
+    std::vector<ActorSlot> init(to - from); for (auto& s : init) { s.hash = 0; s.first = ~0ULL; s.actorNum = EMPTY32; s.repOff = 0; s.repLen = 0; s.pad = 0; }
+    h2d(ctx, actorSlots.p + from, init.data(), init.size() * sizeof(ActorSlot)); sync(ctx);
+  }
+
+  // ---------------------------------------------------------------- error plumbing
+  u64 fetchErr() { u64 w = 0; d2h(ctx, &w, errWord.p, 8); sync(ctx); return w; }
+  std::string opIdText(u64 id) const {
+    const u32 a = id_actor(id);
+    return std::to_string(id_ctr(id)) + "@" + (a < actorIds.size() ? hex_of((const u8*)actorIds[a].data(), actorIds[a].size()) : std::string("?"));
+  }
+  [[noreturn]] void throwKernelError(u64 w, const std::vector<std::string>& actorsNow, const u64* predIdHost = nullptr) {
+    const u32 code = (u32)(w & 0xff); const u64 item = w >> 8; (void)item; (void)actorsNow; (void)predIdHost;
+    switch (code) {
+      case KE_MAGIC: throw Error(AMG_ERR_RANGE, "Data does not begin with magic bytes 85 6f 4a 83");
+      case KE_CHECKSUM: throw Error(AMG_ERR_RANGE, "checksum does not match data");
+      case KE_TRAILING: throw Error(AMG_ERR_RANGE, "Encoded change has trailing data");
+      case KE_CHUNK_TYPE: throw Error(AMG_ERR_RANGE, "Unexpected chunk type");
+      case KE_TRUNCATED: throw Error(AMG_ERR_RANGE, "buffer ended with incomplete number");
+      case KE_NUM_RANGE: throw Error(AMG_ERR_RANGE, "number out of range");
+      case KE_COL_ORDER: throw Error(AMG_ERR_RANGE, "Columns must be in ascending order");
+      case KE_COL_DEFLATE: throw Error(AMG_ERR_RANGE, "change must not contain deflated columns");
+      case KE_RLE_REP1: throw Error(AMG_ERR_RANGE, "Repetition count of 1 is not allowed, use a literal instead");
+      case KE_RLE_SUCC_REP: throw Error(AMG_ERR_RANGE, "Successive repetitions with the same value are not allowed");
+      case KE_RLE_SUCC_LIT: throw Error(AMG_ERR_RANGE, "Successive literals are not allowed");
+      case KE_RLE_SUCC_NULL: throw Error(AMG_ERR_RANGE, "Successive null runs are not allowed");
+      case KE_RLE_ZERO_NULL: throw Error(AMG_ERR_RANGE, "Zero-length null runs are not allowed");
+      case KE_RLE_LIT_REP: throw Error(AMG_ERR_RANGE, "Repetition of values is not allowed in literal");
+      case KE_BOOL_ZERO: throw Error(AMG_ERR_RANGE, "Zero-length runs are not allowed");
+      case KE_OBJ_MISMATCH: throw Error(AMG_ERR_RANGE, "Mismatched object reference");
+      case KE_KEY_MISMATCH: throw Error(AMG_ERR_RANGE, "Mismatched operation key");
+      case KE_ACTOR_INDEX: throw Error(AMG_ERR_RANGE, "actor index out of range");
+      case KE_TOO_LARGE: throw Error(AMG_ERR_UNSUPPORTED, "amgpu: value exceeds the engine's 32-bit counter / 4 GiB arena limits");
+      case KE_UNKNOWN_ACTOR: throw Error(AMG_ERR_RANGE, "actorId is not known to document");
+      case KE_PRED_MISSING: throw Error(AMG_ERR_RANGE, "no matching operation for pred");
+      case KE_REF_ELEM: throw Error(AMG_ERR_RANGE, "Reference element not found");
+      case KE_LIST_ELEM: throw Error(AMG_ERR_RANGE, "could not find list element with ID");
+      case KE_DUP_OPID: throw Error(AMG_ERR_RANGE, "duplicate operation ID");
+      case KE_LAMPORT: throw Error(AMG_ERR_UNSUPPORTED, "amgpu: insert with an opId not greater than its reference element (Lamport order violated)");
+      case KE_HASH_COLLISION: throw Error(AMG_ERR_UNSUPPORTED, "amgpu: 64-bit string hash collision");
+      case KE_UNSUPPORTED_OP: throw Error(AMG_ERR_UNSUPPORTED, "amgpu: operation pattern outside the incremental-patch subset (see DESIGN.md)");
+      default: throw Error(AMG_ERR_INTERNAL, "amgpu: kernel error " + std::to_string(code));
+    }
+  }
+  void checkErr(const std::vector<std::string>& actorsNow) { u64 w = fetchErr(); if (w) throwKernelError(w, actorsNow); }
+
+  // ---------------------------------------------------------------- helpers
+  u32 readU32(const u32* dptr) { u32 v; d2h(ctx, &v, dptr, 4); sync(ctx); return v; }
+  void fill32(u32* p, u32 v, size_t n) { foreach(ctx, n, FillU32Kernel{p, v}); }
+  // sort `perm` (row ids) by successive 64-bit fields produced by keyFn(field) ; stable LSD over fields
+  void sortPairs(DBuf<u64>& keys, DBuf<u32>& vals, size_t n, int bits) { radix_sort_pairs(ctx, sortTmp, keys, vals, n, 0, bits); }
+
+  static std::string inflateChange(const u8* buf, size_t len) {
+    // reference columnar.js:813-823 (pako.inflateRaw -> zlib raw inflate); magic + checksum are kept
+    ByteReader r(buf, 9, (u32)len); const u64 clen = r.uleb();
+    if (r.err || r.pos + clen > len) throw Error(AMG_ERR_RANGE, "buffer ended with incomplete number");
+    z_stream zs; memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) throw Error(AMG_ERR_INTERNAL, "inflateInit failed");
+    std::string out; out.resize(std::max<size_t>(clen * 6, 1024));
+    zs.next_in = (Bytef*)(buf + r.pos); zs.avail_in = (uInt)clen; size_t produced = 0;
+    while (true) {
+      zs.next_out = (Bytef*)out.data() + produced; zs.avail_out = (uInt)(out.size() - produced);
+      int rc = inflate(&zs, Z_NO_FLUSH); produced = out.size() - zs.avail_out;
+      if (rc == Z_STREAM_END) break;
+      if (rc != Z_OK && rc != Z_BUF_ERROR) { inflateEnd(&zs); throw Error(AMG_ERR_RANGE, "invalid deflate data"); }
+      if (zs.avail_out == 0) out.resize(out.size() * 2); else if (zs.avail_in == 0) { inflateEnd(&zs); throw Error(AMG_ERR_RANGE, "unexpected end of deflate data"); }
+    }
+    inflateEnd(&zs); out.resize(produced);
+    std::string res((const char*)buf, 8); res.push_back(1);
+    u64 v = out.size(); do { u8 b = v & 0x7f; v >>= 7; if (v) b |= 0x80; res.push_back((char)b); } while (v);
+    res += out; return res;
+  }
+
+  // ---------------------------------------------------------------- applyChanges
+  struct ApplyResult { PatchOut patch; };
+
+  void applyChanges(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out);
+  void getPatch(PatchOut& out);
+  void buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows* ops, size_t numOps, const IdTable* idt, const u32* rowOfOpD, const u32* posD,
+                  const std::vector<std::string>& actorsNow, PatchOut& out);
+  void fillPatchHeader(PatchOut& out);
+};
+
+}  // namespace amg

@@ -1,0 +1,503 @@
+// amgpu — Engine::applyChanges / getPatch pipeline (see engine.cuh for the state layout).
+#pragma once
+#include "engine.cuh"
+#include "misc.cuh"
+
+namespace amg {
+
+struct PhaseTimer {
+#ifndef AMG_EMU
+  cudaEvent_t ev[10]; int n = 0; Ctx* c;
+  explicit PhaseTimer(Ctx& ctx) : c(&ctx) { for (auto& e : ev) cudaEventCreate(&e); mark(); }
+  ~PhaseTimer() { for (auto& e : ev) cudaEventDestroy(e); }
+  void mark() { if (n < 10) cudaEventRecord(ev[n++], c->stream); }
+  void collect(float* out, int maxN) { cudaEventSynchronize(ev[n - 1]); for (int i = 0; i + 1 < n && i < maxN; i++) cudaEventElapsedTime(&out[i], ev[i], ev[i + 1]); }
+#else
+  explicit PhaseTimer(Ctx&) {}
+  void mark() {}
+  void collect(float*, int) {}
+#endif
+};
+
+inline void parallel_copy(u8* dst, const u8* src, size_t n) {
+  const size_t kChunk = 8u << 20;
+  if (n < 2 * kChunk) { memcpy(dst, src, n); return; }
+  unsigned nt = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+  std::vector<std::thread> ts; size_t per = (n + nt - 1) / nt;
+  for (unsigned t = 0; t < nt; t++) { size_t a = t * per, b = std::min(n, a + per); if (a < b) ts.emplace_back([=] { memcpy(dst + a, src + a, b - a); }); }
+  for (auto& t : ts) t.join();
+}
+
+inline void Engine::fillPatchHeader(PatchOut& out) {
+  out.maxOp = maxOp; out.pendingChanges = queue.size();
+  out.clock.clear(); for (size_t a = 0; a < clock.size(); a++) if (clock[a] > 0) out.clock.emplace_back((u32)a, clock[a]);
+  out.deps = heads; out.actors = actorIds;
+}
+
+inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out) {
+  PhaseTimer timer(ctx);
+  // ------------------------------------------------------------ 0. stage the batch in the arena (host mirror + device)
+  const size_t arenaLen0 = arenaLen; const size_t hostLen0 = hostArena.size();
+  std::vector<HostChange> batch; std::vector<std::string> batchOriginal;   // original bytes only for deflated changes
+  batch.reserve(n + queue.size());
+  struct Rollback { Engine* e; size_t len; bool armed = true; ~Rollback() { if (armed) { e->hostArena.resize(len); e->rebuildActorTable(); } } };
+  bool anyDeflated = false; size_t total = 0;
+  for (size_t i = 0; i < n; i++) {
+    const u8* p = blob ? blob + offsets[i] : bufs[i]; const size_t l = blob ? (size_t)(offsets[i + 1] - offsets[i]) : lens[i];
+    if (l > 8 && p[8] == 2) anyDeflated = true;
+    total += l;
+  }
+  if ((u64)arenaLen0 + total + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
+  Rollback rb{this, hostLen0};
+  size_t cur = arenaLen0;
+  if (!anyDeflated && blob && n > 0) {
+    const size_t base = offsets[0]; const size_t tot = offsets[n] - base;
+    hostArena.resize(cur + tot); parallel_copy(hostArena.data() + cur, blob + base, tot);
+    for (size_t i = 0; i < n; i++) batch.push_back(HostChange{(u32)(cur + offsets[i] - base), (u32)(offsets[i + 1] - offsets[i]), false});
+    batchOriginal.resize(n); cur += tot;
+  } else {
+    for (size_t i = 0; i < n; i++) {
+      const u8* p = blob ? blob + offsets[i] : bufs[i]; const size_t l = blob ? (size_t)(offsets[i + 1] - offsets[i]) : lens[i];
+      if (l > 8 && p[8] == 2) {
+        std::string inflated = inflateChange(p, l);
+        if ((u64)cur + inflated.size() + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
+        hostArena.insert(hostArena.end(), inflated.begin(), inflated.end());
+        batch.push_back(HostChange{(u32)cur, (u32)inflated.size(), true}); batchOriginal.emplace_back((const char*)p, l); cur += inflated.size();
+      } else {
+        hostArena.insert(hostArena.end(), p, p + l);
+        batch.push_back(HostChange{(u32)cur, (u32)l, false}); batchOriginal.emplace_back(); cur += l;
+      }
+    }
+  }
+  const size_t numFresh = batch.size();
+  for (size_t i = 0; i < queue.size(); i++) { batch.push_back(queue[i]); batchOriginal.push_back(queueOriginal[i]); }
+  const size_t B = batch.size();
+  if (B == 0) { rb.armed = false; fillPatchHeader(out); return; }
+  arena.ensure(ctx, cur + 64, arenaLen0);
+  h2d(ctx, arena.p + arenaLen0, hostArena.data() + arenaLen0, cur - arenaLen0);
+  dev_memset(ctx, arena.p + cur, 0, 64);
+  {
+    std::vector<u32> off(B), len(B); for (size_t b = 0; b < B; b++) { off[b] = batch[b].off; len[b] = batch[b].len; }
+    chOff.ensure(ctx, B); chLen.ensure(ctx, B); h2d(ctx, chOff.p, off.data(), B * 4); h2d(ctx, chLen.p, len.data(), B * 4); sync(ctx);
+  }
+  timer.mark();
+  // ------------------------------------------------------------ 1. hash + header parse
+  dev_memset(ctx, errWord.p, 0, 8);
+  hashes.ensure(ctx, (numApplied + B) * 32 + 64, numApplied * 32);
+  foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr});
+  timer.mark();
+  meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
+  nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
+  foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
+  checkErr(actorIds);
+  // ------------------------------------------------------------ 2. causal gate
+  depBase.ensure(ctx, B + 1); scan_exclusive(ctx, scanTmp, nDeps.p, depBase.p, B);
+  const u32 totalDeps = readU32(depBase.p + B);
+  depIdx.ensure(ctx, totalDeps + 1); primary.ensure(ctx, B); pass.ensure(ctx, B);
+  const size_t G = numApplied + B; const size_t tcap = pow2_at_least(2 * G + 2);
+  hashTable.ensure(ctx, tcap); dev_memset(ctx, hashTable.p, 0xff, tcap * 4);
+  foreach(ctx, G, HashInsertKernel{hashes.p, hashTable.p, (u64)tcap - 1});
+  foreach(ctx, B, ResolveDepsKernel{arena.p, hashes.p, hashTable.p, (u64)tcap - 1, meta.p, numApplied, depBase.p, depIdx.p, primary.p});
+  fill32(pass.p, 1, B);
+  for (size_t iter = 0; iter <= B + 1; iter++) {
+    dev_memset(ctx, flagWord.p, 0, 4);
+    foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, meta.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
+    if (!readU32(flagWord.p)) break;
+  }
+  applied.ensure(ctx, B); appRank.ensure(ctx, B + 1); isRow.ensure(ctx, B + 1);
+  dev_memset(ctx, flagWord.p, 0, 8);
+  foreach(ctx, B, AppliedFlagKernel{primary.p, pass.p, numApplied, applied.p, isRow.p, flagWord.p});
+  u32 stats[2]; d2h(ctx, stats, flagWord.p, 8); sync(ctx);
+  const size_t numNew = stats[0]; const bool inOrder = stats[1] <= 1;
+  std::vector<u8> appliedH; std::vector<u32> primaryH, appRankH;
+  if (inOrder) scan_exclusive(ctx, scanTmp, isRow.p, appRank.p, B);
+  else {
+    sortKeys.ensure(ctx, B); sortVals.ensure(ctx, B);
+    foreach(ctx, B, PassKeyKernel{pass.p, applied.p, sortKeys.p, sortVals.p});
+    sortPairs(sortKeys, sortVals, B, 32);
+    foreach(ctx, B, RankFromOrderKernel{sortVals.p, appRank.p, numNew});
+  }
+  if (numNew < B || !inOrder) {
+    appliedH.resize(B); primaryH.resize(B); appRankH.resize(B);
+    d2h(ctx, appliedH.data(), applied.p, B); d2h(ctx, primaryH.data(), primary.p, B * 4); d2h(ctx, appRankH.data(), appRank.p, B * 4); sync(ctx);
+  }
+  auto isApplied = [&](size_t b) { return appliedH.empty() ? true : appliedH[b] != 0; };
+  // the queue after this call: every batch entry whose hash is still not applied (new.js:1569-1570, 1832)
+  std::vector<HostChange> newQueue; std::vector<std::string> newQueueOriginal;
+  if (numNew < B) for (size_t b = 0; b < B; b++) {
+    const u32 pr = primaryH[b];
+    const bool hashApplied = pr < numApplied || appliedH[pr - numApplied];
+    if (!hashApplied) { newQueue.push_back(batch[b]); newQueueOriginal.push_back(batchOriginal[b]); }
+  }
+  timer.mark();
+  std::vector<std::string> actorsNow = actorIds; std::vector<u64> clockNow = clock; std::vector<u32> actorCntH; std::vector<std::pair<u32, u32>> actorRepNow = actorRep;
+  size_t M = 0, P = 0, N = numRows, numPairs = numSucc; u64 maxOpNow = maxOp;
+  IdTable idt{nullptr, nullptr, 0};
+  std::vector<std::array<u8, 32>> headsNow = heads; std::vector<u32> headIdxNow;
+  if (numNew > 0) {
+    // ---------------------------------------------------------- 3. actors
+    authorSlot.ensure(ctx, B); newSlots.ensure(ctx, B + 1);
+    while (true) {   // grow the table until the distinct authors fit at load factor <= 1/2
+      dev_memset(ctx, flagWord.p, 0, 8);
+      foreach(ctx, B, ActorInternKernel{arena.p, meta.p, applied.p, appRank.p, actorSlots.p, (u64)actorCap - 1, authorSlot.p});
+      foreach(ctx, B, NewActorKernel{meta.p, applied.p, authorSlot.p, actorSlots.p, newSlots.p, flagWord.p});
+      const u32 fresh = readU32(flagWord.p);
+      if ((actorIds.size() + fresh) * 2 <= actorCap) break;
+      actorCap *= 4; actorSlots.ensure(ctx, actorCap); rebuildActorTable();
+    }
+    const u32 fresh = readU32(flagWord.p);
+    if (fresh > 0) {
+      std::vector<u32> slotsH(fresh); d2h(ctx, slotsH.data(), newSlots.p, fresh * 4); sync(ctx);
+      std::vector<ActorSlot> recs(fresh); for (u32 i = 0; i < fresh; i++) d2h(ctx, &recs[i], actorSlots.p + slotsH[i], sizeof(ActorSlot));
+      sync(ctx);
+      std::vector<u32> order(fresh); for (u32 i = 0; i < fresh; i++) order[i] = i;
+      std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return recs[a].first < recs[b].first; });
+      std::vector<u32> ids(fresh), nums(fresh);
+      for (u32 k = 0; k < fresh; k++) {
+        const ActorSlot& r = recs[order[k]]; ids[k] = slotsH[order[k]]; nums[k] = (u32)actorsNow.size();
+        actorsNow.emplace_back((const char*)hostArena.data() + r.repOff, r.repLen); actorRepNow.emplace_back(r.repOff, r.repLen);
+      }
+      if (actorsNow.size() > 65535) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 65535 actors in one document");
+      sortVals.ensure(ctx, 2 * fresh); h2d(ctx, sortVals.p, ids.data(), fresh * 4); h2d(ctx, sortVals.p + fresh, nums.data(), fresh * 4);
+      foreach(ctx, fresh, SetActorNumKernel{actorSlots.p, sortVals.p, sortVals.p + fresh});
+    }
+    const size_t A = actorsNow.size(); clockNow.resize(A, 0);
+    {   // rank of every actor in hex-string order (== byte order of the raw ids; new.js:64-65, 1180, 1198)
+      std::vector<u32> order(A), rank(A); for (size_t i = 0; i < A; i++) order[i] = (u32)i;
+      std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return actorsNow[a] < actorsNow[b]; });
+      for (size_t i = 0; i < A; i++) rank[order[i]] = (u32)i;
+      actorRank.ensure(ctx, A + 1); h2d(ctx, actorRank.p, rank.data(), A * 4);
+    }
+    const int rb = bits_for(A > 1 ? A - 1 : 1);
+    Ord ord{actorRank.p, rb};
+    amapBase.ensure(ctx, B + 1); rowSlot.ensure(ctx, B + 1);
+    foreach(ctx, B, MaskedCountKernel{nActors.p, applied.p, rowSlot.p});
+    scan_exclusive(ctx, scanTmp, rowSlot.p, amapBase.p, B);
+    const u32 totalAmap = readU32(amapBase.p + B);
+    amap.ensure(ctx, totalAmap + 1);
+    foreach(ctx, B, ActorMapKernel{arena.p, meta.p, applied.p, appRank.p, actorSlots.p, (u64)actorCap - 1, amapBase.p, amap.p, errWord.p});
+    // ---------------------------------------------------------- 4. sequence numbers
+    changeActor.ensure(ctx, B); actorCnt.ensure(ctx, A + 1); actorBaseD.ensure(ctx, A + 1); seqSlot.ensure(ctx, numNew + 1);
+    dev_memset(ctx, actorCnt.p, 0, (A + 1) * 4);
+    foreach(ctx, B, ChangeActorKernel{amapBase.p, amap.p, applied.p, changeActor.p, actorCnt.p});
+    checkErr(actorsNow);
+    scan_exclusive(ctx, scanTmp, actorCnt.p, actorBaseD.p, A);
+    DBuf<u64>& clockDev = pairKey;   // scratch reuse before the succ phase
+    clockDev.ensure(ctx, A + 1); h2d(ctx, clockDev.p, clockNow.data(), A * 8);
+    dev_memset(ctx, seqSlot.p, 0xff, (numNew + 1) * 4); dev_memset(ctx, flagWord.p, 0, 4);
+    foreach(ctx, B, SeqScatterKernel{meta.p, applied.p, changeActor.p, appRank.p, actorBaseD.p, actorCnt.p, clockDev.p, seqSlot.p, flagWord.p});
+    foreach(ctx, B, SeqMonoKernel{meta.p, applied.p, changeActor.p, actorBaseD.p, clockDev.p, seqSlot.p, flagWord.p});
+    actorCntH.resize(A); d2h(ctx, actorCntH.data(), actorCnt.p, A * 4);
+    if (readU32(flagWord.p)) {
+      // error path: replay the sequence check in application order on the host to produce the reference's message
+      std::vector<ChangeMeta> mh(B); std::vector<u32> ca(B), ar(B); std::vector<u8> ap(B);
+      d2h(ctx, mh.data(), meta.p, B * sizeof(ChangeMeta)); d2h(ctx, ca.data(), changeActor.p, B * 4); d2h(ctx, ar.data(), appRank.p, B * 4); d2h(ctx, ap.data(), applied.p, B); sync(ctx);
+      std::vector<u32> byRank(numNew, 0); for (size_t b = 0; b < B; b++) if (ap[b]) byRank[ar[b]] = (u32)b;
+      std::vector<u64> clk = clockNow;
+      for (size_t k = 0; k < numNew; k++) {
+        const u32 b = byRank[k]; const u64 expected = clk[ca[b]] + 1; const std::string actorHex = hex_of((const u8*)actorsNow[ca[b]].data(), actorsNow[ca[b]].size());
+        if (mh[b].seq < expected) throw Error(AMG_ERR_RANGE, "Reuse of sequence number " + std::to_string(mh[b].seq) + " for actor " + actorHex);
+        if (mh[b].seq > expected) throw Error(AMG_ERR_RANGE, "Skipped sequence number " + std::to_string(expected) + " for actor " + actorHex);
+        clk[ca[b]] = mh[b].seq;
+      }
+      throw Error(AMG_ERR_INTERNAL, "amgpu: sequence check disagreement");
+    }
+    for (size_t a = 0; a < A; a++) clockNow[a] += actorCntH[a];
+    // ---------------------------------------------------------- 5. decode ops
+    opBase.ensure(ctx, B + 1); predBase.ensure(ctx, B + 1); timeBase.ensure(ctx, B + 1);
+    foreach(ctx, B, MaskedCountKernel{nOps.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, opBase.p, B);
+    foreach(ctx, B, MaskedCountKernel{nPreds.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, predBase.p, B);
+    M = readU32(opBase.p + B); P = readU32(predBase.p + B);
+    if (!inOrder) {
+      perm.ensure(ctx, B + 1); dev_memset(ctx, perm.p, 0, (B + 1) * 4);
+      foreach(ctx, B, OpsInOrderKernel{nOps.p, applied.p, appRank.p, perm.p});
+      scan_exclusive(ctx, scanTmp, perm.p, perm.p, numNew);
+    }
+    foreach(ctx, B, TimeBaseKernel{perm.p, applied.p, appRank.p, opBase.p, inOrder ? 1 : 0, timeBase.p});
+    DBuf<u64>& maxOpD = pairSucc; maxOpD.ensure(ctx, 1); h2d(ctx, maxOpD.p, &maxOpNow, 8);
+    foreach(ctx, B, MaxOpKernel{meta.p, applied.p, maxOpD.p});
+    d2h(ctx, &maxOpNow, maxOpD.p, 8);
+    for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, M + 1);
+    r_predActor.ensure(ctx, P + 1); r_predCtr.ensure(ctx, P + 1);
+    // absent columns leave their rows untouched: pre-fill with null
+    for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrLen, &r_action, &r_valLen}) fill32(b->p, NULL32, M);
+    for (DBuf<u32>* b : {&r_keyStrOff, &r_insert, &r_valOff, &r_predNum, &r_predOff}) dev_memset(ctx, b->p, 0, (M + 1) * 4);
+    fill32(r_predActor.p, NULL32, P); fill32(r_predCtr.p, NULL32, P);
+    RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
+    foreach(ctx, (size_t)NCOLS * B, DecodeColumnKernel{arena.p, B, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+    for (DBuf<u64>* b : {&o_id, &o_obj, &o_key}) b->ensure(ctx, M + 1);
+    o_predId.ensure(ctx, P + 1);
+    for (DBuf<u32>* b : {&o_keyStrOff, &o_keyStrLen, &o_flags, &o_valLen, &o_valOff, &o_predOff, &o_predNum, &o_change, &o_time}) b->ensure(ctx, M + 1);
+    OpRows ops{o_id.p, o_obj.p, o_key.p, o_keyStrOff.p, o_keyStrLen.p, o_flags.p, o_valLen.p, o_valOff.p, o_predOff.p, o_predNum.p, o_change.p, o_time.p, o_predId.p};
+    foreach(ctx, M, FinalizeOpsKernel{B, meta.p, opBase.p, timeBase.p, amapBase.p, amap.p, applied.p, raw, ops, errWord.p});
+    checkErr(actorsNow);
+    timer.mark();
+    // ---------------------------------------------------------- 6. op set
+    if (maxOpNow >= (1ULL << 40)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: op counters above 2^40");
+    const int ordBits = bits_for(maxOpNow) + rb;
+    isRow.ensure(ctx, M + 1); rowSlot.ensure(ctx, M + 1); rowOfOp.ensure(ctx, M + 1);
+    foreach(ctx, M, RowFlagKernel{o_flags.p, isRow.p}); scan_exclusive(ctx, scanTmp, isRow.p, rowSlot.p, M);
+    const size_t R = readU32(rowSlot.p + M); N = numRows + R;
+    if (N >= (1u << 29)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 2^29 document rows");
+    doc.ensure(ctx, N + 1, numRows);
+    DocRows w = doc.view();
+    foreach(ctx, M, AppendRowsKernel{ops, isRow.p, rowSlot.p, numRows, w, rowOfOp.p});
+    const size_t icap = pow2_at_least(2 * N + 2); idKeys.ensure(ctx, icap); idVals.ensure(ctx, icap); dev_memset(ctx, idKeys.p, 0, icap * 8);
+    idt = IdTable{idKeys.p, idVals.p, (u64)icap - 1};
+    foreach(ctx, N, IdInsertKernel{w.id, idt, errWord.p});
+    objRow.ensure(ctx, N + 1); elemRow.ensure(ctx, N + 1); parentRow.ensure(ctx, N + 1);
+    foreach(ctx, N, ResolveRowsKernel{w, idt, ord, numRows, objRow.p, elemRow.p, parentRow.p, errWord.p});
+    checkErr(actorsNow);
+    // map keys: intern, verify, rank distinct keys with an LSD string sort
+    const size_t kcap = pow2_at_least(2 * N + 2); keySlots.ensure(ctx, kcap); keySlot.ensure(ctx, N + 1); repList.ensure(ctx, N + 1); repCount.ensure(ctx, 4);
+    foreach(ctx, kcap, KeySlotInitKernel{keySlots.p});
+    foreach(ctx, N, KeyInternKernel{arena.p, w, keySlots.p, (u64)kcap - 1, keySlot.p});
+    dev_memset(ctx, repCount.p, 0, 16);
+    foreach(ctx, N, KeyVerifyKernel{arena.p, w, keySlots.p, keySlot.p, repList.p, repCount.p, errWord.p});
+    u32 rc[2]; d2h(ctx, rc, repCount.p, 8); sync(ctx);
+    const size_t D = rc[0]; const u32 maxKeyLen = rc[1];
+    if (D > 0) {
+      sortKeys.ensure(ctx, D); sortVals.ensure(ctx, D);
+      d2d(ctx, sortVals.p, repList.p, D * 4);
+      const int chunks = (int)((maxKeyLen + 6) / 7);
+      for (int ch = std::max(chunks, 1) - 1; ch >= 0; ch--) {
+        foreach(ctx, D, KeyChunkKernel{arena.p, w, sortVals.p, (u32)ch * 7, sortKeys.p});
+        sortPairs(sortKeys, sortVals, D, 64);
+      }
+      foreach(ctx, D, KeyRankKernel{sortVals.p, keySlot.p, keySlots.p});
+    }
+    // RGA order of every list: sibling sort, Euler tour, pointer jumping
+    listPos.ensure(ctx, N + 1); insItems.ensure(ctx, N + 1); emit.ensure(ctx, N + 1); slot.ensure(ctx, N + 2);
+    foreach(ctx, N, InsertFlagKernel{w, emit.p}); scan_exclusive(ctx, scanTmp, emit.p, slot.p, N);
+    const size_t I = readU32(slot.p + N);
+    if (I > 0) {
+      const int parentBits = bits_for(N) + 1;
+      if (ordBits + parentBits > 64) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: opId range x document size exceeds the 64-bit sibling sort key");
+      foreach(ctx, N, CompactKernel{emit.p, slot.p, insItems.p});
+      sortKeys.ensure(ctx, I); sortVals.ensure(ctx, I);
+      foreach(ctx, I, SiblingKeyKernel{w, insItems.p, parentRow.p, objRow.p, ord, ordBits, sortKeys.p, errWord.p});
+      d2d(ctx, sortVals.p, insItems.p, I * 4);
+      sortPairs(sortKeys, sortVals, I, ordBits + parentBits);
+      const size_t S = 4 * N; eNext.ensure(ctx, S); eNext2.ensure(ctx, S); eRank.ensure(ctx, S); eRank2.ensure(ctx, S);
+      foreach(ctx, S, EulerInitKernel{eNext.p, eRank.p});
+      foreach(ctx, I, EulerLinkKernel{sortKeys.p, sortVals.p, ordBits, eNext.p, eRank.p, I});
+      const int rounds = bits_for(S);
+      for (int k = 0; k < rounds; k++) {
+        foreach(ctx, S, ListRankKernel{eNext.p, eRank.p, eNext2.p, eRank2.p});
+        std::swap(eNext.p, eNext2.p); std::swap(eNext.cap, eNext2.cap); std::swap(eRank.p, eRank2.p); std::swap(eRank.cap, eRank2.cap);
+      }
+      foreach(ctx, N, ListPosKernel{eRank.p, elemRow.p, objRow.p, w, listPos.p});
+    } else dev_memset(ctx, listPos.p, 0, (N + 1) * 4);
+    checkErr(actorsNow);
+    // document order: stable LSD over (object, key rank | list position, opId within the key / element)
+    perm.ensure(ctx, N + 1); pos.ensure(ctx, N + 1); sortKeys.ensure(ctx, N);
+    foreach(ctx, N, IotaKernel{perm.p});
+    const int fieldBits[3] = {ordBits + 1, bits_for(N), ordBits + 1};
+    for (int f = 0; f < 3; f++) {
+      foreach(ctx, N, DocKeyKernel{f, w, perm.p, listPos.p, keySlots.p, keySlot.p, ord, sortKeys.p});
+      sortPairs(sortKeys, perm, N, fieldBits[f]);
+    }
+    foreach(ctx, N, InversePermKernel{perm.p, pos.p});
+    // succ lists
+    numPairs = numSucc + P;
+    pairKey.ensure(ctx, numPairs + 1); pairSucc.ensure(ctx, numPairs + 1); pairIdx.ensure(ctx, numPairs + 1); pairPos.ensure(ctx, numPairs + 1); pairTime.ensure(ctx, numPairs + 1);
+    foreach(ctx, numRows, OldPairsKernel{succOff.p, succ.p, pos.p, ord, pairKey.p, pairIdx.p, pairSucc.p, pairPos.p, pairTime.p});
+    foreach(ctx, M, PredPairsKernel{ops, idt, pos.p, rowOfOp.p, w, elemRow.p, keySlot.p, ord, pairKey.p, pairIdx.p, pairSucc.p, pairPos.p, pairTime.p, numSucc, errWord.p});
+    foreach(ctx, M, DelKeyCheckKernel{arena.p, ops, idt, w, errWord.p});
+    {
+      const u64 w2 = fetchErr();
+      if (w2) {
+        if ((w2 & 0xff) == KE_PRED_MISSING) { u64 pid = 0; d2h(ctx, &pid, o_predId.p + (w2 >> 8), 8); sync(ctx); actorIds.swap(actorsNow); std::string t = opIdText(pid); actorIds.swap(actorsNow); throw Error(AMG_ERR_RANGE, "no matching operation for pred: " + t); }
+        throwKernelError(w2, actorsNow);
+      }
+    }
+    sortPairs(pairKey, pairIdx, numPairs, ordBits);
+    foreach(ctx, numPairs, PairPosKeyKernel{pairPos.p, pairIdx.p, pairKey.p});
+    sortPairs(pairKey, pairIdx, numPairs, bits_for(N));
+    succCnt.ensure(ctx, N + 2); newSuccCnt.ensure(ctx, N + 2); newSuccOff.ensure(ctx, N + 2); firstNewSucc.ensure(ctx, N + 2); newSucc.ensure(ctx, numPairs + 1);
+    dev_memset(ctx, succCnt.p, 0, (N + 2) * 4); dev_memset(ctx, newSuccCnt.p, 0, (N + 2) * 4); dev_memset(ctx, firstNewSucc.p, 0xff, (N + 2) * 4);
+    foreach(ctx, numPairs, CountSuccKernel{pairPos.p, succCnt.p});
+    foreach(ctx, numPairs, NewSuccFlagKernel{pairPos.p, pairTime.p, newSuccCnt.p});
+    foreach(ctx, numPairs, FirstSuccTimeKernel{pairPos.p, pairTime.p, firstNewSucc.p});
+    scan_exclusive(ctx, scanTmp, succCnt.p, newSuccOff.p, N);
+    foreach(ctx, numPairs, WriteSuccKernel{pairIdx.p, pairSucc.p, newSucc.p});
+    sorted.ensure(ctx, N + 1);
+    foreach(ctx, N, GatherRowsKernel{w, sorted.view(), perm.p});
+    timer.mark();
+    // ---------------------------------------------------------- 7. incremental patch
+    if (wantPatch) {
+      objPos.ensure(ctx, N + 1);
+      foreach(ctx, N, ObjPosKernel{perm.p, objRow.p, pos.p, objPos.p});
+      buildPatch(sorted.view(), N, false, &ops, M, &idt, rowOfOp.p, pos.p, actorsNow, out);
+    }
+    checkErr(actorsNow);
+    // heads
+    {
+      DBuf<u32>& isDep = groupLinked; isDep.ensure(ctx, G + 1); dev_memset(ctx, isDep.p, 0, (G + 1) * 4);
+      foreach(ctx, B, MarkDepsKernel{applied.p, meta.p, depBase.p, depIdx.p, isDep.p});
+      emit.ensure(ctx, B + 1); slot.ensure(ctx, B + 2); objStart.ensure(ctx, B + 1);
+      foreach(ctx, B, HeadFlag2Kernel{applied.p, isDep.p, numApplied, emit.p});
+      scan_exclusive(ctx, scanTmp, emit.p, slot.p, B);
+      const u32 nh = readU32(slot.p + B);
+      foreach(ctx, B, CompactKernel{emit.p, slot.p, objStart.p});
+      std::vector<u32> hb(nh); d2h(ctx, hb.data(), objStart.p, nh * 4);
+      std::vector<u32> oldDep(headIdx.size());
+      for (size_t i = 0; i < headIdx.size(); i++) d2h(ctx, &oldDep[i], isDep.p + headIdx[i], 4);
+      sync(ctx);
+      std::vector<std::array<u8, 32>> hs; std::vector<u32> hi;
+      for (size_t i = 0; i < headIdx.size(); i++) if (!oldDep[i]) { hs.push_back(heads[i]); hi.push_back(headIdx[i]); }
+      std::vector<u32> rankOfB(nh);
+      for (u32 k = 0; k < nh; k++) { std::array<u8, 32> h; d2h(ctx, h.data(), hashes.p + (numApplied + hb[k]) * 32, 32); d2h(ctx, &rankOfB[k], appRank.p + hb[k], 4); sync(ctx); hs.push_back(h); hi.push_back((u32)(numApplied + rankOfB[k])); }
+      std::vector<size_t> o(hs.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i;
+      std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return hs[a] < hs[b]; });
+      headsNow.clear(); headIdxNow.clear(); for (size_t i : o) { headsNow.push_back(hs[i]); headIdxNow.push_back(hi[i]); }
+    }
+  } else {
+    headIdxNow = headIdx;
+  }
+  // ------------------------------------------------------------ 8. commit (nothing above mutated persistent state)
+  sync(ctx);
+  if (numNew > 0) {
+    if (!(inOrder && numNew == B)) {   // hashes of applied changes must be contiguous in application order
+      DBuf<u8>& tmp = hashTmp; tmp.ensure(ctx, numNew * 32 + 64);
+      foreach(ctx, B, HashGatherKernel{hashes.p + numApplied * 32, applied.p, appRank.p, tmp.p});
+      d2d(ctx, hashes.p + numApplied * 32, tmp.p, numNew * 32);
+    }
+    std::vector<u32> byRank(numNew);
+    if (appliedH.empty()) for (size_t b = 0; b < B; b++) byRank[b] = (u32)b; else for (size_t b = 0; b < B; b++) if (appliedH[b]) byRank[appRankH[b]] = (u32)b;
+    for (size_t k = 0; k < numNew; k++) {
+      const u32 b = byRank[k];
+      if (batch[b].deflated) deflatedOriginal[(u32)changes.size()] = batchOriginal[b];
+      changes.push_back(batch[b]);
+    }
+    doc.swap(sorted); numRows = N;
+    std::swap(succOff.p, newSuccOff.p); std::swap(succOff.cap, newSuccOff.cap); std::swap(succ.p, newSucc.p); std::swap(succ.cap, newSucc.cap); numSucc = numPairs;
+    fill32(doc.time.p, 0, N);
+    numApplied += numNew; actorRep = actorRepNow; actorIds = actorsNow; clock = clockNow; maxOp = maxOpNow; heads = headsNow; headIdx = headIdxNow;
+    rebuildActorTable();   // slots of actors registered in this call become permanent (first = 0)
+  }
+  arenaLen = cur; queue = newQueue; queueOriginal = newQueueOriginal; rb.armed = false;
+  (void)numFresh;
+  sync(ctx);
+  timer.mark();
+  fillPatchHeader(out);
+  if (isLocal && n == 1) {   // new.js:1874-1877
+    std::vector<ChangeMeta> m0(1); d2h(ctx, m0.data(), meta.p, sizeof(ChangeMeta)); sync(ctx);
+    out.hasActorSeq = true; out.actor.assign((const char*)hostArena.data() + m0[0].actorOff, m0[0].actorLen); out.seq = m0[0].seq;
+  }
+  timer.collect(lastPhaseMs, 8);
+}
+
+}  // namespace amg
+
+namespace amg {
+
+// Patch emission over a document table `d` in document order (N rows). wholeDoc = getPatch semantics
+// (new.js:1604-1635), otherwise incremental semantics for the batch `ops` (new.js:884-1040, 1461-1528).
+// Uses succCnt (per position) and, in incremental mode, newSuccCnt / firstNewSucc / objPos.
+inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows* ops, size_t numOps, const IdTable* idt, const u32* rowOfOpD, const u32* posD,
+                               const std::vector<std::string>& actorsNow, PatchOut& out) {
+  out.props.clear(); out.edits.clear(); out.editElem.clear();
+  if (N == 0) return;
+  // groups (map key / list element) and their visibility
+  head.ensure(ctx, N + 1); headScan.ensure(ctx, N + 2); groupOf.ensure(ctx, N + 1);
+  foreach(ctx, N, GroupHeadKernel{arena.p, d, head.p});
+  scan_exclusive(ctx, scanTmp, head.p, headScan.p, N);
+  const size_t numGroups = readU32(headScan.p + N);
+  groupRows.ensure(ctx, numGroups + 1); groupVisible.ensure(ctx, numGroups + 1); groupFirst.ensure(ctx, numGroups + 1); groupTouched.ensure(ctx, numGroups + 1);
+  DBuf<u32>& groupLinkedB = linkDone;   // linkDone doubles as per-group linked flags storage below (separate buffers)
+  (void)groupLinkedB;
+  dev_memset(ctx, groupRows.p, 0, (numGroups + 1) * 4); dev_memset(ctx, groupVisible.p, 0, (numGroups + 1) * 4); dev_memset(ctx, groupTouched.p, 0, (numGroups + 1) * 4);
+  foreach(ctx, N, GroupStatsKernel{headScan.p, head.p, succCnt.p, d, groupOf.p, groupRows.p, groupVisible.p, groupFirst.p, errWord.p, 0});
+  // objects in document order
+  isObjHead.ensure(ctx, N + 1); objIdx.ensure(ctx, N + 2); 
+  foreach(ctx, N, ObjHeadKernel{d, isObjHead.p});
+  scan_exclusive(ctx, scanTmp, isObjHead.p, objIdx.p, N);
+  const size_t numObjs = readU32(objIdx.p + N);
+  objStart.ensure(ctx, numObjs + 2);
+  foreach(ctx, N, ObjStartKernel{isObjHead.p, objIdx.p, objStart.p, N});
+  { const u32 nn = (u32)N; h2d(ctx, objStart.p + numObjs, &nn, 4); }
+  emit.ensure(ctx, N + 1); marker.ensure(ctx, N + 1); slot.ensure(ctx, N + 2);
+  groupLinked.ensure(ctx, std::max(numGroups, numApplied + 1) + 2);
+  dev_memset(ctx, groupLinked.p, 0, (numGroups + 1) * 4);
+  if (!wholeDoc) {
+    objTouchedAt.ensure(ctx, N + 1); linkDone.ensure(ctx, N + 1);
+    dev_memset(ctx, objTouchedAt.p, 0, (N + 1) * 4); dev_memset(ctx, linkDone.p, 0, (N + 1) * 4); dev_memset(ctx, flagWord.p, 0, 16);
+    foreach(ctx, N, TouchKernel{d, groupOf.p, firstNewSucc.p, groupTouched.p, objTouchedAt.p, objPos.p, flagWord.p + 2});
+    for (int iter = 0; iter < 1000; iter++) {
+      dev_memset(ctx, flagWord.p, 0, 4);
+      foreach(ctx, N, LinkKernel{d, groupOf.p, groupVisible.p, objPos.p, groupLinked.p, objTouchedAt.p, flagWord.p + 2, linkDone.p, flagWord.p, errWord.p});
+      if (!readU32(flagWord.p)) break;
+    }
+  }
+  // ---- map props
+  foreach(ctx, N, PropFlagKernel{d, groupOf.p, groupTouched.p, groupLinked.p, groupVisible.p, head.p, succCnt.p, wholeDoc ? 1 : 0, emit.p, marker.p});
+  scan_exclusive(ctx, scanTmp, emit.p, slot.p, N);
+  const size_t numProps = readU32(slot.p + N);
+  propOut.ensure(ctx, numProps + 1);
+  foreach(ctx, N, PropEmitKernel{d, emit.p, marker.p, slot.p, propOut.p});
+  out.props.resize(numProps); d2h(ctx, out.props.data(), propOut.p, numProps * sizeof(PropRec));
+  // ---- list edits
+  size_t numEdits = 0;
+  if (wholeDoc) {
+    elemVis.ensure(ctx, N + 1); elemVisScan.ensure(ctx, N + 2); rowEmit.ensure(ctx, N + 1); firstVis.ensure(ctx, numGroups + 1);
+    foreach(ctx, N, ListVisFlagKernel{d, groupOf.p, groupVisible.p, head.p, succCnt.p, elemVis.p, rowEmit.p});
+    scan_exclusive(ctx, scanTmp, elemVis.p, elemVisScan.p, N);
+    scan_exclusive(ctx, scanTmp, rowEmit.p, slot.p, N);
+    numEdits = readU32(slot.p + N);
+    dev_memset(ctx, firstVis.p, 0xff, (numGroups + 1) * 4);
+    foreach(ctx, N, FirstVisKernel{groupOf.p, succCnt.p, firstVis.p});
+    editOut.ensure(ctx, numEdits + 1); editElem.ensure(ctx, numEdits + 1);
+    foreach(ctx, N, DocEditEmitKernel{d, rowEmit.p, slot.p, elemVisScan.p, objIdx.p, objStart.p, groupOf.p, groupFirst.p, succCnt.p, firstVis.p, editOut.p});
+    foreach(ctx, N, EditElemKernel{d, rowEmit.p, slot.p, groupOf.p, groupFirst.p, editElem.p});
+  } else {
+    state.ensure(ctx, N + 1); nItems.ensure(ctx, N + 1); itemBase.ensure(ctx, N + 2); qIndex.ensure(ctx, 2 * N + 2);
+    foreach(ctx, N, ElemStateKernel{d, succCnt.p, newSuccCnt.p, firstNewSucc.p, groupRows.p, groupVisible.p, groupOf.p, groupTouched.p, state.p, nItems.p, errWord.p});
+    checkErr(actorsNow);
+    scan_exclusive(ctx, scanTmp, nItems.p, itemBase.p, N);
+    const size_t T = readU32(itemBase.p + N);
+    // any list edit to produce at all? (every new list op has a query item)
+    emit.ensure(ctx, numOps + 1); slot.ensure(ctx, std::max(numOps, N) + 2);
+    foreach(ctx, numOps, OpEditFlagKernel{*ops, posD, *idt, firstNewSucc.p, state.p, emit.p});
+    scan_exclusive(ctx, scanTmp, emit.p, slot.p, numOps);
+    numEdits = readU32(slot.p + numOps);
+    if (numEdits > 0) {
+      items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zero.ensure(ctx, T + 1); wzero.ensure(ctx, T + 1); zscan.ensure(ctx, T + 2); wscan.ensure(ctx, T + 2);
+      foreach(ctx, N, DomBuildKernel{d, state.p, firstNewSucc.p, itemBase.p, objIdx.p, objStart.p, items.p});
+      const int tbits = bits_for(numOps + 1);
+      for (int bit = tbits - 1; bit >= 0; bit--) {
+        foreach(ctx, T, DomFlagKernel{items.p, bit, zero.p, wzero.p});
+        scan_exclusive(ctx, scanTmp, zero.p, zscan.p, T); scan_exclusive(ctx, scanTmp, wzero.p, wscan.p, T);
+        foreach(ctx, T, DomLevelKernel{items.p, items2.p, zscan.p, wscan.p, bit});
+        std::swap(items.p, items2.p); std::swap(items.cap, items2.cap);
+      }
+      foreach(ctx, T, DomResultKernel{items.p, qIndex.p});
+      editOut.ensure(ctx, numEdits + 1); editElem.ensure(ctx, numEdits + 1); editObjKey.ensure(ctx, numEdits + 1);
+      foreach(ctx, numOps, OpEditEmitKernel{*ops, emit.p, slot.p, rowOfOpD, posD, *idt, qIndex.p, editOut.p, editElem.p, editObjKey.p, objIdx.p});
+      // order edits by (object, application time): op order is time order within a pass-ordered batch
+      sortKeys.ensure(ctx, numEdits + 1); sortVals.ensure(ctx, numEdits + 1);
+      foreach(ctx, numEdits, EditKeyKernel{editObjKey.p, editOut.p, sortKeys.p, sortVals.p});
+      sortPairs(sortKeys, sortVals, numEdits, bits_for(numObjs));
+      editOut2.ensure(ctx, numEdits + 1); editElem2.ensure(ctx, numEdits + 1);
+      foreach(ctx, numEdits, EditGatherKernel{editOut.p, editElem.p, sortVals.p, editOut2.p, editElem2.p});
+      std::swap(editOut.p, editOut2.p); std::swap(editOut.cap, editOut2.cap); std::swap(editElem.p, editElem2.p); std::swap(editElem.cap, editElem2.cap);
+    }
+  }
+  if (numEdits > 0) {
+    foreach(ctx, numEdits, RunFlagKernel{editOut.p, editElem.p, numEdits});
+    out.edits.resize(numEdits); out.editElem.resize(numEdits);
+    d2h(ctx, out.edits.data(), editOut.p, numEdits * sizeof(EditRec)); d2h(ctx, out.editElem.data(), editElem.p, numEdits * 8);
+  }
+  sync(ctx);
+}
+
+inline void Engine::getPatch(PatchOut& out) {
+  dev_memset(ctx, errWord.p, 0, 8);
+  succCnt.ensure(ctx, numRows + 2);
+  foreach(ctx, numRows, SuccCntFromOffKernel{succOff.p, succCnt.p});
+  buildPatch(doc.view(), numRows, true, nullptr, 0, nullptr, nullptr, nullptr, actorIds, out);
+  checkErr(actorIds);
+  fillPatchHeader(out);
+}
+
+}  // namespace amg

@@ -1,0 +1,72 @@
+// amgpu — small glue kernels of the pipeline (flags, compaction, sequence-number check, heads).
+#pragma once
+#include "patch.cuh"
+
+namespace amg {
+
+// applied[b] = change b is the first copy of its hash and became causally ready (new.js:1555-1586)
+struct AppliedFlagKernel {
+  const u32* primary; const u32* pass; size_t numApplied; u8* applied; u32* applied32; u32* stats /* [0] count, [1] max finite pass */;
+  HD void operator()(size_t b) const {
+    const bool a = primary[b] == (u32)(numApplied + b) && pass[b] < PASS_INF;
+    applied[b] = a ? 1 : 0; applied32[b] = a ? 1u : 0u;
+    if (a) { atomic_add(stats, 1u); atomic_max(stats + 1, pass[b]); }
+  }
+};
+struct PassKeyKernel { const u32* pass; const u8* applied; u64* key; u32* val; HD void operator()(size_t b) const { key[b] = applied[b] ? pass[b] : 0xffffffffu; val[b] = (u32)b; } };
+struct RankFromOrderKernel { const u32* order; u32* appRank; size_t numNew; HD void operator()(size_t j) const { if (j < numNew) appRank[order[j]] = (u32)j; } };
+struct MaskedCountKernel { const u32* v; const u8* applied; u32* out; HD void operator()(size_t b) const { out[b] = applied[b] ? v[b] : 0u; } };
+// general (multi-pass) order: ops of change b start at time 1 + (ops of changes applied before b)
+struct OpsInOrderKernel { const u32* nOps; const u8* applied; const u32* appRank; u32* tmp; HD void operator()(size_t b) const { if (applied[b]) tmp[appRank[b]] = nOps[b]; } };
+struct TimeBaseKernel { const u32* scanned; const u8* applied; const u32* appRank; const u32* opBase; int inOrder; u32* timeBase; HD void operator()(size_t b) const { timeBase[b] = applied[b] ? (inOrder ? opBase[b] : scanned[appRank[b]]) + 1 : 0; } };
+struct MaxOpKernel { const ChangeMeta* meta; const u8* applied; u64* maxOp; HD void operator()(size_t b) const { if (applied[b] && meta[b].nOps > 0) atomic_max(maxOp, meta[b].startOp + meta[b].nOps - 1); } };
+
+// new actors: the applied change with the smallest application rank per fresh slot registers the representative bytes
+struct NewActorKernel {
+  const ChangeMeta* meta; const u8* applied; const u32* authorSlot; ActorSlot* slots; u32* newSlots; u32* newCount;
+  HD void operator()(size_t b) const {
+    if (!applied[b]) return;
+    ActorSlot& s = slots[authorSlot[b]];
+    if (s.actorNum != EMPTY32 || (u32)(s.first & 0xffffffffu) != (u32)b) return;
+    s.repOff = meta[b].actorOff; s.repLen = meta[b].actorLen;
+    newSlots[atomic_add(newCount, 1u)] = authorSlot[b];
+  }
+};
+struct SetActorNumKernel { ActorSlot* slots; const u32* slotIds; const u32* nums; HD void operator()(size_t i) const { slots[slotIds[i]].actorNum = nums[i]; } };
+struct ChangeActorKernel { const u32* amapBase; const u32* amap; const u8* applied; u32* changeActor; u32* actorCnt; HD void operator()(size_t b) const { if (!applied[b]) { changeActor[b] = EMPTY32; return; } const u32 a = amap[amapBase[b]]; changeActor[b] = a; atomic_add(&actorCnt[a], 1u); } };
+// seq == clock + 1 in application order (new.js:1559, 1571-1579): the seqs of an actor's applied changes must be
+// exactly clock+1 .. clock+count, in increasing application order
+struct SeqScatterKernel {
+  const ChangeMeta* meta; const u8* applied; const u32* changeActor; const u32* appRank; const u32* actorBase; const u32* actorCnt; const u64* clock; u32* seqSlot; u32* bad;
+  HD void operator()(size_t b) const {
+    if (!applied[b]) return;
+    const u32 a = changeActor[b]; const u64 seq = meta[b].seq, c0 = clock[a];
+    if (seq <= c0 || seq - c0 - 1 >= actorCnt[a]) { *bad = 1; return; }
+    if (atomic_cas(&seqSlot[actorBase[a] + (u32)(seq - c0 - 1)], EMPTY32, appRank[b]) != EMPTY32) *bad = 1;
+  }
+};
+struct SeqMonoKernel {
+  const ChangeMeta* meta; const u8* applied; const u32* changeActor; const u32* actorBase; const u64* clock; const u32* seqSlot; u32* bad;
+  HD void operator()(size_t b) const {
+    if (!applied[b]) return;
+    const u32 a = changeActor[b]; const u64 idx = meta[b].seq - clock[a] - 1;
+    if (idx > 0) { const u32 j = actorBase[a] + (u32)idx; if (seqSlot[j - 1] == EMPTY32 || seqSlot[j - 1] > seqSlot[j]) *bad = 1; }
+  }
+};
+// heads (new.js:1582-1583): every dependency of an applied change stops being a head
+struct MarkDepsKernel { const u8* applied; const ChangeMeta* meta; const u32* depBase; const u32* depIdx; u32* isDep; HD void operator()(size_t b) const { if (!applied[b]) return; for (u32 j = 0; j < meta[b].nDeps; j++) { const u32 d = depIdx[depBase[b] + j]; if (d != DEP_MISSING) isDep[d] = 1; } } };
+struct HeadFlag2Kernel { const u8* applied; const u32* isDep; size_t numApplied; u32* flag; HD void operator()(size_t b) const { flag[b] = (applied[b] && !isDep[numApplied + b]) ? 1u : 0u; } };
+struct CompactKernel { const u32* flag; const u32* slot; u32* out; HD void operator()(size_t i) const { if (flag[i]) out[slot[i]] = (u32)i; } };
+struct HashGatherKernel { const u8* src; const u8* applied; const u32* appRank; u8* dst; HD void operator()(size_t b) const { if (!applied[b]) return; const u64* s = reinterpret_cast<const u64*>(src + b * 32); u64* d = reinterpret_cast<u64*>(dst + (size_t)appRank[b] * 32); d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; } };
+struct KeySlotInitKernel { KeySlot* s; HD void operator()(size_t i) const { s[i].hash = 0; s[i].rep = 0xffffffffu; s[i].rank = 0; } };
+struct InsertFlagKernel { DocRows w; u32* flag; HD void operator()(size_t r) const { flag[r] = (w.keyStrLen[r] == NULL32 && (w.flags[r] & F_INSERT)) ? 1u : 0u; } };
+struct GatherU32Kernel { const u32* src; const u32* idx; u32* out; HD void operator()(size_t i) const { out[i] = src[idx[i]]; } };
+struct GatherToU64Kernel { const u32* src; const u32* idx; u64* out; HD void operator()(size_t i) const { out[i] = src[idx[i]]; } };
+struct NewSuccFlagKernel { const u32* pairPos; const u32* pairTime; u32* newCnt; HD void operator()(size_t q) const { if (pairTime[q] != 0) atomic_add(&newCnt[pairPos[q]], 1u); } };
+struct ObjPosKernel { const u32* perm; const u32* objRow; const u32* pos; u32* objPos; HD void operator()(size_t p) const { const u32 o = objRow[perm[p]]; objPos[p] = o == ROW_NONE ? ROW_NONE : pos[o]; } };
+struct SuccCntFromOffKernel { const u32* off; u32* cnt; HD void operator()(size_t p) const { cnt[p] = off[p + 1] - off[p]; } };
+struct EditKeyKernel { const u32* objKey; const EditRec* e; u64* key; u32* val; HD void operator()(size_t j) const { key[j] = objKey[j]; val[j] = (u32)j; } };
+struct EditTimeKeyKernel { const u32* t; u64* key; u32* val; HD void operator()(size_t j) const { key[j] = t[j]; val[j] = (u32)j; } };
+struct EditGatherKernel { const EditRec* in; const u64* elemIn; const u32* idx; EditRec* out; u64* elemOut; HD void operator()(size_t j) const { out[j] = in[idx[j]]; elemOut[j] = elemIn[idx[j]]; } };
+
+}  // namespace amg

@@ -1,0 +1,198 @@
+// amgpu primitives: exclusive scan and stable LSD radix sort (key-value), hand-written for sm_100a.
+//
+// scan_exclusive : 3 kernels (tile reduce -> single-CTA scan of tile sums -> tile scan + offset);
+//                  tiles of 2048 u32 read as 128-bit vectors, warp-shuffle scans inside the CTA.
+// radix_sort_pairs: 8-bit digits; per pass: tile histogram (shared-memory atomics) -> scan of the
+//                  digit-major histogram -> stable scatter. The stable in-tile rank uses
+//                  __match_any_sync warp multisplit (one leader lane per digit value per round bumps
+//                  a per-warp shared-memory counter), so no sorting network and no second key read.
+//                  Only the significant key bits [begin_bit, end_bit) are sorted.
+// Both are HBM-bound streaming passes: 4 B (scan) / 12 B (sort) per element read + written per pass.
+#pragma once
+#include "common.cuh"
+#ifdef AMG_EMU
+#include <algorithm>
+#include <numeric>
+#endif
+
+namespace amg {
+
+#ifndef AMG_EMU
+// ---------------------------------------------------------------- scan
+static const int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ u32 warp_incl_scan(u32 v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+  return v;
+}
+// exclusive scan of one value per thread across a 256-thread CTA; returns exclusive prefix, *total = CTA sum
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32* total, u32* smem /* >= 9 u32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 incl = warp_incl_scan(v);
+  if (lane == 31) smem[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    u32 w = lane < (SCAN_THREADS / 32) ? smem[lane] : 0;
+    u32 wi = warp_incl_scan(w);
+    if (lane < (SCAN_THREADS / 32)) smem[lane] = wi - w;
+    if (lane == (SCAN_THREADS / 32) - 1) smem[8] = wi;
+  }
+  __syncthreads();
+  u32 res = smem[warp] + incl - v;
+  *total = smem[8];
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(256) k_scan_reduce(const u32* __restrict__ in, u32* __restrict__ tileSums, size_t n) {
+  __shared__ u32 sm[9];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  u32 s = 0;
+  if (base + SCAN_ITEMS <= n && ((reinterpret_cast<uintptr_t>(in + base) & 15) == 0)) {
+    const uint4 a = *reinterpret_cast<const uint4*>(in + base), b = *reinterpret_cast<const uint4*>(in + base + 4);
+    s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  } else {
+    for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) s += in[base + k];
+  }
+  u32 total; block_excl_scan(s, &total, sm);
+  if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+// single CTA: exclusive scan of the tile sums in place; writes grand total to *totalOut
+__global__ void __launch_bounds__(256) k_scan_tiles(u32* __restrict__ tileSums, size_t numTiles, u32* __restrict__ totalOut) {
+  __shared__ u32 sm[9];
+  u32 carry = 0;
+  for (size_t base = 0; base < numTiles; base += SCAN_THREADS) {
+    size_t i = base + threadIdx.x;
+    u32 v = i < numTiles ? tileSums[i] : 0, total;
+    u32 ex = block_excl_scan(v, &total, sm);
+    if (i < numTiles) tileSums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *totalOut = carry;
+}
+__global__ void __launch_bounds__(256) k_scan_apply(const u32* in, u32* out, const u32* __restrict__ tileOffsets, size_t n) {   // in may alias out
+  __shared__ u32 sm[9];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  u32 v[SCAN_ITEMS]; u32 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
+  u32 total; u32 ex = block_excl_scan(s, &total, sm) + tileOffsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+}
+#endif
+
+struct ScanTemp { DBuf<u32> tiles; };
+
+// out[0..n) = exclusive prefix sums of in[0..n); out[n] = total (out must hold n+1). in == out allowed.
+inline void scan_exclusive(Ctx& c, ScanTemp& t, const u32* in, u32* out, size_t n) {
+#ifdef AMG_EMU
+  u32 acc = 0; for (size_t i = 0; i < n; i++) { u32 v = in[i]; out[i] = acc; acc += v; } out[n] = acc; c.launches += 3;
+#else
+  if (n == 0) { dev_memset(c, out, 0, sizeof(u32)); return; }
+  size_t numTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  t.tiles.ensure(c, numTiles + 1);
+  k_scan_reduce<<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, t.tiles.p, n);
+  k_scan_tiles<<<1, SCAN_THREADS, 0, c.stream>>>(t.tiles.p, numTiles, out + n);
+  k_scan_apply<<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, out, t.tiles.p, n);
+  CUDA_CHECK(cudaGetLastError());
+  c.launches += 3;
+#endif
+}
+
+// ---------------------------------------------------------------- radix sort
+#ifndef AMG_EMU
+static const int RS_THREADS = 256, RS_ITEMS = 16, RS_TILE = RS_THREADS * RS_ITEMS, RS_WARPS = RS_THREADS / 32, RS_STRIP = 32 * RS_ITEMS;
+
+__global__ void __launch_bounds__(256) k_rs_hist(const u64* __restrict__ keys, u32* __restrict__ histG, size_t n, int shift, unsigned numTiles) {
+  __shared__ u32 hist[256];
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+  for (int j = 0; j < RS_ITEMS; j++) {
+    size_t i = base + (size_t)j * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&hist[(u32)(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  histG[(size_t)threadIdx.x * numTiles + blockIdx.x] = hist[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) k_rs_scatter(const u64* __restrict__ keysIn, const u32* __restrict__ valsIn, u64* __restrict__ keysOut,
+                                                     u32* __restrict__ valsOut, const u32* __restrict__ histScan, size_t n, int shift, unsigned numTiles) {
+  __shared__ u32 warpHist[RS_WARPS][256];
+  __shared__ u32 digitBase[256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&warpHist[0][0])[k] = 0;
+  __syncthreads();
+  const size_t stripBase = (size_t)blockIdx.x * RS_TILE + (size_t)warp * RS_STRIP;
+  u64 key[RS_ITEMS]; u32 val[RS_ITEMS]; u32 rank[RS_ITEMS];
+  const u32 ltMask = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; j++) {
+    const size_t i = stripBase + (size_t)j * 32 + lane;
+    const bool active = i < n;
+    key[j] = active ? keysIn[i] : 0; val[j] = active ? valsIn[i] : 0;
+    const u32 d = active ? ((u32)(key[j] >> shift) & 255u) : 0xffffffffu;
+    const u32 peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    u32 base = 0;
+    if (active && lane == leader) { base = warpHist[warp][d]; warpHist[warp][d] = base + __popc(peers); }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    rank[j] = base + __popc(peers & ltMask);
+    __syncwarp();
+  }
+  __syncthreads();
+  {   // thread d: turn per-warp counts of digit d into exclusive prefixes, add the global base
+    const int d = threadIdx.x; u32 acc = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) { u32 cnt = warpHist[w][d]; warpHist[w][d] = acc; acc += cnt; }
+    digitBase[d] = histScan[(size_t)d * numTiles + blockIdx.x];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; j++) {
+    const size_t i = stripBase + (size_t)j * 32 + lane;
+    if (i < n) {
+      const u32 d = (u32)(key[j] >> shift) & 255u;
+      const size_t dst = (size_t)digitBase[d] + warpHist[warp][d] + rank[j];
+      keysOut[dst] = key[j]; valsOut[dst] = val[j];
+    }
+  }
+}
+#endif
+
+struct SortTemp { DBuf<u32> hist; ScanTemp scan; DBuf<u64> keysAlt; DBuf<u32> valsAlt; };
+
+// Stable sort of (keys, vals) by key bits [beginBit, endBit). `keys`/`vals` are DBufs of size >= n; on
+// return they hold the sorted data (the buffers may have been swapped with the temporaries).
+inline void radix_sort_pairs(Ctx& c, SortTemp& t, DBuf<u64>& keys, DBuf<u32>& vals, size_t n, int beginBit, int endBit) {
+  if (n <= 1 || endBit <= beginBit) return;
+#ifdef AMG_EMU
+  std::vector<size_t> idx(n); std::iota(idx.begin(), idx.end(), 0);
+  const u64 mask = (endBit - beginBit >= 64) ? ~0ULL : (((1ULL << (endBit - beginBit)) - 1) << beginBit);
+  std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return (keys.p[a] & mask) < (keys.p[b] & mask); });
+  std::vector<u64> k2(n); std::vector<u32> v2(n);
+  for (size_t i = 0; i < n; i++) { k2[i] = keys.p[idx[i]]; v2[i] = vals.p[idx[i]]; }
+  memcpy(keys.p, k2.data(), n * 8); memcpy(vals.p, v2.data(), n * 4);
+  c.launches += 5 * ((endBit - beginBit + 7) / 8);
+#else
+  const unsigned numTiles = (unsigned)((n + RS_TILE - 1) / RS_TILE);
+  t.hist.ensure(c, (size_t)256 * numTiles + 1);
+  t.keysAlt.ensure(c, n); t.valsAlt.ensure(c, n);
+  for (int shift = beginBit; shift < endBit; shift += 8) {
+    k_rs_hist<<<numTiles, RS_THREADS, 0, c.stream>>>(keys.p, t.hist.p, n, shift, numTiles);
+    c.launches++;
+    scan_exclusive(c, t.scan, t.hist.p, t.hist.p, (size_t)256 * numTiles);
+    k_rs_scatter<<<numTiles, RS_THREADS, 0, c.stream>>>(keys.p, vals.p, t.keysAlt.p, t.valsAlt.p, t.hist.p, n, shift, numTiles);
+    CUDA_CHECK(cudaGetLastError());
+    c.launches++;
+    std::swap(keys.p, t.keysAlt.p); std::swap(keys.cap, t.keysAlt.cap);
+    std::swap(vals.p, t.valsAlt.p); std::swap(vals.cap, t.valsAlt.cap);
+  }
+#endif
+}
+
+}  // namespace amg
