@@ -177,16 +177,21 @@ template <class T> inline T atomic_max(T* p, T v) { T o = *p; if (v > o) *p = v;
 template <class T> inline T atomic_or(T* p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> inline T atomic_cas(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 #else
-DEV uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
-DEV int atomic_add(int* p, int v) { return atomicAdd(p, v); }
-DEV unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
-DEV uint32_t atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
-DEV unsigned long long atomic_min(unsigned long long* p, unsigned long long v) { return atomicMin(p, v); }
-DEV uint32_t atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
-DEV unsigned long long atomic_max(unsigned long long* p, unsigned long long v) { return atomicMax(p, v); }
-DEV uint32_t atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
-DEV unsigned long long atomic_cas(unsigned long long* p, unsigned long long cmp, unsigned long long v) { return atomicCAS(p, cmp, v); }
-DEV uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
+// host bodies exist only so that the functors can stay __host__ __device__; they are never executed in the CUDA build
+#if defined(__CUDA_ARCH__)
+#define AMG_ATOMIC(devexpr, hostexpr) return devexpr;
+#else
+#define AMG_ATOMIC(devexpr, hostexpr) hostexpr
+#endif
+HD uint32_t atomic_add(uint32_t* p, uint32_t v) { AMG_ATOMIC(atomicAdd(p, v), { uint32_t o = *p; *p = o + v; return o; }) }
+HD unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { AMG_ATOMIC(atomicAdd(p, v), { unsigned long long o = *p; *p = o + v; return o; }) }
+HD uint32_t atomic_min(uint32_t* p, uint32_t v) { AMG_ATOMIC(atomicMin(p, v), { uint32_t o = *p; if (v < o) *p = v; return o; }) }
+HD unsigned long long atomic_min(unsigned long long* p, unsigned long long v) { AMG_ATOMIC(atomicMin(p, v), { unsigned long long o = *p; if (v < o) *p = v; return o; }) }
+HD uint32_t atomic_max(uint32_t* p, uint32_t v) { AMG_ATOMIC(atomicMax(p, v), { uint32_t o = *p; if (v > o) *p = v; return o; }) }
+HD unsigned long long atomic_max(unsigned long long* p, unsigned long long v) { AMG_ATOMIC(atomicMax(p, v), { unsigned long long o = *p; if (v > o) *p = v; return o; }) }
+HD uint32_t atomic_or(uint32_t* p, uint32_t v) { AMG_ATOMIC(atomicOr(p, v), { uint32_t o = *p; *p = o | v; return o; }) }
+HD unsigned long long atomic_cas(unsigned long long* p, unsigned long long cmp, unsigned long long v) { AMG_ATOMIC(atomicCAS(p, cmp, v), { unsigned long long o = *p; if (o == cmp) *p = v; return o; }) }
+HD uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) { AMG_ATOMIC(atomicCAS(p, cmp, v), { uint32_t o = *p; if (o == cmp) *p = v; return o; }) }
 #endif
 
 typedef unsigned long long u64;

@@ -108,7 +108,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   dev_memset(ctx, flagWord.p, 0, 8);
   foreach(ctx, B, AppliedFlagKernel{primary.p, pass.p, numApplied, applied.p, isRow.p, flagWord.p});
   u32 stats[2]; d2h(ctx, stats, flagWord.p, 8); sync(ctx);
-  const size_t numNew = stats[0]; const bool inOrder = stats[1] <= 1;
+  const size_t numNew = stats[0]; const bool inOrder = stats[1] <= 1; batchInOrder = inOrder;
   std::vector<u8> appliedH; std::vector<u32> primaryH, appRankH;
   if (inOrder) scan_exclusive(ctx, scanTmp, isRow.p, appRank.p, B);
   else {
@@ -301,6 +301,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     // succ lists
     numPairs = numSucc + P;
     pairKey.ensure(ctx, numPairs + 1); pairSucc.ensure(ctx, numPairs + 1); pairIdx.ensure(ctx, numPairs + 1); pairPos.ensure(ctx, numPairs + 1); pairTime.ensure(ctx, numPairs + 1);
+    foreach(ctx, M, DelElemCheckKernel{ops, idt, w, errWord.p});
+    checkErr(actorsNow);
     foreach(ctx, numRows, OldPairsKernel{succOff.p, succ.p, pos.p, ord, pairKey.p, pairIdx.p, pairSucc.p, pairPos.p, pairTime.p});
     foreach(ctx, M, PredPairsKernel{ops, idt, pos.p, rowOfOp.p, w, elemRow.p, keySlot.p, ord, pairKey.p, pairIdx.p, pairSucc.p, pairPos.p, pairTime.p, numSucc, errWord.p});
     foreach(ctx, M, DelKeyCheckKernel{arena.p, ops, idt, w, errWord.p});
@@ -473,10 +475,16 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
       }
       foreach(ctx, T, DomResultKernel{items.p, qIndex.p});
       editOut.ensure(ctx, numEdits + 1); editElem.ensure(ctx, numEdits + 1); editObjKey.ensure(ctx, numEdits + 1);
-      foreach(ctx, numOps, OpEditEmitKernel{*ops, emit.p, slot.p, rowOfOpD, posD, *idt, qIndex.p, editOut.p, editElem.p, editObjKey.p, objIdx.p});
-      // order edits by (object, application time): op order is time order within a pass-ordered batch
+      editTime.ensure(ctx, numEdits + 1);
+      foreach(ctx, numOps, OpEditEmitKernel{*ops, emit.p, slot.p, rowOfOpD, posD, *idt, qIndex.p, editOut.p, editElem.p, editObjKey.p, editTime.p, objIdx.p});
+      // order edits by (object, application time); op order already is time order unless the batch needed several passes
       sortKeys.ensure(ctx, numEdits + 1); sortVals.ensure(ctx, numEdits + 1);
-      foreach(ctx, numEdits, EditKeyKernel{editObjKey.p, editOut.p, sortKeys.p, sortVals.p});
+      if (batchInOrder) foreach(ctx, numEdits, EditKeyKernel{editObjKey.p, editOut.p, sortKeys.p, sortVals.p});
+      else {
+        foreach(ctx, numEdits, EditTimeKeyKernel{editTime.p, sortKeys.p, sortVals.p});
+        sortPairs(sortKeys, sortVals, numEdits, bits_for(numOps + 1));
+        foreach(ctx, numEdits, GatherToU64Kernel{editObjKey.p, sortVals.p, sortKeys.p});
+      }
       sortPairs(sortKeys, sortVals, numEdits, bits_for(numObjs));
       editOut2.ensure(ctx, numEdits + 1); editElem2.ensure(ctx, numEdits + 1);
       foreach(ctx, numEdits, EditGatherKernel{editOut.p, editElem.p, sortVals.p, editOut2.p, editElem2.p});

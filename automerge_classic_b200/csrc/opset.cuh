@@ -84,7 +84,7 @@ struct ResolveRowsKernel {
         }
       } else {
         er = id_lookup(t, key);
-        if (er == ROW_NONE || w.obj[er] != obj || !(w.flags[er] & F_INSERT)) { if (r >= numOld) raise(errWord, KE_LIST_ELEM, r); er = ROW_NONE; }
+        if (er == ROW_NONE || w.obj[er] != obj || !(w.flags[er] & F_INSERT)) { if (r >= numOld) raise(errWord, KE_REF_ELEM, r); er = ROW_NONE; }
       }
     }
     elemRow[r] = er; parentRow[r] = pr;
@@ -239,6 +239,15 @@ struct PredPairsKernel {
       if (!ok) raise(errWord, KE_PRED_MISSING, p);
       pairPos[q] = pos[target];
     }
+  }
+};
+// list `del` ops have no row: their element must exist (seekToOp would throw first, new.js:293-301)
+struct DelElemCheckKernel {
+  OpRows ops; IdTable t; DocRows w; u64* errWord;
+  HD void operator()(size_t i) const {
+    if (flags_action(ops.flags[i]) != ACT_DEL || ops.keyStrLen[i] != NULL32) return;
+    const u32 e = id_lookup(t, ops.key[i]);
+    if (e == ROW_NONE || w.obj[e] != ops.obj[i] || !(w.flags[e] & F_INSERT) || w.keyStrLen[e] != NULL32) raise(errWord, KE_REF_ELEM, i);
   }
 };
 // map-key `del` ops have no row: check their preds' keys by bytes

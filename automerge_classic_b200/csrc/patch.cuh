@@ -228,7 +228,7 @@ struct OpEditFlagKernel {
   }
 };
 struct OpEditEmitKernel {
-  OpRows ops; const u32* emit; const u32* slot; const u32* rowOfOp; const u32* pos; IdTable t; const u32* qIndex; EditRec* out; u64* elemOut; u32* objKeyOut /* sort key: index of the object in document order */; const u32* objIdx;
+  OpRows ops; const u32* emit; const u32* slot; const u32* rowOfOp; const u32* pos; IdTable t; const u32* qIndex; EditRec* out; u64* elemOut; u32* objKeyOut /* sort key: index of the object in document order */; u32* timeOut; const u32* objIdx;
   HD void operator()(size_t i) const {
     if (!emit[i]) return;
     EditRec e; e.obj = ops.obj[i]; u32 p;
@@ -241,7 +241,7 @@ struct OpEditEmitKernel {
       p = pos[rowOfOp[i]];
       e.opId = ops.id[i]; e.index = qIndex[2 * p]; e.kind = EK_INSERT | (flags_action(ops.flags[i]) << 16); e.valLen = ops.valLen[i]; e.valOff = ops.valOff[i]; elemOut[slot[i]] = ops.id[i];
     }
-    out[slot[i]] = e; objKeyOut[slot[i]] = objIdx[p];
+    out[slot[i]] = e; objKeyOut[slot[i]] = objIdx[p]; timeOut[slot[i]] = ops.time[i];
   }
 };
 // appendEdit coalescing (new.js:747-782): edit j continues the run of edit j-1

@@ -269,7 +269,7 @@ class GpuBackendDoc:
         p = self._lib.L.amg_arena(self.h, C.byref(n))
         if not p or n.value == 0:
             return memoryview(b'')
-        return memoryview((C.c_uint8 * n.value).from_address(p))
+        return memoryview((C.c_uint8 * n.value).from_address(p)).cast('B')
 
     def _take_patch(self, pp):
         n = C.c_size_t()

@@ -1,0 +1,108 @@
+"""Parity checks shared by the GPU tests (tests/test_engine_gpu.py, CUDA through the C ABI) and the
+host-logic emulation tests (tests/test_pipeline_emu.py, same kernel sources run serially on the CPU)."""
+import numpy as np
+
+import replay
+
+
+def _dump_equal(gpu, orc):
+    """document-ordered op table + succ lists (SURVEY.md §8c parity item 3)"""
+    gr, gs = gpu.dump_ops()
+    orows, osucc, oactors = orc.dump_ops()
+    gactors = gpu._state().actors
+    assert gactors == oactors
+    assert len(gr) == len(orows)
+    none = np.uint64(0xffffffffffffffff)
+    o = orows.astype(np.int64)
+    exp = np.stack([o[:, 0], o[:, 1], o[:, 4], o[:, 5], o[:, 2], o[:, 3]], axis=1)   # objCtr,objActor,idCtr,idActor,keyCtr,keyActor
+    got = gr[:, :6].astype(np.int64)
+    got[gr[:, :6] == none] = -1
+    # the oracle reports keyCtr/keyActor null (-1) for map rows and keyCtr 0 / keyActor null for _head
+    assert np.array_equal(got[:, :4], exp[:, :4])
+    assert np.array_equal(got[:, 4:6], exp[:, 4:6])
+    assert np.array_equal(gr[:, 7].astype(np.int64), o[:, 9])      # succNum
+    assert np.array_equal(gs.astype(np.int64), osucc)
+
+
+def check_trace_parity(gpu_doc, oracle_mod, cfg, n, a):
+    from automerge_classic_b200 import tracegen
+    t = tracegen.generate(cfg, n, a)
+    ch = t.changes()
+    orc = oracle_mod.OracleDoc()
+    po = orc.apply_changes(ch)
+    g = gpu_doc()
+    pg = g.apply_changes(ch)
+    for k in ('maxOp', 'clock', 'deps', 'pendingChanges'):
+        assert pg[k] == po[k], k
+    if cfg != 'C4':   # C4: the reference's incremental map patch omits some conflicting values; final state is compared below
+        d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+        assert d is None, d
+    d = replay.deep_equal(replay.decode(g.get_patch()), replay.decode(orc.get_patch()))
+    assert d is None, d
+    _dump_equal(g, orc)
+
+
+def check_incremental_calls(gpu_doc, oracle_mod):
+    """Applying a trace in several applyChanges calls gives the same patches as the oracle call by call."""
+    from automerge_classic_b200 import tracegen
+    ch = tracegen.generate('C3', 4000, 4).changes()
+    orc, g = oracle_mod.OracleDoc(), gpu_doc()
+    for lo in range(0, len(ch), 997):
+        po = orc.apply_changes(ch[lo:lo + 997])
+        pg = g.apply_changes(ch[lo:lo + 997])
+        d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+        assert d is None, (lo, d)
+    _dump_equal(g, orc)
+
+
+def check_out_of_order(gpu_doc, oracle_mod):
+    """Changes delivered in reverse order are queued and applied in the reference's pass order."""
+    from automerge_classic_b200 import tracegen
+    ch = tracegen.generate('C3', 300, 3).changes()
+    rev = ch[:1] + ch[1:][::-1]
+    orc, g = oracle_mod.OracleDoc(), gpu_doc()
+    po, pg = orc.apply_changes(rev), g.apply_changes(rev)
+    d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+    assert d is None, d
+    # missing dependency: everything after the gap stays pending
+    orc2, g2 = oracle_mod.OracleDoc(), gpu_doc()
+    po, pg = orc2.apply_changes(ch[:5] + ch[6:40]), g2.apply_changes(ch[:5] + ch[6:40])
+    assert pg['pendingChanges'] == po['pendingChanges'] and pg['pendingChanges'] > 0
+    d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+    assert d is None, d
+    po, pg = orc2.apply_changes([ch[5]]), g2.apply_changes([ch[5]])
+    d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+    assert d is None, d
+
+
+def check_errors_atomic(gpu_doc):
+    from automerge_classic_b200 import tracegen
+    from automerge_classic_b200.engine import AmgError
+    ch = tracegen.generate('C2', 50, 0).changes()
+    g = gpu_doc()
+    g.apply_changes(ch[:10])
+    before = g.get_patch()
+    bad = bytearray(ch[10]); bad[20] ^= 0xff
+    for payload, msg in ((bytes(bad), 'checksum does not match data'), (b'\x00' * 40, 'magic bytes')):
+        try:
+            g.apply_changes([payload])
+        except AmgError as e:
+            assert msg in str(e), str(e)
+        else:
+            raise AssertionError('expected error: ' + msg)
+    assert g.get_patch() == before
+    g.apply_changes(ch[10:])
+
+
+def check_large_text(gpu_doc, oracle_mod, n):
+    """C3 at 100k ops: full parity against the oracle (the oracle finishes this size in seconds)."""
+    from automerge_classic_b200 import tracegen
+    t = tracegen.generate('C3', n, 10)
+    g = gpu_doc()
+    fp = g.apply_packed_flat(t.blob, t.offsets, t.n_changes)
+    orc = oracle_mod.OracleDoc()
+    po = orc.apply_changes(t.changes())
+    pg = fp.to_patch(False)
+    d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+    assert d is None, d
+    _dump_equal(g, orc)

@@ -139,6 +139,19 @@ class Replayer:
 
         for step in test['steps']:
             op = step['op']
+            # a step whose inputs were never produced (an earlier step failed) cannot run
+            needs = [step.get(k) for k in ('h', 'src', 'h1') if k in step and op.startswith('b_') and op not in ('b_init', 'b_load')]
+            if op == 'b_get_changes_added':
+                needs.append(step['h2'])
+            if any(x not in self.handles or self.handles[x] is None for x in needs):
+                if not fails:
+                    fails.append('step %s: input handle missing' % op)
+                continue
+            if op in ('apply', 'get_patch', 'save', 'heads', 'clock', 'max_op', 'get_changes', 'get_missing_deps', 'blocks', 'clone') and \
+                    (step.get('doc', step.get('src')) not in self.docs):
+                if not fails:
+                    fails.append('step %s: input doc missing' % op)
+                continue
             if op == 'new_doc':
                 self.docs[step['doc']] = self.doc_class()
             elif op == 'load_doc':
@@ -211,7 +224,8 @@ class Replayer:
                 self.handles[step['h']] = self.facade.init()
             elif op == 'b_clone':
                 out, failed = guarded(step, lambda: self.facade.clone(self.handles[step['src']]))
-                self.handles[step['h']] = out
+                if not failed:
+                    self.handles[step['h']] = out
             elif op == 'b_free':
                 self.facade.free(self.handles[step['h']])
             elif op == 'b_apply':
@@ -229,11 +243,16 @@ class Replayer:
                 out, failed = guarded(step, lambda: self.facade.save(self.handles[step['h']]))
                 self.results[step['res']] = out
             elif op == 'b_load':
+                if 'data' not in step or step['data'] is None:
+                    fails.append('b_load: fixture carries no data')
+                    continue
                 out, failed = guarded(step, lambda: self.facade.load(bytes.fromhex(step['data'])))
-                self.handles[step['h']] = out
+                if not failed:
+                    self.handles[step['h']] = out
             elif op == 'b_load_changes':
                 out, failed = guarded(step, lambda: self.facade.loadChanges(self.handles[step['h']], changes_of(step)))
-                self.handles[step['h2']] = out
+                if not failed:
+                    self.handles[step['h2']] = out
             elif op == 'b_get_patch':
                 out, failed = guarded(step, lambda: self.facade.getPatch(self.handles[step['h']]))
                 self.results[step['res']] = decode(out)
