@@ -6,7 +6,7 @@
 
 using namespace amg;
 
-struct amg_patch { std::vector<u8> bytes; };
+struct amg_patch { const u8* p; size_t len; };   // view into the engine's pinned patch buffer
 struct amg_buffers { std::vector<std::string> items; };
 
 namespace {
@@ -63,25 +63,7 @@ void setErr(amg_error* err, int code, const std::string& msg) {
   try { __VA_ARGS__ } catch (amg::Error& e) { setErr(err, e.code, e.what()); return e.code; } \
   catch (std::exception& e) { setErr(err, AMG_INTERNAL_ERROR, e.what()); return AMG_INTERNAL_ERROR; }
 
-void pad8(std::vector<u8>& b) { while (b.size() % 8) b.push_back(0); }
-template <class T> void put(std::vector<u8>& b, const T& v) { const u8* p = (const u8*)&v; b.insert(b.end(), p, p + sizeof(T)); }
-
-amg_patch* serialize(const PatchOut& p) {
-  auto* out = new amg_patch(); std::vector<u8>& b = out->bytes;
-  u64 hdr[18] = {0}; hdr[0] = 0x31504747414d41ULL; hdr[1] = p.maxOp; hdr[2] = p.pendingChanges; hdr[3] = p.hasActorSeq ? 1 : 0; hdr[4] = p.seq;
-  b.resize(sizeof(hdr));
-  hdr[5] = b.size(); hdr[6] = p.actor.size(); b.insert(b.end(), p.actor.begin(), p.actor.end()); pad8(b);
-  hdr[7] = b.size(); hdr[8] = p.actors.size();
-  for (auto& a : p.actors) { put<u32>(b, (u32)a.size()); b.insert(b.end(), a.begin(), a.end()); while (b.size() % 4) b.push_back(0); }
-  pad8(b);
-  hdr[9] = b.size(); hdr[10] = p.clock.size(); for (auto& c : p.clock) { put<u64>(b, c.first); put<u64>(b, c.second); }
-  hdr[11] = b.size(); hdr[12] = p.deps.size(); for (auto& d : p.deps) b.insert(b.end(), d.begin(), d.end());
-  hdr[13] = b.size(); hdr[14] = p.props.size(); { const u8* s = (const u8*)p.props.data(); b.insert(b.end(), s, s + p.props.size() * sizeof(PropRec)); }
-  hdr[15] = b.size(); hdr[16] = p.edits.size(); { const u8* s = (const u8*)p.edits.data(); b.insert(b.end(), s, s + p.edits.size() * sizeof(EditRec)); }
-  hdr[17] = b.size(); { const u8* s = (const u8*)p.editElem.data(); b.insert(b.end(), s, s + p.editElem.size() * 8); }
-  memcpy(b.data(), hdr, sizeof(hdr));
-  return out;
-}
+amg_patch* serialize(const PatchOut& p) { return new amg_patch{p.bytes, p.bytesLen}; }
 Hash toHash(const u8* p) { Hash h; memcpy(h.data(), p, 32); return h; }
 std::string hashHex(const Hash& h) { return hex_of(h.data(), 32); }
 }  // namespace
@@ -94,13 +76,15 @@ amg_backend* amg_init(int cuda_device, amg_error* err) {
   catch (std::exception& e) { setErr(err, AMG_INTERNAL_ERROR, e.what()); return nullptr; }
 }
 void amg_free(amg_backend* b) { delete b; }
+int amg_reset(amg_backend* b, amg_error* err) { AMG_GUARD(b->g = HostGraph(); b->eng.reset(); return 0;) }
+int amg_reserve(amg_backend* b, size_t arena_bytes, amg_error* err) { AMG_GUARD(b->eng.hostArena.reserve(arena_bytes); b->eng.arena.ensure(b->eng.ctx, arena_bytes + 64, b->eng.arenaLen); return 0;) }
 
 amg_backend* amg_clone(amg_backend* src, amg_error* err) {
   try {
     auto* b = new amg_backend(src->eng.ctx.device);
     Engine& d = b->eng; Engine& s = src->eng; Ctx& c = d.ctx;
     sync(s.ctx);
-    d.hostArena = s.hostArena; d.arenaLen = s.arenaLen; d.arena.ensure(c, s.arenaLen + 64); d2d(c, d.arena.p, s.arena.p, s.arenaLen);
+    d.hostArena.assign(s.hostArena); d.arenaLen = s.arenaLen; d.arena.ensure(c, s.arenaLen + 64); d2d(c, d.arena.p, s.arena.p, s.arenaLen);
     d.numApplied = s.numApplied; d.hashes.ensure(c, s.numApplied * 32 + 64); d2d(c, d.hashes.p, s.hashes.p, s.numApplied * 32);
     d.numRows = s.numRows; d.doc.ensure(c, s.numRows + 1);
     d2d(c, d.doc.id.p, s.doc.id.p, s.numRows * 8); d2d(c, d.doc.obj.p, s.doc.obj.p, s.numRows * 8); d2d(c, d.doc.key.p, s.doc.key.p, s.numRows * 8);
@@ -129,9 +113,9 @@ int amg_get_patch(amg_backend* b, amg_patch** out, amg_error* err) {
   AMG_GUARD(PatchOut p; b->eng.getPatch(p); *out = serialize(p); return 0;)
 }
 int amg_get_state(amg_backend* b, amg_patch** out, amg_error* err) {
-  AMG_GUARD(PatchOut p; b->eng.fillPatchHeader(p); *out = serialize(p); return 0;)
+  AMG_GUARD(PatchOut p; b->eng.fillPatchHeader(p); b->eng.finishPatch(p); *out = serialize(p); return 0;)
 }
-const uint8_t* amg_patch_bytes(const amg_patch* p, size_t* len) { *len = p->bytes.size(); return p->bytes.data(); }
+const uint8_t* amg_patch_bytes(const amg_patch* p, size_t* len) { *len = p->len; return p->p; }
 void amg_patch_free(amg_patch* p) { delete p; }
 const uint8_t* amg_arena(amg_backend* b, size_t* len) { *len = b->eng.hostArena.size(); return b->eng.hostArena.data(); }
 
@@ -241,10 +225,10 @@ int amg_debug_dump_ops(amg_backend* b, uint64_t** rows_out, size_t* n, uint64_t*
     *rows_out = (uint64_t*)r; *n = N; *succ_out = (uint64_t*)s; *m = S; return 0;)
 }
 
-int amg_debug_decode(amg_backend*, const uint8_t*, const uint64_t*, size_t, uint8_t*, uint32_t*, uint32_t**, size_t*, amg_error* err) {
-  setErr(err, AMG_UNSUPPORTED, "amg_debug_decode: not built yet"); return AMG_UNSUPPORTED;
+int amg_debug_decode(amg_backend* b, const uint8_t* blob, const uint64_t* offsets, size_t n, uint8_t* hashes_out, uint32_t* n_ops_out, uint32_t** rows_out, size_t* total_ops, amg_error* err) {
+  AMG_GUARD(b->eng.decodeRaw(blob, (const u64*)offsets, n, hashes_out, n_ops_out, rows_out, total_ops); return 0;)
 }
-int amg_bench_decode(amg_backend*, int, float*, float*, float*, uint64_t*, amg_error* err) {
-  setErr(err, AMG_UNSUPPORTED, "amg_bench_decode: not built yet"); return AMG_UNSUPPORTED;
+int amg_bench_decode(amg_backend* b, int iters, float* ms_sha, float* ms_parse, float* ms_decode, uint64_t* algo_bytes, amg_error* err) {
+  AMG_GUARD(u64 bytes = 0; b->eng.benchDecode(iters, ms_sha, ms_parse, ms_decode, &bytes); *algo_bytes = bytes; return 0;)
 }
 }  // extern "C"

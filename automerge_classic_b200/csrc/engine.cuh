@@ -34,15 +34,25 @@ struct DocBufs {
   }
 };
 
-struct PatchOut {   // flat patch (see include/amgpu.h for the byte layout produced by serialize())
+struct PatchOut {   // flat patch, written straight into the engine's pinned output buffer (layout: include/amgpu.h)
   u64 maxOp = 0, pendingChanges = 0; bool hasActorSeq = false; std::string actor; u64 seq = 0;
-  std::vector<std::pair<u32, u64>> clock; std::vector<std::array<u8, 32>> deps;
-  std::vector<PropRec> props; std::vector<EditRec> edits; std::vector<u64> editElem;
-  std::vector<std::string> actors;
-  std::vector<u8> bytes;
+  std::vector<std::pair<u32, u64>> clock; std::vector<std::array<u8, 32>> deps; std::vector<std::string> actors;
+  size_t propsOff = 0, numProps = 0, editsOff = 0, numEdits = 0, elemOff = 0, bigEnd = 0;   // byte offsets into Engine::patchBuf
+  const u8* bytes = nullptr; size_t bytesLen = 0;   // final serialised patch (valid until the next call on the same engine)
 };
 
 struct HostChange { u32 off, len; bool deflated; };
+
+// Pinned host mirror of the arena: grows without zero-filling; H2D copies read straight from it.
+struct HostArena {
+  HBuf<u8> buf; size_t len = 0;
+  u8* data() { return buf.p; } const u8* data() const { return buf.p; }
+  size_t size() const { return len; }
+  void reserve(size_t n) { buf.ensure(n + 64); }
+  void resize(size_t n) { if (n > len) buf.ensure(n + 64); len = n; }
+  void append(const void* p, size_t n) { const size_t at = len; resize(len + n); memcpy(buf.p + at, p, n); }
+  void assign(const HostArena& o) { resize(o.len); if (o.len) memcpy(buf.p, o.buf.p, o.len); }
+};
 
 inline std::string hex_of(const u8* p, size_t n) { static const char* d = "0123456789abcdef"; std::string s; for (size_t i = 0; i < n; i++) { s.push_back(d[p[i] >> 4]); s.push_back(d[p[i] & 15]); } return s; }
 
@@ -50,7 +60,7 @@ class Engine {
  public:
   Ctx ctx;
   // ---- persistent device state
-  DBuf<u8> arena; size_t arenaLen = 0; std::vector<u8> hostArena;   // host mirror (values / keys / changes are read from it)
+  DBuf<u8> arena; size_t arenaLen = 0; HostArena hostArena;   // pinned host mirror (values / keys / changes are read from it)
   DBuf<u8> hashes; size_t numApplied = 0;
   DocBufs doc; size_t numRows = 0; DBuf<u32> succOff; DBuf<u64> succ; size_t numSucc = 0;
   DBuf<ActorSlot> actorSlots; size_t actorCap = 0;
@@ -66,6 +76,7 @@ class Engine {
   std::vector<HostChange> queue; std::vector<std::string> queueOriginal;   // not yet causally ready
   u64 maxOp = 0;
   float lastPhaseMs[8] = {0};
+  HBuf<u8> patchBuf;   // pinned: patch records are copied device -> host directly into their final place
   // ---- scratch (grow-only)
   DBuf<u32> chOff, chLen, nOps, nPreds, nDeps, nActors, colOff, colLen, depBase, depIdx, primary, pass, flagWord, appRank, opBase, predBase, timeBase, amapBase, amap, authorSlot, newSlots;
   DBuf<u8> applied; DBuf<ChangeMeta> meta; DBuf<u64> errWord; DBuf<u32> hashTable;
@@ -80,6 +91,7 @@ class Engine {
   DBuf<u32> isObjHead, objIdx, objStart, elemVis, elemVisScan, rowEmit, firstVis, state, nItems, itemBase, qIndex, zero, wzero, zscan, wscan, editObjKey;
   DBuf<DomItem> items, items2; DBuf<PropRec> propOut; DBuf<EditRec> editOut, editOut2; DBuf<u64> editElem, editElem2;
   DBuf<u32> seqSlot, actorCnt, actorBaseD, clockD, changeActor, editTime; DBuf<u8> hashTmp; bool batchInOrder = true;
+  DBuf<u32> finalTime, gFailed, memberFinal, opAt, runHead, opGroupHead; DBuf<u64> gBound; DocRows workView{};
 
   explicit Engine(int device) {
     ctx.device = device;
@@ -192,6 +204,11 @@ class Engine {
   void buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows* ops, size_t numOps, const IdTable* idt, const u32* rowOfOpD, const u32* posD,
                   const std::vector<std::string>& actorsNow, PatchOut& out);
   void fillPatchHeader(PatchOut& out);
+  void finishPatch(PatchOut& out);
+  void reset();
+  void benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes);
+  void decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* hashesOut, u32* nOpsOut, u32** rowsOut, size_t* totalOps);
+  size_t lastB = 0, lastM = 0, lastP = 0, lastBytes = 0;
 };
 
 }  // namespace amg

@@ -20,9 +20,8 @@ struct PhaseTimer {
 };
 
 inline void parallel_copy(u8* dst, const u8* src, size_t n) {
-  const size_t kChunk = 8u << 20;
-  if (n < 2 * kChunk) { memcpy(dst, src, n); return; }
-  unsigned nt = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+  if (n < (4u << 20)) { memcpy(dst, src, n); return; }
+  unsigned nt = std::min<unsigned>(4, std::max(1u, std::thread::hardware_concurrency()));
   std::vector<std::thread> ts; size_t per = (n + nt - 1) / nt;
   for (unsigned t = 0; t < nt; t++) { size_t a = t * per, b = std::min(n, a + per); if (a < b) ts.emplace_back([=] { memcpy(dst + a, src + a, b - a); }); }
   for (auto& t : ts) t.join();
@@ -34,6 +33,33 @@ inline void Engine::fillPatchHeader(PatchOut& out) {
   out.deps = heads; out.actors = actorIds;
 }
 
+// writes the header and the small sections (actor, actors, clock, deps) after the big record sections
+inline void Engine::finishPatch(PatchOut& out) {
+  if (out.bigEnd == 0) { out.propsOff = out.editsOff = out.elemOff = 18 * 8; out.bigEnd = 18 * 8; }
+  size_t small = 64 + out.actor.size(); for (auto& a : out.actors) small += 8 + a.size(); small += out.clock.size() * 16 + out.deps.size() * 32 + 64;
+  patchBuf.ensure(out.bigEnd + small);   // growth preserves what is already there
+  u8* b = patchBuf.p; size_t at = out.bigEnd;
+  auto pad8 = [&]() { while (at % 8) b[at++] = 0; };
+  u64 hdr[18] = {0}; hdr[0] = 0x31504747414d41ULL; hdr[1] = out.maxOp; hdr[2] = out.pendingChanges; hdr[3] = out.hasActorSeq ? 1 : 0; hdr[4] = out.seq;
+  pad8(); hdr[5] = at; hdr[6] = out.actor.size(); memcpy(b + at, out.actor.data(), out.actor.size()); at += out.actor.size(); pad8();
+  hdr[7] = at; hdr[8] = out.actors.size();
+  for (auto& a : out.actors) { const u32 l = (u32)a.size(); memcpy(b + at, &l, 4); at += 4; memcpy(b + at, a.data(), l); at += l; while (at % 4) b[at++] = 0; }
+  pad8(); hdr[9] = at; hdr[10] = out.clock.size();
+  for (auto& c : out.clock) { const u64 a = c.first, s = c.second; memcpy(b + at, &a, 8); memcpy(b + at + 8, &s, 8); at += 16; }
+  hdr[11] = at; hdr[12] = out.deps.size(); for (auto& d : out.deps) { memcpy(b + at, d.data(), 32); at += 32; }
+  hdr[13] = out.propsOff; hdr[14] = out.numProps; hdr[15] = out.editsOff; hdr[16] = out.numEdits; hdr[17] = out.elemOff;
+  memcpy(b, hdr, sizeof(hdr));
+  out.bytes = b; out.bytesLen = at;
+}
+
+// forgets the document but keeps every allocation (steady-state serving / benchmarking)
+inline void Engine::reset() {
+  sync(ctx);
+  arenaLen = 0; hostArena.len = 0; numApplied = 0; numRows = 0; numSucc = 0; dev_memset(ctx, succOff.p, 0, 4);
+  actorIds.clear(); actorRep.clear(); clock.clear(); heads.clear(); headIdx.clear(); changes.clear(); changeHashes.clear(); deflatedOriginal.clear();
+  queue.clear(); queueOriginal.clear(); maxOp = 0; rebuildActorTable();
+}
+
 inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out) {
   PhaseTimer timer(ctx);
   // ------------------------------------------------------------ 0. stage the batch in the arena (host mirror + device)
@@ -41,7 +67,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   std::vector<HostChange> batch; std::vector<std::string> batchOriginal;   // original bytes only for deflated changes
   batch.reserve(n + queue.size());
   struct Rollback { Engine* e; size_t len; bool armed = true; ~Rollback() { if (armed) { e->hostArena.resize(len); e->rebuildActorTable(); } } };
-  bool anyDeflated = false; size_t total = 0;
+  bool anyDeflated = false, uploaded = false; size_t total = 0;
   for (size_t i = 0; i < n; i++) {
     const u8* p = blob ? blob + offsets[i] : bufs[i]; const size_t l = blob ? (size_t)(offsets[i + 1] - offsets[i]) : lens[i];
     if (l > 8 && p[8] == 2) anyDeflated = true;
@@ -52,7 +78,14 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   size_t cur = arenaLen0;
   if (!anyDeflated && blob && n > 0) {
     const size_t base = offsets[0]; const size_t tot = offsets[n] - base;
-    hostArena.resize(cur + tot); parallel_copy(hostArena.data() + cur, blob + base, tot);
+    hostArena.resize(cur + tot); arena.ensure(ctx, cur + tot + 64, arenaLen0);
+    const size_t kChunk = 16u << 20;   // copy into the pinned mirror and upload chunk by chunk (H2D overlaps the next host copy)
+    for (size_t o = 0; o < tot; o += kChunk) {
+      const size_t m = std::min(kChunk, tot - o);
+      parallel_copy(hostArena.data() + cur + o, blob + base + o, m);
+      h2d(ctx, arena.p + cur + o, hostArena.data() + cur + o, m);
+    }
+    uploaded = true;
     for (size_t i = 0; i < n; i++) batch.push_back(HostChange{(u32)(cur + offsets[i] - base), (u32)(offsets[i + 1] - offsets[i]), false});
     batchOriginal.resize(n); cur += tot;
   } else {
@@ -61,10 +94,10 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       if (l > 8 && p[8] == 2) {
         std::string inflated = inflateChange(p, l);
         if ((u64)cur + inflated.size() + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
-        hostArena.insert(hostArena.end(), inflated.begin(), inflated.end());
+        hostArena.append(inflated.data(), inflated.size());
         batch.push_back(HostChange{(u32)cur, (u32)inflated.size(), true}); batchOriginal.emplace_back((const char*)p, l); cur += inflated.size();
       } else {
-        hostArena.insert(hostArena.end(), p, p + l);
+        hostArena.append(p, l);
         batch.push_back(HostChange{(u32)cur, (u32)l, false}); batchOriginal.emplace_back(); cur += l;
       }
     }
@@ -72,9 +105,9 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   const size_t numFresh = batch.size();
   for (size_t i = 0; i < queue.size(); i++) { batch.push_back(queue[i]); batchOriginal.push_back(queueOriginal[i]); }
   const size_t B = batch.size();
-  if (B == 0) { rb.armed = false; fillPatchHeader(out); return; }
+  if (B == 0) { rb.armed = false; fillPatchHeader(out); finishPatch(out); return; }
   arena.ensure(ctx, cur + 64, arenaLen0);
-  h2d(ctx, arena.p + arenaLen0, hostArena.data() + arenaLen0, cur - arenaLen0);
+  if (!uploaded) h2d(ctx, arena.p + arenaLen0, hostArena.data() + arenaLen0, cur - arenaLen0);
   dev_memset(ctx, arena.p + cur, 0, 64);
   {
     std::vector<u32> off(B), len(B); for (size_t b = 0; b < B; b++) { off[b] = batch[b].off; len[b] = batch[b].len; }
@@ -330,6 +363,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     if (wantPatch) {
       objPos.ensure(ctx, N + 1);
       foreach(ctx, N, ObjPosKernel{perm.p, objRow.p, pos.p, objPos.p});
+      workView = w;
       buildPatch(sorted.view(), N, false, &ops, M, &idt, rowOfOp.p, pos.p, actorsNow, out);
     }
     checkErr(actorsNow);
@@ -387,6 +421,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     std::vector<ChangeMeta> m0(1); d2h(ctx, m0.data(), meta.p, sizeof(ChangeMeta)); sync(ctx);
     out.hasActorSeq = true; out.actor.assign((const char*)hostArena.data() + m0[0].actorOff, m0[0].actorLen); out.seq = m0[0].seq;
   }
+  lastB = B; lastM = M; lastP = P; lastBytes = 0; for (auto& c : batch) lastBytes += c.len;
+  finishPatch(out);
   timer.collect(lastPhaseMs, 8);
 }
 
@@ -399,7 +435,7 @@ namespace amg {
 // Uses succCnt (per position) and, in incremental mode, newSuccCnt / firstNewSucc / objPos.
 inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows* ops, size_t numOps, const IdTable* idt, const u32* rowOfOpD, const u32* posD,
                                const std::vector<std::string>& actorsNow, PatchOut& out) {
-  out.props.clear(); out.edits.clear(); out.editElem.clear();
+  out.numProps = out.numEdits = 0; out.bigEnd = 0;
   if (N == 0) return;
   // groups (map key / list element) and their visibility
   head.ensure(ctx, N + 1); headScan.ensure(ctx, N + 2); groupOf.ensure(ctx, N + 1);
@@ -433,12 +469,27 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
     }
   }
   // ---- map props
-  foreach(ctx, N, PropFlagKernel{d, groupOf.p, groupTouched.p, groupLinked.p, groupVisible.p, head.p, succCnt.p, wholeDoc ? 1 : 0, emit.p, marker.p});
+  DBuf<u32>& groupEmitted = elemVis;   // scratch reuse (list edits re-initialise it later)
+  groupEmitted.ensure(ctx, std::max(numGroups, N) + 2); dev_memset(ctx, groupEmitted.p, 0, (numGroups + 1) * 4);
+  finalTime.ensure(ctx, numGroups + 1); gBound.ensure(ctx, numGroups + 1); gFailed.ensure(ctx, numGroups + 1); memberFinal.ensure(ctx, N + 1);
+  dev_memset(ctx, finalTime.p, 0, (numGroups + 1) * 4);
+  Ord ordNow{actorRank.p, bits_for(actorsNow.size() > 1 ? actorsNow.size() - 1 : 1)};
+  if (!wholeDoc && numOps > 0) {
+    dev_memset(ctx, memberFinal.p, 0, (N + 1) * 4); dev_memset(ctx, gFailed.p, 0, (numGroups + 1) * 4);
+    opAt.ensure(ctx, numOps + 1); runHead.ensure(ctx, numOps + 1); opGroupHead.ensure(ctx, numOps + 1);
+    foreach(ctx, numOps, OpAtTimeKernel{ops->time, opAt.p});
+    MapGroupCtx mg{arena.p, *ops, opAt.p, numOps};
+    foreach(ctx, numOps, RunHeadKernel{mg, runHead.p});
+    foreach(ctx, numOps, GroupSplitKernel{mg, runHead.p, opGroupHead.p});
+    for (int pass = 0; pass < 2; pass++)
+      foreach(ctx, numOps, GroupFinalKernel{pass, mg, opGroupHead.p, *idt, rowOfOpD, posD, groupOf.p, workView, ordNow, finalTime.p, gBound.p, gFailed.p, memberFinal.p});
+  }
+  foreach(ctx, N, PropFlagKernel{d, groupOf.p, groupTouched.p, groupLinked.p, succCnt.p, wholeDoc ? 1 : 0, finalTime.p, gBound.p, gFailed.p, memberFinal.p, ordNow, emit.p, groupEmitted.p});
+  foreach(ctx, N, PropMarkerKernel{d, groupOf.p, groupTouched.p, head.p, groupEmitted.p, wholeDoc ? 1 : 0, emit.p, marker.p});
   scan_exclusive(ctx, scanTmp, emit.p, slot.p, N);
   const size_t numProps = readU32(slot.p + N);
   propOut.ensure(ctx, numProps + 1);
   foreach(ctx, N, PropEmitKernel{d, emit.p, marker.p, slot.p, propOut.p});
-  out.props.resize(numProps); d2h(ctx, out.props.data(), propOut.p, numProps * sizeof(PropRec));
   // ---- list edits
   size_t numEdits = 0;
   if (wholeDoc) {
@@ -491,11 +542,12 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
       std::swap(editOut.p, editOut2.p); std::swap(editOut.cap, editOut2.cap); std::swap(editElem.p, editElem2.p); std::swap(editElem.cap, editElem2.cap);
     }
   }
-  if (numEdits > 0) {
-    foreach(ctx, numEdits, RunFlagKernel{editOut.p, editElem.p, numEdits});
-    out.edits.resize(numEdits); out.editElem.resize(numEdits);
-    d2h(ctx, out.edits.data(), editOut.p, numEdits * sizeof(EditRec)); d2h(ctx, out.editElem.data(), editElem.p, numEdits * 8);
-  }
+  if (numEdits > 0) foreach(ctx, numEdits, RunFlagKernel{editOut.p, editElem.p, numEdits});
+  out.numProps = numProps; out.numEdits = numEdits;
+  out.propsOff = 18 * 8; out.editsOff = out.propsOff + numProps * sizeof(PropRec); out.elemOff = out.editsOff + numEdits * sizeof(EditRec); out.bigEnd = out.elemOff + numEdits * 8;
+  patchBuf.ensure(out.bigEnd + 4096);
+  d2h(ctx, patchBuf.p + out.propsOff, propOut.p, numProps * sizeof(PropRec));
+  if (numEdits > 0) { d2h(ctx, patchBuf.p + out.editsOff, editOut.p, numEdits * sizeof(EditRec)); d2h(ctx, patchBuf.p + out.elemOff, editElem.p, numEdits * 8); }
   sync(ctx);
 }
 
@@ -506,6 +558,70 @@ inline void Engine::getPatch(PatchOut& out) {
   buildPatch(doc.view(), numRows, true, nullptr, 0, nullptr, nullptr, nullptr, actorIds, out);
   checkErr(actorIds);
   fillPatchHeader(out);
+  finishPatch(out);
+}
+
+}  // namespace amg
+
+namespace amg {
+
+// Re-runs the decode kernels over the last applied batch (bytes resident in HBM) and times them with CUDA events.
+inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes) {
+  if (lastB == 0 || iters <= 0) throw Error(AMG_ERR_RANGE, "amg_bench_decode: no batch has been applied yet");
+  const size_t B = lastB;
+  hashTmp.ensure(ctx, B * 32 + 64);
+  RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
+  *algoBytes = (u64)lastBytes + 48ull * lastM + 8ull * lastP + 96ull * B;
+#ifndef AMG_EMU
+  cudaEvent_t e[4]; for (auto& x : e) cudaEventCreate(&x);
+  cudaEventRecord(e[0], ctx.stream);
+  for (int i = 0; i < iters; i++) foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr});
+  cudaEventRecord(e[1], ctx.stream);
+  for (int i = 0; i < iters; i++) foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
+  cudaEventRecord(e[2], ctx.stream);
+  for (int i = 0; i < iters; i++) foreach(ctx, (size_t)NCOLS * B, DecodeColumnKernel{arena.p, B, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+  cudaEventRecord(e[3], ctx.stream);
+  CUDA_CHECK(cudaEventSynchronize(e[3]));
+  float a, b, c; cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[2], e[3]);
+  *msSha = a / iters; *msParse = b / iters; *msDec = c / iters;
+  for (auto& x : e) cudaEventDestroy(x);
+#else
+  *msSha = *msParse = *msDec = 0;
+#endif
+}
+
+// Parity hook: hashes, op counts and the raw decoded columns (change-local values) of a batch, without touching the document.
+inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* hashesOut, u32* nOpsOut, u32** rowsOut, size_t* totalOps) {
+  std::vector<u32> off(n), len(n); std::string staged;
+  for (size_t i = 0; i < n; i++) {
+    const u8* p = blob + offsets[i]; const size_t l = offsets[i + 1] - offsets[i];
+    std::string inflated; if (l > 8 && p[8] == 2) inflated = inflateChange(p, l);
+    off[i] = (u32)staged.size(); len[i] = (u32)(inflated.empty() ? l : inflated.size());
+    if (inflated.empty()) staged.append((const char*)p, l); else staged += inflated;
+  }
+  DBuf<u8> ar; ar.ensure(ctx, staged.size() + 64); h2d(ctx, ar.p, staged.data(), staged.size()); dev_memset(ctx, ar.p + staged.size(), 0, 64);
+  chOff.ensure(ctx, n); chLen.ensure(ctx, n); h2d(ctx, chOff.p, off.data(), n * 4); h2d(ctx, chLen.p, len.data(), n * 4);
+  dev_memset(ctx, errWord.p, 0, 8); hashTmp.ensure(ctx, n * 32 + 64);
+  foreach(ctx, n, ShaKernel{ar.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr});
+  meta.ensure(ctx, n); colOff.ensure(ctx, (size_t)NCOLS * n); colLen.ensure(ctx, (size_t)NCOLS * n);
+  nOps.ensure(ctx, n + 1); nPreds.ensure(ctx, n + 1); nDeps.ensure(ctx, n + 1); nActors.ensure(ctx, n + 1);
+  foreach(ctx, n, ParseKernel{ar.p, chOff.p, chLen.p, n, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
+  checkErr(actorIds);
+  opBase.ensure(ctx, n + 1); predBase.ensure(ctx, n + 1); applied.ensure(ctx, n); dev_memset(ctx, applied.p, 1, n);
+  scan_exclusive(ctx, scanTmp, nOps.p, opBase.p, n); scan_exclusive(ctx, scanTmp, nPreds.p, predBase.p, n);
+  const size_t M = readU32(opBase.p + n), P = readU32(predBase.p + n);
+  DBuf<u32>* cols[12] = {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff};
+  for (auto* b : cols) b->ensure(ctx, M + 1);
+  r_predActor.ensure(ctx, P + 1); r_predCtr.ensure(ctx, P + 1);
+  for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrLen, &r_action, &r_valLen}) fill32(b->p, NULL32, M);
+  for (DBuf<u32>* b : {&r_keyStrOff, &r_insert, &r_valOff, &r_predNum, &r_predOff}) dev_memset(ctx, b->p, 0, (M + 1) * 4);
+  RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
+  foreach(ctx, (size_t)NCOLS * n, DecodeColumnKernel{ar.p, n, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+  checkErr(actorIds);
+  d2h(ctx, hashesOut, hashTmp.p, n * 32); d2h(ctx, nOpsOut, nOps.p, n * 4);
+  u32* rows = (u32*)malloc(sizeof(u32) * 12 * (M + 1));
+  for (int k = 0; k < 12; k++) d2h(ctx, rows + (size_t)k * M, cols[k]->p, M * 4);
+  sync(ctx); *rowsOut = rows; *totalOps = M; lastB = 0;
 }
 
 }  // namespace amg

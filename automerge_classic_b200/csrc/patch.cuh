@@ -76,17 +76,109 @@ struct LinkKernel {
     if (objPos[p] == ROW_NONE) *rootTouched = 1; else objTouchedAt[objPos[p]] = 1;
   }
 };
-struct PropFlagKernel {   // which positions emit a prop record; marker = "key is now empty" ({} in the patch)
-  DocRows d; const u32* groupOf; const u32* groupTouched; const u32* groupLinked; const u32* groupVisible; const u32* head; const u32* succCnt; int wholeDoc; u32* emit; u32* marker;
-  HD void operator()(size_t p) const {
-    u32 e = 0, m = 0;
-    if (d.keyStrLen[p] != NULL32) {
-      const u32 g = groupOf[p]; const bool vis = succCnt[p] == 0;
-      if (wholeDoc) e = vis ? 1 : 0;
-      else if (groupTouched[g]) { if (vis) e = 1; else if (groupVisible[g] == 0 && head[p]) { e = 1; m = 1; } }
-      else if (groupLinked[g]) e = vis ? 1 : 0;
+// ---------------------------------------------------------------- which conflicting values the reference re-emits
+// mergeDocChangeOps (new.js:1085-1138) processes the change ops of one author in "groups" (consecutive ops on the
+// same key that do not overwrite each other). After a group's last op is placed, the remaining document ops of
+// that key (those with a greater opId) are only re-emitted into the patch if no further group could be gathered
+// into the same pass (new.js:1119-1129, 1149); otherwise they are passed over silently (new.js:1225-1230). The
+// patch content of a key is what the LAST pass touching it emitted (props[key] is reset per pass, new.js:1037).
+HD int key_cmp_utf16(const u8* a, u32 la, const u8* b, u32 lb) {   // JS string `<` on UTF-8 bytes
+  const u32 n = la < lb ? la : lb;
+  for (u32 i = 0; i < n; i++) {
+    u32 x = a[i], y = b[i];
+    if (x != y) {
+      if (x == 0xEE || x == 0xEF) x += 5; else if (x >= 0xF0 && x <= 0xF4) x -= 2;
+      if (y == 0xEE || y == 0xEF) y += 5; else if (y >= 0xF0 && y <= 0xF4) y -= 2;
+      return x < y ? -1 : 1;
     }
-    emit[p] = e; marker[p] = m;
+  }
+  return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+struct OpAtTimeKernel { const u32* time; u32* opAt; HD void operator()(size_t i) const { opAt[time[i] - 1] = (u32)i; } };
+struct MapGroupCtx {
+  const u8* arena; OpRows ops; const u32* opAt; size_t numOps;
+  HD bool isMapOp(u32 i) const { return ops.keyStrLen[i] != NULL32; }
+  HD bool sameKey(u32 i, u32 j) const {
+    if (ops.keyStrLen[i] != ops.keyStrLen[j]) return false;
+    for (u32 k = 0; k < ops.keyStrLen[i]; k++) if (arena[ops.keyStrOff[i] + k] != arena[ops.keyStrOff[j] + k]) return false;
+    return true;
+  }
+  HD bool sameRun(u32 i, u32 j) const {
+    return isMapOp(i) && isMapOp(j) && id_actor(ops.id[i]) == id_actor(ops.id[j]) && ((ops.flags[i] ^ ops.flags[j]) & F_INSERT) == 0 &&
+           ops.obj[i] == ops.obj[j] && sameKey(i, j);
+  }
+};
+struct RunHeadKernel { MapGroupCtx c; u32* runHead; HD void operator()(size_t t) const { runHead[t] = (t == 0 || !c.sameRun(c.opAt[t], c.opAt[t - 1])) ? 1u : 0u; } };
+struct GroupSplitKernel {   // one thread per run: a new group starts where an op overwrites an op of the current group (new.js:1092-1101)
+  MapGroupCtx c; const u32* runHead; u32* groupHead;
+  HD void operator()(size_t t0) const {
+    if (!runHead[t0]) return;
+    size_t gstart = t0; groupHead[t0] = 1;
+    for (size_t t = t0 + 1; t < c.numOps && !runHead[t]; t++) {
+      const u32 i = c.opAt[t]; bool over = false;
+      for (u32 j = 0; j < c.ops.predNum[i] && !over; j++) {
+        const u64 p = c.ops.predId[c.ops.predOff[i] + j];
+        for (size_t u = gstart; u < t && !over; u++) over = c.ops.id[c.opAt[u]] == p;
+      }
+      groupHead[t] = over ? 1u : 0u;
+      if (over) gstart = t;
+    }
+  }
+};
+struct GroupFinalKernel {   // pass 0: finalTime[g] = latest group on key group g; pass 1: that group publishes bound / failed / members
+  int pass; MapGroupCtx c; const u32* groupHead; IdTable t; const u32* rowOfOp; const u32* pos; const u32* groupOf; DocRows w; Ord ord;
+  u32* finalTime; u64* bound; u32* failed; u32* member;
+  HD void operator()(size_t t0) const {
+    if (!groupHead[t0]) return;
+    const u32 i0 = c.opAt[t0]; if (!c.isMapOp(i0)) return;
+    u64 b = 0; u32 g = ROW_NONE; size_t t = t0;
+    for (; t < c.numOps && (t == t0 || !groupHead[t]); t++) {
+      const u32 i = c.opAt[t];
+      if (flags_action(c.ops.flags[i]) == ACT_DEL) {
+        for (u32 j = 0; j < c.ops.predNum[i]; j++) {
+          const u32 target = id_lookup(this->t, c.ops.predId[c.ops.predOff[i] + j]); if (target == ROW_NONE) continue;
+          const u64 o = ord(w.id[target]); if (o > b) b = o; g = groupOf[pos[target]];
+        }
+      } else {
+        const u64 o = ord(c.ops.id[i]); if (o > b) b = o;
+        if (rowOfOp[i] != ROW_NONE) { g = groupOf[pos[rowOfOp[i]]]; if (pass == 1 && finalTime[g] == (u32)t0 + 1) member[pos[rowOfOp[i]]] = 1; }
+      }
+    }
+    if (g == ROW_NONE) return;
+    if (pass == 0) { atomic_max(&finalTime[g], (u32)t0 + 1); return; }
+    if (finalTime[g] != (u32)t0 + 1) return;
+    bool gathered = false;
+    if (t < c.numOps) {
+      const u32 nx = c.opAt[t];
+      gathered = c.isMapOp(nx) && id_actor(c.ops.id[nx]) == id_actor(c.ops.id[i0]) && ((c.ops.flags[nx] ^ c.ops.flags[i0]) & F_INSERT) == 0 && c.ops.obj[nx] == c.ops.obj[i0] &&
+                 key_cmp_utf16(c.arena + c.ops.keyStrOff[i0], c.ops.keyStrLen[i0], c.arena + c.ops.keyStrOff[nx], c.ops.keyStrLen[nx]) < 0;
+    }
+    bound[g] = b; failed[g] = gathered ? 0u : 1u;
+    // members of a group that straddles the walk above were flagged on the fly; flag again now that finalTime is known
+    for (size_t u = t0; u < t; u++) { const u32 i = c.opAt[u]; if (rowOfOp[i] != ROW_NONE) member[pos[rowOfOp[i]]] = 1; }
+  }
+};
+struct PropFlagKernel {   // which positions emit a prop record
+  DocRows d; const u32* groupOf; const u32* groupTouched; const u32* groupLinked; const u32* succCnt; int wholeDoc;
+  const u32* finalTime; const u64* bound; const u32* failed; const u32* member; Ord ord; u32* emit; u32* groupEmitted;
+  HD void operator()(size_t p) const {
+    u32 e = 0;
+    if (d.keyStrLen[p] != NULL32 && succCnt[p] == 0) {
+      const u32 g = groupOf[p];
+      if (wholeDoc) e = 1;
+      else if (groupTouched[g]) e = (finalTime[g] == 0 || failed[g] || member[p] || ord(d.id[p]) <= bound[g]) ? 1 : 0;
+      else if (groupLinked[g]) e = 1;
+    }
+    emit[p] = e;
+    if (e) atomic_add(&groupEmitted[groupOf[p]], 1u);
+  }
+};
+struct PropMarkerKernel {   // a touched key with nothing to show is reported as `key: {}` (new.js:1037)
+  DocRows d; const u32* groupOf; const u32* groupTouched; const u32* head; const u32* groupEmitted; int wholeDoc; u32* emit; u32* marker;
+  HD void operator()(size_t p) const {
+    u32 m = 0;
+    if (!wholeDoc && d.keyStrLen[p] != NULL32 && head[p] && groupTouched[groupOf[p]] && groupEmitted[groupOf[p]] == 0) { m = 1; emit[p] = 1; }
+    marker[p] = m;
   }
 };
 struct PropEmitKernel {

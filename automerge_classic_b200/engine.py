@@ -305,7 +305,12 @@ class GpuBackendDoc:
 
     def apply_packed_flat(self, blob, offs, n, is_local=False, want_patch=True):
         pp, err = C.c_void_p(), _ErrStruct()
-        buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob) if isinstance(blob, (bytes, bytearray)) else blob
+        if isinstance(blob, (bytes, bytearray)):
+            buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob)
+        elif isinstance(blob, np.ndarray):
+            buf = blob.ctypes.data_as(C.c_void_p)
+        else:
+            buf = blob   # a ctypes pointer / address (e.g. pinned host memory)
         rc = self._lib.L.amg_apply_changes_packed(self.h, buf, offs.ctypes.data_as(C.c_void_p), C.c_size_t(n), int(is_local), int(want_patch),
                                                   C.byref(pp), C.byref(err))
         self._lib.check(rc, err)

@@ -35,6 +35,11 @@ amg_backend* amg_clone(amg_backend* b, amg_error* err);
 /* Backend.free()  — backend/backend.js:16-19 */
 void amg_free(amg_backend* b);
 
+/* Drops the document but keeps every device / pinned allocation (steady-state serving, benchmarking). */
+int amg_reset(amg_backend* b, amg_error* err);
+/* Pre-sizes the change arena (pinned host mirror + device) so that a bulk replay does not grow it mid-call. */
+int amg_reserve(amg_backend* b, size_t arena_bytes, amg_error* err);
+
 /* Backend.applyChanges(state, changes) — backend/backend.js:27-32 -> BackendDoc.applyChanges, new.js:1797-1879.
  * `bufs[i]` / `lens[i]`: the binary changes (chunk type 1, or 2 = DEFLATE, inflated on the host with zlib as
  * columnar.js:813-823 does with pako). is_local != 0 mirrors the `isLocal` argument used by applyLocalChange
@@ -88,6 +93,7 @@ void amg_buffers_free(amg_buffers* l);
  * edits.kind = (0 insert | 1 remove | 2 update) | 0x100 if the edit starts a new run (edits without the bit
  * continue the previous insert as `multi-insert` / add to the previous remove's count, new.js:747-782) | action << 16.
  * The nested Patch object of @types/automerge/index.d.ts:236-316 is assembled from this by the binding. */
+/* The bytes live in a pinned buffer owned by the backend: valid until the next call on the same backend. */
 const uint8_t* amg_patch_bytes(const amg_patch* p, size_t* len);
 void amg_patch_free(amg_patch* p);
 /* host mirror of the document arena that keyOff / valOff refer to (valid until the next mutating call) */

@@ -34,9 +34,8 @@ def check_trace_parity(gpu_doc, oracle_mod, cfg, n, a):
     pg = g.apply_changes(ch)
     for k in ('maxOp', 'clock', 'deps', 'pendingChanges'):
         assert pg[k] == po[k], k
-    if cfg != 'C4':   # C4: the reference's incremental map patch omits some conflicting values; final state is compared below
-        d = replay.deep_equal(replay.decode(pg), replay.decode(po))
-        assert d is None, d
+    d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+    assert d is None, d
     d = replay.deep_equal(replay.decode(g.get_patch()), replay.decode(orc.get_patch()))
     assert d is None, d
     _dump_equal(g, orc)
