@@ -205,6 +205,7 @@ struct ShaKernel {
   const u8* arena; const u32* chOff; const u32* chLen; u8* hashOut /* [n][32] */; u64* errWord; const u32* Kdev;
   HD void operator()(size_t c) const {
     const u8* p = arena + chOff[c]; const u32 len = chLen[c];
+    if (len > 8 && p[8] == 2 && p[0] == 0x85) { errWord[1] = 1; return; }   // DEFLATEd change: the host inflates and re-stages the batch
     if (len < 10 || p[0] != 0x85 || p[1] != 0x6f || p[2] != 0x4a || p[3] != 0x83) { raise(errWord, KE_MAGIC, c); return; }
 #if defined(__CUDA_ARCH__)
     const u32* K = c_sha.k;

@@ -41,7 +41,7 @@ struct PatchOut {   // flat patch, written straight into the engine's pinned out
   const u8* bytes = nullptr; size_t bytesLen = 0;   // final serialised patch (valid until the next call on the same engine)
 };
 
-struct HostChange { u32 off, len; bool deflated; };
+struct HostChange { u32 off, len; };   // (arena offset, length) of the inflated change
 
 // Pinned host mirror of the arena: grows without zero-filling; H2D copies read straight from it.
 struct HostArena {
@@ -91,7 +91,7 @@ class Engine {
   DBuf<u32> isObjHead, objIdx, objStart, elemVis, elemVisScan, rowEmit, firstVis, state, nItems, itemBase, qIndex, zero, wzero, zscan, wscan, editObjKey;
   DBuf<DomItem> items, items2; DBuf<PropRec> propOut; DBuf<EditRec> editOut, editOut2; DBuf<u64> editElem, editElem2;
   DBuf<u32> seqSlot, actorCnt, actorBaseD, clockD, changeActor, editTime; DBuf<u8> hashTmp; bool batchInOrder = true;
-  DBuf<u32> finalTime, gFailed, memberFinal, opAt, runHead, opGroupHead; DBuf<u64> gBound; DocRows workView{};
+  DBuf<u32> finalTime, gFailed, memberFinal, opAt, runHead, opGroupHead; DBuf<u64> gBound; DocRows workView{}; DBuf<HostChange> chPairs; std::thread mirrorThread;
 
   explicit Engine(int device) {
     ctx.device = device;
@@ -199,7 +199,7 @@ class Engine {
   // ---------------------------------------------------------------- applyChanges
   struct ApplyResult { PatchOut patch; };
 
-  void applyChanges(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out);
+  void applyChanges(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out, bool hostScan = false);
   void getPatch(PatchOut& out);
   void buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows* ops, size_t numOps, const IdTable* idt, const u32* rowOfOpD, const u32* posD,
                   const std::vector<std::string>& actorsNow, PatchOut& out);

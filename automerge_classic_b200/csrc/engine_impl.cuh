@@ -21,7 +21,7 @@ struct PhaseTimer {
 
 inline void parallel_copy(u8* dst, const u8* src, size_t n) {
   if (n < (4u << 20)) { memcpy(dst, src, n); return; }
-  unsigned nt = std::min<unsigned>(4, std::max(1u, std::thread::hardware_concurrency()));
+  unsigned nt = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
   std::vector<std::thread> ts; size_t per = (n + nt - 1) / nt;
   for (unsigned t = 0; t < nt; t++) { size_t a = t * per, b = std::min(n, a + per); if (a < b) ts.emplace_back([=] { memcpy(dst + a, src + a, b - a); }); }
   for (auto& t : ts) t.join();
@@ -60,69 +60,86 @@ inline void Engine::reset() {
   queue.clear(); queueOriginal.clear(); maxOp = 0; rebuildActorTable();
 }
 
-inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out) {
+inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out, bool hostScan) {
   PhaseTimer timer(ctx);
-  // ------------------------------------------------------------ 0. stage the batch in the arena (host mirror + device)
+  // ------------------------------------------------------------ 0. stage the batch in the arena (pinned host mirror + device)
   const size_t arenaLen0 = arenaLen; const size_t hostLen0 = hostArena.size();
-  std::vector<HostChange> batch; std::vector<std::string> batchOriginal;   // original bytes only for deflated changes
-  batch.reserve(n + queue.size());
+  std::vector<HostChange> batch; std::vector<std::string> batchOriginal;   // originals only for deflated changes (else empty vector)
   struct Rollback { Engine* e; size_t len; bool armed = true; ~Rollback() { if (armed) { e->hostArena.resize(len); e->rebuildActorTable(); } } };
-  bool anyDeflated = false, uploaded = false; size_t total = 0;
-  for (size_t i = 0; i < n; i++) {
-    const u8* p = blob ? blob + offsets[i] : bufs[i]; const size_t l = blob ? (size_t)(offsets[i + 1] - offsets[i]) : lens[i];
-    if (l > 8 && p[8] == 2) anyDeflated = true;
-    total += l;
-  }
+  size_t total = 0;
+  if (blob && n > 0) total = offsets[n] - offsets[0]; else for (size_t i = 0; i < n; i++) total += lens[i];
   if ((u64)arenaLen0 + total + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
   Rollback rb{this, hostLen0};
-  size_t cur = arenaLen0;
-  if (!anyDeflated && blob && n > 0) {
+  struct MirrorJoin { Engine* e; ~MirrorJoin() { if (e->mirrorThread.joinable()) e->mirrorThread.join(); } } mirrorJoin{this};   // declared after rb: joins first
+  size_t cur = arenaLen0; bool uploaded = false;
+  const size_t Bq = queue.size(); batch.resize(n + Bq);
+  if (blob && n > 0 && !hostScan) {
+    // bulk path: no per-change host work beyond one (offset, length) pair; DEFLATEd changes are detected on the device
     const size_t base = offsets[0]; const size_t tot = offsets[n] - base;
     hostArena.resize(cur + tot); arena.ensure(ctx, cur + tot + 64, arenaLen0);
-    const size_t kChunk = 16u << 20;   // copy into the pinned mirror and upload chunk by chunk (H2D overlaps the next host copy)
-    for (size_t o = 0; o < tot; o += kChunk) {
-      const size_t m = std::min(kChunk, tot - o);
-      parallel_copy(hostArena.data() + cur + o, blob + base + o, m);
-      h2d(ctx, arena.p + cur + o, hostArena.data() + cur + o, m);
+    bool callerPinned = false;
+#ifndef AMG_EMU
+    { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, blob) == cudaSuccess && at.type == cudaMemoryTypeHost) callerPinned = true; else cudaGetLastError(); }
+#endif
+    if (callerPinned) {
+      // the caller's buffer is pinned: DMA straight from it, and fill the host mirror on a CPU thread while the GPU works
+      h2d(ctx, arena.p + cur, blob + base, tot);
+      u8* dst = hostArena.data() + cur; const u8* src = blob + base;
+      mirrorThread = std::thread([dst, src, tot] { parallel_copy(dst, src, tot); });
+    } else {
+      const size_t kChunk = 32u << 20;   // copy into the pinned mirror and upload chunk by chunk (H2D overlaps the next host copy)
+      for (size_t o = 0; o < tot; o += kChunk) {
+        const size_t m = std::min(kChunk, tot - o);
+        parallel_copy(hostArena.data() + cur + o, blob + base + o, m);
+        h2d(ctx, arena.p + cur + o, hostArena.data() + cur + o, m);
+      }
     }
-    uploaded = true;
-    for (size_t i = 0; i < n; i++) batch.push_back(HostChange{(u32)(cur + offsets[i] - base), (u32)(offsets[i + 1] - offsets[i]), false});
-    batchOriginal.resize(n); cur += tot;
+    const u32 shift = (u32)(cur - base);
+    for (size_t i = 0; i < n; i++) { batch[i].off = (u32)offsets[i] + shift; batch[i].len = (u32)(offsets[i + 1] - offsets[i]); }
+    uploaded = true; cur += tot;
   } else {
+    bool anyDeflated = false;
     for (size_t i = 0; i < n; i++) {
       const u8* p = blob ? blob + offsets[i] : bufs[i]; const size_t l = blob ? (size_t)(offsets[i + 1] - offsets[i]) : lens[i];
-      if (l > 8 && p[8] == 2) {
+      if (l > 8 && p[8] == 2) {   // reference columnar.js:742
         std::string inflated = inflateChange(p, l);
         if ((u64)cur + inflated.size() + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
         hostArena.append(inflated.data(), inflated.size());
-        batch.push_back(HostChange{(u32)cur, (u32)inflated.size(), true}); batchOriginal.emplace_back((const char*)p, l); cur += inflated.size();
-      } else {
-        hostArena.append(p, l);
-        batch.push_back(HostChange{(u32)cur, (u32)l, false}); batchOriginal.emplace_back(); cur += l;
-      }
+        if (!anyDeflated) { anyDeflated = true; batchOriginal.resize(n + Bq); }
+        batch[i] = HostChange{(u32)cur, (u32)inflated.size()}; batchOriginal[i].assign((const char*)p, l); cur += inflated.size();
+      } else { hostArena.append(p, l); batch[i] = HostChange{(u32)cur, (u32)l}; cur += l; }
     }
   }
-  const size_t numFresh = batch.size();
-  for (size_t i = 0; i < queue.size(); i++) { batch.push_back(queue[i]); batchOriginal.push_back(queueOriginal[i]); }
+  if (Bq > 0) {
+    if (batchOriginal.empty()) batchOriginal.resize(n + Bq);
+    for (size_t i = 0; i < Bq; i++) { batch[n + i] = queue[i]; batchOriginal[n + i] = queueOriginal[i]; }
+  }
   const size_t B = batch.size();
   if (B == 0) { rb.armed = false; fillPatchHeader(out); finishPatch(out); return; }
   arena.ensure(ctx, cur + 64, arenaLen0);
   if (!uploaded) h2d(ctx, arena.p + arenaLen0, hostArena.data() + arenaLen0, cur - arenaLen0);
   dev_memset(ctx, arena.p + cur, 0, 64);
-  {
-    std::vector<u32> off(B), len(B); for (size_t b = 0; b < B; b++) { off[b] = batch[b].off; len[b] = batch[b].len; }
-    chOff.ensure(ctx, B); chLen.ensure(ctx, B); h2d(ctx, chOff.p, off.data(), B * 4); h2d(ctx, chLen.p, len.data(), B * 4); sync(ctx);
-  }
+  chPairs.ensure(ctx, B); chOff.ensure(ctx, B); chLen.ensure(ctx, B);
+  h2d(ctx, chPairs.p, batch.data(), B * sizeof(HostChange));
+  foreach(ctx, B, SplitPairsKernel{chPairs.p, chOff.p, chLen.p});
   timer.mark();
   // ------------------------------------------------------------ 1. hash + header parse
-  dev_memset(ctx, errWord.p, 0, 8);
+  dev_memset(ctx, errWord.p, 0, 16);
   hashes.ensure(ctx, (numApplied + B) * 32 + 64, numApplied * 32);
   foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr});
   timer.mark();
   meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
   nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
   foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
-  checkErr(actorIds);
+  {
+    u64 ew[2]; d2h(ctx, ew, errWord.p, 16); sync(ctx);
+    if (ew[1]) {   // the batch contains DEFLATEd changes: redo the staging with host-side inflate (columnar.js:813-823)
+      if (mirrorThread.joinable()) mirrorThread.join();
+      rb.armed = false; hostArena.resize(hostLen0);
+      return applyChanges(bufs, lens, n, blob, offsets, isLocal, wantPatch, out, true);
+    }
+    if (ew[0]) throwKernelError(ew[0], actorIds);
+  }
   // ------------------------------------------------------------ 2. causal gate
   depBase.ensure(ctx, B + 1); scan_exclusive(ctx, scanTmp, nDeps.p, depBase.p, B);
   const u32 totalDeps = readU32(depBase.p + B);
@@ -160,7 +177,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   if (numNew < B) for (size_t b = 0; b < B; b++) {
     const u32 pr = primaryH[b];
     const bool hashApplied = pr < numApplied || appliedH[pr - numApplied];
-    if (!hashApplied) { newQueue.push_back(batch[b]); newQueueOriginal.push_back(batchOriginal[b]); }
+    if (!hashApplied) { newQueue.push_back(batch[b]); newQueueOriginal.push_back(batchOriginal.empty() ? std::string() : batchOriginal[b]); }
   }
   timer.mark();
   std::vector<std::string> actorsNow = actorIds; std::vector<u64> clockNow = clock; std::vector<u32> actorCntH; std::vector<std::pair<u32, u32>> actorRepNow = actorRep;
@@ -183,6 +200,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       std::vector<u32> slotsH(fresh); d2h(ctx, slotsH.data(), newSlots.p, fresh * 4); sync(ctx);
       std::vector<ActorSlot> recs(fresh); for (u32 i = 0; i < fresh; i++) d2h(ctx, &recs[i], actorSlots.p + slotsH[i], sizeof(ActorSlot));
       sync(ctx);
+      if (mirrorThread.joinable()) mirrorThread.join();   // actor bytes are read from the host mirror
       std::vector<u32> order(fresh); for (u32 i = 0; i < fresh; i++) order[i] = i;
       std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return recs[a].first < recs[b].first; });
       std::vector<u32> ids(fresh), nums(fresh);
@@ -399,12 +417,15 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       foreach(ctx, B, HashGatherKernel{hashes.p + numApplied * 32, applied.p, appRank.p, tmp.p});
       d2d(ctx, hashes.p + numApplied * 32, tmp.p, numNew * 32);
     }
-    std::vector<u32> byRank(numNew);
-    if (appliedH.empty()) for (size_t b = 0; b < B; b++) byRank[b] = (u32)b; else for (size_t b = 0; b < B; b++) if (appliedH[b]) byRank[appRankH[b]] = (u32)b;
-    for (size_t k = 0; k < numNew; k++) {
-      const u32 b = byRank[k];
-      if (batch[b].deflated) deflatedOriginal[(u32)changes.size()] = batchOriginal[b];
-      changes.push_back(batch[b]);
+    if (appliedH.empty() && batchOriginal.empty()) changes.insert(changes.end(), batch.begin(), batch.end());   // all applied, in order
+    else {
+      std::vector<u32> byRank(numNew);
+      if (appliedH.empty()) for (size_t b = 0; b < B; b++) byRank[b] = (u32)b; else for (size_t b = 0; b < B; b++) if (appliedH[b]) byRank[appRankH[b]] = (u32)b;
+      for (size_t k = 0; k < numNew; k++) {
+        const u32 b = byRank[k];
+        if (!batchOriginal.empty() && !batchOriginal[b].empty()) deflatedOriginal[(u32)changes.size()] = batchOriginal[b];
+        changes.push_back(batch[b]);
+      }
     }
     doc.swap(sorted); numRows = N;
     std::swap(succOff.p, newSuccOff.p); std::swap(succOff.cap, newSuccOff.cap); std::swap(succ.p, newSucc.p); std::swap(succ.cap, newSucc.cap); numSucc = numPairs;
@@ -413,15 +434,15 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     rebuildActorTable();   // slots of actors registered in this call become permanent (first = 0)
   }
   arenaLen = cur; queue = newQueue; queueOriginal = newQueueOriginal; rb.armed = false;
-  (void)numFresh;
   sync(ctx);
   timer.mark();
   fillPatchHeader(out);
   if (isLocal && n == 1) {   // new.js:1874-1877
     std::vector<ChangeMeta> m0(1); d2h(ctx, m0.data(), meta.p, sizeof(ChangeMeta)); sync(ctx);
+    if (mirrorThread.joinable()) mirrorThread.join();
     out.hasActorSeq = true; out.actor.assign((const char*)hostArena.data() + m0[0].actorOff, m0[0].actorLen); out.seq = m0[0].seq;
   }
-  lastB = B; lastM = M; lastP = P; lastBytes = 0; for (auto& c : batch) lastBytes += c.len;
+  lastB = B; lastM = M; lastP = P; lastBytes = cur - arenaLen0; for (auto& c : queue) lastBytes += 0 * c.len;
   finishPatch(out);
   timer.collect(lastPhaseMs, 8);
 }

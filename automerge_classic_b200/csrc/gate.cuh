@@ -98,8 +98,9 @@ struct ActorSlot { u64 hash; u64 first; /* (appRank << 32 | batch change), min w
 HD u32 actor_find_or_insert(ActorSlot* slots, u64 mask, u64 h) {
   u64 s = mix64(h) & mask;
   while (true) {
-    u64 cur = atomic_cas(&slots[s].hash, (u64)0, h);
-    if (cur == 0 || cur == h) return (u32)s;
+    u64 cur = slots[s].hash;   // read first: after the first few inserts every lookup hits without an atomic
+    if (cur == h) return (u32)s;
+    if (cur == 0) { cur = atomic_cas(&slots[s].hash, (u64)0, h); if (cur == 0 || cur == h) return (u32)s; }
     s = (s + 1) & mask;
   }
 }
@@ -114,7 +115,8 @@ struct ActorInternKernel {
     if (!applied[b]) { authorSlot[b] = EMPTY32; return; }
     const u64 h = fnv1a64(arena + meta[b].actorOff, meta[b].actorLen);
     const u32 s = actor_find_or_insert(slots, mask, h);
-    atomic_min(&slots[s].first, ((u64)appRank[b] << 32) | (u64)b);
+    const u64 cand = ((u64)appRank[b] << 32) | (u64)b;
+    if (cand < slots[s].first) atomic_min(&slots[s].first, cand);
     authorSlot[b] = s;
   }
 };

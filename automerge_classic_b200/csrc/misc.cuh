@@ -1,6 +1,7 @@
 // amgpu — small glue kernels of the pipeline (flags, compaction, sequence-number check, heads).
 #pragma once
 #include "patch.cuh"
+namespace amg { struct HostChange; }
 
 namespace amg {
 
@@ -10,7 +11,7 @@ struct AppliedFlagKernel {
   HD void operator()(size_t b) const {
     const bool a = primary[b] == (u32)(numApplied + b) && pass[b] < PASS_INF;
     applied[b] = a ? 1 : 0; applied32[b] = a ? 1u : 0u;
-    if (a) { atomic_add(stats, 1u); atomic_max(stats + 1, pass[b]); }
+    if (a) { atomic_add(stats, 1u); if (pass[b] > stats[1]) atomic_max(stats + 1, pass[b]); }
   }
 };
 struct PassKeyKernel { const u32* pass; const u8* applied; u64* key; u32* val; HD void operator()(size_t b) const { key[b] = applied[b] ? pass[b] : 0xffffffffu; val[b] = (u32)b; } };
@@ -19,7 +20,7 @@ struct MaskedCountKernel { const u32* v; const u8* applied; u32* out; HD void op
 // general (multi-pass) order: ops of change b start at time 1 + (ops of changes applied before b)
 struct OpsInOrderKernel { const u32* nOps; const u8* applied; const u32* appRank; u32* tmp; HD void operator()(size_t b) const { if (applied[b]) tmp[appRank[b]] = nOps[b]; } };
 struct TimeBaseKernel { const u32* scanned; const u8* applied; const u32* appRank; const u32* opBase; int inOrder; u32* timeBase; HD void operator()(size_t b) const { timeBase[b] = applied[b] ? (inOrder ? opBase[b] : scanned[appRank[b]]) + 1 : 0; } };
-struct MaxOpKernel { const ChangeMeta* meta; const u8* applied; u64* maxOp; HD void operator()(size_t b) const { if (applied[b] && meta[b].nOps > 0) atomic_max(maxOp, meta[b].startOp + meta[b].nOps - 1); } };
+struct MaxOpKernel { const ChangeMeta* meta; const u8* applied; u64* maxOp; HD void operator()(size_t b) const { if (applied[b] && meta[b].nOps > 0) { const u64 v = meta[b].startOp + meta[b].nOps - 1; if (v > *maxOp) atomic_max(maxOp, v); } } };   // read first: a monotone max rarely needs the atomic
 
 // new actors: the applied change with the smallest application rank per fresh slot registers the representative bytes
 struct NewActorKernel {
@@ -58,6 +59,7 @@ struct MarkDepsKernel { const u8* applied; const ChangeMeta* meta; const u32* de
 struct HeadFlag2Kernel { const u8* applied; const u32* isDep; size_t numApplied; u32* flag; HD void operator()(size_t b) const { flag[b] = (applied[b] && !isDep[numApplied + b]) ? 1u : 0u; } };
 struct CompactKernel { const u32* flag; const u32* slot; u32* out; HD void operator()(size_t i) const { if (flag[i]) out[slot[i]] = (u32)i; } };
 struct HashGatherKernel { const u8* src; const u8* applied; const u32* appRank; u8* dst; HD void operator()(size_t b) const { if (!applied[b]) return; const u64* s = reinterpret_cast<const u64*>(src + b * 32); u64* d = reinterpret_cast<u64*>(dst + (size_t)appRank[b] * 32); d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; } };
+struct SplitPairsKernel { const HostChange* pairs; u32* off; u32* len; HD void operator()(size_t b) const { off[b] = pairs[b].off; len[b] = pairs[b].len; } };
 struct KeySlotInitKernel { KeySlot* s; HD void operator()(size_t i) const { s[i].hash = 0; s[i].rep = 0xffffffffu; s[i].rank = 0; } };
 struct InsertFlagKernel { DocRows w; u32* flag; HD void operator()(size_t r) const { flag[r] = (w.keyStrLen[r] == NULL32 && (w.flags[r] & F_INSERT)) ? 1u : 0u; } };
 struct GatherU32Kernel { const u32* src; const u32* idx; u32* out; HD void operator()(size_t i) const { out[i] = src[idx[i]]; } };
