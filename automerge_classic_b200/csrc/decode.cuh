@@ -20,6 +20,7 @@ namespace amg {
 
 static const u32 NULL32 = 0xffffffffu;
 static const int NCOLS = 14;   // known change columns, in this order:
+static const u32 SMALL_CHANGE_OPS = 16;   // changes with at most this many ops are decoded by one thread (DecodeSmallKernel)
 enum ColIx { CX_OBJ_ACTOR = 0, CX_OBJ_CTR, CX_KEY_ACTOR, CX_KEY_CTR, CX_KEY_STR, CX_INSERT, CX_ACTION, CX_VAL_LEN, CX_VAL_RAW,
              CX_CHLD_ACTOR, CX_CHLD_CTR, CX_PRED_NUM, CX_PRED_ACTOR, CX_PRED_CTR };
 HD int col_index_of(u32 columnId) {
@@ -60,6 +61,7 @@ struct ChangeMeta {
   u32 otherOff, nOther;    // other-actor table entries (len-prefixed), after the count
   u32 extraOff, extraLen;  // trailing bytes
   u32 nOps, nPreds;
+  u32 dirOff, dataOff;     // column directory entries / first column's data
   u64 seq, startOp; long long time;
 };
 
@@ -184,8 +186,8 @@ HD u32 load_be32(const u8* p) {
 }
 HD void sha256_compress(u32* h, u32* w, const u32* K) {
   u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
-#pragma unroll 16
-  for (int i = 0; i < 64; i++) {
+#pragma unroll 64
+  for (int i = 0; i < 64; i++) {   // fully unrolled: every w[] index is static, the schedule stays in registers
     u32 wi;
     if (i < 16) wi = w[i];
     else {
@@ -225,6 +227,7 @@ struct ShaKernel {
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       u32 v = 0;
+#pragma unroll
       for (int b = 0; b < 4; b++) {
         const u32 ix = 4 * i + b; u32 byte = 0;
         if (ix < rem) byte = m[done + ix]; else if (ix == rem) byte = 0x80;
@@ -253,7 +256,6 @@ struct ParseKernel {
   HD void operator()(size_t c) const {
     const u32 off = chOff[c], len = chLen[c];
     ChangeMeta m; memset(&m, 0, sizeof(m)); m.off = off; m.len = len;
-    for (int k = 0; k < NCOLS; k++) { colOff[(size_t)k * numChanges + c] = 0; colLen[(size_t)k * numChanges + c] = 0; }
     nOpsOut[c] = 0; nPredsOut[c] = 0; nDepsOut[c] = 0; nActorsOut[c] = 1;
     ByteReader r(arena, off + 8, off + len);
     const u32 chunkType = r.done() ? 0xff : arena[r.pos]; r.pos++;
@@ -273,27 +275,23 @@ struct ParseKernel {
     const u64 nCols = r.uleb();
     if (r.err) { raise(errWord, r.err, c); meta[c] = m; return; }
     const u32 dirPos = r.pos; long long lastId = -1; u64 total = 0;
+    u32 actOff = 0, actLen = 0, pnOff = 0, pnLen = 0;   // the two columns needed for counting, relative to the data start
     for (u64 i = 0; i < nCols && !r.err; i++) {
       const u64 id = r.uleb(), l = r.uleb();
       if (lastId >= 0 && ((u32)id & ~8u) <= ((u32)lastId & ~8u)) { raise(errWord, KE_COL_ORDER, c); meta[c] = m; return; }
       if (id & 8) { raise(errWord, KE_COL_DEFLATE, c); meta[c] = m; return; }
+      if (id == 0x42) { actOff = (u32)total; actLen = (u32)l; } else if (id == 0x70) { pnOff = (u32)total; pnLen = (u32)l; }
       lastId = (long long)id; total += l;
     }
     if (r.err) { raise(errWord, r.err, c); meta[c] = m; return; }
-    u32 dataPos = r.pos;
+    const u32 dataPos = r.pos;
     if ((u64)dataPos + total > (u64)off + len) { raise(errWord, KE_TRUNCATED, c); meta[c] = m; return; }
-    ByteReader d(arena, dirPos, dataPos);
-    for (u64 i = 0; i < nCols; i++) {
-      const u64 id = d.uleb(), l = d.uleb();
-      const int ix = col_index_of((u32)id);
-      if (ix >= 0) { colOff[(size_t)ix * numChanges + c] = dataPos; colLen[(size_t)ix * numChanges + c] = (u32)l; }
-      dataPos += (u32)l;
-    }
-    m.extraOff = dataPos; m.extraLen = off + len - dataPos;
+    m.dirOff = dirPos; m.dataOff = dataPos;
+    m.extraOff = dataPos + (u32)total; m.extraLen = off + len - m.extraOff;
     // count ops (values of the action column) and preds (sum of the predNum column)
     u32 nOps = 0; u64 nPreds = 0; u32 kerr = 0;
     {
-      RleReader a(arena, colOff[(size_t)CX_ACTION * numChanges + c], colOff[(size_t)CX_ACTION * numChanges + c] + colLen[(size_t)CX_ACTION * numChanges + c], 0);
+      RleReader a(arena, dataPos + actOff, dataPos + actOff + actLen, 0);
       // record-level count: no need to touch every value of a repetition / null run
       while (!a.done() && !a.r.err) {
         long long n; u32 o, l; a.next(n, o, l);
@@ -304,7 +302,7 @@ struct ParseKernel {
       kerr = a.r.err;
     }
     if (!kerr) {
-      RleReader pn(arena, colOff[(size_t)CX_PRED_NUM * numChanges + c], colOff[(size_t)CX_PRED_NUM * numChanges + c] + colLen[(size_t)CX_PRED_NUM * numChanges + c], 0);
+      RleReader pn(arena, dataPos + pnOff, dataPos + pnOff + pnLen, 0);
       u32 seen = 0;
       while (!pn.done() && !pn.r.err && seen < nOps) {
         long long n = 0; u32 o, l; const bool nn = pn.next(n, o, l);
@@ -318,97 +316,158 @@ struct ParseKernel {
     if (kerr) { raise(errWord, kerr, c); meta[c] = m; return; }
     if (nPreds > 0x7fffffffULL) { raise(errWord, KE_TOO_LARGE, c); meta[c] = m; return; }
     m.nOps = nOps; m.nPreds = (u32)nPreds;
+    if (nOps > SMALL_CHANGE_OPS) {   // large change: publish the directory for the (column, change)-parallel kernel
+      ByteReader d(arena, dirPos, dataPos); u32 pos = dataPos;
+      for (int k = 0; k < NCOLS; k++) { colOff[(size_t)k * numChanges + c] = 0; colLen[(size_t)k * numChanges + c] = 0; }
+      for (u64 i = 0; i < nCols; i++) {
+        const u64 id = d.uleb(), l = d.uleb(); const int ix = col_index_of((u32)id);
+        if (ix >= 0) { colOff[(size_t)ix * numChanges + c] = pos; colLen[(size_t)ix * numChanges + c] = (u32)l; }
+        pos += (u32)l;
+      }
+    }
     meta[c] = m; nOpsOut[c] = nOps; nPredsOut[c] = (u32)nPreds; nDepsOut[c] = m.nDeps; nActorsOut[c] = 1 + m.nOther;
   }
 };
 
-// ---------------------------------------------------------------- column expansion, one thread per (column, change)
+// ---------------------------------------------------------------- column expansion
 struct RawRows {   // SoA, one entry per op of the batch (raw change-local values; NULL32 = null)
   u32 *objActor, *objCtr, *keyActor, *keyCtr, *keyStrOff, *keyStrLen, *insert, *action, *valLen, *valOff, *predNum, *predOff;
   u32 *predActor, *predCtr;   // one entry per pred of the batch
 };
 
-struct DecodeColumnKernel {
-  const u8* arena; size_t numChanges; const ChangeMeta* meta; const u32* colOff; const u32* colLen;
-  const u32* opBase /* exclusive scan of nOps */; const u32* predBase; const u8* applied /* per change: decode only if 1 */;
-  RawRows rows; u64* errWord;
-  HD void operator()(size_t t) const {
-    const int col = (int)(t / numChanges); const size_t c = t % numChanges;
-    if (!applied[c]) return;
-    const u32 nOps = meta[c].nOps; if (nOps == 0) return;
-    const u32 base = opBase[c], cOff = colOff[(size_t)col * numChanges + c], cEnd = cOff + colLen[(size_t)col * numChanges + c];
-    u32 kerr = 0;
-    switch (col) {
-      case CX_OBJ_ACTOR: case CX_OBJ_CTR: case CX_KEY_ACTOR: case CX_ACTION: case CX_VAL_LEN: case CX_PRED_NUM: {
-        u32* out = col == CX_OBJ_ACTOR ? rows.objActor : col == CX_OBJ_CTR ? rows.objCtr : col == CX_KEY_ACTOR ? rows.keyActor
-                 : col == CX_ACTION ? rows.action : col == CX_VAL_LEN ? rows.valLen : rows.predNum;
-        RleReader r(arena, cOff, cEnd, 0);
-        u32 running = 0;   // VAL_LEN: byte offset into valRaw; PRED_NUM: pred offset
-        const u32 rawBase = col == CX_VAL_LEN ? colOff[(size_t)CX_VAL_RAW * numChanges + c] : (col == CX_PRED_NUM ? predBase[c] : 0);
-        for (u32 i = 0; i < nOps; i++) {
-          long long n = 0; u32 o, l; const bool nn = r.next(n, o, l);
-          if (nn && (u64)n > 0xfffffffeULL) kerr = KE_TOO_LARGE;
-          out[base + i] = nn ? (u32)n : NULL32;
-          if (col == CX_VAL_LEN) { rows.valOff[base + i] = rawBase + running; running += nn ? (u32)((u64)n >> 4) : 0; }
-          if (col == CX_PRED_NUM) { rows.predOff[base + i] = rawBase + running; running += nn ? (u32)n : 0; if (!nn) out[base + i] = 0; }
-        }
-        if (col == CX_VAL_LEN && running > colLen[(size_t)CX_VAL_RAW * numChanges + c]) kerr = KE_TRUNCATED;
-        if (!kerr) kerr = r.r.err;
-        break;
+// Expands one column of one change into the raw rows. Returns a KErr code (0 = ok).
+HD u32 decode_one_column(const u8* arena, int col, u32 nOps, u32 base, u32 cOff, u32 cEnd, u32 valRawOff, u32 valRawLen, u32 predBase, u32 nPreds, const RawRows& rows) {
+  u32 kerr = 0;
+  switch (col) {
+    case CX_OBJ_ACTOR: case CX_OBJ_CTR: case CX_KEY_ACTOR: case CX_ACTION: case CX_VAL_LEN: case CX_PRED_NUM: {
+      u32* out = col == CX_OBJ_ACTOR ? rows.objActor : col == CX_OBJ_CTR ? rows.objCtr : col == CX_KEY_ACTOR ? rows.keyActor
+               : col == CX_ACTION ? rows.action : col == CX_VAL_LEN ? rows.valLen : rows.predNum;
+      RleReader r(arena, cOff, cEnd, 0);
+      u32 running = 0;   // VAL_LEN: byte offset into valRaw; PRED_NUM: pred offset
+      const u32 rawBase = col == CX_VAL_LEN ? valRawOff : (col == CX_PRED_NUM ? predBase : 0);
+      for (u32 i = 0; i < nOps; i++) {
+        long long n = 0; u32 o, l; const bool nn = r.next(n, o, l);
+        if (nn && (u64)n > 0xfffffffeULL) kerr = KE_TOO_LARGE;
+        out[base + i] = nn ? (u32)n : NULL32;
+        if (col == CX_VAL_LEN) { rows.valOff[base + i] = rawBase + running; running += nn ? (u32)((u64)n >> 4) : 0; }
+        if (col == CX_PRED_NUM) { rows.predOff[base + i] = rawBase + running; running += nn ? (u32)n : 0; if (!nn) out[base + i] = 0; }
       }
-      case CX_KEY_CTR: {
-        RleReader r(arena, cOff, cEnd, 1); long long acc = 0;
-        for (u32 i = 0; i < nOps; i++) {
-          long long n = 0; u32 o, l; const bool nn = r.next(n, o, l);
-          if (nn) { acc += n; if (acc < 0 || acc > 0xfffffffeLL) kerr = KE_TOO_LARGE; }
-          rows.keyCtr[base + i] = nn ? (u32)acc : NULL32;
-        }
-        if (!kerr) kerr = r.r.err;
-        break;
-      }
-      case CX_KEY_STR: {
-        RleReader r(arena, cOff, cEnd, 2);
-        for (u32 i = 0; i < nOps; i++) {
-          long long n; u32 o = 0, l = 0; const bool nn = r.next(n, o, l);
-          rows.keyStrOff[base + i] = nn ? o : 0; rows.keyStrLen[base + i] = nn ? l : NULL32;
-        }
-        kerr = r.r.err;
-        break;
-      }
-      case CX_INSERT: {   // BooleanDecoder encoding.js:1141-1207
-        ByteReader r(arena, cOff, cEnd); bool val = true, first = true; u64 count = 0;
-        for (u32 i = 0; i < nOps; i++) {
-          bool v = false;
-          if (!(count == 0 && r.done())) {
-            while (count == 0) {
-              count = r.uleb(); val = !val;
-              if (r.err) break;
-              if (count == 0 && !first) { kerr = KE_BOOL_ZERO; break; }
-              first = false;
-            }
-            if (r.err || kerr) break;
-            count--; v = val;
-          }
-          rows.insert[base + i] = v ? 1u : 0u;
-        }
-        if (!kerr) kerr = r.err;
-        break;
-      }
-      case CX_PRED_ACTOR: case CX_PRED_CTR: {
-        const u32 nPreds = meta[c].nPreds, pb = predBase[c];
-        RleReader r(arena, cOff, cEnd, col == CX_PRED_CTR ? 1 : 0); long long acc = 0;
-        for (u32 j = 0; j < nPreds; j++) {
-          long long n = 0; u32 o, l; const bool nn = r.next(n, o, l);
-          if (col == CX_PRED_CTR) { if (nn) { acc += n; if (acc < 0 || acc > 0xfffffffeLL) kerr = KE_TOO_LARGE; } rows.predCtr[pb + j] = nn ? (u32)acc : NULL32; }
-          else { if (nn && (u64)n > 0xfffffffeULL) kerr = KE_TOO_LARGE; rows.predActor[pb + j] = nn ? (u32)n : NULL32; }
-        }
-        if (!kerr) kerr = r.r.err;
-        break;
-      }
-      default: break;   // VAL_RAW is referenced in place; chld* columns are not needed by the op set
+      if (col == CX_VAL_LEN && running > valRawLen) kerr = KE_TRUNCATED;
+      if (!kerr) kerr = r.r.err;
+      break;
     }
+    case CX_KEY_CTR: {
+      RleReader r(arena, cOff, cEnd, 1); long long acc = 0;
+      for (u32 i = 0; i < nOps; i++) {
+        long long n = 0; u32 o, l; const bool nn = r.next(n, o, l);
+        if (nn) { acc += n; if (acc < 0 || acc > 0xfffffffeLL) kerr = KE_TOO_LARGE; }
+        rows.keyCtr[base + i] = nn ? (u32)acc : NULL32;
+      }
+      if (!kerr) kerr = r.r.err;
+      break;
+    }
+    case CX_KEY_STR: {
+      RleReader r(arena, cOff, cEnd, 2);
+      for (u32 i = 0; i < nOps; i++) {
+        long long n; u32 o = 0, l = 0; const bool nn = r.next(n, o, l);
+        rows.keyStrOff[base + i] = nn ? o : 0; rows.keyStrLen[base + i] = nn ? l : NULL32;
+      }
+      kerr = r.r.err;
+      break;
+    }
+    case CX_INSERT: {   // BooleanDecoder encoding.js:1141-1207
+      ByteReader r(arena, cOff, cEnd); bool val = true, first = true; u64 count = 0;
+      for (u32 i = 0; i < nOps; i++) {
+        bool v = false;
+        if (!(count == 0 && r.done())) {
+          while (count == 0) {
+            count = r.uleb(); val = !val;
+            if (r.err) break;
+            if (count == 0 && !first) { kerr = KE_BOOL_ZERO; break; }
+            first = false;
+          }
+          if (r.err || kerr) break;
+          count--; v = val;
+        }
+        rows.insert[base + i] = v ? 1u : 0u;
+      }
+      if (!kerr) kerr = r.err;
+      break;
+    }
+    case CX_PRED_ACTOR: case CX_PRED_CTR: {
+      RleReader r(arena, cOff, cEnd, col == CX_PRED_CTR ? 1 : 0); long long acc = 0;
+      for (u32 j = 0; j < nPreds; j++) {
+        long long n = 0; u32 o, l; const bool nn = r.next(n, o, l);
+        if (col == CX_PRED_CTR) { if (nn) { acc += n; if (acc < 0 || acc > 0xfffffffeLL) kerr = KE_TOO_LARGE; } rows.predCtr[predBase + j] = nn ? (u32)acc : NULL32; }
+        else { if (nn && (u64)n > 0xfffffffeULL) kerr = KE_TOO_LARGE; rows.predActor[predBase + j] = nn ? (u32)n : NULL32; }
+      }
+      if (!kerr) kerr = r.r.err;
+      break;
+    }
+    default: break;   // VAL_RAW is referenced in place; chld* columns are not needed by the op set
+  }
+  return kerr;
+}
+// default (column absent) values of the rows of one change
+HD void fill_absent_column(int col, u32 nOps, u32 base, u32 predBase, u32 nPreds, const RawRows& rows) {
+  u32* out = nullptr; u32 v = NULL32;
+  switch (col) {
+    case CX_OBJ_ACTOR: out = rows.objActor; break; case CX_OBJ_CTR: out = rows.objCtr; break; case CX_KEY_ACTOR: out = rows.keyActor; break;
+    case CX_KEY_CTR: out = rows.keyCtr; break; case CX_ACTION: out = rows.action; break; case CX_VAL_LEN: out = rows.valLen; break;
+    case CX_KEY_STR: for (u32 i = 0; i < nOps; i++) { rows.keyStrOff[base + i] = 0; rows.keyStrLen[base + i] = NULL32; } return;
+    case CX_INSERT: out = rows.insert; v = 0; break;
+    case CX_PRED_NUM: for (u32 i = 0; i < nOps; i++) { rows.predNum[base + i] = 0; rows.predOff[base + i] = predBase; } return;
+    case CX_PRED_ACTOR: for (u32 j = 0; j < nPreds; j++) rows.predActor[predBase + j] = NULL32; return;
+    case CX_PRED_CTR: for (u32 j = 0; j < nPreds; j++) rows.predCtr[predBase + j] = NULL32; return;
+    default: return;
+  }
+  for (u32 i = 0; i < nOps; i++) out[base + i] = v;
+  if (col == CX_VAL_LEN) for (u32 i = 0; i < nOps; i++) rows.valOff[base + i] = 0;
+}
+
+// Small changes (<= SMALL_CHANGE_OPS ops): one thread per change walks the column directory and expands every
+// column of its few ops; consecutive threads write consecutive rows (coalesced). No directory round trip through HBM.
+struct DecodeSmallKernel {
+  const u8* arena; const ChangeMeta* meta; const u32* opBase; const u32* predBase; const u8* applied; RawRows rows; u64* errWord;
+  HD void operator()(size_t c) const {
+    if (!applied[c]) return;
+    const u32 nOps = meta[c].nOps; if (nOps == 0 || nOps > SMALL_CHANGE_OPS) return;
+    const u32 base = opBase[c], pb = predBase[c], nPreds = meta[c].nPreds;
+    ByteReader d(arena, meta[c].dirOff, meta[c].dataOff); u32 pos = meta[c].dataOff; u32 seen = 0, kerr = 0;
+    while (!d.done()) {
+      const u32 id = (u32)d.uleb(), l = (u32)d.uleb(); const int ix = col_index_of(id);
+      if (ix >= 0 && ix != CX_VAL_RAW && ix != CX_CHLD_ACTOR && ix != CX_CHLD_CTR) {
+        u32 rawOff = 0, rawLen = 0;
+        if (ix == CX_VAL_LEN) {   // VALUE_RAW (0x57) directly follows VALUE_LEN (0x56) in the directory when present
+          ByteReader peek = d; if (!peek.done()) { const u32 nid = (u32)peek.uleb(), nl = (u32)peek.uleb(); if (nid == 0x57) { rawOff = pos + l; rawLen = nl; } }
+        }
+        const u32 e = decode_one_column(arena, ix, nOps, base, pos, pos + l, rawOff, rawLen, pb, nPreds, rows);
+        if (e && !kerr) kerr = e;
+        seen |= 1u << ix;
+      }
+      pos += l;
+    }
+    for (int k = 0; k < NCOLS; k++) if (!(seen & (1u << k))) fill_absent_column(k, nOps, base, pb, nPreds, rows);
     if (kerr) raise(errWord, kerr, c);
   }
 };
+
+// Large changes: one thread per (column, large change); `large` lists the change indices
+struct DecodeColumnKernel {
+  const u8* arena; size_t numChanges; const u32* large; size_t numLarge; const ChangeMeta* meta; const u32* colOff; const u32* colLen;
+  const u32* opBase /* exclusive scan of nOps */; const u32* predBase; const u8* applied /* per change: decode only if 1 */;
+  RawRows rows; u64* errWord;
+  HD void operator()(size_t t) const {
+    const int col = (int)(t / numLarge); const size_t c = large[t % numLarge];
+    if (!applied[c]) return;
+    const u32 nOps = meta[c].nOps; if (nOps == 0) return;
+    const u32 cOff = colOff[(size_t)col * numChanges + c], cLen = colLen[(size_t)col * numChanges + c];
+    if (cLen == 0) { fill_absent_column(col, nOps, opBase[c], predBase[c], meta[c].nPreds, rows); return; }
+    const u32 e = decode_one_column(arena, col, nOps, opBase[c], cOff, cOff + cLen, colOff[(size_t)CX_VAL_RAW * numChanges + c], colLen[(size_t)CX_VAL_RAW * numChanges + c],
+                                    predBase[c], meta[c].nPreds, rows);
+    if (e) raise(errWord, e, c);
+  }
+};
+struct LargeFlagKernel { const ChangeMeta* meta; const u8* applied; u32* flag; HD void operator()(size_t c) const { flag[c] = (applied[c] && meta[c].nOps > SMALL_CHANGE_OPS) ? 1u : 0u; } };
 
 }  // namespace amg

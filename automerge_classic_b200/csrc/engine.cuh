@@ -75,7 +75,7 @@ class Engine {
   std::map<u32, std::string> deflatedOriginal;    // applied change index -> original compressed bytes
   std::vector<HostChange> queue; std::vector<std::string> queueOriginal;   // not yet causally ready
   u64 maxOp = 0;
-  float lastPhaseMs[8] = {0};
+  float lastPhaseMs[16] = {0};   // [0..7] CUDA-event phases, [8..15] host wall-clock markers (ms since call start)
   HBuf<u8> patchBuf;   // pinned: patch records are copied device -> host directly into their final place
   // ---- scratch (grow-only)
   DBuf<u32> chOff, chLen, nOps, nPreds, nDeps, nActors, colOff, colLen, depBase, depIdx, primary, pass, flagWord, appRank, opBase, predBase, timeBase, amapBase, amap, authorSlot, newSlots;
@@ -91,7 +91,7 @@ class Engine {
   DBuf<u32> isObjHead, objIdx, objStart, elemVis, elemVisScan, rowEmit, firstVis, state, nItems, itemBase, qIndex, zero, wzero, zscan, wscan, editObjKey;
   DBuf<DomItem> items, items2; DBuf<PropRec> propOut; DBuf<EditRec> editOut, editOut2; DBuf<u64> editElem, editElem2;
   DBuf<u32> seqSlot, actorCnt, actorBaseD, clockD, changeActor, editTime; DBuf<u8> hashTmp; bool batchInOrder = true;
-  DBuf<u32> finalTime, gFailed, memberFinal, opAt, runHead, opGroupHead; DBuf<u64> gBound; DocRows workView{}; DBuf<HostChange> chPairs; std::thread mirrorThread;
+  DBuf<u32> finalTime, gFailed, memberFinal, opAt, runHead, opGroupHead; DBuf<u64> gBound; DocRows workView{}; DBuf<HostChange> chPairs; std::thread mirrorThread; DBuf<u32> largeFlag, largeSlot, largeList; size_t lastNumLarge = 0;
 
   explicit Engine(int device) {
     ctx.device = device;

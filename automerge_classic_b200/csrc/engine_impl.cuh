@@ -1,10 +1,15 @@
 // amgpu — Engine::applyChanges / getPatch pipeline (see engine.cuh for the state layout).
 #pragma once
+#include <chrono>
 #include "engine.cuh"
 #include "misc.cuh"
 
 namespace amg {
 
+struct HostClock {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  float ms() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
 struct PhaseTimer {
 #ifndef AMG_EMU
   cudaEvent_t ev[10]; int n = 0; Ctx* c;
@@ -61,7 +66,8 @@ inline void Engine::reset() {
 }
 
 inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out, bool hostScan) {
-  PhaseTimer timer(ctx);
+  PhaseTimer timer(ctx); HostClock hclk; int hmark = 8;
+  auto hostMark = [&]() { if (hmark < 16) lastPhaseMs[hmark++] = hclk.ms(); };
   // ------------------------------------------------------------ 0. stage the batch in the arena (pinned host mirror + device)
   const size_t arenaLen0 = arenaLen; const size_t hostLen0 = hostArena.size();
   std::vector<HostChange> batch; std::vector<std::string> batchOriginal;   // originals only for deflated changes (else empty vector)
@@ -122,12 +128,12 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   chPairs.ensure(ctx, B); chOff.ensure(ctx, B); chLen.ensure(ctx, B);
   h2d(ctx, chPairs.p, batch.data(), B * sizeof(HostChange));
   foreach(ctx, B, SplitPairsKernel{chPairs.p, chOff.p, chLen.p});
-  timer.mark();
+  timer.mark(); hostMark();
   // ------------------------------------------------------------ 1. hash + header parse
   dev_memset(ctx, errWord.p, 0, 16);
   hashes.ensure(ctx, (numApplied + B) * 32 + 64, numApplied * 32);
   foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr});
-  timer.mark();
+  timer.mark(); hostMark();
   meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
   nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
   foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
@@ -179,7 +185,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     const bool hashApplied = pr < numApplied || appliedH[pr - numApplied];
     if (!hashApplied) { newQueue.push_back(batch[b]); newQueueOriginal.push_back(batchOriginal.empty() ? std::string() : batchOriginal[b]); }
   }
-  timer.mark();
+  timer.mark(); hostMark();
   std::vector<std::string> actorsNow = actorIds; std::vector<u64> clockNow = clock; std::vector<u32> actorCntH; std::vector<std::pair<u32, u32>> actorRepNow = actorRep;
   size_t M = 0, P = 0, N = numRows, numPairs = numSucc; u64 maxOpNow = maxOp;
   IdTable idt{nullptr, nullptr, 0};
@@ -200,13 +206,13 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       std::vector<u32> slotsH(fresh); d2h(ctx, slotsH.data(), newSlots.p, fresh * 4); sync(ctx);
       std::vector<ActorSlot> recs(fresh); for (u32 i = 0; i < fresh; i++) d2h(ctx, &recs[i], actorSlots.p + slotsH[i], sizeof(ActorSlot));
       sync(ctx);
-      if (mirrorThread.joinable()) mirrorThread.join();   // actor bytes are read from the host mirror
       std::vector<u32> order(fresh); for (u32 i = 0; i < fresh; i++) order[i] = i;
       std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return recs[a].first < recs[b].first; });
       std::vector<u32> ids(fresh), nums(fresh);
       for (u32 k = 0; k < fresh; k++) {
         const ActorSlot& r = recs[order[k]]; ids[k] = slotsH[order[k]]; nums[k] = (u32)actorsNow.size();
-        actorsNow.emplace_back((const char*)hostArena.data() + r.repOff, r.repLen); actorRepNow.emplace_back(r.repOff, r.repLen);
+        std::string idBytes(r.repLen, '\0'); d2h(ctx, &idBytes[0], arena.p + r.repOff, r.repLen); sync(ctx);   // from the device copy: the host mirror may still be filling
+        actorsNow.push_back(idBytes); actorRepNow.emplace_back(r.repOff, r.repLen);
       }
       if (actorsNow.size() > 65535) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 65535 actors in one document");
       sortVals.ensure(ctx, 2 * fresh); h2d(ctx, sortVals.p, ids.data(), fresh * 4); h2d(ctx, sortVals.p + fresh, nums.data(), fresh * 4);
@@ -270,19 +276,25 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     d2h(ctx, &maxOpNow, maxOpD.p, 8);
     for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, M + 1);
     r_predActor.ensure(ctx, P + 1); r_predCtr.ensure(ctx, P + 1);
-    // absent columns leave their rows untouched: pre-fill with null
-    for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrLen, &r_action, &r_valLen}) fill32(b->p, NULL32, M);
-    for (DBuf<u32>* b : {&r_keyStrOff, &r_insert, &r_valOff, &r_predNum, &r_predOff}) dev_memset(ctx, b->p, 0, (M + 1) * 4);
-    fill32(r_predActor.p, NULL32, P); fill32(r_predCtr.p, NULL32, P);
     RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
-    foreach(ctx, (size_t)NCOLS * B, DecodeColumnKernel{arena.p, B, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+    foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+    {   // changes with more than SMALL_CHANGE_OPS ops: (column, change)-parallel expansion
+      largeFlag.ensure(ctx, B + 1); largeSlot.ensure(ctx, B + 2); largeList.ensure(ctx, B + 1);
+      foreach(ctx, B, LargeFlagKernel{meta.p, applied.p, largeFlag.p});
+      scan_exclusive(ctx, scanTmp, largeFlag.p, largeSlot.p, B);
+      lastNumLarge = readU32(largeSlot.p + B);
+      if (lastNumLarge > 0) {
+        foreach(ctx, B, CompactKernel{largeFlag.p, largeSlot.p, largeList.p});
+        foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{arena.p, B, largeList.p, lastNumLarge, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+      }
+    }
     for (DBuf<u64>* b : {&o_id, &o_obj, &o_key}) b->ensure(ctx, M + 1);
     o_predId.ensure(ctx, P + 1);
     for (DBuf<u32>* b : {&o_keyStrOff, &o_keyStrLen, &o_flags, &o_valLen, &o_valOff, &o_predOff, &o_predNum, &o_change, &o_time}) b->ensure(ctx, M + 1);
     OpRows ops{o_id.p, o_obj.p, o_key.p, o_keyStrOff.p, o_keyStrLen.p, o_flags.p, o_valLen.p, o_valOff.p, o_predOff.p, o_predNum.p, o_change.p, o_time.p, o_predId.p};
     foreach(ctx, M, FinalizeOpsKernel{B, meta.p, opBase.p, timeBase.p, amapBase.p, amap.p, applied.p, raw, ops, errWord.p});
     checkErr(actorsNow);
-    timer.mark();
+    timer.mark(); hostMark();
     // ---------------------------------------------------------- 6. op set
     if (maxOpNow >= (1ULL << 40)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: op counters above 2^40");
     const int ordBits = bits_for(maxOpNow) + rb;
@@ -376,7 +388,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     foreach(ctx, numPairs, WriteSuccKernel{pairIdx.p, pairSucc.p, newSucc.p});
     sorted.ensure(ctx, N + 1);
     foreach(ctx, N, GatherRowsKernel{w, sorted.view(), perm.p});
-    timer.mark();
+    timer.mark(); hostMark();
     // ---------------------------------------------------------- 7. incremental patch
     if (wantPatch) {
       objPos.ensure(ctx, N + 1);
@@ -435,7 +447,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   }
   arenaLen = cur; queue = newQueue; queueOriginal = newQueueOriginal; rb.armed = false;
   sync(ctx);
-  timer.mark();
+  timer.mark(); hostMark();
   fillPatchHeader(out);
   if (isLocal && n == 1) {   // new.js:1874-1877
     std::vector<ChangeMeta> m0(1); d2h(ctx, m0.data(), meta.p, sizeof(ChangeMeta)); sync(ctx);
@@ -600,7 +612,10 @@ inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* 
   cudaEventRecord(e[1], ctx.stream);
   for (int i = 0; i < iters; i++) foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
   cudaEventRecord(e[2], ctx.stream);
-  for (int i = 0; i < iters; i++) foreach(ctx, (size_t)NCOLS * B, DecodeColumnKernel{arena.p, B, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+  for (int i = 0; i < iters; i++) {
+    foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+    if (lastNumLarge > 0) foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{arena.p, B, largeList.p, lastNumLarge, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+  }
   cudaEventRecord(e[3], ctx.stream);
   CUDA_CHECK(cudaEventSynchronize(e[3]));
   float a, b, c; cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[2], e[3]);
@@ -634,10 +649,16 @@ inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* 
   DBuf<u32>* cols[12] = {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff};
   for (auto* b : cols) b->ensure(ctx, M + 1);
   r_predActor.ensure(ctx, P + 1); r_predCtr.ensure(ctx, P + 1);
-  for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrLen, &r_action, &r_valLen}) fill32(b->p, NULL32, M);
-  for (DBuf<u32>* b : {&r_keyStrOff, &r_insert, &r_valOff, &r_predNum, &r_predOff}) dev_memset(ctx, b->p, 0, (M + 1) * 4);
   RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
-  foreach(ctx, (size_t)NCOLS * n, DecodeColumnKernel{ar.p, n, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+  foreach(ctx, n, DecodeSmallKernel{ar.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+  largeFlag.ensure(ctx, n + 1); largeSlot.ensure(ctx, n + 2); largeList.ensure(ctx, n + 1);
+  foreach(ctx, n, LargeFlagKernel{meta.p, applied.p, largeFlag.p});
+  scan_exclusive(ctx, scanTmp, largeFlag.p, largeSlot.p, n);
+  const size_t nl = readU32(largeSlot.p + n);
+  if (nl > 0) {
+    foreach(ctx, n, CompactKernel{largeFlag.p, largeSlot.p, largeList.p});
+    foreach(ctx, (size_t)NCOLS * nl, DecodeColumnKernel{ar.p, n, largeList.p, nl, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+  }
   checkErr(actorIds);
   d2h(ctx, hashesOut, hashTmp.p, n * 32); d2h(ctx, nOpsOut, nOps.p, n * 4);
   u32* rows = (u32*)malloc(sizeof(u32) * 12 * (M + 1));

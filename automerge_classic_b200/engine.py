@@ -386,8 +386,8 @@ class GpuBackendDoc:
         return r, s
 
     def timings(self):
-        out = (C.c_float * 8)()
-        self._lib.L.amg_last_timings(self.h, out, 8)
+        out = (C.c_float * 16)()
+        self._lib.L.amg_last_timings(self.h, out, 16)
         return list(out)
 
     def launches(self):
