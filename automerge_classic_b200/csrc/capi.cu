@@ -205,7 +205,7 @@ int amg_hash_by_actor(amg_backend* b, const uint8_t* actor, size_t actor_len, ui
             if (it != b->g.hashesByActor.end() && index < it->second.size()) { memcpy(hash_out, it->second[index].data(), 32); *found = 1; } return 0;)
 }
 
-int amg_last_timings(amg_backend* b, float* ms_out, int n) { for (int i = 0; i < n && i < 16; i++) ms_out[i] = b->eng.lastPhaseMs[i]; return 0; }
+int amg_last_timings(amg_backend* b, float* ms_out, int n) { for (int i = 0; i < n && i < 24; i++) ms_out[i] = b->eng.lastPhaseMs[i]; return 0; }
 uint64_t amg_kernel_launches(amg_backend* b) { return b->eng.ctx.launches; }
 
 int amg_debug_dump_ops(amg_backend* b, uint64_t** rows_out, size_t* n, uint64_t** succ_out, size_t* m, amg_error* err) {

@@ -11,6 +11,7 @@
 #pragma once
 #include <algorithm>
 #include <array>
+#include <functional>
 #include <map>
 #include <thread>
 #include <zlib.h>
@@ -75,7 +76,8 @@ class Engine {
   std::map<u32, std::string> deflatedOriginal;    // applied change index -> original compressed bytes
   std::vector<HostChange> queue; std::vector<std::string> queueOriginal;   // not yet causally ready
   u64 maxOp = 0;
-  float lastPhaseMs[16] = {0};   // [0..7] CUDA-event phases, [8..15] host wall-clock markers (ms since call start)
+  float lastPhaseMs[24] = {0};   // [0..11] CUDA-event phases, [12..23] host wall-clock markers (ms since call start)
+  struct PhaseTimer* curTimer = nullptr; std::function<void()> curHostMark;
   HBuf<u8> patchBuf;   // pinned: patch records are copied device -> host directly into their final place
   // ---- scratch (grow-only)
   DBuf<u32> chOff, chLen, nOps, nPreds, nDeps, nActors, colOff, colLen, depBase, depIdx, primary, pass, flagWord, appRank, opBase, predBase, timeBase, amapBase, amap, authorSlot, newSlots;

@@ -12,10 +12,10 @@ struct HostClock {
 };
 struct PhaseTimer {
 #ifndef AMG_EMU
-  cudaEvent_t ev[10]; int n = 0; Ctx* c;
+  cudaEvent_t ev[13]; int n = 0; Ctx* c;
   explicit PhaseTimer(Ctx& ctx) : c(&ctx) { for (auto& e : ev) cudaEventCreate(&e); mark(); }
   ~PhaseTimer() { for (auto& e : ev) cudaEventDestroy(e); }
-  void mark() { if (n < 10) cudaEventRecord(ev[n++], c->stream); }
+  void mark() { if (n < 13) cudaEventRecord(ev[n++], c->stream); }
   void collect(float* out, int maxN) { cudaEventSynchronize(ev[n - 1]); for (int i = 0; i + 1 < n && i < maxN; i++) cudaEventElapsedTime(&out[i], ev[i], ev[i + 1]); }
 #else
   explicit PhaseTimer(Ctx&) {}
@@ -66,8 +66,11 @@ inline void Engine::reset() {
 }
 
 inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out, bool hostScan) {
-  PhaseTimer timer(ctx); HostClock hclk; int hmark = 8;
-  auto hostMark = [&]() { if (hmark < 16) lastPhaseMs[hmark++] = hclk.ms(); };
+  PhaseTimer timer(ctx); HostClock hclk; int hmark = 12;
+  for (auto& x : lastPhaseMs) x = 0;
+  auto hostMark = [&]() { if (hmark < 24) lastPhaseMs[hmark++] = hclk.ms(); };
+  curTimer = &timer; curHostMark = hostMark;
+  struct ClearTimer { Engine* e; ~ClearTimer() { e->curTimer = nullptr; e->curHostMark = nullptr; } } clearTimer{this};
   // ------------------------------------------------------------ 0. stage the batch in the arena (pinned host mirror + device)
   const size_t arenaLen0 = arenaLen; const size_t hostLen0 = hostArena.size();
   std::vector<HostChange> batch; std::vector<std::string> batchOriginal;   // originals only for deflated changes (else empty vector)
@@ -397,6 +400,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       buildPatch(sorted.view(), N, false, &ops, M, &idt, rowOfOp.p, pos.p, actorsNow, out);
     }
     checkErr(actorsNow);
+    timer.mark(); hostMark();
     // heads
     {
       DBuf<u32>& isDep = groupLinked; isDep.ensure(ctx, G + 1); dev_memset(ctx, isDep.p, 0, (G + 1) * 4);
@@ -456,7 +460,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   }
   lastB = B; lastM = M; lastP = P; lastBytes = cur - arenaLen0; for (auto& c : queue) lastBytes += 0 * c.len;
   finishPatch(out);
-  timer.collect(lastPhaseMs, 8);
+  timer.collect(lastPhaseMs, 12);
 }
 
 }  // namespace amg
@@ -523,6 +527,7 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   const size_t numProps = readU32(slot.p + N);
   propOut.ensure(ctx, numProps + 1);
   foreach(ctx, N, PropEmitKernel{d, emit.p, marker.p, slot.p, propOut.p});
+  if (curTimer) { curTimer->mark(); curHostMark(); }
   // ---- list edits
   size_t numEdits = 0;
   if (wholeDoc) {
@@ -558,6 +563,7 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
         std::swap(items.p, items2.p); std::swap(items.cap, items2.cap);
       }
       foreach(ctx, T, DomResultKernel{items.p, qIndex.p});
+      if (curTimer) { curTimer->mark(); curHostMark(); }
       editOut.ensure(ctx, numEdits + 1); editElem.ensure(ctx, numEdits + 1); editObjKey.ensure(ctx, numEdits + 1);
       editTime.ensure(ctx, numEdits + 1);
       foreach(ctx, numOps, OpEditEmitKernel{*ops, emit.p, slot.p, rowOfOpD, posD, *idt, qIndex.p, editOut.p, editElem.p, editObjKey.p, editTime.p, objIdx.p});

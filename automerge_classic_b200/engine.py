@@ -386,8 +386,8 @@ class GpuBackendDoc:
         return r, s
 
     def timings(self):
-        out = (C.c_float * 16)()
-        self._lib.L.amg_last_timings(self.h, out, 16)
+        out = (C.c_float * 24)()
+        self._lib.L.amg_last_timings(self.h, out, 24)
         return list(out)
 
     def launches(self):

@@ -167,7 +167,7 @@ def main():
     for _ in range(args.steps):
         dt, ph, patch_bytes = step()
         wall.append(dt)
-        dev.append(sum(ph[1:6]) / 1e3)   # phases after the upload, CUDA events
+        dev.append(sum(ph[1:12]) / 1e3)   # phases after the upload, CUDA events
         last_ph = ph
     torch.cuda.synchronize()
     if world > 1:
@@ -218,8 +218,8 @@ def main():
                        'ops_per_gpu': trace.n_ops, 'changes_per_gpu': trace.n_changes, 'change_bytes_per_gpu': nbytes, 'parallelism': 'replicas x%d' % world,
                        'l2': 'inputs (%.0f MB) + working tables exceed the 126 MB L2; document reset every step' % (nbytes / 1e6),
                        'device_ms_per_step': t_dev * 1e3,
-                       'phase_ms_last_step': {'stage_upload': last_ph[0], 'sha256': last_ph[1], 'parse_gate': last_ph[2], 'actors_decode': last_ph[3], 'opset': last_ph[4], 'patch_commit': last_ph[5],
-                                              'host_marks_ms': [round(x, 3) for x in last_ph[8:15]]}},
+                       'phase_ms_last_step': dict(zip(['stage_upload', 'sha256', 'parse_gate', 'actors_decode', 'opset', 'patch_groups_props', 'patch_list_index', 'patch_edits_copyout', 'heads_commit'], [round(x, 3) for x in last_ph[:9]])),
+                       'host_marks_ms': [round(x, 3) for x in last_ph[12:22]]},
             'e2e': {'value': total_ops / t_wall, 'unit': 'ops/s', 'h2d_bytes_per_step': nbytes + 8 * (trace.n_changes + 1), 'd2h_bytes_per_step': patch_bytes},
             'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks}))
     if world > 1:

@@ -105,7 +105,8 @@ int amg_debug_decode(amg_backend* b, const uint8_t* blob, const uint64_t* offset
                      uint32_t* n_ops_out /* n */, uint32_t** rows_out /* 12 columns x total ops, malloc'ed */, size_t* total_ops, amg_error* err);
 /* document-ordered op table: rows[n][8] = {objCtr,objActor,idCtr,idActor,keyCtr,keyActor,flags,succNum}; succ[m][2] = {ctr, actor} */
 int amg_debug_dump_ops(amg_backend* b, uint64_t** rows_out, size_t* n, uint64_t** succ_out, size_t* m, amg_error* err);
-/* CUDA-event timings (ms) of the phases of the last applyChanges call: stage+h2d, sha256, parse+gate, actors+decode, opset, patch+commit */
+/* timings of the last applyChanges call: [0..11] CUDA-event phases in ms (stage+upload, sha256, parse+gate, actors+decode, op set,
+ * patch groups+props, list index, edits+copy-out, heads+commit), [12..23] host wall-clock marks (ms since the call started) */
 int amg_last_timings(amg_backend* b, float* ms_out, int n);
 uint64_t amg_kernel_launches(amg_backend* b);
 void amg_free_mem(void* p);
