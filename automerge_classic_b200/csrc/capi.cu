@@ -48,7 +48,7 @@ struct amg_backend {
   }
   std::string changeBytes(u32 idx) {
     auto it = eng.deflatedOriginal.find(idx);
-    if (it != eng.deflatedOriginal.end()) return it->second;
+    if (it != eng.deflatedOriginal.end()) return std::string((const char*)eng.hostArena.data() + it->second.off, it->second.len);
     const HostChange& c = eng.changes[idx];
     return std::string((const char*)eng.hostArena.data() + c.off, c.len);
   }
@@ -206,6 +206,10 @@ int amg_hash_by_actor(amg_backend* b, const uint8_t* actor, size_t actor_len, ui
 }
 
 int amg_last_timings(amg_backend* b, float* ms_out, int n) { for (int i = 0; i < n && i < 24; i++) ms_out[i] = b->eng.lastPhaseMs[i]; return 0; }
+size_t amg_debug_marks(amg_backend* b, char* buf, size_t cap) {
+  std::string s; for (auto& m : b->eng.dbgMarks) { char t[96]; snprintf(t, sizeof t, "%s=%.3f ", m.first, m.second); s += t; }
+  if (cap) { snprintf(buf, cap, "%s", s.c_str()); } return s.size();
+}
 uint64_t amg_kernel_launches(amg_backend* b) { return b->eng.ctx.launches; }
 
 int amg_debug_dump_ops(amg_backend* b, uint64_t** rows_out, size_t* n, uint64_t** succ_out, size_t* m, amg_error* err) {

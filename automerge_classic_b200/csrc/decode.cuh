@@ -184,30 +184,38 @@ HD u32 load_be32(const u8* p) {
   return (u32)p[0] << 24 | (u32)p[1] << 16 | (u32)p[2] << 8 | p[3];
 #endif
 }
+// One compression. The 64 rounds run as 4 iterations of a 16-round body: inside the body every w[] index is a
+// compile-time constant (the schedule stays in registers) while the code stays small enough for the instruction
+// cache (a fully unrolled 64-round body made ShaKernel stall on instruction fetch: ncu "no_instruction").
 HD void sha256_compress(u32* h, u32* w, const u32* K) {
   u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
-#pragma unroll 64
-  for (int i = 0; i < 64; i++) {   // fully unrolled: every w[] index is static, the schedule stays in registers
-    u32 wi;
-    if (i < 16) wi = w[i];
-    else {
-      const u32 w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
-      const u32 s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3), s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
-      wi = w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+#pragma unroll 1
+  for (int r = 0; r < 64; r += 16) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      if (r > 0) {
+        const u32 w15 = w[(j + 1) & 15], w2 = w[(j + 14) & 15];
+        const u32 s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3), s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+        w[j] = w[j] + s0 + w[(j + 9) & 15] + s1;
+      }
+      const u32 t1 = hh + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + K[r + j] + w[j];
+      const u32 t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
     }
-    const u32 t1 = hh + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + wi;
-    const u32 t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
-    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
   }
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
 
 // hashes arena[off+8 .. off+len) of every change; writes 32-byte digests; checks magic + checksum
 struct ShaKernel {
-  const u8* arena; const u32* chOff; const u32* chLen; u8* hashOut /* [n][32] */; u64* errWord; const u32* Kdev;
-  HD void operator()(size_t c) const {
+  const u8* arena; const u32* chOff; const u32* chLen; u8* hashOut /* [n][32] */; u64* errWord; const u32* subset /* optional: only these changes */; u32* deflList;
+  HD void operator()(size_t ci) const {
+    const size_t c = subset ? subset[ci] : ci;
     const u8* p = arena + chOff[c]; const u32 len = chLen[c];
-    if (len > 8 && p[8] == 2 && p[0] == 0x85) { errWord[1] = 1; return; }   // DEFLATEd change: the host inflates and re-stages the batch
+    if (len > 8 && p[8] == 2 && p[0] == 0x85) {   // DEFLATEd change (columnar.js:742): listed for the host, which inflates it and re-points this entry
+      if (deflList) deflList[atomic_add(errWord + 1, (u64)1)] = (u32)c; else raise(errWord, KE_CHUNK_TYPE, c);
+      return;
+    }
     if (len < 10 || p[0] != 0x85 || p[1] != 0x6f || p[2] != 0x4a || p[3] != 0x83) { raise(errWord, KE_MAGIC, c); return; }
 #if defined(__CUDA_ARCH__)
     const u32* K = c_sha.k;
@@ -216,32 +224,29 @@ struct ShaKernel {
 #endif
     u32 h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
     const u8* m = p + 8; const u32 mlen = len - 8;
-    u32 w[16]; u32 done = 0;
-    while (done + 64 <= mlen) {
+    // blocks: all full 64-byte blocks, then one or two padded blocks (0x80, zeros, 64-bit bit length); one call site
+    const u32 nBlocks = (mlen + 9 + 63) / 64; u32 w[16];
+    for (u32 blk = 0; blk < nBlocks; blk++) {
+      const u32 done = blk * 64;
+      if (done + 64 <= mlen) {
 #pragma unroll
-      for (int i = 0; i < 16; i++) w[i] = load_be32(m + done + 4 * i);
-      sha256_compress(h, w, K); done += 64;
-    }
-    // tail: remaining bytes + 0x80 + zero pad + 64-bit bit length
-    const u32 rem = mlen - done;
+        for (int i = 0; i < 16; i++) w[i] = load_be32(m + done + 4 * i);
+      } else {
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-      u32 v = 0;
+        for (int i = 0; i < 16; i++) {
+          u32 v = 0;
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
-        const u32 ix = 4 * i + b; u32 byte = 0;
-        if (ix < rem) byte = m[done + ix]; else if (ix == rem) byte = 0x80;
-        v = (v << 8) | byte;
+          for (int b = 0; b < 4; b++) {
+            const u32 ix = done + 4 * i + b; u32 byte = 0;
+            if (ix < mlen) byte = m[ix]; else if (ix == mlen) byte = 0x80;
+            v = (v << 8) | byte;
+          }
+          w[i] = v;
+        }
+        if (blk == nBlocks - 1) { w[14] = (u32)(((u64)mlen * 8) >> 32); w[15] = (u32)((u64)mlen * 8); }
       }
-      w[i] = v;
-    }
-    if (rem >= 56) {
       sha256_compress(h, w, K);
-#pragma unroll
-      for (int i = 0; i < 16; i++) w[i] = 0;
     }
-    w[14] = (u32)(((u64)mlen * 8) >> 32); w[15] = (u32)((u64)mlen * 8);
-    sha256_compress(h, w, K);
     u8* out = hashOut + c * 32;
 #pragma unroll
     for (int i = 0; i < 8; i++) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }

@@ -73,11 +73,12 @@ class Engine {
   std::vector<std::pair<u32, u32>> actorRep;   // arena (offset, length) of each actor's id bytes
   std::vector<HostChange> changes;     // applied, in application order
   std::vector<std::array<u8, 32>> changeHashes;   // host copy of applied hashes (filled lazily)
-  std::map<u32, std::string> deflatedOriginal;    // applied change index -> original compressed bytes
-  std::vector<HostChange> queue; std::vector<std::string> queueOriginal;   // not yet causally ready
+  std::map<u32, HostChange> deflatedOriginal;     // applied change index -> arena range of the original DEFLATEd bytes
+  std::vector<HostChange> queue, queueOriginal;   // not yet causally ready (+ original range, len 0 = not deflated)
   u64 maxOp = 0;
   float lastPhaseMs[24] = {0};   // [0..11] CUDA-event phases, [12..23] host wall-clock markers (ms since call start)
   struct PhaseTimer* curTimer = nullptr; std::function<void()> curHostMark;
+  std::vector<std::pair<const char*, float>> dbgMarks; std::function<void(const char*)> dbgMark = [](const char*) {};
   HBuf<u8> patchBuf;   // pinned: patch records are copied device -> host directly into their final place
   // ---- scratch (grow-only)
   DBuf<u32> chOff, chLen, nOps, nPreds, nDeps, nActors, colOff, colLen, depBase, depIdx, primary, pass, flagWord, appRank, opBase, predBase, timeBase, amapBase, amap, authorSlot, newSlots;
@@ -93,7 +94,7 @@ class Engine {
   DBuf<u32> isObjHead, objIdx, objStart, elemVis, elemVisScan, rowEmit, firstVis, state, nItems, itemBase, qIndex, zero, wzero, zscan, wscan, editObjKey;
   DBuf<DomItem> items, items2; DBuf<PropRec> propOut; DBuf<EditRec> editOut, editOut2; DBuf<u64> editElem, editElem2;
   DBuf<u32> seqSlot, actorCnt, actorBaseD, clockD, changeActor, editTime; DBuf<u8> hashTmp; bool batchInOrder = true;
-  DBuf<u32> finalTime, gFailed, memberFinal, opAt, runHead, opGroupHead; DBuf<u64> gBound; DocRows workView{}; DBuf<HostChange> chPairs; std::thread mirrorThread; DBuf<u32> largeFlag, largeSlot, largeList; size_t lastNumLarge = 0;
+  DBuf<u32> finalTime, gFailed, memberFinal, opAt, runHead, opGroupHead; DBuf<u64> gBound; DocRows workView{}; DBuf<HostChange> chPairs; std::thread mirrorThread; DBuf<u32> largeFlag, largeSlot, largeList; size_t lastNumLarge = 0; DBuf<u64> zwScan; DBuf<u32> deflList, patchTriples;
 
   explicit Engine(int device) {
     ctx.device = device;

@@ -70,10 +70,11 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   for (auto& x : lastPhaseMs) x = 0;
   auto hostMark = [&]() { if (hmark < 24) lastPhaseMs[hmark++] = hclk.ms(); };
   curTimer = &timer; curHostMark = hostMark;
-  struct ClearTimer { Engine* e; ~ClearTimer() { e->curTimer = nullptr; e->curHostMark = nullptr; } } clearTimer{this};
+  dbgMarks.clear(); dbgMark = [this, &hclk](const char* l) { dbgMarks.emplace_back(l, hclk.ms()); };
+  struct ClearTimer { Engine* e; ~ClearTimer() { e->curTimer = nullptr; e->curHostMark = nullptr; e->dbgMark = [](const char*) {}; } } clearTimer{this};
   // ------------------------------------------------------------ 0. stage the batch in the arena (pinned host mirror + device)
   const size_t arenaLen0 = arenaLen; const size_t hostLen0 = hostArena.size();
-  std::vector<HostChange> batch; std::vector<std::string> batchOriginal;   // originals only for deflated changes (else empty vector)
+  std::vector<HostChange> batch, batchOriginal;   // batchOriginal: arena range of the original bytes of DEFLATEd changes (empty vector = none)
   struct Rollback { Engine* e; size_t len; bool armed = true; ~Rollback() { if (armed) { e->hostArena.resize(len); e->rebuildActorTable(); } } };
   size_t total = 0;
   if (blob && n > 0) total = offsets[n] - offsets[0]; else for (size_t i = 0; i < n; i++) total += lens[i];
@@ -90,11 +91,14 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
 #ifndef AMG_EMU
     { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, blob) == cudaSuccess && at.type == cudaMemoryTypeHost) callerPinned = true; else cudaGetLastError(); }
 #endif
+    dbgMark("stage:attrs");
     if (callerPinned) {
       // the caller's buffer is pinned: DMA straight from it, and fill the host mirror on a CPU thread while the GPU works
       h2d(ctx, arena.p + cur, blob + base, tot);
       u8* dst = hostArena.data() + cur; const u8* src = blob + base;
+      dbgMark("stage:h2d-enqueued");
       mirrorThread = std::thread([dst, src, tot] { parallel_copy(dst, src, tot); });
+      dbgMark("stage:thread-spawned");
     } else {
       const size_t kChunk = 32u << 20;   // copy into the pinned mirror and upload chunk by chunk (H2D overlaps the next host copy)
       for (size_t o = 0; o < tot; o += kChunk) {
@@ -105,7 +109,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     }
     const u32 shift = (u32)(cur - base);
     for (size_t i = 0; i < n; i++) { batch[i].off = (u32)offsets[i] + shift; batch[i].len = (u32)(offsets[i + 1] - offsets[i]); }
-    uploaded = true; cur += tot;
+    uploaded = true; cur += tot; dbgMark("stage:batch-filled");
   } else {
     bool anyDeflated = false;
     for (size_t i = 0; i < n; i++) {
@@ -113,14 +117,15 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       if (l > 8 && p[8] == 2) {   // reference columnar.js:742
         std::string inflated = inflateChange(p, l);
         if ((u64)cur + inflated.size() + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
+        if (!anyDeflated) { anyDeflated = true; batchOriginal.assign(n + Bq, HostChange{0, 0}); }
+        hostArena.append(p, l); batchOriginal[i] = HostChange{(u32)cur, (u32)l}; cur += l;   // keep the original bytes (getChanges returns them)
         hostArena.append(inflated.data(), inflated.size());
-        if (!anyDeflated) { anyDeflated = true; batchOriginal.resize(n + Bq); }
-        batch[i] = HostChange{(u32)cur, (u32)inflated.size()}; batchOriginal[i].assign((const char*)p, l); cur += inflated.size();
+        batch[i] = HostChange{(u32)cur, (u32)inflated.size()}; cur += inflated.size();
       } else { hostArena.append(p, l); batch[i] = HostChange{(u32)cur, (u32)l}; cur += l; }
     }
   }
   if (Bq > 0) {
-    if (batchOriginal.empty()) batchOriginal.resize(n + Bq);
+    if (batchOriginal.empty()) batchOriginal.assign(n + Bq, HostChange{0, 0});
     for (size_t i = 0; i < Bq; i++) { batch[n + i] = queue[i]; batchOriginal[n + i] = queueOriginal[i]; }
   }
   const size_t B = batch.size();
@@ -130,25 +135,53 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   dev_memset(ctx, arena.p + cur, 0, 64);
   chPairs.ensure(ctx, B); chOff.ensure(ctx, B); chLen.ensure(ctx, B);
   h2d(ctx, chPairs.p, batch.data(), B * sizeof(HostChange));
+  dbgMark("stage:pairs-h2d");
   foreach(ctx, B, SplitPairsKernel{chPairs.p, chOff.p, chLen.p});
+  dbgMark("stage:done");
   timer.mark(); hostMark();
   // ------------------------------------------------------------ 1. hash + header parse
   dev_memset(ctx, errWord.p, 0, 16);
   hashes.ensure(ctx, (numApplied + B) * 32 + 64, numApplied * 32);
-  foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr});
+  deflList.ensure(ctx, B + 1);
+  foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr, uploaded ? deflList.p : nullptr});
+  std::vector<u32> deflIdx;
+  if (uploaded) {
+    u64 ew[2]; d2h(ctx, ew, errWord.p, 16); sync(ctx);
+    if (ew[1]) {
+      // DEFLATEd changes inside a bulk batch: inflate just those on host threads (zlib, as columnar.js:813-823 does with pako),
+      // append the inflated bytes behind the batch and re-point the entries; their original bytes stay where they are.
+      const size_t nd = (size_t)ew[1]; deflIdx.resize(nd); d2h(ctx, deflIdx.data(), deflList.p, nd * 4); sync(ctx);
+      std::sort(deflIdx.begin(), deflIdx.end());
+      std::vector<std::string> inflated(nd); std::string firstError;
+      { unsigned nt = std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency())); if (nd < 64) nt = 1;
+        std::vector<std::thread> ts; std::vector<std::string> errs(nt);
+        for (unsigned t = 0; t < nt; t++) ts.emplace_back([&, t] { try { for (size_t k = t; k < nd; k += nt) { const u32 b = deflIdx[k]; inflated[k] = inflateChange(blob + offsets[b], (size_t)(offsets[b + 1] - offsets[b])); } } catch (std::exception& e) { errs[t] = e.what(); } });
+        for (auto& th : ts) th.join();
+        for (auto& e : errs) if (!e.empty() && firstError.empty()) firstError = e; }
+      if (!firstError.empty()) throw Error(AMG_ERR_RANGE, firstError);
+      if (mirrorThread.joinable()) mirrorThread.join();   // the mirror may have to grow
+      size_t extra = 0; for (auto& x : inflated) extra += x.size();
+      if ((u64)cur + extra + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
+      const size_t extraStart = cur; hostArena.resize(cur + extra); batchOriginal.assign(B, HostChange{0, 0});
+      std::vector<u32> triples(3 * nd);
+      for (size_t k = 0; k < nd; k++) {
+        const u32 b = deflIdx[k]; batchOriginal[b] = batch[b];
+        memcpy(hostArena.data() + cur, inflated[k].data(), inflated[k].size());
+        batch[b] = HostChange{(u32)cur, (u32)inflated[k].size()}; triples[3 * k] = b; triples[3 * k + 1] = batch[b].off; triples[3 * k + 2] = batch[b].len; cur += inflated[k].size();
+      }
+      arena.ensure(ctx, cur + 64, extraStart); h2d(ctx, arena.p + extraStart, hostArena.data() + extraStart, cur - extraStart); dev_memset(ctx, arena.p + cur, 0, 64);
+      patchTriples.ensure(ctx, 3 * nd); h2d(ctx, patchTriples.p, triples.data(), triples.size() * 4);
+      foreach(ctx, nd, PatchPairsKernel{patchTriples.p, chOff.p, chLen.p});
+      h2d(ctx, deflList.p, deflIdx.data(), nd * 4);
+      foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, deflList.p, nullptr});
+      sync(ctx);
+    }
+  }
   timer.mark(); hostMark();
   meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
   nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
   foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
-  {
-    u64 ew[2]; d2h(ctx, ew, errWord.p, 16); sync(ctx);
-    if (ew[1]) {   // the batch contains DEFLATEd changes: redo the staging with host-side inflate (columnar.js:813-823)
-      if (mirrorThread.joinable()) mirrorThread.join();
-      rb.armed = false; hostArena.resize(hostLen0);
-      return applyChanges(bufs, lens, n, blob, offsets, isLocal, wantPatch, out, true);
-    }
-    if (ew[0]) throwKernelError(ew[0], actorIds);
-  }
+  { u64 ew0 = 0; d2h(ctx, &ew0, errWord.p, 8); sync(ctx); if (ew0) throwKernelError(ew0, actorIds); }
   // ------------------------------------------------------------ 2. causal gate
   depBase.ensure(ctx, B + 1); scan_exclusive(ctx, scanTmp, nDeps.p, depBase.p, B);
   const u32 totalDeps = readU32(depBase.p + B);
@@ -182,11 +215,11 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   }
   auto isApplied = [&](size_t b) { return appliedH.empty() ? true : appliedH[b] != 0; };
   // the queue after this call: every batch entry whose hash is still not applied (new.js:1569-1570, 1832)
-  std::vector<HostChange> newQueue; std::vector<std::string> newQueueOriginal;
+  std::vector<HostChange> newQueue, newQueueOriginal;
   if (numNew < B) for (size_t b = 0; b < B; b++) {
     const u32 pr = primaryH[b];
     const bool hashApplied = pr < numApplied || appliedH[pr - numApplied];
-    if (!hashApplied) { newQueue.push_back(batch[b]); newQueueOriginal.push_back(batchOriginal.empty() ? std::string() : batchOriginal[b]); }
+    if (!hashApplied) { newQueue.push_back(batch[b]); newQueueOriginal.push_back(batchOriginal.empty() ? HostChange{0, 0} : batchOriginal[b]); }
   }
   timer.mark(); hostMark();
   std::vector<std::string> actorsNow = actorIds; std::vector<u64> clockNow = clock; std::vector<u32> actorCntH; std::vector<std::pair<u32, u32>> actorRepNow = actorRep;
@@ -402,6 +435,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     checkErr(actorsNow);
     timer.mark(); hostMark();
     // heads
+    dbgMark("commit:begin");
     {
       DBuf<u32>& isDep = groupLinked; isDep.ensure(ctx, G + 1); dev_memset(ctx, isDep.p, 0, (G + 1) * 4);
       foreach(ctx, B, MarkDepsKernel{applied.p, meta.p, depBase.p, depIdx.p, isDep.p});
@@ -425,29 +459,38 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   } else {
     headIdxNow = headIdx;
   }
+  dbgMark("commit:heads-done");
   // ------------------------------------------------------------ 8. commit (nothing above mutated persistent state)
   sync(ctx);
+  dbgMark("commit:synced");
   if (numNew > 0) {
     if (!(inOrder && numNew == B)) {   // hashes of applied changes must be contiguous in application order
       DBuf<u8>& tmp = hashTmp; tmp.ensure(ctx, numNew * 32 + 64);
       foreach(ctx, B, HashGatherKernel{hashes.p + numApplied * 32, applied.p, appRank.p, tmp.p});
       d2d(ctx, hashes.p + numApplied * 32, tmp.p, numNew * 32);
     }
-    if (appliedH.empty() && batchOriginal.empty()) changes.insert(changes.end(), batch.begin(), batch.end());   // all applied, in order
+    if (appliedH.empty()) {   // all applied, in order
+      const u32 base0 = (u32)changes.size();
+      changes.insert(changes.end(), batch.begin(), batch.end());
+      if (!batchOriginal.empty()) { if (deflIdx.empty()) { for (size_t b = 0; b < B; b++) if (batchOriginal[b].len) deflatedOriginal[base0 + (u32)b] = batchOriginal[b]; } else for (u32 b : deflIdx) deflatedOriginal[base0 + b] = batchOriginal[b]; }
+    }
     else {
       std::vector<u32> byRank(numNew);
       if (appliedH.empty()) for (size_t b = 0; b < B; b++) byRank[b] = (u32)b; else for (size_t b = 0; b < B; b++) if (appliedH[b]) byRank[appRankH[b]] = (u32)b;
       for (size_t k = 0; k < numNew; k++) {
         const u32 b = byRank[k];
-        if (!batchOriginal.empty() && !batchOriginal[b].empty()) deflatedOriginal[(u32)changes.size()] = batchOriginal[b];
+        if (!batchOriginal.empty() && batchOriginal[b].len) deflatedOriginal[(u32)changes.size()] = batchOriginal[b];
         changes.push_back(batch[b]);
       }
     }
+    dbgMark("commit:changes-recorded");
     doc.swap(sorted); numRows = N;
     std::swap(succOff.p, newSuccOff.p); std::swap(succOff.cap, newSuccOff.cap); std::swap(succ.p, newSucc.p); std::swap(succ.cap, newSucc.cap); numSucc = numPairs;
     fill32(doc.time.p, 0, N);
     numApplied += numNew; actorRep = actorRepNow; actorIds = actorsNow; clock = clockNow; maxOp = maxOpNow; heads = headsNow; headIdx = headIdxNow;
+    dbgMark("commit:state-swapped");
     rebuildActorTable();   // slots of actors registered in this call become permanent (first = 0)
+    dbgMark("commit:actors-rebuilt");
   }
   arenaLen = cur; queue = newQueue; queueOriginal = newQueueOriginal; rb.armed = false;
   sync(ctx);
@@ -458,6 +501,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     if (mirrorThread.joinable()) mirrorThread.join();
     out.hasActorSeq = true; out.actor.assign((const char*)hostArena.data() + m0[0].actorOff, m0[0].actorLen); out.seq = m0[0].seq;
   }
+  dbgMark("commit:end");
   lastB = B; lastM = M; lastP = P; lastBytes = cur - arenaLen0; for (auto& c : queue) lastBytes += 0 * c.len;
   finishPatch(out);
   timer.collect(lastPhaseMs, 12);
@@ -553,13 +597,12 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
     scan_exclusive(ctx, scanTmp, emit.p, slot.p, numOps);
     numEdits = readU32(slot.p + numOps);
     if (numEdits > 0) {
-      items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zero.ensure(ctx, T + 1); wzero.ensure(ctx, T + 1); zscan.ensure(ctx, T + 2); wscan.ensure(ctx, T + 2);
+      items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zwScan.ensure(ctx, T + 2);
       foreach(ctx, N, DomBuildKernel{d, state.p, firstNewSucc.p, itemBase.p, objIdx.p, objStart.p, items.p});
       const int tbits = bits_for(numOps + 1);
       for (int bit = tbits - 1; bit >= 0; bit--) {
-        foreach(ctx, T, DomFlagKernel{items.p, bit, zero.p, wzero.p});
-        scan_exclusive(ctx, scanTmp, zero.p, zscan.p, T); scan_exclusive(ctx, scanTmp, wzero.p, wscan.p, T);
-        foreach(ctx, T, DomLevelKernel{items.p, items2.p, zscan.p, wscan.p, bit});
+        scan_exclusive64(ctx, scanTmp, DomScanInput{items.p, bit}, zwScan.p, T);
+        foreach(ctx, T, DomLevelKernel{items.p, items2.p, zwScan.p, bit});
         std::swap(items.p, items2.p); std::swap(items.cap, items2.cap);
       }
       foreach(ctx, T, DomResultKernel{items.p, qIndex.p});
@@ -614,7 +657,7 @@ inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* 
 #ifndef AMG_EMU
   cudaEvent_t e[4]; for (auto& x : e) cudaEventCreate(&x);
   cudaEventRecord(e[0], ctx.stream);
-  for (int i = 0; i < iters; i++) foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr});
+  for (int i = 0; i < iters; i++) foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
   cudaEventRecord(e[1], ctx.stream);
   for (int i = 0; i < iters; i++) foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
   cudaEventRecord(e[2], ctx.stream);
@@ -644,7 +687,7 @@ inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* 
   DBuf<u8> ar; ar.ensure(ctx, staged.size() + 64); h2d(ctx, ar.p, staged.data(), staged.size()); dev_memset(ctx, ar.p + staged.size(), 0, 64);
   chOff.ensure(ctx, n); chLen.ensure(ctx, n); h2d(ctx, chOff.p, off.data(), n * 4); h2d(ctx, chLen.p, len.data(), n * 4);
   dev_memset(ctx, errWord.p, 0, 8); hashTmp.ensure(ctx, n * 32 + 64);
-  foreach(ctx, n, ShaKernel{ar.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr});
+  foreach(ctx, n, ShaKernel{ar.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
   meta.ensure(ctx, n); colOff.ensure(ctx, (size_t)NCOLS * n); colLen.ensure(ctx, (size_t)NCOLS * n);
   nOps.ensure(ctx, n + 1); nPreds.ensure(ctx, n + 1); nDeps.ensure(ctx, n + 1); nActors.ensure(ctx, n + 1);
   foreach(ctx, n, ParseKernel{ar.p, chOff.p, chLen.p, n, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});

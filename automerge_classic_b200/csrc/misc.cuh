@@ -60,6 +60,7 @@ struct HeadFlag2Kernel { const u8* applied; const u32* isDep; size_t numApplied;
 struct CompactKernel { const u32* flag; const u32* slot; u32* out; HD void operator()(size_t i) const { if (flag[i]) out[slot[i]] = (u32)i; } };
 struct HashGatherKernel { const u8* src; const u8* applied; const u32* appRank; u8* dst; HD void operator()(size_t b) const { if (!applied[b]) return; const u64* s = reinterpret_cast<const u64*>(src + b * 32); u64* d = reinterpret_cast<u64*>(dst + (size_t)appRank[b] * 32); d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; } };
 struct SplitPairsKernel { const HostChange* pairs; u32* off; u32* len; HD void operator()(size_t b) const { off[b] = pairs[b].off; len[b] = pairs[b].len; } };
+struct PatchPairsKernel { const u32* triples; u32* off; u32* len; HD void operator()(size_t i) const { const u32 c = triples[3 * i]; off[c] = triples[3 * i + 1]; len[c] = triples[3 * i + 2]; } };
 struct KeySlotInitKernel { KeySlot* s; HD void operator()(size_t i) const { s[i].hash = 0; s[i].rep = 0xffffffffu; s[i].rank = 0; } };
 struct InsertFlagKernel { DocRows w; u32* flag; HD void operator()(size_t r) const { flag[r] = (w.keyStrLen[r] == NULL32 && (w.flags[r] & F_INSERT)) ? 1u : 0u; } };
 struct GatherU32Kernel { const u32* src; const u32* idx; u32* out; HD void operator()(size_t i) const { out[i] = src[idx[i]]; } };

@@ -270,23 +270,24 @@ struct DomBuildKernel {
     }
   }
 };
-struct DomFlagKernel {   // per level: zero flag and weighted zero flag
-  const DomItem* items; int bit; u32* zero; u32* wzero;
-  HD void operator()(size_t i) const {
+struct DomScanInput {   // per level: low word = 1 if the time bit is clear, high word = the item's weight if the bit is clear
+  const DomItem* items; int bit;
+  HD u64 operator()(size_t i) const {
     const bool z = ((items[i].time >> bit) & 1u) == 0;
-    zero[i] = z ? 1u : 0u; wzero[i] = z ? (u32)items[i].w : 0u;
+    return z ? (1ull | ((u64)(u32)items[i].w << 32)) : 0ull;
   }
 };
-struct DomLevelKernel {   // accumulate + stable split of every group on `bit`
-  const DomItem* in; DomItem* out; const u32* Z; const u32* W; int bit;
+struct DomLevelKernel {   // accumulate + stable split of every group on `bit`; ZW = packed exclusive scan of DomScanInput
+  const DomItem* in; DomItem* out; const u64* ZW; int bit;
   HD void operator()(size_t i) const {
     DomItem it = in[i];
-    const u32 zg = Z[it.ge] - Z[it.gs];               // zeros in the group
-    const u32 zb = Z[i] - Z[it.gs];                    // zeros before i in the group
+    const u64 s_i = ZW[i], s_gs = ZW[it.gs], s_ge = ZW[it.ge];
+    const u32 zg = (u32)s_ge - (u32)s_gs;             // zeros in the group
+    const u32 zb = (u32)s_i - (u32)s_gs;               // zeros before i in the group
     const bool one = (it.time >> bit) & 1u;
     u32 dst;
     if (one) {
-      if (it.ref & 0x80000000u) it.acc += W[i] - W[it.gs];
+      if (it.ref & 0x80000000u) it.acc += (u32)(s_i >> 32) - (u32)(s_gs >> 32);
       dst = it.gs + zg + ((u32)i - it.gs - zb);
       it.gs = it.gs + zg;
     } else {

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) k_scan_apply(const u32* in, u32* out, con
 }
 #endif
 
-struct ScanTemp { DBuf<u32> tiles; };
+struct ScanTemp { DBuf<u32> tiles; DBuf<u64> tiles64; };
 
 // out[0..n) = exclusive prefix sums of in[0..n); out[n] = total (out must hold n+1). in == out allowed.
 inline void scan_exclusive(Ctx& c, ScanTemp& t, const u32* in, u32* out, size_t n) {
@@ -97,6 +97,79 @@ inline void scan_exclusive(Ctx& c, ScanTemp& t, const u32* in, u32* out, size_t 
   k_scan_reduce<<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, t.tiles.p, n);
   k_scan_tiles<<<1, SCAN_THREADS, 0, c.stream>>>(t.tiles.p, numTiles, out + n);
   k_scan_apply<<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, out, t.tiles.p, n);
+  CUDA_CHECK(cudaGetLastError());
+  c.launches += 3;
+#endif
+}
+
+// 64-bit variant whose input is produced on the fly by a functor (u64 operator()(size_t i)): used to scan two packed
+// 32-bit quantities at once (low word: a count that never overflows 32 bits; high word: a signed sum, mod 2^32).
+#ifndef AMG_EMU
+__device__ __forceinline__ u64 warp_incl_scan64(u64 v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+  return v;
+}
+__device__ __forceinline__ u64 block_excl_scan64(u64 v, u64* total, u64* smem /* >= 9 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u64 incl = warp_incl_scan64(v);
+  if (lane == 31) smem[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    u64 w = lane < (SCAN_THREADS / 32) ? smem[lane] : 0;
+    u64 wi = warp_incl_scan64(w);
+    if (lane < (SCAN_THREADS / 32)) smem[lane] = wi - w;
+    if (lane == (SCAN_THREADS / 32) - 1) smem[8] = wi;
+  }
+  __syncthreads();
+  u64 res = smem[warp] + incl - v;
+  *total = smem[8];
+  __syncthreads();
+  return res;
+}
+template <class F> __global__ void __launch_bounds__(256) k_scan64_reduce(F in, u64* __restrict__ tileSums, size_t n) {
+  __shared__ u64 sm[9];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  u64 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) s += in(base + k);
+  u64 total; block_excl_scan64(s, &total, sm);
+  if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(256) k_scan64_tiles(u64* __restrict__ tileSums, size_t numTiles, u64* __restrict__ totalOut) {
+  __shared__ u64 sm[9];
+  u64 carry = 0;
+  for (size_t base = 0; base < numTiles; base += SCAN_THREADS) {
+    size_t i = base + threadIdx.x;
+    u64 v = i < numTiles ? tileSums[i] : 0, total;
+    u64 ex = block_excl_scan64(v, &total, sm);
+    if (i < numTiles) tileSums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *totalOut = carry;
+}
+template <class F> __global__ void __launch_bounds__(256) k_scan64_apply(F in, u64* __restrict__ out, const u64* __restrict__ tileOffsets, size_t n) {
+  __shared__ u64 sm[9];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  u64 v[SCAN_ITEMS]; u64 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in(base + k) : 0; s += v[k]; }
+  u64 total; u64 ex = block_excl_scan64(s, &total, sm) + tileOffsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+}
+#endif
+template <class F> inline void scan_exclusive64(Ctx& c, ScanTemp& t, const F& in, u64* out, size_t n) {
+#ifdef AMG_EMU
+  u64 acc = 0; for (size_t i = 0; i < n; i++) { u64 v = in(i); out[i] = acc; acc += v; } out[n] = acc; c.launches += 3;
+#else
+  if (n == 0) { dev_memset(c, out, 0, sizeof(u64)); return; }
+  size_t numTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  t.tiles64.ensure(c, numTiles + 1);
+  k_scan64_reduce<F><<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, t.tiles64.p, n);
+  k_scan64_tiles<<<1, SCAN_THREADS, 0, c.stream>>>(t.tiles64.p, numTiles, out + n);
+  k_scan64_apply<F><<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, out, t.tiles64.p, n);
   CUDA_CHECK(cudaGetLastError());
   c.launches += 3;
 #endif

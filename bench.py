@@ -209,6 +209,10 @@ def main():
         cpu = {'value': ts.n_ops / dt, 'unit': 'ops/s', 'cores': 1, 'kind': 'port',
                'sample': 'first %d ops of the same C3 workload, oracle restatement of backend/new.js (not V8), %.1f s' % (ts.n_ops, dt)}
 
+    if rank == 0 and os.environ.get('AMG_BENCH_MARKS'):
+        buf = C.create_string_buffer(4096)
+        L.amg_debug_marks(doc.h, buf, 4096)
+        print('marks:', buf.value.decode(), file=sys.stderr)
     if rank == 0:
         clocks = sampler.summary()
         print(json.dumps({

@@ -109,6 +109,8 @@ int amg_debug_dump_ops(amg_backend* b, uint64_t** rows_out, size_t* n, uint64_t*
  * patch groups+props, list index, edits+copy-out, heads+commit), [12..23] host wall-clock marks (ms since the call started) */
 int amg_last_timings(amg_backend* b, float* ms_out, int n);
 uint64_t amg_kernel_launches(amg_backend* b);
+/* labelled host wall-clock marks of the last applyChanges call ("label=ms ..."), development aid */
+size_t amg_debug_marks(amg_backend* b, char* buf, size_t cap);
 void amg_free_mem(void* p);
 /* device-only re-run of the decode kernels over the last batch (inputs resident in HBM), for the roofline measurement */
 int amg_bench_decode(amg_backend* b, int iters, float* ms_sha, float* ms_parse, float* ms_decode, uint64_t* algo_bytes, amg_error* err);
