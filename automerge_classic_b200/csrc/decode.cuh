@@ -206,6 +206,14 @@ HD void sha256_compress(u32* h, u32* w, const u32* K) {
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
 
+// lists the DEFLATEd changes (chunk type 2, columnar.js:742) of a bulk batch so that the host can inflate just those
+struct DeflateScanKernel {
+  const u8* arena; const u32* chOff; const u32* chLen; u64* counter; u32* list;
+  HD void operator()(size_t c) const {
+    const u8* p = arena + chOff[c];
+    if (chLen[c] > 8 && p[8] == 2 && p[0] == 0x85) list[atomic_add(counter, (u64)1)] = (u32)c;
+  }
+};
 // hashes arena[off+8 .. off+len) of every change; writes 32-byte digests; checks magic + checksum
 struct ShaKernel {
   const u8* arena; const u32* chOff; const u32* chLen; u8* hashOut /* [n][32] */; u64* errWord; const u32* subset /* optional: only these changes */; u32* deflList;
@@ -213,7 +221,7 @@ struct ShaKernel {
     const size_t c = subset ? subset[ci] : ci;
     const u8* p = arena + chOff[c]; const u32 len = chLen[c];
     if (len > 8 && p[8] == 2 && p[0] == 0x85) {   // DEFLATEd change (columnar.js:742): listed for the host, which inflates it and re-points this entry
-      if (deflList) deflList[atomic_add(errWord + 1, (u64)1)] = (u32)c; else raise(errWord, KE_CHUNK_TYPE, c);
+      if (!deflList) raise(errWord, KE_CHUNK_TYPE, c);   // with a list: skipped here, hashed again once the host has inflated it
       return;
     }
     if (len < 10 || p[0] != 0x85 || p[1] != 0x6f || p[2] != 0x4a || p[3] != 0x83) { raise(errWord, KE_MAGIC, c); return; }

@@ -143,39 +143,41 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   dev_memset(ctx, errWord.p, 0, 16);
   hashes.ensure(ctx, (numApplied + B) * 32 + 64, numApplied * 32);
   deflList.ensure(ctx, B + 1);
-  foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr, uploaded ? deflList.p : nullptr});
   std::vector<u32> deflIdx;
-  if (uploaded) {
-    u64 ew[2]; d2h(ctx, ew, errWord.p, 16); sync(ctx);
-    if (ew[1]) {
-      // DEFLATEd changes inside a bulk batch: inflate just those on host threads (zlib, as columnar.js:813-823 does with pako),
-      // append the inflated bytes behind the batch and re-point the entries; their original bytes stay where they are.
-      const size_t nd = (size_t)ew[1]; deflIdx.resize(nd); d2h(ctx, deflIdx.data(), deflList.p, nd * 4); sync(ctx);
-      std::sort(deflIdx.begin(), deflIdx.end());
-      std::vector<std::string> inflated(nd); std::string firstError;
-      { unsigned nt = std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency())); if (nd < 64) nt = 1;
-        std::vector<std::thread> ts; std::vector<std::string> errs(nt);
-        for (unsigned t = 0; t < nt; t++) ts.emplace_back([&, t] { try { for (size_t k = t; k < nd; k += nt) { const u32 b = deflIdx[k]; inflated[k] = inflateChange(blob + offsets[b], (size_t)(offsets[b + 1] - offsets[b])); } } catch (std::exception& e) { errs[t] = e.what(); } });
-        for (auto& th : ts) th.join();
-        for (auto& e : errs) if (!e.empty() && firstError.empty()) firstError = e; }
-      if (!firstError.empty()) throw Error(AMG_ERR_RANGE, firstError);
-      if (mirrorThread.joinable()) mirrorThread.join();   // the mirror may have to grow
-      size_t extra = 0; for (auto& x : inflated) extra += x.size();
-      if ((u64)cur + extra + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
-      const size_t extraStart = cur; hostArena.resize(cur + extra); batchOriginal.assign(B, HostChange{0, 0});
-      std::vector<u32> triples(3 * nd);
-      for (size_t k = 0; k < nd; k++) {
-        const u32 b = deflIdx[k]; batchOriginal[b] = batch[b];
-        memcpy(hostArena.data() + cur, inflated[k].data(), inflated[k].size());
-        batch[b] = HostChange{(u32)cur, (u32)inflated[k].size()}; triples[3 * k] = b; triples[3 * k + 1] = batch[b].off; triples[3 * k + 2] = batch[b].len; cur += inflated[k].size();
-      }
-      arena.ensure(ctx, cur + 64, extraStart); h2d(ctx, arena.p + extraStart, hostArena.data() + extraStart, cur - extraStart); dev_memset(ctx, arena.p + cur, 0, 64);
-      patchTriples.ensure(ctx, 3 * nd); h2d(ctx, patchTriples.p, triples.data(), triples.size() * 4);
-      foreach(ctx, nd, PatchPairsKernel{patchTriples.p, chOff.p, chLen.p});
-      h2d(ctx, deflList.p, deflIdx.data(), nd * 4);
-      foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, deflList.p, nullptr});
-      sync(ctx);
+  if (uploaded) {   // which changes of the bulk batch are DEFLATEd? (one byte per change; the host then inflates only those)
+    foreach(ctx, B, DeflateScanKernel{arena.p, chOff.p, chLen.p, errWord.p + 1, deflList.p});
+    u64 nd64 = 0; d2h(ctx, &nd64, errWord.p + 1, 8); sync(ctx);
+    if (nd64) { deflIdx.resize((size_t)nd64); d2h(ctx, deflIdx.data(), deflList.p, (size_t)nd64 * 4); sync(ctx); }
+  }
+  // SHA-256 of every change runs on the GPU while the host inflates (zlib, as columnar.js:813-823 does with pako)
+  foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr, uploaded ? deflList.p : nullptr});
+  if (!deflIdx.empty()) {
+    const size_t nd = deflIdx.size();
+    std::sort(deflIdx.begin(), deflIdx.end());
+    std::vector<std::string> inflated(nd); std::string firstError;
+    { unsigned nt = std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency())); if (nd < 64) nt = 1;
+      std::vector<std::thread> ts; std::vector<std::string> errs(nt);
+      for (unsigned t = 0; t < nt; t++) ts.emplace_back([&, t] { try { for (size_t k = t; k < nd; k += nt) { const u32 b = deflIdx[k]; inflated[k] = inflateChange(blob + offsets[b], (size_t)(offsets[b + 1] - offsets[b])); } } catch (std::exception& e) { errs[t] = e.what(); } });
+      for (auto& th : ts) th.join();
+      for (auto& e : errs) if (!e.empty() && firstError.empty()) firstError = e; }
+    if (!firstError.empty()) throw Error(AMG_ERR_RANGE, firstError);
+    if (mirrorThread.joinable()) mirrorThread.join();   // the mirror may have to grow
+    size_t extra = 0; for (auto& x : inflated) extra += x.size();
+    if ((u64)cur + extra + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
+    // the inflated bytes go behind the batch and the entries are re-pointed; the original bytes stay where they are
+    const size_t extraStart = cur; hostArena.resize(cur + extra); batchOriginal.assign(B, HostChange{0, 0});
+    std::vector<u32> triples(3 * nd);
+    for (size_t k = 0; k < nd; k++) {
+      const u32 b = deflIdx[k]; batchOriginal[b] = batch[b];
+      memcpy(hostArena.data() + cur, inflated[k].data(), inflated[k].size());
+      batch[b] = HostChange{(u32)cur, (u32)inflated[k].size()}; triples[3 * k] = b; triples[3 * k + 1] = batch[b].off; triples[3 * k + 2] = batch[b].len; cur += inflated[k].size();
     }
+    arena.ensure(ctx, cur + 64, extraStart); h2d(ctx, arena.p + extraStart, hostArena.data() + extraStart, cur - extraStart); dev_memset(ctx, arena.p + cur, 0, 64);
+    patchTriples.ensure(ctx, 3 * nd); h2d(ctx, patchTriples.p, triples.data(), triples.size() * 4);
+    foreach(ctx, nd, PatchPairsKernel{patchTriples.p, chOff.p, chLen.p});
+    h2d(ctx, deflList.p, deflIdx.data(), nd * 4);
+    foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, deflList.p, nullptr});
+    sync(ctx);   // `triples` / `deflIdx` are pageable host memory: keep them alive until the copies are done
   }
   timer.mark(); hostMark();
   meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
@@ -244,12 +246,13 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       sync(ctx);
       std::vector<u32> order(fresh); for (u32 i = 0; i < fresh; i++) order[i] = i;
       std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return recs[a].first < recs[b].first; });
-      std::vector<u32> ids(fresh), nums(fresh);
+      std::vector<u32> ids(fresh), nums(fresh); actorsNow.reserve(actorsNow.size() + fresh);   // async copies target the strings: no reallocation below
       for (u32 k = 0; k < fresh; k++) {
         const ActorSlot& r = recs[order[k]]; ids[k] = slotsH[order[k]]; nums[k] = (u32)actorsNow.size();
-        std::string idBytes(r.repLen, '\0'); d2h(ctx, &idBytes[0], arena.p + r.repOff, r.repLen); sync(ctx);   // from the device copy: the host mirror may still be filling
-        actorsNow.push_back(idBytes); actorRepNow.emplace_back(r.repOff, r.repLen);
+        actorsNow.emplace_back(r.repLen, '\0'); d2h(ctx, &actorsNow.back()[0], arena.p + r.repOff, r.repLen);   // from the device copy: the host mirror may still be filling
+        actorRepNow.emplace_back(r.repOff, r.repLen);
       }
+      sync(ctx);
       if (actorsNow.size() > 65535) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 65535 actors in one document");
       sortVals.ensure(ctx, 2 * fresh); h2d(ctx, sortVals.p, ids.data(), fresh * 4); h2d(ctx, sortVals.p + fresh, nums.data(), fresh * 4);
       foreach(ctx, fresh, SetActorNumKernel{actorSlots.p, sortVals.p, sortVals.p + fresh});
