@@ -28,6 +28,7 @@ struct amg_backend {
 
   void ensureGraph() {
     Engine& e = eng;
+    if (!e.haveHashGraph) throw amg::Error(AMG_UNSUPPORTED, "amgpu: change history of a loaded document is not reconstructed (decodeDocument / computeHashGraph, new.js:1887-1912, not built)");
     if (g.known == e.numApplied) return;
     const size_t from = g.known, to = e.numApplied;
     std::vector<u8> hs((to - from) * 32); d2h(e.ctx, hs.data(), e.hashes.p + from * 32, hs.size()); sync(e.ctx);
@@ -76,6 +77,12 @@ amg_backend* amg_init(int cuda_device, amg_error* err) {
   catch (std::exception& e) { setErr(err, AMG_INTERNAL_ERROR, e.what()); return nullptr; }
 }
 void amg_free(amg_backend* b) { delete b; }
+amg_backend* amg_load(int cuda_device, const uint8_t* data, size_t len, amg_error* err) {
+  amg_backend* b = nullptr;
+  try { b = new amg_backend(cuda_device); b->eng.loadDocument(data, len); return b; }
+  catch (amg::Error& e) { setErr(err, e.code, e.what()); delete b; return nullptr; }
+  catch (std::exception& e) { setErr(err, AMG_INTERNAL_ERROR, e.what()); delete b; return nullptr; }
+}
 int amg_reset(amg_backend* b, amg_error* err) { AMG_GUARD(b->g = HostGraph(); b->eng.reset(); return 0;) }
 int amg_reserve(amg_backend* b, size_t arena_bytes, amg_error* err) { AMG_GUARD(b->eng.hostArena.reserve(arena_bytes); b->eng.arena.ensure(b->eng.ctx, arena_bytes + 64, b->eng.arenaLen); return 0;) }
 
@@ -92,7 +99,7 @@ amg_backend* amg_clone(amg_backend* src, amg_error* err) {
     d2d(c, d.doc.valLen.p, s.doc.valLen.p, s.numRows * 4); d2d(c, d.doc.valOff.p, s.doc.valOff.p, s.numRows * 4); d2d(c, d.doc.time.p, s.doc.time.p, s.numRows * 4);
     d.numSucc = s.numSucc; d.succOff.ensure(c, s.numRows + 2); d2d(c, d.succOff.p, s.succOff.p, (s.numRows + 1) * 4); d.succ.ensure(c, s.numSucc + 1); d2d(c, d.succ.p, s.succ.p, s.numSucc * 8);
     d.actorIds = s.actorIds; d.actorRep = s.actorRep; d.clock = s.clock; d.heads = s.heads; d.headIdx = s.headIdx; d.changes = s.changes; d.deflatedOriginal = s.deflatedOriginal;
-    d.queue = s.queue; d.queueOriginal = s.queueOriginal; d.maxOp = s.maxOp;
+    d.queue = s.queue; d.queueOriginal = s.queueOriginal; d.maxOp = s.maxOp; d.haveHashGraph = s.haveHashGraph;
     while (d.actorCap < 2 * (d.actorIds.size() + 16)) d.actorCap *= 2;
     d.actorSlots.ensure(c, d.actorCap); d.rebuildActorTable();
     sync(c);

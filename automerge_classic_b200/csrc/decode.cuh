@@ -262,6 +262,31 @@ struct ShaKernel {
   }
 };
 
+// number of values in an RLE column (record-level: runs are not expanded); *err receives a KErr
+HD u32 rle_count_values(const u8* arena, u32 off, u32 end, u32* err) {
+  RleReader a(arena, off, end, 0); u64 n = 0;
+  while (!a.done() && !a.r.err) {
+    long long v; u32 o, l; a.next(v, o, l);
+    u64 adv = 1;
+    if (a.state != 2 && a.count > 0) { adv += (u64)a.count; a.count = 0; }
+    n += adv;
+  }
+  *err = a.r.err; if (n > 0xfffffffeULL) { *err = KE_TOO_LARGE; n = 0; }
+  return (u32)n;
+}
+// sum of the first `limit` values of an RLE uint column (nulls count as 0)
+HD u64 rle_sum_values(const u8* arena, u32 off, u32 end, u32 limit, u32* err) {
+  RleReader pn(arena, off, end, 0); u32 seen = 0; u64 sum = 0;
+  while (!pn.done() && !pn.r.err && seen < limit) {
+    long long n = 0; u32 o, l; const bool nn = pn.next(n, o, l);
+    u64 adv = 1;
+    if (pn.state != 2 && pn.count > 0) { adv += (u64)pn.count; if (seen + adv > limit) adv = limit - seen; pn.count -= (long long)(adv - 1); }
+    if (nn) sum += (u64)n * adv;
+    seen += (u32)adv;
+  }
+  *err = pn.r.err; return sum;
+}
+
 // ---------------------------------------------------------------- header / column directory parse, one thread per change
 struct ParseKernel {
   const u8* arena; const u32* chOff; const u32* chLen; size_t numChanges;
@@ -302,30 +327,10 @@ struct ParseKernel {
     m.dirOff = dirPos; m.dataOff = dataPos;
     m.extraOff = dataPos + (u32)total; m.extraLen = off + len - m.extraOff;
     // count ops (values of the action column) and preds (sum of the predNum column)
-    u32 nOps = 0; u64 nPreds = 0; u32 kerr = 0;
-    {
-      RleReader a(arena, dataPos + actOff, dataPos + actOff + actLen, 0);
-      // record-level count: no need to touch every value of a repetition / null run
-      while (!a.done() && !a.r.err) {
-        long long n; u32 o, l; a.next(n, o, l);
-        u64 adv = 1;
-        if (a.state != 2 && a.count > 0) { adv += (u64)a.count; a.count = 0; }
-        nOps += (u32)adv;
-      }
-      kerr = a.r.err;
-    }
-    if (!kerr) {
-      RleReader pn(arena, dataPos + pnOff, dataPos + pnOff + pnLen, 0);
-      u32 seen = 0;
-      while (!pn.done() && !pn.r.err && seen < nOps) {
-        long long n = 0; u32 o, l; const bool nn = pn.next(n, o, l);
-        u64 adv = 1;
-        if (pn.state != 2 && pn.count > 0) { adv += (u64)pn.count; if (seen + adv > nOps) adv = nOps - seen; pn.count -= (long long)(adv - 1); }
-        if (nn) nPreds += (u64)n * adv;
-        seen += (u32)adv;
-      }
-      kerr = pn.r.err;
-    }
+    u32 kerr = 0;
+    const u32 nOps = rle_count_values(arena, dataPos + actOff, dataPos + actOff + actLen, &kerr);
+    u64 nPreds = 0;
+    if (!kerr) nPreds = rle_sum_values(arena, dataPos + pnOff, dataPos + pnOff + pnLen, nOps, &kerr);
     if (kerr) { raise(errWord, kerr, c); meta[c] = m; return; }
     if (nPreds > 0x7fffffffULL) { raise(errWord, KE_TOO_LARGE, c); meta[c] = m; return; }
     m.nOps = nOps; m.nPreds = (u32)nPreds;

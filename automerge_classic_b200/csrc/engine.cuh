@@ -178,25 +178,28 @@ class Engine {
   // sort `perm` (row ids) by successive 64-bit fields produced by keyFn(field) ; stable LSD over fields
   void sortPairs(DBuf<u64>& keys, DBuf<u32>& vals, size_t n, int bits) { radix_sort_pairs(ctx, sortTmp, keys, vals, n, 0, bits); }
 
-  static std::string inflateChange(const u8* buf, size_t len) {
-    // reference columnar.js:813-823 (pako.inflateRaw -> zlib raw inflate); magic + checksum are kept
+  // reference columnar.js:813-823 (pako.inflateRaw -> zlib raw inflate); magic + checksum are kept. `zs` may be a reusable,
+  // already initialised stream (inflateInit2(.., -15)); it is reset, not re-allocated.
+  static std::string inflateChange(const u8* buf, size_t len, z_stream* reuse = nullptr) {
     ByteReader r(buf, 9, (u32)len); const u64 clen = r.uleb();
     if (r.err || r.pos + clen > len) throw Error(AMG_ERR_RANGE, "buffer ended with incomplete number");
-    z_stream zs; memset(&zs, 0, sizeof(zs));
-    if (inflateInit2(&zs, -15) != Z_OK) throw Error(AMG_ERR_INTERNAL, "inflateInit failed");
-    std::string out; out.resize(std::max<size_t>(clen * 6, 1024));
-    zs.next_in = (Bytef*)(buf + r.pos); zs.avail_in = (uInt)clen; size_t produced = 0;
+    z_stream local; z_stream* zs = reuse;
+    if (!zs) { memset(&local, 0, sizeof(local)); if (inflateInit2(&local, -15) != Z_OK) throw Error(AMG_ERR_INTERNAL, "inflateInit failed"); zs = &local; }
+    else inflateReset(zs);
+    struct End { z_stream* z; bool own; ~End() { if (own) inflateEnd(z); } } end{zs, !reuse};
+    std::string out; out.resize(std::max<size_t>(clen * 4, 512));
+    zs->next_in = (Bytef*)(buf + r.pos); zs->avail_in = (uInt)clen; size_t produced = 0;
     while (true) {
-      zs.next_out = (Bytef*)out.data() + produced; zs.avail_out = (uInt)(out.size() - produced);
-      int rc = inflate(&zs, Z_NO_FLUSH); produced = out.size() - zs.avail_out;
+      zs->next_out = (Bytef*)out.data() + produced; zs->avail_out = (uInt)(out.size() - produced);
+      int rc = inflate(zs, Z_NO_FLUSH); produced = out.size() - zs->avail_out;
       if (rc == Z_STREAM_END) break;
-      if (rc != Z_OK && rc != Z_BUF_ERROR) { inflateEnd(&zs); throw Error(AMG_ERR_RANGE, "invalid deflate data"); }
-      if (zs.avail_out == 0) out.resize(out.size() * 2); else if (zs.avail_in == 0) { inflateEnd(&zs); throw Error(AMG_ERR_RANGE, "unexpected end of deflate data"); }
+      if (rc != Z_OK && rc != Z_BUF_ERROR) throw Error(AMG_ERR_RANGE, "invalid deflate data");
+      if (zs->avail_out == 0) out.resize(out.size() * 2); else if (zs->avail_in == 0) throw Error(AMG_ERR_RANGE, "unexpected end of deflate data");
     }
-    inflateEnd(&zs); out.resize(produced);
-    std::string res((const char*)buf, 8); res.push_back(1);
-    u64 v = out.size(); do { u8 b = v & 0x7f; v >>= 7; if (v) b |= 0x80; res.push_back((char)b); } while (v);
-    res += out; return res;
+    // header: magic + checksum (8 bytes), chunk type 1, LEB128 length, then the inflated body
+    u8 hdr[24]; memcpy(hdr, buf, 8); hdr[8] = 1; size_t hl = 9; u64 v = produced; do { u8 b = v & 0x7f; v >>= 7; if (v) b |= 0x80; hdr[hl++] = b; } while (v);
+    std::string res; res.reserve(hl + produced); res.append((const char*)hdr, hl); res.append(out.data(), produced);
+    return res;
   }
 
   // ---------------------------------------------------------------- applyChanges
@@ -209,6 +212,8 @@ class Engine {
   void fillPatchHeader(PatchOut& out);
   void finishPatch(PatchOut& out);
   void reset();
+  void loadDocument(const u8* buf, size_t len);
+  bool haveHashGraph = true;   // false after Backend.load: change history (hashes, bytes) is not reconstructed (new.js:1887-1912)
   void benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes);
   void decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* hashesOut, u32* nOpsOut, u32** rowsOut, size_t* totalOps);
   size_t lastB = 0, lastM = 0, lastP = 0, lastBytes = 0;

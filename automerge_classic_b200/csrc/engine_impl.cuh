@@ -157,7 +157,10 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     std::vector<std::string> inflated(nd); std::string firstError;
     { unsigned nt = std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency())); if (nd < 64) nt = 1;
       std::vector<std::thread> ts; std::vector<std::string> errs(nt);
-      for (unsigned t = 0; t < nt; t++) ts.emplace_back([&, t] { try { for (size_t k = t; k < nd; k += nt) { const u32 b = deflIdx[k]; inflated[k] = inflateChange(blob + offsets[b], (size_t)(offsets[b + 1] - offsets[b])); } } catch (std::exception& e) { errs[t] = e.what(); } });
+      for (unsigned t = 0; t < nt; t++) ts.emplace_back([&, t] {
+        z_stream zs; memset(&zs, 0, sizeof(zs)); if (inflateInit2(&zs, -15) != Z_OK) { errs[t] = "inflateInit failed"; return; }
+        try { for (size_t k = t; k < nd; k += nt) { const u32 b = deflIdx[k]; inflated[k] = inflateChange(blob + offsets[b], (size_t)(offsets[b + 1] - offsets[b]), &zs); } } catch (std::exception& e) { errs[t] = e.what(); }
+        inflateEnd(&zs); });
       for (auto& th : ts) th.join();
       for (auto& e : errs) if (!e.empty() && firstError.empty()) firstError = e; }
     if (!firstError.empty()) throw Error(AMG_ERR_RANGE, firstError);
@@ -215,7 +218,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     appliedH.resize(B); primaryH.resize(B); appRankH.resize(B);
     d2h(ctx, appliedH.data(), applied.p, B); d2h(ctx, primaryH.data(), primary.p, B * 4); d2h(ctx, appRankH.data(), appRank.p, B * 4); sync(ctx);
   }
-  auto isApplied = [&](size_t b) { return appliedH.empty() ? true : appliedH[b] != 0; };
+  if (!haveHashGraph && numNew < B) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: a change depends on history that was not reconstructed after Backend.load (computeHashGraph, new.js:1887-1912, not built)");
   // the queue after this call: every batch entry whose hash is still not applied (new.js:1569-1570, 1832)
   std::vector<HostChange> newQueue, newQueueOriginal;
   if (numNew < B) for (size_t b = 0; b < B; b++) {
@@ -716,6 +719,125 @@ inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* 
   u32* rows = (u32*)malloc(sizeof(u32) * 12 * (M + 1));
   for (int k = 0; k < 12; k++) d2h(ctx, rows + (size_t)k * M, cols[k]->p, M * 4);
   sync(ctx); *rowsOut = rows; *totalOps = M; lastB = 0;
+}
+
+}  // namespace amg
+
+namespace amg {
+
+inline void host_sha256(const u8* data, size_t len, u8 out[32]) {
+  u32 h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  std::vector<u8> tail(data + (len / 64) * 64, data + len); tail.push_back(0x80);
+  while (tail.size() % 64 != 56) tail.push_back(0);
+  for (int i = 7; i >= 0; i--) tail.push_back((u8)(((u64)len * 8) >> (8 * i)));
+  auto run = [&](const u8* p, size_t n) { for (size_t o = 0; o < n; o += 64) { u32 w[16]; for (int i = 0; i < 16; i++) w[i] = (u32)p[o + 4 * i] << 24 | (u32)p[o + 4 * i + 1] << 16 | (u32)p[o + 4 * i + 2] << 8 | p[o + 4 * i + 3]; sha256_compress(h, w, SHA_K); } };
+  run(data, (len / 64) * 64); run(tail.data(), tail.size());
+  for (int i = 0; i < 8; i++) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }
+}
+inline std::string inflateRawBytes(const u8* p, size_t n) {
+  z_stream zs; memset(&zs, 0, sizeof(zs));
+  if (inflateInit2(&zs, -15) != Z_OK) throw Error(AMG_ERR_INTERNAL, "inflateInit failed");
+  std::string out; out.resize(std::max<size_t>(n * 6, 1024)); zs.next_in = (Bytef*)p; zs.avail_in = (uInt)n; size_t produced = 0;
+  while (true) {
+    zs.next_out = (Bytef*)out.data() + produced; zs.avail_out = (uInt)(out.size() - produced);
+    int rc = inflate(&zs, Z_NO_FLUSH); produced = out.size() - zs.avail_out;
+    if (rc == Z_STREAM_END) break;
+    if (rc != Z_OK && rc != Z_BUF_ERROR) { inflateEnd(&zs); throw Error(AMG_ERR_RANGE, "invalid deflate data"); }
+    if (zs.avail_out == 0) out.resize(out.size() * 2); else if (zs.avail_in == 0) { inflateEnd(&zs); throw Error(AMG_ERR_RANGE, "unexpected end of deflate data"); }
+  }
+  inflateEnd(&zs); out.resize(produced); return out;
+}
+
+// Backend.load(data) = new BackendDoc(buffer) (reference new.js:1709-1750): the document chunk's op columns are already in
+// document order with succ lists, so loading = container check + column decode + one finalize pass. The container
+// checksum (one SHA-256 over the whole chunk: inherently serial) and the DEFLATE of large columns are host pre-passes,
+// as in SURVEY.md §2 row 12; column expansion and everything downstream run on the device.
+inline void Engine::loadDocument(const u8* buf, size_t len) {
+  if (numApplied != 0 || numRows != 0) throw Error(AMG_ERR_INTERNAL, "load needs a fresh backend");
+  // columnar.js:688-708 decodeContainerHeader
+  if (len < 10 || buf[0] != 0x85 || buf[1] != 0x6f || buf[2] != 0x4a || buf[3] != 0x83) throw Error(AMG_ERR_RANGE, "Data does not begin with magic bytes 85 6f 4a 83");
+  ByteReader r(buf, 8, (u32)len); const u32 chunkType = buf[8]; r.pos = 9; const u64 chunkLen = r.uleb();
+  if (r.err || (u64)r.pos + chunkLen > len) throw Error(AMG_ERR_RANGE, "buffer ended with incomplete number");
+  u8 digest[32]; host_sha256(buf + 8, r.pos + (size_t)chunkLen - 8, digest);
+  if (memcmp(digest, buf + 4, 4) != 0) throw Error(AMG_ERR_RANGE, "checksum does not match data");
+  if ((u64)r.pos + chunkLen != len) throw Error(AMG_ERR_RANGE, "Encoded document has trailing data");
+  if (chunkType != 0) throw Error(AMG_ERR_RANGE, "Unexpected chunk type: " + std::to_string(chunkType));
+  // columnar.js:1006-1038 decodeDocumentHeader
+  std::vector<std::string> actors; const u64 numActors = r.uleb();
+  for (u64 i = 0; i < numActors && !r.err; i++) { const u64 l = r.uleb(); if ((u64)r.pos + l > len) { r.err = KE_TRUNCATED; break; } actors.emplace_back((const char*)buf + r.pos, l); r.skip(l); }
+  std::vector<std::array<u8, 32>> hs; const u64 numHeads = r.uleb();
+  for (u64 i = 0; i < numHeads && !r.err; i++) { if ((u64)r.pos + 32 > len) { r.err = KE_TRUNCATED; break; } std::array<u8, 32> h; memcpy(h.data(), buf + r.pos, 32); hs.push_back(h); r.skip(32); }
+  struct ColInfo { u32 id; u64 len; std::string data; };
+  auto readInfo = [&](std::vector<ColInfo>& cols) {
+    const u64 n = r.uleb(); long long last = -1;
+    for (u64 i = 0; i < n && !r.err; i++) { const u64 id = r.uleb(), l = r.uleb(); if (last >= 0 && ((u32)id & ~8u) <= ((u32)last & ~8u)) throw Error(AMG_ERR_RANGE, "Columns must be in ascending order"); last = (long long)id; cols.push_back({(u32)id, l, std::string()}); }
+  };
+  std::vector<ColInfo> changeCols, opCols; readInfo(changeCols); readInfo(opCols);
+  auto readData = [&](std::vector<ColInfo>& cols) {
+    for (auto& c : cols) {
+      if (r.err || (u64)r.pos + c.len > len) throw Error(AMG_ERR_RANGE, "subarray exceeds buffer size");
+      if (c.id & 8) { c.data = inflateRawBytes(buf + r.pos, (size_t)c.len); c.id ^= 8; } else c.data.assign((const char*)buf + r.pos, (size_t)c.len);
+      r.skip(c.len);
+    }
+  };
+  readData(changeCols); readData(opCols);
+  if (r.err) throw Error(AMG_ERR_RANGE, "buffer ended with incomplete number");
+  std::vector<u32> headsIndexes; if (!r.done()) for (u64 i = 0; i < numHeads; i++) headsIndexes.push_back((u32)r.uleb());
+  if (actors.size() > 65535) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 65535 actors in one document");
+  // ---- change metadata: clock (new.js:1645-1675 readDocumentChanges). Two small columns, decoded with the same readers on the host.
+  std::vector<u64> clk(actors.size(), 0); size_t numChanges = 0;
+  {
+    const std::string* actorCol = nullptr; const std::string* seqCol = nullptr;
+    for (auto& c : changeCols) { if (c.id == 0x01) actorCol = &c.data; if (c.id == 0x03) seqCol = &c.data; }
+    static const std::string empty;
+    const std::string& ac = actorCol ? *actorCol : empty; const std::string& sc = seqCol ? *seqCol : empty;
+    RleReader ar((const u8*)ac.data(), 0, (u32)ac.size(), 0), sr((const u8*)sc.data(), 0, (u32)sc.size(), 1); long long seqAcc = 0;
+    while (!ar.done()) {
+      long long a = 0, d = 0; u32 o, l; const bool an = ar.next(a, o, l), sn = sr.next(d, o, l);
+      if (ar.r.err || sr.r.err) throw Error(AMG_ERR_RANGE, "malformed change metadata columns");
+      if (!an || (u64)a >= actors.size()) throw Error(AMG_ERR_RANGE, "actor index out of range");
+      if (sn) seqAcc += d;
+      const u64 seq = sn ? (u64)seqAcc : 0;
+      if (seq != 1 && seq != clk[a] + 1) throw Error(AMG_ERR_RANGE, "Expected seq " + std::to_string(clk[a] + 1) + ", got " + std::to_string(seq) + " for actor " + hex_of((const u8*)actors[a].data(), actors[a].size()));
+      clk[a] = seq; numChanges++;
+    }
+  }
+  if (!headsIndexes.empty() && headsIndexes.size() != hs.size()) headsIndexes.clear();
+  if (headsIndexes.empty()) { if (hs.size() == 1) headsIndexes.push_back((u32)(numChanges ? numChanges - 1 : 0)); else if (!hs.empty()) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: document without head indexes and several heads (needs decodeDocument, not built)"); }
+  // ---- stage actor ids and op columns in the arena
+  static const u32 DOC_IDS[16] = {0x01, 0x02, 0x11, 0x13, 0x15, 0x21, 0x23, 0x34, 0x42, 0x56, 0x57, 0x61, 0x63, 0x80, 0x81, 0x83};
+  DocCols dc; memset(&dc, 0, sizeof(dc));
+  hostArena.resize(0); std::vector<std::pair<u32, u32>> reps;
+  for (auto& a : actors) { reps.emplace_back((u32)hostArena.size(), (u32)a.size()); hostArena.append(a.data(), a.size()); }
+  for (auto& c : opCols) for (int k = 0; k < 16; k++) if (c.id == DOC_IDS[k]) { dc.off[k] = (u32)hostArena.size(); dc.len[k] = (u32)c.data.size(); hostArena.append(c.data.data(), c.data.size()); }
+  const size_t cur = hostArena.size();
+  if (cur + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
+  arena.ensure(ctx, cur + 64); h2d(ctx, arena.p, hostArena.data(), cur); dev_memset(ctx, arena.p + cur, 0, 64);
+  dev_memset(ctx, errWord.p, 0, 16); dev_memset(ctx, flagWord.p, 0, 16);
+  foreach(ctx, 1, DocCountKernel{arena.p, dc, flagWord.p, errWord.p});
+  u32 cnt[2]; d2h(ctx, cnt, flagWord.p, 8); sync(ctx); checkErr(actors);
+  const size_t N = cnt[0], S = cnt[1];
+  if (N >= (1u << 29)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 2^29 document rows");
+  for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff, &o_change, &o_time}) b->ensure(ctx, N + 1);
+  r_predActor.ensure(ctx, S + 1); r_predCtr.ensure(ctx, S + 1);
+  RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
+  foreach(ctx, 16, DocColumnKernel{arena.p, dc, (u32)N, (u32)S, raw, o_change.p, o_time.p, errWord.p});
+  doc.ensure(ctx, N + 1); succOff.ensure(ctx, N + 2); succ.ensure(ctx, S + 1);
+  DBuf<u64>& maxOpD = pairSucc; maxOpD.ensure(ctx, 1); dev_memset(ctx, maxOpD.p, 0, 8);
+  foreach(ctx, N, DocFinalizeKernel{raw, o_change.p, o_time.p, (u32)actors.size(), doc.view(), succOff.p, succ.p, maxOpD.p, errWord.p});
+  { const u32 s32 = (u32)S; h2d(ctx, succOff.p + N, &s32, 4); }
+  u64 mx = 0; d2h(ctx, &mx, maxOpD.p, 8); sync(ctx); checkErr(actors);
+  // ---- change history placeholders: only the head hashes are known (new.js:1727-1739)
+  hashes.ensure(ctx, numChanges * 32 + 64); dev_memset(ctx, hashes.p, 0, numChanges * 32 + 64);
+  for (size_t i = 0; i < hs.size(); i++) { if (headsIndexes[i] >= numChanges) throw Error(AMG_ERR_RANGE, "head index out of range"); h2d(ctx, hashes.p + (size_t)headsIndexes[i] * 32, hs[i].data(), 32); }
+  sync(ctx);
+  numRows = N; numSucc = S; numApplied = numChanges; arenaLen = cur; maxOp = mx; actorIds = actors; actorRep = reps; clock = clk;
+  heads = hs; headIdx = headsIndexes;
+  { std::vector<size_t> o(heads.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i; std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return hs[a] < hs[b]; });
+    for (size_t i = 0; i < o.size(); i++) { heads[i] = hs[o[i]]; headIdx[i] = headsIndexes[o[i]]; } }
+  changes.assign(numChanges, HostChange{0, 0}); haveHashGraph = false;
+  while (actorCap < 2 * (actorIds.size() + 16)) actorCap *= 2;
+  actorSlots.ensure(ctx, actorCap); rebuildActorTable();
 }
 
 }  // namespace amg

@@ -61,6 +61,60 @@ struct CompactKernel { const u32* flag; const u32* slot; u32* out; HD void opera
 struct HashGatherKernel { const u8* src; const u8* applied; const u32* appRank; u8* dst; HD void operator()(size_t b) const { if (!applied[b]) return; const u64* s = reinterpret_cast<const u64*>(src + b * 32); u64* d = reinterpret_cast<u64*>(dst + (size_t)appRank[b] * 32); d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; } };
 struct SplitPairsKernel { const HostChange* pairs; u32* off; u32* len; HD void operator()(size_t b) const { off[b] = pairs[b].off; len[b] = pairs[b].len; } };
 struct PatchPairsKernel { const u32* triples; u32* off; u32* len; HD void operator()(size_t i) const { const u32 c = triples[3 * i]; off[c] = triples[3 * i + 1]; len[c] = triples[3 * i + 2]; } };
+// ---------------------------------------------------------------- Backend.load: document chunk -> document table (new.js:1709-1750)
+struct DocCols { u32 off[16]; u32 len[16]; };   // objActor,objCtr,keyActor,keyCtr,keyStr,idActor,idCtr,insert,action,valLen,valRaw,chldActor,chldCtr,succNum,succActor,succCtr
+struct DocCountKernel {   // thread 0: number of rows (action column), then sum of succNum
+  const u8* arena; DocCols c; u32* out /* [0] rows, [1] succ entries */; u64* errWord;
+  HD void operator()(size_t) const {
+    u32 err = 0; const u32 n = rle_count_values(arena, c.off[8], c.off[8] + c.len[8], &err);
+    u64 s = 0; if (!err) s = rle_sum_values(arena, c.off[13], c.off[13] + c.len[13], n, &err);
+    if (err) raise(errWord, err, 0); if (s > 0x7fffffffULL) { raise(errWord, KE_TOO_LARGE, 0); s = 0; }
+    out[0] = n; out[1] = (u32)s;
+  }
+};
+struct DocColumnKernel {   // one thread per document column; the change-column decoders are reused through a remapped row view
+  const u8* arena; DocCols c; u32 n, numSucc; RawRows rows; u32* idActor; u32* idCtr; u64* errWord;
+  HD void operator()(size_t k) const {
+    RawRows r = rows; int col = -1;
+    switch ((int)k) {
+      case 0: col = CX_OBJ_ACTOR; break; case 1: col = CX_OBJ_CTR; break; case 2: col = CX_KEY_ACTOR; break; case 3: col = CX_KEY_CTR; break; case 4: col = CX_KEY_STR; break;
+      case 5: col = CX_OBJ_ACTOR; r.objActor = idActor; break;      // idActor: plain RLE uint
+      case 6: col = CX_KEY_CTR; r.keyCtr = idCtr; break;            // idCtr: delta
+      case 7: col = CX_INSERT; break; case 8: col = CX_ACTION; break; case 9: col = CX_VAL_LEN; break;
+      case 13: col = CX_PRED_NUM; break; case 14: col = CX_PRED_ACTOR; break; case 15: col = CX_PRED_CTR; break;   // succ group == pred group layout
+      default: return;
+    }
+    u32 e;
+    if (c.len[k] == 0) { fill_absent_column(col, n, 0, 0, numSucc, r); e = 0; }
+    else e = decode_one_column(arena, col, n, 0, c.off[k], c.off[k] + c.len[k], c.off[10], c.len[10], 0, numSucc, r);
+    if (e) raise(errWord, e, k);
+  }
+};
+struct DocFinalizeKernel {
+  RawRows raw; const u32* idActor; const u32* idCtr; u32 numActors; DocRows d; u32* succOff; u64* succ; u64* maxOp; u64* errWord;
+  HD void operator()(size_t i) const {
+    bool bad = false;
+    auto actor = [&](u32 a) -> u32 { if (a >= numActors) { bad = true; return 0; } return a; };
+    d.id[i] = pack_id(idCtr[i], actor(idActor[i]));
+    const u32 oa = raw.objActor[i], oc = raw.objCtr[i];
+    d.obj[i] = (oc == NULL32 || oa == NULL32) ? 0 : pack_id(oc, actor(oa));
+    const u32 ka = raw.keyActor[i], kc = raw.keyCtr[i];
+    d.key[i] = (kc == NULL32 || kc == 0 || ka == NULL32) ? 0 : pack_id(kc, actor(ka));
+    d.keyStrOff[i] = raw.keyStrOff[i]; d.keyStrLen[i] = raw.keyStrLen[i];
+    const u32 act = raw.action[i];
+    d.flags[i] = (raw.insert[i] ? F_INSERT : 0) | ((act == NULL32 ? 0xffffu : (act > 0xfffe ? 0xfffeu : act)) << 8);
+    d.valLen[i] = raw.valLen[i] == NULL32 ? 0 : raw.valLen[i]; d.valOff[i] = raw.valOff[i]; d.time[i] = 0;
+    succOff[i] = raw.predOff[i];
+    u64 mx = idCtr[i];
+    for (u32 j = 0; j < raw.predNum[i]; j++) {
+      const u32 p = raw.predOff[i] + j; const u32 sc = raw.predCtr[p], sa = raw.predActor[p];
+      succ[p] = (sc == NULL32 || sa == NULL32) ? 0 : pack_id(sc, actor(sa));
+      if (sc != NULL32 && sc > mx) mx = sc;
+    }
+    if (mx > *maxOp) atomic_max(maxOp, mx);
+    if (bad) raise(errWord, KE_ACTOR_INDEX, i);
+  }
+};
 struct KeySlotInitKernel { KeySlot* s; HD void operator()(size_t i) const { s[i].hash = 0; s[i].rep = 0xffffffffu; s[i].rank = 0; } };
 struct InsertFlagKernel { DocRows w; u32* flag; HD void operator()(size_t r) const { flag[r] = (w.keyStrLen[r] == NULL32 && (w.flags[r] & F_INSERT)) ? 1u : 0u; } };
 struct GatherU32Kernel { const u32* src; const u32* idx; u32* out; HD void operator()(size_t i) const { out[i] = src[idx[i]]; } };

@@ -51,6 +51,8 @@ class Library:
         vp = C.c_void_p
         L.amg_init.restype = vp
         L.amg_init.argtypes = [C.c_int, vp]
+        L.amg_load.restype = vp
+        L.amg_load.argtypes = [C.c_int, vp, C.c_size_t, vp]
         L.amg_clone.restype = vp
         L.amg_clone.argtypes = [vp, vp]
         L.amg_free.argtypes = [vp]
@@ -247,12 +249,15 @@ class GpuBackendDoc:
         if _handle is not None:
             self.h = _handle
             return
-        if data is not None:
-            raise Unsupported(4, 'amgpu: Backend.load() of a saved document is not built yet (SURVEY.md §8 A9)')
         err = _ErrStruct()
-        h = L.amg_init(int(os.environ.get('AMG_DEVICE', device)), C.byref(err))
+        dev = int(os.environ.get('AMG_DEVICE', device))
+        if data is not None:
+            data = bytes(data)
+            h = L.amg_load(dev, data, C.c_size_t(len(data)), C.byref(err))
+        else:
+            h = L.amg_init(dev, C.byref(err))
         if not h:
-            raise AmgError(err.code, err.msg.decode('utf-8', 'replace'))
+            raise (Unsupported if err.code == 4 else AmgError)(err.code, err.msg.decode('utf-8', 'replace'))
         self.h = C.c_void_p(h)
 
     def __del__(self):

@@ -32,6 +32,8 @@ typedef struct { int code; char msg[512]; } amg_error;
 amg_backend* amg_init(int cuda_device, amg_error* err);
 /* Backend.clone() — backend/backend.js:12-14 (BackendDoc.clone, new.js:1773-1790) */
 amg_backend* amg_clone(amg_backend* b, amg_error* err);
+/* Backend.load(data) — backend/backend.js:104-107 -> new BackendDoc(buffer), new.js:1709-1750 (document chunk, type 0) */
+amg_backend* amg_load(int cuda_device, const uint8_t* data, size_t len, amg_error* err);
 /* Backend.free()  — backend/backend.js:16-19 */
 void amg_free(amg_backend* b);
 

@@ -105,3 +105,33 @@ def check_large_text(gpu_doc, oracle_mod, n):
     d = replay.deep_equal(replay.decode(pg), replay.decode(po))
     assert d is None, d
     _dump_equal(g, orc)
+
+
+RUST_DOC = bytes([  # test/backend_test.js:1054 — saved by the Rust backend, expects {birds: 3.0}
+    133, 111, 74, 131, 233, 181, 157, 86, 0, 144, 1, 1, 16, 228, 91, 238, 197, 233, 52, 66, 187, 138, 75, 115, 104, 190, 195, 159, 200, 1, 221, 158, 172, 238, 121, 38, 160, 123, 25, 33,
+    97, 124, 142, 27, 86, 224, 238, 83, 14, 157, 207, 233, 8, 110, 91, 151, 172, 38, 120, 221, 38, 162, 7, 1, 2, 3, 2, 19, 2, 35, 7, 53, 16, 64, 2, 86, 2, 8, 21, 7, 33, 2, 35, 2, 52, 1, 66,
+    2, 86, 3, 87, 8, 128, 1, 2, 127, 0, 127, 1, 127, 1, 127, 243, 145, 234, 194, 149, 47, 127, 14, 73, 110, 105, 116, 105, 97, 108, 105, 122, 97, 116, 105, 111, 110, 127, 0, 127, 7, 127, 5,
+    98, 105, 114, 100, 115, 127, 0, 127, 1, 1, 127, 1, 127, 133, 1, 0, 0, 0, 0, 0, 0, 8, 64, 127, 0])
+
+
+def check_load(gpu_doc, oracle_mod, cfg, n, a):
+    """Backend.load of a document saved by the oracle (= reference format): getPatch, then more changes on top."""
+    from automerge_classic_b200 import tracegen
+    ch = tracegen.generate(cfg, n, a).changes()
+    cut = 1 + 100 * a * ((len(ch) - 1) // (200 * a)) if a else len(ch) // 2    # a merge-round boundary: every later dep is a head
+    orc = oracle_mod.OracleDoc()
+    orc.apply_changes(ch[:cut])
+    saved = orc.save()
+    o2, g = oracle_mod.OracleDoc(saved), gpu_doc(saved)
+    d = replay.deep_equal(replay.decode(g.get_patch()), replay.decode(o2.get_patch()))
+    assert d is None, d
+    po, pg = o2.apply_changes(ch[cut:]), g.apply_changes(ch[cut:])
+    d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+    assert d is None, d
+    _dump_equal(g, o2)
+
+
+def check_rust_document(gpu_doc):
+    p = gpu_doc(RUST_DOC).get_patch()
+    assert p['maxOp'] == 1 and p['clock'] == {'e45beec5e93442bb8a4b7368bec39fc8': 1}
+    assert p['diffs']['props'] == {'birds': {'1@e45beec5e93442bb8a4b7368bec39fc8': {'type': 'value', 'value': 3.0, 'datatype': 'float64'}}}

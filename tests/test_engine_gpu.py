@@ -77,3 +77,12 @@ def test_errors_leave_state_untouched(gpu_doc):
 def test_large_text_trace(gpu_doc, oracle_mod):
     """C3 at 100k ops: full parity against the oracle (the oracle finishes this size in seconds)."""
     parity_checks.check_large_text(gpu_doc, oracle_mod, 100000)
+
+
+@pytest.mark.parametrize('cfg,n,a', [('C2', 600, 0), ('C3', 6000, 3), ('C1', 0, 0)])
+def test_load_saved_document(gpu_doc, oracle_mod, cfg, n, a):
+    parity_checks.check_load(gpu_doc, oracle_mod, cfg, n, a)
+
+
+def test_load_rust_document(gpu_doc):
+    parity_checks.check_rust_document(gpu_doc)

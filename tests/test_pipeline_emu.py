@@ -59,3 +59,12 @@ def test_out_of_order_emu(emu_doc, oracle_mod):
 
 def test_errors_atomic_emu(emu_doc):
     parity_checks.check_errors_atomic(emu_doc)
+
+
+@pytest.mark.parametrize('cfg,n,a', [('C2', 600, 0), ('C3', 6000, 3), ('C1', 0, 0)])
+def test_load_saved_document_emu(emu_doc, oracle_mod, cfg, n, a):
+    parity_checks.check_load(emu_doc, oracle_mod, cfg, n, a)
+
+
+def test_load_rust_document_emu(emu_doc):
+    parity_checks.check_rust_document(emu_doc)
