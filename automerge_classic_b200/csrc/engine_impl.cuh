@@ -148,6 +148,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     foreach(ctx, B, DeflateScanKernel{arena.p, chOff.p, chLen.p, errWord.p + 1, deflList.p});
     u64 nd64 = 0; d2h(ctx, &nd64, errWord.p + 1, 8); sync(ctx);
     if (nd64) { deflIdx.resize((size_t)nd64); d2h(ctx, deflIdx.data(), deflList.p, (size_t)nd64 * 4); sync(ctx); }
+    dbgMark("sha:deflate-scanned");
   }
   // SHA-256 of every change runs on the GPU while the host inflates (zlib, as columnar.js:813-823 does with pako)
   foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr, uploaded ? deflList.p : nullptr});
@@ -163,8 +164,10 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
         inflateEnd(&zs); });
       for (auto& th : ts) th.join();
       for (auto& e : errs) if (!e.empty() && firstError.empty()) firstError = e; }
+    dbgMark("sha:inflated");
     if (!firstError.empty()) throw Error(AMG_ERR_RANGE, firstError);
     if (mirrorThread.joinable()) mirrorThread.join();   // the mirror may have to grow
+    dbgMark("sha:mirror-joined");
     size_t extra = 0; for (auto& x : inflated) extra += x.size();
     if ((u64)cur + extra + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
     // the inflated bytes go behind the batch and the entries are re-pointed; the original bytes stay where they are
@@ -176,11 +179,13 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       batch[b] = HostChange{(u32)cur, (u32)inflated[k].size()}; triples[3 * k] = b; triples[3 * k + 1] = batch[b].off; triples[3 * k + 2] = batch[b].len; cur += inflated[k].size();
     }
     arena.ensure(ctx, cur + 64, extraStart); h2d(ctx, arena.p + extraStart, hostArena.data() + extraStart, cur - extraStart); dev_memset(ctx, arena.p + cur, 0, 64);
+    dbgMark("sha:extra-uploaded");
     patchTriples.ensure(ctx, 3 * nd); h2d(ctx, patchTriples.p, triples.data(), triples.size() * 4);
     foreach(ctx, nd, PatchPairsKernel{patchTriples.p, chOff.p, chLen.p});
     h2d(ctx, deflList.p, deflIdx.data(), nd * 4);
     foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, deflList.p, nullptr});
     sync(ctx);   // `triples` / `deflIdx` are pageable host memory: keep them alive until the copies are done
+    dbgMark("sha:resynced");
   }
   timer.mark(); hostMark();
   meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
@@ -244,6 +249,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     }
     const u32 fresh = readU32(flagWord.p);
     if (fresh > 0) {
+    dbgMark("actors:interned");
       std::vector<u32> slotsH(fresh); d2h(ctx, slotsH.data(), newSlots.p, fresh * 4); sync(ctx);
       std::vector<ActorSlot> recs(fresh); for (u32 i = 0; i < fresh; i++) d2h(ctx, &recs[i], actorSlots.p + slotsH[i], sizeof(ActorSlot));
       sync(ctx);
@@ -268,6 +274,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       actorRank.ensure(ctx, A + 1); h2d(ctx, actorRank.p, rank.data(), A * 4);
     }
     const int rb = bits_for(A > 1 ? A - 1 : 1);
+    dbgMark("actors:numbered");
     Ord ord{actorRank.p, rb};
     amapBase.ensure(ctx, B + 1); rowSlot.ensure(ctx, B + 1);
     foreach(ctx, B, MaskedCountKernel{nActors.p, applied.p, rowSlot.p});
@@ -275,6 +282,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     const u32 totalAmap = readU32(amapBase.p + B);
     amap.ensure(ctx, totalAmap + 1);
     foreach(ctx, B, ActorMapKernel{arena.p, meta.p, applied.p, appRank.p, actorSlots.p, (u64)actorCap - 1, amapBase.p, amap.p, errWord.p});
+    dbgMark("actors:mapped");
     // ---------------------------------------------------------- 4. sequence numbers
     changeActor.ensure(ctx, B); actorCnt.ensure(ctx, A + 1); actorBaseD.ensure(ctx, A + 1); seqSlot.ensure(ctx, numNew + 1);
     dev_memset(ctx, actorCnt.p, 0, (A + 1) * 4);
@@ -302,11 +310,13 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       throw Error(AMG_ERR_INTERNAL, "amgpu: sequence check disagreement");
     }
     for (size_t a = 0; a < A; a++) clockNow[a] += actorCntH[a];
+    dbgMark("seq:checked");
     // ---------------------------------------------------------- 5. decode ops
     opBase.ensure(ctx, B + 1); predBase.ensure(ctx, B + 1); timeBase.ensure(ctx, B + 1);
     foreach(ctx, B, MaskedCountKernel{nOps.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, opBase.p, B);
     foreach(ctx, B, MaskedCountKernel{nPreds.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, predBase.p, B);
     M = readU32(opBase.p + B); P = readU32(predBase.p + B);
+    dbgMark("decode:counts");
     if (!inOrder) {
       perm.ensure(ctx, B + 1); dev_memset(ctx, perm.p, 0, (B + 1) * 4);
       foreach(ctx, B, OpsInOrderKernel{nOps.p, applied.p, appRank.p, perm.p});
@@ -336,6 +346,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     OpRows ops{o_id.p, o_obj.p, o_key.p, o_keyStrOff.p, o_keyStrLen.p, o_flags.p, o_valLen.p, o_valOff.p, o_predOff.p, o_predNum.p, o_change.p, o_time.p, o_predId.p};
     foreach(ctx, M, FinalizeOpsKernel{B, meta.p, opBase.p, timeBase.p, amapBase.p, amap.p, applied.p, raw, ops, errWord.p});
     checkErr(actorsNow);
+    dbgMark("decode:finalized");
     timer.mark(); hostMark();
     // ---------------------------------------------------------- 6. op set
     if (maxOpNow >= (1ULL << 40)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: op counters above 2^40");
@@ -353,6 +364,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     objRow.ensure(ctx, N + 1); elemRow.ensure(ctx, N + 1); parentRow.ensure(ctx, N + 1);
     foreach(ctx, N, ResolveRowsKernel{w, idt, ord, numRows, objRow.p, elemRow.p, parentRow.p, errWord.p});
     checkErr(actorsNow);
+    dbgMark("opset:resolved");
     // map keys: intern, verify, rank distinct keys with an LSD string sort
     const size_t kcap = pow2_at_least(2 * N + 2); keySlots.ensure(ctx, kcap); keySlot.ensure(ctx, N + 1); repList.ensure(ctx, N + 1); repCount.ensure(ctx, 4);
     foreach(ctx, kcap, KeySlotInitKernel{keySlots.p});
@@ -361,6 +373,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     foreach(ctx, N, KeyVerifyKernel{arena.p, w, keySlots.p, keySlot.p, repList.p, repCount.p, errWord.p});
     u32 rc[2]; d2h(ctx, rc, repCount.p, 8); sync(ctx);
     const size_t D = rc[0]; const u32 maxKeyLen = rc[1];
+    dbgMark("opset:keys-interned");
     if (D > 0) {
       sortKeys.ensure(ctx, D); sortVals.ensure(ctx, D);
       d2d(ctx, sortVals.p, repList.p, D * 4);
@@ -375,6 +388,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     listPos.ensure(ctx, N + 1); insItems.ensure(ctx, N + 1); emit.ensure(ctx, N + 1); slot.ensure(ctx, N + 2);
     foreach(ctx, N, InsertFlagKernel{w, emit.p}); scan_exclusive(ctx, scanTmp, emit.p, slot.p, N);
     const size_t I = readU32(slot.p + N);
+    dbgMark("opset:inserts-counted");
     if (I > 0) {
       const int parentBits = bits_for(N) + 1;
       if (ordBits + parentBits > 64) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: opId range x document size exceeds the 64-bit sibling sort key");
@@ -394,6 +408,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       foreach(ctx, N, ListPosKernel{eRank.p, elemRow.p, objRow.p, w, listPos.p});
     } else dev_memset(ctx, listPos.p, 0, (N + 1) * 4);
     checkErr(actorsNow);
+    dbgMark("opset:list-ranked");
     // document order: stable LSD over (object, key rank | list position, opId within the key / element)
     perm.ensure(ctx, N + 1); pos.ensure(ctx, N + 1); sortKeys.ensure(ctx, N);
     foreach(ctx, N, IotaKernel{perm.p});
@@ -403,6 +418,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       sortPairs(sortKeys, perm, N, fieldBits[f]);
     }
     foreach(ctx, N, InversePermKernel{perm.p, pos.p});
+    dbgMark("opset:doc-ordered(enqueued)");
     // succ lists
     numPairs = numSucc + P;
     pairKey.ensure(ctx, numPairs + 1); pairSucc.ensure(ctx, numPairs + 1); pairIdx.ensure(ctx, numPairs + 1); pairPos.ensure(ctx, numPairs + 1); pairTime.ensure(ctx, numPairs + 1);
@@ -430,6 +446,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     foreach(ctx, numPairs, WriteSuccKernel{pairIdx.p, pairSucc.p, newSucc.p});
     sorted.ensure(ctx, N + 1);
     foreach(ctx, N, GatherRowsKernel{w, sorted.view(), perm.p});
+    dbgMark("opset:succ+gather(enqueued)");
     timer.mark(); hostMark();
     // ---------------------------------------------------------- 7. incremental patch
     if (wantPatch) {
