@@ -194,6 +194,17 @@ HD unsigned long long atomic_cas(unsigned long long* p, unsigned long long cmp, 
 HD uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) { AMG_ATOMIC(atomicCAS(p, cmp, v), { uint32_t o = *p; if (o == cmp) *p = v; return o; }) }
 #endif
 
+// counter[index] += 1 with one atomic per distinct index per warp (consecutive items usually share the index)
+HD void warp_agg_inc(uint32_t* counter, uint32_t index) {
+#if defined(__CUDA_ARCH__)
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, index);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counter[index], (uint32_t)__popc(peers));
+#else
+  counter[index] += 1;
+#endif
+}
+
 typedef unsigned long long u64;
 typedef uint32_t u32;
 typedef uint8_t u8;

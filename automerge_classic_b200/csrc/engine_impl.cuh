@@ -550,7 +550,8 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   DBuf<u32>& groupLinkedB = linkDone;   // linkDone doubles as per-group linked flags storage below (separate buffers)
   (void)groupLinkedB;
   dev_memset(ctx, groupRows.p, 0, (numGroups + 1) * 4); dev_memset(ctx, groupVisible.p, 0, (numGroups + 1) * 4); dev_memset(ctx, groupTouched.p, 0, (numGroups + 1) * 4);
-  foreach(ctx, N, GroupStatsKernel{headScan.p, head.p, succCnt.p, d, groupOf.p, groupRows.p, groupVisible.p, groupFirst.p, errWord.p, 0});
+  groupHasChild.ensure(ctx, numGroups + 1); dev_memset(ctx, groupHasChild.p, 0, (numGroups + 1) * 4);
+  foreach(ctx, N, GroupStatsKernel{headScan.p, head.p, succCnt.p, d, groupOf.p, groupRows.p, groupVisible.p, groupFirst.p, errWord.p, 0, groupHasChild.p});
   // objects in document order
   isObjHead.ensure(ctx, N + 1); objIdx.ensure(ctx, N + 2); 
   foreach(ctx, N, ObjHeadKernel{d, isObjHead.p});
@@ -562,29 +563,44 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   emit.ensure(ctx, N + 1); marker.ensure(ctx, N + 1); slot.ensure(ctx, N + 2);
   groupLinked.ensure(ctx, std::max(numGroups, numApplied + 1) + 2);
   dev_memset(ctx, groupLinked.p, 0, (numGroups + 1) * 4);
+  Ord ordNow{actorRank.p, bits_for(actorsNow.size() > 1 ? actorsNow.size() - 1 : 1)};
+  ListCtx lctx{d, succCnt.p, newSuccCnt.p, firstNewSucc.p, groupOf.p, groupFirst.p, groupRows.p};
+  MapGroupCtx mg{arena.p, ops ? *ops : OpRows{}, opAt.p, numOps};
+  bool anyListLink = false;
+  auto listGroups = [&](int pass) {
+    return ListGroupKernel{pass, mg, opGroupHead.p, *idt, rowOfOpD, posD, lctx, gCount.p, gElem.p, gT1.p, gQOrd.p, nQ.p, elemHasRecs.p,
+                           itemBase.p, objIdx.p, objStart.p, items.p, gBase.p, qIndex.p, editOut.p, editElem.p, editObjKey.p, editElemPos.p, errWord.p};
+  };
   if (!wholeDoc) {
+    // op groups of the batch (new.js:1085-1138), then what each list group nets out to
+    nQ.ensure(ctx, N + 1); elemHasRecs.ensure(ctx, N + 1); listLinkTime.ensure(ctx, N + 1);
+    dev_memset(ctx, nQ.p, 0, (N + 1) * 4); dev_memset(ctx, elemHasRecs.p, 0, (N + 1) * 4); dev_memset(ctx, listLinkTime.p, 0xff, (N + 1) * 4);
+    if (numOps > 0) {
+      opAt.ensure(ctx, numOps + 1); runHead.ensure(ctx, numOps + 1); opGroupHead.ensure(ctx, numOps + 1);
+      for (DBuf<u32>* b : {&gCount, &gElem, &gT1, &gQOrd, &gBase, &qIndex}) b->ensure(ctx, numOps + 2);
+      mg.opAt = opAt.p;
+      foreach(ctx, numOps, OpAtTimeKernel{ops->time, opAt.p});
+      foreach(ctx, numOps, RunHeadKernel{mg, runHead.p});
+      foreach(ctx, numOps, GroupSplitKernel{mg, runHead.p, opGroupHead.p});
+      foreach(ctx, numOps, listGroups(0));
+    }
     objTouchedAt.ensure(ctx, N + 1); linkDone.ensure(ctx, N + 1);
-    dev_memset(ctx, objTouchedAt.p, 0, (N + 1) * 4); dev_memset(ctx, linkDone.p, 0, (N + 1) * 4); dev_memset(ctx, flagWord.p, 0, 16);
+    dev_memset(ctx, objTouchedAt.p, 0xff, (N + 1) * 4); dev_memset(ctx, linkDone.p, 0xff, (N + 1) * 4); dev_memset(ctx, flagWord.p, 0, 16);
     foreach(ctx, N, TouchKernel{d, groupOf.p, firstNewSucc.p, groupTouched.p, objTouchedAt.p, objPos.p, flagWord.p + 2});
     for (int iter = 0; iter < 1000; iter++) {
       dev_memset(ctx, flagWord.p, 0, 4);
-      foreach(ctx, N, LinkKernel{d, groupOf.p, groupVisible.p, objPos.p, groupLinked.p, objTouchedAt.p, flagWord.p + 2, linkDone.p, flagWord.p, errWord.p});
+      foreach(ctx, N, LinkKernel{d, groupOf.p, groupHasChild.p, groupFirst.p, objPos.p, groupLinked.p, objTouchedAt.p, flagWord.p + 2, linkDone.p, flagWord.p, elemHasRecs.p, listLinkTime.p, flagWord.p + 3});
       if (!readU32(flagWord.p)) break;
     }
+    anyListLink = readU32(flagWord.p + 3) != 0;
   }
   // ---- map props
   DBuf<u32>& groupEmitted = elemVis;   // scratch reuse (list edits re-initialise it later)
   groupEmitted.ensure(ctx, std::max(numGroups, N) + 2); dev_memset(ctx, groupEmitted.p, 0, (numGroups + 1) * 4);
   finalTime.ensure(ctx, numGroups + 1); gBound.ensure(ctx, numGroups + 1); gFailed.ensure(ctx, numGroups + 1); memberFinal.ensure(ctx, N + 1);
   dev_memset(ctx, finalTime.p, 0, (numGroups + 1) * 4);
-  Ord ordNow{actorRank.p, bits_for(actorsNow.size() > 1 ? actorsNow.size() - 1 : 1)};
   if (!wholeDoc && numOps > 0) {
     dev_memset(ctx, memberFinal.p, 0, (N + 1) * 4); dev_memset(ctx, gFailed.p, 0, (numGroups + 1) * 4);
-    opAt.ensure(ctx, numOps + 1); runHead.ensure(ctx, numOps + 1); opGroupHead.ensure(ctx, numOps + 1);
-    foreach(ctx, numOps, OpAtTimeKernel{ops->time, opAt.p});
-    MapGroupCtx mg{arena.p, *ops, opAt.p, numOps};
-    foreach(ctx, numOps, RunHeadKernel{mg, runHead.p});
-    foreach(ctx, numOps, GroupSplitKernel{mg, runHead.p, opGroupHead.p});
     for (int pass = 0; pass < 2; pass++)
       foreach(ctx, numOps, GroupFinalKernel{pass, mg, opGroupHead.p, *idt, rowOfOpD, posD, groupOf.p, workView, ordNow, finalTime.p, gBound.p, gFailed.p, memberFinal.p});
   }
@@ -609,45 +625,65 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
     foreach(ctx, N, DocEditEmitKernel{d, rowEmit.p, slot.p, elemVisScan.p, objIdx.p, objStart.p, groupOf.p, groupFirst.p, succCnt.p, firstVis.p, editOut.p});
     foreach(ctx, N, EditElemKernel{d, rowEmit.p, slot.p, groupOf.p, groupFirst.p, editElem.p});
   } else {
-    state.ensure(ctx, N + 1); nItems.ensure(ctx, N + 1); itemBase.ensure(ctx, N + 2); qIndex.ensure(ctx, 2 * N + 2);
-    foreach(ctx, N, ElemStateKernel{d, succCnt.p, newSuccCnt.p, firstNewSucc.p, groupRows.p, groupVisible.p, groupOf.p, groupTouched.p, state.p, nItems.p, errWord.p});
-    checkErr(actorsNow);
-    scan_exclusive(ctx, scanTmp, nItems.p, itemBase.p, N);
-    const size_t T = readU32(itemBase.p + N);
-    // any list edit to produce at all? (every new list op has a query item)
-    emit.ensure(ctx, numOps + 1); slot.ensure(ctx, std::max(numOps, N) + 2);
-    foreach(ctx, numOps, OpEditFlagKernel{*ops, posD, *idt, firstNewSucc.p, state.p, emit.p});
-    scan_exclusive(ctx, scanTmp, emit.p, slot.p, numOps);
-    numEdits = readU32(slot.p + numOps);
+    size_t numGroupRecs = 0, numLink = 0;
+    if (numOps > 0) { scan_exclusive(ctx, scanTmp, gCount.p, gBase.p, numOps); numGroupRecs = readU32(gBase.p + numOps); }
+    DBuf<u32>& linkCount = rowEmit; DBuf<u32>& linkBase = slot;
+    if (anyListLink) {   // index of a linked element = visible elements before it once the whole batch is applied
+      elemVis.ensure(ctx, N + 1); elemVisScan.ensure(ctx, N + 2); linkCount.ensure(ctx, N + 1); linkBase.ensure(ctx, N + 2);
+      foreach(ctx, N, ListVisFlagKernel{d, groupOf.p, groupVisible.p, head.p, succCnt.p, elemVis.p, linkCount.p});
+      scan_exclusive(ctx, scanTmp, elemVis.p, elemVisScan.p, N);
+      foreach(ctx, N, ListLinkKernel{0, lctx, listLinkTime.p, elemVisScan.p, objIdx.p, objStart.p, linkCount.p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr});
+      scan_exclusive(ctx, scanTmp, linkCount.p, linkBase.p, N);
+      numLink = readU32(linkBase.p + N);
+    }
+    numEdits = numGroupRecs + numLink;
     if (numEdits > 0) {
-      items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zwScan.ensure(ctx, T + 2);
-      foreach(ctx, N, DomBuildKernel{d, state.p, firstNewSucc.p, itemBase.p, objIdx.p, objStart.p, items.p});
-      const int tbits = bits_for(numOps + 1);
-      for (int bit = tbits - 1; bit >= 0; bit--) {
-        scan_exclusive64(ctx, scanTmp, DomScanInput{items.p, bit}, zwScan.p, T);
-        foreach(ctx, T, DomLevelKernel{items.p, items2.p, zwScan.p, bit});
-        std::swap(items.p, items2.p); std::swap(items.cap, items2.cap);
+      if (numGroupRecs > 0) {
+        nItems.ensure(ctx, N + 1); itemBase.ensure(ctx, N + 2);
+        foreach(ctx, N, ElemEventKernel{0, lctx, head.p, nQ.p, nItems.p, itemBase.p, objIdx.p, objStart.p, items.p});
+        scan_exclusive(ctx, scanTmp, nItems.p, itemBase.p, N);
+        const size_t T = readU32(itemBase.p + N);
+        items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zwScan.ensure(ctx, T + 2);
+        foreach(ctx, N, ElemEventKernel{1, lctx, head.p, nQ.p, nItems.p, itemBase.p, objIdx.p, objStart.p, items.p});
+        foreach(ctx, numOps, listGroups(1));
+        const int tbits = bits_for(numOps + 1);
+        for (int bit = tbits - 1; bit >= 0; bit--) {
+          scan_exclusive64(ctx, scanTmp, DomScanInput{items.p, bit}, zwScan.p, T);
+          foreach(ctx, T, DomLevelKernel{items.p, items2.p, zwScan.p, bit});
+          std::swap(items.p, items2.p); std::swap(items.cap, items2.cap);
+        }
+        foreach(ctx, T, DomResultKernel{items.p, qIndex.p});
       }
-      foreach(ctx, T, DomResultKernel{items.p, qIndex.p});
       if (curTimer) { curTimer->mark(); curHostMark(); }
-      editOut.ensure(ctx, numEdits + 1); editElem.ensure(ctx, numEdits + 1); editObjKey.ensure(ctx, numEdits + 1);
-      editTime.ensure(ctx, numEdits + 1);
-      foreach(ctx, numOps, OpEditEmitKernel{*ops, emit.p, slot.p, rowOfOpD, posD, *idt, qIndex.p, editOut.p, editElem.p, editObjKey.p, editTime.p, objIdx.p});
-      // order edits by (object, application time); op order already is time order unless the batch needed several passes
+      editOut.ensure(ctx, numEdits + 1); editElem.ensure(ctx, numEdits + 1); editObjKey.ensure(ctx, numEdits + 1); editElemPos.ensure(ctx, numEdits + 1);
+      editOut2.ensure(ctx, numEdits + 1); editElem2.ensure(ctx, numEdits + 1); editElemPos2.ensure(ctx, numEdits + 1);
       sortKeys.ensure(ctx, numEdits + 1); sortVals.ensure(ctx, numEdits + 1);
-      if (batchInOrder) foreach(ctx, numEdits, EditKeyKernel{editObjKey.p, editOut.p, sortKeys.p, sortVals.p});
-      else {
+      if (numGroupRecs > 0) foreach(ctx, numOps, listGroups(2));
+      // records of the op groups are in application order by construction; link edits go last, in the order their objects were first touched
+      if (numLink > 0) {
+        editTime.ensure(ctx, numEdits + 1);
+        if (numGroupRecs > 0) foreach(ctx, numOps, GroupTimeKernel{gBase.p, gCount.p, editTime.p});
+        foreach(ctx, N, ListLinkKernel{1, lctx, listLinkTime.p, elemVisScan.p, objIdx.p, objStart.p, linkCount.p, linkBase.p, (u32)numGroupRecs, editOut.p, editElem.p, editObjKey.p, editElemPos.p, editTime.p});
         foreach(ctx, numEdits, EditTimeKeyKernel{editTime.p, sortKeys.p, sortVals.p});
-        sortPairs(sortKeys, sortVals, numEdits, bits_for(numOps + 1));
+        sortPairs(sortKeys, sortVals, numEdits, 32);
         foreach(ctx, numEdits, GatherToU64Kernel{editObjKey.p, sortVals.p, sortKeys.p});
-      }
+      } else foreach(ctx, numEdits, EditKeyKernel{editObjKey.p, editOut.p, sortKeys.p, sortVals.p});
       sortPairs(sortKeys, sortVals, numEdits, bits_for(numObjs));
-      editOut2.ensure(ctx, numEdits + 1); editElem2.ensure(ctx, numEdits + 1);
-      foreach(ctx, numEdits, EditGatherKernel{editOut.p, editElem.p, sortVals.p, editOut2.p, editElem2.p});
-      std::swap(editOut.p, editOut2.p); std::swap(editOut.cap, editOut2.cap); std::swap(editElem.p, editElem2.p); std::swap(editElem.cap, editElem2.cap);
+      foreach(ctx, numEdits, EditGatherKernel{editOut.p, editElem.p, editElemPos.p, sortVals.p, editOut2.p, editElem2.p, editElemPos2.p});
+      // pops, coalescing, compaction
+      for (DBuf<u32>* b : {&editKind, &editPred, &editDead, &editMerge, &editMulti, &editLive}) b->ensure(ctx, numEdits + 2);
+      dev_memset(ctx, editDead.p, 0, (numEdits + 1) * 4); dev_memset(ctx, editMulti.p, 0, (numEdits + 1) * 4);
+      foreach(ctx, numEdits, EditFixKernel{editOut2.p, editElemPos2.p, editKind.p, editPred.p, editDead.p, numEdits});
+      foreach(ctx, numEdits, EditMergeKernel{editOut2.p, editElem2.p, editKind.p, editPred.p, editMerge.p, editMulti.p});
+      foreach(ctx, numEdits, EditLiveKernel{editDead.p, editLive.p});
+      DBuf<u32>& liveSlot = editPred;   // pred is consumed by now
+      scan_exclusive(ctx, scanTmp, editLive.p, liveSlot.p, numEdits);
+      const size_t numLive = readU32(liveSlot.p + numEdits);
+      foreach(ctx, numEdits, EditCompactKernel{editOut2.p, editElem2.p, editDead.p, liveSlot.p, editKind.p, editMerge.p, editMulti.p, editOut.p, editElem.p});
+      numEdits = numLive;
     }
   }
-  if (numEdits > 0) foreach(ctx, numEdits, RunFlagKernel{editOut.p, editElem.p, numEdits});
+  if (wholeDoc && numEdits > 0) foreach(ctx, numEdits, RunFlagKernel{editOut.p, editElem.p, numEdits});
   out.numProps = numProps; out.numEdits = numEdits;
   out.propsOff = 18 * 8; out.editsOff = out.propsOff + numProps * sizeof(PropRec); out.elemOff = out.editsOff + numEdits * sizeof(EditRec); out.bigEnd = out.elemOff + numEdits * 8;
   patchBuf.ensure(out.bigEnd + 4096);

@@ -34,7 +34,7 @@ struct NewActorKernel {
   }
 };
 struct SetActorNumKernel { ActorSlot* slots; const u32* slotIds; const u32* nums; HD void operator()(size_t i) const { slots[slotIds[i]].actorNum = nums[i]; } };
-struct ChangeActorKernel { const u32* amapBase; const u32* amap; const u8* applied; u32* changeActor; u32* actorCnt; HD void operator()(size_t b) const { if (!applied[b]) { changeActor[b] = EMPTY32; return; } const u32 a = amap[amapBase[b]]; changeActor[b] = a; atomic_add(&actorCnt[a], 1u); } };
+struct ChangeActorKernel { const u32* amapBase; const u32* amap; const u8* applied; u32* changeActor; u32* actorCnt; HD void operator()(size_t b) const { if (!applied[b]) { changeActor[b] = EMPTY32; return; } const u32 a = amap[amapBase[b]]; changeActor[b] = a; warp_agg_inc(actorCnt, a); } };
 // seq == clock + 1 in application order (new.js:1559, 1571-1579): the seqs of an actor's applied changes must be
 // exactly clock+1 .. clock+count, in increasing application order
 struct SeqScatterKernel {
@@ -124,6 +124,6 @@ struct ObjPosKernel { const u32* perm; const u32* objRow; const u32* pos; u32* o
 struct SuccCntFromOffKernel { const u32* off; u32* cnt; HD void operator()(size_t p) const { cnt[p] = off[p + 1] - off[p]; } };
 struct EditKeyKernel { const u32* objKey; const EditRec* e; u64* key; u32* val; HD void operator()(size_t j) const { key[j] = objKey[j]; val[j] = (u32)j; } };
 struct EditTimeKeyKernel { const u32* t; u64* key; u32* val; HD void operator()(size_t j) const { key[j] = t[j]; val[j] = (u32)j; } };
-struct EditGatherKernel { const EditRec* in; const u64* elemIn; const u32* idx; EditRec* out; u64* elemOut; HD void operator()(size_t j) const { out[j] = in[idx[j]]; elemOut[j] = elemIn[idx[j]]; } };
+struct EditGatherKernel { const EditRec* in; const u64* elemIn; const u32* posIn; const u32* idx; EditRec* out; u64* elemOut; u32* posOut; HD void operator()(size_t j) const { out[j] = in[idx[j]]; elemOut[j] = elemIn[idx[j]]; posOut[j] = posIn[idx[j]]; } };
 
 }  // namespace amg

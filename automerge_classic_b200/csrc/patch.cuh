@@ -44,36 +44,48 @@ struct GroupHeadKernel {   // group = rows of one map key / one list element (in
 };
 struct GroupStatsKernel {   // group id = inclusive scan of heads - 1; counts rows and visible rows per group
   const u32* headScan /* exclusive scan of head */; const u32* head; const u32* succCnt; DocRows d; u32* groupOf; u32* groupRows; u32* groupVisible; u32* groupFirst; u64* errWord; int allowCounters;
+  u32* groupHasChild /* some visible row of the group is a make* op */;
   HD void operator()(size_t p) const {
     const u32 g = headScan[p] + head[p] - 1; groupOf[p] = g;
     atomic_add(&groupRows[g], 1u);
-    if (succCnt[p] == 0) atomic_add(&groupVisible[g], 1u);
+    if (succCnt[p] == 0) { atomic_add(&groupVisible[g], 1u); const u32 a = flags_action(d.flags[p]); if (a % 2 == 0 && a != ACT_DEL) groupHasChild[g] = 1; }
     if (head[p]) groupFirst[g] = (u32)p;
     if (flags_action(d.flags[p]) == ACT_INC || ((d.valLen[p] & 15) == 8 && flags_action(d.flags[p]) == ACT_SET && succCnt[p] > 0)) { if (!allowCounters) raise(errWord, KE_UNSUPPORTED_OP, p); }
   }
 };
 
 // ---------------------------------------------------------------- incremental: touched groups / objects
-struct TouchKernel {   // new rows and the targets of new succ entries touch their group and object
-  DocRows d; const u32* groupOf; const u32* firstNewSucc; u32* groupTouched; u32* objTouchedAt /* per position of the object's make row */;
+struct TouchKernel {   // new rows and the targets of new succ entries touch their group and object (objTouchedAt = earliest such time)
+  DocRows d; const u32* groupOf; const u32* firstNewSucc; u32* groupTouched; u32* objTouchedAt /* per position of the object's make row; 0xffffffff = untouched */;
   const u32* objPos /* per position: position of the object's make row or ROW_NONE (root) */; u32* rootTouched;
   HD void operator()(size_t p) const {
     if (d.time[p] == 0 && firstNewSucc[p] == 0xffffffffu) return;
     groupTouched[groupOf[p]] = 1;
-    if (objPos[p] == ROW_NONE) *rootTouched = 1; else objTouchedAt[objPos[p]] = 1;
+    u32 t = firstNewSucc[p]; if (d.time[p] != 0 && d.time[p] < t) t = d.time[p];
+    if (objPos[p] == ROW_NONE) *rootTouched = 1; else atomic_min(&objTouchedAt[objPos[p]], t);
   }
 };
-// setupPatches: a touched object links itself into its parent (the group of its make row), recursively
+// setupPatches (new.js:1461-1528): a touched object links itself into its parent (the group of its make row), recursively.
+// Objects are visited in the order they were first touched; the time travels up with the link so that link edits on a
+// list parent can be ordered the same way. A list element that already carries edits of this call needs no link edit.
 struct LinkKernel {
-  DocRows d; const u32* groupOf; const u32* groupVisible; const u32* objPos; u32* groupLinked; u32* objTouchedAt; u32* rootTouched; u32* linkDone; u32* changed; u64* errWord;
+  DocRows d; const u32* groupOf; const u32* groupHasChild; const u32* groupFirst; const u32* objPos; u32* groupLinked; u32* objTouchedAt; u32* rootTouched; u32* linkDone; u32* changed;
+  const u32* elemHasRecs /* per position of an element's insert row */; u32* listLinkTime /* same indexing; 0xffffffff = none */; u32* anyListLink;
   HD void operator()(size_t p) const {
-    if (!objTouchedAt[p] || linkDone[p]) return;
-    linkDone[p] = 1; *changed = 1;
+    const u32 t = objTouchedAt[p];
+    if (t == 0xffffffffu || linkDone[p] == t) return;
+    linkDone[p] = t; *changed = 1;
     const u32 g = groupOf[p];
-    if (groupVisible[g] == 0) return;   // hasChildren false: nothing to link (new.js:1465,1521)
-    if (d.keyStrLen[p] == NULL32) { raise(errWord, KE_UNSUPPORTED_OP, p); return; }   // child object inside a list
-    groupLinked[g] = 1;
-    if (objPos[p] == ROW_NONE) *rootTouched = 1; else objTouchedAt[objPos[p]] = 1;
+    // hasChildren (new.js:1465,1521): objectMeta.children of a key / element is only kept up to date while one of its
+    // visible values is an object (new.js:919-935), so an object that was overwritten by plain values links nothing.
+    // (Not modelled: the reference also keeps a snapshot alive while the lowest-id value stays visible after the last
+    // object value went away; that depends on the order of earlier calls.)
+    if (groupHasChild[g] == 0) return;
+    if (d.keyStrLen[p] == NULL32) {     // child object inside a list: an update edit per visible value unless the element has edits already
+      const u32 e = groupFirst[g];
+      if (!elemHasRecs[e]) { atomic_min(&listLinkTime[e], t); *anyListLink = 1; }
+    } else groupLinked[g] = 1;
+    if (objPos[p] == ROW_NONE) *rootTouched = 1; else atomic_min(&objTouchedAt[objPos[p]], t);
   }
 };
 // ---------------------------------------------------------------- which conflicting values the reference re-emits
@@ -103,9 +115,10 @@ struct MapGroupCtx {
     for (u32 k = 0; k < ops.keyStrLen[i]; k++) if (arena[ops.keyStrOff[i] + k] != arena[ops.keyStrOff[j] + k]) return false;
     return true;
   }
-  HD bool sameRun(u32 i, u32 j) const {
-    return isMapOp(i) && isMapOp(j) && id_actor(ops.id[i]) == id_actor(ops.id[j]) && ((ops.flags[i] ^ ops.flags[j]) & F_INSERT) == 0 &&
-           ops.obj[i] == ops.obj[j] && sameKey(i, j);
+  HD bool sameRun(u32 i, u32 j) const {   // ops that one mergeDocChangeOps call may gather onto one key / list element
+    if (id_actor(ops.id[i]) != id_actor(ops.id[j]) || ((ops.flags[i] ^ ops.flags[j]) & F_INSERT) != 0 || ops.obj[i] != ops.obj[j] || isMapOp(i) != isMapOp(j)) return false;
+    if (isMapOp(i)) return sameKey(i, j);
+    return (ops.flags[i] & F_INSERT) == 0 && ops.key[i] == ops.key[j];
   }
 };
 struct RunHeadKernel { MapGroupCtx c; u32* runHead; HD void operator()(size_t t) const { runHead[t] = (t == 0 || !c.sameRun(c.opAt[t], c.opAt[t - 1])) ? 1u : 0u; } };
@@ -227,47 +240,44 @@ struct EditElemKernel { DocRows d; const u32* rowEmit; const u32* slot; const u3
 // ---------------------------------------------------------------- incremental list edits: dominance counting
 struct DomItem { u32 time; u32 ref /* bit31: query; bits30..0: op index (query) */; int w; u32 acc; u32 gs, ge; };
 
-// Builds items in (position) order. Per position p holding a list element's insert row:
-//   queries first (the insert op itself if new; the first deleter if any), then points (+1 insert, -1 first deletion).
-enum { ES_ELEM = 1, ES_VISIBLE_BEFORE = 2, ES_NEW = 4, ES_DEL_NOW = 8 };
-struct ElemStateKernel {   // per position: state of the list element whose insert row sits there
-  DocRows d; const u32* succCnt; const u32* newSuccCnt; const u32* firstNewSucc; const u32* groupRows; const u32* groupVisible; const u32* groupOf; const u32* groupTouched;
-  u32* state; u32* nItems; u64* errWord;
-  HD void operator()(size_t p) const {
-    u32 st = 0, n = 0;
-    const bool list = d.keyStrLen[p] == NULL32;
-    if (list && (d.flags[p] & F_INSERT)) {
-      const u32 g = groupOf[p]; st = ES_ELEM;
-      const bool isNew = d.time[p] != 0, delNow = firstNewSucc[p] != 0xffffffffu;
-      if (groupTouched[g] && (groupRows[g] != 1 || flags_action(d.flags[p]) != ACT_SET)) raise(errWord, KE_UNSUPPORTED_OP, p);
-      const bool visibleBefore = !isNew && (groupRows[g] == 1 ? (succCnt[p] - newSuccCnt[p]) == 0 : groupVisible[g] > 0);
-      if (isNew) st |= ES_NEW;
-      if (visibleBefore) st |= ES_VISIBLE_BEFORE;
-      if (delNow) st |= ES_DEL_NOW;
-      const bool live = isNew || visibleBefore;      // contributes points during this call
-      if (live) { n += 1; if (delNow) n += 1; }      // +1 insertion, -1 first deletion
-      if (isNew) n += 1;                             // insert query
-      if (delNow && live) n += 1;                    // remove query (first deleter wins, new.js:1026)
-    } else if (list && (d.time[p] != 0 || firstNewSucc[p] != 0xffffffffu)) {
-      raise(errWord, KE_UNSUPPORTED_OP, p);          // update of an existing list element in incremental mode
-    }
-    state[p] = st; nItems[p] = n;
+// Per-position view of a list element's rows: row p exists from d.time[p] (0 = before this call) and is overwritten at
+// minSucc(p) (0 = before this call, 0xffffffff = never). The element whose insert row sits at e owns rows [e, e+rows).
+struct ListCtx {
+  DocRows d; const u32* succCnt; const u32* newSuccCnt; const u32* firstNewSucc; const u32* groupOf; const u32* groupFirst; const u32* groupRows;
+  HD u32 minSucc(u32 p) const { return succCnt[p] > newSuccCnt[p] ? 0u : firstNewSucc[p]; }
+  HD bool visAt(u32 e, u32 rows, u32 T) const {   // some row of the element is present and not overwritten after the op at time T
+    for (u32 r = e; r < e + rows; r++) if (d.time[r] <= T && minSucc(r) > T) return true;
+    return false;
   }
 };
-struct DomBuildKernel {
-  DocRows d; const u32* state; const u32* firstNewSucc; const u32* itemBase; const u32* objIdx; const u32* objStart /* [numObjs+1] positions */;
-  DomItem* items;
+// Visibility toggles of every list element over the times of this call: +1 when it becomes visible, -1 when it stops.
+struct ElemEventKernel {
+  int pass; ListCtx L; const u32* head; const u32* nQ; u32* nItems; const u32* itemBase; const u32* objIdx; const u32* objStart; DomItem* items;
+  HD void put(u32& k, u32 time, int w, u32 gs, u32 ge) const {
+    if (pass == 1) { DomItem a; a.time = time; a.ref = 0; a.w = w; a.acc = 0; a.gs = gs; a.ge = ge; items[k] = a; }
+    k++;
+  }
   HD void operator()(size_t p) const {
-    const u32 st = state[p]; if (!(st & ES_ELEM)) return;
-    const bool isNew = st & ES_NEW, delNow = st & ES_DEL_NOW, live = (st & ES_NEW) || (st & ES_VISIBLE_BEFORE);
-    u32 k = itemBase[p];
-    const u32 gs = itemBase[objStart[objIdx[p]]], ge = itemBase[objStart[objIdx[p] + 1]];
-    if (isNew) { DomItem q; q.time = d.time[p]; q.ref = 0x80000000u | (u32)(2 * p); q.w = 0; q.acc = 0; q.gs = gs; q.ge = ge; items[k++] = q; }
-    if (delNow && live) { DomItem q; q.time = firstNewSucc[p]; q.ref = 0x80000000u | (u32)(2 * p + 1); q.w = 0; q.acc = 0; q.gs = gs; q.ge = ge; items[k++] = q; }
-    if (live) {
-      DomItem a; a.time = d.time[p]; a.ref = 0; a.w = 1; a.acc = 0; a.gs = gs; a.ge = ge; items[k++] = a;
-      if (delNow) { DomItem b; b.time = firstNewSucc[p]; b.ref = 0; b.w = -1; b.acc = 0; b.gs = gs; b.ge = ge; items[k++] = b; }
+    const DocRows& d = L.d;
+    if (!(d.keyStrLen[p] == NULL32 && head[p] && (d.flags[p] & F_INSERT))) { if (pass == 0) nItems[p] = 0; return; }
+    const u32 e = (u32)p, rows = L.groupRows[L.groupOf[p]];
+    u32 gs = 0, ge = 0, k = 0;
+    if (pass == 1) { gs = itemBase[objStart[objIdx[p]]]; ge = itemBase[objStart[objIdx[p] + 1]]; k = itemBase[p] + nQ[p]; }
+    const u32 k0 = k;
+    if (rows == 1) {
+      const u32 s = d.time[e], x = L.minSucc(e);
+      if (x > s) { put(k, s, 1, gs, ge); if (x != 0xffffffffu) put(k, x, -1, gs, ge); }
+    } else {
+      for (u32 r = e; r < e + rows; r++) {
+        const u32 s = d.time[r], x = L.minSucc(r);
+        if (x <= s) continue;
+        bool firstS = true, firstX = true;
+        for (u32 q = e; q < r; q++) { const u32 s2 = d.time[q], x2 = L.minSucc(q); if (x2 <= s2) continue; if (s2 == s) firstS = false; if (x2 == x) firstX = false; }
+        if (firstS && (s == 0 || !L.visAt(e, rows, s - 1))) put(k, s, 1, gs, ge);   // visAt(s) holds because of row r
+        if (firstX && x != 0xffffffffu && !L.visAt(e, rows, x)) put(k, x, -1, gs, ge);   // visible just before x because of row r
+      }
     }
+    if (pass == 0) nItems[p] = nQ[p] + (k - k0);
   }
 };
 struct DomScanInput {   // per level: low word = 1 if the time bit is clear, high word = the item's weight if the bit is clear
@@ -301,59 +311,177 @@ struct DomResultKernel {   // route query results back: qIndex[2p + which] = ind
   const DomItem* items; u32* qIndex;
   HD void operator()(size_t i) const { if (items[i].ref & 0x80000000u) qIndex[items[i].ref & 0x7fffffffu] = items[i].acc; }
 };
-// edits in application order: one slot per op of the batch (insert rows -> insert edit, first deleters -> remove edit)
-struct OpEditFlagKernel {
-  OpRows ops; const u32* pos; IdTable t; const u32* firstNewSuccAtPos; const u32* stateAtPos; u32* emit;
-  HD void operator()(size_t i) const {
-    u32 e = 0;
-    if (ops.keyStrLen[i] == NULL32) {
-      const u32 act = flags_action(ops.flags[i]);
-      if (act == ACT_DEL) {
-        // emits a remove iff this op is the first deleter of a previously visible element
-        for (u32 j = 0; j < ops.predNum[i] && !e; j++) {
-          const u32 target = id_lookup(t, ops.predId[ops.predOff[i] + j]); if (target == ROW_NONE) continue;
-          const u32 p = pos[target];
-          if (firstNewSuccAtPos[p] == ops.time[i] && (stateAtPos[p] & (ES_NEW | ES_VISIBLE_BEFORE))) e = 1;
+// ---------------------------------------------------------------- incremental list edits: one thread per op group
+// An op group (new.js:1085-1138) is one insert op, or a run of same-author non-insert ops on one list element that do
+// not overwrite each other (GroupSplitKernel). With W = element visible just before the group and V = its rows that are
+// visible just after it, updatePatchProperty's state machine (new.js:985-1030) nets out to:
+//   V empty: remove if W.   V non-empty, W: update per V row, the first popping earlier edits of the same index
+//   (appendUpdate, new.js:798-825).   V non-empty, not W: insert of V[0] then updates.
+enum { EF_POP = 0x400, EF_GROUP_FIRST = 0x800, EF_START = 0x100, EF_MULTI = 0x200 };
+struct ListGroupKernel {
+  int pass; MapGroupCtx c; const u32* groupHead; IdTable t; const u32* rowOfOp; const u32* pos; ListCtx L;
+  u32* gCount; u32* gElem; u32* gT1; u32* gQOrd; u32* nQ; u32* elemHasRecs;                     // pass 0 out
+  const u32* itemBase; const u32* objIdx; const u32* objStart; DomItem* items;                     // pass 1: queries
+  const u32* gBase; const u32* qIndex; EditRec* out; u64* elemOut; u32* objKeyOut; u32* elemPosOut; u64* errWord;   // pass 2: records
+  HD static bool shown(u32 flags) { const u32 a = flags_action(flags); return a == ACT_SET || (a % 2 == 0 && a != ACT_DEL); }
+  HD void operator()(size_t t0) const {
+    const u32 i0 = c.opAt[t0];
+    const bool mine = groupHead[t0] && !c.isMapOp(i0);
+    if (pass == 0) {
+      u32 n = 0; gElem[t0] = ROW_NONE;
+      if (mine) {
+        u32 e;
+        if (c.ops.flags[i0] & F_INSERT) e = rowOfOp[i0] == ROW_NONE ? ROW_NONE : pos[rowOfOp[i0]];
+        else { const u32 row = id_lookup(t, c.ops.key[i0]); e = row == ROW_NONE ? ROW_NONE : L.groupFirst[L.groupOf[pos[row]]]; }
+        if (e != ROW_NONE) {
+          size_t tl = t0; while (tl + 1 < c.numOps && !groupHead[tl + 1]) tl++;
+          const u32 T0 = (u32)t0 + 1, T1 = (u32)tl + 1, rows = L.groupRows[L.groupOf[e]];
+          bool W = false; u32 nV = 0;
+          for (u32 r = e; r < e + rows; r++) {
+            const u32 s = L.d.time[r], x = L.minSucc(r);
+            if (s < T0 && x >= T0) W = true;
+            if (s <= T1 && x > T1 && shown(L.d.flags[r])) nV++;
+            const u32 a = flags_action(L.d.flags[r]);
+            if (a == ACT_INC || (a == ACT_SET && (L.d.valLen[r] & 15) == 8 && L.succCnt[r] > 0)) raise(errWord, KE_UNSUPPORTED_OP, r);   // counters inside lists
+          }
+          n = nV ? nV : (W ? 1u : 0u);
+          gElem[t0] = e; gT1[t0] = T1 | (W ? 0x80000000u : 0u);
+          if (n) { gQOrd[t0] = atomic_add(&nQ[e], 1u); if (nV) elemHasRecs[e] = 1; }
         }
-      } else if (ops.flags[i] & F_INSERT) e = 1;
+      }
+      gCount[t0] = n;
+      return;
     }
-    emit[i] = e;
+    if (!mine || gCount[t0] == 0) return;
+    const u32 e = gElem[t0];
+    if (pass == 1) {
+      DomItem q; q.time = (u32)t0 + 1; q.ref = 0x80000000u | (u32)t0; q.w = 0; q.acc = 0;
+      q.gs = itemBase[objStart[objIdx[e]]]; q.ge = itemBase[objStart[objIdx[e] + 1]];
+      items[itemBase[e] + gQOrd[t0]] = q;
+      return;
+    }
+    const u32 T0 = (u32)t0 + 1, T1 = gT1[t0] & 0x7fffffffu; const bool W = gT1[t0] >> 31;
+    const u32 rows = L.groupRows[L.groupOf[e]], idx = qIndex[t0];
+    // Reference quirk, reproduced: when one mergeDocChangeOps call walks from an element straight into the next one
+    // (new.js:1116-1121), the insert row of that next element is reported with the list index of the previous element:
+    // listIndex is only advanced after updatePatchProperty has seen the row (new.js:1204-1211). It matters for the edits
+    // that row itself produces (its own value, or the remove of an element whose insert row was the visible one).
+    u32 headIdx = idx;
+    if (t0 > 0 && !(c.ops.flags[i0] & F_INSERT)) {
+      size_t tp = t0 - 1; while (tp > 0 && !groupHead[tp]) tp--;
+      const u32 ip = c.opAt[tp];
+      if (!c.isMapOp(ip) && !(c.ops.flags[ip] & F_INSERT) && id_actor(c.ops.id[ip]) == id_actor(c.ops.id[i0]) && c.ops.obj[ip] == c.ops.obj[i0] && gElem[tp] != ROW_NONE && gElem[tp] != e) {
+        const u32 e1 = gElem[tp]; u32 p = e;
+        while (p > 0 && L.d.obj[p - 1] == L.d.obj[e] && L.d.time[p - 1] >= T0) p--;      // rows that arrive later in this batch were not there yet
+        if (p > 0 && L.d.obj[p - 1] == L.d.obj[e] && L.d.keyStrLen[p - 1] == NULL32 && L.groupFirst[L.groupOf[p - 1]] == e1 &&
+            L.visAt(e1, L.groupRows[L.groupOf[e1]], T0 - 1)) headIdx = idx - 1;
+      }
+    }
+    u32 k = gBase[t0], nV = 0;
+    for (u32 r = e; r < e + rows; r++) {
+      if (!(L.d.time[r] <= T1 && L.minSucc(r) > T1 && shown(L.d.flags[r]))) continue;
+      EditRec rec; rec.obj = L.d.obj[r]; rec.opId = L.d.id[r]; rec.index = r == e ? headIdx : idx; rec.valLen = L.d.valLen[r]; rec.valOff = L.d.valOff[r];
+      rec.kind = (nV == 0 ? (W ? (u32)EK_UPDATE | EF_POP : (u32)EK_INSERT) | EF_GROUP_FIRST : (u32)EK_UPDATE) | (flags_action(L.d.flags[r]) << 16);
+      out[k] = rec; elemOut[k] = L.d.id[e]; objKeyOut[k] = objIdx[e]; elemPosOut[k] = e; k++; nV++;
+    }
+    if (nV == 0) {
+      const bool atHead = L.d.time[e] < T0 && L.minSucc(e) >= T0;   // the remove is registered at the first previously visible row
+      EditRec rec; rec.obj = L.d.obj[e]; rec.opId = c.ops.id[i0]; rec.index = atHead ? headIdx : idx; rec.valLen = 0; rec.valOff = 0; rec.kind = (u32)EK_REMOVE | EF_GROUP_FIRST | (ACT_DEL << 16);
+      out[k] = rec; elemOut[k] = 0; objKeyOut[k] = objIdx[e]; elemPosOut[k] = e;
+    }
   }
 };
-struct OpEditEmitKernel {
-  OpRows ops; const u32* emit; const u32* slot; const u32* rowOfOp; const u32* pos; IdTable t; const u32* qIndex; EditRec* out; u64* elemOut; u32* objKeyOut /* sort key: index of the object in document order */; u32* timeOut; const u32* objIdx;
-  HD void operator()(size_t i) const {
-    if (!emit[i]) return;
-    EditRec e; e.obj = ops.obj[i]; u32 p;
-    if (flags_action(ops.flags[i]) == ACT_DEL) {
-      u32 target = ROW_NONE;
-      for (u32 j = 0; j < ops.predNum[i] && target == ROW_NONE; j++) target = id_lookup(t, ops.predId[ops.predOff[i] + j]);
-      p = pos[target];
-      e.opId = ops.id[i]; e.index = qIndex[2 * p + 1]; e.kind = EK_REMOVE | (ACT_DEL << 16); e.valLen = 0; e.valOff = 0; elemOut[slot[i]] = 0;
-    } else {
-      p = pos[rowOfOp[i]];
-      e.opId = ops.id[i]; e.index = qIndex[2 * p]; e.kind = EK_INSERT | (flags_action(ops.flags[i]) << 16); e.valLen = ops.valLen[i]; e.valOff = ops.valOff[i]; elemOut[slot[i]] = ops.id[i];
+// setupPatches link edits on list parents: an update per visible value of the element, at its index after the call
+struct ListLinkKernel {
+  int pass; ListCtx L; const u32* listLinkTime; const u32* elemVisScan; const u32* objIdx; const u32* objStart; u32* count; const u32* base; u32 recBase;
+  EditRec* out; u64* elemOut; u32* objKeyOut; u32* elemPosOut; u32* timeOut;
+  HD void operator()(size_t p) const {
+    if (listLinkTime[p] == 0xffffffffu) { if (pass == 0) count[p] = 0; return; }
+    const u32 e = (u32)p, rows = L.groupRows[L.groupOf[e]]; u32 n = 0, k = pass ? recBase + base[p] : 0;
+    for (u32 r = e; r < e + rows; r++) {
+      if (L.succCnt[r] != 0 || !ListGroupKernel::shown(L.d.flags[r])) continue;
+      if (pass == 1) {
+        EditRec rec; rec.obj = L.d.obj[r]; rec.opId = L.d.id[r]; rec.index = elemVisScan[e] - elemVisScan[objStart[objIdx[e]]]; rec.valLen = L.d.valLen[r]; rec.valOff = L.d.valOff[r];
+        rec.kind = (u32)EK_UPDATE | (n == 0 ? (u32)EF_GROUP_FIRST : 0u) | (flags_action(L.d.flags[r]) << 16);
+        out[k] = rec; elemOut[k] = L.d.id[e]; objKeyOut[k] = objIdx[e]; elemPosOut[k] = e; timeOut[k] = 0x80000000u | listLinkTime[p]; k++;
+      }
+      n++;
     }
-    out[slot[i]] = e; objKeyOut[slot[i]] = objIdx[p]; timeOut[slot[i]] = ops.time[i];
+    if (pass == 0) count[p] = n;
   }
 };
-// appendEdit coalescing (new.js:747-782): edit j continues the run of edit j-1
-struct RunFlagKernel {
-  EditRec* edits; const u64* elem; size_t n;
+struct GroupTimeKernel { const u32* gBase; const u32* gCount; u32* timeOut; HD void operator()(size_t t0) const { for (u32 k = 0; k < gCount[t0]; k++) timeOut[gBase[t0] + k] = (u32)t0 + 1; } };
+// appendUpdate's pops (new.js:798-825) on the ordered record list: the first record of a popping group kills the
+// contiguous insert/update records of the same element before it and turns into an insert if one of them was one.
+struct EditFixKernel {
+  const EditRec* edits; const u32* elemPos; u32* newKind; u32* pred; u32* dead; size_t n;
+  HD void operator()(size_t j) const {
+    const u32 kind = edits[j].kind; u32 nk = kind & 0xffu; u32 pr = j == 0 ? ROW_NONE : (u32)(j - 1);
+    if (kind & EF_POP) {
+      bool insertSeen = false; size_t k = j;
+      while (k > 0) {
+        const EditRec& a = edits[k - 1]; const u32 ka = a.kind & 0xffu;
+        if (!(a.obj == edits[j].obj && a.index == edits[j].index && (ka == EK_INSERT || ka == EK_UPDATE))) break;   // by index only, as the reference
+        dead[k - 1] = 1; k--;
+        if (ka == EK_INSERT) { insertSeen = true; break; }   // an update that an earlier pop turned into an insert had its own insert further down
+      }
+      if (insertSeen) nk = EK_INSERT;
+      pr = k == 0 ? ROW_NONE : (u32)(k - 1);
+    }
+    newKind[j] = nk; pred[j] = pr;
+  }
+};
+// appendEdit coalescing (new.js:747-782) against the record that was last in the list when this one was appended
+struct EditMergeKernel {
+  const EditRec* edits; const u64* elem; const u32* newKind; const u32* pred; u32* mergePrev; u32* multi;
   HD u32 cls(u32 valLen) const { const u32 t = valLen & 15; return t == 2 ? 1 : t; }
   HD void operator()(size_t j) const {
-    bool cont = false;
-    if (j > 0) {
-      const EditRec a = edits[j - 1], b = edits[j]; const u32 ka = a.kind & 0xff, kb = b.kind & 0xff;
+    bool cont = false; const u32 i = pred[j];
+    if (i != ROW_NONE) {
+      const EditRec a = edits[i], b = edits[j]; const u32 ka = newKind[i], kb = newKind[j];
       if (a.obj == b.obj) {
         if (ka == EK_INSERT && kb == EK_INSERT) {
           const u32 actA = (a.kind >> 16) & 0xffff, actB = (b.kind >> 16) & 0xffff;
-          cont = b.index == a.index + 1 && actA == ACT_SET && actB == ACT_SET && elem[j - 1] == a.opId && elem[j] == b.opId &&
+          cont = b.index == a.index + 1 && actA == ACT_SET && actB == ACT_SET && elem[i] == a.opId && elem[j] == b.opId &&
                  id_actor(a.opId) == id_actor(b.opId) && id_ctr(a.opId) + 1 == id_ctr(b.opId) && cls(a.valLen) == cls(b.valLen);
+          if (cont) { multi[i] = 1; multi[j] = 1; }
         } else if (ka == EK_REMOVE && kb == EK_REMOVE) cont = a.index == b.index;
       }
     }
-    if (!cont) edits[j].kind |= 0x100u;   // run start
+    mergePrev[j] = cont ? 1u : 0u;
+  }
+};
+struct EditLiveKernel { const u32* dead; u32* live; HD void operator()(size_t j) const { live[j] = dead[j] ? 0u : 1u; } };
+struct EditCompactKernel {
+  const EditRec* in; const u64* elemIn; const u32* dead; const u32* slot; const u32* newKind; const u32* mergePrev; const u32* multi; EditRec* out; u64* elemOut;
+  HD void operator()(size_t j) const {
+    if (dead[j]) return;
+    EditRec r = in[j];
+    r.kind = newKind[j] | (r.kind & 0xffff0000u) | (mergePrev[j] ? 0u : (u32)EF_START) | (multi[j] ? (u32)EF_MULTI : 0u);
+    out[slot[j]] = r; elemOut[slot[j]] = elemIn[j];
+  }
+};
+// getPatch: runs over the document-ordered edit list (nothing is ever popped there)
+struct RunFlagKernel {
+  EditRec* edits; const u64* elem; size_t n;
+  HD u32 cls(u32 valLen) const { const u32 t = valLen & 15; return t == 2 ? 1 : t; }
+  HD bool cont(size_t j) const {
+    if (j == 0 || j >= n) return false;
+    const EditRec a = edits[j - 1], b = edits[j]; const u32 ka = a.kind & 0xff, kb = b.kind & 0xff;
+    if (a.obj != b.obj) return false;
+    if (ka == EK_INSERT && kb == EK_INSERT) {
+      const u32 actA = (a.kind >> 16) & 0xffff, actB = (b.kind >> 16) & 0xffff;
+      return b.index == a.index + 1 && actA == ACT_SET && actB == ACT_SET && elem[j - 1] == a.opId && elem[j] == b.opId &&
+             id_actor(a.opId) == id_actor(b.opId) && id_ctr(a.opId) + 1 == id_ctr(b.opId) && cls(a.valLen) == cls(b.valLen);
+    }
+    return ka == EK_REMOVE && kb == EK_REMOVE && a.index == b.index;
+  }
+  HD void operator()(size_t j) const {
+    u32 f = 0;
+    const bool c0 = cont(j);
+    if (!c0) f |= EF_START;
+    if ((edits[j].kind & 0xff) == EK_INSERT && (c0 || cont(j + 1))) f |= EF_MULTI;
+    atomic_or(&edits[j].kind, f);
   }
 };
 

@@ -7,6 +7,7 @@
 //   C2  makeText + n single-op insert changes, one actor (C2b: the same ops in ONE bulk change)
 //   C3  makeText + A actors x n/A single-op changes, 70 % insert / 30 % delete, merge every 100 changes
 //   C4  nested maps: A actors x rounds x 100-op `set` changes, Zipf keys, Lamport-conflict heavy
+//   C6  one list of scalars and map objects: inserts, element updates / conflicts / deletes, keys set inside element maps
 // Seeded SplitMix64; actor k = first 16 bytes of SHA-256("amgpu-actor-" || seed || k).
 // The oracle (tests) decodes and re-applies these bytes, which cross-checks this independent encoder.
 #include <zlib.h>
@@ -263,10 +264,85 @@ void genC4(Trace& t, uint64_t seed, uint64_t nOps, int A, int nChild, int nKeysP
     maxOp = base + opsPerChange;
   }
 }
+
+// C6: one list of mixed elements: scalar inserts, inserted map objects with keys set inside them, value updates and
+// concurrent conflicting updates of existing elements, conflict-adding sets (empty pred), deletes, several ops of one
+// change on the same element. Every actor works on the state of the round start (so same-round writers conflict).
+void genRichList(Trace& t, uint64_t seed, uint64_t nOps, int A, int maxOpsPerChange) {
+  Rng rng{seed}; std::vector<Actor> actors = makeActors(seed, A); Encoder enc{&actors};
+  std::vector<uint64_t> seq(A, 0); std::vector<Hash> lastHash(A); std::vector<bool> hasHash(A, false);
+  OpId list{1, 0};
+  { Op mk; mk.action = 2; mk.isMapKey = true; mk.key = "items"; Hash h; t.add(enc.encode(0, ++seq[0], 1, {}, {mk}, &h), 1); lastHash[0] = h; hasHash[0] = true; }
+  uint64_t maxOp = 1, produced = 0;
+  struct Row { OpId id; bool isMap; };
+  struct Elem { OpId id; std::vector<Row> vis; };
+  std::vector<Elem> elems; std::unordered_map<uint64_t, size_t> elemAt;
+  std::unordered_map<uint64_t, std::vector<OpId>> mapKeyVis;   // (map object key * 8 + key index) -> visible set rows
+  auto keyOf = [](const OpId& o) { return o.ctr * 65536 + (uint64_t)o.actor; };
+  auto intValue = [&](Op& op) { op.hasValue = true; op.valTag = 4; sleb(op.valRaw, (int64_t)rng.below(100000)); };
+  while (produced < nOps) {
+    std::vector<Hash> roundHeads; for (int a = 0; a < A; a++) if (hasHash[a]) roundHeads.push_back(lastHash[a]);
+    const uint64_t base = maxOp; uint64_t newMax = maxOp;
+    struct Pending { std::vector<Elem> newElems; std::vector<std::pair<size_t, Row>> newRows; std::vector<OpId> overwritten; std::vector<std::pair<uint64_t, OpId>> mapSets; };
+    std::vector<Pending> pend(A);
+    for (int a = 0; a < A && produced < nOps; a++) {
+      Pending& P = pend[a]; std::vector<Op> ops; const int want = 1 + (int)rng.below(maxOpsPerChange);
+      std::unordered_map<size_t, std::vector<Row>> localVis;     // element slot -> rows visible to this change so far
+      std::unordered_map<uint64_t, std::vector<OpId>> localKey;  // nested map key -> rows visible to this change so far
+      auto visOf = [&](size_t e) -> std::vector<Row>& { auto it = localVis.find(e); if (it == localVis.end()) it = localVis.emplace(e, elems[e].vis).first; return it->second; };
+      OpId lastIns{0, 0}; long lastTouched = -1;
+      while ((int)ops.size() < want) {
+        const uint64_t ctr = base + 1 + ops.size(); const OpId me{ctr, a}; const double u = rng.unit(); Op op; op.obj = list;
+        size_t e = elems.empty() ? 0 : (size_t)rng.below(elems.size());
+        if (lastTouched >= 0 && rng.unit() < 0.25) e = (size_t)lastTouched;   // several ops of one change on the same element
+        if (elems.empty() || u < 0.35) {            // insert a scalar
+          op.action = 1; op.insert = true; intValue(op);
+          const double w = rng.unit(); op.elem = w < 0.6 ? lastIns : (w < 0.95 && !elems.empty() ? elems[rng.below(elems.size())].id : OpId{0, 0});
+          P.newElems.push_back(Elem{me, {Row{me, false}}}); lastIns = me; ops.push_back(op);
+        } else if (u < 0.45) {                      // insert a map object and set a key inside it
+          op.action = 0; op.insert = true; op.elem = rng.unit() < 0.5 ? lastIns : elems[e].id;
+          P.newElems.push_back(Elem{me, {Row{me, true}}}); lastIns = me; ops.push_back(op);
+          if ((int)ops.size() < want) { Op st; st.action = 1; st.obj = me; st.isMapKey = true; st.key = "k0"; intValue(st); const OpId sid{ctr + 1, a}; P.mapSets.push_back({keyOf(me) * 8, sid}); localKey[keyOf(me) * 8] = {sid}; ops.push_back(st); }
+        } else if (u < 0.70) {                      // overwrite the value(s) of an element (also re-inserts a concurrently deleted one)
+          std::vector<Row>& v = visOf(e); op.action = rng.unit() < 0.15 ? 0 : 1; op.elem = elems[e].id; if (op.action == 1) intValue(op);
+          for (auto& r : v) { op.pred.push_back(r.id); P.overwritten.push_back(r.id); }
+          v.clear(); v.push_back(Row{me, op.action == 0}); P.newRows.push_back({e, v.back()}); lastTouched = (long)e; ops.push_back(op);
+        } else if (u < 0.75) {                      // add a conflicting value without overwriting anything
+          std::vector<Row>& v = visOf(e); op.action = 1; op.elem = elems[e].id; intValue(op);
+          v.push_back(Row{me, false}); P.newRows.push_back({e, v.back()}); lastTouched = (long)e; ops.push_back(op);
+        } else if (u < 0.88) {                      // delete an element
+          std::vector<Row>& v = visOf(e); if (v.empty()) continue;
+          op.action = 3; op.elem = elems[e].id; for (auto& r : v) { op.pred.push_back(r.id); P.overwritten.push_back(r.id); }
+          v.clear(); lastTouched = (long)e; ops.push_back(op);
+        } else {                                    // set a key inside a map that lives in a list element
+          std::vector<Row>& v = visOf(e); const Row* m = nullptr; for (auto& r : v) if (r.isMap) m = &r;
+          if (!m) continue;
+          const uint64_t kk = keyOf(m->id) * 8 + rng.below(3); op.obj = m->id; op.action = 1; op.isMapKey = true; op.key = std::string("k") + (char)('0' + kk % 8); intValue(op);
+          auto it = localKey.find(kk); if (it == localKey.end()) it = localKey.emplace(kk, mapKeyVis[kk]).first;
+          for (auto& r : it->second) { op.pred.push_back(r); P.overwritten.push_back(r); }
+          it->second = {me}; P.mapSets.push_back({kk, me}); ops.push_back(op);
+        }
+      }
+      std::vector<Hash> deps = roundHeads; if (hasHash[a] && std::find(deps.begin(), deps.end(), lastHash[a]) == deps.end()) deps.push_back(lastHash[a]);
+      Hash h; t.add(enc.encode(a, ++seq[a], base + 1, deps, ops, &h), ops.size()); lastHash[a] = h; hasHash[a] = true;
+      produced += ops.size(); newMax = std::max<uint64_t>(newMax, base + ops.size());
+    }
+    // merge the round: rows named in any pred disappear, everything else written this round becomes visible
+    std::unordered_map<uint64_t, bool> gone; for (auto& P : pend) for (auto& o : P.overwritten) gone[keyOf(o)] = true;
+    for (auto& el : elems) { std::vector<Row> keep; for (auto& r : el.vis) if (!gone.count(keyOf(r.id))) keep.push_back(r); el.vis.swap(keep); }
+    for (auto& kv : mapKeyVis) { std::vector<OpId> keep; for (auto& r : kv.second) if (!gone.count(keyOf(r))) keep.push_back(r); kv.second.swap(keep); }
+    for (auto& P : pend) {
+      for (auto& nr : P.newRows) if (!gone.count(keyOf(nr.second.id))) elems[nr.first].vis.push_back(nr.second);
+      for (auto& ms : P.mapSets) if (!gone.count(keyOf(ms.second))) mapKeyVis[ms.first].push_back(ms.second);
+      for (auto& ne : P.newElems) { Elem el = ne; if (gone.count(keyOf(el.id))) el.vis.clear(); elemAt[keyOf(el.id)] = elems.size(); elems.push_back(el); }
+    }
+    maxOp = newMax;
+  }
+}
 }  // namespace
 
 extern "C" {
-// config: 1 = C1, 2 = C2, 22 = C2b (bulk), 3 = C3, 4 = C4. Returns malloc'ed blob + offsets (n_changes + 1).
+// config: 1 = C1, 2 = C2, 22 = C2b (bulk), 3 = C3, 4 = C4, 6 = C6 (rich list). Returns malloc'ed blob + offsets (n_changes + 1).
 int amg_trace_generate(int config, uint64_t seed, uint64_t n_ops, int n_actors, uint8_t** blob, size_t* blob_len, uint64_t** offsets, size_t* n_changes, uint64_t* total_ops) {
   Trace t;
   if (config == 1) genC1(t, seed);
@@ -274,6 +350,7 @@ int amg_trace_generate(int config, uint64_t seed, uint64_t n_ops, int n_actors, 
   else if (config == 22) genText(t, seed, n_ops, 1, true, 0.0, 100);
   else if (config == 3) genText(t, seed, n_ops, n_actors > 0 ? n_actors : 10, false, 0.3, 100);
   else if (config == 4) genC4(t, seed, n_ops, n_actors > 0 ? n_actors : 100, 100, 100, 100);
+  else if (config == 6) genRichList(t, seed, n_ops, n_actors > 0 ? n_actors : 4, 6);
   else return 1;
   *blob = (uint8_t*)malloc(t.blob.size() + 64); memcpy(*blob, t.blob.data(), t.blob.size()); memset(*blob + t.blob.size(), 0, 64); *blob_len = t.blob.size();
   *offsets = (uint64_t*)malloc(t.offsets.size() * 8); memcpy(*offsets, t.offsets.data(), t.offsets.size() * 8);

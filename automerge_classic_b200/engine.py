@@ -200,10 +200,10 @@ class FlatPatch:
             if p is None or 'edits' not in p:
                 continue
             edits = p['edits']
-            kind, run_start, action = int(rec['kind']) & 0xff, bool(int(rec['kind']) & 0x100), int(rec['kind']) >> 16
+            kind, run_start, multi, action = int(rec['kind']) & 0xff, bool(int(rec['kind']) & 0x100), bool(int(rec['kind']) & 0x200), int(rec['kind']) >> 16
             index = int(rec['index'])
             if kind == 1:
-                if run_start or not edits or edits[-1]['action'] != 'remove':
+                if run_start:
                     edits.append({'action': 'remove', 'index': index, 'count': 1})
                 else:
                     edits[-1]['count'] += 1
@@ -217,19 +217,15 @@ class FlatPatch:
                 continue
             if kind == 2:
                 edits.append({'action': 'update', 'index': index, 'opId': self.op_id(rec['opId']), 'value': value})
-            elif run_start or not edits or edits[-1]['action'] not in ('insert', 'multi-insert'):
-                edits.append({'action': 'insert', 'index': index, 'elemId': self.op_id(self.edit_elem[j]), 'opId': self.op_id(rec['opId']), 'value': value})
+            elif not run_start:
+                edits[-1]['values'].append(value['value'])     # continues the multi-insert opened by an earlier record
+            elif multi:
+                edit = {'action': 'multi-insert', 'index': index, 'elemId': self.op_id(self.edit_elem[j]), 'values': [value['value']]}
+                if value.get('datatype'):
+                    edit['datatype'] = value['datatype']
+                edits.append(edit)
             else:
-                last = edits[-1]
-                if last['action'] == 'insert':
-                    first = last.pop('value')
-                    last.pop('opId')
-                    last['action'] = 'multi-insert'
-                    if value.get('datatype'):
-                        last['datatype'] = value['datatype']
-                    last['values'] = [first['value'], value['value']]
-                else:
-                    last['values'].append(value['value'])
+                edits.append({'action': 'insert', 'index': index, 'elemId': self.op_id(self.edit_elem[j]), 'opId': self.op_id(rec['opId']), 'value': value})
         out = self.header()
         out['diffs'] = patches['_root']
         return out

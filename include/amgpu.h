@@ -93,7 +93,9 @@ void amg_buffers_free(amg_buffers* l);
  * (amg_arena); valLen is the reference's VALUE_LEN tag (length << 4 | type, columnar.js:46-49).
  * props.flags = action << 8 | 1 if the key has no visible value (reference emits `key: {}`);
  * edits.kind = (0 insert | 1 remove | 2 update) | 0x100 if the edit starts a new run (edits without the bit
- * continue the previous insert as `multi-insert` / add to the previous remove's count, new.js:747-782) | action << 16.
+ * continue the previous insert as `multi-insert` / add to the previous remove's count, new.js:747-782)
+ * | 0x200 if the insert is rendered as `multi-insert` (set on every member of a run, and on a run start whose
+ * followers were popped again by appendUpdate, new.js:811-813) | action << 16.
  * The nested Patch object of @types/automerge/index.d.ts:236-316 is assembled from this by the binding. */
 /* The bytes live in a pinned buffer owned by the backend: valid until the next call on the same backend. */
 const uint8_t* amg_patch_bytes(const amg_patch* p, size_t* len);

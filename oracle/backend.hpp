@@ -378,6 +378,10 @@ static int64_t mergeDocChangeOps(Patches& patches, Block& newBlock, std::vector<
       takeDocOp = true;
     }
 
+    // Not in the reference: with neither side taken nothing changes any more, i.e. the reference spins forever here. That
+    // happens when an insertion's reference element has update rows on both sides of a block boundary: seekWithinBlock's
+    // resumeInsertion path (new.js:59-73, 143-145) compares against object ids it never read and stops at the block start.
+    if (!takeDocOp && takeChangeOps == 0) throw RangeError("oracle: the reference does not terminate on this input (mergeDocChangeOps makes no progress)");
     if (takeDocOp) {
       outOps.push_back(docOp);
       addBlockOperation(newBlock, docOp, ds, false);

@@ -62,6 +62,13 @@ def test_trace_parity(gpu_doc, oracle_mod, cfg, n, a):
     parity_checks.check_trace_parity(gpu_doc, oracle_mod, cfg, n, a)
 
 
+@pytest.mark.parametrize('n,a,chunk', [(60, 2, 1000), (300, 3, 7), (400, 4, 50), (200, 1, 3), (450, 5, 1), (1500, 4, 1000)])
+def test_rich_list_parity(gpu_doc, oracle_mod, n, a, chunk):
+    """C6: element updates / conflicts / deletes / re-insertions and objects nested in list elements."""
+    compared = sum(parity_checks.check_rich_list(gpu_doc, oracle_mod, seed, n, a, chunk) for seed in range(1, 9))
+    assert compared >= 3
+
+
 def test_incremental_calls_match_bulk(gpu_doc, oracle_mod):
     parity_checks.check_incremental_calls(gpu_doc, oracle_mod)
 

@@ -49,6 +49,12 @@ def test_trace_parity_emu(emu_doc, oracle_mod, cfg, n, a):
     parity_checks.check_trace_parity(emu_doc, oracle_mod, cfg, n, a)
 
 
+@pytest.mark.parametrize('n,a,chunk', [(60, 2, 1000), (300, 3, 7), (400, 4, 50), (200, 1, 3), (450, 5, 1)])
+def test_rich_list_emu(emu_doc, oracle_mod, n, a, chunk):
+    compared = sum(parity_checks.check_rich_list(emu_doc, oracle_mod, seed, n, a, chunk) for seed in range(1, 7))
+    assert compared >= 4
+
+
 def test_incremental_calls_emu(emu_doc, oracle_mod):
     parity_checks.check_incremental_calls(emu_doc, oracle_mod)
 
