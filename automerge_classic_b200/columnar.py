@@ -212,8 +212,9 @@ def encode_value(op, val_len, val_raw):
         raise ValueError('Unsupported value in operation: %r' % (value,))
 
 
-def encode_change_raw(change, compress=True):
-    """Returns (bytes, hash_hex). `change` is the JSON form used throughout the reference's tests."""
+def encode_change_raw(change, compress=True, level=6):
+    """Returns (bytes, hash_hex). `change` is the JSON form used throughout the reference's tests.
+    `level` is the zlib level of the DEFLATE step (the reference uses pako's default, 6)."""
     actor = change['actor']
     ops = expand_multi_ops(change['ops'], change['startOp'], actor)
     # parseAllOpIds(single=True): actor table = [author] + sorted(other actors)
@@ -301,14 +302,14 @@ def encode_change_raw(change, compress=True):
     digest = hashlib.sha256(header + bytes(body)).digest()
     raw = MAGIC + digest[:4] + header + bytes(body)
     if compress and len(raw) >= DEFLATE_MIN_SIZE:
-        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
         comp = co.compress(bytes(body)) + co.flush()
         raw = MAGIC + digest[:4] + bytes([2]) + uleb(len(comp)) + comp
     return raw, digest.hex()
 
 
-def encode_change(change, compress=True):
-    return encode_change_raw(change, compress)[0]
+def encode_change(change, compress=True, level=6):
+    return encode_change_raw(change, compress, level)[0]
 
 
 def change_hash(change):

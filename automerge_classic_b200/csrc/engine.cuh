@@ -16,6 +16,7 @@
 #include <thread>
 #include <zlib.h>
 #include "patch.cuh"
+#include "inflate.cuh"
 #include "prims.cuh"
 
 namespace amg {
@@ -93,7 +94,7 @@ class Engine {
   DBuf<u32> elemPos, keyRankAt, objPos, head, headScan, groupOf, groupRows, groupVisible, groupFirst, groupTouched, groupLinked, objTouchedAt, linkDone, emit, marker, slot;
   DBuf<u32> isObjHead, objIdx, objStart, elemVis, elemVisScan, rowEmit, firstVis, state, nItems, itemBase, qIndex, zero, wzero, zscan, wscan, editObjKey;
   DBuf<DomItem> items, items2; DBuf<PropRec> propOut; DBuf<EditRec> editOut, editOut2; DBuf<u64> editElem, editElem2;
-  DBuf<u32> groupHasChild, gCount, gElem, gT1, gQOrd, gBase, nQ, elemHasRecs, listLinkTime, editElemPos, editElemPos2, editKind, editPred, editDead, editMerge, editMulti, editLive;
+  DBuf<u32> inflLen, inflOff, groupHasChild, gCount, gElem, gT1, gQOrd, gBase, nQ, elemHasRecs, listLinkTime, editElemPos, editElemPos2, editKind, editPred, editDead, editMerge, editMulti, editLive;
   DBuf<u32> seqSlot, actorCnt, actorBaseD, clockD, changeActor, editTime; DBuf<u8> hashTmp; bool batchInOrder = true;
   DBuf<u32> finalTime, gFailed, memberFinal, opAt, runHead, opGroupHead; DBuf<u64> gBound; DocRows workView{}; DBuf<HostChange> chPairs; std::thread mirrorThread; DBuf<u32> largeFlag, largeSlot, largeList; size_t lastNumLarge = 0; DBuf<u64> zwScan; DBuf<u32> deflList, patchTriples;
 
@@ -145,6 +146,7 @@ class Engine {
       case KE_CHECKSUM: throw Error(AMG_ERR_RANGE, "checksum does not match data");
       case KE_TRAILING: throw Error(AMG_ERR_RANGE, "Encoded change has trailing data");
       case KE_CHUNK_TYPE: throw Error(AMG_ERR_RANGE, "Unexpected chunk type");
+      case KE_DEFLATE: throw Error(AMG_ERR_RANGE, "invalid deflate data");
       case KE_TRUNCATED: throw Error(AMG_ERR_RANGE, "buffer ended with incomplete number");
       case KE_NUM_RANGE: throw Error(AMG_ERR_RANGE, "number out of range");
       case KE_COL_ORDER: throw Error(AMG_ERR_RANGE, "Columns must be in ascending order");

@@ -111,17 +111,9 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     for (size_t i = 0; i < n; i++) { batch[i].off = (u32)offsets[i] + shift; batch[i].len = (u32)(offsets[i + 1] - offsets[i]); }
     uploaded = true; cur += tot; dbgMark("stage:batch-filled");
   } else {
-    bool anyDeflated = false;
     for (size_t i = 0; i < n; i++) {
       const u8* p = blob ? blob + offsets[i] : bufs[i]; const size_t l = blob ? (size_t)(offsets[i + 1] - offsets[i]) : lens[i];
-      if (l > 8 && p[8] == 2) {   // reference columnar.js:742
-        std::string inflated = inflateChange(p, l);
-        if ((u64)cur + inflated.size() + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
-        if (!anyDeflated) { anyDeflated = true; batchOriginal.assign(n + Bq, HostChange{0, 0}); }
-        hostArena.append(p, l); batchOriginal[i] = HostChange{(u32)cur, (u32)l}; cur += l;   // keep the original bytes (getChanges returns them)
-        hostArena.append(inflated.data(), inflated.size());
-        batch[i] = HostChange{(u32)cur, (u32)inflated.size()}; cur += inflated.size();
-      } else { hostArena.append(p, l); batch[i] = HostChange{(u32)cur, (u32)l}; cur += l; }
+      hostArena.append(p, l); batch[i] = HostChange{(u32)cur, (u32)l}; cur += l;
     }
   }
   if (Bq > 0) {
@@ -142,50 +134,43 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   // ------------------------------------------------------------ 1. hash + header parse
   dev_memset(ctx, errWord.p, 0, 16);
   hashes.ensure(ctx, (numApplied + B) * 32 + 64, numApplied * 32);
-  deflList.ensure(ctx, B + 1);
   std::vector<u32> deflIdx;
-  if (uploaded) {   // which changes of the bulk batch are DEFLATEd? (one byte per change; the host then inflates only those)
-    foreach(ctx, B, DeflateScanKernel{arena.p, chOff.p, chLen.p, errWord.p + 1, deflList.p});
-    u64 nd64 = 0; d2h(ctx, &nd64, errWord.p + 1, 8); sync(ctx);
-    if (nd64) { deflIdx.resize((size_t)nd64); d2h(ctx, deflIdx.data(), deflList.p, (size_t)nd64 * 4); sync(ctx); }
+  {
+    // Which changes of the bulk batch are DEFLATEd (columnar.js:742)? Those are inflated on the device, behind the batch:
+    // flag -> scan -> ordered list -> InflateKernel pass 0 (sizes) -> scan -> pass 1 (bytes); the originals stay in place.
+    emit.ensure(ctx, B + 1); slot.ensure(ctx, B + 2); deflList.ensure(ctx, B + 1);
+    foreach(ctx, B, DeflateFlagKernel{arena.p, chOff.p, chLen.p, emit.p});
+    scan_exclusive(ctx, scanTmp, emit.p, slot.p, B);
+    const size_t nd = readU32(slot.p + B);
     dbgMark("sha:deflate-scanned");
-  }
-  // SHA-256 of every change runs on the GPU while the host inflates (zlib, as columnar.js:813-823 does with pako)
-  foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr, uploaded ? deflList.p : nullptr});
-  if (!deflIdx.empty()) {
-    const size_t nd = deflIdx.size();
-    std::sort(deflIdx.begin(), deflIdx.end());
-    std::vector<std::string> inflated(nd); std::string firstError;
-    { unsigned nt = std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency())); if (nd < 64) nt = 1;
-      std::vector<std::thread> ts; std::vector<std::string> errs(nt);
-      for (unsigned t = 0; t < nt; t++) ts.emplace_back([&, t] {
-        z_stream zs; memset(&zs, 0, sizeof(zs)); if (inflateInit2(&zs, -15) != Z_OK) { errs[t] = "inflateInit failed"; return; }
-        try { for (size_t k = t; k < nd; k += nt) { const u32 b = deflIdx[k]; inflated[k] = inflateChange(blob + offsets[b], (size_t)(offsets[b + 1] - offsets[b]), &zs); } } catch (std::exception& e) { errs[t] = e.what(); }
-        inflateEnd(&zs); });
-      for (auto& th : ts) th.join();
-      for (auto& e : errs) if (!e.empty() && firstError.empty()) firstError = e; }
-    dbgMark("sha:inflated");
-    if (!firstError.empty()) throw Error(AMG_ERR_RANGE, firstError);
-    if (mirrorThread.joinable()) mirrorThread.join();   // the mirror may have to grow
-    dbgMark("sha:mirror-joined");
-    size_t extra = 0; for (auto& x : inflated) extra += x.size();
-    if ((u64)cur + extra + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
-    // the inflated bytes go behind the batch and the entries are re-pointed; the original bytes stay where they are
-    const size_t extraStart = cur; hostArena.resize(cur + extra); batchOriginal.assign(B, HostChange{0, 0});
-    std::vector<u32> triples(3 * nd);
-    for (size_t k = 0; k < nd; k++) {
-      const u32 b = deflIdx[k]; batchOriginal[b] = batch[b];
-      memcpy(hostArena.data() + cur, inflated[k].data(), inflated[k].size());
-      batch[b] = HostChange{(u32)cur, (u32)inflated[k].size()}; triples[3 * k] = b; triples[3 * k + 1] = batch[b].off; triples[3 * k + 2] = batch[b].len; cur += inflated[k].size();
+    foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr, nd ? deflList.p : nullptr});
+    if (nd > 0) {
+      foreach(ctx, B, CompactKernel{emit.p, slot.p, deflList.p});
+      inflLen.ensure(ctx, nd + 1); inflOff.ensure(ctx, nd + 2); patchTriples.ensure(ctx, 2 * nd + 2);
+      u32* origOff = patchTriples.p; u32* origLen = patchTriples.p + nd;
+      foreach(ctx, nd, InflateKernel{0, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, nullptr, 0, origOff, origLen, errWord.p});
+      scan_exclusive(ctx, scanTmp, inflLen.p, inflOff.p, nd);
+      const size_t extra = readU32(inflOff.p + nd);
+      { u64 ew0 = 0; d2h(ctx, &ew0, errWord.p, 8); sync(ctx); if (ew0) throwKernelError(ew0, actorIds); }
+      if ((u64)cur + extra + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
+      const size_t extraStart = cur; cur += extra;
+      arena.ensure(ctx, cur + 64, extraStart);
+      foreach(ctx, nd, InflateKernel{1, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, inflOff.p, (u32)extraStart, origOff, origLen, errWord.p});
+      dev_memset(ctx, arena.p + cur, 0, 64);
+      foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, deflList.p, nullptr});
+      // host bookkeeping: which entries moved where, and the inflated bytes for the mirror
+      deflIdx.resize(nd); std::vector<u32> newLen(nd), newOff(nd), oOff(nd), oLen(nd);
+      d2h(ctx, deflIdx.data(), deflList.p, nd * 4); d2h(ctx, newLen.data(), inflLen.p, nd * 4); d2h(ctx, newOff.data(), inflOff.p, nd * 4);
+      d2h(ctx, oOff.data(), origOff, nd * 4); d2h(ctx, oLen.data(), origLen, nd * 4);
+      if (mirrorThread.joinable()) mirrorThread.join();   // the mirror has to grow
+      dbgMark("sha:mirror-joined");
+      hostArena.resize(cur);
+      d2h(ctx, hostArena.data() + extraStart, arena.p + extraStart, extra);
+      sync(ctx);
+      if (batchOriginal.empty()) batchOriginal.assign(B, HostChange{0, 0});
+      for (size_t k = 0; k < nd; k++) { const u32 bi = deflIdx[k]; batchOriginal[bi] = HostChange{oOff[k], oLen[k]}; batch[bi] = HostChange{(u32)extraStart + newOff[k], newLen[k]}; }
+      dbgMark("sha:inflated");
     }
-    arena.ensure(ctx, cur + 64, extraStart); h2d(ctx, arena.p + extraStart, hostArena.data() + extraStart, cur - extraStart); dev_memset(ctx, arena.p + cur, 0, 64);
-    dbgMark("sha:extra-uploaded");
-    patchTriples.ensure(ctx, 3 * nd); h2d(ctx, patchTriples.p, triples.data(), triples.size() * 4);
-    foreach(ctx, nd, PatchPairsKernel{patchTriples.p, chOff.p, chLen.p});
-    h2d(ctx, deflList.p, deflIdx.data(), nd * 4);
-    foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, deflList.p, nullptr});
-    sync(ctx);   // `triples` / `deflIdx` are pageable host memory: keep them alive until the copies are done
-    dbgMark("sha:resynced");
   }
   timer.mark(); hostMark();
   meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
@@ -495,7 +480,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     if (appliedH.empty()) {   // all applied, in order
       const u32 base0 = (u32)changes.size();
       changes.insert(changes.end(), batch.begin(), batch.end());
-      if (!batchOriginal.empty()) { if (deflIdx.empty()) { for (size_t b = 0; b < B; b++) if (batchOriginal[b].len) deflatedOriginal[base0 + (u32)b] = batchOriginal[b]; } else for (u32 b : deflIdx) deflatedOriginal[base0 + b] = batchOriginal[b]; }
+      if (!batchOriginal.empty()) { if (deflIdx.empty() || Bq > 0) { for (size_t b = 0; b < B; b++) if (batchOriginal[b].len) deflatedOriginal[base0 + (u32)b] = batchOriginal[b]; } else for (u32 b : deflIdx) deflatedOriginal[base0 + b] = batchOriginal[b]; }
     }
     else {
       std::vector<u32> byRank(numNew);

@@ -65,6 +65,54 @@ def check_rich_list(gpu_doc, oracle_mod, seed, n, a, chunk):
     return True
 
 
+def check_deflate_variants(gpu_doc, oracle_mod):
+    """DEFLATEd changes (columnar.js:738-742, 798-823) built with stored, fixed-Huffman and dynamic-Huffman blocks, long
+    matches and incompressible payloads: same patches and op table as the oracle; corrupt streams are rejected."""
+    import random
+    from automerge_classic_b200 import columnar
+    rnd = random.Random(7)
+    actor = '0123456789abcdef0123456789abcdef'
+    payloads = [
+        'a' * 5000,                                                             # one long match chain
+        ''.join(rnd.choice('abcdefghijklmnopqrstuvwxyz ') for _ in range(3000)),  # text-like: dynamic codes
+        ''.join(chr(rnd.randrange(0x20, 0x2fff)) for _ in range(2000)),         # close to incompressible
+        'xy' * 40000,                                                           # > 64 KiB: several stored blocks at level 0
+        'The quick brown fox jumps over the lazy dog. ' * 30,
+    ]
+    orc, g = oracle_mod.OracleDoc(), gpu_doc()
+    deps, seq, start, batch = [], 0, 1, []
+    for level in (0, 1, 6, 9):
+        for pi, text in enumerate(payloads):
+            seq += 1
+            change = {'actor': actor, 'seq': seq, 'startOp': start, 'time': 0, 'message': '', 'deps': deps, 'ops': [
+                {'action': 'set', 'obj': '_root', 'key': 'k%d_%d' % (level, pi), 'value': text, 'pred': []}]}
+            raw, h = columnar.encode_change_raw(change, True, level)
+            assert raw[8] == 2
+            batch.append(raw); deps = [h]; start += 1
+    half = len(batch) // 2
+    for part in (batch[:half], batch[half:]):
+        po, pg = orc.apply_changes(part), g.apply_changes(part)
+        d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+        assert d is None, d
+    _dump_equal(g, orc)
+    assert g.get_changes([]) == batch          # the original (compressed) bytes come back
+    # corrupt streams: flip bytes inside the compressed body of a fresh change
+    from automerge_classic_b200.engine import AmgError
+    seq += 1
+    change = {'actor': actor, 'seq': seq, 'startOp': start, 'time': 0, 'message': '', 'deps': deps, 'ops': [
+        {'action': 'set', 'obj': '_root', 'key': 'bad', 'value': payloads[1], 'pred': []}]}
+    raw = bytearray(columnar.encode_change(change, True, 6))
+    rejected = 0
+    for pos in (12, 20, 40, len(raw) // 2, len(raw) - 3):
+        bad = bytearray(raw); bad[pos] ^= 0x5a
+        try:
+            g.apply_changes([bytes(bad)])
+        except AmgError:
+            rejected += 1
+    assert rejected == 5                         # either the stream breaks or the checksum over the inflated bytes does
+    assert g.apply_changes([bytes(raw)])['pendingChanges'] == 0
+
+
 def check_incremental_calls(gpu_doc, oracle_mod):
     """Applying a trace in several applyChanges calls gives the same patches as the oracle call by call."""
     from automerge_classic_b200 import tracegen

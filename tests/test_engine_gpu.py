@@ -69,6 +69,10 @@ def test_rich_list_parity(gpu_doc, oracle_mod, n, a, chunk):
     assert compared >= 3
 
 
+def test_deflate_variants(gpu_doc, oracle_mod):
+    parity_checks.check_deflate_variants(gpu_doc, oracle_mod)
+
+
 def test_incremental_calls_match_bulk(gpu_doc, oracle_mod):
     parity_checks.check_incremental_calls(gpu_doc, oracle_mod)
 

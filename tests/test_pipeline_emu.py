@@ -55,6 +55,10 @@ def test_rich_list_emu(emu_doc, oracle_mod, n, a, chunk):
     assert compared >= 4
 
 
+def test_deflate_variants_emu(emu_doc, oracle_mod):
+    parity_checks.check_deflate_variants(emu_doc, oracle_mod)
+
+
 def test_incremental_calls_emu(emu_doc, oracle_mod):
     parity_checks.check_incremental_calls(emu_doc, oracle_mod)
 
