@@ -48,8 +48,7 @@ struct amg_backend {
     g.known = to;
   }
   std::string changeBytes(u32 idx) {
-    auto it = eng.deflatedOriginal.find(idx);
-    if (it != eng.deflatedOriginal.end()) return std::string((const char*)eng.hostArena.data() + it->second.off, it->second.len);
+    if (const HostChange* o = eng.originalOf(idx)) return std::string((const char*)eng.hostArena.data() + o->off, o->len);
     const HostChange& c = eng.changes[idx];
     return std::string((const char*)eng.hostArena.data() + c.off, c.len);
   }

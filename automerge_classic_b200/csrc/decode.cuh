@@ -72,6 +72,12 @@ struct ByteReader {
   HD bool done() const { return pos >= end; }
   // encoding.js:416-441 readUint64 + :389-395 53-bit range check
   HD u64 uleb() {
+    if (pos + 1 < end) {   // one- and two-byte values (nearly all of them) without the 64-bit loop
+      const u32 b0 = base[pos];
+      if (!(b0 & 0x80)) { pos++; return b0; }
+      const u32 b1 = base[pos + 1];
+      if (!(b1 & 0x80)) { pos += 2; return (b0 & 0x7f) | (b1 << 7); }
+    }
     u64 result = 0; int shift = 0;
     while (pos < end) {
       u8 b = base[pos];
@@ -83,6 +89,12 @@ struct ByteReader {
   }
   // encoding.js:450-488 readInt64 + :402-408
   HD long long sleb() {
+    if (pos + 1 < end) {
+      const u32 b0 = base[pos];
+      if (!(b0 & 0x80)) { pos++; return (long long)((int)(b0 << 25) >> 25); }
+      const u32 b1 = base[pos + 1];
+      if (!(b1 & 0x80)) { pos += 2; return (long long)((int)(((b0 & 0x7f) | (b1 << 7)) << 18) >> 18); }
+    }
     u64 result = 0; int shift = 0;
     while (pos < end) {
       u8 b = base[pos];

@@ -74,7 +74,12 @@ class Engine {
   std::vector<std::pair<u32, u32>> actorRep;   // arena (offset, length) of each actor's id bytes
   std::vector<HostChange> changes;     // applied, in application order
   std::vector<std::array<u8, 32>> changeHashes;   // host copy of applied hashes (filled lazily)
-  std::map<u32, HostChange> deflatedOriginal;     // applied change index -> arena range of the original DEFLATEd bytes
+  struct OrigRange { u32 idx; HostChange range; };
+  std::vector<OrigRange> deflatedOriginal;        // (applied change index, arena range of the original DEFLATEd bytes), ascending index
+  const HostChange* originalOf(u32 idx) const {
+    auto it = std::lower_bound(deflatedOriginal.begin(), deflatedOriginal.end(), idx, [](const OrigRange& a, u32 v) { return a.idx < v; });
+    return it != deflatedOriginal.end() && it->idx == idx ? &it->range : nullptr;
+  }
   std::vector<HostChange> queue, queueOriginal;   // not yet causally ready (+ original range, len 0 = not deflated)
   u64 maxOp = 0;
   float lastPhaseMs[24] = {0};   // [0..11] CUDA-event phases, [12..23] host wall-clock markers (ms since call start)
@@ -94,7 +99,7 @@ class Engine {
   DBuf<u32> elemPos, keyRankAt, objPos, head, headScan, groupOf, groupRows, groupVisible, groupFirst, groupTouched, groupLinked, objTouchedAt, linkDone, emit, marker, slot;
   DBuf<u32> isObjHead, objIdx, objStart, elemVis, elemVisScan, rowEmit, firstVis, state, nItems, itemBase, qIndex, zero, wzero, zscan, wscan, editObjKey;
   DBuf<DomItem> items, items2; DBuf<PropRec> propOut; DBuf<EditRec> editOut, editOut2; DBuf<u64> editElem, editElem2;
-  DBuf<u32> inflLen, inflOff, groupHasChild, gCount, gElem, gT1, gQOrd, gBase, nQ, elemHasRecs, listLinkTime, editElemPos, editElemPos2, editKind, editPred, editDead, editMerge, editMulti, editLive;
+  DBuf<u32> domTw, domTw2, oldVisScan, inflLen, inflOff, groupHasChild, gCount, gElem, gT1, gQOrd, gBase, nQ, elemHasRecs, listLinkTime, editElemPos, editElemPos2, editKind, editPred, editDead, editMerge, editMulti, editLive;
   DBuf<u32> seqSlot, actorCnt, actorBaseD, clockD, changeActor, editTime; DBuf<u8> hashTmp; bool batchInOrder = true;
   DBuf<u32> finalTime, gFailed, memberFinal, opAt, runHead, opGroupHead; DBuf<u64> gBound; DocRows workView{}; DBuf<HostChange> chPairs; std::thread mirrorThread; DBuf<u32> largeFlag, largeSlot, largeList; size_t lastNumLarge = 0; DBuf<u64> zwScan; DBuf<u32> deflList, patchTriples;
 

@@ -479,15 +479,18 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     }
     if (appliedH.empty()) {   // all applied, in order
       const u32 base0 = (u32)changes.size();
-      changes.insert(changes.end(), batch.begin(), batch.end());
-      if (!batchOriginal.empty()) { if (deflIdx.empty() || Bq > 0) { for (size_t b = 0; b < B; b++) if (batchOriginal[b].len) deflatedOriginal[base0 + (u32)b] = batchOriginal[b]; } else for (u32 b : deflIdx) deflatedOriginal[base0 + b] = batchOriginal[b]; }
+      if (!batchOriginal.empty()) {
+        if (deflIdx.empty() || Bq > 0) { for (size_t b = 0; b < B; b++) if (batchOriginal[b].len) deflatedOriginal.push_back({base0 + (u32)b, batchOriginal[b]}); }
+        else { deflatedOriginal.reserve(deflatedOriginal.size() + deflIdx.size()); for (u32 b : deflIdx) deflatedOriginal.push_back({base0 + b, batchOriginal[b]}); }
+      }
+      if (changes.empty()) changes.swap(batch); else changes.insert(changes.end(), batch.begin(), batch.end());
     }
     else {
       std::vector<u32> byRank(numNew);
       if (appliedH.empty()) for (size_t b = 0; b < B; b++) byRank[b] = (u32)b; else for (size_t b = 0; b < B; b++) if (appliedH[b]) byRank[appRankH[b]] = (u32)b;
       for (size_t k = 0; k < numNew; k++) {
         const u32 b = byRank[k];
-        if (!batchOriginal.empty() && batchOriginal[b].len) deflatedOriginal[(u32)changes.size()] = batchOriginal[b];
+        if (!batchOriginal.empty() && batchOriginal[b].len) deflatedOriginal.push_back({(u32)changes.size(), batchOriginal[b]});
         changes.push_back(batch[b]);
       }
     }
@@ -554,7 +557,7 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   bool anyListLink = false;
   auto listGroups = [&](int pass) {
     return ListGroupKernel{pass, mg, opGroupHead.p, *idt, rowOfOpD, posD, lctx, gCount.p, gElem.p, gT1.p, gQOrd.p, nQ.p, elemHasRecs.p,
-                           itemBase.p, objIdx.p, objStart.p, items.p, gBase.p, qIndex.p, editOut.p, editElem.p, editObjKey.p, editElemPos.p, errWord.p};
+                           itemBase.p, objIdx.p, objStart.p, items.p, domTw.p, oldVisScan.p, gBase.p, qIndex.p, editOut.p, editElem.p, editObjKey.p, editElemPos.p, errWord.p};
   };
   if (!wholeDoc) {
     // op groups of the batch (new.js:1085-1138), then what each list group nets out to
@@ -624,18 +627,21 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
     numEdits = numGroupRecs + numLink;
     if (numEdits > 0) {
       if (numGroupRecs > 0) {
-        nItems.ensure(ctx, N + 1); itemBase.ensure(ctx, N + 2);
-        foreach(ctx, N, ElemEventKernel{0, lctx, head.p, nQ.p, nItems.p, itemBase.p, objIdx.p, objStart.p, items.p});
+        // list index of a group = elements in front that were visible before the batch (one prefix sum)
+        //                       + net visibility changes in front that earlier groups of the batch made (dominance count)
+        nItems.ensure(ctx, N + 1); itemBase.ensure(ctx, N + 2); oldVisScan.ensure(ctx, N + 2);
+        foreach(ctx, N, OldVisFlagKernel{lctx, head.p, nItems.p});
+        scan_exclusive(ctx, scanTmp, nItems.p, oldVisScan.p, N);
+        foreach(ctx, N, DomItemCountKernel{nQ.p, nItems.p});
         scan_exclusive(ctx, scanTmp, nItems.p, itemBase.p, N);
         const size_t T = readU32(itemBase.p + N);
-        items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zwScan.ensure(ctx, T + 2);
-        foreach(ctx, N, ElemEventKernel{1, lctx, head.p, nQ.p, nItems.p, itemBase.p, objIdx.p, objStart.p, items.p});
+        items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zwScan.ensure(ctx, T + 2); domTw.ensure(ctx, T + 1); domTw2.ensure(ctx, T + 1);
         foreach(ctx, numOps, listGroups(1));
         const int tbits = bits_for(numOps + 1);
         for (int bit = tbits - 1; bit >= 0; bit--) {
-          scan_exclusive64(ctx, scanTmp, DomScanInput{items.p, bit}, zwScan.p, T);
-          foreach(ctx, T, DomLevelKernel{items.p, items2.p, zwScan.p, bit});
-          std::swap(items.p, items2.p); std::swap(items.cap, items2.cap);
+          scan_exclusive64(ctx, scanTmp, DomScanInput{domTw.p, bit}, zwScan.p, T);
+          foreach(ctx, T, DomLevelKernel{items.p, items2.p, domTw2.p, zwScan.p, bit});
+          std::swap(items.p, items2.p); std::swap(items.cap, items2.cap); std::swap(domTw.p, domTw2.p); std::swap(domTw.cap, domTw2.cap);
         }
         foreach(ctx, T, DomResultKernel{items.p, qIndex.p});
       }

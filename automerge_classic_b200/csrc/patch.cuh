@@ -238,7 +238,14 @@ struct FirstVisKernel { const u32* groupOf; const u32* succCnt; u32* firstVisInG
 struct EditElemKernel { DocRows d; const u32* rowEmit; const u32* slot; const u32* groupOf; const u32* groupFirst; u64* elemOut; HD void operator()(size_t p) const { if (rowEmit[p]) elemOut[slot[p]] = d.id[groupFirst[groupOf[p]]]; } };
 
 // ---------------------------------------------------------------- incremental list edits: dominance counting
-struct DomItem { u32 time; u32 ref /* bit31: query; bits30..0: op index (query) */; int w; u32 acc; u32 gs, ge; };
+// An item is a query (an op group asking for its list index), a point (a visibility change of an element: +1 / -1) or
+// both at once. tw = time (bits 0..26) | (weight + 1) << 27 | query << 29. The query result is routed by time (every
+// group has its own start time). gs / ge = current partition [gs, ge) of the item.
+struct DomItem { u32 tw, acc, gs, ge; };
+HD u32 dom_tw(u32 time, int w, bool query) { return time | ((u32)(w + 1) << 27) | (query ? 1u << 29 : 0u); }
+HD u32 dom_time(u32 tw) { return tw & 0x7ffffffu; }
+HD int dom_w(u32 tw) { return (int)((tw >> 27) & 3u) - 1; }
+HD bool dom_query(u32 tw) { return (tw >> 29) & 1u; }
 
 // Per-position view of a list element's rows: row p exists from d.time[p] (0 = before this call) and is overwritten at
 // minSucc(p) (0 = before this call, 0xffffffff = never). The element whose insert row sits at e owns rows [e, e+rows).
@@ -250,66 +257,41 @@ struct ListCtx {
     return false;
   }
 };
-// Visibility toggles of every list element over the times of this call: +1 when it becomes visible, -1 when it stops.
-struct ElemEventKernel {
-  int pass; ListCtx L; const u32* head; const u32* nQ; u32* nItems; const u32* itemBase; const u32* objIdx; const u32* objStart; DomItem* items;
-  HD void put(u32& k, u32 time, int w, u32 gs, u32 ge) const {
-    if (pass == 1) { DomItem a; a.time = time; a.ref = 0; a.w = w; a.acc = 0; a.gs = gs; a.ge = ge; items[k] = a; }
-    k++;
-  }
-  HD void operator()(size_t p) const {
-    const DocRows& d = L.d;
-    if (!(d.keyStrLen[p] == NULL32 && head[p] && (d.flags[p] & F_INSERT))) { if (pass == 0) nItems[p] = 0; return; }
-    const u32 e = (u32)p, rows = L.groupRows[L.groupOf[p]];
-    u32 gs = 0, ge = 0, k = 0;
-    if (pass == 1) { gs = itemBase[objStart[objIdx[p]]]; ge = itemBase[objStart[objIdx[p] + 1]]; k = itemBase[p] + nQ[p]; }
-    const u32 k0 = k;
-    if (rows == 1) {
-      const u32 s = d.time[e], x = L.minSucc(e);
-      if (x > s) { put(k, s, 1, gs, ge); if (x != 0xffffffffu) put(k, x, -1, gs, ge); }
-    } else {
-      for (u32 r = e; r < e + rows; r++) {
-        const u32 s = d.time[r], x = L.minSucc(r);
-        if (x <= s) continue;
-        bool firstS = true, firstX = true;
-        for (u32 q = e; q < r; q++) { const u32 s2 = d.time[q], x2 = L.minSucc(q); if (x2 <= s2) continue; if (s2 == s) firstS = false; if (x2 == x) firstX = false; }
-        if (firstS && (s == 0 || !L.visAt(e, rows, s - 1))) put(k, s, 1, gs, ge);   // visAt(s) holds because of row r
-        if (firstX && x != 0xffffffffu && !L.visAt(e, rows, x)) put(k, x, -1, gs, ge);   // visible just before x because of row r
-      }
-    }
-    if (pass == 0) nItems[p] = nQ[p] + (k - k0);
-  }
-};
+// Elements that were visible before the batch are not items: their count in front of a position is one prefix sum.
+struct OldVisFlagKernel { ListCtx L; const u32* head; u32* flag; HD void operator()(size_t p) const { flag[p] = (L.d.keyStrLen[p] == NULL32 && head[p] && (L.d.flags[p] & F_INSERT) && L.visAt((u32)p, L.groupRows[L.groupOf[p]], 0)) ? 1u : 0u; } };
+// items per position: one merged item for an element with one op group, otherwise its queries first and its points after
+// (a query must not see the points of its own element)
+struct DomItemCountKernel { const u32* nQ; u32* nItems; HD void operator()(size_t p) const { const u32 k = nQ[p]; nItems[p] = k <= 1 ? k : 2 * k; } };
 struct DomScanInput {   // per level: low word = 1 if the time bit is clear, high word = the item's weight if the bit is clear
-  const DomItem* items; int bit;
+  const u32* tw; int bit;
   HD u64 operator()(size_t i) const {
-    const bool z = ((items[i].time >> bit) & 1u) == 0;
-    return z ? (1ull | ((u64)(u32)items[i].w << 32)) : 0ull;
+    const u32 x = tw[i];
+    return ((x >> bit) & 1u) == 0 ? (1ull | ((u64)(u32)dom_w(x) << 32)) : 0ull;
   }
 };
-struct DomLevelKernel {   // accumulate + stable split of every group on `bit`; ZW = packed exclusive scan of DomScanInput
-  const DomItem* in; DomItem* out; const u64* ZW; int bit;
+struct DomLevelKernel {   // accumulate + stable split of every partition on `bit`; ZW = packed exclusive scan of DomScanInput
+  const DomItem* in; DomItem* out; u32* twOut; const u64* ZW; int bit;
   HD void operator()(size_t i) const {
     DomItem it = in[i];
     const u64 s_i = ZW[i], s_gs = ZW[it.gs], s_ge = ZW[it.ge];
-    const u32 zg = (u32)s_ge - (u32)s_gs;             // zeros in the group
-    const u32 zb = (u32)s_i - (u32)s_gs;               // zeros before i in the group
-    const bool one = (it.time >> bit) & 1u;
+    const u32 zg = (u32)s_ge - (u32)s_gs;             // zeros in the partition
+    const u32 zb = (u32)s_i - (u32)s_gs;               // zeros before i in the partition
+    const bool one = (it.tw >> bit) & 1u;
     u32 dst;
     if (one) {
-      if (it.ref & 0x80000000u) it.acc += (u32)(s_i >> 32) - (u32)(s_gs >> 32);
+      if (dom_query(it.tw)) it.acc += (u32)(s_i >> 32) - (u32)(s_gs >> 32);
       dst = it.gs + zg + ((u32)i - it.gs - zb);
       it.gs = it.gs + zg;
     } else {
       dst = it.gs + zb;
       it.ge = it.gs + zg;
     }
-    out[dst] = it;
+    out[dst] = it; twOut[dst] = it.tw;
   }
 };
-struct DomResultKernel {   // route query results back: qIndex[2p + which] = index
+struct DomResultKernel {   // route query results back by group start time
   const DomItem* items; u32* qIndex;
-  HD void operator()(size_t i) const { if (items[i].ref & 0x80000000u) qIndex[items[i].ref & 0x7fffffffu] = items[i].acc; }
+  HD void operator()(size_t i) const { if (dom_query(items[i].tw)) qIndex[dom_time(items[i].tw) - 1] = items[i].acc; }
 };
 // ---------------------------------------------------------------- incremental list edits: one thread per op group
 // An op group (new.js:1085-1138) is one insert op, or a run of same-author non-insert ops on one list element that do
@@ -320,8 +302,8 @@ struct DomResultKernel {   // route query results back: qIndex[2p + which] = ind
 enum { EF_POP = 0x400, EF_GROUP_FIRST = 0x800, EF_START = 0x100, EF_MULTI = 0x200 };
 struct ListGroupKernel {
   int pass; MapGroupCtx c; const u32* groupHead; IdTable t; const u32* rowOfOp; const u32* pos; ListCtx L;
-  u32* gCount; u32* gElem; u32* gT1; u32* gQOrd; u32* nQ; u32* elemHasRecs;                     // pass 0 out
-  const u32* itemBase; const u32* objIdx; const u32* objStart; DomItem* items;                     // pass 1: queries
+  u32* gCount; u32* gElem; u32* gT1; u32* gQOrd; u32* nQ; u32* elemHasRecs;                     // pass 0 out (gT1: T1 | (net weight + 1) << 29 | W << 31)
+  const u32* itemBase; const u32* objIdx; const u32* objStart; DomItem* items; u32* twArr; const u32* oldVisScan;   // pass 1: items
   const u32* gBase; const u32* qIndex; EditRec* out; u64* elemOut; u32* objKeyOut; u32* elemPosOut; u64* errWord;   // pass 2: records
   HD static bool shown(u32 flags) { const u32 a = flags_action(flags); return a == ACT_SET || (a % 2 == 0 && a != ACT_DEL); }
   HD void operator()(size_t t0) const {
@@ -345,23 +327,31 @@ struct ListGroupKernel {
             if (a == ACT_INC || (a == ACT_SET && (L.d.valLen[r] & 15) == 8 && L.succCnt[r] > 0)) raise(errWord, KE_UNSUPPORTED_OP, r);   // counters inside lists
           }
           n = nV ? nV : (W ? 1u : 0u);
-          gElem[t0] = e; gT1[t0] = T1 | (W ? 0x80000000u : 0u);
-          if (n) { gQOrd[t0] = atomic_add(&nQ[e], 1u); if (nV) elemHasRecs[e] = 1; }
+          const int wNet = (int)L.visAt(e, rows, T1) - (int)L.visAt(e, rows, T0 - 1);
+          gElem[t0] = e; gT1[t0] = T1 | ((u32)(wNet + 1) << 29) | (W ? 0x80000000u : 0u);
+          if (n || wNet) gQOrd[t0] = atomic_add(&nQ[e], 1u); else gQOrd[t0] = ROW_NONE;
+          if (nV) elemHasRecs[e] = 1;
         }
       }
       gCount[t0] = n;
       return;
     }
-    if (!mine || gCount[t0] == 0) return;
+    if (!mine || gElem[t0] == ROW_NONE) return;
     const u32 e = gElem[t0];
     if (pass == 1) {
-      DomItem q; q.time = (u32)t0 + 1; q.ref = 0x80000000u | (u32)t0; q.w = 0; q.acc = 0;
-      q.gs = itemBase[objStart[objIdx[e]]]; q.ge = itemBase[objStart[objIdx[e] + 1]];
-      items[itemBase[e] + gQOrd[t0]] = q;
+      if (gQOrd[t0] == ROW_NONE) return;
+      const int wNet = (int)((gT1[t0] >> 29) & 3u) - 1; const bool isQ = gCount[t0] != 0; const u32 k = nQ[e], o = gQOrd[t0];
+      DomItem q; q.acc = 0; q.gs = itemBase[objStart[objIdx[e]]]; q.ge = itemBase[objStart[objIdx[e] + 1]];
+      if (k == 1) { q.tw = dom_tw((u32)t0 + 1, wNet, isQ); items[itemBase[e]] = q; twArr[itemBase[e]] = q.tw; }
+      else {
+        q.tw = dom_tw((u32)t0 + 1, 0, isQ); items[itemBase[e] + o] = q; twArr[itemBase[e] + o] = q.tw;
+        q.tw = dom_tw((u32)t0 + 1, wNet, false); items[itemBase[e] + k + o] = q; twArr[itemBase[e] + k + o] = q.tw;
+      }
       return;
     }
-    const u32 T0 = (u32)t0 + 1, T1 = gT1[t0] & 0x7fffffffu; const bool W = gT1[t0] >> 31;
-    const u32 rows = L.groupRows[L.groupOf[e]], idx = qIndex[t0];
+    if (gCount[t0] == 0) return;
+    const u32 T0 = (u32)t0 + 1, T1 = gT1[t0] & 0x1fffffffu; const bool W = gT1[t0] >> 31;
+    const u32 rows = L.groupRows[L.groupOf[e]], idx = qIndex[t0] + oldVisScan[e] - oldVisScan[objStart[objIdx[e]]];
     // Reference quirk, reproduced: when one mergeDocChangeOps call walks from an element straight into the next one
     // (new.js:1116-1121), the insert row of that next element is reported with the list index of the previous element:
     // listIndex is only advanced after updatePatchProperty has seen the row (new.js:1204-1211). It matters for the edits
