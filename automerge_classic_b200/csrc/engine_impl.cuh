@@ -412,10 +412,12 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     foreach(ctx, numRows, OldPairsKernel{succOff.p, succ.p, pos.p, ord, pairKey.p, pairIdx.p, pairSucc.p, pairPos.p, pairTime.p});
     foreach(ctx, M, PredPairsKernel{ops, idt, pos.p, rowOfOp.p, w, elemRow.p, keySlot.p, ord, pairKey.p, pairIdx.p, pairSucc.p, pairPos.p, pairTime.p, numSucc, errWord.p});
     foreach(ctx, M, DelKeyCheckKernel{arena.p, ops, idt, w, errWord.p});
+    foreach(ctx, M, IncCheckKernel{ops, idt, w, errWord.p});
     {
       const u64 w2 = fetchErr();
       if (w2) {
         if ((w2 & 0xff) == KE_PRED_MISSING) { u64 pid = 0; d2h(ctx, &pid, o_predId.p + (w2 >> 8), 8); sync(ctx); actorIds.swap(actorsNow); std::string t = opIdText(pid); actorIds.swap(actorsNow); throw Error(AMG_ERR_RANGE, "no matching operation for pred: " + t); }
+        if ((w2 & 0xff) == KE_UNKNOWN_COUNTER) { u64 oid = 0; d2h(ctx, &oid, o_id.p + (w2 >> 8), 8); sync(ctx); actorIds.swap(actorsNow); std::string t = opIdText(oid); actorIds.swap(actorsNow); throw Error(AMG_ERR_RANGE, "increment operation " + t + " for unknown counter"); }
         throwKernelError(w2, actorsNow);
       }
     }
@@ -438,7 +440,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       objPos.ensure(ctx, N + 1);
       foreach(ctx, N, ObjPosKernel{perm.p, objRow.p, pos.p, objPos.p});
       workView = w;
-      buildPatch(sorted.view(), N, false, &ops, M, &idt, rowOfOp.p, pos.p, actorsNow, out);
+      buildPatch(sorted.view(), N, false, &ops, M, &idt, rowOfOp.p, pos.p, actorsNow, out, newSuccOff.p, newSucc.p);
     }
     checkErr(actorsNow);
     timer.mark(); hostMark();
@@ -526,7 +528,7 @@ namespace amg {
 // (new.js:1604-1635), otherwise incremental semantics for the batch `ops` (new.js:884-1040, 1461-1528).
 // Uses succCnt (per position) and, in incremental mode, newSuccCnt / firstNewSucc / objPos.
 inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows* ops, size_t numOps, const IdTable* idt, const u32* rowOfOpD, const u32* posD,
-                               const std::vector<std::string>& actorsNow, PatchOut& out) {
+                               const std::vector<std::string>& actorsNow, PatchOut& out, const u32* succOffD, const u64* succD) {
   out.numProps = out.numEdits = 0; out.bigEnd = 0;
   if (N == 0) return;
   // groups (map key / list element) and their visibility
@@ -592,12 +594,14 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
     for (int pass = 0; pass < 2; pass++)
       foreach(ctx, numOps, GroupFinalKernel{pass, mg, opGroupHead.p, *idt, rowOfOpD, posD, groupOf.p, workView, ordNow, finalTime.p, gBound.p, gFailed.p, memberFinal.p});
   }
-  foreach(ctx, N, PropFlagKernel{d, groupOf.p, groupTouched.p, groupLinked.p, succCnt.p, wholeDoc ? 1 : 0, finalTime.p, gBound.p, gFailed.p, memberFinal.p, ordNow, emit.p, groupEmitted.p});
+  counterLast.ensure(ctx, N + 1); counterTotal.ensure(ctx, N + 1);
+  foreach(ctx, N, CounterKernel{arena.p, d, succOffD, succD, groupOf.p, groupFirst.p, groupRows.p, counterLast.p, counterTotal.p});
+  foreach(ctx, N, PropFlagKernel{d, groupOf.p, groupTouched.p, groupLinked.p, succCnt.p, wholeDoc ? 1 : 0, finalTime.p, gBound.p, gFailed.p, memberFinal.p, ordNow, emit.p, groupEmitted.p, counterLast.p});
   foreach(ctx, N, PropMarkerKernel{d, groupOf.p, groupTouched.p, head.p, groupEmitted.p, wholeDoc ? 1 : 0, emit.p, marker.p});
   scan_exclusive(ctx, scanTmp, emit.p, slot.p, N);
   const size_t numProps = readU32(slot.p + N);
   propOut.ensure(ctx, numProps + 1);
-  foreach(ctx, N, PropEmitKernel{d, emit.p, marker.p, slot.p, propOut.p});
+  foreach(ctx, N, PropEmitKernel{d, emit.p, marker.p, slot.p, propOut.p, counterLast.p, counterTotal.p});
   if (curTimer) { curTimer->mark(); curHostMark(); }
   // ---- list edits
   size_t numEdits = 0;
@@ -687,7 +691,7 @@ inline void Engine::getPatch(PatchOut& out) {
   dev_memset(ctx, errWord.p, 0, 8);
   succCnt.ensure(ctx, numRows + 2);
   foreach(ctx, numRows, SuccCntFromOffKernel{succOff.p, succCnt.p});
-  buildPatch(doc.view(), numRows, true, nullptr, 0, nullptr, nullptr, nullptr, actorIds, out);
+  buildPatch(doc.view(), numRows, true, nullptr, 0, nullptr, nullptr, nullptr, actorIds, out, succOff.p, succ.p);
   checkErr(actorIds);
   fillPatchHeader(out);
   finishPatch(out);

@@ -241,6 +241,19 @@ struct PredPairsKernel {
     }
   }
 };
+// an `inc` op needs a counter to add to: one of its preds must be a `set` of datatype counter (new.js:953-957)
+struct IncCheckKernel {
+  OpRows ops; IdTable t; DocRows w; u64* errWord;
+  HD void operator()(size_t i) const {
+    if (flags_action(ops.flags[i]) != ACT_INC) return;
+    bool ok = false;
+    for (u32 j = 0; j < ops.predNum[i] && !ok; j++) {
+      const u32 target = id_lookup(t, ops.predId[ops.predOff[i] + j]);
+      ok = target != ROW_NONE && flags_action(w.flags[target]) == ACT_SET && (w.valLen[target] & 15) == 8;
+    }
+    if (!ok) raise(errWord, KE_UNKNOWN_COUNTER, i);
+  }
+};
 // list `del` ops have no row: their element must exist (seekToOp would throw first, new.js:293-301)
 struct DelElemCheckKernel {
   OpRows ops; IdTable t; DocRows w; u64* errWord;

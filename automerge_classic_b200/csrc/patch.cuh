@@ -21,7 +21,7 @@
 namespace amg {
 
 // flat patch records (copied to the host verbatim)
-struct PropRec { u64 obj, opId; u32 keyOff, keyLen, valLen, valOff, flags /* action<<8 | 1 = empty key */, pad; };
+struct PropRec { u64 obj, opId; u32 keyOff, keyLen, valLen, valOff, flags /* action<<8 | 1 = empty key | 2 = counter: value is the int64 (pad:valOff) */, pad; };
 struct EditRec { u64 obj, opId; u32 index, kind /* 0 insert 1 remove 2 update | runStart<<8 | action<<16 */, valLen, valOff; };
 enum { EK_INSERT = 0, EK_REMOVE = 1, EK_UPDATE = 2 };
 
@@ -50,7 +50,8 @@ struct GroupStatsKernel {   // group id = inclusive scan of heads - 1; counts ro
     atomic_add(&groupRows[g], 1u);
     if (succCnt[p] == 0) { atomic_add(&groupVisible[g], 1u); const u32 a = flags_action(d.flags[p]); if (a % 2 == 0 && a != ACT_DEL) groupHasChild[g] = 1; }
     if (head[p]) groupFirst[g] = (u32)p;
-    if (flags_action(d.flags[p]) == ACT_INC || ((d.valLen[p] & 15) == 8 && flags_action(d.flags[p]) == ACT_SET && succCnt[p] > 0)) { if (!allowCounters) raise(errWord, KE_UNSUPPORTED_OP, p); }
+    if (d.keyStrLen[p] == NULL32 && (flags_action(d.flags[p]) == ACT_INC || ((d.valLen[p] & 15) == 8 && flags_action(d.flags[p]) == ACT_SET && succCnt[p] > 0)))
+      raise(errWord, KE_UNSUPPORTED_OP, p);   // counters inside list elements (the reference itself leaves them half done, new.js:965)
   }
 };
 
@@ -171,16 +172,45 @@ struct GroupFinalKernel {   // pass 0: finalTime[g] = latest group on key group 
     for (size_t u = t0; u < t; u++) { const u32 i = c.opAt[u]; if (rowOfOp[i] != ROW_NONE) member[pos[rowOfOp[i]]] = 1; }
   }
 };
+// Counters (new.js:941-966): increments are successors of the `set` that created the counter. The counter shows with the
+// summed value once every successor turned out to be an `inc`; the reference emits it while processing the last of them.
+struct CounterKernel {
+  const u8* arena; DocRows d; const u32* succOff; const u64* succ; const u32* groupOf; const u32* groupFirst; const u32* groupRows;
+  u32* counterLast /* position of the last inc row, ROW_NONE = not a visible counter */; u64* counterTotal;
+  HD long long valueOf(u32 r) const {
+    ByteReader br(arena, d.valOff[r], d.valOff[r] + (d.valLen[r] >> 4));
+    return (d.valLen[r] & 15) == 3 ? (long long)br.uleb() : br.sleb();
+  }
+  HD void operator()(size_t p) const {
+    counterLast[p] = ROW_NONE;
+    if (d.keyStrLen[p] == NULL32 || flags_action(d.flags[p]) != ACT_SET || (d.valLen[p] & 15) != 8) return;
+    const u32 s0 = succOff[p], s1 = succOff[p + 1]; if (s0 == s1) return;
+    const u32 g = groupOf[p], gf = groupFirst[g], rows = groupRows[g];
+    long long total = valueOf((u32)p); u32 last = 0;
+    for (u32 s = s0; s < s1; s++) {
+      u32 r = ROW_NONE;
+      for (u32 q = gf; q < gf + rows; q++) if (d.id[q] == succ[s]) { r = q; break; }
+      if (r == ROW_NONE || flags_action(d.flags[r]) != ACT_INC) return;   // deleted or overwritten: the counter is gone
+      total += valueOf(r); if (r > last) last = r;
+    }
+    counterLast[p] = last; counterTotal[p] = (u64)total;
+  }
+};
 struct PropFlagKernel {   // which positions emit a prop record
   DocRows d; const u32* groupOf; const u32* groupTouched; const u32* groupLinked; const u32* succCnt; int wholeDoc;
-  const u32* finalTime; const u64* bound; const u32* failed; const u32* member; Ord ord; u32* emit; u32* groupEmitted;
+  const u32* finalTime; const u64* bound; const u32* failed; const u32* member; Ord ord; u32* emit; u32* groupEmitted; const u32* counterLast;
   HD void operator()(size_t p) const {
     u32 e = 0;
-    if (d.keyStrLen[p] != NULL32 && succCnt[p] == 0) {
-      const u32 g = groupOf[p];
-      if (wholeDoc) e = 1;
-      else if (groupTouched[g]) e = (finalTime[g] == 0 || failed[g] || member[p] || ord(d.id[p]) <= bound[g]) ? 1 : 0;
-      else if (groupLinked[g]) e = 1;
+    if (d.keyStrLen[p] != NULL32) {
+      // q = the row whose processing puts this value into the patch: the row itself, or a counter's last increment
+      u32 q = ROW_NONE;
+      if (counterLast[p] != ROW_NONE) q = counterLast[p]; else if (succCnt[p] == 0 && flags_action(d.flags[p]) != ACT_INC) q = (u32)p;
+      if (q != ROW_NONE) {
+        const u32 g = groupOf[p];
+        if (wholeDoc) e = 1;
+        else if (groupTouched[g]) e = (finalTime[g] == 0 || failed[g] || member[q] || ord(d.id[q]) <= bound[g]) ? 1 : 0;
+        else if (groupLinked[g]) e = 1;
+      }
     }
     emit[p] = e;
     if (e) atomic_add(&groupEmitted[groupOf[p]], 1u);
@@ -195,11 +225,13 @@ struct PropMarkerKernel {   // a touched key with nothing to show is reported as
   }
 };
 struct PropEmitKernel {
-  DocRows d; const u32* emit; const u32* marker; const u32* slot; PropRec* out;
+  DocRows d; const u32* emit; const u32* marker; const u32* slot; PropRec* out; const u32* counterLast; const u64* counterTotal;
   HD void operator()(size_t p) const {
     if (!emit[p]) return;
     PropRec r; r.obj = d.obj[p]; r.opId = d.id[p]; r.keyOff = d.keyStrOff[p]; r.keyLen = d.keyStrLen[p]; r.valLen = d.valLen[p]; r.valOff = d.valOff[p];
-    r.flags = (flags_action(d.flags[p]) << 8) | (marker[p] ? 1u : 0u); r.pad = 0; out[slot[p]] = r;
+    r.flags = (flags_action(d.flags[p]) << 8) | (marker[p] ? 1u : 0u); r.pad = 0;
+    if (!marker[p] && counterLast[p] != ROW_NONE) { r.flags |= 2u; r.valOff = (u32)counterTotal[p]; r.pad = (u32)(counterTotal[p] >> 32); }   // summed counter value instead of arena bytes
+    out[slot[p]] = r;
   }
 };
 

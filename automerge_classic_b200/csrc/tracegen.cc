@@ -7,6 +7,7 @@
 //   C2  makeText + n single-op insert changes, one actor (C2b: the same ops in ONE bulk change)
 //   C3  makeText + A actors x n/A single-op changes, 70 % insert / 30 % delete, merge every 100 changes
 //   C4  nested maps: A actors x rounds x 100-op `set` changes, Zipf keys, Lamport-conflict heavy
+//   C7  counters in root keys: create / increment / overwrite / delete, concurrent writers
 //   C6  one list of scalars and map objects: inserts, element updates / conflicts / deletes, keys set inside element maps
 // Seeded SplitMix64; actor k = first 16 bytes of SHA-256("amgpu-actor-" || seed || k).
 // The oracle (tests) decodes and re-applies these bytes, which cross-checks this independent encoder.
@@ -339,10 +340,61 @@ void genRichList(Trace& t, uint64_t seed, uint64_t nOps, int A, int maxOpsPerCha
     maxOp = newMax;
   }
 }
+
+// C7: counters in maps: `set` of datatype counter, concurrent `inc` ops (pred = the counter's set op), deletes and plain
+// overwrites of counter keys; a few root keys so that same-round writers collide.
+void genCounters(Trace& t, uint64_t seed, uint64_t nOps, int A, int nKeys, int maxOpsPerChange) {
+  Rng rng{seed}; std::vector<Actor> actors = makeActors(seed, A); Encoder enc{&actors};
+  std::vector<uint64_t> seq(A, 0); std::vector<Hash> lastHash(A); std::vector<bool> hasHash(A, false);
+  struct Val { OpId id; bool counter; };
+  std::vector<std::vector<Val>> visible(nKeys);     // visible set ops per key (an `inc` never becomes a value of its own)
+  uint64_t maxOp = 0, produced = 0;
+  auto keyOf = [](const OpId& o) { return o.ctr * 65536 + (uint64_t)o.actor; };
+  while (produced < nOps) {
+    std::vector<Hash> roundHeads; for (int a = 0; a < A; a++) if (hasHash[a]) roundHeads.push_back(lastHash[a]);
+    const uint64_t base = maxOp; uint64_t newMax = maxOp;
+    std::vector<std::vector<std::pair<int, Val>>> written(A); std::vector<OpId> overwritten;
+    for (int a = 0; a < A && produced < nOps; a++) {
+      std::vector<Op> ops; const int want = 1 + (int)rng.below(maxOpsPerChange);
+      std::unordered_map<int, std::vector<Val>> local;
+      auto visOf = [&](int k) -> std::vector<Val>& { auto it = local.find(k); if (it == local.end()) it = local.emplace(k, visible[k]).first; return it->second; };
+      while ((int)ops.size() < want) {
+        const uint64_t ctr = base + 1 + ops.size(); const OpId me{ctr, a}; const int k = (int)rng.below(nKeys); std::vector<Val>& v = visOf(k);
+        Op op; op.isMapKey = true; char kb[8]; snprintf(kb, sizeof kb, "c%02d", k); op.key = kb; const double u = rng.unit();
+        const Val* counter = nullptr; for (auto& x : v) if (x.counter) counter = &x;
+        if (counter && u < 0.55) {            // increment (possibly negative)
+          op.action = 5; op.hasValue = true; const bool neg = rng.unit() < 0.3; op.valTag = neg ? 4 : 3;
+          if (neg) sleb(op.valRaw, -(int64_t)rng.below(50)); else uleb(op.valRaw, rng.below(1000));
+          op.pred = {counter->id};
+        } else if (u < 0.80) {                // (re)create a counter, overwriting whatever is visible
+          op.action = 1; op.hasValue = true; op.valTag = 8; sleb(op.valRaw, (int64_t)rng.below(100));
+          for (auto& x : v) { op.pred.push_back(x.id); overwritten.push_back(x.id); }
+          v.clear(); v.push_back(Val{me, true}); written[a].push_back({k, v.back()});
+        } else if (u < 0.90) {                // plain value
+          op.action = 1; op.hasValue = true; op.valTag = 4; sleb(op.valRaw, (int64_t)rng.below(100000));
+          for (auto& x : v) { op.pred.push_back(x.id); overwritten.push_back(x.id); }
+          v.clear(); v.push_back(Val{me, false}); written[a].push_back({k, v.back()});
+        } else {                              // delete the key
+          if (v.empty()) continue;
+          op.action = 3; for (auto& x : v) { op.pred.push_back(x.id); overwritten.push_back(x.id); }
+          v.clear();
+        }
+        ops.push_back(op);
+      }
+      std::vector<Hash> deps = roundHeads; if (hasHash[a] && std::find(deps.begin(), deps.end(), lastHash[a]) == deps.end()) deps.push_back(lastHash[a]);
+      Hash h; t.add(enc.encode(a, ++seq[a], base + 1, deps, ops, &h), ops.size()); lastHash[a] = h; hasHash[a] = true;
+      produced += ops.size(); newMax = std::max<uint64_t>(newMax, base + ops.size());
+    }
+    std::unordered_map<uint64_t, bool> gone; for (auto& o : overwritten) gone[keyOf(o)] = true;
+    for (auto& vs : visible) { std::vector<Val> keep; for (auto& x : vs) if (!gone.count(keyOf(x.id))) keep.push_back(x); vs.swap(keep); }
+    for (auto& w : written) for (auto& kv : w) if (!gone.count(keyOf(kv.second.id))) visible[kv.first].push_back(kv.second);
+    maxOp = newMax;
+  }
+}
 }  // namespace
 
 extern "C" {
-// config: 1 = C1, 2 = C2, 22 = C2b (bulk), 3 = C3, 4 = C4, 6 = C6 (rich list). Returns malloc'ed blob + offsets (n_changes + 1).
+// config: 1 = C1, 2 = C2, 22 = C2b (bulk), 3 = C3, 4 = C4, 6 = C6 (rich list), 7 = C7 (counters). Returns malloc'ed blob + offsets (n_changes + 1).
 int amg_trace_generate(int config, uint64_t seed, uint64_t n_ops, int n_actors, uint8_t** blob, size_t* blob_len, uint64_t** offsets, size_t* n_changes, uint64_t* total_ops) {
   Trace t;
   if (config == 1) genC1(t, seed);
@@ -350,6 +402,7 @@ int amg_trace_generate(int config, uint64_t seed, uint64_t n_ops, int n_actors, 
   else if (config == 22) genText(t, seed, n_ops, 1, true, 0.0, 100);
   else if (config == 3) genText(t, seed, n_ops, n_actors > 0 ? n_actors : 10, false, 0.3, 100);
   else if (config == 4) genC4(t, seed, n_ops, n_actors > 0 ? n_actors : 100, 100, 100, 100);
+  else if (config == 7) genCounters(t, seed, n_ops, n_actors > 0 ? n_actors : 3, 6, 5);
   else if (config == 6) genRichList(t, seed, n_ops, n_actors > 0 ? n_actors : 4, 6);
   else return 1;
   *blob = (uint8_t*)malloc(t.blob.size() + 64); memcpy(*blob, t.blob.data(), t.blob.size()); memset(*blob + t.blob.size(), 0, 64); *blob_len = t.blob.size();

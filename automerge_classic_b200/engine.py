@@ -185,6 +185,10 @@ class FlatPatch:
             action = flags >> 8
             if flags & 1:
                 p['props'].setdefault(key, {})
+            elif action == 1 and flags & 2:     # counter: the engine summed the increments (new.js:941-966)
+                total = int(rec['valOff']) | (int(rec['pad']) << 32)
+                total -= (1 << 64) if total >= (1 << 63) else 0
+                p['props'].setdefault(key, {})[self.op_id(rec['opId'])] = {'type': 'value', 'value': total, 'datatype': 'counter'}
             elif action == 1:
                 vl, vo = int(rec['valLen']), int(rec['valOff'])
                 p['props'].setdefault(key, {})[self.op_id(rec['opId'])] = decode_value(vl, arena[vo:vo + (vl >> 4)])

@@ -113,6 +113,21 @@ def check_deflate_variants(gpu_doc, oracle_mod):
     assert g.apply_changes([bytes(raw)])['pendingChanges'] == 0
 
 
+def check_counters(gpu_doc, oracle_mod, seed, n, a, chunk):
+    """Config C7: counters in map keys (create, concurrent increments, overwrite, delete), applied in calls of `chunk`
+    changes: incremental patches, getPatch and the op table equal the oracle's."""
+    from automerge_classic_b200 import tracegen
+    ch = tracegen.generate('C7', n, a, seed=seed).changes()
+    orc, g = oracle_mod.OracleDoc(), gpu_doc()
+    for lo in range(0, len(ch), chunk):
+        po, pg = orc.apply_changes(ch[lo:lo + chunk]), g.apply_changes(ch[lo:lo + chunk])
+        d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+        assert d is None, (seed, n, a, chunk, lo, d)
+    d = replay.deep_equal(replay.decode(g.get_patch()), replay.decode(orc.get_patch()))
+    assert d is None, d
+    _dump_equal(g, orc)
+
+
 def check_incremental_calls(gpu_doc, oracle_mod):
     """Applying a trace in several applyChanges calls gives the same patches as the oracle call by call."""
     from automerge_classic_b200 import tracegen

@@ -73,6 +73,12 @@ def test_deflate_variants(gpu_doc, oracle_mod):
     parity_checks.check_deflate_variants(gpu_doc, oracle_mod)
 
 
+@pytest.mark.parametrize('n,a,chunk', [(80, 2, 1000), (300, 3, 5), (500, 4, 40), (200, 1, 1)])
+def test_counters_parity(gpu_doc, oracle_mod, n, a, chunk):
+    for seed in range(1, 6):
+        parity_checks.check_counters(gpu_doc, oracle_mod, seed, n, a, chunk)
+
+
 def test_incremental_calls_match_bulk(gpu_doc, oracle_mod):
     parity_checks.check_incremental_calls(gpu_doc, oracle_mod)
 
