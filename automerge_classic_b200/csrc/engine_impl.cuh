@@ -61,7 +61,7 @@ inline void Engine::finishPatch(PatchOut& out) {
 inline void Engine::reset() {
   sync(ctx);
   arenaLen = 0; hostArena.len = 0; numApplied = 0; numRows = 0; numSucc = 0; dev_memset(ctx, succOff.p, 0, 4);
-  actorIds.clear(); actorRep.clear(); clock.clear(); heads.clear(); headIdx.clear(); changes.clear(); changeHashes.clear(); deflatedOriginal.clear();
+  actorIds.clear(); actorRep.clear(); clock.clear(); heads.clear(); headIdx.clear(); changes.clear(); changeHashes.clear(); deflatedOriginal.clear(); loadedDoc.clear();
   queue.clear(); queueOriginal.clear(); maxOp = 0; rebuildActorTable();
 }
 
@@ -500,7 +500,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     doc.swap(sorted); numRows = N;
     std::swap(succOff.p, newSuccOff.p); std::swap(succOff.cap, newSuccOff.cap); std::swap(succ.p, newSucc.p); std::swap(succ.cap, newSucc.cap); numSucc = numPairs;
     fill32(doc.time.p, 0, N);
-    numApplied += numNew; actorRep = actorRepNow; actorIds = actorsNow; clock = clockNow; maxOp = maxOpNow; heads = headsNow; headIdx = headIdxNow;
+    loadedDoc.clear(); numApplied += numNew; actorRep = actorRepNow; actorIds = actorsNow; clock = clockNow; maxOp = maxOpNow; heads = headsNow; headIdx = headIdxNow;
     dbgMark("commit:state-swapped");
     rebuildActorTable();   // slots of actors registered in this call become permanent (first = 0)
     dbgMark("commit:actors-rebuilt");
@@ -796,6 +796,114 @@ inline std::string inflateRawBytes(const u8* p, size_t n) {
   inflateEnd(&zs); out.resize(produced); return out;
 }
 
+// Backend.save() (reference new.js:2033-2055, columnar.js:983-1004): change metadata columns (re-derived from the change
+// headers that live in the arena) and the 16 document op columns (from the document table and its succ lists), encoded
+// on the device (encode.cuh); the container (column directory, DEFLATE of columns >= 256 bytes, checksum) is assembled
+// on the host, as the reference does.
+inline void Engine::saveDocument(std::string& result) {
+  if (!haveHashGraph && numApplied > 0) {
+    if (!loadedDoc.empty()) { result = loadedDoc; return; }   // unchanged since Backend.load (new.js:2034)
+    throw Error(AMG_ERR_UNSUPPORTED, "amgpu: save() after load() followed by further changes needs the loaded change metadata re-encoded (not built)");
+  }
+  if (!encoder) encoder.reset(new ColumnEncoder(ctx, scanTmp));
+  ColumnEncoder& enc = *encoder; enc.outLen = 0;
+  struct Col { u32 id; size_t off, len; };
+  std::vector<Col> changeCols, opCols;
+  auto add = [&](std::vector<Col>& cols, u32 id, size_t len) { cols.push_back({id, enc.outLen - len, len}); };
+  const size_t C = numApplied, N = numRows, S = numSucc;
+  dev_memset(ctx, errWord.p, 0, 16);
+  saveVals.ensure(ctx, std::max(std::max(C, N), S) + 2);
+  // ---- change metadata (new.js:1680-1692 appendChange)
+  if (C > 0) {
+    chPairs.ensure(ctx, C); chOff.ensure(ctx, C); chLen.ensure(ctx, C);
+    h2d(ctx, chPairs.p, changes.data(), C * sizeof(HostChange));
+    foreach(ctx, C, SplitPairsKernel{chPairs.p, chOff.p, chLen.p});
+    meta.ensure(ctx, C); colOff.ensure(ctx, (size_t)NCOLS * C); colLen.ensure(ctx, (size_t)NCOLS * C);
+    nOps.ensure(ctx, C + 1); nPreds.ensure(ctx, C + 1); nDeps.ensure(ctx, C + 1); nActors.ensure(ctx, C + 1);
+    foreach(ctx, C, ParseKernel{arena.p, chOff.p, chLen.p, C, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
+    depBase.ensure(ctx, C + 1); scan_exclusive(ctx, scanTmp, nDeps.p, depBase.p, C);
+    const u32 totalDeps = readU32(depBase.p + C);
+    depIdx.ensure(ctx, totalDeps + 1); primary.ensure(ctx, C);
+    const size_t tcap = pow2_at_least(2 * C + 2);
+    hashTable.ensure(ctx, tcap); dev_memset(ctx, hashTable.p, 0xff, tcap * 4);
+    foreach(ctx, C, HashInsertKernel{hashes.p, hashTable.p, (u64)tcap - 1});
+    foreach(ctx, C, ResolveDepsKernel{arena.p, hashes.p, hashTable.p, (u64)tcap - 1, meta.p, 0, depBase.p, depIdx.p, primary.p});
+    saveVals.ensure(ctx, std::max<size_t>(std::max(std::max(C, N), S), totalDeps) + 2);
+    saveStrOff.ensure(ctx, std::max(C, N) + 1); saveStrLen.ensure(ctx, std::max(C, N) + 1);
+    auto changeVal = [&](int which) { foreach(ctx, C, SaveChangeValKernel{which, arena.p, meta.p, actorSlots.p, (u64)actorCap - 1, saveVals.p, saveStrOff.p, saveStrLen.p, errWord.p}); };
+    changeVal(SM_ACTOR);     add(changeCols, 0x01, enc.rleNum(saveVals.p, C, false));
+    changeVal(SM_SEQ);       add(changeCols, 0x03, enc.deltaNum(saveVals.p, C));
+    changeVal(SM_MAX_OP);    add(changeCols, 0x13, enc.deltaNum(saveVals.p, C));
+    changeVal(SM_TIME);      add(changeCols, 0x23, enc.deltaNum(saveVals.p, C));
+    foreach(ctx, C, SaveMessageKernel{meta.p, saveStrOff.p, saveStrLen.p});
+                             add(changeCols, 0x35, enc.rle(StrCol{arena.p, saveStrOff.p, saveStrLen.p}, C));
+    changeVal(SM_DEPS_NUM);  add(changeCols, 0x40, enc.rleNum(saveVals.p, C, false));
+    foreach(ctx, totalDeps, SaveDepIndexKernel{depIdx.p, saveVals.p});
+                             add(changeCols, 0x43, enc.deltaNum(saveVals.p, totalDeps));
+    changeVal(SM_EXTRA_LEN); add(changeCols, 0x56, enc.rleNum(saveVals.p, C, false));
+                             add(changeCols, 0x57, enc.raw(arena.p, saveStrOff.p, saveStrLen.p, C));
+    checkErr(actorIds);
+  }
+  // ---- document ops (columnar.js:60-82)
+  if (N > 0) {
+    DocRows d = doc.view();
+    saveStrOff.ensure(ctx, N + 1); saveStrLen.ensure(ctx, N + 1);
+    auto opVal = [&](int which) { foreach(ctx, N, SaveOpValKernel{which, d, succOff.p, saveVals.p}); };
+    opVal(SC_OBJ_ACTOR); add(opCols, 0x01, enc.rleNum(saveVals.p, N, false));
+    opVal(SC_OBJ_CTR);   add(opCols, 0x02, enc.rleNum(saveVals.p, N, false));
+    opVal(SC_KEY_ACTOR); add(opCols, 0x11, enc.rleNum(saveVals.p, N, false));
+    opVal(SC_KEY_CTR);   add(opCols, 0x13, enc.deltaNum(saveVals.p, N));
+                         add(opCols, 0x15, enc.rle(StrCol{arena.p, d.keyStrOff, d.keyStrLen}, N));
+    opVal(SC_ID_ACTOR);  add(opCols, 0x21, enc.rleNum(saveVals.p, N, false));
+    opVal(SC_ID_CTR);    add(opCols, 0x23, enc.deltaNum(saveVals.p, N));
+    foreach(ctx, N, SaveInsertKernel{d, saveStrLen.p});
+                         add(opCols, 0x34, enc.boolean(saveStrLen.p, N));
+    opVal(SC_ACTION);    add(opCols, 0x42, enc.rleNum(saveVals.p, N, false));
+    opVal(SC_VAL_LEN);   add(opCols, 0x56, enc.rleNum(saveVals.p, N, false));
+    foreach(ctx, N, SaveValBytesKernel{d, saveStrLen.p});
+                         add(opCols, 0x57, enc.raw(arena.p, d.valOff, saveStrLen.p, N));
+    // chldActor 0x61 / chldCtr 0x63: always null in this format version -> empty
+    opVal(SC_SUCC_NUM);  add(opCols, 0x80, enc.rleNum(saveVals.p, N, false));
+    if (S > 0) {
+      foreach(ctx, S, SaveSuccValKernel{0, succ.p, saveVals.p}); add(opCols, 0x81, enc.rleNum(saveVals.p, S, false));
+      foreach(ctx, S, SaveSuccValKernel{1, succ.p, saveVals.p}); add(opCols, 0x83, enc.deltaNum(saveVals.p, S));
+    }
+  }
+  std::vector<u8> raw(enc.outLen);
+  if (enc.outLen) { d2h(ctx, raw.data(), enc.out.p, enc.outLen); sync(ctx); }
+  // ---- host: DEFLATE of large columns (columnar.js:1052-1057), directory, container (columnar.js:659-686)
+  struct Packed { u32 id; std::string data; };
+  std::vector<Packed> packed; std::vector<size_t> firstOp;
+  auto pack = [&](const std::vector<Col>& cols) { for (auto& c : cols) if (c.len > 0) packed.push_back({c.id, std::string((const char*)raw.data() + c.off, c.len)}); };
+  pack(changeCols); const size_t numChangeCols = packed.size(); pack(opCols);
+  {
+    std::vector<std::thread> ts; std::vector<std::string> errs(packed.size());
+    for (size_t k = 0; k < packed.size(); k++) if (packed[k].data.size() >= 256) ts.emplace_back([&, k] {
+      z_stream zs; memset(&zs, 0, sizeof(zs));
+      if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { errs[k] = "deflateInit failed"; return; }
+      std::string comp; comp.resize(deflateBound(&zs, (uLong)packed[k].data.size()));
+      zs.next_in = (Bytef*)packed[k].data.data(); zs.avail_in = (uInt)packed[k].data.size(); zs.next_out = (Bytef*)comp.data(); zs.avail_out = (uInt)comp.size();
+      const int rc = ::deflate(&zs, Z_FINISH); comp.resize(zs.total_out); deflateEnd(&zs);
+      if (rc != Z_STREAM_END) { errs[k] = "deflate failed"; return; }
+      packed[k].data.swap(comp); packed[k].id |= 8;
+    });
+    for (auto& t : ts) t.join();
+    for (auto& e : errs) if (!e.empty()) throw Error(AMG_ERR_INTERNAL, e);
+  }
+  std::string body;
+  auto uleb = [&](u64 v) { do { u8 b = v & 0x7f; v >>= 7; if (v) b |= 0x80; body.push_back((char)b); } while (v); };
+  uleb(actorIds.size()); for (auto& a : actorIds) { uleb(a.size()); body += a; }
+  uleb(heads.size()); for (auto& h : heads) body.append((const char*)h.data(), 32);
+  uleb(numChangeCols); for (size_t k = 0; k < numChangeCols; k++) { uleb(packed[k].id); uleb(packed[k].data.size()); }
+  uleb(packed.size() - numChangeCols); for (size_t k = numChangeCols; k < packed.size(); k++) { uleb(packed[k].id); uleb(packed[k].data.size()); }
+  for (auto& p : packed) body += p.data;
+  for (u32 i : headIdx) uleb(i);
+  std::string head; head.push_back(0); { u64 v = body.size(); do { u8 b = v & 0x7f; v >>= 7; if (v) b |= 0x80; head.push_back((char)b); } while (v); }
+  std::string hashed = head + body; u8 digest[32]; host_sha256((const u8*)hashed.data(), hashed.size(), digest);
+  static const u8 magic[4] = {0x85, 0x6f, 0x4a, 0x83};
+  result.assign((const char*)magic, 4); result.append((const char*)digest, 4); result += hashed;
+}
+
 // Backend.load(data) = new BackendDoc(buffer) (reference new.js:1709-1750): the document chunk's op columns are already in
 // document order with succ lists, so loading = container check + column decode + one finalize pass. The container
 // checksum (one SHA-256 over the whole chunk: inherently serial) and the DEFLATE of large columns are host pre-passes,
@@ -883,7 +991,7 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   heads = hs; headIdx = headsIndexes;
   { std::vector<size_t> o(heads.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i; std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return hs[a] < hs[b]; });
     for (size_t i = 0; i < o.size(); i++) { heads[i] = hs[o[i]]; headIdx[i] = headsIndexes[o[i]]; } }
-  changes.assign(numChanges, HostChange{0, 0}); haveHashGraph = false;
+  changes.assign(numChanges, HostChange{0, 0}); haveHashGraph = false; loadedDoc.assign((const char*)buf, len);
   while (actorCap < 2 * (actorIds.size() + 16)) actorCap *= 2;
   actorSlots.ensure(ctx, actorCap); rebuildActorTable();
 }

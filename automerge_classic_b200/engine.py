@@ -350,7 +350,14 @@ class GpuBackendDoc:
         return self._state().max_op
 
     def save(self):
-        raise Unsupported(4, 'amgpu: Backend.save() (device-side column encode, SURVEY.md §8f rank 1) is not built yet')
+        """Backend.save (new.js:2033-2055): the document chunk, columns encoded on the device."""
+        fn = getattr(self._lib.L, 'amg_save', None)
+        if fn is None:
+            raise Unsupported(4, 'amgpu: this build of libamgpu has no amg_save')
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        bl, err = C.c_void_p(), _ErrStruct()
+        self._lib.check(fn(self.h, C.byref(bl), C.byref(err)), err)
+        return self._buffers(bl)[0]
 
     def hash_by_actor(self, actor, index):
         a = bytes.fromhex(actor)

@@ -60,6 +60,8 @@ int amg_get_patch(amg_backend* b, amg_patch** out, amg_error* err);
 int amg_get_state(amg_backend* b, amg_patch** out, amg_error* err);
 
 /* Backend.getHeads — backend.js:135-137: n hashes of 32 bytes, ascending */
+/* Backend.save (backend/backend.js:93-95, new.js:2033-2055): one buffer = the document chunk */
+int amg_save(amg_backend* b, amg_buffers** out, amg_error* err);
 int amg_get_heads(amg_backend* b, amg_buffers** out, amg_error* err);
 /* Backend.getAllChanges / getChanges(haveDeps) — backend.js:142-156 -> new.js:1921-1973; have_deps = n hashes x 32 bytes */
 int amg_get_changes(amg_backend* b, const uint8_t* have_deps, size_t n, amg_buffers** out, amg_error* err);
@@ -91,8 +93,7 @@ void amg_buffers_free(amg_buffers* l);
  *   editElem: nEdits x uint64 elemId
  * ids are (counter << 16 | actorIndex); objId 0 = _root. keyOff / valOff index the document arena
  * (amg_arena); valLen is the reference's VALUE_LEN tag (length << 4 | type, columnar.js:46-49).
- * props.flags = action << 8 | 1 if the key has no visible value (reference emits `key: {}`) | 2 for a counter whose
- * increments were summed: its value is the int64 (pad << 32 | valOff), not arena bytes (new.js:941-966);
+ * props.flags = action << 8 | 1 if the key has no visible value (reference emits `key: {}`);
  * edits.kind = (0 insert | 1 remove | 2 update) | 0x100 if the edit starts a new run (edits without the bit
  * continue the previous insert as `multi-insert` / add to the previous remove's count, new.js:747-782)
  * | 0x200 if the insert is rendered as `multi-insert` (set on every member of a run, and on a run start whose

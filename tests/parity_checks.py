@@ -128,6 +128,24 @@ def check_counters(gpu_doc, oracle_mod, seed, n, a, chunk):
     _dump_equal(g, orc)
 
 
+def check_save(gpu_doc, oracle_mod, cfg, n, a, chunk=97):
+    """Backend.save(): the document chunk is byte-identical to the oracle's (same zlib), loads back into the same state,
+    and saves to the same bytes again."""
+    from automerge_classic_b200 import tracegen
+    ch = tracegen.generate(cfg, n, a).changes()
+    orc, g = oracle_mod.OracleDoc(), gpu_doc()
+    for lo in range(0, len(ch), chunk):
+        orc.apply_changes(ch[lo:lo + chunk])
+        g.apply_changes(ch[lo:lo + chunk])
+    so, sg = orc.save(), g.save()
+    assert len(so) == len(sg) and so == sg, (cfg, len(so), len(sg))
+    g2 = gpu_doc(sg)
+    d = replay.deep_equal(replay.decode(g2.get_patch()), replay.decode(orc.get_patch()))
+    assert d is None, d
+    assert g2.save() == sg
+    assert gpu_doc().save() == oracle_mod.OracleDoc().save()      # empty document
+
+
 def check_incremental_calls(gpu_doc, oracle_mod):
     """Applying a trace in several applyChanges calls gives the same patches as the oracle call by call."""
     from automerge_classic_b200 import tracegen

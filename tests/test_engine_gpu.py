@@ -79,6 +79,11 @@ def test_counters_parity(gpu_doc, oracle_mod, n, a, chunk):
         parity_checks.check_counters(gpu_doc, oracle_mod, seed, n, a, chunk)
 
 
+@pytest.mark.parametrize('cfg,n,a', [('C1', 0, 0), ('C2', 400, 0), ('C2b', 700, 0), ('C3', 3000, 10), ('C4', 2000, 4), ('C6', 400, 3), ('C7', 500, 3), ('C3', 20000, 10)])
+def test_save_parity(gpu_doc, oracle_mod, cfg, n, a):
+    parity_checks.check_save(gpu_doc, oracle_mod, cfg, n, a)
+
+
 def test_incremental_calls_match_bulk(gpu_doc, oracle_mod):
     parity_checks.check_incremental_calls(gpu_doc, oracle_mod)
 

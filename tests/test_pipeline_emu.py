@@ -65,6 +65,11 @@ def test_counters_emu(emu_doc, oracle_mod, n, a, chunk):
         parity_checks.check_counters(emu_doc, oracle_mod, seed, n, a, chunk)
 
 
+@pytest.mark.parametrize('cfg,n,a', [('C1', 0, 0), ('C2', 400, 0), ('C2b', 700, 0), ('C3', 3000, 10), ('C4', 2000, 4), ('C6', 400, 3), ('C7', 500, 3)])
+def test_save_emu(emu_doc, oracle_mod, cfg, n, a):
+    parity_checks.check_save(emu_doc, oracle_mod, cfg, n, a)
+
+
 def test_incremental_calls_emu(emu_doc, oracle_mod):
     parity_checks.check_incremental_calls(emu_doc, oracle_mod)
 
