@@ -126,6 +126,26 @@ struct SaveChangeValKernel {   // one int64 value per applied change, from its p
 struct SaveMessageKernel { const ChangeMeta* meta; u32* strOff; u32* strLen; HD void operator()(size_t c) const { strOff[c] = meta[c].msgOff; strLen[c] = meta[c].msgLen; } };
 struct SaveDepIndexKernel { const u32* depIdx; long long* out; HD void operator()(size_t k) const { out[k] = depIdx[k]; } };
 
+// change metadata of a loaded document: its columns are decoded again (one thread per column, as Backend.load does for
+// the op columns) so that changes applied after the load can be appended before re-encoding
+enum { LC_UINT, LC_DELTA, LC_STRING, LC_EXTRA_LEN, LC_SUM };
+struct LoadedColKernel {
+  int kind; const u8* arena; u32 off, len, rawOff; u32 count; long long* out; u32* strOff; u32* strLen; u64* sum;
+  HD void operator()(size_t) const {
+    RleReader r(arena, off, off + len, kind == LC_STRING ? 2 : (kind == LC_DELTA ? 1 : 0));
+    long long acc = 0; u64 total = 0; u32 raw = rawOff;
+    for (u32 i = 0; kind == LC_SUM ? !r.done() : i < count; i++) {
+      long long n = 0; u32 o = 0, l = 0; const bool nn = r.next(n, o, l);
+      if (kind == LC_SUM) { if (nn) total += (u64)n; continue; }
+      if (kind == LC_STRING) { strOff[i] = o; strLen[i] = nn ? l : NULL32; continue; }
+      if (kind == LC_DELTA) { if (nn) { acc += n; out[i] = acc; } else out[i] = NULLV; continue; }
+      out[i] = nn ? n : NULLV;
+      if (kind == LC_EXTRA_LEN) { const u32 bytes = nn ? (u32)((u64)n >> 4) : 0; strOff[i] = raw; strLen[i] = bytes; raw += bytes; }
+    }
+    if (kind == LC_SUM) *sum = total;
+  }
+};
+
 struct ColumnEncoder {
   Ctx& ctx; ScanTemp& st;
   DBuf<u32> head, headScan, runStart, recHead, recScan, recFirst, bytes, byteOff, nnFlag, nnSlot; DBuf<long long> compact, delta;

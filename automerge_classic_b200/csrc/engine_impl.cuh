@@ -61,7 +61,7 @@ inline void Engine::finishPatch(PatchOut& out) {
 inline void Engine::reset() {
   sync(ctx);
   arenaLen = 0; hostArena.len = 0; numApplied = 0; numRows = 0; numSucc = 0; dev_memset(ctx, succOff.p, 0, 4);
-  actorIds.clear(); actorRep.clear(); clock.clear(); heads.clear(); headIdx.clear(); changes.clear(); changeHashes.clear(); deflatedOriginal.clear(); loadedDoc.clear();
+  actorIds.clear(); actorRep.clear(); clock.clear(); heads.clear(); headIdx.clear(); changes.clear(); changeHashes.clear(); deflatedOriginal.clear(); loadedDoc.clear(); numLoaded = 0;
   queue.clear(); queueOriginal.clear(); maxOp = 0; rebuildActorTable();
 }
 
@@ -74,7 +74,13 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   struct ClearTimer { Engine* e; ~ClearTimer() { e->curTimer = nullptr; e->curHostMark = nullptr; e->dbgMark = [](const char*) {}; } } clearTimer{this};
   // ------------------------------------------------------------ 0. stage the batch in the arena (pinned host mirror + device)
   const size_t arenaLen0 = arenaLen; const size_t hostLen0 = hostArena.size();
-  std::vector<HostChange> batch, batchOriginal;   // batchOriginal: arena range of the original bytes of DEFLATEd changes (empty vector = none)
+  std::vector<HostChange> batch, batchOriginal, inflOrig;   // originals of DEFLATEd changes: batchOriginal (dense, queue entries) / inflOrig (sparse, parallel to deflIdx)
+  std::vector<u32> deflIdx;
+  auto originalOf = [&](size_t b) -> HostChange {
+    if (!batchOriginal.empty() && batchOriginal[b].len) return batchOriginal[b];
+    auto it = std::lower_bound(deflIdx.begin(), deflIdx.end(), (u32)b);
+    return it != deflIdx.end() && *it == (u32)b ? inflOrig[it - deflIdx.begin()] : HostChange{0, 0};
+  };
   struct Rollback { Engine* e; size_t len; bool armed = true; ~Rollback() { if (armed) { e->hostArena.resize(len); e->rebuildActorTable(); } } };
   size_t total = 0;
   if (blob && n > 0) total = offsets[n] - offsets[0]; else for (size_t i = 0; i < n; i++) total += lens[i];
@@ -134,7 +140,6 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   // ------------------------------------------------------------ 1. hash + header parse
   dev_memset(ctx, errWord.p, 0, 16);
   hashes.ensure(ctx, (numApplied + B) * 32 + 64, numApplied * 32);
-  std::vector<u32> deflIdx;
   {
     // Which changes of the bulk batch are DEFLATEd (columnar.js:742)? Those are inflated on the device, behind the batch:
     // flag -> scan -> ordered list -> InflateKernel pass 0 (sizes) -> scan -> pass 1 (bytes); the originals stay in place.
@@ -167,8 +172,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       hostArena.resize(cur);
       d2h(ctx, hostArena.data() + extraStart, arena.p + extraStart, extra);
       sync(ctx);
-      if (batchOriginal.empty()) batchOriginal.assign(B, HostChange{0, 0});
-      for (size_t k = 0; k < nd; k++) { const u32 bi = deflIdx[k]; batchOriginal[bi] = HostChange{oOff[k], oLen[k]}; batch[bi] = HostChange{(u32)extraStart + newOff[k], newLen[k]}; }
+      inflOrig.resize(nd);   // deflIdx is ascending: (batch index, original range), looked up by binary search
+      for (size_t k = 0; k < nd; k++) { const u32 bi = deflIdx[k]; inflOrig[k] = HostChange{oOff[k], oLen[k]}; batch[bi] = HostChange{(u32)extraStart + newOff[k], newLen[k]}; }
       dbgMark("sha:inflated");
     }
   }
@@ -214,7 +219,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   if (numNew < B) for (size_t b = 0; b < B; b++) {
     const u32 pr = primaryH[b];
     const bool hashApplied = pr < numApplied || appliedH[pr - numApplied];
-    if (!hashApplied) { newQueue.push_back(batch[b]); newQueueOriginal.push_back(batchOriginal.empty() ? HostChange{0, 0} : batchOriginal[b]); }
+    if (!hashApplied) { newQueue.push_back(batch[b]); newQueueOriginal.push_back(originalOf(b)); }
   }
   timer.mark(); hostMark();
   std::vector<std::string> actorsNow = actorIds; std::vector<u64> clockNow = clock; std::vector<u32> actorCntH; std::vector<std::pair<u32, u32>> actorRepNow = actorRep;
@@ -481,10 +486,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     }
     if (appliedH.empty()) {   // all applied, in order
       const u32 base0 = (u32)changes.size();
-      if (!batchOriginal.empty()) {
-        if (deflIdx.empty() || Bq > 0) { for (size_t b = 0; b < B; b++) if (batchOriginal[b].len) deflatedOriginal.push_back({base0 + (u32)b, batchOriginal[b]}); }
-        else { deflatedOriginal.reserve(deflatedOriginal.size() + deflIdx.size()); for (u32 b : deflIdx) deflatedOriginal.push_back({base0 + b, batchOriginal[b]}); }
-      }
+      if (!batchOriginal.empty()) for (size_t b = 0; b < B; b++) { const HostChange o = originalOf(b); if (o.len) deflatedOriginal.push_back({base0 + (u32)b, o}); }
+      else { deflatedOriginal.reserve(deflatedOriginal.size() + deflIdx.size()); for (size_t k = 0; k < deflIdx.size(); k++) deflatedOriginal.push_back({base0 + deflIdx[k], inflOrig[k]}); }
       if (changes.empty()) changes.swap(batch); else changes.insert(changes.end(), batch.begin(), batch.end());
     }
     else {
@@ -492,7 +495,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       if (appliedH.empty()) for (size_t b = 0; b < B; b++) byRank[b] = (u32)b; else for (size_t b = 0; b < B; b++) if (appliedH[b]) byRank[appRankH[b]] = (u32)b;
       for (size_t k = 0; k < numNew; k++) {
         const u32 b = byRank[k];
-        if (!batchOriginal.empty() && batchOriginal[b].len) deflatedOriginal.push_back({(u32)changes.size(), batchOriginal[b]});
+        { const HostChange o = originalOf(b); if (o.len) deflatedOriginal.push_back({(u32)changes.size(), o}); }
         changes.push_back(batch[b]);
       }
     }
@@ -801,47 +804,55 @@ inline std::string inflateRawBytes(const u8* p, size_t n) {
 // on the device (encode.cuh); the container (column directory, DEFLATE of columns >= 256 bytes, checksum) is assembled
 // on the host, as the reference does.
 inline void Engine::saveDocument(std::string& result) {
-  if (!haveHashGraph && numApplied > 0) {
-    if (!loadedDoc.empty()) { result = loadedDoc; return; }   // unchanged since Backend.load (new.js:2034)
-    throw Error(AMG_ERR_UNSUPPORTED, "amgpu: save() after load() followed by further changes needs the loaded change metadata re-encoded (not built)");
-  }
+  if (!loadedDoc.empty()) { result = loadedDoc; return; }   // unchanged since Backend.load (new.js:2034)
   if (!encoder) encoder.reset(new ColumnEncoder(ctx, scanTmp));
   ColumnEncoder& enc = *encoder; enc.outLen = 0;
   struct Col { u32 id; size_t off, len; };
   std::vector<Col> changeCols, opCols;
   auto add = [&](std::vector<Col>& cols, u32 id, size_t len) { cols.push_back({id, enc.outLen - len, len}); };
-  const size_t C = numApplied, N = numRows, S = numSucc;
+  const size_t C = numApplied, N = numRows, S = numSucc, L = numLoaded, K = C - L;   // K changes have their bytes in the arena
   dev_memset(ctx, errWord.p, 0, 16);
   saveVals.ensure(ctx, std::max(std::max(C, N), S) + 2);
-  // ---- change metadata (new.js:1680-1692 appendChange)
+  // ---- change metadata (new.js:1680-1692 appendChange); the first L rows come from the loaded document's own columns
   if (C > 0) {
-    chPairs.ensure(ctx, C); chOff.ensure(ctx, C); chLen.ensure(ctx, C);
-    h2d(ctx, chPairs.p, changes.data(), C * sizeof(HostChange));
-    foreach(ctx, C, SplitPairsKernel{chPairs.p, chOff.p, chLen.p});
-    meta.ensure(ctx, C); colOff.ensure(ctx, (size_t)NCOLS * C); colLen.ensure(ctx, (size_t)NCOLS * C);
-    nOps.ensure(ctx, C + 1); nPreds.ensure(ctx, C + 1); nDeps.ensure(ctx, C + 1); nActors.ensure(ctx, C + 1);
-    foreach(ctx, C, ParseKernel{arena.p, chOff.p, chLen.p, C, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
-    depBase.ensure(ctx, C + 1); scan_exclusive(ctx, scanTmp, nDeps.p, depBase.p, C);
-    const u32 totalDeps = readU32(depBase.p + C);
-    depIdx.ensure(ctx, totalDeps + 1); primary.ensure(ctx, C);
-    const size_t tcap = pow2_at_least(2 * C + 2);
-    hashTable.ensure(ctx, tcap); dev_memset(ctx, hashTable.p, 0xff, tcap * 4);
-    foreach(ctx, C, HashInsertKernel{hashes.p, hashTable.p, (u64)tcap - 1});
-    foreach(ctx, C, ResolveDepsKernel{arena.p, hashes.p, hashTable.p, (u64)tcap - 1, meta.p, 0, depBase.p, depIdx.p, primary.p});
-    saveVals.ensure(ctx, std::max<size_t>(std::max(std::max(C, N), S), totalDeps) + 2);
+    u32 totalDeps = 0, loadedDeps = 0;
+    if (K > 0) {
+      chPairs.ensure(ctx, K); chOff.ensure(ctx, K); chLen.ensure(ctx, K);
+      h2d(ctx, chPairs.p, changes.data() + L, K * sizeof(HostChange));
+      foreach(ctx, K, SplitPairsKernel{chPairs.p, chOff.p, chLen.p});
+      meta.ensure(ctx, K); colOff.ensure(ctx, (size_t)NCOLS * K); colLen.ensure(ctx, (size_t)NCOLS * K);
+      nOps.ensure(ctx, K + 1); nPreds.ensure(ctx, K + 1); nDeps.ensure(ctx, K + 1); nActors.ensure(ctx, K + 1);
+      foreach(ctx, K, ParseKernel{arena.p, chOff.p, chLen.p, K, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
+      depBase.ensure(ctx, K + 1); scan_exclusive(ctx, scanTmp, nDeps.p, depBase.p, K);
+      totalDeps = readU32(depBase.p + K);
+      depIdx.ensure(ctx, totalDeps + 1); primary.ensure(ctx, K);
+      const size_t tcap = pow2_at_least(2 * C + 2);
+      hashTable.ensure(ctx, tcap); dev_memset(ctx, hashTable.p, 0xff, tcap * 4);
+      foreach(ctx, C, HashInsertKernel{hashes.p, hashTable.p, (u64)tcap - 1});
+      foreach(ctx, K, ResolveDepsKernel{arena.p, hashes.p, hashTable.p, (u64)tcap - 1, meta.p, L, depBase.p, depIdx.p, primary.p});
+    }
+    auto loadedCol = [&](u32 id) -> const HostChange& { static const u32 IDS[9] = {0x01, 0x03, 0x13, 0x23, 0x35, 0x40, 0x43, 0x56, 0x57}; for (int k = 0; k < 9; k++) if (IDS[k] == id) return loadedCols[k]; return loadedCols[0]; };
+    if (L > 0) {   // number of dependency indexes the loaded changes carry
+      DBuf<u64>& sumD = pairSucc; sumD.ensure(ctx, 1);
+      const HostChange& dn = loadedCol(0x40);
+      foreach(ctx, 1, LoadedColKernel{LC_SUM, arena.p, dn.off, dn.len, 0, 0, nullptr, nullptr, nullptr, sumD.p});
+      u64 sum = 0; d2h(ctx, &sum, sumD.p, 8); sync(ctx); loadedDeps = (u32)sum;
+    }
+    saveVals.ensure(ctx, std::max<size_t>(std::max(std::max(C, N), S), (size_t)loadedDeps + totalDeps) + 2);
     saveStrOff.ensure(ctx, std::max(C, N) + 1); saveStrLen.ensure(ctx, std::max(C, N) + 1);
-    auto changeVal = [&](int which) { foreach(ctx, C, SaveChangeValKernel{which, arena.p, meta.p, actorSlots.p, (u64)actorCap - 1, saveVals.p, saveStrOff.p, saveStrLen.p, errWord.p}); };
-    changeVal(SM_ACTOR);     add(changeCols, 0x01, enc.rleNum(saveVals.p, C, false));
-    changeVal(SM_SEQ);       add(changeCols, 0x03, enc.deltaNum(saveVals.p, C));
-    changeVal(SM_MAX_OP);    add(changeCols, 0x13, enc.deltaNum(saveVals.p, C));
-    changeVal(SM_TIME);      add(changeCols, 0x23, enc.deltaNum(saveVals.p, C));
-    foreach(ctx, C, SaveMessageKernel{meta.p, saveStrOff.p, saveStrLen.p});
-                             add(changeCols, 0x35, enc.rle(StrCol{arena.p, saveStrOff.p, saveStrLen.p}, C));
-    changeVal(SM_DEPS_NUM);  add(changeCols, 0x40, enc.rleNum(saveVals.p, C, false));
-    foreach(ctx, totalDeps, SaveDepIndexKernel{depIdx.p, saveVals.p});
-                             add(changeCols, 0x43, enc.deltaNum(saveVals.p, totalDeps));
-    changeVal(SM_EXTRA_LEN); add(changeCols, 0x56, enc.rleNum(saveVals.p, C, false));
-                             add(changeCols, 0x57, enc.raw(arena.p, saveStrOff.p, saveStrLen.p, C));
+    auto loadedVal = [&](int kind, u32 id, u32 count) { if (L == 0) return; const HostChange& c = loadedCol(id); foreach(ctx, 1, LoadedColKernel{kind, arena.p, c.off, c.len, loadedCol(0x57).off, count, saveVals.p, saveStrOff.p, saveStrLen.p, nullptr}); };
+    auto changeVal = [&](int which) { if (K == 0) return; foreach(ctx, K, SaveChangeValKernel{which, arena.p, meta.p, actorSlots.p, (u64)actorCap - 1, saveVals.p + L, saveStrOff.p + L, saveStrLen.p + L, errWord.p}); };
+    loadedVal(LC_UINT, 0x01, (u32)L);  changeVal(SM_ACTOR);     add(changeCols, 0x01, enc.rleNum(saveVals.p, C, false));
+    loadedVal(LC_DELTA, 0x03, (u32)L); changeVal(SM_SEQ);       add(changeCols, 0x03, enc.deltaNum(saveVals.p, C));
+    loadedVal(LC_DELTA, 0x13, (u32)L); changeVal(SM_MAX_OP);    add(changeCols, 0x13, enc.deltaNum(saveVals.p, C));
+    loadedVal(LC_DELTA, 0x23, (u32)L); changeVal(SM_TIME);      add(changeCols, 0x23, enc.deltaNum(saveVals.p, C));
+    loadedVal(LC_STRING, 0x35, (u32)L); if (K > 0) foreach(ctx, K, SaveMessageKernel{meta.p, saveStrOff.p + L, saveStrLen.p + L});
+                                       add(changeCols, 0x35, enc.rle(StrCol{arena.p, saveStrOff.p, saveStrLen.p}, C));
+    loadedVal(LC_UINT, 0x40, (u32)L);  changeVal(SM_DEPS_NUM);  add(changeCols, 0x40, enc.rleNum(saveVals.p, C, false));
+    loadedVal(LC_DELTA, 0x43, loadedDeps); if (totalDeps > 0) foreach(ctx, totalDeps, SaveDepIndexKernel{depIdx.p, saveVals.p + loadedDeps});
+                                       add(changeCols, 0x43, enc.deltaNum(saveVals.p, (size_t)loadedDeps + totalDeps));
+    loadedVal(LC_EXTRA_LEN, 0x56, (u32)L); changeVal(SM_EXTRA_LEN); add(changeCols, 0x56, enc.rleNum(saveVals.p, C, false));
+                                       add(changeCols, 0x57, enc.raw(arena.p, saveStrOff.p, saveStrLen.p, C));
     checkErr(actorIds);
   }
   // ---- document ops (columnar.js:60-82)
@@ -966,6 +977,11 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   hostArena.resize(0); std::vector<std::pair<u32, u32>> reps;
   for (auto& a : actors) { reps.emplace_back((u32)hostArena.size(), (u32)a.size()); hostArena.append(a.data(), a.size()); }
   for (auto& c : opCols) for (int k = 0; k < 16; k++) if (c.id == DOC_IDS[k]) { dc.off[k] = (u32)hostArena.size(); dc.len[k] = (u32)c.data.size(); hostArena.append(c.data.data(), c.data.size()); }
+  {   // the change metadata columns stay available for a later save() (new.js:1717 keeps them as encoders)
+    static const u32 CHANGE_IDS[9] = {0x01, 0x03, 0x13, 0x23, 0x35, 0x40, 0x43, 0x56, 0x57};
+    for (int k = 0; k < 9; k++) loadedCols[k] = HostChange{(u32)hostArena.size(), 0};
+    for (auto& c : changeCols) for (int k = 0; k < 9; k++) if (c.id == CHANGE_IDS[k]) { loadedCols[k] = HostChange{(u32)hostArena.size(), (u32)c.data.size()}; hostArena.append(c.data.data(), c.data.size()); }
+  }
   const size_t cur = hostArena.size();
   if (cur + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
   arena.ensure(ctx, cur + 64); h2d(ctx, arena.p, hostArena.data(), cur); dev_memset(ctx, arena.p + cur, 0, 64);
@@ -991,7 +1007,7 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   heads = hs; headIdx = headsIndexes;
   { std::vector<size_t> o(heads.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i; std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return hs[a] < hs[b]; });
     for (size_t i = 0; i < o.size(); i++) { heads[i] = hs[o[i]]; headIdx[i] = headsIndexes[o[i]]; } }
-  changes.assign(numChanges, HostChange{0, 0}); haveHashGraph = false; loadedDoc.assign((const char*)buf, len);
+  changes.assign(numChanges, HostChange{0, 0}); haveHashGraph = false; loadedDoc.assign((const char*)buf, len); numLoaded = numChanges;
   while (actorCap < 2 * (actorIds.size() + 16)) actorCap *= 2;
   actorSlots.ensure(ctx, actorCap); rebuildActorTable();
 }

@@ -392,11 +392,11 @@ struct ListGroupKernel {
     if (t0 > 0 && !(c.ops.flags[i0] & F_INSERT)) {
       size_t tp = t0 - 1; while (tp > 0 && !groupHead[tp]) tp--;
       const u32 ip = c.opAt[tp];
-      if (!c.isMapOp(ip) && !(c.ops.flags[ip] & F_INSERT) && id_actor(c.ops.id[ip]) == id_actor(c.ops.id[i0]) && c.ops.obj[ip] == c.ops.obj[i0] && gElem[tp] != ROW_NONE && gElem[tp] != e) {
+      if (!c.isMapOp(ip) && !(c.ops.flags[ip] & F_INSERT) && id_actor(c.ops.id[ip]) == id_actor(c.ops.id[i0]) && c.ops.obj[ip] == c.ops.obj[i0] && gElem[tp] != ROW_NONE && gElem[tp] < e &&
+          L.visAt(gElem[tp], L.groupRows[L.groupOf[gElem[tp]]], T0 - 1)) {   // cheap tests first: the walk below can be long
         const u32 e1 = gElem[tp]; u32 p = e;
         while (p > 0 && L.d.obj[p - 1] == L.d.obj[e] && L.d.time[p - 1] >= T0) p--;      // rows that arrive later in this batch were not there yet
-        if (p > 0 && L.d.obj[p - 1] == L.d.obj[e] && L.d.keyStrLen[p - 1] == NULL32 && L.groupFirst[L.groupOf[p - 1]] == e1 &&
-            L.visAt(e1, L.groupRows[L.groupOf[e1]], T0 - 1)) headIdx = idx - 1;
+        if (p > 0 && L.d.obj[p - 1] == L.d.obj[e] && L.d.keyStrLen[p - 1] == NULL32 && L.groupFirst[L.groupOf[p - 1]] == e1) headIdx = idx - 1;
       }
     }
     u32 k = gBase[t0], nV = 0;

@@ -146,6 +146,28 @@ def check_save(gpu_doc, oracle_mod, cfg, n, a, chunk=97):
     assert gpu_doc().save() == oracle_mod.OracleDoc().save()      # empty document
 
 
+def check_save_after_load(gpu_doc, oracle_mod, cfg, n, a):
+    """load -> applyChanges -> save (new.js:1709-1750, 2033-2055): the loaded change metadata is re-encoded together with
+    the new changes; bytes equal the oracle's and those of a document that never went through save / load."""
+    from automerge_classic_b200 import tracegen
+    ch = tracegen.generate(cfg, n, a).changes()
+    cut = len(ch) // 2
+    orc, g = oracle_mod.OracleDoc(), gpu_doc()
+    orc.apply_changes(ch[:cut]); g.apply_changes(ch[:cut])
+    s1 = g.save()
+    assert s1 == orc.save()
+    o2, g2 = oracle_mod.OracleDoc(s1), gpu_doc(s1)
+    assert g2.save() == s1
+    po, pg = o2.apply_changes(ch[cut:]), g2.apply_changes(ch[cut:])
+    d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+    assert d is None, d
+    so, sg = o2.save(), g2.save()
+    orc.apply_changes(ch[cut:])
+    assert sg == so and sg == orc.save()
+    d = replay.deep_equal(replay.decode(gpu_doc(sg).get_patch()), replay.decode(orc.get_patch()))
+    assert d is None, d
+
+
 def check_incremental_calls(gpu_doc, oracle_mod):
     """Applying a trace in several applyChanges calls gives the same patches as the oracle call by call."""
     from automerge_classic_b200 import tracegen

@@ -84,6 +84,11 @@ def test_save_parity(gpu_doc, oracle_mod, cfg, n, a):
     parity_checks.check_save(gpu_doc, oracle_mod, cfg, n, a)
 
 
+@pytest.mark.parametrize('cfg,n,a', [('C1', 0, 0), ('C2', 400, 0), ('C6', 300, 1), ('C7', 300, 1)])
+def test_save_after_load(gpu_doc, oracle_mod, cfg, n, a):
+    parity_checks.check_save_after_load(gpu_doc, oracle_mod, cfg, n, a)
+
+
 def test_incremental_calls_match_bulk(gpu_doc, oracle_mod):
     parity_checks.check_incremental_calls(gpu_doc, oracle_mod)
 

@@ -70,6 +70,11 @@ def test_save_emu(emu_doc, oracle_mod, cfg, n, a):
     parity_checks.check_save(emu_doc, oracle_mod, cfg, n, a)
 
 
+@pytest.mark.parametrize('cfg,n,a', [('C1', 0, 0), ('C2', 400, 0), ('C6', 300, 1), ('C7', 300, 1)])
+def test_save_after_load_emu(emu_doc, oracle_mod, cfg, n, a):
+    parity_checks.check_save_after_load(emu_doc, oracle_mod, cfg, n, a)
+
+
 def test_incremental_calls_emu(emu_doc, oracle_mod):
     parity_checks.check_incremental_calls(emu_doc, oracle_mod)
 
