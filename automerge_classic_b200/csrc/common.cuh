@@ -45,6 +45,8 @@ enum ErrCode {
 struct Ctx {
 #ifndef AMG_EMU
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;        // second stream: work that may overlap the main pipeline (joined through events)
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
 #endif
   int device = 0;
   int numSMs = 148;
@@ -154,7 +156,7 @@ template <class F> __global__ void __launch_bounds__(256) k_foreach(size_t n, F 
 }
 #endif
 
-template <class F> inline void foreach(Ctx& c, size_t n, const F& f) {
+template <class F> inline void foreach(Ctx& c, size_t n, const F& f, bool onSide = false) {
   if (n == 0) return;
 #ifdef AMG_EMU
   for (size_t i = 0; i < n; i++) f(i);
@@ -163,10 +165,21 @@ template <class F> inline void foreach(Ctx& c, size_t n, const F& f) {
   size_t want = (n + block - 1) / block;
   size_t maxGrid = (size_t)c.numSMs * 8;   // 8 resident CTAs of 256 threads per SM
   int grid = (int)(want < maxGrid ? want : maxGrid);
-  k_foreach<F><<<grid, block, 0, c.stream>>>(n, f);
+  k_foreach<F><<<grid, block, 0, onSide ? c.side : c.stream>>>(n, f);
   CUDA_CHECK(cudaGetLastError());
 #endif
   c.launches++;
+}
+// side stream: fork() makes it wait for everything enqueued on the main stream so far, join() the reverse
+inline void side_fork(Ctx& c) {
+#ifndef AMG_EMU
+  CUDA_CHECK(cudaEventRecord(c.evFork, c.stream)); CUDA_CHECK(cudaStreamWaitEvent(c.side, c.evFork, 0));
+#endif
+}
+inline void side_join(Ctx& c) {
+#ifndef AMG_EMU
+  CUDA_CHECK(cudaEventRecord(c.evJoin, c.side)); CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.evJoin, 0));
+#endif
 }
 
 // ---------------------------------------------------------------- atomics (serial in EMU)
@@ -208,6 +221,37 @@ HD void warp_agg_inc(uint32_t* counter, uint32_t index) {
 typedef unsigned long long u64;
 typedef uint32_t u32;
 typedef uint8_t u8;
+
+// *target = max(*target, v) / min with one atomic per warp: every lane calls it (inside divergent code is fine, the
+// active lanes form the group)
+HD void warp_agg_max(u64* target, u64 v) {
+#if defined(__CUDA_ARCH__)
+  const unsigned active = __activemask();
+  const uint32_t hi = __reduce_max_sync(active, (uint32_t)(v >> 32));
+  const uint32_t lo = __reduce_max_sync(active, (uint32_t)(v >> 32) == hi ? (uint32_t)v : 0u);
+  if ((int)(threadIdx.x & 31) == __ffs(active) - 1) { const u64 m = ((u64)hi << 32) | lo; if (m > *target) atomicMax(target, m); }
+#else
+  if (v > *target) *target = v;
+#endif
+}
+HD void warp_agg_max(uint32_t* target, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  const unsigned active = __activemask();
+  const uint32_t m = __reduce_max_sync(active, v);
+  if ((int)(threadIdx.x & 31) == __ffs(active) - 1 && m > *target) atomicMax(target, m);
+#else
+  if (v > *target) *target = v;
+#endif
+}
+HD void warp_agg_add(uint32_t* target, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  const unsigned active = __activemask();
+  const uint32_t sum = __reduce_add_sync(active, v);
+  if ((int)(threadIdx.x & 31) == __ffs(active) - 1) atomicAdd(target, sum);
+#else
+  *target += v;
+#endif
+}
 
 HD u64 mix64(u64 x) {   // splitmix64 finaliser: hash for open-addressing tables
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 27; x *= 0x94d049bb133111ebULL; x ^= x >> 31; return x;

@@ -339,10 +339,14 @@ struct ParseKernel {
     m.dirOff = dirPos; m.dataOff = dataPos;
     m.extraOff = dataPos + (u32)total; m.extraLen = off + len - m.extraOff;
     // count ops (values of the action column) and preds (sum of the predNum column)
-    u32 kerr = 0;
-    const u32 nOps = rle_count_values(arena, dataPos + actOff, dataPos + actOff + actLen, &kerr);
-    u64 nPreds = 0;
-    if (!kerr) nPreds = rle_sum_values(arena, dataPos + pnOff, dataPos + pnOff + pnLen, nOps, &kerr);
+    u32 kerr = 0; u32 nOps; u64 nPreds = 0;
+    // single-op changes (the shape of editing traces): both columns are one literal record [-1, value]
+    const u8* ap = arena + dataPos + actOff; const u8* pp = arena + dataPos + pnOff;
+    if (actLen == 2 && ap[0] == 0x7f && ap[1] < 0x80 && ((pnLen == 2 && pp[0] == 0x7f && pp[1] < 0x80) || pnLen == 0)) { nOps = 1; nPreds = pnLen ? pp[1] : 0; }
+    else {
+      nOps = rle_count_values(arena, dataPos + actOff, dataPos + actOff + actLen, &kerr);
+      if (!kerr) nPreds = rle_sum_values(arena, dataPos + pnOff, dataPos + pnOff + pnLen, nOps, &kerr);
+    }
     if (kerr) { raise(errWord, kerr, c); meta[c] = m; return; }
     if (nPreds > 0x7fffffffULL) { raise(errWord, KE_TOO_LARGE, c); meta[c] = m; return; }
     m.nOps = nOps; m.nPreds = (u32)nPreds;
@@ -459,6 +463,43 @@ HD void fill_absent_column(int col, u32 nOps, u32 base, u32 predBase, u32 nPreds
 // column of its few ops; consecutive threads write consecutive rows (coalesced). No directory round trip through HBM.
 struct DecodeSmallKernel {
   const u8* arena; const ChangeMeta* meta; const u32* opBase; const u32* predBase; const u8* applied; RawRows rows; u64* errWord;
+  // A column that holds exactly one value is either the literal record [-1, v] or the null run [0, 1]. Handles those two
+  // byte patterns directly (v in one or two LEB bytes); anything else returns false and takes the general decoder,
+  // which also reports the malformed cases.
+  HD bool decode_single(int ix, u32 pos, u32 l, u32 base, u32 rawOff, u32 rawLen, u32 pb, u32 nPreds) const {
+    const u8* p = arena + pos;
+    if (ix == CX_INSERT) {
+      if (l == 1 && p[0] == 1) { rows.insert[base] = 0; return true; }
+      if (l == 2 && p[0] == 0 && p[1] == 1) { rows.insert[base] = 1; return true; }
+      return false;
+    }
+    if (ix == CX_PRED_ACTOR || ix == CX_PRED_CTR) { if (nPreds != 1) return false; }
+    bool isNull = false; u32 v = 0, used = 0;
+    if (l == 2 && p[0] == 0 && p[1] == 1) { isNull = true; used = 2; }
+    else if (l >= 2 && p[0] == 0x7f) {
+      if (ix == CX_KEY_STR) { if (p[1] >= 0x80) return false; v = p[1]; used = 2 + v; }
+      else if (p[1] < 0x80) { v = p[1]; used = 2; }
+      else if (l >= 3 && p[2] < 0x80) { v = (p[1] & 0x7fu) | ((u32)p[2] << 7); used = 3; }
+      else return false;
+    } else return false;
+    if (used != l) return false;
+    const bool isDelta = ix == CX_KEY_CTR || ix == CX_PRED_CTR;
+    if (isDelta && !isNull) { const int sv = used == 2 ? ((int)(v << 25) >> 25) : ((int)(v << 18) >> 18); if (sv < 0) return false; v = (u32)sv; }
+    switch (ix) {
+      case CX_OBJ_ACTOR: rows.objActor[base] = isNull ? NULL32 : v; break;
+      case CX_OBJ_CTR: rows.objCtr[base] = isNull ? NULL32 : v; break;
+      case CX_KEY_ACTOR: rows.keyActor[base] = isNull ? NULL32 : v; break;
+      case CX_KEY_CTR: rows.keyCtr[base] = isNull ? NULL32 : v; break;
+      case CX_ACTION: rows.action[base] = isNull ? NULL32 : v; break;
+      case CX_KEY_STR: rows.keyStrOff[base] = isNull ? 0 : pos + 2; rows.keyStrLen[base] = isNull ? NULL32 : v; break;
+      case CX_VAL_LEN: { const u32 bytes = isNull ? 0 : (v >> 4); if (bytes > rawLen) return false; rows.valLen[base] = isNull ? NULL32 : v; rows.valOff[base] = rawOff; } break;
+      case CX_PRED_NUM: rows.predNum[base] = isNull ? 0 : v; rows.predOff[base] = pb; break;
+      case CX_PRED_ACTOR: rows.predActor[pb] = isNull ? NULL32 : v; break;
+      case CX_PRED_CTR: rows.predCtr[pb] = isNull ? NULL32 : v; break;
+      default: return false;
+    }
+    return true;
+  }
   HD void operator()(size_t c) const {
     if (!applied[c]) return;
     const u32 nOps = meta[c].nOps; if (nOps == 0 || nOps > SMALL_CHANGE_OPS) return;
@@ -471,8 +512,10 @@ struct DecodeSmallKernel {
         if (ix == CX_VAL_LEN) {   // VALUE_RAW (0x57) directly follows VALUE_LEN (0x56) in the directory when present
           ByteReader peek = d; if (!peek.done()) { const u32 nid = (u32)peek.uleb(), nl = (u32)peek.uleb(); if (nid == 0x57) { rawOff = pos + l; rawLen = nl; } }
         }
-        const u32 e = decode_one_column(arena, ix, nOps, base, pos, pos + l, rawOff, rawLen, pb, nPreds, rows);
-        if (e && !kerr) kerr = e;
+        if (!(nOps == 1 && decode_single(ix, pos, l, base, rawOff, rawLen, pb, nPreds))) {
+          const u32 e = decode_one_column(arena, ix, nOps, base, pos, pos + l, rawOff, rawLen, pb, nPreds, rows);
+          if (e && !kerr) kerr = e;
+        }
         seen |= 1u << ix;
       }
       pos += l;

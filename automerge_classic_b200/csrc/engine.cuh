@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <array>
 #include <functional>
+#include <initializer_list>
 #include <map>
 #include <memory>
 #include <thread>
@@ -96,7 +97,7 @@ class Engine {
   DBuf<u32> isRow, rowSlot, rowOfOp; DocBufs work, sorted;
   DBuf<u64> idKeys; DBuf<u32> idVals; DBuf<u32> objRow, elemRow, parentRow, keySlot, repList, repCount, listPos, perm, pos;
   DBuf<KeySlot> keySlots; DBuf<u64> sortKeys; DBuf<u32> sortVals; SortTemp sortTmp; ScanTemp scanTmp;
-  DBuf<u32> eNext, eNext2, eRank, eRank2, insItems;
+  DBuf<u32> eNext, eNext2, eRank, eRank2, insItems, itemIdx, objSlot;
   DBuf<u64> pairKey, pairSucc, newSucc; DBuf<u32> pairIdx, pairPos, pairTime, succCnt, newSuccCnt, newSuccOff, firstNewSucc;
   DBuf<u32> elemPos, keyRankAt, objPos, head, headScan, groupOf, groupRows, groupVisible, groupFirst, groupTouched, groupLinked, objTouchedAt, linkDone, emit, marker, slot;
   DBuf<u32> isObjHead, objIdx, objStart, elemVis, elemVisScan, rowEmit, firstVis, state, nItems, itemBase, qIndex, zero, wzero, zscan, wscan, editObjKey;
@@ -113,6 +114,8 @@ class Engine {
     CUDA_CHECK(cudaSetDevice(device));
     cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device)); ctx.numSMs = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.side, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evFork, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evJoin, cudaEventDisableTiming));
     ShaConsts k; memcpy(k.k, SHA_K, sizeof(SHA_K)); CUDA_CHECK(cudaMemcpyToSymbol(c_sha, &k, sizeof(k)));
 #endif
     errWord.ensure(ctx, 4); flagWord.ensure(ctx, 16);
@@ -122,6 +125,9 @@ class Engine {
   ~Engine() {
 #ifndef AMG_EMU
     if (ctx.stream) cudaStreamDestroy(ctx.stream);
+    if (ctx.side) cudaStreamDestroy(ctx.side);
+    if (ctx.evFork) cudaEventDestroy(ctx.evFork);
+    if (ctx.evJoin) cudaEventDestroy(ctx.evJoin);
 #endif
   }
 
@@ -141,7 +147,19 @@ class Engine {
   }
 
   // ---------------------------------------------------------------- error plumbing
-  u64 fetchErr() { u64 w = 0; d2h(ctx, &w, errWord.p, 8); sync(ctx); return w; }
+  // Every small device -> host read also brings the error word along (same sync); a later error check is free when no
+  // kernel was launched in between.
+  u64 errSnapshot = 0; uint64_t errSnapLaunches = ~0ull;
+  u64* pinnedWords(size_t n) { hostWord.ensure(n + 1); return hostWord.p; }
+  void readWords(std::initializer_list<std::pair<const void*, size_t>> srcs, void* const* dsts) {   // one sync for all of them + the error word
+    u64* w = pinnedWords(srcs.size() + 1); size_t k = 0;
+    for (auto& s : srcs) { w[k] = 0; d2h(ctx, &w[k], s.first, s.second); k++; }
+    d2h(ctx, &w[k], errWord.p, 8); const uint64_t launchesNow = ctx.launches;
+    sync(ctx);
+    k = 0; for (auto& s : srcs) { memcpy(dsts[k], &w[k], s.second); k++; }
+    errSnapshot = w[k]; errSnapLaunches = launchesNow;
+  }
+  u64 fetchErr() { if (errSnapLaunches != ctx.launches) { void* none[1] = {nullptr}; readWords({}, none); } return errSnapshot; }
   std::string opIdText(u64 id) const {
     const u32 a = id_actor(id);
     return std::to_string(id_ctr(id)) + "@" + (a < actorIds.size() ? hex_of((const u8*)actorIds[a].data(), actorIds[a].size()) : std::string("?"));
@@ -183,7 +201,9 @@ class Engine {
   void checkErr(const std::vector<std::string>& actorsNow) { u64 w = fetchErr(); if (w) throwKernelError(w, actorsNow); }
 
   // ---------------------------------------------------------------- helpers
-  u32 readU32(const u32* dptr) { u32 v; d2h(ctx, &v, dptr, 4); sync(ctx); return v; }
+  HBuf<u64> hostWord;   // pinned landing slots for the small device -> host reads that size the next stage
+  u32 readU32(const u32* dptr) { u32 v = 0; void* d[1] = {&v}; readWords({{dptr, 4}}, d); return v; }
+  void readU32x2(const u32* a, const u32* b, u32* va, u32* vb) { void* d[2] = {va, vb}; readWords({{a, 4}, {b, 4}}, d); }
   void fill32(u32* p, u32 v, size_t n) { foreach(ctx, n, FillU32Kernel{p, v}); }
   // sort `perm` (row ids) by successive 64-bit fields produced by keyFn(field) ; stable LSD over fields
   void sortPairs(DBuf<u64>& keys, DBuf<u32>& vals, size_t n, int bits) { radix_sort_pairs(ctx, sortTmp, keys, vals, n, 0, bits); }

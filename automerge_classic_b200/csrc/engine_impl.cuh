@@ -138,7 +138,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   dbgMark("stage:done");
   timer.mark(); hostMark();
   // ------------------------------------------------------------ 1. hash + header parse
-  dev_memset(ctx, errWord.p, 0, 16);
+  dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull;
   hashes.ensure(ctx, (numApplied + B) * 32 + 64, numApplied * 32);
   {
     // Which changes of the bulk batch are DEFLATEd (columnar.js:742)? Those are inflated on the device, behind the batch:
@@ -148,7 +148,11 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     scan_exclusive(ctx, scanTmp, emit.p, slot.p, B);
     const size_t nd = readU32(slot.p + B);
     dbgMark("sha:deflate-scanned");
-    foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr, nd ? deflList.p : nullptr});
+    // the SHA-256 of the whole batch (ALU-bound, ~0.5 ms at 1M changes) runs on the side stream while the few
+    // DEFLATEd changes are inflated, laid out and hashed on the main one; joined before the header parse
+    side_fork(ctx);
+    struct SideJoin { Ctx& c; ~SideJoin() { side_join(c); } } sideJoin{ctx};   // also on the error paths: nothing of this call outlives it on the side stream
+    foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr, nd ? deflList.p : nullptr}, true);
     if (nd > 0) {
       foreach(ctx, B, CompactKernel{emit.p, slot.p, deflList.p});
       inflLen.ensure(ctx, nd + 1); inflOff.ensure(ctx, nd + 2); patchTriples.ensure(ctx, 2 * nd + 2);
@@ -162,6 +166,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       arena.ensure(ctx, cur + 64, extraStart);
       foreach(ctx, nd, InflateKernel{1, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, inflOff.p, (u32)extraStart, origOff, origLen, errWord.p});
       dev_memset(ctx, arena.p + cur, 0, 64);
+      side_join(ctx);
+      foreach(ctx, nd, InflatePatchKernel{deflList.p, inflLen.p, inflOff.p, (u32)extraStart, chOff.p, chLen.p});
       foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, deflList.p, nullptr});
       // host bookkeeping: which entries moved where, and the inflated bytes for the mirror
       deflIdx.resize(nd); std::vector<u32> newLen(nd), newOff(nd), oOff(nd), oLen(nd);
@@ -177,6 +183,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       dbgMark("sha:inflated");
     }
   }
+  side_join(ctx);
   timer.mark(); hostMark();
   meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
   nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
@@ -191,7 +198,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   foreach(ctx, G, HashInsertKernel{hashes.p, hashTable.p, (u64)tcap - 1});
   foreach(ctx, B, ResolveDepsKernel{arena.p, hashes.p, hashTable.p, (u64)tcap - 1, meta.p, numApplied, depBase.p, depIdx.p, primary.p});
   fill32(pass.p, 1, B);
-  for (size_t iter = 0; iter <= B + 1; iter++) {
+  for (size_t iter = 0; iter <= B + 1; iter += 2) {   // two sweeps per host round trip: the common batch settles in the first
+    foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, meta.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
     dev_memset(ctx, flagWord.p, 0, 4);
     foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, meta.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
     if (!readU32(flagWord.p)) break;
@@ -199,7 +207,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   applied.ensure(ctx, B); appRank.ensure(ctx, B + 1); isRow.ensure(ctx, B + 1);
   dev_memset(ctx, flagWord.p, 0, 8);
   foreach(ctx, B, AppliedFlagKernel{primary.p, pass.p, numApplied, applied.p, isRow.p, flagWord.p});
-  u32 stats[2]; d2h(ctx, stats, flagWord.p, 8); sync(ctx);
+  u32 stats[2]; readU32x2(flagWord.p, flagWord.p + 1, &stats[0], &stats[1]);
   const size_t numNew = stats[0]; const bool inOrder = stats[1] <= 1; batchInOrder = inOrder;
   std::vector<u8> appliedH; std::vector<u32> primaryH, appRankH;
   if (inOrder) scan_exclusive(ctx, scanTmp, isRow.p, appRank.p, B);
@@ -228,16 +236,15 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   std::vector<std::array<u8, 32>> headsNow = heads; std::vector<u32> headIdxNow;
   if (numNew > 0) {
     // ---------------------------------------------------------- 3. actors
-    authorSlot.ensure(ctx, B); newSlots.ensure(ctx, B + 1);
+    authorSlot.ensure(ctx, B); newSlots.ensure(ctx, B + 1); u32 fresh = 0;
     while (true) {   // grow the table until the distinct authors fit at load factor <= 1/2
       dev_memset(ctx, flagWord.p, 0, 8);
       foreach(ctx, B, ActorInternKernel{arena.p, meta.p, applied.p, appRank.p, actorSlots.p, (u64)actorCap - 1, authorSlot.p});
       foreach(ctx, B, NewActorKernel{meta.p, applied.p, authorSlot.p, actorSlots.p, newSlots.p, flagWord.p});
-      const u32 fresh = readU32(flagWord.p);
+      fresh = readU32(flagWord.p);
       if ((actorIds.size() + fresh) * 2 <= actorCap) break;
       actorCap *= 4; actorSlots.ensure(ctx, actorCap); rebuildActorTable();
     }
-    const u32 fresh = readU32(flagWord.p);
     if (fresh > 0) {
     dbgMark("actors:interned");
       std::vector<u32> slotsH(fresh); d2h(ctx, slotsH.data(), newSlots.p, fresh * 4); sync(ctx);
@@ -305,7 +312,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     opBase.ensure(ctx, B + 1); predBase.ensure(ctx, B + 1); timeBase.ensure(ctx, B + 1);
     foreach(ctx, B, MaskedCountKernel{nOps.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, opBase.p, B);
     foreach(ctx, B, MaskedCountKernel{nPreds.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, predBase.p, B);
-    M = readU32(opBase.p + B); P = readU32(predBase.p + B);
+    { u32 m32 = 0, p32 = 0; readU32x2(opBase.p + B, predBase.p + B, &m32, &p32); M = m32; P = p32; }
     dbgMark("decode:counts");
     if (!inOrder) {
       perm.ensure(ctx, B + 1); dev_memset(ctx, perm.p, 0, (B + 1) * 4);
@@ -361,7 +368,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     foreach(ctx, N, KeyInternKernel{arena.p, w, keySlots.p, (u64)kcap - 1, keySlot.p});
     dev_memset(ctx, repCount.p, 0, 16);
     foreach(ctx, N, KeyVerifyKernel{arena.p, w, keySlots.p, keySlot.p, repList.p, repCount.p, errWord.p});
-    u32 rc[2]; d2h(ctx, rc, repCount.p, 8); sync(ctx);
+    u32 rc[2]; readU32x2(repCount.p, repCount.p + 1, &rc[0], &rc[1]);
     const size_t D = rc[0]; const u32 maxKeyLen = rc[1];
     dbgMark("opset:keys-interned");
     if (D > 0) {
@@ -387,15 +394,20 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       foreach(ctx, I, SiblingKeyKernel{w, insItems.p, parentRow.p, objRow.p, ord, ordBits, sortKeys.p, errWord.p});
       d2d(ctx, sortVals.p, insItems.p, I * 4);
       sortPairs(sortKeys, sortVals, I, ordBits + parentBits);
-      const size_t S = 4 * N; eNext.ensure(ctx, S); eNext2.ensure(ctx, S); eRank.ensure(ctx, S); eRank2.ensure(ctx, S);
+      checkErr(actorsNow);
+      itemIdx.ensure(ctx, N + 1); objSlot.ensure(ctx, N + 2);
+      foreach(ctx, I, ItemIndexKernel{sortVals.p, itemIdx.p});
+      foreach(ctx, N, ListObjFlagKernel{w, emit.p}); scan_exclusive(ctx, scanTmp, emit.p, objSlot.p, N);
+      const size_t Lo = readU32(objSlot.p + N);
+      const size_t S = 2 * I + 2 * Lo; eNext.ensure(ctx, S + 1); eNext2.ensure(ctx, S + 1); eRank.ensure(ctx, S + 1); eRank2.ensure(ctx, S + 1);
       foreach(ctx, S, EulerInitKernel{eNext.p, eRank.p});
-      foreach(ctx, I, EulerLinkKernel{sortKeys.p, sortVals.p, ordBits, eNext.p, eRank.p, I});
+      foreach(ctx, I, EulerLinkKernel{sortKeys.p, ordBits, itemIdx.p, objSlot.p, eNext.p, eRank.p, I});
       const int rounds = bits_for(S);
       for (int k = 0; k < rounds; k++) {
         foreach(ctx, S, ListRankKernel{eNext.p, eRank.p, eNext2.p, eRank2.p});
         std::swap(eNext.p, eNext2.p); std::swap(eNext.cap, eNext2.cap); std::swap(eRank.p, eRank2.p); std::swap(eRank.cap, eRank2.cap);
       }
-      foreach(ctx, N, ListPosKernel{eRank.p, elemRow.p, objRow.p, w, listPos.p});
+      foreach(ctx, N, ListPosKernel{eRank.p, elemRow.p, objRow.p, itemIdx.p, objSlot.p, (u32)I, listPos.p});
     } else dev_memset(ctx, listPos.p, 0, (N + 1) * 4);
     checkErr(actorsNow);
     dbgMark("opset:list-ranked");
@@ -538,7 +550,11 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   head.ensure(ctx, N + 1); headScan.ensure(ctx, N + 2); groupOf.ensure(ctx, N + 1);
   foreach(ctx, N, GroupHeadKernel{arena.p, d, head.p});
   scan_exclusive(ctx, scanTmp, head.p, headScan.p, N);
-  const size_t numGroups = readU32(headScan.p + N);
+  isObjHead.ensure(ctx, N + 1); objIdx.ensure(ctx, N + 2);
+  foreach(ctx, N, ObjHeadKernel{d, isObjHead.p});
+  scan_exclusive(ctx, scanTmp, isObjHead.p, objIdx.p, N);
+  u32 numGroups32 = 0, numObjs32 = 0; readU32x2(headScan.p + N, objIdx.p + N, &numGroups32, &numObjs32);
+  const size_t numGroups = numGroups32, numObjs = numObjs32;
   groupRows.ensure(ctx, numGroups + 1); groupVisible.ensure(ctx, numGroups + 1); groupFirst.ensure(ctx, numGroups + 1); groupTouched.ensure(ctx, numGroups + 1);
   DBuf<u32>& groupLinkedB = linkDone;   // linkDone doubles as per-group linked flags storage below (separate buffers)
   (void)groupLinkedB;
@@ -546,10 +562,6 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   groupHasChild.ensure(ctx, numGroups + 1); dev_memset(ctx, groupHasChild.p, 0, (numGroups + 1) * 4);
   foreach(ctx, N, GroupStatsKernel{headScan.p, head.p, succCnt.p, d, groupOf.p, groupRows.p, groupVisible.p, groupFirst.p, errWord.p, 0, groupHasChild.p});
   // objects in document order
-  isObjHead.ensure(ctx, N + 1); objIdx.ensure(ctx, N + 2); 
-  foreach(ctx, N, ObjHeadKernel{d, isObjHead.p});
-  scan_exclusive(ctx, scanTmp, isObjHead.p, objIdx.p, N);
-  const size_t numObjs = readU32(objIdx.p + N);
   objStart.ensure(ctx, numObjs + 2);
   foreach(ctx, N, ObjStartKernel{isObjHead.p, objIdx.p, objStart.p, N});
   { const u32 nn = (u32)N; h2d(ctx, objStart.p + numObjs, &nn, 4); }
@@ -558,7 +570,7 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   dev_memset(ctx, groupLinked.p, 0, (numGroups + 1) * 4);
   Ord ordNow{actorRank.p, bits_for(actorsNow.size() > 1 ? actorsNow.size() - 1 : 1)};
   ListCtx lctx{d, succCnt.p, newSuccCnt.p, firstNewSucc.p, groupOf.p, groupFirst.p, groupRows.p};
-  MapGroupCtx mg{arena.p, ops ? *ops : OpRows{}, opAt.p, numOps};
+  MapGroupCtx mg{arena.p, ops ? *ops : OpRows{}, opAt.p, numOps, pass.p};
   bool anyListLink = false;
   auto listGroups = [&](int pass) {
     return ListGroupKernel{pass, mg, opGroupHead.p, *idt, rowOfOpD, posD, lctx, gCount.p, gElem.p, gT1.p, gQOrd.p, nQ.p, elemHasRecs.p,
@@ -580,12 +592,15 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
     objTouchedAt.ensure(ctx, N + 1); linkDone.ensure(ctx, N + 1);
     dev_memset(ctx, objTouchedAt.p, 0xff, (N + 1) * 4); dev_memset(ctx, linkDone.p, 0xff, (N + 1) * 4); dev_memset(ctx, flagWord.p, 0, 16);
     foreach(ctx, N, TouchKernel{d, groupOf.p, firstNewSucc.p, groupTouched.p, objTouchedAt.p, objPos.p, flagWord.p + 2});
-    for (int iter = 0; iter < 1000; iter++) {
+    u32 linkChanged = 1, anyLink32 = 0;
+    for (int iter = 0; iter < 1000 && linkChanged; iter++) {   // three sweeps per host round trip (object nesting is shallow)
+      LinkKernel lk{d, groupOf.p, groupHasChild.p, groupFirst.p, objPos.p, groupLinked.p, objTouchedAt.p, flagWord.p + 2, linkDone.p, flagWord.p, elemHasRecs.p, listLinkTime.p, flagWord.p + 3};
+      foreach(ctx, N, lk); foreach(ctx, N, lk);
       dev_memset(ctx, flagWord.p, 0, 4);
-      foreach(ctx, N, LinkKernel{d, groupOf.p, groupHasChild.p, groupFirst.p, objPos.p, groupLinked.p, objTouchedAt.p, flagWord.p + 2, linkDone.p, flagWord.p, elemHasRecs.p, listLinkTime.p, flagWord.p + 3});
-      if (!readU32(flagWord.p)) break;
+      foreach(ctx, N, lk);
+      readU32x2(flagWord.p, flagWord.p + 3, &linkChanged, &anyLink32);
     }
-    anyListLink = readU32(flagWord.p + 3) != 0;
+    anyListLink = anyLink32 != 0;
   }
   // ---- map props
   DBuf<u32>& groupEmitted = elemVis;   // scratch reuse (list edits re-initialise it later)
@@ -691,7 +706,7 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
 }
 
 inline void Engine::getPatch(PatchOut& out) {
-  dev_memset(ctx, errWord.p, 0, 8);
+  dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull;
   succCnt.ensure(ctx, numRows + 2);
   foreach(ctx, numRows, SuccCntFromOffKernel{succOff.p, succCnt.p});
   buildPatch(doc.view(), numRows, true, nullptr, 0, nullptr, nullptr, nullptr, actorIds, out, succOff.p, succ.p);
@@ -743,7 +758,7 @@ inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* 
   }
   DBuf<u8> ar; ar.ensure(ctx, staged.size() + 64); h2d(ctx, ar.p, staged.data(), staged.size()); dev_memset(ctx, ar.p + staged.size(), 0, 64);
   chOff.ensure(ctx, n); chLen.ensure(ctx, n); h2d(ctx, chOff.p, off.data(), n * 4); h2d(ctx, chLen.p, len.data(), n * 4);
-  dev_memset(ctx, errWord.p, 0, 8); hashTmp.ensure(ctx, n * 32 + 64);
+  dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull; hashTmp.ensure(ctx, n * 32 + 64);
   foreach(ctx, n, ShaKernel{ar.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
   meta.ensure(ctx, n); colOff.ensure(ctx, (size_t)NCOLS * n); colLen.ensure(ctx, (size_t)NCOLS * n);
   nOps.ensure(ctx, n + 1); nPreds.ensure(ctx, n + 1); nDeps.ensure(ctx, n + 1); nActors.ensure(ctx, n + 1);
@@ -811,7 +826,7 @@ inline void Engine::saveDocument(std::string& result) {
   std::vector<Col> changeCols, opCols;
   auto add = [&](std::vector<Col>& cols, u32 id, size_t len) { cols.push_back({id, enc.outLen - len, len}); };
   const size_t C = numApplied, N = numRows, S = numSucc, L = numLoaded, K = C - L;   // K changes have their bytes in the arena
-  dev_memset(ctx, errWord.p, 0, 16);
+  dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull;
   saveVals.ensure(ctx, std::max(std::max(C, N), S) + 2);
   // ---- change metadata (new.js:1680-1692 appendChange); the first L rows come from the loaded document's own columns
   if (C > 0) {
@@ -985,7 +1000,7 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   const size_t cur = hostArena.size();
   if (cur + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
   arena.ensure(ctx, cur + 64); h2d(ctx, arena.p, hostArena.data(), cur); dev_memset(ctx, arena.p + cur, 0, 64);
-  dev_memset(ctx, errWord.p, 0, 16); dev_memset(ctx, flagWord.p, 0, 16);
+  dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull; dev_memset(ctx, flagWord.p, 0, 16);
   foreach(ctx, 1, DocCountKernel{arena.p, dc, flagWord.p, errWord.p});
   u32 cnt[2]; d2h(ctx, cnt, flagWord.p, 8); sync(ctx); checkErr(actors);
   const size_t N = cnt[0], S = cnt[1];

@@ -133,8 +133,8 @@ HD u32 inflate_raw(const u8* src, u32 begin, u32 end, u8* dst, u32 dstCap, u32* 
 HD u32 uleb_len(u64 v) { u32 n = 1; while (v >>= 7) n++; return n; }
 
 // list[k] = batch index of the k-th DEFLATEd change (ascending). pass 0: outLen[k] = size of the inflated change
-// (8 bytes magic + checksum, chunk type 1, LEB128 length, body). pass 1: writes it at arena[extraStart + outOff[k]),
-// re-points the change there and keeps the original range (getChanges hands the original bytes back).
+// (8 bytes magic + checksum, chunk type 1, LEB128 length, body) and the original range is kept (getChanges hands the
+// original bytes back). pass 1: writes it at arena[extraStart + outOff[k]).
 struct InflateKernel {
   int pass; u8* arena; u32* chOff; u32* chLen; const u32* list; u32* outLen; const u32* outOff; u32 extraStart; u32* origOff; u32* origLen; u64* errWord;
   HD void operator()(size_t k) const {
@@ -156,8 +156,12 @@ struct InflateKernel {
     { u64 v = n; do { u8 x = v & 0x7f; v >>= 7; if (v) x |= 0x80; dst[hl++] = x; } while (v); }
     u32 produced = 0; const u32 e = inflate_raw(arena, r.pos, r.pos + (u32)clen, dst + hl, n, &produced);
     if (e || produced != n) { raise(errWord, e ? e : (u32)KE_DEFLATE, c); return; }
-    chOff[c] = extraStart + outOff[k]; chLen[c] = total;
   }
+};
+// re-points the inflated changes (separate from pass 1: the batch-wide SHA kernel may still be reading the old entries)
+struct InflatePatchKernel {
+  const u32* list; const u32* outLen; const u32* outOff; u32 extraStart; u32* chOff; u32* chLen;
+  HD void operator()(size_t k) const { if (outLen[k] == 0) return; const u32 c = list[k]; chOff[c] = extraStart + outOff[k]; chLen[c] = outLen[k]; }
 };
 struct DeflateFlagKernel {   // 1 for chunks of type 2 (columnar.js:742)
   const u8* arena; const u32* chOff; const u32* chLen; u32* flag;

@@ -11,7 +11,7 @@ struct AppliedFlagKernel {
   HD void operator()(size_t b) const {
     const bool a = primary[b] == (u32)(numApplied + b) && pass[b] < PASS_INF;
     applied[b] = a ? 1 : 0; applied32[b] = a ? 1u : 0u;
-    if (a) { atomic_add(stats, 1u); if (pass[b] > stats[1]) atomic_max(stats + 1, pass[b]); }
+    warp_agg_add(stats, a ? 1u : 0u); warp_agg_max(stats + 1, a ? pass[b] : 0u);
   }
 };
 struct PassKeyKernel { const u32* pass; const u8* applied; u64* key; u32* val; HD void operator()(size_t b) const { key[b] = applied[b] ? pass[b] : 0xffffffffu; val[b] = (u32)b; } };
@@ -20,7 +20,7 @@ struct MaskedCountKernel { const u32* v; const u8* applied; u32* out; HD void op
 // general (multi-pass) order: ops of change b start at time 1 + (ops of changes applied before b)
 struct OpsInOrderKernel { const u32* nOps; const u8* applied; const u32* appRank; u32* tmp; HD void operator()(size_t b) const { if (applied[b]) tmp[appRank[b]] = nOps[b]; } };
 struct TimeBaseKernel { const u32* scanned; const u8* applied; const u32* appRank; const u32* opBase; int inOrder; u32* timeBase; HD void operator()(size_t b) const { timeBase[b] = applied[b] ? (inOrder ? opBase[b] : scanned[appRank[b]]) + 1 : 0; } };
-struct MaxOpKernel { const ChangeMeta* meta; const u8* applied; u64* maxOp; HD void operator()(size_t b) const { if (applied[b] && meta[b].nOps > 0) { const u64 v = meta[b].startOp + meta[b].nOps - 1; if (v > *maxOp) atomic_max(maxOp, v); } } };   // read first: a monotone max rarely needs the atomic
+struct MaxOpKernel { const ChangeMeta* meta; const u8* applied; u64* maxOp; HD void operator()(size_t b) const { u64 v = 0; if (applied[b] && meta[b].nOps > 0) v = meta[b].startOp + meta[b].nOps - 1; warp_agg_max(maxOp, v); } };   // one atomic per warp
 
 // new actors: the applied change with the smallest application rank per fresh slot registers the representative bytes
 struct NewActorKernel {

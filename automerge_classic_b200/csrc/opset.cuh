@@ -150,26 +150,30 @@ struct InversePermKernel { const u32* perm; u32* inv; HD void operator()(size_t 
 struct HeadFlagKernel { const u64* a; const u64* b; u32* flag; HD void operator()(size_t j) const { flag[j] = (j == 0 || a[j] != a[j - 1] || (b && b[j] != b[j - 1])) ? 1u : 0u; } };
 
 // ---------------------------------------------------------------- RGA order: Euler tour + list ranking
-// slots per row r: 4r = element enter, 4r+1 = element exit, 4r+2 = head enter (r is the list's make op), 4r+3 = head exit
+// Compact slots: after the sibling sort the j-th insert row owns 2j (enter) and 2j+1 (exit), so a node's next sibling is
+// its memory neighbour; the k-th list object owns 2I+2k (head enter) and 2I+2k+1 (head exit).
 struct SiblingKeyKernel {   // sort key (parent code, descending opId) for insert rows; `items` lists the insert rows
   DocRows w; const u32* items; const u32* parentRow; const u32* objRow; Ord ord; int ordBits; u64* key; u64* errWord;
   HD void operator()(size_t j) const {
     const u32 r = items[j]; const u32 pr = parentRow[r];
     if (pr == ROW_NONE && objRow[r] == ROW_NONE) { raise(errWord, KE_UNSUPPORTED_OP, r); key[j] = 0; return; }   // list op on _root
+    if (pr == ROW_NONE) { const u32 a = flags_action(w.flags[objRow[r]]); if (a != ACT_MAKE_LIST && a != ACT_MAKE_TEXT) { raise(errWord, KE_UNSUPPORTED_OP, r); key[j] = 0; return; } }   // list op on a map
     const u64 parentCode = pr != ROW_NONE ? ((u64)pr << 1) : (((u64)objRow[r] << 1) | 1);   // head of the object
     const u64 maxOrd = (1ULL << ordBits) - 1;
     key[j] = (parentCode << ordBits) | (maxOrd - ord(w.id[r]));
   }
 };
+struct ListObjFlagKernel { DocRows w; u32* flag; HD void operator()(size_t r) const { const u32 a = flags_action(w.flags[r]); flag[r] = (a == ACT_MAKE_LIST || a == ACT_MAKE_TEXT) ? 1u : 0u; } };
+struct ItemIndexKernel { const u32* items; u32* itemIdx; HD void operator()(size_t j) const { itemIdx[items[j]] = (u32)j; } };
 struct EulerLinkKernel {   // after sorting siblings: set first-child and next-sibling links
-  const u64* key; const u32* items; int ordBits; u32* next /* [4N] */; u32* weight; size_t n;
+  const u64* key; int ordBits; const u32* itemIdx; const u32* objSlot; u32* next /* [2I + 2L] */; u32* weight; size_t n;
   HD void operator()(size_t j) const {
-    const u32 r = items[j]; const u64 pc = key[j] >> ordBits;
+    const u64 pc = key[j] >> ordBits;
     const bool firstOfParent = j == 0 || (key[j - 1] >> ordBits) != pc, lastOfParent = j + 1 == n || (key[j + 1] >> ordBits) != pc;
-    const u32 parentEnter = (pc & 1) ? (u32)(4 * (pc >> 1) + 2) : (u32)(4 * (pc >> 1)), parentExit = parentEnter + 1;
-    if (firstOfParent) next[parentEnter] = 4 * r;              // enter(parent) -> enter(first child)
-    next[4 * r + 1] = lastOfParent ? parentExit : 4 * items[j + 1];   // exit(r) -> enter(next sibling) | exit(parent)
-    weight[4 * r] = 1;
+    const u32 parentEnter = (pc & 1) ? (u32)(2 * n + 2 * objSlot[pc >> 1]) : 2 * itemIdx[pc >> 1], parentExit = parentEnter + 1;
+    if (firstOfParent) next[parentEnter] = (u32)(2 * j);                      // enter(parent) -> enter(first child)
+    next[2 * j + 1] = lastOfParent ? parentExit : (u32)(2 * j + 2);           // exit -> enter(next sibling) | exit(parent)
+    weight[2 * j] = 1;
   }
 };
 struct EulerInitKernel {   // default links: enter -> own exit, exit -> self (terminal until linked)
@@ -187,11 +191,11 @@ struct ListRankKernel {
 };
 // list position of every list row = number of elements before its element in its object
 struct ListPosKernel {
-  const u32* rank; const u32* elemRow; const u32* objRow; DocRows w; u32* listPos;
+  const u32* rank; const u32* elemRow; const u32* objRow; const u32* itemIdx; const u32* objSlot; u32 numItems; u32* listPos;
   HD void operator()(size_t r) const {
     const u32 e = elemRow[r];
     if (e == ROW_NONE || objRow[e] == ROW_NONE) { listPos[r] = 0; return; }
-    listPos[r] = rank[4 * (size_t)objRow[e] + 2] - rank[4 * (size_t)e];   // total(list) - suffix(enter e)
+    listPos[r] = rank[2 * (size_t)numItems + 2 * objSlot[objRow[e]]] - rank[2 * (size_t)itemIdx[e]];   // total(list) - suffix(enter e)
   }
 };
 

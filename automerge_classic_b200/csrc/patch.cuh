@@ -63,7 +63,7 @@ struct TouchKernel {   // new rows and the targets of new succ entries touch the
     if (d.time[p] == 0 && firstNewSucc[p] == 0xffffffffu) return;
     groupTouched[groupOf[p]] = 1;
     u32 t = firstNewSucc[p]; if (d.time[p] != 0 && d.time[p] < t) t = d.time[p];
-    if (objPos[p] == ROW_NONE) *rootTouched = 1; else atomic_min(&objTouchedAt[objPos[p]], t);
+    if (objPos[p] == ROW_NONE) *rootTouched = 1; else if (objTouchedAt[objPos[p]] > t) atomic_min(&objTouchedAt[objPos[p]], t);   // read first: all rows of one object meet here
   }
 };
 // setupPatches (new.js:1461-1528): a touched object links itself into its parent (the group of its make row), recursively.
@@ -109,7 +109,8 @@ HD int key_cmp_utf16(const u8* a, u32 la, const u8* b, u32 lb) {   // JS string 
 }
 struct OpAtTimeKernel { const u32* time; u32* opAt; HD void operator()(size_t i) const { opAt[time[i] - 1] = (u32)i; } };
 struct MapGroupCtx {
-  const u8* arena; OpRows ops; const u32* opAt; size_t numOps;
+  const u8* arena; OpRows ops; const u32* opAt; size_t numOps; const u32* passOf /* per batch change: pass of the causal gate */;
+  HD bool samePass(u32 i, u32 j) const { return passOf[ops.change[i]] == passOf[ops.change[j]]; }   // every pass is its own applyOps run (new.js:1822-1841)
   HD bool isMapOp(u32 i) const { return ops.keyStrLen[i] != NULL32; }
   HD bool sameKey(u32 i, u32 j) const {
     if (ops.keyStrLen[i] != ops.keyStrLen[j]) return false;
@@ -117,7 +118,7 @@ struct MapGroupCtx {
     return true;
   }
   HD bool sameRun(u32 i, u32 j) const {   // ops that one mergeDocChangeOps call may gather onto one key / list element
-    if (id_actor(ops.id[i]) != id_actor(ops.id[j]) || ((ops.flags[i] ^ ops.flags[j]) & F_INSERT) != 0 || ops.obj[i] != ops.obj[j] || isMapOp(i) != isMapOp(j)) return false;
+    if (id_actor(ops.id[i]) != id_actor(ops.id[j]) || ((ops.flags[i] ^ ops.flags[j]) & F_INSERT) != 0 || ops.obj[i] != ops.obj[j] || isMapOp(i) != isMapOp(j) || !samePass(i, j)) return false;
     if (isMapOp(i)) return sameKey(i, j);
     return (ops.flags[i] & F_INSERT) == 0 && ops.key[i] == ops.key[j];
   }
@@ -164,7 +165,7 @@ struct GroupFinalKernel {   // pass 0: finalTime[g] = latest group on key group 
     bool gathered = false;
     if (t < c.numOps) {
       const u32 nx = c.opAt[t];
-      gathered = c.isMapOp(nx) && id_actor(c.ops.id[nx]) == id_actor(c.ops.id[i0]) && ((c.ops.flags[nx] ^ c.ops.flags[i0]) & F_INSERT) == 0 && c.ops.obj[nx] == c.ops.obj[i0] &&
+      gathered = c.isMapOp(nx) && c.samePass(nx, i0) && id_actor(c.ops.id[nx]) == id_actor(c.ops.id[i0]) && ((c.ops.flags[nx] ^ c.ops.flags[i0]) & F_INSERT) == 0 && c.ops.obj[nx] == c.ops.obj[i0] &&
                  key_cmp_utf16(c.arena + c.ops.keyStrOff[i0], c.ops.keyStrLen[i0], c.arena + c.ops.keyStrOff[nx], c.ops.keyStrLen[nx]) < 0;
     }
     bound[g] = b; failed[g] = gathered ? 0u : 1u;
@@ -392,7 +393,7 @@ struct ListGroupKernel {
     if (t0 > 0 && !(c.ops.flags[i0] & F_INSERT)) {
       size_t tp = t0 - 1; while (tp > 0 && !groupHead[tp]) tp--;
       const u32 ip = c.opAt[tp];
-      if (!c.isMapOp(ip) && !(c.ops.flags[ip] & F_INSERT) && id_actor(c.ops.id[ip]) == id_actor(c.ops.id[i0]) && c.ops.obj[ip] == c.ops.obj[i0] && gElem[tp] != ROW_NONE && gElem[tp] < e &&
+      if (!c.isMapOp(ip) && !(c.ops.flags[ip] & F_INSERT) && c.samePass(ip, i0) && id_actor(c.ops.id[ip]) == id_actor(c.ops.id[i0]) && c.ops.obj[ip] == c.ops.obj[i0] && gElem[tp] != ROW_NONE && gElem[tp] < e &&
           L.visAt(gElem[tp], L.groupRows[L.groupOf[gElem[tp]]], T0 - 1)) {   // cheap tests first: the walk below can be long
         const u32 e1 = gElem[tp]; u32 p = e;
         while (p > 0 && L.d.obj[p - 1] == L.d.obj[e] && L.d.time[p - 1] >= T0) p--;      // rows that arrive later in this batch were not there yet
