@@ -303,7 +303,8 @@ HD u64 rle_sum_values(const u8* arena, u32 off, u32 end, u32 limit, u32* err) {
 struct ParseKernel {
   const u8* arena; const u32* chOff; const u32* chLen; size_t numChanges;
   ChangeMeta* meta; u32* colOff /* [NCOLS][numChanges] */; u32* colLen; u32* nOpsOut; u32* nPredsOut; u32* nDepsOut; u32* nActorsOut; u64* errWord;
-  HD void operator()(size_t c) const {
+  HD void operator()(size_t c) const { (*this)(c, this->arena); }
+  HD void operator()(size_t c, const u8* arena) const {   // `arena` may be the block's shared-memory copy (foreach_staged)
     const u32 off = chOff[c], len = chLen[c];
     ChangeMeta m; memset(&m, 0, sizeof(m)); m.off = off; m.len = len;
     nOpsOut[c] = 0; nPredsOut[c] = 0; nDepsOut[c] = 0; nActorsOut[c] = 1;
@@ -466,7 +467,7 @@ struct DecodeSmallKernel {
   // A column that holds exactly one value is either the literal record [-1, v] or the null run [0, 1]. Handles those two
   // byte patterns directly (v in one or two LEB bytes); anything else returns false and takes the general decoder,
   // which also reports the malformed cases.
-  HD bool decode_single(int ix, u32 pos, u32 l, u32 base, u32 rawOff, u32 rawLen, u32 pb, u32 nPreds) const {
+  HD bool decode_single(const u8* arena, int ix, u32 pos, u32 l, u32 base, u32 rawOff, u32 rawLen, u32 pb, u32 nPreds) const {
     const u8* p = arena + pos;
     if (ix == CX_INSERT) {
       if (l == 1 && p[0] == 1) { rows.insert[base] = 0; return true; }
@@ -500,7 +501,8 @@ struct DecodeSmallKernel {
     }
     return true;
   }
-  HD void operator()(size_t c) const {
+  HD void operator()(size_t c) const { (*this)(c, this->arena); }
+  HD void operator()(size_t c, const u8* arena) const {
     if (!applied[c]) return;
     const u32 nOps = meta[c].nOps; if (nOps == 0 || nOps > SMALL_CHANGE_OPS) return;
     const u32 base = opBase[c], pb = predBase[c], nPreds = meta[c].nPreds;
@@ -512,7 +514,7 @@ struct DecodeSmallKernel {
         if (ix == CX_VAL_LEN) {   // VALUE_RAW (0x57) directly follows VALUE_LEN (0x56) in the directory when present
           ByteReader peek = d; if (!peek.done()) { const u32 nid = (u32)peek.uleb(), nl = (u32)peek.uleb(); if (nid == 0x57) { rawOff = pos + l; rawLen = nl; } }
         }
-        if (!(nOps == 1 && decode_single(ix, pos, l, base, rawOff, rawLen, pb, nPreds))) {
+        if (!(nOps == 1 && decode_single(arena, ix, pos, l, base, rawOff, rawLen, pb, nPreds))) {
           const u32 e = decode_one_column(arena, ix, nOps, base, pos, pos + l, rawOff, rawLen, pb, nPreds, rows);
           if (e && !kerr) kerr = e;
         }

@@ -90,6 +90,7 @@ class Engine {
   std::vector<std::pair<const char*, float>> dbgMarks; std::function<void(const char*)> dbgMark = [](const char*) {};
   HBuf<u8> patchBuf;   // pinned: patch records are copied device -> host directly into their final place
   // ---- scratch (grow-only)
+  DBuf<u32> chOff0, chLen0; const u32* lastWinOff = nullptr; const u32* lastWinLen = nullptr;
   DBuf<u32> chOff, chLen, nOps, nPreds, nDeps, nActors, colOff, colLen, depBase, depIdx, primary, pass, flagWord, appRank, opBase, predBase, timeBase, amapBase, amap, authorSlot, newSlots;
   DBuf<u8> applied; DBuf<ChangeMeta> meta; DBuf<u64> errWord; DBuf<u32> hashTable;
   DBuf<u32> r_objActor, r_objCtr, r_keyActor, r_keyCtr, r_keyStrOff, r_keyStrLen, r_insert, r_action, r_valLen, r_valOff, r_predNum, r_predOff, r_predActor, r_predCtr;

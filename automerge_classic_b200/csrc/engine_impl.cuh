@@ -76,6 +76,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   const size_t arenaLen0 = arenaLen; const size_t hostLen0 = hostArena.size();
   std::vector<HostChange> batch, batchOriginal, inflOrig;   // originals of DEFLATEd changes: batchOriginal (dense, queue entries) / inflOrig (sparse, parallel to deflIdx)
   std::vector<u32> deflIdx;
+  const u32* winOff = nullptr; const u32* winLen = nullptr;
   auto originalOf = [&](size_t b) -> HostChange {
     if (!batchOriginal.empty() && batchOriginal[b].len) return batchOriginal[b];
     auto it = std::lower_bound(deflIdx.begin(), deflIdx.end(), (u32)b);
@@ -167,6 +168,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       foreach(ctx, nd, InflateKernel{1, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, inflOff.p, (u32)extraStart, origOff, origLen, errWord.p});
       dev_memset(ctx, arena.p + cur, 0, 64);
       side_join(ctx);
+      chOff0.ensure(ctx, B); chLen0.ensure(ctx, B); d2d(ctx, chOff0.p, chOff.p, B * 4); d2d(ctx, chLen0.p, chLen.p, B * 4);   // original layout: the staging window of the parse kernels
+      winOff = chOff0.p; winLen = chLen0.p;
       foreach(ctx, nd, InflatePatchKernel{deflList.p, inflLen.p, inflOff.p, (u32)extraStart, chOff.p, chLen.p});
       foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, deflList.p, nullptr});
       // host bookkeeping: which entries moved where, and the inflated bytes for the mirror
@@ -184,10 +187,12 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     }
   }
   side_join(ctx);
+  if (!winOff) { winOff = chOff.p; winLen = chLen.p; }
+  lastWinOff = winOff; lastWinLen = winLen;
   timer.mark(); hostMark();
   meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
   nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
-  foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
+  foreach_staged(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p}, arena.p, chOff.p, chLen.p, winOff, winLen);
   { u64 ew0 = 0; d2h(ctx, &ew0, errWord.p, 8); sync(ctx); if (ew0) throwKernelError(ew0, actorIds); }
   // ------------------------------------------------------------ 2. causal gate
   depBase.ensure(ctx, B + 1); scan_exclusive(ctx, scanTmp, nDeps.p, depBase.p, B);
@@ -326,7 +331,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, M + 1);
     r_predActor.ensure(ctx, P + 1); r_predCtr.ensure(ctx, P + 1);
     RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
-    foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+    foreach_staged(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p}, arena.p, chOff.p, chLen.p, winOff, winLen);
     {   // changes with more than SMALL_CHANGE_OPS ops: (column, change)-parallel expansion
       largeFlag.ensure(ctx, B + 1); largeSlot.ensure(ctx, B + 2); largeList.ensure(ctx, B + 1);
       foreach(ctx, B, LargeFlagKernel{meta.p, applied.p, largeFlag.p});
@@ -722,6 +727,7 @@ namespace amg {
 // Re-runs the decode kernels over the last applied batch (bytes resident in HBM) and times them with CUDA events.
 inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes) {
   if (lastB == 0 || iters <= 0) throw Error(AMG_ERR_RANGE, "amg_bench_decode: no batch has been applied yet");
+  const u32* winOff = lastWinOff; const u32* winLen = lastWinLen;
   const size_t B = lastB;
   hashTmp.ensure(ctx, B * 32 + 64);
   RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
@@ -731,10 +737,10 @@ inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* 
   cudaEventRecord(e[0], ctx.stream);
   for (int i = 0; i < iters; i++) foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
   cudaEventRecord(e[1], ctx.stream);
-  for (int i = 0; i < iters; i++) foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
+  for (int i = 0; i < iters; i++) foreach_staged(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p}, arena.p, chOff.p, chLen.p, winOff, winLen);
   cudaEventRecord(e[2], ctx.stream);
   for (int i = 0; i < iters; i++) {
-    foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+    foreach_staged(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p}, arena.p, chOff.p, chLen.p, winOff, winLen);
     if (lastNumLarge > 0) foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{arena.p, B, largeList.p, lastNumLarge, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
   }
   cudaEventRecord(e[3], ctx.stream);
