@@ -156,47 +156,6 @@ template <class F> __global__ void __launch_bounds__(256) k_foreach(size_t n, F 
 }
 #endif
 
-// Byte-parsing kernels: item i reads arena[off[i], off[i] + len[i]) and consecutive items are (normally) adjacent in the
-// arena. The block stages its whole byte range in shared memory with coalesced 16-byte loads and hands the functor a
-// base pointer through which the ABSOLUTE arena offsets stay valid; blocks whose items are not laid out that way, or whose
-// range does not fit, read from global memory as before. The dependent byte-by-byte LEB128 walks then wait on shared
-// memory instead of L1/L2.
-static const unsigned STAGE_BYTES = 40 * 1024;
-#ifndef AMG_EMU
-template <class F> __global__ void __launch_bounds__(256) k_foreach_staged(size_t n, F f, const uint8_t* arena, const uint32_t* off, const uint32_t* len, const uint32_t* winOff, const uint32_t* winLen) {
-  extern __shared__ uint4 stage4[];
-  for (size_t start = (size_t)blockIdx.x * 256; start < n; start += (size_t)gridDim.x * 256) {
-    const size_t last = start + 255 < n ? start + 255 : n - 1, i = start + threadIdx.x;
-    // window = where the block's items were laid out originally; items that moved (inflated changes) read global memory
-    const uint32_t lo = winOff[start] & ~15u, hi = winOff[last] + winLen[last];
-    const bool fits = hi >= lo && hi - lo <= STAGE_BYTES - 16;   // block-uniform
-    const uint8_t* base = arena;
-    if (fits) {
-      const uint4* src = reinterpret_cast<const uint4*>(arena + lo); const uint32_t vecs = (hi - lo + 15) / 16;
-      for (uint32_t k = threadIdx.x; k < vecs; k += 256) stage4[k] = src[k];
-      __syncthreads();
-      if (i < n && off[i] >= lo && off[i] + len[i] <= hi && off[i] + len[i] >= off[i]) base = reinterpret_cast<const uint8_t*>(stage4) - lo;
-    }
-    if (i < n) f(i, base);
-    __syncthreads();
-  }
-}
-#endif
-template <class F> inline void foreach_staged(Ctx& c, size_t n, const F& f, const uint8_t* arena, const uint32_t* off, const uint32_t* len, const uint32_t* winOff, const uint32_t* winLen) {
-  if (n == 0) return;
-#ifdef AMG_EMU
-  for (size_t i = 0; i < n; i++) f(i, arena);
-#else
-  static bool attrSet = false;   // per functor type
-  if (!attrSet) { CUDA_CHECK(cudaFuncSetAttribute(k_foreach_staged<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGE_BYTES)); attrSet = true; }
-  size_t want = (n + 255) / 256, maxGrid = (size_t)c.numSMs * 5;
-  int grid = (int)(want < maxGrid ? want : maxGrid);
-  k_foreach_staged<F><<<grid, 256, STAGE_BYTES, c.stream>>>(n, f, arena, off, len, winOff, winLen);
-  CUDA_CHECK(cudaGetLastError());
-#endif
-  c.launches++;
-}
-
 template <class F> inline void foreach(Ctx& c, size_t n, const F& f, bool onSide = false) {
   if (n == 0) return;
 #ifdef AMG_EMU

@@ -505,7 +505,11 @@ struct DecodeSmallKernel {
   HD void operator()(size_t c, const u8* arena) const {
     if (!applied[c]) return;
     const u32 nOps = meta[c].nOps; if (nOps == 0 || nOps > SMALL_CHANGE_OPS) return;
-    const u32 base = opBase[c], pb = predBase[c], nPreds = meta[c].nPreds;
+    decodeAt(c, arena, opBase[c], predBase[c], errWord);
+  }
+  // expands the columns of change c into rows [base, base + nOps) and preds [pb, pb + nPreds)
+  HD void decodeAt(size_t c, const u8* arena, u32 base, u32 pb, u64* errWord) const {
+    const u32 nOps = meta[c].nOps, nPreds = meta[c].nPreds;
     ByteReader d(arena, meta[c].dirOff, meta[c].dataOff); u32 pos = meta[c].dataOff; u32 seen = 0, kerr = 0;
     while (!d.done()) {
       const u32 id = (u32)d.uleb(), l = (u32)d.uleb(); const int ix = col_index_of(id);

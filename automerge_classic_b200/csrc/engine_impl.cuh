@@ -76,7 +76,23 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   const size_t arenaLen0 = arenaLen; const size_t hostLen0 = hostArena.size();
   std::vector<HostChange> batch, batchOriginal, inflOrig;   // originals of DEFLATEd changes: batchOriginal (dense, queue entries) / inflOrig (sparse, parallel to deflIdx)
   std::vector<u32> deflIdx;
-  const u32* winOff = nullptr; const u32* winLen = nullptr;
+  size_t inflNd = 0, inflExtraStart = 0, inflExtra = 0; bool inflPending = false;
+  // Host side of the device inflate: which batch entries moved where, and the inflated bytes for the host mirror. Not on
+  // the critical path: runs when the information is first needed (queue hand-over, commit); by then the mirror copy is done.
+  auto finishInflate = [&]() {
+    if (!inflPending) return;
+    inflPending = false; const size_t nd = inflNd;
+    u32* origOff = patchTriples.p; u32* origLen = patchTriples.p + nd;
+    deflIdx.resize(nd); std::vector<u32> newLen(nd), newOff(nd), oOff(nd), oLen(nd);
+    d2h(ctx, deflIdx.data(), deflList.p, nd * 4); d2h(ctx, newLen.data(), inflLen.p, nd * 4); d2h(ctx, newOff.data(), inflOff.p, nd * 4);
+    d2h(ctx, oOff.data(), origOff, nd * 4); d2h(ctx, oLen.data(), origLen, nd * 4);
+    if (mirrorThread.joinable()) mirrorThread.join();   // the mirror has to grow
+    hostArena.resize(inflExtraStart + inflExtra);
+    d2h(ctx, hostArena.data() + inflExtraStart, arena.p + inflExtraStart, inflExtra);
+    sync(ctx);
+    inflOrig.resize(nd);   // deflIdx is ascending: (batch index, original range), looked up by binary search
+    for (size_t k = 0; k < nd; k++) { const u32 bi = deflIdx[k]; inflOrig[k] = HostChange{oOff[k], oLen[k]}; batch[bi] = HostChange{(u32)inflExtraStart + newOff[k], newLen[k]}; }
+  };
   auto originalOf = [&](size_t b) -> HostChange {
     if (!batchOriginal.empty() && batchOriginal[b].len) return batchOriginal[b];
     auto it = std::lower_bound(deflIdx.begin(), deflIdx.end(), (u32)b);
@@ -88,7 +104,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   if ((u64)arenaLen0 + total + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
   Rollback rb{this, hostLen0};
   struct MirrorJoin { Engine* e; ~MirrorJoin() { if (e->mirrorThread.joinable()) e->mirrorThread.join(); } } mirrorJoin{this};   // declared after rb: joins first
-  size_t cur = arenaLen0; bool uploaded = false;
+  size_t cur = arenaLen0; bool uploaded = false; std::function<void()> startMirror;
   const size_t Bq = queue.size(); batch.resize(n + Bq);
   if (blob && n > 0 && !hostScan) {
     // bulk path: no per-change host work beyond one (offset, length) pair; DEFLATEd changes are detected on the device
@@ -104,8 +120,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       h2d(ctx, arena.p + cur, blob + base, tot);
       u8* dst = hostArena.data() + cur; const u8* src = blob + base;
       dbgMark("stage:h2d-enqueued");
-      mirrorThread = std::thread([dst, src, tot] { parallel_copy(dst, src, tot); });
-      dbgMark("stage:thread-spawned");
+      startMirror = [this, dst, src, tot] { mirrorThread = std::thread([dst, src, tot] { parallel_copy(dst, src, tot); }); };   // started once the DMA is done: the copy would compete with it for host memory bandwidth
     } else {
       const size_t kChunk = 32u << 20;   // copy into the pinned mirror and upload chunk by chunk (H2D overlaps the next host copy)
       for (size_t o = 0; o < tot; o += kChunk) {
@@ -148,6 +163,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     foreach(ctx, B, DeflateFlagKernel{arena.p, chOff.p, chLen.p, emit.p});
     scan_exclusive(ctx, scanTmp, emit.p, slot.p, B);
     const size_t nd = readU32(slot.p + B);
+    if (startMirror) { startMirror(); startMirror = nullptr; }   // the upload has completed (the read above waited for it)
     dbgMark("sha:deflate-scanned");
     // the SHA-256 of the whole batch (ALU-bound, ~0.5 ms at 1M changes) runs on the side stream while the few
     // DEFLATEd changes are inflated, laid out and hashed on the main one; joined before the header parse
@@ -168,31 +184,28 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       foreach(ctx, nd, InflateKernel{1, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, inflOff.p, (u32)extraStart, origOff, origLen, errWord.p});
       dev_memset(ctx, arena.p + cur, 0, 64);
       side_join(ctx);
-      chOff0.ensure(ctx, B); chLen0.ensure(ctx, B); d2d(ctx, chOff0.p, chOff.p, B * 4); d2d(ctx, chLen0.p, chLen.p, B * 4);   // original layout: the staging window of the parse kernels
-      winOff = chOff0.p; winLen = chLen0.p;
       foreach(ctx, nd, InflatePatchKernel{deflList.p, inflLen.p, inflOff.p, (u32)extraStart, chOff.p, chLen.p});
       foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, deflList.p, nullptr});
-      // host bookkeeping: which entries moved where, and the inflated bytes for the mirror
-      deflIdx.resize(nd); std::vector<u32> newLen(nd), newOff(nd), oOff(nd), oLen(nd);
-      d2h(ctx, deflIdx.data(), deflList.p, nd * 4); d2h(ctx, newLen.data(), inflLen.p, nd * 4); d2h(ctx, newOff.data(), inflOff.p, nd * 4);
-      d2h(ctx, oOff.data(), origOff, nd * 4); d2h(ctx, oLen.data(), origLen, nd * 4);
-      if (mirrorThread.joinable()) mirrorThread.join();   // the mirror has to grow
-      dbgMark("sha:mirror-joined");
-      hostArena.resize(cur);
-      d2h(ctx, hostArena.data() + extraStart, arena.p + extraStart, extra);
-      sync(ctx);
-      inflOrig.resize(nd);   // deflIdx is ascending: (batch index, original range), looked up by binary search
-      for (size_t k = 0; k < nd; k++) { const u32 bi = deflIdx[k]; inflOrig[k] = HostChange{oOff[k], oLen[k]}; batch[bi] = HostChange{(u32)extraStart + newOff[k], newLen[k]}; }
+      inflNd = nd; inflExtraStart = extraStart; inflExtra = extra; inflPending = true;   // host bookkeeping happens in finishInflate()
       dbgMark("sha:inflated");
     }
   }
   side_join(ctx);
-  if (!winOff) { winOff = chOff.p; winLen = chLen.p; }
-  lastWinOff = winOff; lastWinLen = winLen;
   timer.mark(); hostMark();
   meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
   nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
-  foreach_staged(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p}, arena.p, chOff.p, chLen.p, winOff, winLen);
+  // one pass over the change bytes: header parse + (speculatively, as if every change gets applied) column expansion
+  const size_t capOps = std::max<size_t>(2 * B + 1024, lastM + lastM / 4 + 1024), capPreds = std::max<size_t>(2 * B + 1024, lastP + lastP / 4 + 1024);
+  for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, capOps + 1);
+  r_predActor.ensure(ctx, capPreds + 1); r_predCtr.ensure(ctx, capPreds + 1);
+  specOpBase.ensure(ctx, B + 2); specPredBase.ensure(ctx, B + 2); tileState.ensure(ctx, (B + 255) / 256 + 1); fusedWords.ensure(ctx, 4);
+  dev_memset(ctx, tileState.p, 0, ((B + 255) / 256 + 1) * 8); dev_memset(ctx, fusedWords.p, 0, 16); dev_memset(ctx, errWord.p + 2, 0, 8);
+  {
+    RawRows raw0{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
+    parse_decode(ctx, B, FusedArgs{ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p},
+                                   DecodeSmallKernel{arena.p, meta.p, nullptr, nullptr, nullptr, raw0, errWord.p + 2},
+                                   specOpBase.p, specPredBase.p, tileState.p, fusedWords.p, errWord.p + 2, fusedWords.p + 1, (u32)capOps, (u32)capPreds});
+  }
   { u64 ew0 = 0; d2h(ctx, &ew0, errWord.p, 8); sync(ctx); if (ew0) throwKernelError(ew0, actorIds); }
   // ------------------------------------------------------------ 2. causal gate
   depBase.ensure(ctx, B + 1); scan_exclusive(ctx, scanTmp, nDeps.p, depBase.p, B);
@@ -229,6 +242,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   if (!haveHashGraph && numNew < B) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: a change depends on history that was not reconstructed after Backend.load (computeHashGraph, new.js:1887-1912, not built)");
   // the queue after this call: every batch entry whose hash is still not applied (new.js:1569-1570, 1832)
   std::vector<HostChange> newQueue, newQueueOriginal;
+  if (numNew < B) finishInflate();
   if (numNew < B) for (size_t b = 0; b < B; b++) {
     const u32 pr = primaryH[b];
     const bool hashApplied = pr < numApplied || appliedH[pr - numApplied];
@@ -315,9 +329,21 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     dbgMark("seq:checked");
     // ---------------------------------------------------------- 5. decode ops
     opBase.ensure(ctx, B + 1); predBase.ensure(ctx, B + 1); timeBase.ensure(ctx, B + 1);
-    foreach(ctx, B, MaskedCountKernel{nOps.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, opBase.p, B);
-    foreach(ctx, B, MaskedCountKernel{nPreds.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, predBase.p, B);
-    { u32 m32 = 0, p32 = 0; readU32x2(opBase.p + B, predBase.p + B, &m32, &p32); M = m32; P = p32; }
+    bool speculated = false;
+    if (numNew == B) {   // every change of the batch is applied: the rows expanded by the fused kernel are in place
+      u32 m32 = 0, p32 = 0, over = 0; u64 specErr = 0; void* dst[4] = {&m32, &p32, &over, &specErr};
+      readWords({{specOpBase.p + B, 4}, {specPredBase.p + B, 4}, {fusedWords.p + 1, 4}, {errWord.p + 2, 8}}, dst);
+      if (!over) {
+        if (specErr) throwKernelError(specErr, actorsNow);
+        M = m32; P = p32; speculated = true;
+        std::swap(opBase.p, specOpBase.p); std::swap(opBase.cap, specOpBase.cap); std::swap(predBase.p, specPredBase.p); std::swap(predBase.cap, specPredBase.cap);
+      }
+    }
+    if (!speculated) {
+      foreach(ctx, B, MaskedCountKernel{nOps.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, opBase.p, B);
+      foreach(ctx, B, MaskedCountKernel{nPreds.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, predBase.p, B);
+      u32 m32 = 0, p32 = 0; readU32x2(opBase.p + B, predBase.p + B, &m32, &p32); M = m32; P = p32;
+    }
     dbgMark("decode:counts");
     if (!inOrder) {
       perm.ensure(ctx, B + 1); dev_memset(ctx, perm.p, 0, (B + 1) * 4);
@@ -331,7 +357,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, M + 1);
     r_predActor.ensure(ctx, P + 1); r_predCtr.ensure(ctx, P + 1);
     RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
-    foreach_staged(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p}, arena.p, chOff.p, chLen.p, winOff, winLen);
+    if (!speculated) foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
     {   // changes with more than SMALL_CHANGE_OPS ops: (column, change)-parallel expansion
       largeFlag.ensure(ctx, B + 1); largeSlot.ensure(ctx, B + 2); largeList.ensure(ctx, B + 1);
       foreach(ctx, B, LargeFlagKernel{meta.p, applied.p, largeFlag.p});
@@ -495,6 +521,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   // ------------------------------------------------------------ 8. commit (nothing above mutated persistent state)
   sync(ctx);
   dbgMark("commit:synced");
+  finishInflate();
   if (numNew > 0) {
     if (!(inOrder && numNew == B)) {   // hashes of applied changes must be contiguous in application order
       DBuf<u8>& tmp = hashTmp; tmp.ensure(ctx, numNew * 32 + 64);
@@ -725,31 +752,40 @@ inline void Engine::getPatch(PatchOut& out) {
 namespace amg {
 
 // Re-runs the decode kernels over the last applied batch (bytes resident in HBM) and times them with CUDA events.
-inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes) {
+inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes, float* msFused) {
   if (lastB == 0 || iters <= 0) throw Error(AMG_ERR_RANGE, "amg_bench_decode: no batch has been applied yet");
-  const u32* winOff = lastWinOff; const u32* winLen = lastWinLen;
   const size_t B = lastB;
   hashTmp.ensure(ctx, B * 32 + 64);
   RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
   *algoBytes = (u64)lastBytes + 48ull * lastM + 8ull * lastP + 96ull * B;
 #ifndef AMG_EMU
-  cudaEvent_t e[4]; for (auto& x : e) cudaEventCreate(&x);
+  cudaEvent_t e[5]; for (auto& x : e) cudaEventCreate(&x);
   cudaEventRecord(e[0], ctx.stream);
   for (int i = 0; i < iters; i++) foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
   cudaEventRecord(e[1], ctx.stream);
-  for (int i = 0; i < iters; i++) foreach_staged(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p}, arena.p, chOff.p, chLen.p, winOff, winLen);
+  for (int i = 0; i < iters; i++) foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
   cudaEventRecord(e[2], ctx.stream);
   for (int i = 0; i < iters; i++) {
-    foreach_staged(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p}, arena.p, chOff.p, chLen.p, winOff, winLen);
+    foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
     if (lastNumLarge > 0) foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{arena.p, B, largeList.p, lastNumLarge, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
   }
   cudaEventRecord(e[3], ctx.stream);
-  CUDA_CHECK(cudaEventSynchronize(e[3]));
-  float a, b, c; cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[2], e[3]);
-  *msSha = a / iters; *msParse = b / iters; *msDec = c / iters;
+  {   // the single-pass kernel the pipeline actually runs (parse + expansion fused)
+    const size_t capOps = std::max<size_t>(2 * B + 1024, lastM + lastM / 4 + 1024), capPreds = std::max<size_t>(2 * B + 1024, lastP + lastP / 4 + 1024);
+    for (int i = 0; i < iters; i++) {
+      dev_memset(ctx, tileState.p, 0, ((B + 255) / 256 + 1) * 8); dev_memset(ctx, fusedWords.p, 0, 16);
+      parse_decode(ctx, B, FusedArgs{ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p},
+                                     DecodeSmallKernel{arena.p, meta.p, nullptr, nullptr, nullptr, raw, errWord.p + 2},
+                                     specOpBase.p, specPredBase.p, tileState.p, fusedWords.p, errWord.p + 2, fusedWords.p + 1, (u32)capOps, (u32)capPreds});
+    }
+  }
+  cudaEventRecord(e[4], ctx.stream);
+  CUDA_CHECK(cudaEventSynchronize(e[4]));
+  float a, b, c, d; cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[2], e[3]); cudaEventElapsedTime(&d, e[3], e[4]);
+  *msSha = a / iters; *msParse = b / iters; *msDec = c / iters; if (msFused) *msFused = d / iters;
   for (auto& x : e) cudaEventDestroy(x);
 #else
-  *msSha = *msParse = *msDec = 0;
+  *msSha = *msParse = *msDec = 0; if (msFused) *msFused = 0;
 #endif
 }
 
