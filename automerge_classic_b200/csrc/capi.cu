@@ -246,7 +246,4 @@ int amg_debug_decode(amg_backend* b, const uint8_t* blob, const uint64_t* offset
 int amg_bench_decode(amg_backend* b, int iters, float* ms_sha, float* ms_parse, float* ms_decode, uint64_t* algo_bytes, amg_error* err) {
   AMG_GUARD(u64 bytes = 0; b->eng.benchDecode(iters, ms_sha, ms_parse, ms_decode, &bytes); *algo_bytes = bytes; return 0;)
 }
-int amg_bench_decode_fused(amg_backend* b, int iters, float* ms_fused, uint64_t* algo_bytes, amg_error* err) {
-  AMG_GUARD(u64 bytes = 0; float a = 0, p = 0, d = 0; b->eng.benchDecode(iters, &a, &p, &d, &bytes, ms_fused); *algo_bytes = bytes; return 0;)
-}
 }  // extern "C"

@@ -92,6 +92,14 @@ inline void d2h(Ctx& c, void* dst, const void* src, size_t bytes) {
   CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
 #endif
 }
+inline void d2h_side(Ctx& c, void* dst, const void* src, size_t bytes) {   // on the side stream (after side_fork): overlaps later kernels of the main one
+  if (!bytes) return;
+#ifdef AMG_EMU
+  memcpy(dst, src, bytes);
+#else
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.side));
+#endif
+}
 inline void d2d(Ctx& c, void* dst, const void* src, size_t bytes) {
   if (!bytes) return;
 #ifdef AMG_EMU
@@ -150,8 +158,10 @@ template <class T> struct HBuf {
 };
 
 // ---------------------------------------------------------------- kernel launch
+// minimum resident CTAs per SM a functor asks for (caps its registers): latency-bound byte parsers want more warps in flight
+template <class F> struct LaunchTraits { static const int minBlocks = 1; };
 #ifndef AMG_EMU
-template <class F> __global__ void __launch_bounds__(256) k_foreach(size_t n, F f) {
+template <class F> __global__ void __launch_bounds__(256, LaunchTraits<F>::minBlocks) k_foreach(size_t n, F f) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) f(i);
 }
 #endif

@@ -547,6 +547,11 @@ struct DecodeColumnKernel {
     if (e) raise(errWord, e, c);
   }
 };
+#ifndef AMG_PARSE_MINBLOCKS
+#define AMG_PARSE_MINBLOCKS 6
+#endif
+template <> struct LaunchTraits<ParseKernel> { static const int minBlocks = AMG_PARSE_MINBLOCKS; };
+template <> struct LaunchTraits<DecodeSmallKernel> { static const int minBlocks = AMG_PARSE_MINBLOCKS; };
 struct LargeFlagKernel { const ChangeMeta* meta; const u8* applied; u32* flag; HD void operator()(size_t c) const { flag[c] = (applied[c] && meta[c].nOps > SMALL_CHANGE_OPS) ? 1u : 0u; } };
 
 }  // namespace amg

@@ -20,7 +20,6 @@
 #include "patch.cuh"
 #include "inflate.cuh"
 #include "encode.cuh"
-#include "fused.cuh"
 #include "prims.cuh"
 
 namespace amg {
@@ -91,7 +90,6 @@ class Engine {
   std::vector<std::pair<const char*, float>> dbgMarks; std::function<void(const char*)> dbgMark = [](const char*) {};
   HBuf<u8> patchBuf;   // pinned: patch records are copied device -> host directly into their final place
   // ---- scratch (grow-only)
-  DBuf<u32> specOpBase, specPredBase, fusedWords; DBuf<u64> tileState;
   DBuf<u32> chOff, chLen, nOps, nPreds, nDeps, nActors, colOff, colLen, depBase, depIdx, primary, pass, flagWord, appRank, opBase, predBase, timeBase, amapBase, amap, authorSlot, newSlots;
   DBuf<u8> applied; DBuf<ChangeMeta> meta; DBuf<u64> errWord; DBuf<u32> hashTable;
   DBuf<u32> r_objActor, r_objCtr, r_keyActor, r_keyCtr, r_keyStrOff, r_keyStrLen, r_insert, r_action, r_valLen, r_valOff, r_predNum, r_predOff, r_predActor, r_predCtr;
@@ -247,7 +245,7 @@ class Engine {
   void reset();
   void loadDocument(const u8* buf, size_t len);
   bool haveHashGraph = true;   // false after Backend.load: change history (hashes, bytes) is not reconstructed (new.js:1887-1912)
-  void benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes, float* msFused = nullptr);
+  void benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes);
   void decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* hashesOut, u32* nOpsOut, u32** rowsOut, size_t* totalOps);
   size_t lastB = 0, lastM = 0, lastP = 0, lastBytes = 0;
 };

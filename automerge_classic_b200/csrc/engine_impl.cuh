@@ -71,6 +71,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   auto hostMark = [&]() { if (hmark < 24) lastPhaseMs[hmark++] = hclk.ms(); };
   curTimer = &timer; curHostMark = hostMark;
   dbgMarks.clear(); dbgMark = [this, &hclk](const char* l) { dbgMarks.emplace_back(l, hclk.ms()); };
+  struct SideJoinAll { Ctx& c; ~SideJoinAll() { side_join(c); } } sideJoinAll{ctx};   // whatever this call put on the side stream is ordered before the next call
   struct ClearTimer { Engine* e; ~ClearTimer() { e->curTimer = nullptr; e->curHostMark = nullptr; e->dbgMark = [](const char*) {}; } } clearTimer{this};
   // ------------------------------------------------------------ 0. stage the batch in the arena (pinned host mirror + device)
   const size_t arenaLen0 = arenaLen; const size_t hostLen0 = hostArena.size();
@@ -194,18 +195,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   timer.mark(); hostMark();
   meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
   nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
-  // one pass over the change bytes: header parse + (speculatively, as if every change gets applied) column expansion
-  const size_t capOps = std::max<size_t>(2 * B + 1024, lastM + lastM / 4 + 1024), capPreds = std::max<size_t>(2 * B + 1024, lastP + lastP / 4 + 1024);
-  for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, capOps + 1);
-  r_predActor.ensure(ctx, capPreds + 1); r_predCtr.ensure(ctx, capPreds + 1);
-  specOpBase.ensure(ctx, B + 2); specPredBase.ensure(ctx, B + 2); tileState.ensure(ctx, (B + 255) / 256 + 1); fusedWords.ensure(ctx, 4);
-  dev_memset(ctx, tileState.p, 0, ((B + 255) / 256 + 1) * 8); dev_memset(ctx, fusedWords.p, 0, 16); dev_memset(ctx, errWord.p + 2, 0, 8);
-  {
-    RawRows raw0{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
-    parse_decode(ctx, B, FusedArgs{ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p},
-                                   DecodeSmallKernel{arena.p, meta.p, nullptr, nullptr, nullptr, raw0, errWord.p + 2},
-                                   specOpBase.p, specPredBase.p, tileState.p, fusedWords.p, errWord.p + 2, fusedWords.p + 1, (u32)capOps, (u32)capPreds});
-  }
+  foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
   { u64 ew0 = 0; d2h(ctx, &ew0, errWord.p, 8); sync(ctx); if (ew0) throwKernelError(ew0, actorIds); }
   // ------------------------------------------------------------ 2. causal gate
   depBase.ensure(ctx, B + 1); scan_exclusive(ctx, scanTmp, nDeps.p, depBase.p, B);
@@ -329,21 +319,9 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     dbgMark("seq:checked");
     // ---------------------------------------------------------- 5. decode ops
     opBase.ensure(ctx, B + 1); predBase.ensure(ctx, B + 1); timeBase.ensure(ctx, B + 1);
-    bool speculated = false;
-    if (numNew == B) {   // every change of the batch is applied: the rows expanded by the fused kernel are in place
-      u32 m32 = 0, p32 = 0, over = 0; u64 specErr = 0; void* dst[4] = {&m32, &p32, &over, &specErr};
-      readWords({{specOpBase.p + B, 4}, {specPredBase.p + B, 4}, {fusedWords.p + 1, 4}, {errWord.p + 2, 8}}, dst);
-      if (!over) {
-        if (specErr) throwKernelError(specErr, actorsNow);
-        M = m32; P = p32; speculated = true;
-        std::swap(opBase.p, specOpBase.p); std::swap(opBase.cap, specOpBase.cap); std::swap(predBase.p, specPredBase.p); std::swap(predBase.cap, specPredBase.cap);
-      }
-    }
-    if (!speculated) {
-      foreach(ctx, B, MaskedCountKernel{nOps.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, opBase.p, B);
-      foreach(ctx, B, MaskedCountKernel{nPreds.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, predBase.p, B);
-      u32 m32 = 0, p32 = 0; readU32x2(opBase.p + B, predBase.p + B, &m32, &p32); M = m32; P = p32;
-    }
+    foreach(ctx, B, MaskedCountKernel{nOps.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, opBase.p, B);
+    foreach(ctx, B, MaskedCountKernel{nPreds.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, predBase.p, B);
+    { u32 m32 = 0, p32 = 0; readU32x2(opBase.p + B, predBase.p + B, &m32, &p32); M = m32; P = p32; }
     dbgMark("decode:counts");
     if (!inOrder) {
       perm.ensure(ctx, B + 1); dev_memset(ctx, perm.p, 0, (B + 1) * 4);
@@ -357,7 +335,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, M + 1);
     r_predActor.ensure(ctx, P + 1); r_predCtr.ensure(ctx, P + 1);
     RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
-    if (!speculated) foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+    foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
     {   // changes with more than SMALL_CHANGE_OPS ops: (column, change)-parallel expansion
       largeFlag.ensure(ctx, B + 1); largeSlot.ensure(ctx, B + 2); largeList.ensure(ctx, B + 1);
       foreach(ctx, B, LargeFlagKernel{meta.p, applied.p, largeFlag.p});
@@ -553,7 +531,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     dbgMark("commit:actors-rebuilt");
   }
   arenaLen = cur; queue = newQueue; queueOriginal = newQueueOriginal; rb.armed = false;
-  sync(ctx);
+  side_join(ctx); sync(ctx);
   timer.mark(); hostMark();
   fillPatchHeader(out);
   if (isLocal && n == 1) {   // new.js:1874-1877
@@ -732,16 +710,19 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   out.numProps = numProps; out.numEdits = numEdits;
   out.propsOff = 18 * 8; out.editsOff = out.propsOff + numProps * sizeof(PropRec); out.elemOff = out.editsOff + numEdits * sizeof(EditRec); out.bigEnd = out.elemOff + numEdits * 8;
   patchBuf.ensure(out.bigEnd + 4096);
-  d2h(ctx, patchBuf.p + out.propsOff, propOut.p, numProps * sizeof(PropRec));
-  if (numEdits > 0) { d2h(ctx, patchBuf.p + out.editsOff, editOut.p, numEdits * sizeof(EditRec)); d2h(ctx, patchBuf.p + out.elemOff, editElem.p, numEdits * 8); }
-  sync(ctx);
+  // the copy-out runs on the side stream: the caller joins it before reading the patch, later kernels overlap it
+  side_fork(ctx);
+  d2h_side(ctx, patchBuf.p + out.propsOff, propOut.p, numProps * sizeof(PropRec));
+  if (numEdits > 0) { d2h_side(ctx, patchBuf.p + out.editsOff, editOut.p, numEdits * sizeof(EditRec)); d2h_side(ctx, patchBuf.p + out.elemOff, editElem.p, numEdits * 8); }
 }
 
 inline void Engine::getPatch(PatchOut& out) {
   dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull;
   succCnt.ensure(ctx, numRows + 2);
   foreach(ctx, numRows, SuccCntFromOffKernel{succOff.p, succCnt.p});
+  struct SideJoin { Ctx& c; ~SideJoin() { side_join(c); } } sideJoin{ctx};
   buildPatch(doc.view(), numRows, true, nullptr, 0, nullptr, nullptr, nullptr, actorIds, out, succOff.p, succ.p);
+  side_join(ctx); sync(ctx);
   checkErr(actorIds);
   fillPatchHeader(out);
   finishPatch(out);
@@ -752,14 +733,14 @@ inline void Engine::getPatch(PatchOut& out) {
 namespace amg {
 
 // Re-runs the decode kernels over the last applied batch (bytes resident in HBM) and times them with CUDA events.
-inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes, float* msFused) {
+inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes) {
   if (lastB == 0 || iters <= 0) throw Error(AMG_ERR_RANGE, "amg_bench_decode: no batch has been applied yet");
   const size_t B = lastB;
   hashTmp.ensure(ctx, B * 32 + 64);
   RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
   *algoBytes = (u64)lastBytes + 48ull * lastM + 8ull * lastP + 96ull * B;
 #ifndef AMG_EMU
-  cudaEvent_t e[5]; for (auto& x : e) cudaEventCreate(&x);
+  cudaEvent_t e[4]; for (auto& x : e) cudaEventCreate(&x);
   cudaEventRecord(e[0], ctx.stream);
   for (int i = 0; i < iters; i++) foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
   cudaEventRecord(e[1], ctx.stream);
@@ -770,22 +751,12 @@ inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* 
     if (lastNumLarge > 0) foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{arena.p, B, largeList.p, lastNumLarge, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
   }
   cudaEventRecord(e[3], ctx.stream);
-  {   // the single-pass kernel the pipeline actually runs (parse + expansion fused)
-    const size_t capOps = std::max<size_t>(2 * B + 1024, lastM + lastM / 4 + 1024), capPreds = std::max<size_t>(2 * B + 1024, lastP + lastP / 4 + 1024);
-    for (int i = 0; i < iters; i++) {
-      dev_memset(ctx, tileState.p, 0, ((B + 255) / 256 + 1) * 8); dev_memset(ctx, fusedWords.p, 0, 16);
-      parse_decode(ctx, B, FusedArgs{ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p},
-                                     DecodeSmallKernel{arena.p, meta.p, nullptr, nullptr, nullptr, raw, errWord.p + 2},
-                                     specOpBase.p, specPredBase.p, tileState.p, fusedWords.p, errWord.p + 2, fusedWords.p + 1, (u32)capOps, (u32)capPreds});
-    }
-  }
-  cudaEventRecord(e[4], ctx.stream);
-  CUDA_CHECK(cudaEventSynchronize(e[4]));
-  float a, b, c, d; cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[2], e[3]); cudaEventElapsedTime(&d, e[3], e[4]);
-  *msSha = a / iters; *msParse = b / iters; *msDec = c / iters; if (msFused) *msFused = d / iters;
+  CUDA_CHECK(cudaEventSynchronize(e[3]));
+  float a, b, c; cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[2], e[3]);
+  *msSha = a / iters; *msParse = b / iters; *msDec = c / iters;
   for (auto& x : e) cudaEventDestroy(x);
 #else
-  *msSha = *msParse = *msDec = 0; if (msFused) *msFused = 0;
+  *msSha = *msParse = *msDec = 0;
 #endif
 }
 

@@ -193,19 +193,12 @@ def main():
             # ALU-bound (64 rounds per 64-byte block) and is reported next to it, not folded into the HBM figure.
             t_dec = (ms_parse.value + ms_dec.value) / 1e3
             kernel_name = 'column decode = ParseKernel + DecodeSmallKernel (+ DecodeColumnKernel for large changes)'
-            ms_fused = C.c_float(0)
-            fn = getattr(L, 'amg_bench_decode_fused', None)
-            if fn is not None:      # the single-pass kernel the pipeline runs: header parse + column expansion fused
-                a2 = C.c_uint64()
-                if fn(doc.h, 20, C.byref(ms_fused), C.byref(a2), C.byref(err)) == 0 and ms_fused.value > 0:
-                    t_dec = ms_fused.value / 1e3
-                    kernel_name = 'column decode = k_parse_decode (header parse + column expansion in one pass, decoupled look-back prefix sum)'
             ach = algo.value / t_dec / 1e9
             n_blocks = (trace.blob.size + 64 * trace.n_changes) / 64.0          # ~ message blocks incl. padding
             roofline = {'bound': 'hbm', 'kernel': kernel_name,
                         'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
                         'algorithmic_bytes_per_launch': int(algo.value),
-                        'ms': {'fused_parse_decode': ms_fused.value or None, 'parse_alone': ms_parse.value, 'decode_columns_alone': ms_dec.value},
+                        'ms': {'parse': ms_parse.value, 'decode_columns': ms_dec.value},
                         'sha256_kernel': {'bound': 'alu', 'ms': ms_sha.value, 'bytes_hashed': int(trace.blob.size),
                                           'gb_per_s': trace.blob.size / (ms_sha.value / 1e3) / 1e9 if ms_sha.value else None,
                                           'blocks_per_s': n_blocks / (ms_sha.value / 1e3) if ms_sha.value else None},

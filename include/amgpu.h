@@ -120,8 +120,6 @@ size_t amg_debug_marks(amg_backend* b, char* buf, size_t cap);
 void amg_free_mem(void* p);
 /* device-only re-run of the decode kernels over the last batch (inputs resident in HBM), for the roofline measurement */
 int amg_bench_decode(amg_backend* b, int iters, float* ms_sha, float* ms_parse, float* ms_decode, uint64_t* algo_bytes, amg_error* err);
-/* the same for the single-pass parse + expand kernel the pipeline runs (ms per launch) */
-int amg_bench_decode_fused(amg_backend* b, int iters, float* ms_fused, uint64_t* algo_bytes, amg_error* err);
 
 #ifdef __cplusplus
 }
