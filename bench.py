@@ -36,6 +36,15 @@ N_OPS, N_ACTORS = 1_000_000, 10
 CPU_SAMPLE_OPS = 200_000
 
 
+def read_traffic():
+    """DRAM bytes per launch of the decode kernels from the committed ncu capture (None if the file is missing)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic_r01.json')) as fh:
+            return int(json.load(fh)['decode_total_bytes']), 'profiles/traffic_r01.json (ncu --set full, see profiles/README_r01.md)'
+    except Exception:
+        return None, None
+
+
 def read_peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
@@ -188,6 +197,7 @@ def main():
         ms_sha, ms_parse, ms_dec, algo = C.c_float(), C.c_float(), C.c_float(), C.c_uint64()
         rc = L.amg_bench_decode(doc.h, 20, C.byref(ms_sha), C.byref(ms_parse), C.byref(ms_dec), C.byref(algo), C.byref(err))
         peak, peak_src = read_peaks()
+        traffic, traffic_src = read_traffic()
         if rc == 0:
             # the HBM-bound part of the decode: header parse + column expansion. SHA-256 over the same bytes is
             # ALU-bound (64 rounds per 64-byte block) and is reported next to it, not folded into the HBM figure.
@@ -196,7 +206,7 @@ def main():
             ach = algo.value / t_dec / 1e9
             n_blocks = (trace.blob.size + 64 * trace.n_changes) / 64.0          # ~ message blocks incl. padding
             roofline = {'bound': 'hbm', 'kernel': kernel_name,
-                        'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                        'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                         'algorithmic_bytes_per_launch': int(algo.value),
                         'ms': {'parse': ms_parse.value, 'decode_columns': ms_dec.value},
                         'sha256_kernel': {'bound': 'alu', 'ms': ms_sha.value, 'bytes_hashed': int(trace.blob.size),
