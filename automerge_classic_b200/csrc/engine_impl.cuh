@@ -584,7 +584,7 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   bool anyListLink = false;
   auto listGroups = [&](int pass) {
     return ListGroupKernel{pass, mg, opGroupHead.p, *idt, rowOfOpD, posD, lctx, gCount.p, gElem.p, gT1.p, gQOrd.p, nQ.p, elemHasRecs.p,
-                           itemBase.p, objIdx.p, objStart.p, items.p, domTw.p, oldVisScan.p, gBase.p, qIndex.p, editOut.p, editElem.p, editObjKey.p, editElemPos.p, errWord.p};
+                           itemBase.p, objIdx.p, objStart.p, items.p, domTw.p, domW.p, oldVisScan.p, runHeadFlag.p, runScan.p, runStart.p, gBase.p, qIndex.p, editOut.p, editElem.p, editObjKey.p, editElemPos.p, errWord.p};
   };
   if (!wholeDoc) {
     // op groups of the batch (new.js:1085-1138), then what each list group nets out to
@@ -598,6 +598,12 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
       foreach(ctx, numOps, RunHeadKernel{mg, runHead.p});
       foreach(ctx, numOps, GroupSplitKernel{mg, runHead.p, opGroupHead.p});
       foreach(ctx, numOps, listGroups(0));
+      runHeadFlag.ensure(ctx, numOps + 1); runScan.ensure(ctx, numOps + 2); runStart.ensure(ctx, numOps + 2); elemFollower.ensure(ctx, N + 1);
+      dev_memset(ctx, elemFollower.p, 0, (N + 1) * 4);
+      foreach(ctx, numOps, FollowerFlagKernel{mg, opGroupHead.p, lctx, gElem.p, gT1.p, gCount.p, nQ.p, runHeadFlag.p, elemFollower.p});
+      scan_exclusive(ctx, scanTmp, runHeadFlag.p, runScan.p, numOps);
+      foreach(ctx, numOps, RunStartKernel{runHeadFlag.p, runScan.p, runStart.p});
+      foreach(ctx, 1, RunEndKernel{runScan.p, runStart.p, (u32)numOps});
     }
     objTouchedAt.ensure(ctx, N + 1); linkDone.ensure(ctx, N + 1);
     dev_memset(ctx, objTouchedAt.p, 0xff, (N + 1) * 4); dev_memset(ctx, linkDone.p, 0xff, (N + 1) * 4); dev_memset(ctx, flagWord.p, 0, 16);
@@ -664,16 +670,16 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
         nItems.ensure(ctx, N + 1); itemBase.ensure(ctx, N + 2); oldVisScan.ensure(ctx, N + 2);
         foreach(ctx, N, OldVisFlagKernel{lctx, head.p, nItems.p});
         scan_exclusive(ctx, scanTmp, nItems.p, oldVisScan.p, N);
-        foreach(ctx, N, DomItemCountKernel{nQ.p, nItems.p});
+        foreach(ctx, N, DomItemCountKernel{nQ.p, elemFollower.p, nItems.p});
         scan_exclusive(ctx, scanTmp, nItems.p, itemBase.p, N);
         const size_t T = readU32(itemBase.p + N);
-        items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zwScan.ensure(ctx, T + 2); domTw.ensure(ctx, T + 1); domTw2.ensure(ctx, T + 1);
+        items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zwScan.ensure(ctx, T + 2); domTw.ensure(ctx, T + 1); domTw2.ensure(ctx, T + 1); domW.ensure(ctx, T + 1); domW2.ensure(ctx, T + 1);
         foreach(ctx, numOps, listGroups(1));
         const int tbits = bits_for(numOps + 1);
         for (int bit = tbits - 1; bit >= 0; bit--) {
-          scan_exclusive64(ctx, scanTmp, DomScanInput{domTw.p, bit}, zwScan.p, T);
-          foreach(ctx, T, DomLevelKernel{items.p, items2.p, domTw2.p, zwScan.p, bit});
-          std::swap(items.p, items2.p); std::swap(items.cap, items2.cap); std::swap(domTw.p, domTw2.p); std::swap(domTw.cap, domTw2.cap);
+          scan_exclusive64(ctx, scanTmp, DomScanInput{domTw.p, domW.p, bit}, zwScan.p, T);
+          foreach(ctx, T, DomLevelKernel{items.p, items2.p, domTw2.p, domW2.p, zwScan.p, bit});
+          std::swap(items.p, items2.p); std::swap(items.cap, items2.cap); std::swap(domTw.p, domTw2.p); std::swap(domTw.cap, domTw2.cap); std::swap(domW.p, domW2.p); std::swap(domW.cap, domW2.cap);
         }
         foreach(ctx, T, DomResultKernel{items.p, qIndex.p});
       }

@@ -271,13 +271,12 @@ struct FirstVisKernel { const u32* groupOf; const u32* succCnt; u32* firstVisInG
 struct EditElemKernel { DocRows d; const u32* rowEmit; const u32* slot; const u32* groupOf; const u32* groupFirst; u64* elemOut; HD void operator()(size_t p) const { if (rowEmit[p]) elemOut[slot[p]] = d.id[groupFirst[groupOf[p]]]; } };
 
 // ---------------------------------------------------------------- incremental list edits: dominance counting
-// An item is a query (an op group asking for its list index), a point (a visibility change of an element: +1 / -1) or
-// both at once. tw = time (bits 0..26) | (weight + 1) << 27 | query << 29. The query result is routed by time (every
+// An item is a query (an op group asking for its list index), a point (a visibility change: weight +1 / -1, or +L for
+// a whole typing run) or both at once. tw = time (bits 0..26) | query << 29. The query result is routed by time (every
 // group has its own start time). gs / ge = current partition [gs, ge) of the item.
-struct DomItem { u32 tw, acc, gs, ge; };
-HD u32 dom_tw(u32 time, int w, bool query) { return time | ((u32)(w + 1) << 27) | (query ? 1u << 29 : 0u); }
+struct DomItem { u32 tw; int w; u32 acc, gs, ge; };
+HD u32 dom_tw(u32 time, bool query) { return time | (query ? 1u << 29 : 0u); }
 HD u32 dom_time(u32 tw) { return tw & 0x7ffffffu; }
-HD int dom_w(u32 tw) { return (int)((tw >> 27) & 3u) - 1; }
 HD bool dom_query(u32 tw) { return (tw >> 29) & 1u; }
 
 // Per-position view of a list element's rows: row p exists from d.time[p] (0 = before this call) and is overwritten at
@@ -294,16 +293,34 @@ struct ListCtx {
 struct OldVisFlagKernel { ListCtx L; const u32* head; u32* flag; HD void operator()(size_t p) const { flag[p] = (L.d.keyStrLen[p] == NULL32 && head[p] && (L.d.flags[p] & F_INSERT) && L.visAt((u32)p, L.groupRows[L.groupOf[p]], 0)) ? 1u : 0u; } };
 // items per position: one merged item for an element with one op group, otherwise its queries first and its points after
 // (a query must not see the points of its own element)
-struct DomItemCountKernel { const u32* nQ; u32* nItems; HD void operator()(size_t p) const { const u32 k = nQ[p]; nItems[p] = k <= 1 ? k : 2 * k; } };
-struct DomScanInput {   // per level: low word = 1 if the time bit is clear, high word = the item's weight if the bit is clear
-  const u32* tw; int bit;
-  HD u64 operator()(size_t i) const {
-    const u32 x = tw[i];
-    return ((x >> bit) & 1u) == 0 ? (1ull | ((u64)(u32)dom_w(x) << 32)) : 0ull;
+struct DomItemCountKernel { const u32* nQ; const u32* elemFollower; u32* nItems; HD void operator()(size_t p) const { const u32 k = nQ[p]; nItems[p] = elemFollower[p] ? 0u : (k <= 1 ? k : 2 * k); } };
+// Typing runs: consecutive insert ops (consecutive application times) whose elements end up next to each other in the
+// document, each touched by nothing else in the batch. Every other query sees such a run entirely or not at all, so the
+// run is ONE item: the query of its first op, weighted with the run length; member j has index(head) + j.
+struct FollowerFlagKernel {
+  MapGroupCtx c; const u32* groupHead; ListCtx L; const u32* gElem; const u32* gT1; const u32* gCount; const u32* nQ; u32* runHeadFlag; u32* elemFollower;
+  HD bool plainInsert(size_t t) const {
+    const u32 i = c.opAt[t];
+    return groupHead[t] && !c.isMapOp(i) && (c.ops.flags[i] & F_INSERT) && gElem[t] != ROW_NONE && nQ[gElem[t]] == 1 && gCount[t] >= 1 && ((gT1[t] >> 29) & 3u) == 2u;
+  }
+  HD void operator()(size_t t0) const {
+    bool f = false;
+    if (t0 > 0 && plainInsert(t0) && plainInsert(t0 - 1)) {
+      const u32 e = gElem[t0], e1 = gElem[t0 - 1];
+      f = e == e1 + L.groupRows[L.groupOf[e1]] && L.d.obj[e] == L.d.obj[e1];
+    }
+    runHeadFlag[t0] = f ? 0u : 1u;
+    if (f) elemFollower[gElem[t0]] = 1;
   }
 };
+struct RunEndKernel { const u32* runScan; u32* runStart; u32 numOps; HD void operator()(size_t) const { runStart[runScan[numOps]] = numOps; } };   // sentinel behind the last run
+struct RunStartKernel { const u32* runHeadFlag; const u32* runScan; u32* runStart; HD void operator()(size_t t) const { if (runHeadFlag[t]) runStart[runScan[t]] = (u32)t; } };
+struct DomScanInput {   // per level: low word = 1 if the time bit is clear, high word = the item's weight if the bit is clear
+  const u32* tw; const int* w; int bit;
+  HD u64 operator()(size_t i) const { return ((tw[i] >> bit) & 1u) == 0 ? (1ull | ((u64)(u32)w[i] << 32)) : 0ull; }
+};
 struct DomLevelKernel {   // accumulate + stable split of every partition on `bit`; ZW = packed exclusive scan of DomScanInput
-  const DomItem* in; DomItem* out; u32* twOut; const u64* ZW; int bit;
+  const DomItem* in; DomItem* out; u32* twOut; int* wOut; const u64* ZW; int bit;
   HD void operator()(size_t i) const {
     DomItem it = in[i];
     const u64 s_i = ZW[i], s_gs = ZW[it.gs], s_ge = ZW[it.ge];
@@ -319,7 +336,7 @@ struct DomLevelKernel {   // accumulate + stable split of every partition on `bi
       dst = it.gs + zb;
       it.ge = it.gs + zg;
     }
-    out[dst] = it; twOut[dst] = it.tw;
+    out[dst] = it; twOut[dst] = it.tw; wOut[dst] = it.w;
   }
 };
 struct DomResultKernel {   // route query results back by group start time
@@ -336,7 +353,8 @@ enum { EF_POP = 0x400, EF_GROUP_FIRST = 0x800, EF_START = 0x100, EF_MULTI = 0x20
 struct ListGroupKernel {
   int pass; MapGroupCtx c; const u32* groupHead; IdTable t; const u32* rowOfOp; const u32* pos; ListCtx L;
   u32* gCount; u32* gElem; u32* gT1; u32* gQOrd; u32* nQ; u32* elemHasRecs;                     // pass 0 out (gT1: T1 | (net weight + 1) << 29 | W << 31)
-  const u32* itemBase; const u32* objIdx; const u32* objStart; DomItem* items; u32* twArr; const u32* oldVisScan;   // pass 1: items
+  const u32* itemBase; const u32* objIdx; const u32* objStart; DomItem* items; u32* twArr; int* wArr; const u32* oldVisScan;   // pass 1: items
+  const u32* runHeadFlag; const u32* runScan; const u32* runStart;   // typing runs (FollowerFlagKernel)
   const u32* gBase; const u32* qIndex; EditRec* out; u64* elemOut; u32* objKeyOut; u32* elemPosOut; u64* errWord;   // pass 2: records
   HD static bool shown(u32 flags) { const u32 a = flags_action(flags); return a == ACT_SET || (a % 2 == 0 && a != ACT_DEL); }
   HD void operator()(size_t t0) const {
@@ -372,19 +390,21 @@ struct ListGroupKernel {
     if (!mine || gElem[t0] == ROW_NONE) return;
     const u32 e = gElem[t0];
     if (pass == 1) {
-      if (gQOrd[t0] == ROW_NONE) return;
-      const int wNet = (int)((gT1[t0] >> 29) & 3u) - 1; const bool isQ = gCount[t0] != 0; const u32 k = nQ[e], o = gQOrd[t0];
+      if (gQOrd[t0] == ROW_NONE || !runHeadFlag[t0]) return;   // members of a typing run are represented by its head
+      int wNet = (int)((gT1[t0] >> 29) & 3u) - 1; const bool isQ = gCount[t0] != 0; const u32 k = nQ[e], o = gQOrd[t0];
+      { const u32 run = runScan[t0]; const u32 len = runStart[run + 1] - (u32)t0; if (len > 1) wNet = (int)len; }   // head of a run: all its +1s at once
       DomItem q; q.acc = 0; q.gs = itemBase[objStart[objIdx[e]]]; q.ge = itemBase[objStart[objIdx[e] + 1]];
-      if (k == 1) { q.tw = dom_tw((u32)t0 + 1, wNet, isQ); items[itemBase[e]] = q; twArr[itemBase[e]] = q.tw; }
+      if (k == 1) { q.tw = dom_tw((u32)t0 + 1, isQ); q.w = wNet; items[itemBase[e]] = q; twArr[itemBase[e]] = q.tw; wArr[itemBase[e]] = q.w; }
       else {
-        q.tw = dom_tw((u32)t0 + 1, 0, isQ); items[itemBase[e] + o] = q; twArr[itemBase[e] + o] = q.tw;
-        q.tw = dom_tw((u32)t0 + 1, wNet, false); items[itemBase[e] + k + o] = q; twArr[itemBase[e] + k + o] = q.tw;
+        q.tw = dom_tw((u32)t0 + 1, isQ); q.w = 0; items[itemBase[e] + o] = q; twArr[itemBase[e] + o] = q.tw; wArr[itemBase[e] + o] = 0;
+        q.tw = dom_tw((u32)t0 + 1, false); q.w = wNet; items[itemBase[e] + k + o] = q; twArr[itemBase[e] + k + o] = q.tw; wArr[itemBase[e] + k + o] = wNet;
       }
       return;
     }
     if (gCount[t0] == 0) return;
     const u32 T0 = (u32)t0 + 1, T1 = gT1[t0] & 0x1fffffffu; const bool W = gT1[t0] >> 31;
-    const u32 rows = L.groupRows[L.groupOf[e]], idx = qIndex[t0] + oldVisScan[e] - oldVisScan[objStart[objIdx[e]]];
+    const u32 runHeadT = runStart[runScan[t0] + runHeadFlag[t0] - 1];   // == t0 unless this op is a member of a typing run
+    const u32 rows = L.groupRows[L.groupOf[e]], idx = qIndex[runHeadT] + ((u32)t0 - runHeadT) + oldVisScan[e] - oldVisScan[objStart[objIdx[e]]];
     // Reference quirk, reproduced: when one mergeDocChangeOps call walks from an element straight into the next one
     // (new.js:1116-1121), the insert row of that next element is reported with the list index of the previous element:
     // listIndex is only advanced after updatePatchProperty has seen the row (new.js:1204-1211). It matters for the edits

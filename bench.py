@@ -31,6 +31,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+    os.environ['NCCL_DEBUG'] = 'WARN'   # keep stdout to the one JSON line (NCCL prints its version banner there)
 
 N_OPS, N_ACTORS = 1_000_000, 10
 CPU_SAMPLE_OPS = 200_000
