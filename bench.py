@@ -218,6 +218,27 @@ def main():
         else:
             roofline = {'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None, 'traffic': None, 'error': err.msg.decode()}
 
+    # the other routes of SURVEY §8d, once each on rank 0 (wall clock through the C ABI): (ii) loadChanges + getPatch,
+    # (iii) save, then load + getPatch of the saved document
+    other = None
+    if rank == 0:
+        try:
+            def wall(fn):
+                torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); return r, time.perf_counter() - t0
+            lib.check(L.amg_reset(doc.h, C.byref(err)), err)
+            _, t_lc = wall(lambda: doc.apply_packed_flat(blob_ptr, offs, trace.n_changes, want_patch=False))
+            _, t_gp = wall(doc.get_patch_flat)
+            saved, t_sv = wall(doc.save)
+            d2, t_ld = wall(lambda: GpuBackendDoc(saved, device=local))
+            _, t_gp2 = wall(d2.get_patch_flat)
+            del d2
+            other = {'loadChanges_plus_getPatch_ops_per_s': trace.n_ops / (t_lc + t_gp), 'loadChanges_ms': t_lc * 1e3, 'getPatch_ms': t_gp * 1e3,
+                     'save_ms': t_sv * 1e3, 'saved_document_bytes': len(saved),
+                     'load_plus_getPatch_ops_per_s': trace.n_ops / (t_ld + t_gp2), 'load_ms': t_ld * 1e3, 'getPatch_after_load_ms': t_gp2 * 1e3,
+                     'note': 'single cold invocation each, host buffers in and out'}
+        except Exception as e:   # never lose the headline line over the extras
+            other = {'error': repr(e)[:200]}
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         import oracle
@@ -244,7 +265,7 @@ def main():
                        'l2': 'inputs (%.0f MB) + working tables exceed the 126 MB L2; document reset every step' % (nbytes / 1e6),
                        'device_ms_per_step': t_dev * 1e3,
                        'phase_ms_last_step': dict(zip(['stage_upload', 'sha256', 'parse_gate', 'actors_decode', 'opset', 'patch_groups_props', 'patch_list_index', 'patch_edits_copyout', 'heads_commit'], [round(x, 3) for x in last_ph[:9]])),
-                       'host_marks_ms': [round(x, 3) for x in last_ph[12:22]]},
+                       'host_marks_ms': [round(x, 3) for x in last_ph[12:22]], 'other_paths': other},
             'e2e': {'value': total_ops / t_wall, 'unit': 'ops/s', 'h2d_bytes_per_step': nbytes + 8 * (trace.n_changes + 1), 'd2h_bytes_per_step': patch_bytes},
             'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks}))
     if world > 1:
