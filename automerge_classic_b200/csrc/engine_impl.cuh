@@ -40,7 +40,7 @@ inline void Engine::fillPatchHeader(PatchOut& out) {
 
 // writes the header and the small sections (actor, actors, clock, deps) after the big record sections
 inline void Engine::finishPatch(PatchOut& out) {
-  if (out.bigEnd == 0) { out.propsOff = out.editsOff = out.elemOff = 18 * 8; out.bigEnd = 18 * 8; }
+  if (out.bigEnd == 0) { out.propsOff = out.editsOff = 18 * 8; out.elemOff = 0; out.bigEnd = 18 * 8; }
   size_t small = 64 + out.actor.size(); for (auto& a : out.actors) small += 8 + a.size(); small += out.clock.size() * 16 + out.deps.size() * 32 + 64;
   patchBuf.ensure(out.bigEnd + small);   // growth preserves what is already there
   u8* b = patchBuf.p; size_t at = out.bigEnd;
@@ -84,15 +84,15 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     if (!inflPending) return;
     inflPending = false; const size_t nd = inflNd;
     u32* origOff = patchTriples.p; u32* origLen = patchTriples.p + nd;
-    deflIdx.resize(nd); std::vector<u32> newLen(nd), newOff(nd), oOff(nd), oLen(nd);
-    d2h(ctx, deflIdx.data(), deflList.p, nd * 4); d2h(ctx, newLen.data(), inflLen.p, nd * 4); d2h(ctx, newOff.data(), inflOff.p, nd * 4);
-    d2h(ctx, oOff.data(), origOff, nd * 4); d2h(ctx, oLen.data(), origLen, nd * 4);
+    pinnedScratch.ensure(5 * nd + 16); u32* ps = pinnedScratch.p;   // pinned: the five small copies queue up and complete with one sync
+    d2h(ctx, ps, deflList.p, nd * 4); d2h(ctx, ps + nd, inflLen.p, nd * 4); d2h(ctx, ps + 2 * nd, inflOff.p, nd * 4);
+    d2h(ctx, ps + 3 * nd, origOff, nd * 4); d2h(ctx, ps + 4 * nd, origLen, nd * 4);
     if (mirrorThread.joinable()) mirrorThread.join();   // the mirror has to grow
     hostArena.resize(inflExtraStart + inflExtra);
     d2h(ctx, hostArena.data() + inflExtraStart, arena.p + inflExtraStart, inflExtra);
     sync(ctx);
-    inflOrig.resize(nd);   // deflIdx is ascending: (batch index, original range), looked up by binary search
-    for (size_t k = 0; k < nd; k++) { const u32 bi = deflIdx[k]; inflOrig[k] = HostChange{oOff[k], oLen[k]}; batch[bi] = HostChange{(u32)inflExtraStart + newOff[k], newLen[k]}; }
+    deflIdx.assign(ps, ps + nd); inflOrig.resize(nd);   // deflIdx is ascending: (batch index, original range), looked up by binary search
+    for (size_t k = 0; k < nd; k++) { const u32 bi = ps[k]; inflOrig[k] = HostChange{ps[3 * nd + k], ps[4 * nd + k]}; batch[bi] = HostChange{(u32)inflExtraStart + ps[2 * nd + k], ps[nd + k]}; }
   };
   auto originalOf = [&](size_t b) -> HostChange {
     if (!batchOriginal.empty() && batchOriginal[b].len) return batchOriginal[b];
@@ -256,18 +256,26 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     }
     if (fresh > 0) {
     dbgMark("actors:interned");
-      std::vector<u32> slotsH(fresh); d2h(ctx, slotsH.data(), newSlots.p, fresh * 4); sync(ctx);
-      std::vector<ActorSlot> recs(fresh); for (u32 i = 0; i < fresh; i++) d2h(ctx, &recs[i], actorSlots.p + slotsH[i], sizeof(ActorSlot));
-      sync(ctx);
+      // slot numbers, slot records and id bytes of the new actors in ONE round trip (gathered into a staging buffer)
+      static const u32 ACTOR_STAGE = 64;
+      hashTmp.ensure(ctx, (size_t)fresh * (4 + sizeof(ActorSlot) + ACTOR_STAGE) + 64);
+      u8* stageD = hashTmp.p; const size_t recsAt = ((size_t)fresh * 4 + 15) & ~(size_t)15, bytesAt = recsAt + (size_t)fresh * sizeof(ActorSlot), stageLen = bytesAt + (size_t)fresh * ACTOR_STAGE;
+      foreach(ctx, fresh, GatherNewActorsKernel{arena.p, actorSlots.p, newSlots.p, reinterpret_cast<u32*>(stageD), reinterpret_cast<ActorSlot*>(stageD + recsAt), stageD + bytesAt, ACTOR_STAGE});
+      std::vector<u8> stageH(stageLen); d2h(ctx, stageH.data(), stageD, stageLen); sync(ctx);
+      std::vector<u32> slotsH(fresh); memcpy(slotsH.data(), stageH.data(), (size_t)fresh * 4);
+      std::vector<ActorSlot> recs(fresh); memcpy(recs.data(), stageH.data() + recsAt, (size_t)fresh * sizeof(ActorSlot));
       std::vector<u32> order(fresh); for (u32 i = 0; i < fresh; i++) order[i] = i;
       std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return recs[a].first < recs[b].first; });
       std::vector<u32> ids(fresh), nums(fresh); actorsNow.reserve(actorsNow.size() + fresh);   // async copies target the strings: no reallocation below
+      bool longIds = false;
       for (u32 k = 0; k < fresh; k++) {
         const ActorSlot& r = recs[order[k]]; ids[k] = slotsH[order[k]]; nums[k] = (u32)actorsNow.size();
-        actorsNow.emplace_back(r.repLen, '\0'); d2h(ctx, &actorsNow.back()[0], arena.p + r.repOff, r.repLen);   // from the device copy: the host mirror may still be filling
+        actorsNow.emplace_back(r.repLen, '\0');
+        if (r.repLen <= ACTOR_STAGE) memcpy(&actorsNow.back()[0], stageH.data() + bytesAt + (size_t)order[k] * ACTOR_STAGE, r.repLen);
+        else { d2h(ctx, &actorsNow.back()[0], arena.p + r.repOff, r.repLen); longIds = true; }   // from the device copy: the host mirror may still be filling
         actorRepNow.emplace_back(r.repOff, r.repLen);
       }
-      sync(ctx);
+      if (longIds) sync(ctx);
       if (actorsNow.size() > 65535) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 65535 actors in one document");
       sortVals.ensure(ctx, 2 * fresh); h2d(ctx, sortVals.p, ids.data(), fresh * 4); h2d(ctx, sortVals.p + fresh, nums.data(), fresh * 4);
       foreach(ctx, fresh, SetActorNumKernel{actorSlots.p, sortVals.p, sortVals.p + fresh});
@@ -486,8 +494,10 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       sync(ctx);
       std::vector<std::array<u8, 32>> hs; std::vector<u32> hi;
       for (size_t i = 0; i < headIdx.size(); i++) if (!oldDep[i]) { hs.push_back(heads[i]); hi.push_back(headIdx[i]); }
-      std::vector<u32> rankOfB(nh);
-      for (u32 k = 0; k < nh; k++) { std::array<u8, 32> h; d2h(ctx, h.data(), hashes.p + (numApplied + hb[k]) * 32, 32); d2h(ctx, &rankOfB[k], appRank.p + hb[k], 4); sync(ctx); hs.push_back(h); hi.push_back((u32)(numApplied + rankOfB[k])); }
+      std::vector<u32> rankOfB(nh); std::vector<std::array<u8, 32>> newHeads(nh);
+      for (u32 k = 0; k < nh; k++) { d2h(ctx, newHeads[k].data(), hashes.p + (numApplied + hb[k]) * 32, 32); d2h(ctx, &rankOfB[k], appRank.p + hb[k], 4); }
+      if (nh) sync(ctx);   // one round trip for all of them
+      for (u32 k = 0; k < nh; k++) { hs.push_back(newHeads[k]); hi.push_back((u32)(numApplied + rankOfB[k])); }
       std::vector<size_t> o(hs.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i;
       std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return hs[a] < hs[b]; });
       headsNow.clear(); headIdxNow.clear(); for (size_t i : o) { headsNow.push_back(hs[i]); headIdxNow.push_back(hi[i]); }
@@ -638,7 +648,7 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   foreach(ctx, N, PropEmitKernel{d, emit.p, marker.p, slot.p, propOut.p, counterLast.p, counterTotal.p});
   if (curTimer) { curTimer->mark(); curHostMark(); }
   // ---- list edits
-  size_t numEdits = 0;
+  size_t numEdits = 0; bool shipElem = true;
   if (wholeDoc) {
     elemVis.ensure(ctx, N + 1); elemVisScan.ensure(ctx, N + 2); rowEmit.ensure(ctx, N + 1); firstVis.ensure(ctx, numGroups + 1);
     foreach(ctx, N, ListVisFlagKernel{d, groupOf.p, groupVisible.p, head.p, succCnt.p, elemVis.p, rowEmit.p});
@@ -704,22 +714,26 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
       dev_memset(ctx, editDead.p, 0, (numEdits + 1) * 4); dev_memset(ctx, editMulti.p, 0, (numEdits + 1) * 4);
       foreach(ctx, numEdits, EditFixKernel{editOut2.p, editElemPos2.p, editKind.p, editPred.p, editDead.p, numEdits});
       foreach(ctx, numEdits, EditMergeKernel{editOut2.p, editElem2.p, editKind.p, editPred.p, editMerge.p, editMulti.p});
-      foreach(ctx, numEdits, EditLiveKernel{editDead.p, editLive.p});
+      dev_memset(ctx, flagWord.p, 0, 4);
+      foreach(ctx, numEdits, EditLiveKernel{editDead.p, editLive.p, editOut2.p, editElem2.p, editKind.p, flagWord.p});
       DBuf<u32>& liveSlot = editPred;   // pred is consumed by now
       scan_exclusive(ctx, scanTmp, editLive.p, liveSlot.p, numEdits);
-      const size_t numLive = readU32(liveSlot.p + numEdits);
+      u32 numLive32 = 0, needElem32 = 0; readU32x2(liveSlot.p + numEdits, flagWord.p, &numLive32, &needElem32);
+      const size_t numLive = numLive32; shipElem = needElem32 != 0;
       foreach(ctx, numEdits, EditCompactKernel{editOut2.p, editElem2.p, editDead.p, liveSlot.p, editKind.p, editMerge.p, editMulti.p, editOut.p, editElem.p});
       numEdits = numLive;
     }
   }
   if (wholeDoc && numEdits > 0) foreach(ctx, numEdits, RunFlagKernel{editOut.p, editElem.p, numEdits});
   out.numProps = numProps; out.numEdits = numEdits;
-  out.propsOff = 18 * 8; out.editsOff = out.propsOff + numProps * sizeof(PropRec); out.elemOff = out.editsOff + numEdits * sizeof(EditRec); out.bigEnd = out.elemOff + numEdits * 8;
+  out.propsOff = 18 * 8; out.editsOff = out.propsOff + numProps * sizeof(PropRec);
+  if (shipElem) { out.elemOff = out.editsOff + numEdits * sizeof(EditRec); out.bigEnd = out.elemOff + numEdits * 8; }
+  else { out.elemOff = 0; out.bigEnd = out.editsOff + numEdits * sizeof(EditRec); }   // elemOff 0: every insert's elemId is its opId
   patchBuf.ensure(out.bigEnd + 4096);
   // the copy-out runs on the side stream: the caller joins it before reading the patch, later kernels overlap it
   side_fork(ctx);
   d2h_side(ctx, patchBuf.p + out.propsOff, propOut.p, numProps * sizeof(PropRec));
-  if (numEdits > 0) { d2h_side(ctx, patchBuf.p + out.editsOff, editOut.p, numEdits * sizeof(EditRec)); d2h_side(ctx, patchBuf.p + out.elemOff, editElem.p, numEdits * 8); }
+  if (numEdits > 0) { d2h_side(ctx, patchBuf.p + out.editsOff, editOut.p, numEdits * sizeof(EditRec)); if (shipElem) d2h_side(ctx, patchBuf.p + out.elemOff, editElem.p, numEdits * 8); }
 }
 
 inline void Engine::getPatch(PatchOut& out) {

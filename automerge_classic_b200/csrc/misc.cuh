@@ -33,6 +33,13 @@ struct NewActorKernel {
     newSlots[atomic_add(newCount, 1u)] = authorSlot[b];
   }
 };
+struct GatherNewActorsKernel {   // slot number, slot record and (up to `stride`) id bytes of every new actor, packed for one copy
+  const u8* arena; const ActorSlot* slots; const u32* newSlots; u32* slotOut; ActorSlot* recOut; u8* bytesOut; u32 stride;
+  HD void operator()(size_t k) const {
+    const u32 s = newSlots[k]; const ActorSlot r = slots[s]; slotOut[k] = s; recOut[k] = r;
+    for (u32 j = 0; j < r.repLen && j < stride; j++) bytesOut[k * stride + j] = arena[r.repOff + j];
+  }
+};
 struct SetActorNumKernel { ActorSlot* slots; const u32* slotIds; const u32* nums; HD void operator()(size_t i) const { slots[slotIds[i]].actorNum = nums[i]; } };
 struct ChangeActorKernel { const u32* amapBase; const u32* amap; const u8* applied; u32* changeActor; u32* actorCnt; HD void operator()(size_t b) const { if (!applied[b]) { changeActor[b] = EMPTY32; return; } const u32 a = amap[amapBase[b]]; changeActor[b] = a; warp_agg_inc(actorCnt, a); } };
 // seq == clock + 1 in application order (new.js:1559, 1571-1579): the seqs of an actor's applied changes must be

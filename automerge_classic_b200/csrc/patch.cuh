@@ -494,7 +494,10 @@ struct EditMergeKernel {
     mergePrev[j] = cont ? 1u : 0u;
   }
 };
-struct EditLiveKernel { const u32* dead; u32* live; HD void operator()(size_t j) const { live[j] = dead[j] ? 0u : 1u; } };
+struct EditLiveKernel {   // also: does any surviving insert carry an elemId different from its opId? (otherwise the elemId section is not shipped)
+  const u32* dead; u32* live; const EditRec* edits; const u64* elem; const u32* newKind; u32* needElem;
+  HD void operator()(size_t j) const { live[j] = dead[j] ? 0u : 1u; if (!dead[j] && newKind[j] == EK_INSERT && elem[j] != edits[j].opId) *needElem = 1; }
+};
 struct EditCompactKernel {
   const EditRec* in; const u64* elemIn; const u32* dead; const u32* slot; const u32* newKind; const u32* mergePrev; const u32* multi; EditRec* out; u64* elemOut;
   HD void operator()(size_t j) const {

@@ -147,7 +147,8 @@ class FlatPatch:
         self.deps = [bytes(raw[int(h[11]) + 32 * i:int(h[11]) + 32 * i + 32]).hex() for i in range(int(h[12]))]
         self.props = np.frombuffer(raw, dtype=PROP_DT, count=int(h[14]), offset=int(h[13]))
         self.edits = np.frombuffer(raw, dtype=EDIT_DT, count=int(h[16]), offset=int(h[15]))
-        self.edit_elem = np.frombuffer(raw, dtype='<u8', count=int(h[16]), offset=int(h[17]))
+        # elemOff == 0: the section is not shipped because every insert's elemId equals its opId
+        self.edit_elem = np.frombuffer(raw, dtype='<u8', count=int(h[16]), offset=int(h[17])) if int(h[17]) else self.edits['opId']
 
     def op_id(self, x):
         x = int(x)

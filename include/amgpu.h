@@ -90,7 +90,7 @@ void amg_buffers_free(amg_buffers* l);
  *   deps   : nDeps x 32 bytes
  *   props  : nProps x { uint64 objId; uint64 opId; uint32 keyOff, keyLen, valLen, valOff, flags, pad }   (map entries)
  *   edits  : nEdits x { uint64 objId; uint64 opId; uint32 index, kind, valLen, valOff }                  (list edits, per object in order)
- *   editElem: nEdits x uint64 elemId
+ *   editElem: nEdits x uint64 elemId (offset 0 in the header = section absent: every insert's elemId is its opId)
  * ids are (counter << 16 | actorIndex); objId 0 = _root. keyOff / valOff index the document arena
  * (amg_arena); valLen is the reference's VALUE_LEN tag (length << 4 | type, columnar.js:46-49).
  * props.flags = action << 8 | 1 if the key has no visible value (reference emits `key: {}`);
