@@ -180,6 +180,27 @@ template <class F> inline void foreach(Ctx& c, size_t n, const F& f, bool onSide
 #endif
   c.launches++;
 }
+// One item per WARP (lane 0 works): for long serial state machines whose control flow differs from item to item
+// (Huffman streams, RLE column walks). Packed 32 to a warp they would execute one after the other in lockstep.
+#ifndef AMG_EMU
+template <class F> __global__ void __launch_bounds__(256) k_foreach_warp(size_t n, F f) {
+  if (threadIdx.x & 31) return;
+  const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t k = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < n; k += warps) f(k);
+}
+#endif
+template <class F> inline void foreach_warp(Ctx& c, size_t n, const F& f) {
+  if (n == 0) return;
+#ifdef AMG_EMU
+  for (size_t i = 0; i < n; i++) f(i);
+#else
+  size_t want = (n + 7) / 8, maxGrid = (size_t)c.numSMs * 8;
+  int grid = (int)(want < maxGrid ? want : maxGrid);
+  k_foreach_warp<F><<<grid, 256, 0, c.stream>>>(n, f);
+  CUDA_CHECK(cudaGetLastError());
+#endif
+  c.launches++;
+}
 // side stream: fork() makes it wait for everything enqueued on the main stream so far, join() the reverse
 inline void side_fork(Ctx& c) {
 #ifndef AMG_EMU

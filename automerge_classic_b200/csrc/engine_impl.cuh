@@ -175,14 +175,14 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       foreach(ctx, B, CompactKernel{emit.p, slot.p, deflList.p});
       inflLen.ensure(ctx, nd + 1); inflOff.ensure(ctx, nd + 2); patchTriples.ensure(ctx, 2 * nd + 2);
       u32* origOff = patchTriples.p; u32* origLen = patchTriples.p + nd;
-      foreach(ctx, nd, InflateKernel{0, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, nullptr, 0, origOff, origLen, errWord.p});
+      foreach_warp(ctx, nd, InflateKernel{0, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, nullptr, 0, origOff, origLen, errWord.p});
       scan_exclusive(ctx, scanTmp, inflLen.p, inflOff.p, nd);
       const size_t extra = readU32(inflOff.p + nd);
       { u64 ew0 = 0; d2h(ctx, &ew0, errWord.p, 8); sync(ctx); if (ew0) throwKernelError(ew0, actorIds); }
       if ((u64)cur + extra + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
       const size_t extraStart = cur; cur += extra;
       arena.ensure(ctx, cur + 64, extraStart);
-      foreach(ctx, nd, InflateKernel{1, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, inflOff.p, (u32)extraStart, origOff, origLen, errWord.p});
+      foreach_warp(ctx, nd, InflateKernel{1, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, inflOff.p, (u32)extraStart, origOff, origLen, errWord.p});
       dev_memset(ctx, arena.p + cur, 0, 64);
       side_join(ctx);
       foreach(ctx, nd, InflatePatchKernel{deflList.p, inflLen.p, inflOff.p, (u32)extraStart, chOff.p, chLen.p});
@@ -883,12 +883,12 @@ inline void Engine::saveDocument(std::string& result) {
     if (L > 0) {   // number of dependency indexes the loaded changes carry
       DBuf<u64>& sumD = pairSucc; sumD.ensure(ctx, 1);
       const HostChange& dn = loadedCol(0x40);
-      foreach(ctx, 1, LoadedColKernel{LC_SUM, arena.p, dn.off, dn.len, 0, 0, nullptr, nullptr, nullptr, sumD.p});
+      foreach_warp(ctx, 1, LoadedColKernel{LC_SUM, arena.p, dn.off, dn.len, 0, 0, nullptr, nullptr, nullptr, sumD.p});
       u64 sum = 0; d2h(ctx, &sum, sumD.p, 8); sync(ctx); loadedDeps = (u32)sum;
     }
     saveVals.ensure(ctx, std::max<size_t>(std::max(std::max(C, N), S), (size_t)loadedDeps + totalDeps) + 2);
     saveStrOff.ensure(ctx, std::max(C, N) + 1); saveStrLen.ensure(ctx, std::max(C, N) + 1);
-    auto loadedVal = [&](int kind, u32 id, u32 count) { if (L == 0) return; const HostChange& c = loadedCol(id); foreach(ctx, 1, LoadedColKernel{kind, arena.p, c.off, c.len, loadedCol(0x57).off, count, saveVals.p, saveStrOff.p, saveStrLen.p, nullptr}); };
+    auto loadedVal = [&](int kind, u32 id, u32 count) { if (L == 0) return; const HostChange& c = loadedCol(id); foreach_warp(ctx, 1, LoadedColKernel{kind, arena.p, c.off, c.len, loadedCol(0x57).off, count, saveVals.p, saveStrOff.p, saveStrLen.p, nullptr}); };
     auto changeVal = [&](int which) { if (K == 0) return; foreach(ctx, K, SaveChangeValKernel{which, arena.p, meta.p, actorSlots.p, (u64)actorCap - 1, saveVals.p + L, saveStrOff.p + L, saveStrLen.p + L, errWord.p}); };
     loadedVal(LC_UINT, 0x01, (u32)L);  changeVal(SM_ACTOR);     add(changeCols, 0x01, enc.rleNum(saveVals.p, C, false));
     loadedVal(LC_DELTA, 0x03, (u32)L); changeVal(SM_SEQ);       add(changeCols, 0x03, enc.deltaNum(saveVals.p, C));
@@ -1041,7 +1041,7 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff, &o_change, &o_time}) b->ensure(ctx, N + 1);
   r_predActor.ensure(ctx, S + 1); r_predCtr.ensure(ctx, S + 1);
   RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
-  foreach(ctx, 16, DocColumnKernel{arena.p, dc, (u32)N, (u32)S, raw, o_change.p, o_time.p, errWord.p});
+  foreach_warp(ctx, 16, DocColumnKernel{arena.p, dc, (u32)N, (u32)S, raw, o_change.p, o_time.p, errWord.p});
   doc.ensure(ctx, N + 1); succOff.ensure(ctx, N + 2); succ.ensure(ctx, S + 1);
   DBuf<u64>& maxOpD = pairSucc; maxOpD.ensure(ctx, 1); dev_memset(ctx, maxOpD.p, 0, 8);
   foreach(ctx, N, DocFinalizeKernel{raw, o_change.p, o_time.p, (u32)actors.size(), doc.view(), succOff.p, succ.p, maxOpD.p, errWord.p});
