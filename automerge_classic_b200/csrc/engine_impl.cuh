@@ -464,7 +464,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     foreach(ctx, numPairs, NewSuccFlagKernel{pairPos.p, pairTime.p, newSuccCnt.p});
     foreach(ctx, numPairs, FirstSuccTimeKernel{pairPos.p, pairTime.p, firstNewSucc.p});
     scan_exclusive(ctx, scanTmp, succCnt.p, newSuccOff.p, N);
-    foreach(ctx, numPairs, WriteSuccKernel{pairIdx.p, pairSucc.p, newSucc.p});
+    newSuccTime.ensure(ctx, numPairs + 1);
+    foreach(ctx, numPairs, WriteSuccKernel{pairIdx.p, pairSucc.p, newSucc.p, pairTime.p, newSuccTime.p});
     sorted.ensure(ctx, N + 1);
     foreach(ctx, N, GatherRowsKernel{w, sorted.view(), perm.p});
     dbgMark("opset:succ+gather(enqueued)");
@@ -589,12 +590,12 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   groupLinked.ensure(ctx, std::max(numGroups, numApplied + 1) + 2);
   dev_memset(ctx, groupLinked.p, 0, (numGroups + 1) * 4);
   Ord ordNow{actorRank.p, bits_for(actorsNow.size() > 1 ? actorsNow.size() - 1 : 1)};
-  ListCtx lctx{d, succCnt.p, newSuccCnt.p, firstNewSucc.p, groupOf.p, groupFirst.p, groupRows.p};
+  ListCtx lctx{d, succCnt.p, newSuccCnt.p, firstNewSucc.p, groupOf.p, groupFirst.p, groupRows.p, arena.p, succOffD, succD, newSuccTime.p};
   MapGroupCtx mg{arena.p, ops ? *ops : OpRows{}, opAt.p, numOps, pass.p};
   bool anyListLink = false;
   auto listGroups = [&](int pass) {
     return ListGroupKernel{pass, mg, opGroupHead.p, *idt, rowOfOpD, posD, lctx, gCount.p, gElem.p, gT1.p, gQOrd.p, nQ.p, elemHasRecs.p,
-                           itemBase.p, objIdx.p, objStart.p, items.p, domTw.p, domW.p, oldVisScan.p, runHeadFlag.p, runScan.p, runStart.p, gBase.p, qIndex.p, editOut.p, editElem.p, editObjKey.p, editElemPos.p, errWord.p};
+                           itemBase.p, objIdx.p, objStart.p, items.p, domTw.p, domW.p, oldVisScan.p, runHeadFlag.p, runScan.p, runStart.p, gBase.p, qIndex.p, editOut.p, editElem.p, editObjKey.p, editElemPos.p, editRowPos.p, errWord.p};
   };
   if (!wholeDoc) {
     // op groups of the batch (new.js:1085-1138), then what each list group nets out to
@@ -620,7 +621,7 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
     foreach(ctx, N, TouchKernel{d, groupOf.p, firstNewSucc.p, groupTouched.p, objTouchedAt.p, objPos.p, flagWord.p + 2});
     u32 linkChanged = 1, anyLink32 = 0;
     for (int iter = 0; iter < 1000 && linkChanged; iter++) {   // three sweeps per host round trip (object nesting is shallow)
-      LinkKernel lk{d, groupOf.p, groupHasChild.p, groupFirst.p, objPos.p, groupLinked.p, objTouchedAt.p, flagWord.p + 2, linkDone.p, flagWord.p, elemHasRecs.p, listLinkTime.p, flagWord.p + 3};
+      LinkKernel lk{d, groupOf.p, groupHasChild.p, groupFirst.p, objPos.p, groupLinked.p, objTouchedAt.p, flagWord.p + 2, linkDone.p, flagWord.p, listLinkTime.p, flagWord.p + 3};
       foreach(ctx, N, lk); foreach(ctx, N, lk);
       dev_memset(ctx, flagWord.p, 0, 4);
       foreach(ctx, N, lk);
@@ -638,8 +639,8 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
     for (int pass = 0; pass < 2; pass++)
       foreach(ctx, numOps, GroupFinalKernel{pass, mg, opGroupHead.p, *idt, rowOfOpD, posD, groupOf.p, workView, ordNow, finalTime.p, gBound.p, gFailed.p, memberFinal.p});
   }
-  counterLast.ensure(ctx, N + 1); counterTotal.ensure(ctx, N + 1);
-  foreach(ctx, N, CounterKernel{arena.p, d, succOffD, succD, groupOf.p, groupFirst.p, groupRows.p, counterLast.p, counterTotal.p});
+  counterLast.ensure(ctx, N + 1); counterTotal.ensure(ctx, N + 1); counterOwner.ensure(ctx, N + 1); dev_memset(ctx, counterOwner.p, 0xff, (N + 1) * 4);
+  foreach(ctx, N, CounterKernel{arena.p, d, succOffD, succD, groupOf.p, groupFirst.p, groupRows.p, counterLast.p, counterTotal.p, counterOwner.p});
   foreach(ctx, N, PropFlagKernel{d, groupOf.p, groupTouched.p, groupLinked.p, succCnt.p, wholeDoc ? 1 : 0, finalTime.p, gBound.p, gFailed.p, memberFinal.p, ordNow, emit.p, groupEmitted.p, counterLast.p});
   foreach(ctx, N, PropMarkerKernel{d, groupOf.p, groupTouched.p, head.p, groupEmitted.p, wholeDoc ? 1 : 0, emit.p, marker.p});
   scan_exclusive(ctx, scanTmp, emit.p, slot.p, N);
@@ -651,78 +652,93 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   size_t numEdits = 0; bool shipElem = true;
   if (wholeDoc) {
     elemVis.ensure(ctx, N + 1); elemVisScan.ensure(ctx, N + 2); rowEmit.ensure(ctx, N + 1); firstVis.ensure(ctx, numGroups + 1);
-    foreach(ctx, N, ListVisFlagKernel{d, groupOf.p, groupVisible.p, head.p, succCnt.p, elemVis.p, rowEmit.p});
+    rowClass.ensure(ctx, N + 1); firstBare.ensure(ctx, numGroups + 1);
+    dev_memset(ctx, firstVis.p, 0xff, (numGroups + 1) * 4); dev_memset(ctx, firstBare.p, 0xff, (numGroups + 1) * 4);
+    foreach(ctx, N, ListRowClassKernel{d, groupOf.p, succCnt.p, counterOwner.p, rowClass.p, firstVis.p, firstBare.p});
+    foreach(ctx, N, ListVisFlagKernel{d, groupOf.p, groupVisible.p, head.p, succCnt.p, elemVis.p, rowEmit.p, rowClass.p, firstVis.p, firstBare.p});
     scan_exclusive(ctx, scanTmp, elemVis.p, elemVisScan.p, N);
     scan_exclusive(ctx, scanTmp, rowEmit.p, slot.p, N);
     numEdits = readU32(slot.p + N);
-    dev_memset(ctx, firstVis.p, 0xff, (numGroups + 1) * 4);
-    foreach(ctx, N, FirstVisKernel{groupOf.p, succCnt.p, firstVis.p});
     editOut.ensure(ctx, numEdits + 1); editElem.ensure(ctx, numEdits + 1);
-    foreach(ctx, N, DocEditEmitKernel{d, rowEmit.p, slot.p, elemVisScan.p, objIdx.p, objStart.p, groupOf.p, groupFirst.p, succCnt.p, firstVis.p, editOut.p});
+    foreach(ctx, N, DocEditEmitKernel{d, rowEmit.p, slot.p, elemVisScan.p, objIdx.p, objStart.p, groupOf.p, groupFirst.p, rowClass.p, firstVis.p, firstBare.p, editOut.p, counterOwner.p, counterTotal.p});
     foreach(ctx, N, EditElemKernel{d, rowEmit.p, slot.p, groupOf.p, groupFirst.p, editElem.p});
   } else {
-    size_t numGroupRecs = 0, numLink = 0;
+    size_t numGroupRecs = 0, numLink = 0, numLive = 0;
     if (numOps > 0) { scan_exclusive(ctx, scanTmp, gCount.p, gBase.p, numOps); numGroupRecs = readU32(gBase.p + numOps); }
-    DBuf<u32>& linkCount = rowEmit; DBuf<u32>& linkBase = slot;
-    if (anyListLink) {   // index of a linked element = visible elements before it once the whole batch is applied
+    DBuf<u32>& elemHasLive = elemHasRecs; dev_memset(ctx, elemHasLive.p, 0, (N + 1) * 4);
+    auto ensureEdits = [&](size_t n) {
+      editOut.ensure(ctx, n + 1, numLive); editElem.ensure(ctx, n + 1, numLive); editObjKey.ensure(ctx, n + 1, numLive); editElemPos.ensure(ctx, n + 1);
+      editOut2.ensure(ctx, n + 1); editElem2.ensure(ctx, n + 1); editElemPos2.ensure(ctx, n + 1); editObjKey2.ensure(ctx, n + 1); editRowPos.ensure(ctx, n + 1); editRowPos2.ensure(ctx, n + 1);
+      sortKeys.ensure(ctx, n + 1); sortVals.ensure(ctx, n + 1);
+    };
+    // ---- A. records of the op groups: indexes, emission, per-object order, pops / coalescing, compaction
+    if (numGroupRecs > 0) {
+      // list index of a group = elements in front that were visible before the batch (one prefix sum)
+      //                       + net visibility changes in front that earlier groups of the batch made (dominance count)
+      nItems.ensure(ctx, N + 1); itemBase.ensure(ctx, N + 2); oldVisScan.ensure(ctx, N + 2);
+      foreach(ctx, N, OldVisFlagKernel{lctx, head.p, nItems.p});
+      scan_exclusive(ctx, scanTmp, nItems.p, oldVisScan.p, N);
+      foreach(ctx, N, DomItemCountKernel{nQ.p, elemFollower.p, nItems.p});
+      scan_exclusive(ctx, scanTmp, nItems.p, itemBase.p, N);
+      const size_t T = readU32(itemBase.p + N);
+      items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zwScan.ensure(ctx, T + 2); domTw.ensure(ctx, T + 1); domTw2.ensure(ctx, T + 1); domW.ensure(ctx, T + 1); domW2.ensure(ctx, T + 1);
+      foreach(ctx, numOps, listGroups(1));
+      const int tbits = bits_for(numOps + 1);
+      for (int bit = tbits - 1; bit >= 0; bit--) {
+        scan_exclusive64(ctx, scanTmp, DomScanInput{domTw.p, domW.p, bit}, zwScan.p, T);
+        foreach(ctx, T, DomLevelKernel{items.p, items2.p, domTw2.p, domW2.p, zwScan.p, bit});
+        std::swap(items.p, items2.p); std::swap(items.cap, items2.cap); std::swap(domTw.p, domTw2.p); std::swap(domTw.cap, domTw2.cap); std::swap(domW.p, domW2.p); std::swap(domW.cap, domW2.cap);
+      }
+      foreach(ctx, T, DomResultKernel{items.p, qIndex.p});
+      if (curTimer) { curTimer->mark(); curHostMark(); }
+      ensureEdits(numGroupRecs);
+      foreach(ctx, numOps, listGroups(2));
+      // the records are in application order by construction: one stable sort by object gives the per-object edit lists
+      foreach(ctx, numGroupRecs, EditKeyKernel{editObjKey.p, editOut.p, sortKeys.p, sortVals.p});
+      sortPairs(sortKeys, sortVals, numGroupRecs, bits_for(numObjs));
+      foreach(ctx, numGroupRecs, EditGatherKernel{editOut.p, editElem.p, editElemPos.p, editObjKey.p, sortVals.p, editOut2.p, editElem2.p, editElemPos2.p, editObjKey2.p});
+      foreach(ctx, numGroupRecs, GatherU32Kernel{editRowPos.p, sortVals.p, editRowPos2.p});
+      for (DBuf<u32>* b : {&editKind, &editPred, &editDead, &editMerge, &editMulti, &editLive}) b->ensure(ctx, numGroupRecs + 2);
+      dev_memset(ctx, editDead.p, 0, (numGroupRecs + 1) * 4); dev_memset(ctx, editMulti.p, 0, (numGroupRecs + 1) * 4);
+      foreach(ctx, numGroupRecs, EditFixKernel{editOut2.p, editElemPos2.p, editKind.p, editPred.p, editDead.p, numGroupRecs});
+      foreach(ctx, numGroupRecs, EditMergeKernel{editOut2.p, editElem2.p, editKind.p, editPred.p, editMerge.p, editMulti.p});
+      dev_memset(ctx, flagWord.p, 0, 4);
+      foreach(ctx, numGroupRecs, EditLiveKernel{editDead.p, editLive.p, editOut2.p, editElem2.p, editKind.p, flagWord.p, editElemPos2.p, elemHasLive.p, editRowPos2.p, succCnt.p, counterLast.p});
+      DBuf<u32>& liveSlot = editPred;   // pred is consumed by now
+      scan_exclusive(ctx, scanTmp, editLive.p, liveSlot.p, numGroupRecs);
+      u32 numLive32 = 0, needElem32 = 0; readU32x2(liveSlot.p + numGroupRecs, flagWord.p, &numLive32, &needElem32);
+      numLive = numLive32; shipElem = needElem32 != 0;
+      foreach(ctx, numGroupRecs, EditCompactKernel{editOut2.p, editElem2.p, editDead.p, liveSlot.p, editKind.p, editMerge.p, editMulti.p, editOut.p, editElem.p, editObjKey2.p, editObjKey.p});
+    } else if (curTimer) { curTimer->mark(); curHostMark(); }
+    // ---- B. setupPatches link edits on list parents: only for elements that did not keep an edit of their own; appended
+    //         behind the object's other edits in the order the child objects were first touched
+    if (anyListLink) {
+      DBuf<u32>& linkCount = rowEmit; DBuf<u32>& linkBase = slot;
       elemVis.ensure(ctx, N + 1); elemVisScan.ensure(ctx, N + 2); linkCount.ensure(ctx, N + 1); linkBase.ensure(ctx, N + 2);
-      foreach(ctx, N, ListVisFlagKernel{d, groupOf.p, groupVisible.p, head.p, succCnt.p, elemVis.p, linkCount.p});
-      scan_exclusive(ctx, scanTmp, elemVis.p, elemVisScan.p, N);
-      foreach(ctx, N, ListLinkKernel{0, lctx, listLinkTime.p, elemVisScan.p, objIdx.p, objStart.p, linkCount.p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr});
+      foreach(ctx, N, ListVisFlagKernel{d, groupOf.p, groupVisible.p, head.p, succCnt.p, elemVis.p, linkCount.p, nullptr, nullptr, nullptr});
+      scan_exclusive(ctx, scanTmp, elemVis.p, elemVisScan.p, N);   // index of a linked element = visible elements before it once the whole batch is applied
+      foreach(ctx, N, ListLinkKernel{0, lctx, listLinkTime.p, elemVisScan.p, objIdx.p, objStart.p, linkCount.p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, elemHasLive.p});
       scan_exclusive(ctx, scanTmp, linkCount.p, linkBase.p, N);
       numLink = readU32(linkBase.p + N);
-    }
-    numEdits = numGroupRecs + numLink;
-    if (numEdits > 0) {
-      if (numGroupRecs > 0) {
-        // list index of a group = elements in front that were visible before the batch (one prefix sum)
-        //                       + net visibility changes in front that earlier groups of the batch made (dominance count)
-        nItems.ensure(ctx, N + 1); itemBase.ensure(ctx, N + 2); oldVisScan.ensure(ctx, N + 2);
-        foreach(ctx, N, OldVisFlagKernel{lctx, head.p, nItems.p});
-        scan_exclusive(ctx, scanTmp, nItems.p, oldVisScan.p, N);
-        foreach(ctx, N, DomItemCountKernel{nQ.p, elemFollower.p, nItems.p});
-        scan_exclusive(ctx, scanTmp, nItems.p, itemBase.p, N);
-        const size_t T = readU32(itemBase.p + N);
-        items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zwScan.ensure(ctx, T + 2); domTw.ensure(ctx, T + 1); domTw2.ensure(ctx, T + 1); domW.ensure(ctx, T + 1); domW2.ensure(ctx, T + 1);
-        foreach(ctx, numOps, listGroups(1));
-        const int tbits = bits_for(numOps + 1);
-        for (int bit = tbits - 1; bit >= 0; bit--) {
-          scan_exclusive64(ctx, scanTmp, DomScanInput{domTw.p, domW.p, bit}, zwScan.p, T);
-          foreach(ctx, T, DomLevelKernel{items.p, items2.p, domTw2.p, domW2.p, zwScan.p, bit});
-          std::swap(items.p, items2.p); std::swap(items.cap, items2.cap); std::swap(domTw.p, domTw2.p); std::swap(domTw.cap, domTw2.cap); std::swap(domW.p, domW2.p); std::swap(domW.cap, domW2.cap);
-        }
-        foreach(ctx, T, DomResultKernel{items.p, qIndex.p});
-      }
-      if (curTimer) { curTimer->mark(); curHostMark(); }
-      editOut.ensure(ctx, numEdits + 1); editElem.ensure(ctx, numEdits + 1); editObjKey.ensure(ctx, numEdits + 1); editElemPos.ensure(ctx, numEdits + 1);
-      editOut2.ensure(ctx, numEdits + 1); editElem2.ensure(ctx, numEdits + 1); editElemPos2.ensure(ctx, numEdits + 1);
-      sortKeys.ensure(ctx, numEdits + 1); sortVals.ensure(ctx, numEdits + 1);
-      if (numGroupRecs > 0) foreach(ctx, numOps, listGroups(2));
-      // records of the op groups are in application order by construction; link edits go last, in the order their objects were first touched
       if (numLink > 0) {
-        editTime.ensure(ctx, numEdits + 1);
-        if (numGroupRecs > 0) foreach(ctx, numOps, GroupTimeKernel{gBase.p, gCount.p, editTime.p});
-        foreach(ctx, N, ListLinkKernel{1, lctx, listLinkTime.p, elemVisScan.p, objIdx.p, objStart.p, linkCount.p, linkBase.p, (u32)numGroupRecs, editOut.p, editElem.p, editObjKey.p, editElemPos.p, editTime.p});
-        foreach(ctx, numEdits, EditTimeKeyKernel{editTime.p, sortKeys.p, sortVals.p});
-        sortPairs(sortKeys, sortVals, numEdits, 32);
-        foreach(ctx, numEdits, GatherToU64Kernel{editObjKey.p, sortVals.p, sortKeys.p});
-      } else foreach(ctx, numEdits, EditKeyKernel{editObjKey.p, editOut.p, sortKeys.p, sortVals.p});
-      sortPairs(sortKeys, sortVals, numEdits, bits_for(numObjs));
-      foreach(ctx, numEdits, EditGatherKernel{editOut.p, editElem.p, editElemPos.p, sortVals.p, editOut2.p, editElem2.p, editElemPos2.p});
-      // pops, coalescing, compaction
-      for (DBuf<u32>* b : {&editKind, &editPred, &editDead, &editMerge, &editMulti, &editLive}) b->ensure(ctx, numEdits + 2);
-      dev_memset(ctx, editDead.p, 0, (numEdits + 1) * 4); dev_memset(ctx, editMulti.p, 0, (numEdits + 1) * 4);
-      foreach(ctx, numEdits, EditFixKernel{editOut2.p, editElemPos2.p, editKind.p, editPred.p, editDead.p, numEdits});
-      foreach(ctx, numEdits, EditMergeKernel{editOut2.p, editElem2.p, editKind.p, editPred.p, editMerge.p, editMulti.p});
-      dev_memset(ctx, flagWord.p, 0, 4);
-      foreach(ctx, numEdits, EditLiveKernel{editDead.p, editLive.p, editOut2.p, editElem2.p, editKind.p, flagWord.p});
-      DBuf<u32>& liveSlot = editPred;   // pred is consumed by now
-      scan_exclusive(ctx, scanTmp, editLive.p, liveSlot.p, numEdits);
-      u32 numLive32 = 0, needElem32 = 0; readU32x2(liveSlot.p + numEdits, flagWord.p, &numLive32, &needElem32);
-      const size_t numLive = numLive32; shipElem = needElem32 != 0;
-      foreach(ctx, numEdits, EditCompactKernel{editOut2.p, editElem2.p, editDead.p, liveSlot.p, editKind.p, editMerge.p, editMulti.p, editOut.p, editElem.p});
-      numEdits = numLive;
+        const size_t total = numLive + numLink;
+        ensureEdits(total); editTime.ensure(ctx, total + 1);
+        foreach(ctx, N, ListLinkKernel{1, lctx, listLinkTime.p, elemVisScan.p, objIdx.p, objStart.p, linkCount.p, linkBase.p, (u32)numLive, editOut.p, editElem.p, editObjKey.p, editElemPos.p, editTime.p, elemHasLive.p});
+        // order: surviving group records as they are, then the link edits by first-touch time; then stably by object
+        foreach(ctx, numLive, OffsetIotaKernel{sortVals.p, 0});
+        if (numLink > 1) {
+          DBuf<u64>& k2 = pairKey; DBuf<u32>& v2 = pairIdx; k2.ensure(ctx, numLink + 1); v2.ensure(ctx, numLink + 1);
+          foreach(ctx, numLink, EditTimeKeyAtKernel{editTime.p, (u32)numLive, k2.p, v2.p});
+          sortPairs(k2, v2, numLink, 32);
+          d2d(ctx, sortVals.p + numLive, v2.p, numLink * 4);
+        } else foreach(ctx, numLink, OffsetIotaKernel{sortVals.p + numLive, (u32)numLive});
+        foreach(ctx, total, GatherToU64Kernel{editObjKey.p, sortVals.p, sortKeys.p});
+        sortPairs(sortKeys, sortVals, total, bits_for(numObjs));
+        foreach(ctx, total, EditGatherKernel{editOut.p, editElem.p, nullptr, nullptr, sortVals.p, editOut2.p, editElem2.p, nullptr, nullptr});
+        std::swap(editOut.p, editOut2.p); std::swap(editOut.cap, editOut2.cap); std::swap(editElem.p, editElem2.p); std::swap(editElem.cap, editElem2.cap);
+      }
     }
+    numEdits = numLive + numLink;
   }
   if (wholeDoc && numEdits > 0) foreach(ctx, numEdits, RunFlagKernel{editOut.p, editElem.p, numEdits});
   out.numProps = numProps; out.numEdits = numEdits;

@@ -131,6 +131,11 @@ struct ObjPosKernel { const u32* perm; const u32* objRow; const u32* pos; u32* o
 struct SuccCntFromOffKernel { const u32* off; u32* cnt; HD void operator()(size_t p) const { cnt[p] = off[p + 1] - off[p]; } };
 struct EditKeyKernel { const u32* objKey; const EditRec* e; u64* key; u32* val; HD void operator()(size_t j) const { key[j] = objKey[j]; val[j] = (u32)j; } };
 struct EditTimeKeyKernel { const u32* t; u64* key; u32* val; HD void operator()(size_t j) const { key[j] = t[j]; val[j] = (u32)j; } };
-struct EditGatherKernel { const EditRec* in; const u64* elemIn; const u32* posIn; const u32* idx; EditRec* out; u64* elemOut; u32* posOut; HD void operator()(size_t j) const { out[j] = in[idx[j]]; elemOut[j] = elemIn[idx[j]]; posOut[j] = posIn[idx[j]]; } };
+struct EditGatherKernel {   // permutes the parallel edit arrays (posIn / keyIn may be null)
+  const EditRec* in; const u64* elemIn; const u32* posIn; const u32* keyIn; const u32* idx; EditRec* out; u64* elemOut; u32* posOut; u32* keyOut;
+  HD void operator()(size_t j) const { const u32 s = idx[j]; out[j] = in[s]; elemOut[j] = elemIn[s]; if (posIn) posOut[j] = posIn[s]; if (keyIn) keyOut[j] = keyIn[s]; }
+};
+struct OffsetIotaKernel { u32* val; u32 base; HD void operator()(size_t j) const { val[j] = base + (u32)j; } };
+struct EditTimeKeyAtKernel { const u32* t; u32 base; u64* key; u32* val; HD void operator()(size_t j) const { key[j] = t[base + j]; val[j] = base + (u32)j; } };
 
 }  // namespace amg

@@ -289,8 +289,8 @@ struct OldPairsKernel {   // old succ entries keep their row; re-key to the row'
 struct CountSuccKernel { const u32* pairPos; u32* cnt; HD void operator()(size_t q) const { atomic_add(&cnt[pairPos[q]], 1u); } };
 struct PairPosKeyKernel { const u32* pairPos; const u32* idx; u64* key; HD void operator()(size_t j) const { key[j] = pairPos[idx[j]]; } };
 struct WriteSuccKernel {   // pairs are sorted by (position, succ ord): write the CSR payload
-  const u32* idx; const u64* pairSucc; u64* succOut;
-  HD void operator()(size_t j) const { succOut[j] = pairSucc[idx[j]]; }
+  const u32* idx; const u64* pairSucc; u64* succOut; const u32* pairTime; u32* succTimeOut /* application time of the entry, 0 = before this call */;
+  HD void operator()(size_t j) const { succOut[j] = pairSucc[idx[j]]; succTimeOut[j] = pairTime[idx[j]]; }
 };
 // first deleter of each row during this call: min application time over new succ entries
 struct FirstSuccTimeKernel {

@@ -24,6 +24,7 @@ namespace amg {
 struct PropRec { u64 obj, opId; u32 keyOff, keyLen, valLen, valOff, flags /* action<<8 | 1 = empty key | 2 = counter: value is the int64 (pad:valOff) */, pad; };
 struct EditRec { u64 obj, opId; u32 index, kind /* 0 insert 1 remove 2 update | runStart<<8 | action<<16 */, valLen, valOff; };
 enum { EK_INSERT = 0, EK_REMOVE = 1, EK_UPDATE = 2 };
+enum { EF_POP = 0x400, EF_GROUP_FIRST = 0x800, EF_START = 0x100, EF_MULTI = 0x200, EF_COUNTER = 0x1000 /* value = int64 (valOff:valLen), not arena bytes */ };
 
 // ---------------------------------------------------------------- per-position state in document order
 struct GroupHeadKernel {   // group = rows of one map key / one list element (insert row + its update rows), adjacent in document order
@@ -50,8 +51,7 @@ struct GroupStatsKernel {   // group id = inclusive scan of heads - 1; counts ro
     atomic_add(&groupRows[g], 1u);
     if (succCnt[p] == 0) { atomic_add(&groupVisible[g], 1u); const u32 a = flags_action(d.flags[p]); if (a % 2 == 0 && a != ACT_DEL) groupHasChild[g] = 1; }
     if (head[p]) groupFirst[g] = (u32)p;
-    if (d.keyStrLen[p] == NULL32 && (flags_action(d.flags[p]) == ACT_INC || ((d.valLen[p] & 15) == 8 && flags_action(d.flags[p]) == ACT_SET && succCnt[p] > 0)))
-      raise(errWord, KE_UNSUPPORTED_OP, p);   // counters inside list elements (the reference itself leaves them half done, new.js:965)
+
   }
 };
 
@@ -71,7 +71,7 @@ struct TouchKernel {   // new rows and the targets of new succ entries touch the
 // list parent can be ordered the same way. A list element that already carries edits of this call needs no link edit.
 struct LinkKernel {
   DocRows d; const u32* groupOf; const u32* groupHasChild; const u32* groupFirst; const u32* objPos; u32* groupLinked; u32* objTouchedAt; u32* rootTouched; u32* linkDone; u32* changed;
-  const u32* elemHasRecs /* per position of an element's insert row */; u32* listLinkTime /* same indexing; 0xffffffff = none */; u32* anyListLink;
+  u32* listLinkTime /* per position of an element's insert row; 0xffffffff = none */; u32* anyListLink;
   HD void operator()(size_t p) const {
     const u32 t = objTouchedAt[p];
     if (t == 0xffffffffu || linkDone[p] == t) return;
@@ -84,7 +84,7 @@ struct LinkKernel {
     if (groupHasChild[g] == 0) return;
     if (d.keyStrLen[p] == NULL32) {     // child object inside a list: an update edit per visible value unless the element has edits already
       const u32 e = groupFirst[g];
-      if (!elemHasRecs[e]) { atomic_min(&listLinkTime[e], t); *anyListLink = 1; }
+      atomic_min(&listLinkTime[e], t); *anyListLink = 1;   // whether an edit is really needed is known once the pops are replayed (elemHasLive)
     } else groupLinked[g] = 1;
     if (objPos[p] == ROW_NONE) *rootTouched = 1; else atomic_min(&objTouchedAt[objPos[p]], t);
   }
@@ -177,14 +177,14 @@ struct GroupFinalKernel {   // pass 0: finalTime[g] = latest group on key group 
 // summed value once every successor turned out to be an `inc`; the reference emits it while processing the last of them.
 struct CounterKernel {
   const u8* arena; DocRows d; const u32* succOff; const u64* succ; const u32* groupOf; const u32* groupFirst; const u32* groupRows;
-  u32* counterLast /* position of the last inc row, ROW_NONE = not a visible counter */; u64* counterTotal;
+  u32* counterLast /* position of the last inc row, ROW_NONE = not a visible counter */; u64* counterTotal; u32* counterOwner /* per inc row that completes a counter: the counter's row */;
   HD long long valueOf(u32 r) const {
     ByteReader br(arena, d.valOff[r], d.valOff[r] + (d.valLen[r] >> 4));
     return (d.valLen[r] & 15) == 3 ? (long long)br.uleb() : br.sleb();
   }
   HD void operator()(size_t p) const {
     counterLast[p] = ROW_NONE;
-    if (d.keyStrLen[p] == NULL32 || flags_action(d.flags[p]) != ACT_SET || (d.valLen[p] & 15) != 8) return;
+    if (flags_action(d.flags[p]) != ACT_SET || (d.valLen[p] & 15) != 8) return;
     const u32 s0 = succOff[p], s1 = succOff[p + 1]; if (s0 == s1) return;
     const u32 g = groupOf[p], gf = groupFirst[g], rows = groupRows[g];
     long long total = valueOf((u32)p); u32 last = 0;
@@ -194,7 +194,7 @@ struct CounterKernel {
       if (r == ROW_NONE || flags_action(d.flags[r]) != ACT_INC) return;   // deleted or overwritten: the counter is gone
       total += valueOf(r); if (r > last) last = r;
     }
-    counterLast[p] = last; counterTotal[p] = (u64)total;
+    counterLast[p] = last; counterTotal[p] = (u64)total; counterOwner[last] = (u32)p;
   }
 };
 struct PropFlagKernel {   // which positions emit a prop record
@@ -237,12 +237,33 @@ struct PropEmitKernel {
 };
 
 // ---------------------------------------------------------------- whole-document list edits (getPatch)
-struct ListVisFlagKernel {   // element visible (any visible row) flagged on the group head; visible rows flagged individually
+// Whole-document list edits (documentPatch, new.js:1604-1635, through updatePatchProperty with isWholeDoc): a row that
+// carries a value (pv: visible set / make*, or the increment that completes a counter) inserts the element if it is
+// the first event of the element, otherwise updates it. A visible row WITHOUT a value (an `inc` that does not complete
+// its counter: deleted counter, or one of several increments) registers a `remove` when it comes first; a later value
+// undoes it and is then reported as an update; with no later value the remove stays (reference behaviour, new.js:965 TODO).
+struct ListRowClassKernel {
+  DocRows d; const u32* groupOf; const u32* succCnt; const u32* counterOwner; u32* rowClass /* 0 nothing, 1 value, 2 visible without value */; u32* firstPv; u32* firstBare;
+  HD void operator()(size_t p) const {
+    u32 c = 0;
+    if (d.keyStrLen[p] == NULL32) {
+      const u32 a = flags_action(d.flags[p]);
+      if (counterOwner[p] != ROW_NONE || (succCnt[p] == 0 && (a == ACT_SET || (a % 2 == 0 && a != ACT_DEL)))) c = 1;
+      else if (succCnt[p] == 0) c = 2;
+      if (c == 1) atomic_min(&firstPv[groupOf[p]], (u32)p); else if (c == 2) atomic_min(&firstBare[groupOf[p]], (u32)p);
+    }
+    rowClass[p] = c;
+  }
+};
+struct ListVisFlagKernel {   // element visible (any visible row) flagged on the group head; emitting rows flagged individually
   DocRows d; const u32* groupOf; const u32* groupVisible; const u32* head; const u32* succCnt; u32* elemVis; u32* rowEmit;
+  const u32* rowClass; const u32* firstPv; const u32* firstBare;   // null: link mode (plain visible rows only)
   HD void operator()(size_t p) const {
     const bool list = d.keyStrLen[p] == NULL32;
-    elemVis[p] = (list && head[p] && groupVisible[groupOf[p]] > 0) ? 1u : 0u;
-    rowEmit[p] = (list && succCnt[p] == 0) ? 1u : 0u;
+    elemVis[p] = (list && head[p] && groupVisible[groupOf[p]] > 0) ? 1u : 0u;   // an `inc` row counts as visible here, as in the reference (new.js:1622-1626)
+    if (!rowClass) { rowEmit[p] = (list && succCnt[p] == 0) ? 1u : 0u; return; }
+    const u32 g = groupOf[p];
+    rowEmit[p] = (rowClass[p] == 1 || (rowClass[p] == 2 && firstBare[g] == (u32)p && firstPv[g] == 0xffffffffu)) ? 1u : 0u;
   }
 };
 struct ObjHeadKernel { DocRows d; u32* isObjHead; HD void operator()(size_t p) const { isObjHead[p] = (p == 0 || d.obj[p] != d.obj[p - 1]) ? 1u : 0u; } };
@@ -255,18 +276,21 @@ struct ObjStartKernel {   // objIdx = exclusive scan of heads (+head-1 fix-up); 
 };
 struct DocEditEmitKernel {   // getPatch: visible rows of list objects in document order
   DocRows d; const u32* rowEmit; const u32* slot; const u32* elemVisScan /* exclusive */; const u32* objIdx; const u32* objStart;
-  const u32* groupOf; const u32* groupFirst; const u32* succCnt; const u32* firstVisInGroup /* per group: first visible position */; EditRec* out;
+  const u32* groupOf; const u32* groupFirst; const u32* rowClass; const u32* firstPv; const u32* firstBare; EditRec* out;
+  const u32* counterOwner; const u64* counterTotal;
   HD void operator()(size_t p) const {
     if (!rowEmit[p]) return;
     const u32 g = groupOf[p]; const u32 gp = groupFirst[g];
-    EditRec e; e.obj = d.obj[p]; e.opId = d.id[p];
+    const u32 src = counterOwner[p] != ROW_NONE ? counterOwner[p] : (u32)p;
+    EditRec e; e.obj = d.obj[src]; e.opId = d.id[src];
     e.index = elemVisScan[gp] - elemVisScan[objStart[objIdx[p]]];
-    const u32 kind = (firstVisInGroup[g] == (u32)p) ? EK_INSERT : EK_UPDATE;
-    e.kind = kind | (flags_action(d.flags[p]) << 16); e.valLen = d.valLen[p]; e.valOff = d.valOff[p];
+    if (rowClass[p] == 2) { e.kind = (u32)EK_REMOVE | (ACT_DEL << 16); e.valLen = 0; e.valOff = 0; out[slot[p]] = e; return; }
+    const u32 kind = (firstPv[g] == (u32)p && !(firstBare[g] < (u32)p)) ? EK_INSERT : EK_UPDATE;
+    e.kind = kind | (flags_action(d.flags[src]) << 16); e.valLen = d.valLen[src]; e.valOff = d.valOff[src];
+    if (src != (u32)p) { e.kind |= EF_COUNTER; e.valLen = (u32)counterTotal[src]; e.valOff = (u32)(counterTotal[src] >> 32); }
     out[slot[p]] = e;
   }
 };
-struct FirstVisKernel { const u32* groupOf; const u32* succCnt; u32* firstVisInGroup; HD void operator()(size_t p) const { if (succCnt[p] == 0) atomic_min(&firstVisInGroup[groupOf[p]], (u32)p); } };
 // elemId of an edit = id of the group's insert row (needed for insert edits whose opId differs, i.e. conflicts)
 struct EditElemKernel { DocRows d; const u32* rowEmit; const u32* slot; const u32* groupOf; const u32* groupFirst; u64* elemOut; HD void operator()(size_t p) const { if (rowEmit[p]) elemOut[slot[p]] = d.id[groupFirst[groupOf[p]]]; } };
 
@@ -283,7 +307,42 @@ HD bool dom_query(u32 tw) { return (tw >> 29) & 1u; }
 // minSucc(p) (0 = before this call, 0xffffffff = never). The element whose insert row sits at e owns rows [e, e+rows).
 struct ListCtx {
   DocRows d; const u32* succCnt; const u32* newSuccCnt; const u32* firstNewSucc; const u32* groupOf; const u32* groupFirst; const u32* groupRows;
+  const u8* arena; const u32* succOff; const u64* succ; const u32* succTime;   // successors of every row with their application times (0 = before this call)
   HD u32 minSucc(u32 p) const { return succCnt[p] > newSuccCnt[p] ? 0u : firstNewSucc[p]; }
+  HD long long valueOf(u32 r) const { ByteReader br(arena, d.valOff[r], d.valOff[r] + (d.valLen[r] >> 4)); return (d.valLen[r] & 15) == 3 ? (long long)br.uleb() : br.sleb(); }
+  HD bool isCounterRow(u32 r) const { return flags_action(d.flags[r]) == ACT_SET && (d.valLen[r] & 15) == 8; }
+  // Counter row c of the element [e, e + rows) at time T: true if it has increments by then and nothing else overwrote it;
+  // *total = summed value, *lastInc = position of the latest of those increments (new.js:941-966).
+  HD bool counterAt(u32 e, u32 rows, u32 c, u32 T, long long* total, u32* lastInc) const {
+    long long sum = valueOf(c); u32 last = ROW_NONE;
+    for (u32 s = succOff[c]; s < succOff[c + 1]; s++) {
+      if (succTime[s] > T) continue;
+      u32 q = ROW_NONE;
+      for (u32 r = e; r < e + rows; r++) if (d.id[r] == succ[s]) { q = r; break; }
+      if (q == ROW_NONE || flags_action(d.flags[q]) != ACT_INC) return false;
+      sum += valueOf(q); if (last == ROW_NONE || q > last) last = q;
+    }
+    if (last == ROW_NONE) return false;
+    *total = sum; *lastInc = last; return true;
+  }
+  // What the element shows at position q at time T: 1 = the row's own value, 2 = a counter completed by the increment
+  // sitting at q (*owner = the counter's row), 0 = nothing
+  HD int shownAt(u32 e, u32 rows, u32 q, u32 T, u32* owner, long long* total) const {
+    if (d.time[q] > T) return 0;
+    const u32 a = flags_action(d.flags[q]);
+    if (a == ACT_INC) {
+      for (u32 c = e; c < q; c++) {
+        if (!isCounterRow(c) || d.time[c] > T) continue;
+        bool mine = false; for (u32 s = succOff[c]; s < succOff[c + 1] && !mine; s++) mine = succ[s] == d.id[q];
+        if (!mine) continue;
+        u32 last; if (counterAt(e, rows, c, T, total, &last) && last == q) { *owner = c; return 2; }
+        return 0;
+      }
+      return 0;
+    }
+    if (minSucc(q) > T && (a == ACT_SET || (a % 2 == 0 && a != ACT_DEL))) return 1;
+    return 0;
+  }
   HD bool visAt(u32 e, u32 rows, u32 T) const {   // some row of the element is present and not overwritten after the op at time T
     for (u32 r = e; r < e + rows; r++) if (d.time[r] <= T && minSucc(r) > T) return true;
     return false;
@@ -349,13 +408,12 @@ struct DomResultKernel {   // route query results back by group start time
 // visible just after it, updatePatchProperty's state machine (new.js:985-1030) nets out to:
 //   V empty: remove if W.   V non-empty, W: update per V row, the first popping earlier edits of the same index
 //   (appendUpdate, new.js:798-825).   V non-empty, not W: insert of V[0] then updates.
-enum { EF_POP = 0x400, EF_GROUP_FIRST = 0x800, EF_START = 0x100, EF_MULTI = 0x200 };
 struct ListGroupKernel {
   int pass; MapGroupCtx c; const u32* groupHead; IdTable t; const u32* rowOfOp; const u32* pos; ListCtx L;
   u32* gCount; u32* gElem; u32* gT1; u32* gQOrd; u32* nQ; u32* elemHasRecs;                     // pass 0 out (gT1: T1 | (net weight + 1) << 29 | W << 31)
   const u32* itemBase; const u32* objIdx; const u32* objStart; DomItem* items; u32* twArr; int* wArr; const u32* oldVisScan;   // pass 1: items
   const u32* runHeadFlag; const u32* runScan; const u32* runStart;   // typing runs (FollowerFlagKernel)
-  const u32* gBase; const u32* qIndex; EditRec* out; u64* elemOut; u32* objKeyOut; u32* elemPosOut; u64* errWord;   // pass 2: records
+  const u32* gBase; const u32* qIndex; EditRec* out; u64* elemOut; u32* objKeyOut; u32* elemPosOut; u32* rowPosOut; u64* errWord;   // pass 2: records
   HD static bool shown(u32 flags) { const u32 a = flags_action(flags); return a == ACT_SET || (a % 2 == 0 && a != ACT_DEL); }
   HD void operator()(size_t t0) const {
     const u32 i0 = c.opAt[t0];
@@ -373,9 +431,8 @@ struct ListGroupKernel {
           for (u32 r = e; r < e + rows; r++) {
             const u32 s = L.d.time[r], x = L.minSucc(r);
             if (s < T0 && x >= T0) W = true;
-            if (s <= T1 && x > T1 && shown(L.d.flags[r])) nV++;
-            const u32 a = flags_action(L.d.flags[r]);
-            if (a == ACT_INC || (a == ACT_SET && (L.d.valLen[r] & 15) == 8 && L.succCnt[r] > 0)) raise(errWord, KE_UNSUPPORTED_OP, r);   // counters inside lists
+            u32 owner; long long total;
+            if (L.shownAt(e, rows, r, T1, &owner, &total)) nV++;
           }
           n = nV ? nV : (W ? 1u : 0u);
           const int wNet = (int)L.visAt(e, rows, T1) - (int)L.visAt(e, rows, T0 - 1);
@@ -421,31 +478,34 @@ struct ListGroupKernel {
       }
     }
     u32 k = gBase[t0], nV = 0;
-    for (u32 r = e; r < e + rows; r++) {
-      if (!(L.d.time[r] <= T1 && L.minSucc(r) > T1 && shown(L.d.flags[r]))) continue;
-      EditRec rec; rec.obj = L.d.obj[r]; rec.opId = L.d.id[r]; rec.index = r == e ? headIdx : idx; rec.valLen = L.d.valLen[r]; rec.valOff = L.d.valOff[r];
+    for (u32 q = e; q < e + rows; q++) {
+      u32 owner = 0; long long total = 0; const int what = L.shownAt(e, rows, q, T1, &owner, &total);
+      if (!what) continue;
+      const u32 r = what == 2 ? owner : q;
+      EditRec rec; rec.obj = L.d.obj[r]; rec.opId = L.d.id[r]; rec.index = q == e ? headIdx : idx; rec.valLen = L.d.valLen[r]; rec.valOff = L.d.valOff[r];
       rec.kind = (nV == 0 ? (W ? (u32)EK_UPDATE | EF_POP : (u32)EK_INSERT) | EF_GROUP_FIRST : (u32)EK_UPDATE) | (flags_action(L.d.flags[r]) << 16);
-      out[k] = rec; elemOut[k] = L.d.id[e]; objKeyOut[k] = objIdx[e]; elemPosOut[k] = e; k++; nV++;
+      if (what == 2) { rec.kind |= EF_COUNTER; rec.valLen = (u32)(u64)total; rec.valOff = (u32)((u64)total >> 32); }
+      out[k] = rec; elemOut[k] = L.d.id[e]; objKeyOut[k] = objIdx[e]; elemPosOut[k] = e; rowPosOut[k] = r; k++; nV++;
     }
     if (nV == 0) {
       const bool atHead = L.d.time[e] < T0 && L.minSucc(e) >= T0;   // the remove is registered at the first previously visible row
       EditRec rec; rec.obj = L.d.obj[e]; rec.opId = c.ops.id[i0]; rec.index = atHead ? headIdx : idx; rec.valLen = 0; rec.valOff = 0; rec.kind = (u32)EK_REMOVE | EF_GROUP_FIRST | (ACT_DEL << 16);
-      out[k] = rec; elemOut[k] = 0; objKeyOut[k] = objIdx[e]; elemPosOut[k] = e;
+      out[k] = rec; elemOut[k] = 0; objKeyOut[k] = objIdx[e]; elemPosOut[k] = e; rowPosOut[k] = e;
     }
   }
 };
 // setupPatches link edits on list parents: an update per visible value of the element, at its index after the call
 struct ListLinkKernel {
   int pass; ListCtx L; const u32* listLinkTime; const u32* elemVisScan; const u32* objIdx; const u32* objStart; u32* count; const u32* base; u32 recBase;
-  EditRec* out; u64* elemOut; u32* objKeyOut; u32* elemPosOut; u32* timeOut;
+  EditRec* out; u64* elemOut; u32* objKeyOut; u32* elemPosOut; u32* timeOut; const u32* elemHasLive /* the element already shows in a surviving edit (patchExists, new.js:1472-1476) */;
   HD void operator()(size_t p) const {
-    if (listLinkTime[p] == 0xffffffffu) { if (pass == 0) count[p] = 0; return; }
+    if (listLinkTime[p] == 0xffffffffu || elemHasLive[p]) { if (pass == 0) count[p] = 0; return; }
     const u32 e = (u32)p, rows = L.groupRows[L.groupOf[e]]; u32 n = 0, k = pass ? recBase + base[p] : 0;
     for (u32 r = e; r < e + rows; r++) {
       if (L.succCnt[r] != 0 || !ListGroupKernel::shown(L.d.flags[r])) continue;
       if (pass == 1) {
         EditRec rec; rec.obj = L.d.obj[r]; rec.opId = L.d.id[r]; rec.index = elemVisScan[e] - elemVisScan[objStart[objIdx[e]]]; rec.valLen = L.d.valLen[r]; rec.valOff = L.d.valOff[r];
-        rec.kind = (u32)EK_UPDATE | (n == 0 ? (u32)EF_GROUP_FIRST : 0u) | (flags_action(L.d.flags[r]) << 16);
+        rec.kind = (u32)EK_UPDATE | (u32)EF_START | (flags_action(L.d.flags[r]) << 16);   // appended after everything else: never popped, never merged
         out[k] = rec; elemOut[k] = L.d.id[e]; objKeyOut[k] = objIdx[e]; elemPosOut[k] = e; timeOut[k] = 0x80000000u | listLinkTime[p]; k++;
       }
       n++;
@@ -477,7 +537,7 @@ struct EditFixKernel {
 // appendEdit coalescing (new.js:747-782) against the record that was last in the list when this one was appended
 struct EditMergeKernel {
   const EditRec* edits; const u64* elem; const u32* newKind; const u32* pred; u32* mergePrev; u32* multi;
-  HD u32 cls(u32 valLen) const { const u32 t = valLen & 15; return t == 2 ? 1 : t; }
+  HD u32 cls(const EditRec& r) const { if (r.kind & EF_COUNTER) return 8; const u32 t = r.valLen & 15; return t == 2 ? 1 : t; }   // datatype + typeof of the value (new.js:759-760)
   HD void operator()(size_t j) const {
     bool cont = false; const u32 i = pred[j];
     if (i != ROW_NONE) {
@@ -486,7 +546,7 @@ struct EditMergeKernel {
         if (ka == EK_INSERT && kb == EK_INSERT) {
           const u32 actA = (a.kind >> 16) & 0xffff, actB = (b.kind >> 16) & 0xffff;
           cont = b.index == a.index + 1 && actA == ACT_SET && actB == ACT_SET && elem[i] == a.opId && elem[j] == b.opId &&
-                 id_actor(a.opId) == id_actor(b.opId) && id_ctr(a.opId) + 1 == id_ctr(b.opId) && cls(a.valLen) == cls(b.valLen);
+                 id_actor(a.opId) == id_actor(b.opId) && id_ctr(a.opId) + 1 == id_ctr(b.opId) && cls(a) == cls(b);
           if (cont) { multi[i] = 1; multi[j] = 1; }
         } else if (ka == EK_REMOVE && kb == EK_REMOVE) cont = a.index == b.index;
       }
@@ -495,22 +555,29 @@ struct EditMergeKernel {
   }
 };
 struct EditLiveKernel {   // also: does any surviving insert carry an elemId different from its opId? (otherwise the elemId section is not shipped)
-  const u32* dead; u32* live; const EditRec* edits; const u64* elem; const u32* newKind; u32* needElem;
-  HD void operator()(size_t j) const { live[j] = dead[j] ? 0u : 1u; if (!dead[j] && newKind[j] == EK_INSERT && elem[j] != edits[j].opId) *needElem = 1; }
+  const u32* dead; u32* live; const EditRec* edits; const u64* elem; const u32* newKind; u32* needElem; const u32* elemPos; u32* elemHasLive;
+  const u32* rowPos; const u32* succCnt; const u32* counterLast;
+  HD void operator()(size_t j) const {
+    live[j] = dead[j] ? 0u : 1u;
+    if (dead[j]) return;
+    if (newKind[j] == EK_INSERT && elem[j] != edits[j].opId) *needElem = 1;
+    // setupPatches looks for an edit whose opId is one of the element's CURRENT values (new.js:1472-1476)
+    if (newKind[j] != EK_REMOVE && (succCnt[rowPos[j]] == 0 || counterLast[rowPos[j]] != ROW_NONE)) elemHasLive[elemPos[j]] = 1;
+  }
 };
 struct EditCompactKernel {
-  const EditRec* in; const u64* elemIn; const u32* dead; const u32* slot; const u32* newKind; const u32* mergePrev; const u32* multi; EditRec* out; u64* elemOut;
+  const EditRec* in; const u64* elemIn; const u32* dead; const u32* slot; const u32* newKind; const u32* mergePrev; const u32* multi; EditRec* out; u64* elemOut; const u32* objKeyIn; u32* objKeyOut;
   HD void operator()(size_t j) const {
     if (dead[j]) return;
     EditRec r = in[j];
-    r.kind = newKind[j] | (r.kind & 0xffff0000u) | (mergePrev[j] ? 0u : (u32)EF_START) | (multi[j] ? (u32)EF_MULTI : 0u);
-    out[slot[j]] = r; elemOut[slot[j]] = elemIn[j];
+    r.kind = newKind[j] | (r.kind & (0xffff0000u | EF_COUNTER)) | (mergePrev[j] ? 0u : (u32)EF_START) | (multi[j] ? (u32)EF_MULTI : 0u);
+    out[slot[j]] = r; elemOut[slot[j]] = elemIn[j]; objKeyOut[slot[j]] = objKeyIn[j];
   }
 };
 // getPatch: runs over the document-ordered edit list (nothing is ever popped there)
 struct RunFlagKernel {
   EditRec* edits; const u64* elem; size_t n;
-  HD u32 cls(u32 valLen) const { const u32 t = valLen & 15; return t == 2 ? 1 : t; }
+  HD u32 cls(const EditRec& r) const { if (r.kind & EF_COUNTER) return 8; const u32 t = r.valLen & 15; return t == 2 ? 1 : t; }   // datatype + typeof of the value (new.js:759-760)
   HD bool cont(size_t j) const {
     if (j == 0 || j >= n) return false;
     const EditRec a = edits[j - 1], b = edits[j]; const u32 ka = a.kind & 0xff, kb = b.kind & 0xff;
@@ -518,7 +585,7 @@ struct RunFlagKernel {
     if (ka == EK_INSERT && kb == EK_INSERT) {
       const u32 actA = (a.kind >> 16) & 0xffff, actB = (b.kind >> 16) & 0xffff;
       return b.index == a.index + 1 && actA == ACT_SET && actB == ACT_SET && elem[j - 1] == a.opId && elem[j] == b.opId &&
-             id_actor(a.opId) == id_actor(b.opId) && id_ctr(a.opId) + 1 == id_ctr(b.opId) && cls(a.valLen) == cls(b.valLen);
+             id_actor(a.opId) == id_actor(b.opId) && id_ctr(a.opId) + 1 == id_ctr(b.opId) && cls(a) == cls(b);
     }
     return ka == EK_REMOVE && kb == EK_REMOVE && a.index == b.index;
   }

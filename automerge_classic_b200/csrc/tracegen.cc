@@ -8,6 +8,7 @@
 //   C3  makeText + A actors x n/A single-op changes, 70 % insert / 30 % delete, merge every 100 changes
 //   C4  nested maps: A actors x rounds x 100-op `set` changes, Zipf keys, Lamport-conflict heavy
 //   C7  counters in root keys: create / increment / overwrite / delete, concurrent writers
+//   C8  C6 plus counter elements: inserted counters, concurrent increments, overwrites and deletes of them
 //   C6  one list of scalars and map objects: inserts, element updates / conflicts / deletes, keys set inside element maps
 // Seeded SplitMix64; actor k = first 16 bytes of SHA-256("amgpu-actor-" || seed || k).
 // The oracle (tests) decodes and re-applies these bytes, which cross-checks this independent encoder.
@@ -269,13 +270,13 @@ void genC4(Trace& t, uint64_t seed, uint64_t nOps, int A, int nChild, int nKeysP
 // C6: one list of mixed elements: scalar inserts, inserted map objects with keys set inside them, value updates and
 // concurrent conflicting updates of existing elements, conflict-adding sets (empty pred), deletes, several ops of one
 // change on the same element. Every actor works on the state of the round start (so same-round writers conflict).
-void genRichList(Trace& t, uint64_t seed, uint64_t nOps, int A, int maxOpsPerChange) {
+void genRichList(Trace& t, uint64_t seed, uint64_t nOps, int A, int maxOpsPerChange, bool withCounters = false) {
   Rng rng{seed}; std::vector<Actor> actors = makeActors(seed, A); Encoder enc{&actors};
   std::vector<uint64_t> seq(A, 0); std::vector<Hash> lastHash(A); std::vector<bool> hasHash(A, false);
   OpId list{1, 0};
   { Op mk; mk.action = 2; mk.isMapKey = true; mk.key = "items"; Hash h; t.add(enc.encode(0, ++seq[0], 1, {}, {mk}, &h), 1); lastHash[0] = h; hasHash[0] = true; }
   uint64_t maxOp = 1, produced = 0;
-  struct Row { OpId id; bool isMap; };
+  struct Row { OpId id; bool isMap; bool isCounter = false; };
   struct Elem { OpId id; std::vector<Row> vis; };
   std::vector<Elem> elems; std::unordered_map<uint64_t, size_t> elemAt;
   std::unordered_map<uint64_t, std::vector<OpId>> mapKeyVis;   // (map object key * 8 + key index) -> visible set rows
@@ -296,6 +297,19 @@ void genRichList(Trace& t, uint64_t seed, uint64_t nOps, int A, int maxOpsPerCha
         const uint64_t ctr = base + 1 + ops.size(); const OpId me{ctr, a}; const double u = rng.unit(); Op op; op.obj = list;
         size_t e = elems.empty() ? 0 : (size_t)rng.below(elems.size());
         if (lastTouched >= 0 && rng.unit() < 0.25) e = (size_t)lastTouched;   // several ops of one change on the same element
+        if (withCounters && !elems.empty() && rng.unit() < 0.22) {   // counters (C8): insert one, or increment a visible one
+          std::vector<Row>& v = visOf(e); const Row* cnt = nullptr; for (auto& r : v) if (r.isCounter) cnt = &r;
+          if (cnt && rng.unit() < 0.7) {
+            op.action = 5; op.elem = elems[e].id; op.hasValue = true; const bool neg = rng.unit() < 0.3; op.valTag = neg ? 4 : 3;
+            if (neg) sleb(op.valRaw, -(int64_t)rng.below(20)); else uleb(op.valRaw, rng.below(100));
+            op.pred = {cnt->id}; lastTouched = (long)e; ops.push_back(op);
+          } else {
+            op.action = 1; op.insert = true; op.hasValue = true; op.valTag = 8; sleb(op.valRaw, (int64_t)rng.below(50));
+            op.elem = rng.unit() < 0.5 ? lastIns : elems[e].id;
+            Row nr{me, false}; nr.isCounter = true; P.newElems.push_back(Elem{me, {nr}}); lastIns = me; ops.push_back(op);
+          }
+          continue;
+        }
         if (elems.empty() || u < 0.35) {            // insert a scalar
           op.action = 1; op.insert = true; intValue(op);
           const double w = rng.unit(); op.elem = w < 0.6 ? lastIns : (w < 0.95 && !elems.empty() ? elems[rng.below(elems.size())].id : OpId{0, 0});
@@ -394,7 +408,7 @@ void genCounters(Trace& t, uint64_t seed, uint64_t nOps, int A, int nKeys, int m
 }  // namespace
 
 extern "C" {
-// config: 1 = C1, 2 = C2, 22 = C2b (bulk), 3 = C3, 4 = C4, 6 = C6 (rich list), 7 = C7 (counters). Returns malloc'ed blob + offsets (n_changes + 1).
+// config: 1 = C1, 2 = C2, 22 = C2b (bulk), 3 = C3, 4 = C4, 6 = C6 (rich list), 7 = C7 (counters), 8 = C8 (rich list with counter elements). Returns malloc'ed blob + offsets (n_changes + 1).
 int amg_trace_generate(int config, uint64_t seed, uint64_t n_ops, int n_actors, uint8_t** blob, size_t* blob_len, uint64_t** offsets, size_t* n_changes, uint64_t* total_ops) {
   Trace t;
   if (config == 1) genC1(t, seed);
@@ -403,6 +417,7 @@ int amg_trace_generate(int config, uint64_t seed, uint64_t n_ops, int n_actors, 
   else if (config == 3) genText(t, seed, n_ops, n_actors > 0 ? n_actors : 10, false, 0.3, 100);
   else if (config == 4) genC4(t, seed, n_ops, n_actors > 0 ? n_actors : 100, 100, 100, 100);
   else if (config == 7) genCounters(t, seed, n_ops, n_actors > 0 ? n_actors : 3, 6, 5);
+  else if (config == 8) genRichList(t, seed, n_ops, n_actors > 0 ? n_actors : 3, 6, true);
   else if (config == 6) genRichList(t, seed, n_ops, n_actors > 0 ? n_actors : 4, 6);
   else return 1;
   *blob = (uint8_t*)malloc(t.blob.size() + 64); memcpy(*blob, t.blob.data(), t.blob.size()); memset(*blob + t.blob.size(), 0, 64); *blob_len = t.blob.size();

@@ -213,7 +213,11 @@ class FlatPatch:
                 else:
                     edits[-1]['count'] += 1
                 continue
-            if action == 1:
+            if action == 1 and int(rec['kind']) & 0x1000:   # counter with increments: the engine summed them (new.js:941-966)
+                total = int(rec['valLen']) | (int(rec['valOff']) << 32)
+                total -= (1 << 64) if total >= (1 << 63) else 0
+                value = {'type': 'value', 'value': total, 'datatype': 'counter'}
+            elif action == 1:
                 vl, vo = int(rec['valLen']), int(rec['valOff'])
                 value = decode_value(vl, arena[vo:vo + (vl >> 4)])
             elif action % 2 == 0:

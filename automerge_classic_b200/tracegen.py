@@ -6,7 +6,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
-CONFIGS = {'C1': 1, 'C2': 2, 'C2b': 22, 'C3': 3, 'C4': 4, 'C6': 6, 'C7': 7}
+CONFIGS = {'C1': 1, 'C2': 2, 'C2b': 22, 'C3': 3, 'C4': 4, 'C6': 6, 'C7': 7, 'C8': 8}
 SEED = 0xA17E0C1A551C
 
 

@@ -96,6 +96,7 @@ void amg_buffers_free(amg_buffers* l);
  * props.flags = action << 8 | 1 if the key has no visible value (reference emits `key: {}`);
  * edits.kind = (0 insert | 1 remove | 2 update) | 0x100 if the edit starts a new run (edits without the bit
  * continue the previous insert as `multi-insert` / add to the previous remove's count, new.js:747-782)
+ * | 0x1000 for a counter whose increments were summed: its value is the int64 (valOff << 32 | valLen)
  * | 0x200 if the insert is rendered as `multi-insert` (set on every member of a run, and on a run start whose
  * followers were popped again by appendUpdate, new.js:811-813) | action << 16.
  * The nested Patch object of @types/automerge/index.d.ts:236-316 is assembled from this by the binding. */

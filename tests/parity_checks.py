@@ -41,13 +41,14 @@ def check_trace_parity(gpu_doc, oracle_mod, cfg, n, a):
     _dump_equal(g, orc)
 
 
-def check_rich_list(gpu_doc, oracle_mod, seed, n, a, chunk):
-    """Config C6 (list of scalars and map objects; element updates, conflicts, deletes, re-insertions, nested keys),
+def check_rich_list(gpu_doc, oracle_mod, seed, n, a, chunk, cfg='C6'):
+    """Config C6 / C8 (C8 adds counter elements: inserted counters, increments, overwrites and deletes of them)
+    Config C6 (list of scalars and map objects; element updates, conflicts, deletes, re-insertions, nested keys),
     applied in calls of `chunk` changes: every incremental patch, the final getPatch and the op table equal the oracle's.
     Returns False when the oracle reports that the reference itself would not terminate on the trace (block-boundary
     bug of seekWithinBlock's resumeInsertion path, see oracle/backend.hpp) - there is nothing to compare against then."""
     from automerge_classic_b200 import tracegen
-    ch = tracegen.generate('C6', n, a, seed=seed).changes()
+    ch = tracegen.generate(cfg, n, a, seed=seed).changes()
     orc, g = oracle_mod.OracleDoc(), gpu_doc()
     for lo in range(0, len(ch), chunk):
         try:

@@ -75,6 +75,12 @@ def test_save_after_load_emu(emu_doc, oracle_mod, cfg, n, a):
     parity_checks.check_save_after_load(emu_doc, oracle_mod, cfg, n, a)
 
 
+@pytest.mark.parametrize('n,a,chunk', [(80, 2, 1000), (300, 3, 5), (400, 4, 40), (200, 1, 1)])
+def test_list_counters_emu(emu_doc, oracle_mod, n, a, chunk):
+    compared = sum(parity_checks.check_rich_list(emu_doc, oracle_mod, seed, n, a, chunk, cfg='C8') for seed in range(1, 9))
+    assert compared >= 5
+
+
 def test_incremental_calls_emu(emu_doc, oracle_mod):
     parity_checks.check_incremental_calls(emu_doc, oracle_mod)
 
