@@ -303,6 +303,7 @@ HD u64 rle_sum_values(const u8* arena, u32 off, u32 end, u32 limit, u32* err) {
 struct ParseKernel {
   const u8* arena; const u32* chOff; const u32* chLen; size_t numChanges;
   ChangeMeta* meta; u32* colOff /* [NCOLS][numChanges] */; u32* colLen; u32* nOpsOut; u32* nPredsOut; u32* nDepsOut; u32* nActorsOut; u64* errWord;
+  u32* anyLarge /* set when some change has more than SMALL_CHANGE_OPS ops (else the large-change path is skipped entirely) */;
   HD void operator()(size_t c) const { (*this)(c, this->arena); }
   HD void operator()(size_t c, const u8* arena) const {   // `arena` may be the block's shared-memory copy (foreach_staged)
     const u32 off = chOff[c], len = chLen[c];
@@ -311,10 +312,10 @@ struct ParseKernel {
     ByteReader r(arena, off + 8, off + len);
     const u32 chunkType = r.done() ? 0xff : arena[r.pos]; r.pos++;
     const u64 chunkLen = r.uleb();
-    if (r.err) { raise(errWord, r.err, c); meta[c] = m; return; }
-    if ((u64)r.pos + chunkLen > (u64)off + len) { raise(errWord, KE_TRUNCATED, c); meta[c] = m; return; }
-    if ((u64)r.pos + chunkLen != (u64)off + len) { raise(errWord, KE_TRAILING, c); meta[c] = m; return; }
-    if (chunkType != 1) { raise(errWord, KE_CHUNK_TYPE, c); meta[c] = m; return; }
+    if (r.err) { raise(errWord, r.err, c); m.nDeps = 0; m.nOther = 0; m.nOps = 0; m.nPreds = 0; meta[c] = m; return; }
+    if ((u64)r.pos + chunkLen > (u64)off + len) { raise(errWord, KE_TRUNCATED, c); m.nDeps = 0; m.nOther = 0; m.nOps = 0; m.nPreds = 0; meta[c] = m; return; }
+    if ((u64)r.pos + chunkLen != (u64)off + len) { raise(errWord, KE_TRAILING, c); m.nDeps = 0; m.nOther = 0; m.nOps = 0; m.nPreds = 0; meta[c] = m; return; }
+    if (chunkType != 1) { raise(errWord, KE_CHUNK_TYPE, c); m.nDeps = 0; m.nOther = 0; m.nOps = 0; m.nPreds = 0; meta[c] = m; return; }
     // decodeChangeHeader
     const u64 nDeps = r.uleb(); m.depsOff = r.pos; m.nDeps = (u32)nDeps; r.skip(nDeps * 32);
     const u64 actorLen = r.uleb(); m.actorOff = r.pos; m.actorLen = (u32)actorLen; r.skip(actorLen);
@@ -324,19 +325,19 @@ struct ParseKernel {
     for (u64 i = 0; i < nOther && !r.err; i++) { u64 l = r.uleb(); r.skip(l); }
     // decodeColumnInfo
     const u64 nCols = r.uleb();
-    if (r.err) { raise(errWord, r.err, c); meta[c] = m; return; }
+    if (r.err) { raise(errWord, r.err, c); m.nDeps = 0; m.nOther = 0; m.nOps = 0; m.nPreds = 0; meta[c] = m; return; }
     const u32 dirPos = r.pos; long long lastId = -1; u64 total = 0;
     u32 actOff = 0, actLen = 0, pnOff = 0, pnLen = 0;   // the two columns needed for counting, relative to the data start
     for (u64 i = 0; i < nCols && !r.err; i++) {
       const u64 id = r.uleb(), l = r.uleb();
-      if (lastId >= 0 && ((u32)id & ~8u) <= ((u32)lastId & ~8u)) { raise(errWord, KE_COL_ORDER, c); meta[c] = m; return; }
-      if (id & 8) { raise(errWord, KE_COL_DEFLATE, c); meta[c] = m; return; }
+      if (lastId >= 0 && ((u32)id & ~8u) <= ((u32)lastId & ~8u)) { raise(errWord, KE_COL_ORDER, c); m.nDeps = 0; m.nOther = 0; m.nOps = 0; m.nPreds = 0; meta[c] = m; return; }
+      if (id & 8) { raise(errWord, KE_COL_DEFLATE, c); m.nDeps = 0; m.nOther = 0; m.nOps = 0; m.nPreds = 0; meta[c] = m; return; }
       if (id == 0x42) { actOff = (u32)total; actLen = (u32)l; } else if (id == 0x70) { pnOff = (u32)total; pnLen = (u32)l; }
       lastId = (long long)id; total += l;
     }
-    if (r.err) { raise(errWord, r.err, c); meta[c] = m; return; }
+    if (r.err) { raise(errWord, r.err, c); m.nDeps = 0; m.nOther = 0; m.nOps = 0; m.nPreds = 0; meta[c] = m; return; }
     const u32 dataPos = r.pos;
-    if ((u64)dataPos + total > (u64)off + len) { raise(errWord, KE_TRUNCATED, c); meta[c] = m; return; }
+    if ((u64)dataPos + total > (u64)off + len) { raise(errWord, KE_TRUNCATED, c); m.nDeps = 0; m.nOther = 0; m.nOps = 0; m.nPreds = 0; meta[c] = m; return; }
     m.dirOff = dirPos; m.dataOff = dataPos;
     m.extraOff = dataPos + (u32)total; m.extraLen = off + len - m.extraOff;
     // count ops (values of the action column) and preds (sum of the predNum column)
@@ -348,10 +349,11 @@ struct ParseKernel {
       nOps = rle_count_values(arena, dataPos + actOff, dataPos + actOff + actLen, &kerr);
       if (!kerr) nPreds = rle_sum_values(arena, dataPos + pnOff, dataPos + pnOff + pnLen, nOps, &kerr);
     }
-    if (kerr) { raise(errWord, kerr, c); meta[c] = m; return; }
-    if (nPreds > 0x7fffffffULL) { raise(errWord, KE_TOO_LARGE, c); meta[c] = m; return; }
+    if (kerr) { raise(errWord, kerr, c); m.nDeps = 0; m.nOther = 0; m.nOps = 0; m.nPreds = 0; meta[c] = m; return; }
+    if (nPreds > 0x7fffffffULL) { raise(errWord, KE_TOO_LARGE, c); m.nDeps = 0; m.nOther = 0; m.nOps = 0; m.nPreds = 0; meta[c] = m; return; }
     m.nOps = nOps; m.nPreds = (u32)nPreds;
     if (nOps > SMALL_CHANGE_OPS) {   // large change: publish the directory for the (column, change)-parallel kernel
+      *anyLarge = 1;
       ByteReader d(arena, dirPos, dataPos); u32 pos = dataPos;
       for (int k = 0; k < NCOLS; k++) { colOff[(size_t)k * numChanges + c] = 0; colLen[(size_t)k * numChanges + c] = 0; }
       for (u64 i = 0; i < nCols; i++) {

@@ -118,7 +118,12 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     dbgMark("stage:attrs");
     if (callerPinned) {
       // the caller's buffer is pinned: DMA straight from it, and fill the host mirror on a CPU thread while the GPU works
-      h2d(ctx, arena.p + cur, blob + base, tot);
+      // two halves on two streams: two copy engines work on the upload (measured on the B200: see DESIGN.md §6)
+      static const bool splitUpload = !getenv("AMG_NO_SPLIT_UPLOAD");
+      const size_t half = splitUpload && tot > (8u << 20) ? (tot / 2) & ~(size_t)255 : tot;
+      if (half < tot) { side_fork(ctx); h2d_side(ctx, arena.p + cur + half, blob + base + half, tot - half); }
+      h2d(ctx, arena.p + cur, blob + base, half);
+      if (half < tot) side_join(ctx);
       u8* dst = hostArena.data() + cur; const u8* src = blob + base;
       dbgMark("stage:h2d-enqueued");
       startMirror = [this, dst, src, tot] { mirrorThread = std::thread([dst, src, tot] { parallel_copy(dst, src, tot); }); };   // started once the DMA is done: the copy would compete with it for host memory bandwidth
@@ -195,12 +200,14 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   timer.mark(); hostMark();
   meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
   nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
-  foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
-  { u64 ew0 = 0; d2h(ctx, &ew0, errWord.p, 8); sync(ctx); if (ew0) throwKernelError(ew0, actorIds); }
+  dev_memset(ctx, flagWord.p + 8, 0, 4);
+  foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p, flagWord.p + 8});
+  // (parse errors surface with the first host round trip of the gate: the error word travels with every small read, and a
+  //  change that failed to parse has zero deps / ops so the kernels in between have nothing to walk)
   // ------------------------------------------------------------ 2. causal gate
   depBase.ensure(ctx, B + 1); scan_exclusive(ctx, scanTmp, nDeps.p, depBase.p, B);
-  const u32 totalDeps = readU32(depBase.p + B);
-  depIdx.ensure(ctx, totalDeps + 1); primary.ensure(ctx, B); pass.ensure(ctx, B);
+  const size_t depBound = (cur - arenaLen0) / 32 + B + 1;   // every dependency occupies 32 bytes of its change: no need to read the exact total
+  depIdx.ensure(ctx, depBound + 1); primary.ensure(ctx, B); pass.ensure(ctx, B);
   const size_t G = numApplied + B; const size_t tcap = pow2_at_least(2 * G + 2);
   hashTable.ensure(ctx, tcap); dev_memset(ctx, hashTable.p, 0xff, tcap * 4);
   foreach(ctx, G, HashInsertKernel{hashes.p, hashTable.p, (u64)tcap - 1});
@@ -210,7 +217,9 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, meta.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
     dev_memset(ctx, flagWord.p, 0, 4);
     foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, meta.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
-    if (!readU32(flagWord.p)) break;
+    const u32 again = readU32(flagWord.p);
+    checkErr(actorIds);   // free: the error word came with the read
+    if (!again) break;
   }
   applied.ensure(ctx, B); appRank.ensure(ctx, B + 1); isRow.ensure(ctx, B + 1);
   dev_memset(ctx, flagWord.p, 0, 8);
@@ -293,8 +302,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     amapBase.ensure(ctx, B + 1); rowSlot.ensure(ctx, B + 1);
     foreach(ctx, B, MaskedCountKernel{nActors.p, applied.p, rowSlot.p});
     scan_exclusive(ctx, scanTmp, rowSlot.p, amapBase.p, B);
-    const u32 totalAmap = readU32(amapBase.p + B);
-    amap.ensure(ctx, totalAmap + 1);
+    amap.ensure(ctx, B + (cur - arenaLen0) / 2 + 2);   // author + one entry per other-actor table entry (>= 2 bytes each): bound instead of a round trip
     foreach(ctx, B, ActorMapKernel{arena.p, meta.p, applied.p, appRank.p, actorSlots.p, (u64)actorCap - 1, amapBase.p, amap.p, errWord.p});
     dbgMark("actors:mapped");
     // ---------------------------------------------------------- 4. sequence numbers
@@ -329,7 +337,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     opBase.ensure(ctx, B + 1); predBase.ensure(ctx, B + 1); timeBase.ensure(ctx, B + 1);
     foreach(ctx, B, MaskedCountKernel{nOps.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, opBase.p, B);
     foreach(ctx, B, MaskedCountKernel{nPreds.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, predBase.p, B);
-    { u32 m32 = 0, p32 = 0; readU32x2(opBase.p + B, predBase.p + B, &m32, &p32); M = m32; P = p32; }
+    u32 anyLarge = 0;
+    { u32 m32 = 0, p32 = 0; void* dst[3] = {&m32, &p32, &anyLarge}; readWords({{opBase.p + B, 4}, {predBase.p + B, 4}, {flagWord.p + 8, 4}}, dst); M = m32; P = p32; }
     dbgMark("decode:counts");
     if (!inOrder) {
       perm.ensure(ctx, B + 1); dev_memset(ctx, perm.p, 0, (B + 1) * 4);
@@ -344,7 +353,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     r_predActor.ensure(ctx, P + 1); r_predCtr.ensure(ctx, P + 1);
     RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
     foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
-    {   // changes with more than SMALL_CHANGE_OPS ops: (column, change)-parallel expansion
+    lastNumLarge = 0;
+    if (anyLarge) {   // changes with more than SMALL_CHANGE_OPS ops: (column, change)-parallel expansion
       largeFlag.ensure(ctx, B + 1); largeSlot.ensure(ctx, B + 2); largeList.ensure(ctx, B + 1);
       foreach(ctx, B, LargeFlagKernel{meta.p, applied.p, largeFlag.p});
       scan_exclusive(ctx, scanTmp, largeFlag.p, largeSlot.p, B);
@@ -780,7 +790,7 @@ inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* 
   cudaEventRecord(e[0], ctx.stream);
   for (int i = 0; i < iters; i++) foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
   cudaEventRecord(e[1], ctx.stream);
-  for (int i = 0; i < iters; i++) foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
+  for (int i = 0; i < iters; i++) foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p, flagWord.p + 8});
   cudaEventRecord(e[2], ctx.stream);
   for (int i = 0; i < iters; i++) {
     foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
@@ -811,7 +821,7 @@ inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* 
   foreach(ctx, n, ShaKernel{ar.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
   meta.ensure(ctx, n); colOff.ensure(ctx, (size_t)NCOLS * n); colLen.ensure(ctx, (size_t)NCOLS * n);
   nOps.ensure(ctx, n + 1); nPreds.ensure(ctx, n + 1); nDeps.ensure(ctx, n + 1); nActors.ensure(ctx, n + 1);
-  foreach(ctx, n, ParseKernel{ar.p, chOff.p, chLen.p, n, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
+  foreach(ctx, n, ParseKernel{ar.p, chOff.p, chLen.p, n, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p, flagWord.p + 8});
   checkErr(actorIds);
   opBase.ensure(ctx, n + 1); predBase.ensure(ctx, n + 1); applied.ensure(ctx, n); dev_memset(ctx, applied.p, 1, n);
   scan_exclusive(ctx, scanTmp, nOps.p, opBase.p, n); scan_exclusive(ctx, scanTmp, nPreds.p, predBase.p, n);
@@ -886,7 +896,7 @@ inline void Engine::saveDocument(std::string& result) {
       foreach(ctx, K, SplitPairsKernel{chPairs.p, chOff.p, chLen.p});
       meta.ensure(ctx, K); colOff.ensure(ctx, (size_t)NCOLS * K); colLen.ensure(ctx, (size_t)NCOLS * K);
       nOps.ensure(ctx, K + 1); nPreds.ensure(ctx, K + 1); nDeps.ensure(ctx, K + 1); nActors.ensure(ctx, K + 1);
-      foreach(ctx, K, ParseKernel{arena.p, chOff.p, chLen.p, K, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p});
+      foreach(ctx, K, ParseKernel{arena.p, chOff.p, chLen.p, K, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p, flagWord.p + 8});
       depBase.ensure(ctx, K + 1); scan_exclusive(ctx, scanTmp, nDeps.p, depBase.p, K);
       totalDeps = readU32(depBase.p + K);
       depIdx.ensure(ctx, totalDeps + 1); primary.ensure(ctx, K);

@@ -326,6 +326,19 @@ class GpuBackendDoc:
         self._lib.check(rc, err)
         return self._take_patch(pp) if want_patch else None
 
+    def apply_changes_ptrs_flat(self, changes, is_local=False, want_patch=True):
+        """amg_apply_changes: one pointer + length per change (what an N-API binding passes for a Uint8Array[])."""
+        n = len(changes)
+        keep = [bytes(c) for c in changes]
+        bufs = (C.c_char_p * max(n, 1))(*keep)
+        lens = (C.c_size_t * max(n, 1))(*[len(c) for c in keep])
+        pp, err = C.c_void_p(), _ErrStruct()
+        fn = self._lib.L.amg_apply_changes
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        rc = fn(self.h, bufs, lens, C.c_size_t(n), int(is_local), int(want_patch), C.byref(pp), C.byref(err))
+        self._lib.check(rc, err)
+        return self._take_patch(pp) if want_patch else None
+
     def apply_changes(self, changes, is_local=False, want_patch=True):
         if isinstance(changes, (bytes, bytearray)):
             raise TypeError('applyChanges takes an array of Uint8Arrays, not just a single Uint8Array')

@@ -169,6 +169,57 @@ def check_save_after_load(gpu_doc, oracle_mod, cfg, n, a):
     assert d is None, d
 
 
+def check_full_size_properties(gpu_doc, n_ops=1000000, n_actors=10, calls=10):
+    """BASELINE.json's full size (1M-op C3 trace), where the oracle would take minutes: size-independent properties.
+    The document reached by one bulk call, by `calls` consecutive calls and by load(save()) is the same: identical save()
+    bytes (every row, succ list and change record in canonical encoding), heads, clock, maxOp, and identical whole-document
+    edit lists (opId, index, kind, value tag compared with numpy)."""
+    import numpy as np
+    from automerge_classic_b200 import tracegen
+    t = tracegen.generate('C3', n_ops, n_actors)
+    bulk = gpu_doc()
+    fp = bulk.apply_packed_flat(t.blob, t.offsets, t.n_changes)
+    assert fp.pending == 0 and fp.max_op > 0
+    s1 = bulk.save()
+    chunked = gpu_doc()
+    step = (t.n_changes + calls - 1) // calls
+    for lo in range(0, t.n_changes, step):
+        hi = min(t.n_changes, lo + step)
+        offs = (t.offsets[lo:hi + 1] - t.offsets[lo]).astype(np.uint64)
+        chunked.apply_packed_flat(t.blob[int(t.offsets[lo]):int(t.offsets[hi])].copy(), offs, hi - lo, want_patch=False)
+    assert chunked.save() == s1
+    loaded = gpu_doc(s1)
+    assert loaded.save() == s1
+    for other in (chunked, loaded):
+        assert other.heads() == bulk.heads() and other.clock() == bulk.clock() and other.max_op() == bulk.max_op()
+    a = bulk.get_patch_flat()
+    for other in (chunked, loaded):
+        b = other.get_patch_flat()
+        assert len(a.edits) == len(b.edits) and len(a.props) == len(b.props)
+        for f in ('opId', 'index', 'kind', 'valLen'):
+            assert np.array_equal(a.edits[f], b.edits[f]), f
+    # the incremental patch of the bulk call inserts / removes exactly what the final document shows
+    kinds = fp.edits['kind'] & 0xff
+    assert int((kinds == 0).sum()) - int((kinds == 1).sum()) == len(a.edits)
+
+
+def check_pointer_array_entry(gpu_doc, oracle_mod):
+    """amg_apply_changes (array of pointers, the N-API shape) gives the same result as the packed entry point and the oracle,
+    including DEFLATEd changes and several calls."""
+    from automerge_classic_b200 import tracegen
+    ch = tracegen.generate('C3', 2500, 10).changes()
+    assert any(c[8] == 2 for c in ch)
+    orc, g = oracle_mod.OracleDoc(), gpu_doc()
+    for lo in range(0, len(ch), 800):
+        po = orc.apply_changes(ch[lo:lo + 800])
+        pg = g.apply_changes_ptrs_flat(ch[lo:lo + 800]).to_patch(False)
+        d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+        assert d is None, (lo, d)
+    _dump_equal(g, orc)
+    assert g.get_changes([]) == ch
+    assert g.save() == orc.save()
+
+
 def check_incremental_calls(gpu_doc, oracle_mod):
     """Applying a trace in several applyChanges calls gives the same patches as the oracle call by call."""
     from automerge_classic_b200 import tracegen

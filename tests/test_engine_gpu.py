@@ -95,6 +95,14 @@ def test_list_counters_parity(gpu_doc, oracle_mod, n, a, chunk):
     assert compared >= 5
 
 
+def test_full_size_properties(gpu_doc):
+    parity_checks.check_full_size_properties(gpu_doc)
+
+
+def test_pointer_array_entry(gpu_doc, oracle_mod):
+    parity_checks.check_pointer_array_entry(gpu_doc, oracle_mod)
+
+
 def test_incremental_calls_match_bulk(gpu_doc, oracle_mod):
     parity_checks.check_incremental_calls(gpu_doc, oracle_mod)
 

@@ -81,6 +81,14 @@ def test_list_counters_emu(emu_doc, oracle_mod, n, a, chunk):
     assert compared >= 5
 
 
+def test_full_size_properties_emu(emu_doc):
+    parity_checks.check_full_size_properties(emu_doc, n_ops=20000, n_actors=5, calls=7)
+
+
+def test_pointer_array_entry_emu(emu_doc, oracle_mod):
+    parity_checks.check_pointer_array_entry(emu_doc, oracle_mod)
+
+
 def test_incremental_calls_emu(emu_doc, oracle_mod):
     parity_checks.check_incremental_calls(emu_doc, oracle_mod)
 
