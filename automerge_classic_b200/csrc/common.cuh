@@ -92,14 +92,6 @@ inline void d2h(Ctx& c, void* dst, const void* src, size_t bytes) {
   CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
 #endif
 }
-inline void h2d_side(Ctx& c, void* dst, const void* src, size_t bytes) {
-  if (!bytes) return;
-#ifdef AMG_EMU
-  memcpy(dst, src, bytes);
-#else
-  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.side));
-#endif
-}
 inline void d2h_side(Ctx& c, void* dst, const void* src, size_t bytes) {   // on the side stream (after side_fork): overlaps later kernels of the main one
   if (!bytes) return;
 #ifdef AMG_EMU

@@ -118,12 +118,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     dbgMark("stage:attrs");
     if (callerPinned) {
       // the caller's buffer is pinned: DMA straight from it, and fill the host mirror on a CPU thread while the GPU works
-      // two halves on two streams: two copy engines work on the upload (measured on the B200: see DESIGN.md §6)
-      static const bool splitUpload = !getenv("AMG_NO_SPLIT_UPLOAD");
-      const size_t half = splitUpload && tot > (8u << 20) ? (tot / 2) & ~(size_t)255 : tot;
-      if (half < tot) { side_fork(ctx); h2d_side(ctx, arena.p + cur + half, blob + base + half, tot - half); }
-      h2d(ctx, arena.p + cur, blob + base, half);
-      if (half < tot) side_join(ctx);
+      h2d(ctx, arena.p + cur, blob + base, tot);   // (splitting the upload over two streams / copy engines was measured: no gain)
       u8* dst = hostArena.data() + cur; const u8* src = blob + base;
       dbgMark("stage:h2d-enqueued");
       startMirror = [this, dst, src, tot] { mirrorThread = std::thread([dst, src, tot] { parallel_copy(dst, src, tot); }); };   // started once the DMA is done: the copy would compete with it for host memory bandwidth

@@ -82,10 +82,58 @@ __global__ void __launch_bounds__(256) k_scan_apply(const u32* in, u32* out, con
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
 }
+// Single-pass variant: one launch. Tiles take tickets in order; a tile publishes its aggregate, looks back over its
+// predecessors (aggregates until the first inclusive prefix) and publishes its own inclusive prefix.
+// state word = epoch << 34 | status << 32 | value (status 1 = aggregate, 2 = inclusive prefix).
+__global__ void __launch_bounds__(256) k_scan_onepass(const u32* in, u32* out, u64* state, u32* ticket, u32 epoch, size_t n, u32 numTiles) {   // in may alias out
+  __shared__ u32 sm[9]; __shared__ u32 sTile, sExcl;
+  if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 tile = sTile;
+  const size_t base = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  u32 v[SCAN_ITEMS]; u32 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
+  u32 total; u32 ex = block_excl_scan(s, &total, sm);
+  if (threadIdx.x == 0) {
+    volatile u64* st = state; const u64 tag = (u64)epoch << 34; u32 excl = 0;
+    if (tile == 0) st[0] = tag | (2ull << 32) | total;
+    else {
+      st[tile] = tag | (1ull << 32) | total;
+      for (u32 p = tile; p-- > 0;) {
+        u64 w; do { w = st[p]; } while ((w >> 34) != epoch || ((w >> 32) & 3) == 0);
+        excl += (u32)w;
+        if (((w >> 32) & 3) == 2) break;
+      }
+      st[tile] = tag | (2ull << 32) | (u32)(excl + total);
+    }
+    sExcl = excl;
+    if (tile == numTiles - 1) { out[n] = excl + total; *ticket = 0; }   // the last ticket holder re-arms the counter
+  }
+  __syncthreads();
+  ex += sExcl;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+}
 #endif
 
-struct ScanTemp { DBuf<u32> tiles; DBuf<u64> tiles64; };
+struct ScanTemp {
+  DBuf<u32> tiles; DBuf<u64> tiles64;
+  // single-pass scans (decoupled look-back): per-tile status words tagged with an epoch (no clearing between scans)
+  DBuf<u64> state; DBuf<u64> aggVal, inclVal; DBuf<u32> ticket; u32 epoch = 0; size_t stateTiles = 0;
+};
 
+inline bool scan_single_pass() { static const bool on = !getenv("AMG_SCAN_THREE_PASS"); return on; }
+#ifndef AMG_EMU
+inline void scan_prepare(Ctx& c, ScanTemp& t, size_t numTiles) {   // a fresh epoch; (re)allocation or epoch wrap clears the status words
+  if (numTiles + 1 > t.stateTiles || t.epoch >= (1u << 30) - 2) {
+    t.stateTiles = numTiles + 1 + numTiles / 2;
+    t.state.ensure(c, t.stateTiles); t.aggVal.ensure(c, t.stateTiles); t.inclVal.ensure(c, t.stateTiles); t.ticket.ensure(c, 4);
+    dev_memset(c, t.state.p, 0, t.state.cap * 8); dev_memset(c, t.ticket.p, 0, 16); t.epoch = 0;
+  }
+  t.epoch++;
+}
+#endif
 // out[0..n) = exclusive prefix sums of in[0..n); out[n] = total (out must hold n+1). in == out allowed.
 inline void scan_exclusive(Ctx& c, ScanTemp& t, const u32* in, u32* out, size_t n) {
 #ifdef AMG_EMU
@@ -93,6 +141,12 @@ inline void scan_exclusive(Ctx& c, ScanTemp& t, const u32* in, u32* out, size_t 
 #else
   if (n == 0) { dev_memset(c, out, 0, sizeof(u32)); return; }
   size_t numTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (scan_single_pass()) {
+    scan_prepare(c, t, numTiles);
+    k_scan_onepass<<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, out, t.state.p, t.ticket.p, t.epoch, n, (u32)numTiles);
+    CUDA_CHECK(cudaGetLastError());
+    c.launches += 1; return;
+  }
   t.tiles.ensure(c, numTiles + 1);
   k_scan_reduce<<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, t.tiles.p, n);
   k_scan_tiles<<<1, SCAN_THREADS, 0, c.stream>>>(t.tiles.p, numTiles, out + n);
@@ -160,12 +214,52 @@ template <class F> __global__ void __launch_bounds__(256) k_scan64_apply(F in, u
   for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
 }
 #endif
+#ifndef AMG_EMU
+// 64-bit values do not fit next to a status in one word: value slots (aggregate / inclusive) + a flag word, fenced.
+template <class F> __global__ void __launch_bounds__(256) k_scan64_onepass(F in, u64* __restrict__ out, u64* flag, u64* aggVal, u64* inclVal, u32* ticket, u32 epoch, size_t n, u32 numTiles) {
+  __shared__ u64 sm[9]; __shared__ u32 sTile; __shared__ u64 sExcl;
+  if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 tile = sTile;
+  const size_t base = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  u64 v[SCAN_ITEMS]; u64 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in(base + k) : 0; s += v[k]; }
+  u64 total; u64 ex = block_excl_scan64(s, &total, sm);
+  if (threadIdx.x == 0) {
+    volatile u64* fl = flag; volatile u64* av = aggVal; volatile u64* iv = inclVal; const u64 tag = (u64)epoch << 2; u64 excl = 0;
+    if (tile == 0) { iv[0] = total; __threadfence(); fl[0] = tag | 2; }
+    else {
+      av[tile] = total; __threadfence(); fl[tile] = tag | 1;
+      for (u32 p = tile; p-- > 0;) {
+        u64 w; do { w = fl[p]; } while ((w >> 2) != epoch || (w & 3) == 0);
+        __threadfence();
+        if ((w & 3) == 2) { excl += iv[p]; break; }
+        excl += av[p];
+      }
+      iv[tile] = excl + total; __threadfence(); fl[tile] = tag | 2;
+    }
+    sExcl = excl;
+    if (tile == numTiles - 1) { out[n] = excl + total; *ticket = 0; }
+  }
+  __syncthreads();
+  ex += sExcl;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+}
+#endif
 template <class F> inline void scan_exclusive64(Ctx& c, ScanTemp& t, const F& in, u64* out, size_t n) {
 #ifdef AMG_EMU
   u64 acc = 0; for (size_t i = 0; i < n; i++) { u64 v = in(i); out[i] = acc; acc += v; } out[n] = acc; c.launches += 3;
 #else
   if (n == 0) { dev_memset(c, out, 0, sizeof(u64)); return; }
   size_t numTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (scan_single_pass()) {
+    scan_prepare(c, t, numTiles);
+    k_scan64_onepass<F><<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, out, t.state.p, t.aggVal.p, t.inclVal.p, t.ticket.p, t.epoch, n, (u32)numTiles);
+    CUDA_CHECK(cudaGetLastError());
+    c.launches += 1; return;
+  }
   t.tiles64.ensure(c, numTiles + 1);
   k_scan64_reduce<F><<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, t.tiles64.p, n);
   k_scan64_tiles<<<1, SCAN_THREADS, 0, c.stream>>>(t.tiles64.p, numTiles, out + n);
