@@ -274,6 +274,17 @@ HD void warp_agg_max(uint32_t* target, uint32_t v) {
   if (v > *target) *target = v;
 #endif
 }
+// base[index] = min(base[index], v) with one atomic per distinct index per warp
+HD void warp_agg_min_at(uint32_t* base, uint32_t index, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, index);
+  const uint32_t m = __reduce_min_sync(peers, v);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1 && base[index] > m) atomicMin(&base[index], m);
+#else
+  if (v < base[index]) base[index] = v;
+#endif
+}
 HD void warp_agg_add(uint32_t* target, uint32_t v) {
 #if defined(__CUDA_ARCH__)
   const unsigned active = __activemask();

@@ -63,7 +63,7 @@ struct TouchKernel {   // new rows and the targets of new succ entries touch the
     if (d.time[p] == 0 && firstNewSucc[p] == 0xffffffffu) return;
     groupTouched[groupOf[p]] = 1;
     u32 t = firstNewSucc[p]; if (d.time[p] != 0 && d.time[p] < t) t = d.time[p];
-    if (objPos[p] == ROW_NONE) *rootTouched = 1; else if (objTouchedAt[objPos[p]] > t) atomic_min(&objTouchedAt[objPos[p]], t);   // read first: all rows of one object meet here
+    if (objPos[p] == ROW_NONE) *rootTouched = 1; else warp_agg_min_at(objTouchedAt, objPos[p], t);   // all rows of one object meet here: one atomic per warp
   }
 };
 // setupPatches (new.js:1461-1528): a touched object links itself into its parent (the group of its make row), recursively.

@@ -166,29 +166,39 @@ __global__ void __launch_bounds__(256) k_scan64_tiles(u64* __restrict__ tileSums
   }
   if (threadIdx.x == 0) *totalOut = carry;
 }
-template <class F> __global__ void __launch_bounds__(256) k_scan64_apply(F in, u64* __restrict__ out, const u64* __restrict__ tileOffsets, size_t n) {
+// `tileOffsets` holds exclusive prefix sums of the tile sums (k_scan64_tiles), or - with sumTiles - the raw tile sums,
+// which every block then adds up for itself (few tiles: saves the single-block kernel in between)
+template <class F> __global__ void __launch_bounds__(256) k_scan64_apply(F in, u64* __restrict__ out, const u64* __restrict__ tileOffsets, size_t n, int sumTiles) {
   __shared__ u64 sm[9];
   const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  u64 offset;
+  if (sumTiles) {
+    u64 part = 0;
+    for (unsigned j = threadIdx.x; j < blockIdx.x; j += SCAN_THREADS) part += tileOffsets[j];
+    u64 all; block_excl_scan64(part, &all, sm); offset = all;
+  } else offset = tileOffsets[blockIdx.x];
   u64 v[SCAN_ITEMS]; u64 s = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in(base + k) : 0; s += v[k]; }
-  u64 total; u64 ex = block_excl_scan64(s, &total, sm) + tileOffsets[blockIdx.x];
+  u64 total; u64 ex = block_excl_scan64(s, &total, sm) + offset;
+  if (sumTiles && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = offset + total;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
 }
 #endif
 template <class F> inline void scan_exclusive64(Ctx& c, ScanTemp& t, const F& in, u64* out, size_t n) {
 #ifdef AMG_EMU
-  u64 acc = 0; for (size_t i = 0; i < n; i++) { u64 v = in(i); out[i] = acc; acc += v; } out[n] = acc; c.launches += 3;
+  u64 acc = 0; for (size_t i = 0; i < n; i++) { u64 v = in(i); out[i] = acc; acc += v; } out[n] = acc; c.launches += 2;
 #else
   if (n == 0) { dev_memset(c, out, 0, sizeof(u64)); return; }
   size_t numTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   t.tiles64.ensure(c, numTiles + 1);
   k_scan64_reduce<F><<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, t.tiles64.p, n);
-  k_scan64_tiles<<<1, SCAN_THREADS, 0, c.stream>>>(t.tiles64.p, numTiles, out + n);
-  k_scan64_apply<F><<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, out, t.tiles64.p, n);
+  const bool few = numTiles <= 4096;   // every apply block adds up the tile sums in front of it
+  if (!few) k_scan64_tiles<<<1, SCAN_THREADS, 0, c.stream>>>(t.tiles64.p, numTiles, out + n);
+  k_scan64_apply<F><<<(unsigned)numTiles, SCAN_THREADS, 0, c.stream>>>(in, out, t.tiles64.p, n, few ? 1 : 0);
   CUDA_CHECK(cudaGetLastError());
-  c.launches += 3;
+  c.launches += few ? 2 : 3;
 #endif
 }
 
