@@ -352,7 +352,9 @@ struct ListCtx {
 struct OldVisFlagKernel { ListCtx L; const u32* head; u32* flag; HD void operator()(size_t p) const { flag[p] = (L.d.keyStrLen[p] == NULL32 && head[p] && (L.d.flags[p] & F_INSERT) && L.visAt((u32)p, L.groupRows[L.groupOf[p]], 0)) ? 1u : 0u; } };
 // items per position: one merged item for an element with one op group, otherwise its queries first and its points after
 // (a query must not see the points of its own element)
-struct DomItemCountKernel { const u32* nQ; const u32* elemFollower; u32* nItems; HD void operator()(size_t p) const { const u32 k = nQ[p]; nItems[p] = elemFollower[p] ? 0u : (k <= 1 ? k : 2 * k); } };
+// one or two groups on an element: one merged item each, the LATER group first (then neither query can see the other
+// group's point: the earlier one fails the time test, the later one the order test); three and more: queries, then points
+struct DomItemCountKernel { const u32* nQ; const u32* elemFollower; u32* nItems; HD void operator()(size_t p) const { const u32 k = nQ[p]; nItems[p] = elemFollower[p] ? 0u : (k <= 2 ? k : 2 * k); } };
 // Typing runs: consecutive insert ops (consecutive application times) whose elements end up next to each other in the
 // document, each touched by nothing else in the batch. Every other query sees such a run entirely or not at all, so the
 // run is ONE item: the query of its first op, weighted with the run length; member j has index(head) + j.
@@ -410,7 +412,7 @@ struct DomResultKernel {   // route query results back by group start time
 //   (appendUpdate, new.js:798-825).   V non-empty, not W: insert of V[0] then updates.
 struct ListGroupKernel {
   int pass; MapGroupCtx c; const u32* groupHead; IdTable t; const u32* rowOfOp; const u32* pos; ListCtx L;
-  u32* gCount; u32* gElem; u32* gT1; u32* gQOrd; u32* nQ; u32* elemHasRecs;                     // pass 0 out (gT1: T1 | (net weight + 1) << 29 | W << 31)
+  u32* gCount; u32* gElem; u32* gT1; u32* gQOrd; u32* nQ; u32* elemHasRecs; u32* elemMinT;      // pass 0 out (gT1: T1 | (net weight + 1) << 29 | W << 31)
   const u32* itemBase; const u32* objIdx; const u32* objStart; DomItem* items; u32* twArr; int* wArr; const u32* oldVisScan;   // pass 1: items
   const u32* runHeadFlag; const u32* runScan; const u32* runStart;   // typing runs (FollowerFlagKernel)
   const u32* gBase; const u32* qIndex; EditRec* out; u64* elemOut; u32* objKeyOut; u32* elemPosOut; u32* rowPosOut; u64* errWord;   // pass 2: records
@@ -437,7 +439,7 @@ struct ListGroupKernel {
           n = nV ? nV : (W ? 1u : 0u);
           const int wNet = (int)L.visAt(e, rows, T1) - (int)L.visAt(e, rows, T0 - 1);
           gElem[t0] = e; gT1[t0] = T1 | ((u32)(wNet + 1) << 29) | (W ? 0x80000000u : 0u);
-          if (n || wNet) gQOrd[t0] = atomic_add(&nQ[e], 1u); else gQOrd[t0] = ROW_NONE;
+          if (n || wNet) { gQOrd[t0] = atomic_add(&nQ[e], 1u); atomic_min(&elemMinT[e], T0); } else gQOrd[t0] = ROW_NONE;
           if (nV) elemHasRecs[e] = 1;
         }
       }
@@ -451,8 +453,10 @@ struct ListGroupKernel {
       int wNet = (int)((gT1[t0] >> 29) & 3u) - 1; const bool isQ = gCount[t0] != 0; const u32 k = nQ[e], o = gQOrd[t0];
       { const u32 run = runScan[t0]; const u32 len = runStart[run + 1] - (u32)t0; if (len > 1) wNet = (int)len; }   // head of a run: all its +1s at once
       DomItem q; q.acc = 0; q.gs = itemBase[objStart[objIdx[e]]]; q.ge = itemBase[objStart[objIdx[e] + 1]];
-      if (k == 1) { q.tw = dom_tw((u32)t0 + 1, isQ); q.w = wNet; items[itemBase[e]] = q; twArr[itemBase[e]] = q.tw; wArr[itemBase[e]] = q.w; }
-      else {
+      if (k <= 2) {
+        const u32 at = itemBase[e] + ((k == 2 && elemMinT[e] == (u32)t0 + 1) ? 1u : 0u);   // of two groups the earlier one sits second
+        q.tw = dom_tw((u32)t0 + 1, isQ); q.w = wNet; items[at] = q; twArr[at] = q.tw; wArr[at] = q.w;
+      } else {
         q.tw = dom_tw((u32)t0 + 1, isQ); q.w = 0; items[itemBase[e] + o] = q; twArr[itemBase[e] + o] = q.tw; wArr[itemBase[e] + o] = 0;
         q.tw = dom_tw((u32)t0 + 1, false); q.w = wNet; items[itemBase[e] + k + o] = q; twArr[itemBase[e] + k + o] = q.tw; wArr[itemBase[e] + k + o] = wNet;
       }
