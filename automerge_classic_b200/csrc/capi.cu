@@ -243,6 +243,9 @@ int amg_debug_dump_ops(amg_backend* b, uint64_t** rows_out, size_t* n, uint64_t*
 int amg_debug_decode(amg_backend* b, const uint8_t* blob, const uint64_t* offsets, size_t n, uint8_t* hashes_out, uint32_t* n_ops_out, uint32_t** rows_out, size_t* total_ops, amg_error* err) {
   AMG_GUARD(b->eng.decodeRaw(blob, (const u64*)offsets, n, hashes_out, n_ops_out, rows_out, total_ops); return 0;)
 }
+int amg_debug_decode_column(amg_backend* b, const uint8_t* bytes, size_t len, int kind, size_t n, int parallel, int64_t* out, amg_error* err) {
+  AMG_GUARD(return b->eng.debugDecodeColumn(bytes, len, kind, n, parallel != 0, (long long*)out);)
+}
 int amg_bench_decode(amg_backend* b, int iters, float* ms_sha, float* ms_parse, float* ms_decode, uint64_t* algo_bytes, amg_error* err) {
   AMG_GUARD(u64 bytes = 0; b->eng.benchDecode(iters, ms_sha, ms_parse, ms_decode, &bytes); *algo_bytes = bytes; return 0;)
 }

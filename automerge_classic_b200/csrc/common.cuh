@@ -47,6 +47,8 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;        // second stream: work that may overlap the main pipeline (joined through events)
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  cudaStream_t copy = nullptr;        // third stream: device -> host copy of the uploaded change bytes into the host mirror
+  cudaEvent_t evUp = nullptr, evMirror = nullptr; bool mirrorPending = false;
 #endif
   int device = 0;
   int numSMs = 148;
@@ -210,6 +212,28 @@ inline void side_fork(Ctx& c) {
 inline void side_join(Ctx& c) {
 #ifndef AMG_EMU
   CUDA_CHECK(cudaEventRecord(c.evJoin, c.side)); CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.evJoin, 0));
+#endif
+}
+
+// Host mirror of freshly uploaded bytes: copied back from the device by the copy engine (no CPU time, and the caller's
+// buffer is not touched after the upload), ordered after everything queued on the main stream so far. mirror_wait() is
+// the host-side join; nothing else on the device waits for it.
+inline void mirror_start(Ctx& c, void* dstPinnedHost, const void* srcDev, size_t bytes) {
+#ifdef AMG_EMU
+  memcpy(dstPinnedHost, srcDev, bytes);
+#else
+  CUDA_CHECK(cudaEventRecord(c.evUp, c.stream)); CUDA_CHECK(cudaStreamWaitEvent(c.copy, c.evUp, 0));
+  // in pieces: the small device -> host reads that size the pipeline stages share the copy engine with this transfer and
+  // can only slip in between two operations (one 132 MB copy held each of them up for its whole remaining time)
+  const size_t kPiece = 1u << 20;
+  for (size_t o = 0; o < bytes; o += kPiece)
+    CUDA_CHECK(cudaMemcpyAsync((char*)dstPinnedHost + o, (const char*)srcDev + o, std::min(kPiece, bytes - o), cudaMemcpyDeviceToHost, c.copy));
+  CUDA_CHECK(cudaEventRecord(c.evMirror, c.copy)); c.mirrorPending = true;
+#endif
+}
+inline void mirror_wait(Ctx& c) noexcept {
+#ifndef AMG_EMU
+  if (c.mirrorPending) { cudaEventSynchronize(c.evMirror); c.mirrorPending = false; }
 #endif
 }
 

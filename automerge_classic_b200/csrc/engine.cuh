@@ -21,6 +21,8 @@
 #include "inflate.cuh"
 #include "encode.cuh"
 #include "prims.cuh"
+#include "domlocal.cuh"
+#include "doccols.cuh"
 
 namespace amg {
 
@@ -97,6 +99,7 @@ class Engine {
   DBuf<u32> isRow, rowSlot, rowOfOp; DocBufs work, sorted;
   DBuf<u64> idKeys; DBuf<u32> idVals; DBuf<u32> objRow, elemRow, parentRow, keySlot, repList, repCount, listPos, perm, pos;
   DBuf<KeySlot> keySlots; DBuf<u64> sortKeys; DBuf<u32> sortVals; SortTemp sortTmp; ScanTemp scanTmp;
+  ParColumnDecoder parCols{ctx, scanTmp}; size_t parDocMinRows = 4096;   // documents with at least this many rows decode their columns in parallel (doccols.cuh); AMG_PAR_DOC_MIN overrides
   DBuf<u32> eNext, eNext2, eRank, eRank2, insItems, itemIdx, objSlot;
   DBuf<u64> pairKey, pairSucc, newSucc; DBuf<u32> pairIdx, pairPos, pairTime, succCnt, newSuccCnt, newSuccOff, firstNewSucc;
   DBuf<u32> elemPos, keyRankAt, objPos, head, headScan, groupOf, groupRows, groupVisible, groupFirst, groupTouched, groupLinked, objTouchedAt, linkDone, emit, marker, slot;
@@ -104,7 +107,7 @@ class Engine {
   DBuf<DomItem> items, items2; DBuf<PropRec> propOut; DBuf<EditRec> editOut, editOut2; DBuf<u64> editElem, editElem2;
   std::unique_ptr<ColumnEncoder> encoder; DBuf<long long> saveVals; DBuf<u32> saveStrOff, saveStrLen; std::string loadedDoc; size_t numLoaded = 0; HostChange loadedCols[9] = {}; DBuf<u64> counterTotal; DBuf<int> domW, domW2; DBuf<u32> elemMinT, editRowPos, editRowPos2, editObjKey2, rowClass, firstBare, counterOwner, newSuccTime, counterLast, runHeadFlag, runScan, runStart, elemFollower, domTw, domTw2, oldVisScan, inflLen, inflOff, groupHasChild, gCount, gElem, gT1, gQOrd, gBase, nQ, elemHasRecs, listLinkTime, editElemPos, editElemPos2, editKind, editPred, editDead, editMerge, editMulti, editLive;
   DBuf<u32> seqSlot, actorCnt, actorBaseD, clockD, changeActor, editTime; DBuf<u8> hashTmp; bool batchInOrder = true;
-  DBuf<u32> finalTime, gFailed, memberFinal, opAt, runHead, opGroupHead; DBuf<u64> gBound; DocRows workView{}; DBuf<HostChange> chPairs; std::thread mirrorThread; DBuf<u32> largeFlag, largeSlot, largeList; size_t lastNumLarge = 0; DBuf<u64> zwScan; DBuf<u32> deflList, patchTriples;
+  DBuf<u32> finalTime, gFailed, memberFinal, opAt, runHead, opGroupHead; DBuf<u64> gBound; DocRows workView{}; DBuf<HostChange> chPairs; DBuf<u32> largeFlag, largeSlot, largeList; size_t lastNumLarge = 0; DBuf<u64> zwScan; DBuf<u32> deflList, patchTriples;
 
   explicit Engine(int device) {
     ctx.device = device;
@@ -115,6 +118,8 @@ class Engine {
     cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, device)); ctx.numSMs = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.side, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.copy, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evUp, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evMirror, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evFork, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evJoin, cudaEventDisableTiming));
     ShaConsts k; memcpy(k.k, SHA_K, sizeof(SHA_K)); CUDA_CHECK(cudaMemcpyToSymbol(c_sha, &k, sizeof(k)));
 #endif
@@ -125,7 +130,11 @@ class Engine {
   ~Engine() {
 #ifndef AMG_EMU
     if (ctx.stream) cudaStreamDestroy(ctx.stream);
+    mirror_wait(ctx);
     if (ctx.side) cudaStreamDestroy(ctx.side);
+    if (ctx.copy) cudaStreamDestroy(ctx.copy);
+    if (ctx.evUp) cudaEventDestroy(ctx.evUp);
+    if (ctx.evMirror) cudaEventDestroy(ctx.evMirror);
     if (ctx.evFork) cudaEventDestroy(ctx.evFork);
     if (ctx.evJoin) cudaEventDestroy(ctx.evJoin);
 #endif
@@ -201,6 +210,8 @@ class Engine {
   void checkErr(const std::vector<std::string>& actorsNow) { u64 w = fetchErr(); if (w) throwKernelError(w, actorsNow); }
 
   // ---------------------------------------------------------------- helpers
+  bool domLocalReady = false;   // k_dom_local's dynamic shared memory size has been raised on this device
+  std::vector<HostChange> batchStore;   // applyChanges: (offset, length) of the batch entries
   HBuf<u32> pinnedScratch; HBuf<u64> hostWord;   // pinned landing slots for the small device -> host reads that size the next stage
   u32 readU32(const u32* dptr) { u32 v = 0; void* d[1] = {&v}; readWords({{dptr, 4}}, d); return v; }
   void readU32x2(const u32* a, const u32* b, u32* va, u32* vb) { void* d[2] = {va, vb}; readWords({{a, 4}, {b, 4}}, d); }
@@ -246,6 +257,7 @@ class Engine {
   void loadDocument(const u8* buf, size_t len);
   bool haveHashGraph = true;   // false after Backend.load: change history (hashes, bytes) is not reconstructed (new.js:1887-1912)
   void benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes);
+  int debugDecodeColumn(const u8* bytes, size_t len, int kind, size_t n, bool parallel, long long* out);
   void decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* hashesOut, u32* nOpsOut, u32** rowsOut, size_t* totalOps);
   size_t lastB = 0, lastM = 0, lastP = 0, lastBytes = 0;
 };

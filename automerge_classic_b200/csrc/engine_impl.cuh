@@ -75,7 +75,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   struct ClearTimer { Engine* e; ~ClearTimer() { e->curTimer = nullptr; e->curHostMark = nullptr; e->dbgMark = [](const char*) {}; } } clearTimer{this};
   // ------------------------------------------------------------ 0. stage the batch in the arena (pinned host mirror + device)
   const size_t arenaLen0 = arenaLen; const size_t hostLen0 = hostArena.size();
-  std::vector<HostChange> batch, batchOriginal, inflOrig;   // originals of DEFLATEd changes: batchOriginal (dense, queue entries) / inflOrig (sparse, parallel to deflIdx)
+  std::vector<HostChange>& batch = batchStore; batch.clear();   // member: the 8 MB of a 1M-change batch keep their pages across calls
+  std::vector<HostChange> batchOriginal, inflOrig;   // originals of DEFLATEd changes: batchOriginal (dense, queue entries) / inflOrig (sparse, parallel to deflIdx)
   std::vector<u32> deflIdx;
   size_t inflNd = 0, inflExtraStart = 0, inflExtra = 0; bool inflPending = false;
   // Host side of the device inflate: which batch entries moved where, and the inflated bytes for the host mirror. Not on
@@ -87,7 +88,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     pinnedScratch.ensure(5 * nd + 16); u32* ps = pinnedScratch.p;   // pinned: the five small copies queue up and complete with one sync
     d2h(ctx, ps, deflList.p, nd * 4); d2h(ctx, ps + nd, inflLen.p, nd * 4); d2h(ctx, ps + 2 * nd, inflOff.p, nd * 4);
     d2h(ctx, ps + 3 * nd, origOff, nd * 4); d2h(ctx, ps + 4 * nd, origLen, nd * 4);
-    if (mirrorThread.joinable()) mirrorThread.join();   // the mirror has to grow
+    mirror_wait(ctx);   // the mirror has to grow
     hostArena.resize(inflExtraStart + inflExtra);
     d2h(ctx, hostArena.data() + inflExtraStart, arena.p + inflExtraStart, inflExtra);
     sync(ctx);
@@ -104,9 +105,9 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   if (blob && n > 0) total = offsets[n] - offsets[0]; else for (size_t i = 0; i < n; i++) total += lens[i];
   if ((u64)arenaLen0 + total + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
   Rollback rb{this, hostLen0};
-  struct MirrorJoin { Engine* e; ~MirrorJoin() { if (e->mirrorThread.joinable()) e->mirrorThread.join(); } } mirrorJoin{this};   // declared after rb: joins first
-  size_t cur = arenaLen0; bool uploaded = false; std::function<void()> startMirror;
-  const size_t Bq = queue.size(); batch.resize(n + Bq);
+  struct MirrorJoin { Engine* e; ~MirrorJoin() { mirror_wait(e->ctx); } } mirrorJoin{this};   // declared after rb: joins first
+  size_t cur = arenaLen0; bool uploaded = false;
+  const size_t Bq = queue.size();
   if (blob && n > 0 && !hostScan) {
     // bulk path: no per-change host work beyond one (offset, length) pair; DEFLATEd changes are detected on the device
     const size_t base = offsets[0]; const size_t tot = offsets[n] - base;
@@ -117,11 +118,11 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
 #endif
     dbgMark("stage:attrs");
     if (callerPinned) {
-      // the caller's buffer is pinned: DMA straight from it, and fill the host mirror on a CPU thread while the GPU works
+      // the caller's buffer is pinned: DMA straight from it; the host mirror is filled from the device copy by the copy
+      // engine while the kernels run (a CPU copy of the same bytes took longer than the whole device pipeline)
       h2d(ctx, arena.p + cur, blob + base, tot);   // (splitting the upload over two streams / copy engines was measured: no gain)
-      u8* dst = hostArena.data() + cur; const u8* src = blob + base;
+      mirror_start(ctx, hostArena.data() + cur, arena.p + cur, tot);
       dbgMark("stage:h2d-enqueued");
-      startMirror = [this, dst, src, tot] { mirrorThread = std::thread([dst, src, tot] { parallel_copy(dst, src, tot); }); };   // started once the DMA is done: the copy would compete with it for host memory bandwidth
     } else {
       const size_t kChunk = 32u << 20;   // copy into the pinned mirror and upload chunk by chunk (H2D overlaps the next host copy)
       for (size_t o = 0; o < tot; o += kChunk) {
@@ -131,9 +132,11 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
       }
     }
     const u32 shift = (u32)(cur - base);
+    batch.resize(n + Bq);   // after the DMA is under way: everything the host does from here to the next device read is in its shadow
     for (size_t i = 0; i < n; i++) { batch[i].off = (u32)offsets[i] + shift; batch[i].len = (u32)(offsets[i + 1] - offsets[i]); }
     uploaded = true; cur += tot; dbgMark("stage:batch-filled");
   } else {
+    batch.resize(n + Bq);
     for (size_t i = 0; i < n; i++) {
       const u8* p = blob ? blob + offsets[i] : bufs[i]; const size_t l = blob ? (size_t)(offsets[i + 1] - offsets[i]) : lens[i];
       hostArena.append(p, l); batch[i] = HostChange{(u32)cur, (u32)l}; cur += l;
@@ -164,7 +167,6 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     foreach(ctx, B, DeflateFlagKernel{arena.p, chOff.p, chLen.p, emit.p});
     scan_exclusive(ctx, scanTmp, emit.p, slot.p, B);
     const size_t nd = readU32(slot.p + B);
-    if (startMirror) { startMirror(); startMirror = nullptr; }   // the upload has completed (the read above waited for it)
     dbgMark("sha:deflate-scanned");
     // the SHA-256 of the whole batch (ALU-bound, ~0.5 ms at 1M changes) runs on the side stream while the few
     // DEFLATEd changes are inflated, laid out and hashed on the main one; joined before the header parse
@@ -552,7 +554,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   fillPatchHeader(out);
   if (isLocal && n == 1) {   // new.js:1874-1877
     std::vector<ChangeMeta> m0(1); d2h(ctx, m0.data(), meta.p, sizeof(ChangeMeta)); sync(ctx);
-    if (mirrorThread.joinable()) mirrorThread.join();
+    mirror_wait(ctx);
     out.hasActorSeq = true; out.actor.assign((const char*)hostArena.data() + m0[0].actorOff, m0[0].actorLen); out.seq = m0[0].seq;
   }
   dbgMark("commit:end");
@@ -690,12 +692,30 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
       items.ensure(ctx, T + 1); items2.ensure(ctx, T + 1); zwScan.ensure(ctx, T + 2); domTw.ensure(ctx, T + 1); domTw2.ensure(ctx, T + 1); domW.ensure(ctx, T + 1); domW2.ensure(ctx, T + 1);
       foreach(ctx, numOps, listGroups(1));
       const int tbits = bits_for(numOps + 1);
-      for (int bit = tbits - 1; bit >= 0; bit--) {
+#ifdef AMG_EMU
+      const int localBits = 0;
+#else
+      const int localBits = std::min(tbits, DOM_LOCAL_BITS);   // the last levels run inside shared memory (k_dom_local)
+#endif
+      for (int bit = tbits - 1; bit >= localBits; bit--) {
         scan_exclusive64(ctx, scanTmp, DomScanInput{domTw.p, domW.p, bit}, zwScan.p, T);
         foreach(ctx, T, DomLevelKernel{items.p, items2.p, domTw2.p, domW2.p, zwScan.p, bit});
         std::swap(items.p, items2.p); std::swap(items.cap, items2.cap); std::swap(domTw.p, domTw2.p); std::swap(domTw.cap, domTw2.cap); std::swap(domW.p, domW2.p); std::swap(domW.cap, domW2.cap);
       }
+#ifdef AMG_EMU
       foreach(ctx, T, DomResultKernel{items.p, qIndex.p});
+#else
+      {   // partition heads -> compact list (device-side count), then one CTA per partition
+        DBuf<u32>& partFlag = domTw2; DBuf<u32>& partScan = nItems; DBuf<u32>& partHead = itemBase;   // scratch that is free by now
+        partScan.ensure(ctx, T + 2); partHead.ensure(ctx, T + 2);
+        foreach(ctx, T, DomPartHeadKernel{items.p, partFlag.p});
+        scan_exclusive(ctx, scanTmp, partFlag.p, partScan.p, T);
+        foreach(ctx, T, CompactKernel{partFlag.p, partScan.p, partHead.p});
+        if (!domLocalReady) { CUDA_CHECK(cudaFuncSetAttribute(k_dom_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DomLocalSmem))); domLocalReady = true; }
+        k_dom_local<<<ctx.numSMs * 2, 256, sizeof(DomLocalSmem), ctx.stream>>>(items.p, partHead.p, partScan.p + T, qIndex.p, localBits, errWord.p);
+        CUDA_CHECK(cudaGetLastError()); ctx.launches++;
+      }
+#endif
       if (curTimer) { curTimer->mark(); curHostMark(); }
       ensureEdits(numGroupRecs);
       foreach(ctx, numOps, listGroups(2));
@@ -800,6 +820,29 @@ inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* 
 #else
   *msSha = *msParse = *msDec = 0;
 #endif
+}
+
+// Parity hook: one document column through the parallel or the serial decoder (include/amgpu.h)
+inline int Engine::debugDecodeColumn(const u8* bytes, size_t len, int kind, size_t n, bool parallel, long long* out) {
+  if (kind < 0 || kind > 3 || len >= 0x7fffffffULL || n >= 0x7fffffffULL) throw Error(AMG_ERR_RANGE, "amg_debug_decode_column: bad arguments");
+  DBuf<u8> colBytes; DBuf<long long> outD; DBuf<u32> tmp;
+  colBytes.ensure(ctx, len + 64); dev_memset(ctx, colBytes.p, 0, len + 64); if (len) h2d(ctx, colBytes.p, bytes, len);
+  outD.ensure(ctx, n + 1); tmp.ensure(ctx, n + 1);
+  if (parallel) {
+    bool ok = false;
+    if (kind == 0) ok = parCols.toI64(colBytes.p, len, false, n, outD.p);
+    else if (kind == 1) ok = parCols.toI64(colBytes.p, len, true, n, outD.p);
+    else if (kind == 2) ok = parCols.deltaToI64(colBytes.p, len, n, outD.p);
+    else { ok = parCols.boolean(colBytes.p, len, n, tmp.p); if (ok && n) foreach(ctx, n, U32ToI64Kernel{tmp.p, outD.p}); }
+    if (!ok) { sync(ctx); return 1; }
+  } else {
+    dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull;
+    foreach_warp(ctx, 1, DebugColumnKernel{kind, colBytes.p, (u32)len, (u32)n, outD.p, tmp.p, errWord.p});
+    checkErr(actorIds);
+  }
+  if (n) d2h(ctx, out, outD.p, n * 8);
+  sync(ctx);
+  return 0;
 }
 
 // Parity hook: hashes, op counts and the raw decoded columns (change-local values) of a batch, without touching the document.
@@ -1056,14 +1099,58 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   if (cur + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
   arena.ensure(ctx, cur + 64); h2d(ctx, arena.p, hostArena.data(), cur); dev_memset(ctx, arena.p + cur, 0, 64);
   dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull; dev_memset(ctx, flagWord.p, 0, 16);
-  foreach(ctx, 1, DocCountKernel{arena.p, dc, flagWord.p, errWord.p});
-  u32 cnt[2]; d2h(ctx, cnt, flagWord.p, 8); sync(ctx); checkErr(actors);
-  const size_t N = cnt[0], S = cnt[1];
+  // Number of rows = values of the action column, number of succ entries = sum of succNum. Long columns take the parallel
+  // decoder (doccols.cuh); short, malformed or non-canonical ones the serial walkers, which also report the errors.
+  { const char* e = getenv("AMG_PAR_DOC_MIN"); if (e) parDocMinRows = (size_t)strtoull(e, nullptr, 10); }
+  size_t N = 0, S = 0; u32 serialMask = 0xffffu; bool counted = false;
+  auto colBytes = [&](int k) { return arena.p + dc.off[k]; };
+  auto ensureRows = [&]() {
+    for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff, &o_change, &o_time}) b->ensure(ctx, N + 1);
+  };
+  if (dc.len[8] >= parDocMinRows / 8 + 16) {   // (a long column can still be a handful of records; then the serial count is instant anyway)
+    u32 total = 0;
+    if (parCols.rleRecords(colBytes(8), dc.len[8], &total) && total >= parDocMinRows && total < (1u << 29)) {
+      N = total; ensureRows();
+      u64 sum = 0;
+      if (dc.len[13] == 0) { counted = true; S = 0; }
+      else if (parCols.countColumn(colBytes(13), dc.len[13], N, r_predNum.p, r_predOff.p, &sum)) { counted = true; S = (size_t)sum; serialMask &= ~(1u << 13); }
+    }
+  }
+  if (!counted) {
+    serialMask = 0xffffu;
+    foreach(ctx, 1, DocCountKernel{arena.p, dc, flagWord.p, errWord.p});
+    u32 cnt[2]; d2h(ctx, cnt, flagWord.p, 8); sync(ctx); checkErr(actors);
+    N = cnt[0]; S = cnt[1];
+  }
   if (N >= (1u << 29)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 2^29 document rows");
-  for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff, &o_change, &o_time}) b->ensure(ctx, N + 1);
+  ensureRows();
   r_predActor.ensure(ctx, S + 1); r_predCtr.ensure(ctx, S + 1);
   RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
-  foreach_warp(ctx, 16, DocColumnKernel{arena.p, dc, (u32)N, (u32)S, raw, o_change.p, o_time.p, errWord.p});
+  if (N >= parDocMinRows) {
+    struct Plan { int k, col; u32* out; };   // document column -> row field, as DocColumnKernel maps them
+    const Plan plan[] = {{0, CX_OBJ_ACTOR, raw.objActor}, {1, CX_OBJ_CTR, raw.objCtr}, {2, CX_KEY_ACTOR, raw.keyActor}, {3, CX_KEY_CTR, raw.keyCtr}, {4, CX_KEY_STR, nullptr},
+                         {5, CX_OBJ_ACTOR, o_change.p}, {6, CX_KEY_CTR, o_time.p}, {7, CX_INSERT, raw.insert}, {8, CX_ACTION, raw.action}, {9, CX_VAL_LEN, raw.valLen},
+                         {13, CX_PRED_NUM, raw.predNum}, {14, CX_PRED_ACTOR, raw.predActor}, {15, CX_PRED_CTR, raw.predCtr}};
+    for (const Plan& pl : plan) {
+      if (!((serialMask >> pl.k) & 1u)) continue;
+      const size_t cnt = (pl.k == 14 || pl.k == 15) ? S : N; const u32 len = dc.len[pl.k]; const u8* bytes = colBytes(pl.k); bool done = false;
+      if (len == 0) {
+        RawRows rr = raw; if (pl.k == 5) rr.objActor = o_change.p; if (pl.k == 6) rr.keyCtr = o_time.p;
+        if (cnt > 0) foreach(ctx, cnt, DocAbsentKernel{pl.col, rr});
+        done = true;
+      } else if (cnt > 0) switch (pl.col) {
+        case CX_OBJ_ACTOR: case CX_OBJ_CTR: case CX_KEY_ACTOR: case CX_ACTION: case CX_PRED_ACTOR: done = parCols.toU32(bytes, len, cnt, pl.out); break;
+        case CX_KEY_CTR: case CX_PRED_CTR: done = parCols.deltaToU32(bytes, len, cnt, pl.out); break;
+        case CX_INSERT: done = parCols.boolean(bytes, len, cnt, pl.out); break;
+        case CX_VAL_LEN: { u64 sum = 0; done = parCols.lenColumn(bytes, len, cnt, raw.valLen, raw.valOff, dc.off[10], &sum) && sum <= dc.len[10]; } break;
+        case CX_PRED_NUM: { u64 sum = 0; done = parCols.countColumn(bytes, len, cnt, raw.predNum, raw.predOff, &sum) && sum == S; } break;
+        default: break;   // utf8 keys: serial
+      }
+      if (done) serialMask &= ~(1u << pl.k);
+    }
+  }
+  if (getenv("AMG_PAR_DOC_TRACE")) fprintf(stderr, "amgpu load: %zu rows, %zu succ entries, columns left to the serial decoder: mask %04x (counted in parallel: %d)\n", N, S, serialMask & 0xe3ffu, counted ? 1 : 0);
+  if (serialMask & 0xe3ffu) foreach_warp(ctx, 16, DocColumnKernel{arena.p, dc, (u32)N, (u32)S, raw, o_change.p, o_time.p, errWord.p, serialMask});
   doc.ensure(ctx, N + 1); succOff.ensure(ctx, N + 2); succ.ensure(ctx, S + 1);
   DBuf<u64>& maxOpD = pairSucc; maxOpD.ensure(ctx, 1); dev_memset(ctx, maxOpD.p, 0, 8);
   foreach(ctx, N, DocFinalizeKernel{raw, o_change.p, o_time.p, (u32)actors.size(), doc.view(), succOff.p, succ.p, maxOpD.p, errWord.p});

@@ -80,8 +80,9 @@ struct DocCountKernel {   // thread 0: number of rows (action column), then sum 
   }
 };
 struct DocColumnKernel {   // one thread per document column; the change-column decoders are reused through a remapped row view
-  const u8* arena; DocCols c; u32 n, numSucc; RawRows rows; u32* idActor; u32* idCtr; u64* errWord;
+  const u8* arena; DocCols c; u32 n, numSucc; RawRows rows; u32* idActor; u32* idCtr; u64* errWord; u32 mask /* columns to decode here */;
   HD void operator()(size_t k) const {
+    if (!((mask >> k) & 1u)) return;
     RawRows r = rows; int col = -1;
     switch ((int)k) {
       case 0: col = CX_OBJ_ACTOR; break; case 1: col = CX_OBJ_CTR; break; case 2: col = CX_KEY_ACTOR; break; case 3: col = CX_KEY_CTR; break; case 4: col = CX_KEY_STR; break;
@@ -97,6 +98,42 @@ struct DocColumnKernel {   // one thread per document column; the change-column 
     if (e) raise(errWord, e, k);
   }
 };
+struct DocAbsentKernel {   // fill_absent_column for a long document, one thread per row (col as in DocColumnKernel, rows already remapped)
+  int col; RawRows r;
+  HD void operator()(size_t i) const {
+    switch (col) {
+      case CX_OBJ_ACTOR: r.objActor[i] = NULL32; break; case CX_OBJ_CTR: r.objCtr[i] = NULL32; break; case CX_KEY_ACTOR: r.keyActor[i] = NULL32; break;
+      case CX_KEY_CTR: r.keyCtr[i] = NULL32; break; case CX_ACTION: r.action[i] = NULL32; break;
+      case CX_VAL_LEN: r.valLen[i] = NULL32; r.valOff[i] = 0; break;
+      case CX_KEY_STR: r.keyStrOff[i] = 0; r.keyStrLen[i] = NULL32; break;
+      case CX_INSERT: r.insert[i] = 0; break;
+      case CX_PRED_NUM: r.predNum[i] = 0; r.predOff[i] = 0; break;
+      case CX_PRED_ACTOR: r.predActor[i] = NULL32; break; case CX_PRED_CTR: r.predCtr[i] = NULL32; break;
+      default: break;
+    }
+  }
+};
+struct DebugColumnKernel {   // amg_debug_decode_column, serial side: the readers of the load path on one column
+  int kind; const u8* bytes; u32 len; u32 n; long long* out; u32* tmp; u64* errWord;
+  HD void operator()(size_t) const {
+    u32 kerr = 0;
+    if (kind == 3) {
+      RawRows rr; memset(&rr, 0, sizeof(rr)); rr.insert = tmp;
+      kerr = decode_one_column(bytes, CX_INSERT, n, 0, 0, len, 0, 0, 0, 0, rr);
+      for (u32 i = 0; i < n; i++) out[i] = tmp[i];
+    } else {
+      RleReader r(bytes, 0, len, kind == 0 ? 0 : 1); long long acc = 0;
+      for (u32 i = 0; i < n; i++) {
+        long long v = 0; u32 o, l; const bool nn = r.next(v, o, l);
+        if (!nn) { out[i] = NULLV; continue; }
+        if (kind == 2) { acc += v; out[i] = acc; } else out[i] = v;
+      }
+      kerr = r.r.err;
+    }
+    if (kerr) raise(errWord, kerr, 0);
+  }
+};
+struct U32ToI64Kernel { const u32* in; long long* out; HD void operator()(size_t i) const { out[i] = in[i]; } };
 struct DocFinalizeKernel {
   RawRows raw; const u32* idActor; const u32* idCtr; u32 numActors; DocRows d; u32* succOff; u64* succ; u64* maxOp; u64* errWord;
   HD void operator()(size_t i) const {

@@ -400,6 +400,12 @@ struct DomLevelKernel {   // accumulate + stable split of every partition on `bi
     out[dst] = it; twOut[dst] = it.tw; wOut[dst] = it.w;
   }
 };
+// The last levels in shared memory. After the global levels on the high time bits every partition spans at most
+// 2^DOM_LOCAL_BITS distinct times, i.e. at most 2 * 2^DOM_LOCAL_BITS items (one query and one point per time at most), and
+// is contiguous: one CTA loads it and runs the remaining levels (same scan + stable split, on shared-memory arrays)
+// without touching HBM in between; queries then write their result.
+static const int DOM_LOCAL_BITS = 10, DOM_LOCAL_MAX = 2 << DOM_LOCAL_BITS;
+struct DomPartHeadKernel { const DomItem* items; u32* flag; HD void operator()(size_t i) const { flag[i] = items[i].gs == (u32)i ? 1u : 0u; } };
 struct DomResultKernel {   // route query results back by group start time
   const DomItem* items; u32* qIndex;
   HD void operator()(size_t i) const { if (dom_query(items[i].tw)) qIndex[dom_time(items[i].tw) - 1] = items[i].acc; }

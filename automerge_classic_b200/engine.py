@@ -71,7 +71,7 @@ class Library:
         L.amg_free_mem.argtypes = [vp]
         for name in ('amg_apply_changes', 'amg_apply_changes_packed', 'amg_get_patch', 'amg_get_state', 'amg_get_heads', 'amg_get_changes',
                      'amg_get_changes_added', 'amg_get_change_by_hash', 'amg_get_missing_deps', 'amg_clock_of', 'amg_hash_by_actor',
-                     'amg_debug_dump_ops', 'amg_debug_decode', 'amg_bench_decode', 'amg_last_timings'):
+                     'amg_debug_dump_ops', 'amg_debug_decode', 'amg_debug_decode_column', 'amg_bench_decode', 'amg_last_timings'):
             getattr(L, name).restype = C.c_int
 
     def check(self, rc, err):
@@ -414,6 +414,16 @@ class GpuBackendDoc:
         self._lib.L.amg_free_mem(rows)
         self._lib.L.amg_free_mem(succ)
         return r, s
+
+    def debug_decode_column(self, buf, kind, n, parallel):
+        """One document column through the parallel (True) or serial decoder; (rc, values, message), rc 1 = declined."""
+        out = np.zeros(max(n, 1), dtype=np.int64)
+        err = _ErrStruct()
+        raw = bytes(buf)
+        b = (C.c_uint8 * max(len(raw), 1)).from_buffer_copy(raw if raw else b'\0')
+        rc = self._lib.L.amg_debug_decode_column(self.h, b, C.c_size_t(len(raw)), C.c_int(kind), C.c_size_t(n), C.c_int(1 if parallel else 0),
+                                                 out.ctypes.data_as(C.c_void_p), C.byref(err))
+        return rc, out[:n].tolist(), err.msg.decode('utf-8', 'replace')
 
     def timings(self):
         out = (C.c_float * 24)()

@@ -119,6 +119,11 @@ uint64_t amg_kernel_launches(amg_backend* b);
 /* labelled host wall-clock marks of the last applyChanges call ("label=ms ..."), development aid */
 size_t amg_debug_marks(amg_backend* b, char* buf, size_t cap);
 void amg_free_mem(void* p);
+/* one column of a document through either decoder of the load path: kind 0 = RLE of unsigned numbers, 1 = RLE of signed
+ * numbers, 2 = delta column, 3 = boolean column; out[n] (INT64_MIN = null). parallel = 1: the token / record decoder for
+ * long columns (returns 1 without touching out when it declines the stream); parallel = 0: the serial walker (malformed
+ * input is an error, as in the reference). For differential tests of the two. */
+int amg_debug_decode_column(amg_backend* b, const uint8_t* bytes, size_t len, int kind, size_t n, int parallel, int64_t* out, amg_error* err);
 /* device-only re-run of the decode kernels over the last batch (inputs resident in HBM), for the roofline measurement */
 int amg_bench_decode(amg_backend* b, int iters, float* ms_sha, float* ms_parse, float* ms_decode, uint64_t* algo_bytes, amg_error* err);
 

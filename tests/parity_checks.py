@@ -314,3 +314,92 @@ def check_rust_document(gpu_doc):
     p = gpu_doc(RUST_DOC).get_patch()
     assert p['maxOp'] == 1 and p['clock'] == {'e45beec5e93442bb8a4b7368bec39fc8': 1}
     assert p['diffs']['props'] == {'birds': {'1@e45beec5e93442bb8a4b7368bec39fc8': {'type': 'value', 'value': 3.0, 'datatype': 'float64'}}}
+
+
+def check_column_decoders(Doc, seed, iters):
+    """Differential test of the two document-column decoders (include/amgpu.h amg_debug_decode_column): whenever the
+    parallel token / record decoder accepts a stream, the serial walker (the restatement of encoding.js:789-920,
+    1004-1051, 1141-1207 that reports errors like the reference) must accept it too and give the same values; canonical
+    streams from the Python codec must be accepted and decode to what was encoded."""
+    import random
+    from automerge_classic_b200 import columnar as K
+    g = Doc()
+    rnd = random.Random(seed)
+    NULLV = -(1 << 63)
+
+    def gen_values(n, kind):
+        vals = []
+        while len(vals) < n:
+            mode = rnd.random()
+            run = rnd.choice([1, 1, 2, 3, 5, 40, 200]) if rnd.random() < 0.7 else rnd.randint(1, 8)
+            if mode < 0.15:
+                vals += [None] * run
+            elif mode < 0.5:
+                v = rnd.choice([0, 1, 5, 127, 128, 300, 16383, 16384, 1 << 20, (1 << 32) + 5, (1 << 53) - 1]) if rnd.random() < 0.5 else rnd.randint(0, 1000)
+                vals += [-v if kind != 0 and rnd.random() < 0.5 else v] * run
+            else:
+                for _ in range(run):
+                    v = rnd.randint(0, 70000) if rnd.random() < 0.8 else rnd.randint(0, 1 << 40)
+                    vals.append(-v if kind != 0 and rnd.random() < 0.5 else v)
+        return vals[:n]
+
+    stats = {'taken': 0, 'declined': 0, 'serial_err': 0}
+
+    def compare(buf, kind, n, expect=None):
+        rs, vs, es = g.debug_decode_column(buf, kind, n, False)
+        rp, vp, ep = g.debug_decode_column(buf, kind, n, True)
+        if rp == 0:
+            stats['taken'] += 1
+            assert rs == 0, ('parallel decoder accepted what the serial decoder rejects', es, bytes(buf).hex()[:200], kind, n)
+            assert vs == vp, ('values differ', kind, n, bytes(buf).hex()[:200], [(i, a, b) for i, (a, b) in enumerate(zip(vs, vp)) if a != b][:5])
+        else:
+            assert rp == 1, (rp, ep)
+            stats['declined'] += 1
+        if rs != 0:
+            stats['serial_err'] += 1
+        if expect is not None:
+            assert rs == 0 and vs == expect, ('serial decoder differs from the Python codec', kind, n, es)
+        return rp
+
+    for _ in range(iters):
+        n = rnd.choice([1, 2, 3, 10, 100, 1000, 5000])
+        kind = rnd.choice([0, 1, 2, 3])
+        if kind == 3:
+            vals = []
+            while len(vals) < n:
+                vals += [rnd.random() < 0.5] * rnd.choice([1, 1, 2, 7, 100])
+            vals = vals[:n]
+            buf, exp = K.bool_encode(vals), [1 if v else 0 for v in vals]
+        elif kind == 2:
+            vals = [None if v is None else v % (1 << 30) for v in gen_values(n, 0)]
+            buf, exp = K.delta_encode(vals), [NULLV if v is None else v for v in vals]
+        else:
+            vals = gen_values(n, kind)
+            buf, exp = K.rle_encode(vals, 'uint' if kind == 0 else 'int'), [NULLV if v is None else v for v in vals]
+        if len(buf) == 0:
+            continue
+        assert compare(buf, kind, n, exp) == 0, ('canonical stream declined', kind, n, buf.hex()[:100])
+        for m in (n - 1, n + 1, n + 7):     # the column does not hold the expected number of values
+            if m > 0:
+                compare(buf, kind, m)
+        for _ in range(6):                  # corrupted streams
+            b = bytearray(buf)
+            op, p = rnd.random(), rnd.randrange(len(b))
+            if op < 0.4:
+                b[p] = rnd.randrange(256)
+            elif op < 0.7:
+                b.insert(p, rnd.randrange(256))
+            elif len(b) > 1:
+                del b[p]
+            compare(bytes(b), kind, n)
+        if kind in (0, 1) and n >= 2:       # decodable but not canonical: two encodings back to back
+            kk = 'uint' if kind == 0 else 'int'
+            compare(K.rle_encode(vals[:n // 2], kk) + K.rle_encode(vals[n // 2:], kk), kind, n)
+    assert stats['taken'] > iters // 2, stats
+    return stats
+
+
+def check_load_parallel_columns(Doc, oracle, cases):
+    """Backend.load with the parallel column decoders (doccols.cuh) on documents saved by the oracle."""
+    for cfg, n, a in cases:
+        check_load(Doc, oracle, cfg, n, a)

@@ -127,3 +127,20 @@ def test_load_saved_document(gpu_doc, oracle_mod, cfg, n, a):
 
 def test_load_rust_document(gpu_doc):
     parity_checks.check_rust_document(gpu_doc)
+
+
+@pytest.mark.parametrize('seed', [1, 2, 3, 4])
+def test_column_decoders(gpu_doc, seed):
+    parity_checks.check_column_decoders(gpu_doc, seed, 150)
+
+
+def test_load_parallel_columns_forced(gpu_doc, oracle_mod, monkeypatch):
+    monkeypatch.setenv('AMG_PAR_DOC_MIN', '1')   # every document takes the parallel column decoders (doccols.cuh)
+    parity_checks.check_load_parallel_columns(gpu_doc, oracle_mod, [('C2', 600, 0), ('C3', 6000, 3), ('C4', 3000, 4), ('C6', 500, 3), ('C7', 400, 3), ('C8', 400, 3)])
+    parity_checks.check_rust_document(gpu_doc)
+    parity_checks.check_save_after_load(gpu_doc, oracle_mod, 'C6', 300, 1)
+
+
+@pytest.mark.parametrize('cfg,n,a', [('C3', 60000, 10), ('C2', 30000, 0), ('C4', 40000, 10)])
+def test_load_long_document(gpu_doc, oracle_mod, cfg, n, a):
+    parity_checks.check_load(gpu_doc, oracle_mod, cfg, n, a)   # above the default row threshold of the parallel decoders

@@ -108,3 +108,15 @@ def test_load_saved_document_emu(emu_doc, oracle_mod, cfg, n, a):
 
 def test_load_rust_document_emu(emu_doc):
     parity_checks.check_rust_document(emu_doc)
+
+
+@pytest.mark.parametrize('seed', [1, 2, 3])
+def test_column_decoders_emu(emu_doc, seed):
+    parity_checks.check_column_decoders(emu_doc, seed, 120)
+
+
+def test_load_parallel_columns_emu(emu_doc, oracle_mod, monkeypatch):
+    monkeypatch.setenv('AMG_PAR_DOC_MIN', '1')   # every document takes the parallel column decoders (doccols.cuh)
+    parity_checks.check_load_parallel_columns(emu_doc, oracle_mod, [('C2', 600, 0), ('C3', 6000, 3), ('C4', 3000, 4), ('C6', 500, 3), ('C7', 400, 3), ('C8', 400, 3)])
+    parity_checks.check_rust_document(emu_doc)
+    parity_checks.check_save_after_load(emu_doc, oracle_mod, 'C6', 300, 1)
