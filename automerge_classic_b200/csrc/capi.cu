@@ -60,8 +60,8 @@ void setErr(amg_error* err, int code, const std::string& msg) {
   err->code = code; snprintf(err->msg, sizeof(err->msg), "%s", msg.c_str());
 }
 #define AMG_GUARD(...) \
-  try { __VA_ARGS__ } catch (amg::Error& e) { setErr(err, e.code, e.what()); return e.code; } \
-  catch (std::exception& e) { setErr(err, AMG_INTERNAL_ERROR, e.what()); return AMG_INTERNAL_ERROR; }
+  try { __VA_ARGS__ } catch (amg::Error& e) { amg::drop_pending_peeks(); setErr(err, e.code, e.what()); return e.code; } \
+  catch (std::exception& e) { amg::drop_pending_peeks(); setErr(err, AMG_INTERNAL_ERROR, e.what()); return AMG_INTERNAL_ERROR; }
 
 amg_patch* serialize(const PatchOut& p) { return new amg_patch{p.bytes, p.bytesLen}; }
 Hash toHash(const u8* p) { Hash h; memcpy(h.data(), p, 32); return h; }
@@ -103,8 +103,8 @@ amg_backend* amg_clone(amg_backend* src, amg_error* err) {
     d.actorSlots.ensure(c, d.actorCap); d.rebuildActorTable();
     sync(c);
     return b;
-  } catch (amg::Error& e) { setErr(err, e.code, e.what()); return nullptr; }
-  catch (std::exception& e) { setErr(err, AMG_INTERNAL_ERROR, e.what()); return nullptr; }
+  } catch (amg::Error& e) { amg::drop_pending_peeks(); setErr(err, e.code, e.what()); return nullptr; }
+  catch (std::exception& e) { amg::drop_pending_peeks(); setErr(err, AMG_INTERNAL_ERROR, e.what()); return nullptr; }
 }
 
 int amg_apply_changes(amg_backend* b, const uint8_t* const* bufs, const size_t* lens, size_t n, int is_local, int want_patch, amg_patch** out, amg_error* err) {

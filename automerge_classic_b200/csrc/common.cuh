@@ -49,6 +49,10 @@ struct Ctx {
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaStream_t copy = nullptr;        // third stream: device -> host copy of the uploaded change bytes into the host mirror
   cudaEvent_t evUp = nullptr, evMirror = nullptr; bool mirrorPending = false;
+  // small device -> host reads go through a kernel that stores into pinned (device-visible) host memory, not through the
+  // copy engine: a read of 4 bytes must not queue behind a 100 MB transfer (see d2h / sync)
+  struct Peek { void* dst; size_t off, bytes; };
+  unsigned char* peekBuf = nullptr; size_t peekCap = 0, peekUsed = 0; std::vector<Peek> peeks;
 #endif
   int device = 0;
   int numSMs = 148;
@@ -86,11 +90,27 @@ inline void h2d(Ctx& c, void* dst, const void* src, size_t bytes) {
   CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream));
 #endif
 }
+struct Ctx;
+inline Ctx*& last_peek_ctx() { static thread_local Ctx* p = nullptr; return p; }   // for drop_pending_peeks() in the C ABI's catch handlers
+#ifndef AMG_EMU
+static __global__ void k_peek_bytes(unsigned char* dstPinned, const unsigned char* src, size_t bytes) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes; i += (size_t)gridDim.x * blockDim.x) dstPinned[i] = src[i];
+}
+#endif
+// dst is valid after the next sync(c). Up to 16 KB: read by a kernel into the pinned staging buffer (sync() moves it to
+// dst); larger: an asynchronous copy.
 inline void d2h(Ctx& c, void* dst, const void* src, size_t bytes) {
   if (!bytes) return;
 #ifdef AMG_EMU
   memcpy(dst, src, bytes);
 #else
+  const size_t padded = (bytes + 15) & ~(size_t)15;
+  if (bytes <= (16u << 10) && c.peekBuf && c.peekUsed + padded <= c.peekCap) {
+    k_peek_bytes<<<(unsigned)((bytes + 255) / 256), 256, 0, c.stream>>>(c.peekBuf + c.peekUsed, (const unsigned char*)src, bytes);
+    CUDA_CHECK(cudaGetLastError());
+    c.peeks.push_back(Ctx::Peek{dst, c.peekUsed, bytes}); c.peekUsed += padded; last_peek_ctx() = &c; c.launches++;
+    return;
+  }
   CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
 #endif
 }
@@ -110,9 +130,18 @@ inline void d2d(Ctx& c, void* dst, const void* src, size_t bytes) {
   CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c.stream));
 #endif
 }
+inline void drop_peeks(Ctx& c) {   // after an aborted call: whatever was pending must not be delivered into dead stack frames
+#ifndef AMG_EMU
+  c.peeks.clear(); c.peekUsed = 0;
+#endif
+}
+inline void drop_pending_peeks() { if (last_peek_ctx()) drop_peeks(*last_peek_ctx()); }
 inline void sync(Ctx& c) {
 #ifndef AMG_EMU
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  cudaError_t e = cudaStreamSynchronize(c.stream);
+  if (e != cudaSuccess) { drop_peeks(c); CUDA_CHECK(e); }
+  for (const Ctx::Peek& p : c.peeks) memcpy(p.dst, c.peekBuf + p.off, p.bytes);
+  c.peeks.clear(); c.peekUsed = 0;
 #endif
 }
 
@@ -223,11 +252,9 @@ inline void mirror_start(Ctx& c, void* dstPinnedHost, const void* srcDev, size_t
   memcpy(dstPinnedHost, srcDev, bytes);
 #else
   CUDA_CHECK(cudaEventRecord(c.evUp, c.stream)); CUDA_CHECK(cudaStreamWaitEvent(c.copy, c.evUp, 0));
-  // in pieces: the small device -> host reads that size the pipeline stages share the copy engine with this transfer and
-  // can only slip in between two operations (one 132 MB copy held each of them up for its whole remaining time)
-  const size_t kPiece = 1u << 20;
-  for (size_t o = 0; o < bytes; o += kPiece)
-    CUDA_CHECK(cudaMemcpyAsync((char*)dstPinnedHost + o, (const char*)srcDev + o, std::min(kPiece, bytes - o), cudaMemcpyDeviceToHost, c.copy));
+  // (the small device -> host reads that size the pipeline stages do not use the copy engine, see d2h: behind this
+  // transfer each of them waited for all that was left of it, in one piece or in many)
+  CUDA_CHECK(cudaMemcpyAsync(dstPinnedHost, srcDev, bytes, cudaMemcpyDeviceToHost, c.copy));
   CUDA_CHECK(cudaEventRecord(c.evMirror, c.copy)); c.mirrorPending = true;
 #endif
 }

@@ -223,6 +223,27 @@ struct ParColumnDecoder {
     d2d(ctx, off, recOff.p, n * 4);
     return checkBad();
   }
+  // extraLen-style column of the change metadata: out = value (NULLV for null), strLen = value >> 4, strOff = base + running sum of those
+  bool extraLenColumn(const u8* bytes, size_t len, size_t n, long long* out, u32* strOff, u32* strLen, u32 base) {
+    if (!rle(bytes, len, false, n)) return false;
+    foreach(ctx, n, PcCopyI64Kernel{vals.p, out});
+    recOff.ensure(ctx, n + 3);
+    foreach(ctx, n, PcLenBytesKernel{vals.p, strLen, word.p});
+    scan_exclusive(ctx, st, strLen, recOff.p, n);
+    excl.ensure(ctx, n + 2); scan_exclusive64(ctx, st, PcDeltaInputU32{strLen}, excl.p, n);
+    u64 last = 0; u32 lastN = 0; d2h(ctx, &last, excl.p + n - 1, 8); d2h(ctx, &lastN, strLen + n - 1, 4); sync(ctx);
+    if (last + lastN + base > 0x7fffffffULL) return false;
+    d2d(ctx, strOff, recOff.p, n * 4); if (base) foreach(ctx, n, PcAddBaseKernel{strOff, base});
+    return checkBad();
+  }
+  // sum of the n values of a column of counts (nulls count as 0)
+  bool sumColumn(const u8* bytes, size_t len, size_t n, u64* sumOut) {
+    if (!rle(bytes, len, false, n)) return false;
+    excl.ensure(ctx, n + 2); scan_exclusive64(ctx, st, PcDeltaInput{vals.p}, excl.p, n);
+    u64 last = 0; long long lastV = 0; d2h(ctx, &last, excl.p + n - 1, 8); d2h(ctx, &lastV, vals.p + n - 1, 8); sync(ctx);
+    *sumOut = last + (lastV == NULLV ? 0ull : (u64)lastV);
+    return true;
+  }
   bool boolean(const u8* bytes, size_t len, size_t n, u32* out) {
     if (len == 0 || n == 0 || len >= 0x7fffffffULL) return false;
     if (!tokenize(bytes, len)) return false;

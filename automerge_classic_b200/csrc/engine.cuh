@@ -119,6 +119,7 @@ class Engine {
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.side, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.copy, cudaStreamNonBlocking));
+    ctx.peekCap = 1u << 20; CUDA_CHECK(cudaMallocHost((void**)&ctx.peekBuf, ctx.peekCap));
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evUp, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evMirror, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evFork, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evJoin, cudaEventDisableTiming));
     ShaConsts k; memcpy(k.k, SHA_K, sizeof(SHA_K)); CUDA_CHECK(cudaMemcpyToSymbol(c_sha, &k, sizeof(k)));
@@ -133,6 +134,8 @@ class Engine {
     mirror_wait(ctx);
     if (ctx.side) cudaStreamDestroy(ctx.side);
     if (ctx.copy) cudaStreamDestroy(ctx.copy);
+    if (ctx.peekBuf) cudaFreeHost(ctx.peekBuf);
+    if (last_peek_ctx() == &ctx) last_peek_ctx() = nullptr;
     if (ctx.evUp) cudaEventDestroy(ctx.evUp);
     if (ctx.evMirror) cudaEventDestroy(ctx.evMirror);
     if (ctx.evFork) cudaEventDestroy(ctx.evFork);

@@ -948,12 +948,26 @@ inline void Engine::saveDocument(std::string& result) {
     if (L > 0) {   // number of dependency indexes the loaded changes carry
       DBuf<u64>& sumD = pairSucc; sumD.ensure(ctx, 1);
       const HostChange& dn = loadedCol(0x40);
-      foreach_warp(ctx, 1, LoadedColKernel{LC_SUM, arena.p, dn.off, dn.len, 0, 0, nullptr, nullptr, nullptr, sumD.p});
-      u64 sum = 0; d2h(ctx, &sum, sumD.p, 8); sync(ctx); loadedDeps = (u32)sum;
+      u64 sum = 0;
+      if (!(L >= parDocMinRows && dn.len > 0 && parCols.sumColumn(arena.p + dn.off, dn.len, L, &sum))) {
+        foreach_warp(ctx, 1, LoadedColKernel{LC_SUM, arena.p, dn.off, dn.len, 0, 0, nullptr, nullptr, nullptr, sumD.p});
+        d2h(ctx, &sum, sumD.p, 8); sync(ctx);
+      }
+      loadedDeps = (u32)sum;
     }
     saveVals.ensure(ctx, std::max<size_t>(std::max(std::max(C, N), S), (size_t)loadedDeps + totalDeps) + 2);
     saveStrOff.ensure(ctx, std::max(C, N) + 1); saveStrLen.ensure(ctx, std::max(C, N) + 1);
-    auto loadedVal = [&](int kind, u32 id, u32 count) { if (L == 0) return; const HostChange& c = loadedCol(id); foreach_warp(ctx, 1, LoadedColKernel{kind, arena.p, c.off, c.len, loadedCol(0x57).off, count, saveVals.p, saveStrOff.p, saveStrLen.p, nullptr}); };
+    auto loadedVal = [&](int kind, u32 id, u32 count) {
+      if (L == 0) return; const HostChange& c = loadedCol(id);
+      if (count >= parDocMinRows && c.len > 0) {   // long history: the parallel column decoders (doccols.cuh); they decline what is not canonical
+        const u8* bytes = arena.p + c.off; bool ok = false;
+        if (kind == LC_UINT) ok = parCols.toI64(bytes, c.len, false, count, saveVals.p);
+        else if (kind == LC_DELTA) ok = parCols.deltaToI64(bytes, c.len, count, saveVals.p);
+        else if (kind == LC_EXTRA_LEN) ok = parCols.extraLenColumn(bytes, c.len, count, saveVals.p, saveStrOff.p, saveStrLen.p, loadedCol(0x57).off);
+        if (ok) return;
+      }
+      foreach_warp(ctx, 1, LoadedColKernel{kind, arena.p, c.off, c.len, loadedCol(0x57).off, count, saveVals.p, saveStrOff.p, saveStrLen.p, nullptr});
+    };
     auto changeVal = [&](int which) { if (K == 0) return; foreach(ctx, K, SaveChangeValKernel{which, arena.p, meta.p, actorSlots.p, (u64)actorCap - 1, saveVals.p + L, saveStrOff.p + L, saveStrLen.p + L, errWord.p}); };
     loadedVal(LC_UINT, 0x01, (u32)L);  changeVal(SM_ACTOR);     add(changeCols, 0x01, enc.rleNum(saveVals.p, C, false));
     loadedVal(LC_DELTA, 0x03, (u32)L); changeVal(SM_SEQ);       add(changeCols, 0x03, enc.deltaNum(saveVals.p, C));
@@ -1144,9 +1158,17 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
         case CX_INSERT: done = parCols.boolean(bytes, len, cnt, pl.out); break;
         case CX_VAL_LEN: { u64 sum = 0; done = parCols.lenColumn(bytes, len, cnt, raw.valLen, raw.valOff, dc.off[10], &sum) && sum <= dc.len[10]; } break;
         case CX_PRED_NUM: { u64 sum = 0; done = parCols.countColumn(bytes, len, cnt, raw.predNum, raw.predOff, &sum) && sum == S; } break;
-        default: break;   // utf8 keys: serial
+        default: break;   // utf8 keys: below
       }
       if (done) serialMask &= ~(1u << pl.k);
+    }
+    if ((serialMask >> 4) & 1u) {   // keyStr: serial over records, parallel over rows
+      DBuf<u32>& recStart = parCols.recOff; DBuf<u32>& recStrOff = parCols.recTok; DBuf<u32>& recStrLen = parCols.recN;
+      recStart.ensure(ctx, N + 3); recStrOff.ensure(ctx, N + 3); recStrLen.ensure(ctx, N + 3);
+      foreach_warp(ctx, 1, DocKeyStrRecordsKernel{arena.p, dc.off[4], dc.len[4], (u32)N, recStart.p, recStrOff.p, recStrLen.p, flagWord.p, errWord.p});
+      u32 rc[2]; d2h(ctx, rc, flagWord.p, 8); sync(ctx); checkErr(actors);
+      foreach(ctx, N, DocKeyStrExpandKernel{recStart.p, recStrOff.p, recStrLen.p, rc[0], raw.keyStrOff, raw.keyStrLen});
+      serialMask &= ~(1u << 4);
     }
   }
   if (getenv("AMG_PAR_DOC_TRACE")) fprintf(stderr, "amgpu load: %zu rows, %zu succ entries, columns left to the serial decoder: mask %04x (counted in parallel: %d)\n", N, S, serialMask & 0xe3ffu, counted ? 1 : 0);

@@ -98,6 +98,34 @@ struct DocColumnKernel {   // one thread per document column; the change-column 
     if (e) raise(errWord, e, k);
   }
 };
+// utf8 key column of a long document: one thread walks the records (a repetition or a null run is one step whatever its
+// length; only literal strings are visited one by one), every row then looks its record up. Same reader, same errors.
+struct DocKeyStrRecordsKernel {
+  const u8* arena; u32 off, len, n; u32* recStart; u32* recStrOff; u32* recStrLen; u32* numRecOut /* [0] records, [1] values covered */; u64* errWord;
+  HD void operator()(size_t) const {
+    RleReader a(arena, off, off + len, 2); u32 seen = 0, R = 0;
+    while (!a.done() && !a.r.err && seen < n) {
+      long long v; u32 o = 0, l = 0; const bool nn = a.next(v, o, l);
+      if (a.r.err) break;
+      u64 adv = 1;
+      if (a.state != 2 && a.count > 0) { adv += (u64)a.count; a.count = 0; }
+      if (seen + adv > n) adv = n - seen;
+      recStart[R] = seen; recStrOff[R] = nn ? o : 0; recStrLen[R] = nn ? l : NULL32; R++;
+      seen += (u32)adv;
+    }
+    if (a.r.err) raise(errWord, a.r.err, 4);
+    if (seen < n) { recStart[R] = seen; recStrOff[R] = 0; recStrLen[R] = NULL32; R++; }   // a reader past the end of the column yields null
+    recStart[R] = n; numRecOut[0] = R; numRecOut[1] = seen;
+  }
+};
+struct DocKeyStrExpandKernel {
+  const u32* recStart; const u32* recStrOff; const u32* recStrLen; u32 R; u32* keyStrOff; u32* keyStrLen;
+  HD void operator()(size_t i) const {
+    u32 lo = 0, hi = R;
+    while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (recStart[mid] <= (u32)i) lo = mid; else hi = mid; }
+    keyStrOff[i] = recStrOff[lo]; keyStrLen[i] = recStrLen[lo];
+  }
+};
 struct DocAbsentKernel {   // fill_absent_column for a long document, one thread per row (col as in DocColumnKernel, rows already remapped)
   int col; RawRows r;
   HD void operator()(size_t i) const {
