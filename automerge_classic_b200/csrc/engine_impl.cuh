@@ -120,8 +120,14 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     if (callerPinned) {
       // the caller's buffer is pinned: DMA straight from it; the host mirror is filled from the device copy by the copy
       // engine while the kernels run (a CPU copy of the same bytes took longer than the whole device pipeline)
-      h2d(ctx, arena.p + cur, blob + base, tot);   // (splitting the upload over two streams / copy engines was measured: no gain)
-      mirror_start(ctx, hostArena.data() + cur, arena.p + cur, tot);
+      // in pieces, so that the copy back of piece k (device -> host, the other PCIe direction) overlaps the upload of piece k + 1
+      // (splitting the upload itself over two streams / copy engines was measured: no gain)
+      const size_t kPiece = 16u << 20;
+      for (size_t o = 0; o < tot; o += kPiece) {
+        const size_t m = std::min(kPiece, tot - o);
+        h2d(ctx, arena.p + cur + o, blob + base + o, m);
+        mirror_start(ctx, hostArena.data() + cur + o, arena.p + cur + o, m);
+      }
       dbgMark("stage:h2d-enqueued");
     } else {
       const size_t kChunk = 32u << 20;   // copy into the pinned mirror and upload chunk by chunk (H2D overlaps the next host copy)
@@ -558,6 +564,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     out.hasActorSeq = true; out.actor.assign((const char*)hostArena.data() + m0[0].actorOff, m0[0].actorLen); out.seq = m0[0].seq;
   }
   dbgMark("commit:end");
+  mirror_wait(ctx); dbgMark("commit:mirror-done");
   lastB = B; lastM = M; lastP = P; lastBytes = cur - arenaLen0; for (auto& c : queue) lastBytes += 0 * c.len;
   finishPatch(out);
   timer.collect(lastPhaseMs, 12);
@@ -1067,19 +1074,44 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
     for (u64 i = 0; i < n && !r.err; i++) { const u64 id = r.uleb(), l = r.uleb(); if (last >= 0 && ((u32)id & ~8u) <= ((u32)last & ~8u)) throw Error(AMG_ERR_RANGE, "Columns must be in ascending order"); last = (long long)id; cols.push_back({(u32)id, l, std::string()}); }
   };
   std::vector<ColInfo> changeCols, opCols; readInfo(changeCols); readInfo(opCols);
+  std::vector<std::pair<ColInfo*, const u8*>> deflated;
   auto readData = [&](std::vector<ColInfo>& cols) {
     for (auto& c : cols) {
       if (r.err || (u64)r.pos + c.len > len) throw Error(AMG_ERR_RANGE, "subarray exceeds buffer size");
-      if (c.id & 8) { c.data = inflateRawBytes(buf + r.pos, (size_t)c.len); c.id ^= 8; } else c.data.assign((const char*)buf + r.pos, (size_t)c.len);
+      if (c.id & 8) deflated.emplace_back(&c, buf + r.pos); else c.data.assign((const char*)buf + r.pos, (size_t)c.len);
       r.skip(c.len);
     }
   };
   readData(changeCols); readData(opCols);
+  {   // DEFLATEd columns (columnar.js:1022-1027): independent streams, one host thread each when there are several large ones
+    std::vector<std::string> errs(deflated.size()); std::vector<int> codes(deflated.size(), 0); std::vector<std::thread> ts;
+    auto one = [&](size_t k) { try { ColInfo& c = *deflated[k].first; c.data = inflateRawBytes(deflated[k].second, (size_t)c.len); c.id ^= 8; } catch (Error& e) { errs[k] = e.what(); codes[k] = e.code; } catch (std::exception& e) { errs[k] = e.what(); codes[k] = AMG_ERR_INTERNAL; } };
+    for (size_t k = 0; k < deflated.size(); k++) { if (deflated.size() > 1 && deflated[k].first->len >= (64u << 10)) ts.emplace_back(one, k); else one(k); }
+    for (auto& t : ts) t.join();
+    for (size_t k = 0; k < errs.size(); k++) if (codes[k]) throw Error(codes[k], errs[k]);   // the first in column order, as a sequential reader would meet it
+  }
   if (r.err) throw Error(AMG_ERR_RANGE, "buffer ended with incomplete number");
   std::vector<u32> headsIndexes; if (!r.done()) for (u64 i = 0; i < numHeads; i++) headsIndexes.push_back((u32)r.uleb());
   if (actors.size() > 65535) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 65535 actors in one document");
-  // ---- change metadata: clock (new.js:1645-1675 readDocumentChanges). Two small columns, decoded with the same readers on the host.
+  // ---- stage actor ids and op columns in the arena
+  static const u32 DOC_IDS[16] = {0x01, 0x02, 0x11, 0x13, 0x15, 0x21, 0x23, 0x34, 0x42, 0x56, 0x57, 0x61, 0x63, 0x80, 0x81, 0x83};
+  DocCols dc; memset(&dc, 0, sizeof(dc));
+  hostArena.resize(0); std::vector<std::pair<u32, u32>> reps;
+  for (auto& a : actors) { reps.emplace_back((u32)hostArena.size(), (u32)a.size()); hostArena.append(a.data(), a.size()); }
+  for (auto& c : opCols) for (int k = 0; k < 16; k++) if (c.id == DOC_IDS[k]) { dc.off[k] = (u32)hostArena.size(); dc.len[k] = (u32)c.data.size(); hostArena.append(c.data.data(), c.data.size()); }
+  {   // the change metadata columns stay available for a later save() (new.js:1717 keeps them as encoders)
+    static const u32 CHANGE_IDS[9] = {0x01, 0x03, 0x13, 0x23, 0x35, 0x40, 0x43, 0x56, 0x57};
+    for (int k = 0; k < 9; k++) loadedCols[k] = HostChange{(u32)hostArena.size(), 0};
+    for (auto& c : changeCols) for (int k = 0; k < 9; k++) if (c.id == CHANGE_IDS[k]) { loadedCols[k] = HostChange{(u32)hostArena.size(), (u32)c.data.size()}; hostArena.append(c.data.data(), c.data.size()); }
+  }
+  const size_t cur = hostArena.size();
+  if (cur + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
+  arena.ensure(ctx, cur + 64); h2d(ctx, arena.p, hostArena.data(), cur); dev_memset(ctx, arena.p + cur, 0, 64);
+  // ---- change metadata: clock (new.js:1645-1675 readDocumentChanges). A long history is decoded and checked on the device
+  // (doccols.cuh + one stable sort by actor); a short one, or one the device path declines (malformed columns, a sequence
+  // error to report), by the same readers on the host, which produce the reference's error messages.
   std::vector<u64> clk(actors.size(), 0); size_t numChanges = 0;
+  auto hostClock = [&]()
   {
     const std::string* actorCol = nullptr; const std::string* seqCol = nullptr;
     for (auto& c : changeCols) { if (c.id == 0x01) actorCol = &c.data; if (c.id == 0x03) seqCol = &c.data; }
@@ -1095,23 +1127,25 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
       if (seq != 1 && seq != clk[a] + 1) throw Error(AMG_ERR_RANGE, "Expected seq " + std::to_string(clk[a] + 1) + ", got " + std::to_string(seq) + " for actor " + hex_of((const u8*)actors[a].data(), actors[a].size()));
       clk[a] = seq; numChanges++;
     }
+  };
+  {
+    bool onDevice = false; const HostChange ac = loadedCols[0], sc = loadedCols[1]; u32 total = 0;
+    if (ac.len >= parDocMinRows / 8 + 16 && sc.len > 0 && parCols.rleRecords(arena.p + ac.off, ac.len, &total) && total >= parDocMinRows) {
+      const size_t n = total; DBuf<long long> aV, sV; aV.ensure(ctx, n + 1); sV.ensure(ctx, n + 1);
+      if (parCols.toI64(arena.p + ac.off, ac.len, false, n, aV.p) && parCols.deltaToI64(arena.p + sc.off, sc.len, n, sV.p)) {
+        sortKeys.ensure(ctx, n + 1); sortVals.ensure(ctx, n + 1); DBuf<u64> clkD; clkD.ensure(ctx, actors.size() + 1); dev_memset(ctx, clkD.p, 0, (actors.size() + 1) * 8);
+        dev_memset(ctx, flagWord.p, 0, 16);
+        foreach(ctx, n, ClockKeyKernel{aV.p, (u32)actors.size(), sortKeys.p, sortVals.p, flagWord.p});
+        sortPairs(sortKeys, sortVals, n, bits_for(actors.size() > 1 ? actors.size() - 1 : 1));
+        foreach(ctx, n, ClockCheckKernel{sortKeys.p, sortVals.p, sV.p, (u32)n, clkD.p, flagWord.p});
+        u32 bad = 0; d2h(ctx, &bad, flagWord.p, 4); if (!actors.empty()) d2h(ctx, clk.data(), clkD.p, actors.size() * 8); sync(ctx);
+        if (!bad) { onDevice = true; numChanges = n; } else std::fill(clk.begin(), clk.end(), 0);
+      }
+    }
+    if (!onDevice) hostClock();
   }
   if (!headsIndexes.empty() && headsIndexes.size() != hs.size()) headsIndexes.clear();
   if (headsIndexes.empty()) { if (hs.size() == 1) headsIndexes.push_back((u32)(numChanges ? numChanges - 1 : 0)); else if (!hs.empty()) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: document without head indexes and several heads (needs decodeDocument, not built)"); }
-  // ---- stage actor ids and op columns in the arena
-  static const u32 DOC_IDS[16] = {0x01, 0x02, 0x11, 0x13, 0x15, 0x21, 0x23, 0x34, 0x42, 0x56, 0x57, 0x61, 0x63, 0x80, 0x81, 0x83};
-  DocCols dc; memset(&dc, 0, sizeof(dc));
-  hostArena.resize(0); std::vector<std::pair<u32, u32>> reps;
-  for (auto& a : actors) { reps.emplace_back((u32)hostArena.size(), (u32)a.size()); hostArena.append(a.data(), a.size()); }
-  for (auto& c : opCols) for (int k = 0; k < 16; k++) if (c.id == DOC_IDS[k]) { dc.off[k] = (u32)hostArena.size(); dc.len[k] = (u32)c.data.size(); hostArena.append(c.data.data(), c.data.size()); }
-  {   // the change metadata columns stay available for a later save() (new.js:1717 keeps them as encoders)
-    static const u32 CHANGE_IDS[9] = {0x01, 0x03, 0x13, 0x23, 0x35, 0x40, 0x43, 0x56, 0x57};
-    for (int k = 0; k < 9; k++) loadedCols[k] = HostChange{(u32)hostArena.size(), 0};
-    for (auto& c : changeCols) for (int k = 0; k < 9; k++) if (c.id == CHANGE_IDS[k]) { loadedCols[k] = HostChange{(u32)hostArena.size(), (u32)c.data.size()}; hostArena.append(c.data.data(), c.data.size()); }
-  }
-  const size_t cur = hostArena.size();
-  if (cur + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
-  arena.ensure(ctx, cur + 64); h2d(ctx, arena.p, hostArena.data(), cur); dev_memset(ctx, arena.p + cur, 0, 64);
   dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull; dev_memset(ctx, flagWord.p, 0, 16);
   // Number of rows = values of the action column, number of succ entries = sum of succNum. Long columns take the parallel
   // decoder (doccols.cuh); short, malformed or non-canonical ones the serial walkers, which also report the errors.

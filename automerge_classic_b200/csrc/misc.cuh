@@ -126,6 +126,19 @@ struct DocKeyStrExpandKernel {
     keyStrOff[i] = recStrOff[lo]; keyStrLen[i] = recStrLen[lo];
   }
 };
+// clock of a long loaded document (new.js:1645-1675 readDocumentChanges): changes sorted by actor (stable), every change
+// compared with the same actor's previous one
+struct ClockKeyKernel { const long long* actor; u32 numActors; u64* key; u32* val; u32* bad; HD void operator()(size_t i) const { const long long a = actor[i]; if (a == NULLV || a < 0 || (u64)a >= numActors) { *bad = 1; key[i] = 0; } else key[i] = (u64)a; val[i] = (u32)i; } };
+struct ClockCheckKernel {
+  const u64* key; const u32* val; const long long* seq; u32 n; u64* clock; u32* bad;
+  HD void operator()(size_t j) const {
+    const u32 i = val[j]; const long long s = seq[i] == NULLV ? 0 : seq[i];
+    const bool havePrev = j > 0 && key[j - 1] == key[j];
+    const long long ps = havePrev ? (seq[val[j - 1]] == NULLV ? 0 : seq[val[j - 1]]) : 0;
+    if (!(s == 1 || (havePrev && s == ps + 1)) || s < 0) *bad = 1;
+    if (j + 1 == n || key[j + 1] != key[j]) clock[key[j]] = (u64)s;
+  }
+};
 struct DocAbsentKernel {   // fill_absent_column for a long document, one thread per row (col as in DocColumnKernel, rows already remapped)
   int col; RawRows r;
   HD void operator()(size_t i) const {
