@@ -17,6 +17,9 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <unordered_map>
+#include <mutex>
+#include <map>
 
 #ifdef AMG_EMU
 #define HD inline
@@ -60,18 +63,49 @@ struct Ctx {
 };
 
 // ---------------------------------------------------------------- device buffers
+#ifndef AMG_EMU
+// Process-wide cache of freed device blocks, per device. cudaMalloc / cudaFree cost 0.1 - 1 ms each (they map and unmap
+// memory); a fresh document allocates ~200 tables, so opening documents in a long-lived process was bound by them.
+// A freed block is parked after a device synchronize (what cudaFree does implicitly: nothing in flight still uses it)
+// and handed to the next request of about that size (at most 1.5x). Parked memory is capped, and given back to the
+// driver when an allocation fails.
+struct DevPool {
+  typedef std::pair<int, size_t> Key;   // (device, block bytes)
+  std::mutex m; std::multimap<Key, void*> parked; std::unordered_map<void*, Key> blocks; size_t parkedBytes = 0;
+  static const size_t kMaxParked = 32ull << 30;
+  static DevPool& get() { static DevPool* p = new DevPool(); return *p; }   // never destroyed: must outlive every engine and the runtime's own teardown
+  void trim() { for (auto& kv : parked) { blocks.erase(kv.second); cudaFree(kv.second); } parked.clear(); parkedBytes = 0; }
+};
+#endif
 inline void* dev_alloc(size_t bytes) {
 #ifdef AMG_EMU
   return malloc(bytes ? bytes : 1);
 #else
-  void* p = nullptr; CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1)); return p;
+  const size_t want = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
+  int dev = 0; CUDA_CHECK(cudaGetDevice(&dev));
+  DevPool& pool = DevPool::get(); std::lock_guard<std::mutex> lock(pool.m);
+  auto it = pool.parked.lower_bound(DevPool::Key(dev, want));
+  if (it != pool.parked.end() && it->first.first == dev && it->first.second <= want + want / 2 + 4096) {
+    void* p = it->second; pool.parkedBytes -= it->first.second; pool.parked.erase(it); return p;
+  }
+  void* p = nullptr; cudaError_t e = cudaMalloc(&p, want);
+  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); pool.trim(); e = cudaMalloc(&p, want); }
+  CUDA_CHECK(e);
+  pool.blocks[p] = DevPool::Key(dev, want);
+  return p;
 #endif
 }
 inline void dev_free(void* p) {
 #ifdef AMG_EMU
   free(p);
 #else
-  if (p) cudaFree(p);
+  if (!p) return;
+  cudaDeviceSynchronize();
+  DevPool& pool = DevPool::get(); std::lock_guard<std::mutex> lock(pool.m);
+  auto it = pool.blocks.find(p);
+  if (it == pool.blocks.end()) { cudaFree(p); return; }
+  if (pool.parkedBytes + it->second.second > DevPool::kMaxParked) { pool.blocks.erase(it); cudaFree(p); return; }
+  pool.parked.emplace(it->second, p); pool.parkedBytes += it->second.second;
 #endif
 }
 inline void dev_memset(Ctx& c, void* p, int v, size_t bytes) {

@@ -1055,6 +1055,8 @@ inline void Engine::saveDocument(std::string& result) {
 // as in SURVEY.md §2 row 12; column expansion and everything downstream run on the device.
 inline void Engine::loadDocument(const u8* buf, size_t len) {
   if (numApplied != 0 || numRows != 0) throw Error(AMG_ERR_INTERNAL, "load needs a fresh backend");
+  HostClock lclk; const bool ltrace = getenv("AMG_PAR_DOC_TRACE") != nullptr;
+  auto lmark = [&](const char* what) { if (ltrace) { sync(ctx); fprintf(stderr, "amgpu load: %-28s %8.2f ms\n", what, lclk.ms()); } };
   // columnar.js:688-708 decodeContainerHeader
   if (len < 10 || buf[0] != 0x85 || buf[1] != 0x6f || buf[2] != 0x4a || buf[3] != 0x83) throw Error(AMG_ERR_RANGE, "Data does not begin with magic bytes 85 6f 4a 83");
   ByteReader r(buf, 8, (u32)len); const u32 chunkType = buf[8]; r.pos = 9; const u64 chunkLen = r.uleb();
@@ -1063,6 +1065,7 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   if (memcmp(digest, buf + 4, 4) != 0) throw Error(AMG_ERR_RANGE, "checksum does not match data");
   if ((u64)r.pos + chunkLen != len) throw Error(AMG_ERR_RANGE, "Encoded document has trailing data");
   if (chunkType != 0) throw Error(AMG_ERR_RANGE, "Unexpected chunk type: " + std::to_string(chunkType));
+  lmark("container checksum");
   // columnar.js:1006-1038 decodeDocumentHeader
   std::vector<std::string> actors; const u64 numActors = r.uleb();
   for (u64 i = 0; i < numActors && !r.err; i++) { const u64 l = r.uleb(); if ((u64)r.pos + l > len) { r.err = KE_TRUNCATED; break; } actors.emplace_back((const char*)buf + r.pos, l); r.skip(l); }
@@ -1090,6 +1093,7 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
     for (auto& t : ts) t.join();
     for (size_t k = 0; k < errs.size(); k++) if (codes[k]) throw Error(codes[k], errs[k]);   // the first in column order, as a sequential reader would meet it
   }
+  lmark("columns inflated");
   if (r.err) throw Error(AMG_ERR_RANGE, "buffer ended with incomplete number");
   std::vector<u32> headsIndexes; if (!r.done()) for (u64 i = 0; i < numHeads; i++) headsIndexes.push_back((u32)r.uleb());
   if (actors.size() > 65535) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 65535 actors in one document");
@@ -1107,6 +1111,7 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   const size_t cur = hostArena.size();
   if (cur + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
   arena.ensure(ctx, cur + 64); h2d(ctx, arena.p, hostArena.data(), cur); dev_memset(ctx, arena.p + cur, 0, 64);
+  lmark("staged + uploaded");
   // ---- change metadata: clock (new.js:1645-1675 readDocumentChanges). A long history is decoded and checked on the device
   // (doccols.cuh + one stable sort by actor); a short one, or one the device path declines (malformed columns, a sequence
   // error to report), by the same readers on the host, which produce the reference's error messages.
@@ -1144,6 +1149,7 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
     }
     if (!onDevice) hostClock();
   }
+  lmark("clock");
   if (!headsIndexes.empty() && headsIndexes.size() != hs.size()) headsIndexes.clear();
   if (headsIndexes.empty()) { if (hs.size() == 1) headsIndexes.push_back((u32)(numChanges ? numChanges - 1 : 0)); else if (!hs.empty()) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: document without head indexes and several heads (needs decodeDocument, not built)"); }
   dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull; dev_memset(ctx, flagWord.p, 0, 16);
@@ -1164,12 +1170,23 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
       else if (parCols.countColumn(colBytes(13), dc.len[13], N, r_predNum.p, r_predOff.p, &sum)) { counted = true; S = (size_t)sum; serialMask &= ~(1u << 13); }
     }
   }
+  if (!counted) {   // short action column: rows by the serial record walk, the succ total still in parallel if there are many rows
+    serialMask = 0xffffu;
+    foreach(ctx, 1, DocCountRowsKernel{arena.p, dc, flagWord.p, errWord.p});
+    u32 n32 = 0; d2h(ctx, &n32, flagWord.p, 4); sync(ctx); checkErr(actors);
+    if (n32 >= parDocMinRows && n32 < (1u << 29)) {
+      N = n32; ensureRows(); u64 sum = 0;
+      if (dc.len[13] == 0) { counted = true; S = 0; }
+      else if (parCols.countColumn(colBytes(13), dc.len[13], N, r_predNum.p, r_predOff.p, &sum)) { counted = true; S = (size_t)sum; serialMask &= ~(1u << 13); }
+    }
+  }
   if (!counted) {
     serialMask = 0xffffu;
     foreach(ctx, 1, DocCountKernel{arena.p, dc, flagWord.p, errWord.p});
     u32 cnt[2]; d2h(ctx, cnt, flagWord.p, 8); sync(ctx); checkErr(actors);
     N = cnt[0]; S = cnt[1];
   }
+  lmark("rows counted");
   if (N >= (1u << 29)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 2^29 document rows");
   ensureRows();
   r_predActor.ensure(ctx, S + 1); r_predCtr.ensure(ctx, S + 1);
@@ -1207,11 +1224,13 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   }
   if (getenv("AMG_PAR_DOC_TRACE")) fprintf(stderr, "amgpu load: %zu rows, %zu succ entries, columns left to the serial decoder: mask %04x (counted in parallel: %d)\n", N, S, serialMask & 0xe3ffu, counted ? 1 : 0);
   if (serialMask & 0xe3ffu) foreach_warp(ctx, 16, DocColumnKernel{arena.p, dc, (u32)N, (u32)S, raw, o_change.p, o_time.p, errWord.p, serialMask});
+  lmark("columns decoded");
   doc.ensure(ctx, N + 1); succOff.ensure(ctx, N + 2); succ.ensure(ctx, S + 1);
   DBuf<u64>& maxOpD = pairSucc; maxOpD.ensure(ctx, 1); dev_memset(ctx, maxOpD.p, 0, 8);
   foreach(ctx, N, DocFinalizeKernel{raw, o_change.p, o_time.p, (u32)actors.size(), doc.view(), succOff.p, succ.p, maxOpD.p, errWord.p});
   { const u32 s32 = (u32)S; h2d(ctx, succOff.p + N, &s32, 4); }
   u64 mx = 0; d2h(ctx, &mx, maxOpD.p, 8); sync(ctx); checkErr(actors);
+  lmark("rows finalized");
   // ---- change history placeholders: only the head hashes are known (new.js:1727-1739)
   hashes.ensure(ctx, numChanges * 32 + 64); dev_memset(ctx, hashes.p, 0, numChanges * 32 + 64);
   for (size_t i = 0; i < hs.size(); i++) { if (headsIndexes[i] >= numChanges) throw Error(AMG_ERR_RANGE, "head index out of range"); h2d(ctx, hashes.p + (size_t)headsIndexes[i] * 32, hs[i].data(), 32); }
@@ -1221,6 +1240,7 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   { std::vector<size_t> o(heads.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i; std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return hs[a] < hs[b]; });
     for (size_t i = 0; i < o.size(); i++) { heads[i] = hs[o[i]]; headIdx[i] = headsIndexes[o[i]]; } }
   changes.assign(numChanges, HostChange{0, 0}); haveHashGraph = false; loadedDoc.assign((const char*)buf, len); numLoaded = numChanges;
+  lmark("host state");
   while (actorCap < 2 * (actorIds.size() + 16)) actorCap *= 2;
   actorSlots.ensure(ctx, actorCap); rebuildActorTable();
 }

@@ -79,6 +79,10 @@ struct DocCountKernel {   // thread 0: number of rows (action column), then sum 
     out[0] = n; out[1] = (u32)s;
   }
 };
+struct DocCountRowsKernel {   // rows only; the walk is by record, so a column of a few long runs costs nothing
+  const u8* arena; DocCols c; u32* out; u64* errWord;
+  HD void operator()(size_t) const { u32 err = 0; out[0] = rle_count_values(arena, c.off[8], c.off[8] + c.len[8], &err); if (err) raise(errWord, err, 0); }
+};
 struct DocColumnKernel {   // one thread per document column; the change-column decoders are reused through a remapped row view
   const u8* arena; DocCols c; u32 n, numSucc; RawRows rows; u32* idActor; u32* idCtr; u64* errWord; u32 mask /* columns to decode here */;
   HD void operator()(size_t k) const {

@@ -187,6 +187,7 @@ def main():
     sampler.stop_flag = True
     launches = (doc.launches() - launches0) // max(args.steps, 1)
     t_wall, t_dev = sum(wall) / len(wall), sum(dev) / len(dev)
+    wall_steps, dev_steps = list(wall), list(dev)
     if world > 1:   # a step ends when the slowest rank is done
         tt = torch.tensor([t_wall, t_dev], dtype=torch.float64, device='cuda')
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -263,7 +264,7 @@ def main():
             'config': {'workload': 'C3 text trace: makeText + 10 actors x 100k single-op changes, 70% insert / 30% delete (SURVEY.md 8d); one independent document per GPU (C5)',
                        'ops_per_gpu': trace.n_ops, 'changes_per_gpu': trace.n_changes, 'change_bytes_per_gpu': nbytes, 'parallelism': 'replicas x%d' % world,
                        'l2': 'inputs (%.0f MB) + working tables exceed the 126 MB L2; document reset every step' % (nbytes / 1e6),
-                       'device_ms_per_step': t_dev * 1e3,
+                       'device_ms_per_step': t_dev * 1e3, 'wall_ms_steps': [round(x * 1e3, 3) for x in wall_steps], 'device_ms_steps': [round(x * 1e3, 3) for x in dev_steps],
                        'phase_ms_last_step': dict(zip(['stage_upload', 'sha256', 'parse_gate', 'actors_decode', 'opset', 'patch_groups_props', 'patch_list_index', 'patch_edits_copyout', 'heads_commit'], [round(x, 3) for x in last_ph[:9]])),
                        'host_marks_ms': [round(x, 3) for x in last_ph[12:22]], 'other_paths': other},
             'e2e': {'value': total_ops / t_wall, 'unit': 'ops/s', 'h2d_bytes_per_step': nbytes + 8 * (trace.n_changes + 1), 'd2h_bytes_per_step': patch_bytes},
