@@ -112,8 +112,8 @@ int amg_apply_changes(amg_backend* b, const uint8_t* const* bufs, const size_t* 
             if (out) *out = want_patch ? serialize(p) : nullptr; return 0;)
 }
 int amg_apply_changes_packed(amg_backend* b, const uint8_t* blob, const uint64_t* offsets, size_t n, int is_local, int want_patch, amg_patch** out, amg_error* err) {
-  AMG_GUARD(PatchOut p; b->eng.applyChanges(nullptr, nullptr, n, blob, (const u64*)offsets, is_local != 0, want_patch != 0, p);
-            if (out) *out = want_patch ? serialize(p) : nullptr; return 0;)
+  AMG_GUARD(amg::HostClock whole; { PatchOut p; b->eng.applyChanges(nullptr, nullptr, n, blob, (const u64*)offsets, is_local != 0, want_patch != 0, p);
+            if (out) *out = want_patch ? serialize(p) : nullptr; } b->eng.lastPhaseMs[23] = whole.ms(); return 0;)   // [23]: the whole call as the ABI sees it
 }
 int amg_get_patch(amg_backend* b, amg_patch** out, amg_error* err) {
   AMG_GUARD(PatchOut p; b->eng.getPatch(p); *out = serialize(p); return 0;)

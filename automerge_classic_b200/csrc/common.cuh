@@ -52,6 +52,7 @@ struct Ctx {
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaStream_t copy = nullptr;        // third stream: device -> host copy of the uploaded change bytes into the host mirror
   cudaEvent_t evUp = nullptr, evMirror = nullptr; bool mirrorPending = false;
+  cudaEvent_t phaseEv[13]; bool phaseEvReady = false;   // phase timing of the last call (PhaseTimer)
   // small device -> host reads go through a kernel that stores into pinned (device-visible) host memory, not through the
   // copy engine: a read of 4 bytes must not queue behind a 100 MB transfer (see d2h / sync)
   struct Peek { void* dst; size_t off, bytes; };

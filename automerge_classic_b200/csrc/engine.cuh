@@ -135,6 +135,7 @@ class Engine {
     if (ctx.side) cudaStreamDestroy(ctx.side);
     if (ctx.copy) cudaStreamDestroy(ctx.copy);
     if (ctx.peekBuf) cudaFreeHost(ctx.peekBuf);
+    if (ctx.phaseEvReady) for (auto& e : ctx.phaseEv) cudaEventDestroy(e);
     if (last_peek_ctx() == &ctx) last_peek_ctx() = nullptr;
     if (ctx.evUp) cudaEventDestroy(ctx.evUp);
     if (ctx.evMirror) cudaEventDestroy(ctx.evMirror);

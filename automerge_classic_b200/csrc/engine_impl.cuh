@@ -12,9 +12,8 @@ struct HostClock {
 };
 struct PhaseTimer {
 #ifndef AMG_EMU
-  cudaEvent_t ev[13]; int n = 0; Ctx* c;
-  explicit PhaseTimer(Ctx& ctx) : c(&ctx) { for (auto& e : ev) cudaEventCreate(&e); mark(); }
-  ~PhaseTimer() { for (auto& e : ev) cudaEventDestroy(e); }
+  cudaEvent_t* ev; int n = 0; Ctx* c;   // the events live in the context: creating and destroying 13 timing events per call cost more than a pipeline phase
+  explicit PhaseTimer(Ctx& ctx) : ev(ctx.phaseEv), c(&ctx) { if (!ctx.phaseEvReady) { for (int i = 0; i < 13; i++) cudaEventCreate(&ev[i]); ctx.phaseEvReady = true; } mark(); }
   void mark() { if (n < 13) cudaEventRecord(ev[n++], c->stream); }
   void collect(float* out, int maxN) { cudaEventSynchronize(ev[n - 1]); for (int i = 0; i + 1 < n && i < maxN; i++) cudaEventElapsedTime(&out[i], ev[i], ev[i + 1]); }
 #else
@@ -566,8 +565,8 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
   dbgMark("commit:end");
   mirror_wait(ctx); dbgMark("commit:mirror-done");
   lastB = B; lastM = M; lastP = P; lastBytes = cur - arenaLen0; for (auto& c : queue) lastBytes += 0 * c.len;
-  finishPatch(out);
-  timer.collect(lastPhaseMs, 12);
+  finishPatch(out); dbgMark("call:patch-finished");
+  timer.collect(lastPhaseMs, 12); dbgMark("call:timers-collected");
 }
 
 }  // namespace amg
@@ -1101,6 +1100,7 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   static const u32 DOC_IDS[16] = {0x01, 0x02, 0x11, 0x13, 0x15, 0x21, 0x23, 0x34, 0x42, 0x56, 0x57, 0x61, 0x63, 0x80, 0x81, 0x83};
   DocCols dc; memset(&dc, 0, sizeof(dc));
   hostArena.resize(0); std::vector<std::pair<u32, u32>> reps;
+  { size_t total = 0; for (auto& a : actors) total += a.size(); for (auto& c : opCols) total += c.data.size(); for (auto& c : changeCols) total += c.data.size(); hostArena.reserve(total + 64); }   // one pinned allocation, not one per append
   for (auto& a : actors) { reps.emplace_back((u32)hostArena.size(), (u32)a.size()); hostArena.append(a.data(), a.size()); }
   for (auto& c : opCols) for (int k = 0; k < 16; k++) if (c.id == DOC_IDS[k]) { dc.off[k] = (u32)hostArena.size(); dc.len[k] = (u32)c.data.size(); hostArena.append(c.data.data(), c.data.size()); }
   {   // the change metadata columns stay available for a later save() (new.js:1717 keeps them as encoders)

@@ -159,8 +159,10 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         rc = L.amg_apply_changes_packed(doc.h, blob_ptr, offs.ctypes.data_as(C.c_void_p), C.c_size_t(trace.n_changes), 0, 1, C.byref(pp), C.byref(err))
+        t_call = time.perf_counter() - t0
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        step.call_ms = t_call * 1e3
         lib.check(rc, err)
         n = C.c_size_t()
         L.amg_patch_bytes(pp, C.byref(n))
@@ -264,7 +266,7 @@ def main():
             'config': {'workload': 'C3 text trace: makeText + 10 actors x 100k single-op changes, 70% insert / 30% delete (SURVEY.md 8d); one independent document per GPU (C5)',
                        'ops_per_gpu': trace.n_ops, 'changes_per_gpu': trace.n_changes, 'change_bytes_per_gpu': nbytes, 'parallelism': 'replicas x%d' % world,
                        'l2': 'inputs (%.0f MB) + working tables exceed the 126 MB L2; document reset every step' % (nbytes / 1e6),
-                       'device_ms_per_step': t_dev * 1e3, 'wall_ms_steps': [round(x * 1e3, 3) for x in wall_steps], 'device_ms_steps': [round(x * 1e3, 3) for x in dev_steps],
+                       'device_ms_per_step': t_dev * 1e3, 'wall_ms_steps': [round(x * 1e3, 3) for x in wall_steps], 'call_return_ms_last_step': round(step.call_ms, 3), 'abi_call_ms_last_step': round(last_ph[23], 3), 'device_ms_steps': [round(x * 1e3, 3) for x in dev_steps],
                        'phase_ms_last_step': dict(zip(['stage_upload', 'sha256', 'parse_gate', 'actors_decode', 'opset', 'patch_groups_props', 'patch_list_index', 'patch_edits_copyout', 'heads_commit'], [round(x, 3) for x in last_ph[:9]])),
                        'host_marks_ms': [round(x, 3) for x in last_ph[12:22]], 'other_paths': other},
             'e2e': {'value': total_ops / t_wall, 'unit': 'ops/s', 'h2d_bytes_per_step': nbytes + 8 * (trace.n_changes + 1), 'd2h_bytes_per_step': patch_bytes},
