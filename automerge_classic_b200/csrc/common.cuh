@@ -132,6 +132,13 @@ static __global__ void k_peek_bytes(unsigned char* dstPinned, const unsigned cha
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes; i += (size_t)gridDim.x * blockDim.x) dstPinned[i] = src[i];
 }
 #endif
+#ifndef AMG_EMU
+struct PeekWords { const void* src[8]; unsigned bytes[8]; unsigned off[8]; int n; };
+static __global__ void k_peek_words(PeekWords w, unsigned char* dstPinned) {   // a handful of 4- or 8-byte words in one launch
+  const int k = threadIdx.x >> 3, b = threadIdx.x & 7;
+  if (k < w.n && (unsigned)b < w.bytes[k]) dstPinned[w.off[k] + b] = ((const unsigned char*)w.src[k])[b];
+}
+#endif
 // dst is valid after the next sync(c). Up to 16 KB: read by a kernel into the pinned staging buffer (sync() moves it to
 // dst); larger: an asynchronous copy.
 inline void d2h(Ctx& c, void* dst, const void* src, size_t bytes) {
@@ -163,6 +170,21 @@ inline void d2d(Ctx& c, void* dst, const void* src, size_t bytes) {
   memmove(dst, src, bytes);
 #else
   CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c.stream));
+#endif
+}
+// up to 8 words of at most 8 bytes each, one kernel (readWords: the counts that size the next stage + the error word)
+inline void d2h_words(Ctx& c, int n, const void* const* srcs, const size_t* sizes, void* const* dsts) {
+#ifdef AMG_EMU
+  for (int k = 0; k < n; k++) memcpy(dsts[k], srcs[k], sizes[k]);
+#else
+  bool small = n <= 8 && c.peekBuf && c.peekUsed + 16 * (size_t)n <= c.peekCap;
+  for (int k = 0; k < n && small; k++) if (sizes[k] > 8) small = false;
+  if (!small) { for (int k = 0; k < n; k++) d2h(c, dsts[k], srcs[k], sizes[k]); return; }
+  PeekWords w; w.n = n;
+  for (int k = 0; k < n; k++) { w.src[k] = srcs[k]; w.bytes[k] = (unsigned)sizes[k]; w.off[k] = (unsigned)(c.peekUsed + 16 * (size_t)k); c.peeks.push_back(Ctx::Peek{dsts[k], c.peekUsed + 16 * (size_t)k, sizes[k]}); }
+  k_peek_words<<<1, 64, 0, c.stream>>>(w, c.peekBuf);
+  CUDA_CHECK(cudaGetLastError());
+  c.peekUsed += 16 * (size_t)n; last_peek_ctx() = &c; c.launches++;
 #endif
 }
 inline void drop_peeks(Ctx& c) {   // after an aborted call: whatever was pending must not be delivered into dead stack frames

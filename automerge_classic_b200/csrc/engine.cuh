@@ -166,8 +166,12 @@ class Engine {
   u64* pinnedWords(size_t n) { hostWord.ensure(n + 1); return hostWord.p; }
   void readWords(std::initializer_list<std::pair<const void*, size_t>> srcs, void* const* dsts) {   // one sync for all of them + the error word
     u64* w = pinnedWords(srcs.size() + 1); size_t k = 0;
-    for (auto& s : srcs) { w[k] = 0; d2h(ctx, &w[k], s.first, s.second); k++; }
-    d2h(ctx, &w[k], errWord.p, 8); const uint64_t launchesNow = ctx.launches;
+    const void* from[9]; size_t sizes[9]; void* to[9];
+    if (srcs.size() > 8) throw Error(AMG_ERR_INTERNAL, "readWords: too many words");
+    for (auto& s : srcs) { w[k] = 0; from[k] = s.first; sizes[k] = s.second; to[k] = &w[k]; k++; }
+    from[k] = errWord.p; sizes[k] = 8; to[k] = &w[k];
+    if (k + 1 <= 8) d2h_words(ctx, (int)k + 1, from, sizes, to); else for (size_t i = 0; i <= k; i++) d2h(ctx, to[i], from[i], sizes[i]);
+    const uint64_t launchesNow = ctx.launches;
     sync(ctx);
     k = 0; for (auto& s : srcs) { memcpy(dsts[k], &w[k], s.second); k++; }
     errSnapshot = w[k]; errSnapLaunches = launchesNow;
