@@ -1,6 +1,6 @@
 """Builds the native libraries in-tree (they travel to the GPU box with the repo snapshot).
 
-  libamgpu.so    nvcc, sm_100a only: CUDA kernels + C ABI (csrc/capi.cu and the .cuh it includes)
+  libamgpu.so    nvcc, sm_100a only: CUDA kernels + C ABI (csrc/capi.cu and the .cuh it includes) + csrc/hostsha.cc (host compiler)
   libamgtrace.so g++: synthetic trace generator (csrc/tracegen.cc)
 """
 import os
@@ -17,9 +17,9 @@ def _stale(target, sources):
 
 def build_engine(force=False, verbose=False):
     out = os.path.join(HERE, 'libamgpu.so')
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh'))] + [os.path.join(HERE, '..', 'include', 'amgpu.h')]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', 'hostsha.cc'))] + [os.path.join(HERE, '..', 'include', 'amgpu.h')]
     if force or _stale(out, srcs):
-        cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + [os.path.join(CSRC, 'capi.cu'), '-o', out, '-lz']
+        cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + [os.path.join(CSRC, 'capi.cu'), os.path.join(CSRC, 'hostsha.cc'), '-o', out, '-lz']
         subprocess.check_call(cmd)
     return out
 

@@ -895,15 +895,8 @@ inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* 
 
 namespace amg {
 
-inline void host_sha256(const u8* data, size_t len, u8 out[32]) {
-  u32 h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
-  std::vector<u8> tail(data + (len / 64) * 64, data + len); tail.push_back(0x80);
-  while (tail.size() % 64 != 56) tail.push_back(0);
-  for (int i = 7; i >= 0; i--) tail.push_back((u8)(((u64)len * 8) >> (8 * i)));
-  auto run = [&](const u8* p, size_t n) { for (size_t o = 0; o < n; o += 64) { u32 w[16]; for (int i = 0; i < 16; i++) w[i] = (u32)p[o + 4 * i] << 24 | (u32)p[o + 4 * i + 1] << 16 | (u32)p[o + 4 * i + 2] << 8 | p[o + 4 * i + 3]; sha256_compress(h, w, SHA_K); } };
-  run(data, (len / 64) * 64); run(tail.data(), tail.size());
-  for (int i = 0; i < 8; i++) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }
-}
+extern "C" void amg_host_sha256(const uint8_t* data, size_t len, uint8_t out[32]);   // hostsha.cc (x86 SHA extensions when present)
+inline void host_sha256(const u8* data, size_t len, u8 out[32]) { amg_host_sha256(data, len, out); }
 inline std::string inflateRawBytes(const u8* p, size_t n) {
   z_stream zs; memset(&zs, 0, sizeof(zs));
   if (inflateInit2(&zs, -15) != Z_OK) throw Error(AMG_ERR_INTERNAL, "inflateInit failed");
@@ -926,6 +919,8 @@ inline void Engine::saveDocument(std::string& result) {
   if (!loadedDoc.empty()) { result = loadedDoc; return; }   // unchanged since Backend.load (new.js:2034)
   if (!encoder) encoder.reset(new ColumnEncoder(ctx, scanTmp));
   ColumnEncoder& enc = *encoder; enc.outLen = 0;
+  HostClock sclk; const bool strace = getenv("AMG_PAR_DOC_TRACE") != nullptr;
+  auto smark = [&](const char* what) { if (strace) { sync(ctx); fprintf(stderr, "amgpu save: %-28s %8.2f ms\n", what, sclk.ms()); } };
   struct Col { u32 id; size_t off, len; };
   std::vector<Col> changeCols, opCols;
   auto add = [&](std::vector<Col>& cols, u32 id, size_t len) { cols.push_back({id, enc.outLen - len, len}); };
@@ -1013,6 +1008,7 @@ inline void Engine::saveDocument(std::string& result) {
       foreach(ctx, S, SaveSuccValKernel{1, succ.p, saveVals.p}); add(opCols, 0x83, enc.deltaNum(saveVals.p, S));
     }
   }
+  smark("columns encoded (device)");
   std::vector<u8> raw(enc.outLen);
   if (enc.outLen) { d2h(ctx, raw.data(), enc.out.p, enc.outLen); sync(ctx); }
   // ---- host: DEFLATE of large columns (columnar.js:1052-1057), directory, container (columnar.js:659-686)
@@ -1034,6 +1030,7 @@ inline void Engine::saveDocument(std::string& result) {
     for (auto& t : ts) t.join();
     for (auto& e : errs) if (!e.empty()) throw Error(AMG_ERR_INTERNAL, e);
   }
+  smark("columns deflated (host)");
   std::string body;
   auto uleb = [&](u64 v) { do { u8 b = v & 0x7f; v >>= 7; if (v) b |= 0x80; body.push_back((char)b); } while (v); };
   uleb(actorIds.size()); for (auto& a : actorIds) { uleb(a.size()); body += a; }
@@ -1044,6 +1041,7 @@ inline void Engine::saveDocument(std::string& result) {
   for (u32 i : headIdx) uleb(i);
   std::string head; head.push_back(0); { u64 v = body.size(); do { u8 b = v & 0x7f; v >>= 7; if (v) b |= 0x80; head.push_back((char)b); } while (v); }
   std::string hashed = head + body; u8 digest[32]; host_sha256((const u8*)hashed.data(), hashed.size(), digest);
+  smark("container assembled + hashed");
   static const u8 magic[4] = {0x85, 0x6f, 0x4a, 0x83};
   result.assign((const char*)magic, 4); result.append((const char*)digest, 4); result += hashed;
 }
