@@ -33,6 +33,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
     os.environ['NCCL_DEBUG'] = 'WARN'   # keep stdout to the one JSON line (NCCL prints its version banner there)
+# stdout carries exactly one JSON line: whatever native libraries print to file descriptor 1 (NCCL's version banner does,
+# whatever NCCL_DEBUG says) goes to stderr instead; the JSON line is written through the saved descriptor
+_JSON_OUT = os.fdopen(os.dup(1), 'w')
+os.dup2(2, 1)
+
+
+def _emit(line):
+    print(line, file=_JSON_OUT, flush=True)
+
 
 N_OPS, N_ACTORS = 1_000_000, 10
 CPU_SAMPLE_OPS = 200_000
@@ -104,7 +113,7 @@ def run_reference(args, rank, world):
     ms = 1e3 * sum(times) / len(times)
     v = t.n_ops / (ms / 1e3)
     sample = 'first %d ops of the C3 trace (same generator, 10 actors), applyChanges(init(), all) on 1 core' % t.n_ops
-    print(json.dumps({
+    _emit(json.dumps({
         'impl': 'reference', 'metric': 'ops/sec applied (1M-op text trace)', 'value': v, 'unit': 'ops/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic',
         'config': {'workload': 'C3 text trace: 10 actors x 100k single-op changes (1M ops); reference arm runs a bounded prefix', 'sample_ops': t.n_ops},
@@ -260,7 +269,7 @@ def main():
         print('marks:', buf.value.decode(), file=sys.stderr)
     if rank == 0:
         clocks = sampler.summary()
-        print(json.dumps({
+        _emit(json.dumps({
             'metric': 'ops/sec applied (1M-op text trace)', 'value': total_ops / t_dev, 'unit': 'ops/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': t_wall * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic',
             'config': {'workload': 'C3 text trace: makeText + 10 actors x 100k single-op changes, 70% insert / 30% delete (SURVEY.md 8d); one independent document per GPU (C5)',
