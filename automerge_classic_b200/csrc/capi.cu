@@ -28,7 +28,7 @@ struct amg_backend {
 
   void ensureGraph() {
     Engine& e = eng;
-    if (!e.haveHashGraph) throw amg::Error(AMG_UNSUPPORTED, "amgpu: change history of a loaded document is not reconstructed (decodeDocument / computeHashGraph, new.js:1887-1912, not built)");
+    if (!e.haveHashGraph) e.computeHashGraph();   // new.js:1922, 1980, 2000, 2015
     if (g.known == e.numApplied) return;
     const size_t from = g.known, to = e.numApplied;
     std::vector<u8> hs((to - from) * 32); d2h(e.ctx, hs.data(), e.hashes.p + from * 32, hs.size()); sync(e.ctx);
@@ -47,10 +47,26 @@ struct amg_backend {
     }
     g.known = to;
   }
+  // columnar.js:798-811 deflateChange: magic + checksum of the plain form, chunk type 2, raw DEFLATE of the body
+  static std::string deflateChange(const std::string& plain) {
+    ByteReader r((const u8*)plain.data(), 9, (u32)plain.size()); const u64 bodyLen = r.uleb();
+    if (r.err || r.pos + bodyLen != plain.size()) throw amg::Error(AMG_ERR_INTERNAL, "deflateChange: malformed change");
+    z_stream zs; memset(&zs, 0, sizeof(zs));
+    if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw amg::Error(AMG_ERR_INTERNAL, "deflateInit failed");
+    std::string comp; comp.resize(deflateBound(&zs, (uLong)bodyLen));
+    zs.next_in = (Bytef*)plain.data() + r.pos; zs.avail_in = (uInt)bodyLen; zs.next_out = (Bytef*)comp.data(); zs.avail_out = (uInt)comp.size();
+    const int rc = ::deflate(&zs, Z_FINISH); comp.resize(zs.total_out); deflateEnd(&zs);
+    if (rc != Z_STREAM_END) throw amg::Error(AMG_ERR_INTERNAL, "deflate failed");
+    std::string out(plain, 0, 8); out.push_back(2);
+    { u64 v = comp.size(); do { u8 b = v & 0x7f; v >>= 7; if (v) b |= 0x80; out.push_back((char)b); } while (v); }
+    return out + comp;
+  }
   std::string changeBytes(u32 idx) {
     if (const HostChange* o = eng.originalOf(idx)) return std::string((const char*)eng.hostArena.data() + o->off, o->len);
     const HostChange& c = eng.changes[idx];
-    return std::string((const char*)eng.hostArena.data() + c.off, c.len);
+    std::string plain((const char*)eng.hostArena.data() + c.off, c.len);
+    if (idx < eng.historyRebuilt && plain.size() >= 256) return deflateChange(plain);   // what encodeChange returns for a rebuilt change (columnar.js:738)
+    return plain;
   }
 };
 
@@ -98,7 +114,7 @@ amg_backend* amg_clone(amg_backend* src, amg_error* err) {
     d2d(c, d.doc.valLen.p, s.doc.valLen.p, s.numRows * 4); d2d(c, d.doc.valOff.p, s.doc.valOff.p, s.numRows * 4); d2d(c, d.doc.time.p, s.doc.time.p, s.numRows * 4);
     d.numSucc = s.numSucc; d.succOff.ensure(c, s.numRows + 2); d2d(c, d.succOff.p, s.succOff.p, (s.numRows + 1) * 4); d.succ.ensure(c, s.numSucc + 1); d2d(c, d.succ.p, s.succ.p, s.numSucc * 8);
     d.actorIds = s.actorIds; d.actorRep = s.actorRep; d.clock = s.clock; d.heads = s.heads; d.headIdx = s.headIdx; d.changes = s.changes; d.deflatedOriginal = s.deflatedOriginal; d.loadedDoc = s.loadedDoc; d.numLoaded = s.numLoaded; for (int k = 0; k < 9; k++) d.loadedCols[k] = s.loadedCols[k];
-    d.queue = s.queue; d.queueOriginal = s.queueOriginal; d.maxOp = s.maxOp; d.haveHashGraph = s.haveHashGraph;
+    d.queue = s.queue; d.queueOriginal = s.queueOriginal; d.maxOp = s.maxOp; d.haveHashGraph = s.haveHashGraph; d.historyRebuilt = s.historyRebuilt;
     while (d.actorCap < 2 * (d.actorIds.size() + 16)) d.actorCap *= 2;
     d.actorSlots.ensure(c, d.actorCap); d.rebuildActorTable();
     sync(c);

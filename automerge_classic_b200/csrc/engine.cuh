@@ -23,6 +23,7 @@
 #include "prims.cuh"
 #include "domlocal.cuh"
 #include "doccols.cuh"
+#include "history.cuh"
 
 namespace amg {
 
@@ -189,6 +190,9 @@ class Engine {
       case KE_TRAILING: throw Error(AMG_ERR_RANGE, "Encoded change has trailing data");
       case KE_CHUNK_TYPE: throw Error(AMG_ERR_RANGE, "Unexpected chunk type");
       case KE_DEFLATE: throw Error(AMG_ERR_RANGE, "invalid deflate data");
+      case KE_HIST_RANGE: throw Error(AMG_ERR_RANGE, "Operation ID outside of allowed range");        // columnar.js:925
+      case KE_HIST_OPID: throw Error(AMG_ERR_RANGE, "Expected opId does not match the operation found");   // columnar.js:936
+      case KE_HIST_DEP: throw Error(AMG_ERR_RANGE, "No hash for dependency index");                      // columnar.js:952
       case KE_TRUNCATED: throw Error(AMG_ERR_RANGE, "buffer ended with incomplete number");
       case KE_NUM_RANGE: throw Error(AMG_ERR_RANGE, "number out of range");
       case KE_COL_ORDER: throw Error(AMG_ERR_RANGE, "Columns must be in ascending order");
@@ -255,6 +259,7 @@ class Engine {
   struct ApplyResult { PatchOut patch; };
 
   void applyChanges(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out, bool hostScan = false);
+  void applyChangesOnce(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out, bool hostScan = false);
   void getPatch(PatchOut& out);
   void saveDocument(std::string& result);
   void buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows* ops, size_t numOps, const IdTable* idt, const u32* rowOfOpD, const u32* posD,
@@ -263,8 +268,11 @@ class Engine {
   void finishPatch(PatchOut& out);
   void reset();
   void loadDocument(const u8* buf, size_t len);
+  size_t historyRebuilt = 0;   // changes [0, historyRebuilt) were rebuilt by computeHashGraph (getChanges DEFLATEs the large ones like encodeChange does)
+  DBuf<u64> excl64;
   bool haveHashGraph = true;   // false after Backend.load: change history (hashes, bytes) is not reconstructed (new.js:1887-1912)
   void benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes);
+  void computeHashGraph();   // change history of a loaded document (history.cuh)
   int debugDecodeColumn(const u8* bytes, size_t len, int kind, size_t n, bool parallel, long long* out);
   void decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* hashesOut, u32* nOpsOut, u32** rowsOut, size_t* totalOps);
   size_t lastB = 0, lastM = 0, lastP = 0, lastBytes = 0;

@@ -60,11 +60,27 @@ inline void Engine::finishPatch(PatchOut& out) {
 inline void Engine::reset() {
   sync(ctx);
   arenaLen = 0; hostArena.len = 0; numApplied = 0; numRows = 0; numSucc = 0; dev_memset(ctx, succOff.p, 0, 4);
-  actorIds.clear(); actorRep.clear(); clock.clear(); heads.clear(); headIdx.clear(); changes.clear(); changeHashes.clear(); deflatedOriginal.clear(); loadedDoc.clear(); numLoaded = 0;
+  actorIds.clear(); actorRep.clear(); clock.clear(); heads.clear(); headIdx.clear(); changes.clear(); changeHashes.clear(); deflatedOriginal.clear(); loadedDoc.clear(); numLoaded = 0; historyRebuilt = 0; haveHashGraph = true;
   queue.clear(); queueOriginal.clear(); maxOp = 0; rebuildActorTable();
 }
 
+// After Backend.load the hashes of the loaded changes are unknown until computeHashGraph has run. Like the reference
+// (new.js:1833-1840) the first attempt goes without them; if a change then stays unapplied (or looks out of sequence)
+// because it refers to history, the hash graph is computed and the call starts over. Nothing was committed by then.
+struct NeedHistory {};
 inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out, bool hostScan) {
+  if (haveHashGraph) { applyChangesOnce(bufs, lens, n, blob, offsets, isLocal, wantPatch, out, hostScan); return; }
+  bool retry = false;
+  try { applyChangesOnce(bufs, lens, n, blob, offsets, isLocal, wantPatch, out, hostScan); }
+  catch (NeedHistory&) { retry = true; }
+  catch (Error& e) { if (e.code != AMG_ERR_RANGE) throw; retry = true; }
+  if (!retry) return;
+  drop_peeks(ctx);
+  computeHashGraph();
+  out = PatchOut();
+  applyChangesOnce(bufs, lens, n, blob, offsets, isLocal, wantPatch, out, hostScan);
+}
+inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out, bool hostScan) {
   PhaseTimer timer(ctx); HostClock hclk; int hmark = 12;
   for (auto& x : lastPhaseMs) x = 0;
   auto hostMark = [&]() { if (hmark < 24) lastPhaseMs[hmark++] = hclk.ms(); };
@@ -240,7 +256,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
     appliedH.resize(B); primaryH.resize(B); appRankH.resize(B);
     d2h(ctx, appliedH.data(), applied.p, B); d2h(ctx, primaryH.data(), primary.p, B * 4); d2h(ctx, appRankH.data(), appRank.p, B * 4); sync(ctx);
   }
-  if (!haveHashGraph && numNew < B) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: a change depends on history that was not reconstructed after Backend.load (computeHashGraph, new.js:1887-1912, not built)");
+  if (!haveHashGraph && numNew < B) throw NeedHistory{};   // a change waits for (or repeats) something older than the loaded heads
   // the queue after this call: every batch entry whose hash is still not applied (new.js:1569-1570, 1832)
   std::vector<HostChange> newQueue, newQueueOriginal;
   if (numNew < B) finishInflate();
@@ -826,6 +842,185 @@ inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* 
 #else
   *msSha = *msParse = *msDec = 0;
 #endif
+}
+
+// Change history of a loaded document (reference new.js:1887-1912 computeHashGraph -> columnar.js:876-981): rebuilds every
+// loaded change - ops from the document rows and the deletions implied by their succ lists, preds, actor tables, canonical
+// column bytes - and its hash. Kernels: history.cuh. Nothing persistent is touched until the heads check has passed.
+inline void Engine::computeHashGraph() {
+  if (haveHashGraph) return;
+  const size_t L = numLoaded, N = numRows, S = numSucc, A = actorIds.size();
+  if (L == 0) { haveHashGraph = true; return; }
+  if (L >= (1u << 29) || N + S >= (1u << 30)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: document too large for history reconstruction");
+  DocRows d = doc.view();
+  dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull;
+  // ---- 1. change metadata columns (the same decoders as save() after load())
+  auto loadedCol = [&](u32 id) -> const HostChange& { static const u32 IDS[9] = {0x01, 0x03, 0x13, 0x23, 0x35, 0x40, 0x43, 0x56, 0x57}; for (int k = 0; k < 9; k++) if (IDS[k] == id) return loadedCols[k]; return loadedCols[0]; };
+  DBuf<long long> cActor, cSeq, cMaxOp, cTime, cDepsNum, cExtra, depIdxV, scratchV; DBuf<u32> msgOff, msgLen, extraOff, extraLen, tmpOff, tmpLen, depsNum32, depBase, depIdx;
+  for (DBuf<long long>* b : {&cActor, &cSeq, &cMaxOp, &cTime, &cDepsNum, &cExtra, &scratchV}) b->ensure(ctx, L + 1);
+  for (DBuf<u32>* b : {&msgOff, &msgLen, &extraOff, &extraLen, &tmpOff, &tmpLen, &depsNum32}) b->ensure(ctx, L + 2);
+  depBase.ensure(ctx, L + 2);
+  auto decodeCol = [&](int kind, u32 id, size_t count, long long* out, u32* so, u32* sl) {
+    const HostChange& c = loadedCol(id);
+    if (count >= parDocMinRows && c.len > 0) {
+      const u8* bytes = arena.p + c.off; bool ok = false;
+      if (kind == LC_UINT) ok = parCols.toI64(bytes, c.len, false, count, out);
+      else if (kind == LC_DELTA) ok = parCols.deltaToI64(bytes, c.len, count, out);
+      else if (kind == LC_EXTRA_LEN) ok = parCols.extraLenColumn(bytes, c.len, count, out, so, sl, loadedCol(0x57).off);
+      if (ok) return;
+    }
+    if (count) foreach_warp(ctx, 1, LoadedColKernel{kind, arena.p, c.off, c.len, loadedCol(0x57).off, (u32)count, out, so, sl, nullptr});
+  };
+  decodeCol(LC_UINT, 0x01, L, cActor.p, tmpOff.p, tmpLen.p);
+  decodeCol(LC_DELTA, 0x03, L, cSeq.p, tmpOff.p, tmpLen.p);
+  decodeCol(LC_DELTA, 0x13, L, cMaxOp.p, tmpOff.p, tmpLen.p);
+  decodeCol(LC_DELTA, 0x23, L, cTime.p, tmpOff.p, tmpLen.p);
+  decodeCol(LC_STRING, 0x35, L, scratchV.p, msgOff.p, msgLen.p);
+  decodeCol(LC_UINT, 0x40, L, cDepsNum.p, tmpOff.p, tmpLen.p);
+  decodeCol(LC_EXTRA_LEN, 0x56, L, cExtra.p, extraOff.p, extraLen.p);
+  foreach(ctx, L, HistI64ToU32Kernel{cDepsNum.p, depsNum32.p});
+  foreach(ctx, L, HistI64ToU32Kernel{cDepsNum.p, tmpLen.p});   // (cDepsNum as the kernels read it: nulls -> 0)
+  scan_exclusive(ctx, scanTmp, depsNum32.p, depBase.p, L);
+  const size_t D = readU32(depBase.p + L);
+  depIdxV.ensure(ctx, D + 1); depIdx.ensure(ctx, D + 2);
+  decodeCol(LC_DELTA, 0x43, D, depIdxV.p, tmpOff.p, tmpLen.p);
+  if (D) foreach(ctx, D, HistI64ToU32Kernel{depIdxV.p, depIdx.p});
+  // ---- 2. actor order (hex string order = byte order), representatives
+  std::vector<u32> order(A), rankH(A), repOffH(A), repLenH(A);
+  for (size_t a = 0; a < A; a++) { order[a] = (u32)a; repOffH[a] = actorRep[a].first; repLenH[a] = actorRep[a].second; }
+  std::sort(order.begin(), order.end(), [&](u32 x, u32 y) { return actorIds[x] < actorIds[y]; });
+  for (size_t i = 0; i < A; i++) rankH[order[i]] = (u32)i;
+  DBuf<u32> rankD, actorOfRank, repOff, repLen;
+  for (DBuf<u32>* b : {&rankD, &actorOfRank, &repOff, &repLen}) b->ensure(ctx, A + 1);
+  h2d(ctx, rankD.p, rankH.data(), A * 4); h2d(ctx, actorOfRank.p, order.data(), A * 4); h2d(ctx, repOff.p, repOffH.data(), A * 4); h2d(ctx, repLen.p, repLenH.data(), A * 4);
+  const int ctrBits = bits_for(maxOp + 1), idBits = std::min(64, ctrBits + 16);
+  // ---- 3. (successor, predecessor) pairs -> pred lists and deletions
+  DBuf<u64> predKey, succKey, keyA, keyB, groupId, opId; DBuf<u32> pairRow, valA, pairRowSorted, head, groupIdx, groupStart, groupRow, isDel, delSlot, idRows;
+  DBuf<u64> idSorted; idSorted.ensure(ctx, N + 1); idRows.ensure(ctx, N + 1);
+  if (N) { foreach(ctx, N, HistIdKeyKernel{d, idSorted.p, idRows.p}); radix_sort_pairs(ctx, sortTmp, idSorted, idRows, N, 0, idBits); }
+  size_t G = 0, numDel = 0;
+  for (DBuf<u64>* b : {&predKey, &succKey, &keyA, &keyB}) b->ensure(ctx, S + 1);
+  for (DBuf<u32>* b : {&pairRow, &valA, &pairRowSorted, &head, &groupIdx}) b->ensure(ctx, S + 2);
+  if (S) {
+    foreach(ctx, N, HistPairKernel{d, succOff.p, succ.p, rankD.p, predKey.p, succKey.p, pairRow.p});
+    foreach(ctx, S, HistIotaKernel{valA.p});
+    d2d(ctx, keyA.p, predKey.p, S * 8);
+    radix_sort_pairs(ctx, sortTmp, keyA, valA, S, 0, idBits);                 // by predecessor (counter, actor order) ...
+    foreach(ctx, S, HistGatherKeyKernel{succKey.p, valA.p, keyB.p});
+    radix_sort_pairs(ctx, sortTmp, keyB, valA, S, 0, idBits);                 // ... then, stably, by successor id
+    foreach(ctx, S, HistGatherU32Kernel{pairRow.p, valA.p, pairRowSorted.p});
+    foreach(ctx, S, HistGroupHeadKernel{keyB.p, head.p});
+    scan_exclusive(ctx, scanTmp, head.p, groupIdx.p, S);
+    G = readU32(groupIdx.p + S);
+  }
+  for (DBuf<u32>* b : {&groupStart, &groupRow, &isDel, &delSlot}) b->ensure(ctx, G + 2);
+  groupId.ensure(ctx, G + 1);
+  if (G) {
+    foreach(ctx, S, HistGroupKernel{head.p, groupIdx.p, keyB.p, (u32)S, idSorted.p, idRows.p, (u32)N, groupStart.p, groupId.p, groupRow.p, isDel.p});
+    scan_exclusive(ctx, scanTmp, isDel.p, delSlot.p, G);
+    numDel = readU32(delSlot.p + G);
+  }
+  const size_t M = N + numDel;
+  DBuf<u32> opSrc, opPredStart, opPredNum, opOrder, opChange, predNumSorted, opPredBase;
+  opId.ensure(ctx, M + 1); for (DBuf<u32>* b : {&opSrc, &opPredStart, &opPredNum, &opOrder, &opChange, &predNumSorted}) b->ensure(ctx, M + 2);
+  opPredBase.ensure(ctx, M + 3);
+  if (N) foreach(ctx, N, HistRowOpKernel{d, opId.p, opSrc.p, opPredStart.p, opPredNum.p});
+  if (G) foreach(ctx, G, HistGroupOpKernel{groupStart.p, groupId.p, groupRow.p, isDel.p, delSlot.p, pairRowSorted.p, (u32)G, (u32)S, (u32)N, opId.p, opSrc.p, opPredStart.p, opPredNum.p});
+  // ---- 4. ops by (actor, counter); changes by (actor, seq); every op finds its change
+  DBuf<u64> opKey, chKey; opKey.ensure(ctx, M + 1); chKey.ensure(ctx, L + 1);
+  DBuf<u32> changeOrder, actorStart, chOpStart, chNOps; changeOrder.ensure(ctx, L + 1); actorStart.ensure(ctx, A + 2); chOpStart.ensure(ctx, L + 2); chNOps.ensure(ctx, L + 2);
+  if (M) { foreach(ctx, M, HistOpKeyKernel{opId.p, opKey.p, opOrder.p}); radix_sort_pairs(ctx, sortTmp, opKey, opOrder, M, 0, ctrBits); radix_sort_pairs(ctx, sortTmp, opKey, opOrder, M, 48, 64); }
+  foreach(ctx, L, HistChangeKeyKernel{cActor.p, cSeq.p, chKey.p, changeOrder.p});
+  radix_sort_pairs(ctx, sortTmp, chKey, changeOrder, L, 0, 40); radix_sort_pairs(ctx, sortTmp, chKey, changeOrder, L, 40, 57);
+  foreach(ctx, A + 1, HistLowerBoundKernel{chKey.p, (u32)L, 40, actorStart.p});
+  dev_memset(ctx, chOpStart.p, 0, (L + 1) * 4); dev_memset(ctx, chNOps.p, 0, (L + 1) * 4);
+  if (M) {
+    foreach(ctx, M, HistAssignKernel{opKey.p, actorStart.p, changeOrder.p, cMaxOp.p, (u32)A, numApplied == L ? 1 : 0, opChange.p, errWord.p});
+    foreach(ctx, M, HistChangeStartKernel{opChange.p, chOpStart.p});
+    foreach(ctx, M, HistChangeCountKernel{opChange.p, chNOps.p});
+    foreach(ctx, M, HistCheckIdsKernel{opKey.p, opChange.p, chOpStart.p, chNOps.p, cMaxOp.p, errWord.p});
+    foreach(ctx, M, HistPredNumSortedKernel{opPredNum.p, opOrder.p, predNumSorted.p});
+    scan_exclusive(ctx, scanTmp, predNumSorted.p, opPredBase.p, M);
+  } else dev_memset(ctx, opPredBase.p, 0, 8);
+  const size_t P = M ? readU32(opPredBase.p + M) : 0;
+  checkErr(actorIds);
+  // ---- 5. the other actors of every change
+  HistOpView view{d, opId.p, opSrc.p, opPredStart.p, opPredNum.p, opOrder.p, pairRowSorted.p, (u32)N};
+  DBuf<u32> slotCnt, slotBase, uniq, uniqSlot, otherStart; DBuf<u64> slotKey, other; DBuf<u32> slotVal;
+  slotCnt.ensure(ctx, M + 2); slotBase.ensure(ctx, M + 3); otherStart.ensure(ctx, L + 3);
+  size_t Q = 0, U = 0;
+  if (M) { foreach(ctx, M, HistActorSlotCountKernel{view, slotCnt.p}); scan_exclusive(ctx, scanTmp, slotCnt.p, slotBase.p, M); Q = readU32(slotBase.p + M); }
+  slotKey.ensure(ctx, Q + 1); slotVal.ensure(ctx, Q + 1); uniq.ensure(ctx, Q + 2); uniqSlot.ensure(ctx, Q + 3);
+  if (Q) {
+    foreach(ctx, M, HistActorPairKernel{view, slotBase.p, opChange.p, cActor.p, rankD.p, slotKey.p});
+    foreach(ctx, Q, HistIotaKernel{slotVal.p});
+    radix_sort_pairs(ctx, sortTmp, slotKey, slotVal, Q, 0, 64);
+    foreach(ctx, Q, HistUniqueKernel{slotKey.p, uniq.p});
+    scan_exclusive(ctx, scanTmp, uniq.p, uniqSlot.p, Q);
+    U = readU32(uniqSlot.p + Q);
+  }
+  other.ensure(ctx, U + 1);
+  if (U) foreach(ctx, Q, HistOtherFillKernel{slotKey.p, uniq.p, uniqSlot.p, other.p});
+  foreach(ctx, L + 1, HistLowerBoundKernel{other.p, (u32)U, 16, otherStart.p});
+  // ---- 6. local actor indexes and delta values, then the bytes (two passes)
+  DBuf<u32> objA, keyAi, predA, outLen, outOff, depsAt, bodyAt, chOffD; DBuf<long long> keyDelta, predDelta;
+  objA.ensure(ctx, M + 1); keyAi.ensure(ctx, M + 1); keyDelta.ensure(ctx, M + 1); predA.ensure(ctx, P + 1); predDelta.ensure(ctx, P + 1);
+  for (DBuf<u32>* b : {&outLen, &depsAt, &bodyAt, &chOffD}) b->ensure(ctx, L + 2);
+  outOff.ensure(ctx, L + 3);
+  HistChanges hc{cActor.p, cSeq.p, cMaxOp.p, cTime.p, msgOff.p, msgLen.p, cDepsNum.p, extraOff.p, extraLen.p};
+  foreach(ctx, L, HistPrepKernel{view, hc, chOpStart.p, chNOps.p, opPredBase.p, other.p, otherStart.p, rankD.p, objA.p, keyAi.p, keyDelta.p, predA.p, predDelta.p});
+  HistEncodeKernel enc{0, view, hc, arena.p, chOpStart.p, chNOps.p, opPredBase.p, (u32)M, (u32)P, other.p, otherStart.p, repOff.p, repLen.p, actorOfRank.p,
+                       objA.p, keyAi.p, keyDelta.p, predA.p, predDelta.p, outLen.p, outOff.p, nullptr, 0, depsAt.p, bodyAt.p};
+  foreach(ctx, L, enc);
+  scan_exclusive(ctx, scanTmp, outLen.p, outOff.p, L);
+  excl64.ensure(ctx, L + 2); scan_exclusive64(ctx, scanTmp, ParColumnDecoder::PcDeltaInputU32{outLen.p}, excl64.p, L);
+  u64 tot64 = 0; u32 lastLen = 0; d2h(ctx, &tot64, excl64.p + L - 1, 8); d2h(ctx, &lastLen, outLen.p + L - 1, 4); sync(ctx);
+  const u64 T = tot64 + lastLen;
+  if ((u64)arenaLen + T + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
+  arena.ensure(ctx, arenaLen + T + 64, arenaLen);
+  enc.pass = 1; enc.arena = arena.p; enc.outArena = arena.p; enc.outBase = (u32)arenaLen;
+  foreach(ctx, L, enc);
+  foreach(ctx, L, HistChOffKernel{outOff.p, (u32)arenaLen, chOffD.p});
+  checkErr(actorIds);
+  // ---- 7. dependency levels (host: one pass over the dependency indexes), hashes level by level
+  std::vector<u32> depsNumH(L), depBaseH(L + 1), depIdxH(D), level(L), list(L);
+  d2h(ctx, depsNumH.data(), depsNum32.p, L * 4); d2h(ctx, depBaseH.data(), depBase.p, (L + 1) * 4); if (D) d2h(ctx, depIdxH.data(), depIdx.p, D * 4); sync(ctx);
+  u32 maxLevel = 0; std::vector<u8> isDep(L, 0);
+  for (size_t k = 0; k < L; k++) {
+    u32 lv = 0;
+    for (u32 i = 0; i < depsNumH[k]; i++) { const u32 di = depIdxH[depBaseH[k] + i]; if (di >= k) throw Error(AMG_ERR_RANGE, "No hash for index " + std::to_string(di) + " while processing index " + std::to_string(k)); lv = std::max(lv, level[di] + 1); isDep[di] = 1; }
+    level[k] = lv; maxLevel = std::max(maxLevel, lv);
+  }
+  std::vector<u32> levelStart(maxLevel + 2, 0);
+  for (size_t k = 0; k < L; k++) levelStart[level[k] + 1]++;
+  for (u32 l = 0; l <= maxLevel; l++) levelStart[l + 1] += levelStart[l];
+  { std::vector<u32> at(levelStart.begin(), levelStart.end() - 1); for (size_t k = 0; k < L; k++) list[at[level[k]]++] = (u32)k; }
+  DBuf<u32> listD; listD.ensure(ctx, L + 1); h2d(ctx, listD.p, list.data(), L * 4);
+  DBuf<u8> newHashes; newHashes.ensure(ctx, L * 32 + 64); d2d(ctx, newHashes.p, hashes.p, L * 32);   // scratch copy: committed only after the heads check
+  for (u32 l = 0; l <= maxLevel; l++) {
+    const size_t cnt = levelStart[l + 1] - levelStart[l];
+    if (cnt) foreach(ctx, cnt, HistHashKernel{listD.p + levelStart[l], arena.p, chOffD.p, outLen.p, depsAt.p, bodyAt.p, cDepsNum.p, depBase.p, depIdx.p, (u32)L, newHashes.p, errWord.p});
+  }
+  checkErr(actorIds);
+  // ---- 8. heads: the changes nobody depends on must be exactly the document's heads (columnar.js:968-980)
+  {
+    size_t nHeads = 0; for (size_t k = 0; k < L; k++) if (!isDep[k]) nHeads++;
+    bool ok = numApplied != L || nHeads == heads.size();   // (changes applied after the load have moved the heads)
+    std::vector<std::array<u8, 32>> got(heads.size());
+    if (numApplied == L) {
+      for (size_t i = 0; i < heads.size(); i++) d2h(ctx, got[i].data(), newHashes.p + (size_t)headIdx[i] * 32, 32);
+      sync(ctx);
+      for (size_t i = 0; i < heads.size() && ok; i++) if (isDep[headIdx[i]] || got[i] != heads[i]) ok = false;
+    }
+    if (!ok) throw Error(AMG_ERR_RANGE, "Mismatched heads hashes: the document's heads are not the hashes of its reconstructed changes");
+  }
+  // ---- 9. commit: bytes into the arena and its host mirror, hashes, change table
+  hostArena.resize(arenaLen + T);
+  if (T) d2h(ctx, hostArena.data() + arenaLen, arena.p + arenaLen, T);
+  d2d(ctx, hashes.p, newHashes.p, L * 32);
+  std::vector<u32> offH(L), lenH(L); d2h(ctx, offH.data(), chOffD.p, L * 4); d2h(ctx, lenH.data(), outLen.p, L * 4); sync(ctx);
+  for (size_t k = 0; k < L; k++) changes[k] = HostChange{offH[k], lenH[k]};
+  arenaLen += T; haveHashGraph = true; historyRebuilt = L;
 }
 
 // Parity hook: one document column through the parallel or the serial decoder (include/amgpu.h)

@@ -403,3 +403,42 @@ def check_load_parallel_columns(Doc, oracle, cases):
     """Backend.load with the parallel column decoders (doccols.cuh) on documents saved by the oracle."""
     for cfg, n, a in cases:
         check_load(Doc, oracle, cfg, n, a)
+
+
+def check_history_after_load(Doc, cfg, n, a, frac=0.5):
+    """Backend.load followed by anything that needs the change history (new.js:1887-1912 computeHashGraph,
+    columnar.js:876-981): the changes rebuilt from the document are byte-identical to the original binary changes (so
+    are their hashes), in application order; changes that depend on history older than the loaded heads apply, and the
+    result is the document that never went through save / load; duplicates of loaded changes are skipped."""
+    from automerge_classic_b200 import tracegen, columnar
+    hash_of = lambda c: columnar.decode_change(bytes(c))['hash']
+    ch = tracegen.generate(cfg, n, a).changes()
+    cut = int(len(ch) * frac)
+    full, half = Doc(), Doc()
+    full.apply_changes(ch)
+    half.apply_changes(ch[:cut])
+    saved_full, saved_half = full.save(), half.save()
+    # every change comes back as it went in
+    g = Doc(saved_full)
+    got = g.get_changes([])
+    assert [bytes(c) for c in got] == [bytes(c) for c in full.get_changes([])]
+    assert sorted(hash_of(c) for c in got) == sorted(hash_of(c) for c in ch)
+    assert bytes(g.get_change_by_hash(hash_of(ch[0]))) == bytes(ch[0])
+    assert g.get_missing_deps() == full.get_missing_deps()
+    # changes on top of older history
+    g = Doc(saved_half)
+    p_loaded, p_direct = g.apply_changes(ch[cut:]), half.apply_changes(ch[cut:])
+    d = replay.deep_equal(replay.decode(p_loaded), replay.decode(p_direct))
+    assert d is None, d
+    assert g.save() == saved_full and g.heads() == full.heads()
+    d = replay.deep_equal(replay.decode(g.get_patch()), replay.decode(full.get_patch()))
+    assert d is None, d
+    assert [bytes(c) for c in g.get_changes([])] == [bytes(c) for c in full.get_changes([])]
+    old_heads = Doc(saved_half).heads()
+    assert [bytes(c) for c in g.get_changes(old_heads)] == [bytes(c) for c in full.get_changes(old_heads)]
+    # duplicates
+    g = Doc(saved_full)
+    g.apply_changes(ch[len(ch) // 3: len(ch) // 3 + 5])
+    g.apply_changes(ch)
+    assert g.save() == saved_full and g.heads() == full.heads()
+    return len(ch)

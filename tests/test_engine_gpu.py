@@ -144,3 +144,12 @@ def test_load_parallel_columns_forced(gpu_doc, oracle_mod, monkeypatch):
 @pytest.mark.parametrize('cfg,n,a', [('C3', 60000, 10), ('C2', 30000, 0), ('C4', 40000, 10)])
 def test_load_long_document(gpu_doc, oracle_mod, cfg, n, a):
     parity_checks.check_load(gpu_doc, oracle_mod, cfg, n, a)   # above the default row threshold of the parallel decoders
+
+
+@pytest.mark.parametrize('cfg,n,a', [('C1', 0, 0), ('C2', 300, 0), ('C2b', 400, 0), ('C3', 600, 3), ('C3', 3000, 10), ('C4', 1500, 4), ('C6', 300, 3), ('C7', 300, 3), ('C8', 300, 3), ('C3', 60000, 10), ('C4', 40000, 10)])
+def test_history_after_load(gpu_doc, cfg, n, a):
+    parity_checks.check_history_after_load(gpu_doc, cfg, n, a)
+
+
+def test_history_after_load_late_cut(gpu_doc):
+    parity_checks.check_history_after_load(gpu_doc, 'C3', 1000, 4, frac=0.9)

@@ -120,3 +120,12 @@ def test_load_parallel_columns_emu(emu_doc, oracle_mod, monkeypatch):
     parity_checks.check_load_parallel_columns(emu_doc, oracle_mod, [('C2', 600, 0), ('C3', 6000, 3), ('C4', 3000, 4), ('C6', 500, 3), ('C7', 400, 3), ('C8', 400, 3)])
     parity_checks.check_rust_document(emu_doc)
     parity_checks.check_save_after_load(emu_doc, oracle_mod, 'C6', 300, 1)
+
+
+@pytest.mark.parametrize('cfg,n,a', [('C1', 0, 0), ('C2', 300, 0), ('C2b', 400, 0), ('C3', 600, 3), ('C3', 3000, 10), ('C4', 1500, 4), ('C6', 300, 3), ('C7', 300, 3), ('C8', 300, 3)])
+def test_history_after_load_emu(emu_doc, cfg, n, a):
+    parity_checks.check_history_after_load(emu_doc, cfg, n, a)
+
+
+def test_history_after_load_late_cut_emu(emu_doc):
+    parity_checks.check_history_after_load(emu_doc, 'C3', 1000, 4, frac=0.9)
