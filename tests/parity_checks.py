@@ -442,3 +442,106 @@ def check_history_after_load(Doc, cfg, n, a, frac=0.5):
     g.apply_changes(ch)
     assert g.save() == saved_full and g.heads() == full.heads()
     return len(ch)
+
+
+# ---------------------------------------------------------------------------------------------
+# Sync protocol (automerge_classic_b200/sync.py over the Backend facade; scenarios after test/sync_test.js)
+def _sync_facade(Doc):
+    from automerge_classic_b200 import bind_sync
+    from automerge_classic_b200.backend import Backend as Facade
+    return bind_sync(Facade(Doc))
+
+
+def _local_change(B, backend, actor, seq, key, value):
+    state = backend['state']
+    change = {'actor': actor, 'seq': seq, 'startOp': state.max_op() + 1, 'time': 0, 'message': '', 'deps': list(B.getHeads(backend)),
+              'ops': [{'action': 'set', 'obj': '_root', 'key': key, 'value': value, 'datatype': 'int', 'pred': []}]}
+    backend, _patch, binary = B.applyLocalChange(backend, change)
+    return backend, binary
+
+
+def _sync(B, a, b, sa=None, sb=None, max_iter=12):
+    sa, sb = sa or B.initSyncState(), sb or B.initSyncState()
+    for _ in range(max_iter):
+        sa, ma = B.generateSyncMessage(a, sa)
+        sb, mb = B.generateSyncMessage(b, sb)
+        if ma is None and mb is None:
+            return a, b, sa, sb
+        if ma is not None:
+            b, sb, _ = B.receiveSyncMessage(b, sb, ma)
+        if mb is not None:
+            a, sa, _ = B.receiveSyncMessage(a, sa, mb)
+    raise AssertionError('did not synchronize within %d rounds' % max_iter)
+
+
+def _same_document(B, a, b):
+    d = replay.deep_equal(replay.decode(B.getPatch(a)), replay.decode(B.getPatch(b)))
+    assert d is None, d
+    return B.getHeads(a) == B.getHeads(b) and sorted(bytes(c) for c in B.getAllChanges(a)) == sorted(bytes(c) for c in B.getAllChanges(b))
+
+
+def check_sync_protocol(Doc):
+    from automerge_classic_b200 import sync, tracegen
+    B = _sync_facade(Doc)
+    A1, A2 = '01' * 16, '02' * 16
+    # wire formats
+    hashes = sorted(__import__('hashlib').sha256(bytes([i])).hexdigest() for i in range(40))
+    bloom = sync.BloomFilter(hashes[:30])
+    assert all(bloom.contains_hash(h) for h in hashes[:30])
+    assert sum(bloom.contains_hash(h) for h in hashes[30:]) <= 2
+    again = sync.BloomFilter(bloom.bytes)
+    assert (again.num_entries, again.num_bits_per_entry, again.num_probes, bytes(again.bits)) == (30, 10, 7, bytes(bloom.bits))
+    assert sync.BloomFilter([]).bytes == b'' and not sync.BloomFilter(b'').contains_hash(hashes[0])
+    msg = {'heads': hashes[:2], 'need': hashes[2:3], 'have': [{'lastSync': hashes[3:5], 'bloom': bloom.bytes}], 'changes': [b'abc', b'']}
+    assert B.decodeSyncMessage(B.encodeSyncMessage(msg)) == msg
+    assert B.decodeSyncMessage(B.encodeSyncMessage(msg) + b'future extension') == msg
+    for bad in (lambda: B.decodeSyncMessage(b'\x41'), lambda: B.encodeSyncMessage(dict(msg, heads=hashes[:2][::-1])), lambda: B.decodeSyncState(b'\x42')):
+        try:
+            bad()
+            raise AssertionError('expected an error')
+        except (ValueError, TypeError):
+            pass
+    st = B.initSyncState()
+    st['sharedHeads'] = hashes[:3]
+    assert B.decodeSyncState(B.encodeSyncState(st))['sharedHeads'] == hashes[:3]
+    # empty documents: one message with an empty Bloom filter, then nothing more to say
+    n1, n2 = B.init(), B.init()
+    s1, m1 = B.generateSyncMessage(n1, B.initSyncState())
+    dm = B.decodeSyncMessage(m1)
+    assert dm['heads'] == [] and dm['need'] == [] and dm['changes'] == [] and len(dm['have']) == 1 and dm['have'][0]['lastSync'] == [] and len(dm['have'][0]['bloom']) == 0
+    n2, s2, patch = B.receiveSyncMessage(n2, B.initSyncState(), m1)
+    assert patch is None
+    s2, m2 = B.generateSyncMessage(n2, s2)
+    assert m2 is None
+    # one side has everything, the other nothing
+    n1, n2 = B.init(), B.init()
+    for i in range(5):
+        n1, _ = _local_change(B, n1, A1, i + 1, 'x', i)
+    n1, n2, s1, s2 = _sync(B, n1, n2)
+    assert B.getHeads(n1) == B.getHeads(n2) and B.save(n1) == B.save(n2)
+    s1, m = B.generateSyncMessage(n1, s1)
+    assert m is None                                   # in sync: nothing to send
+    # both sides move on concurrently, with the sync state from before (also through its persisted form)
+    for i in range(5, 9):
+        n1, _ = _local_change(B, n1, A1, i + 1, 'x', i)
+    for i in range(4):
+        n2, _ = _local_change(B, n2, A2, i + 1, 'y', i)
+    s1 = B.decodeSyncState(B.encodeSyncState(s1))
+    n1, n2, s1, s2 = _sync(B, n1, n2, s1, s2)
+    assert _same_document(B, n1, n2) and len(B.getAllChanges(n1)) == 13   # (the saved bytes differ: each side applied the changes in its own order)
+    # a peer that lost its data asks again and gets everything
+    n2 = B.init()
+    n1, n2, s1, s2 = _sync(B, n1, n2, s1, B.initSyncState())
+    assert _same_document(B, n1, n2)
+    # larger histories: two replicas of a multi-actor trace at different points, one of them loaded from a saved document
+    ch = tracegen.generate('C3', 900, 4).changes()
+    p1, p2 = B.init(), B.init()
+    p1, _ = B.applyChanges(p1, ch[:700])
+    p2, _ = B.applyChanges(p2, ch[:300])
+    p2 = B.load(B.save(p2))                            # history comes from computeHashGraph
+    p1, p2, _, _ = _sync(B, p1, p2)
+    assert B.getHeads(p1) == B.getHeads(p2) and B.save(p1) == B.save(p2)
+    full = B.init()
+    full, _ = B.applyChanges(full, ch[:700])
+    assert B.save(p2) == B.save(full)
+    return True

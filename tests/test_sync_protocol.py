@@ -1,0 +1,29 @@
+"""Sync protocol functions (automerge_classic_b200/sync.py) over the engine: CPU run on the serial emulation build, GPU run
+on libamgpu.so. Scenarios follow the reference's test/sync_test.js (which needs the JavaScript frontend to run as is)."""
+import os
+import subprocess
+
+import pytest
+
+import parity_checks
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_sync_protocol_emu():
+    subprocess.check_call([os.path.join(HERE, '_emu', 'build.sh')])
+    from automerge_classic_b200 import build
+    build.build_tracegen()
+    from automerge_classic_b200.engine import doc_class_for
+    assert parity_checks.check_sync_protocol(doc_class_for(os.path.join(HERE, '_emu', 'libamgpu_emu.so')))
+
+
+@pytest.mark.gpu
+def test_sync_protocol_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from automerge_classic_b200 import build
+    build.build_all()
+    from automerge_classic_b200.engine import GpuBackendDoc
+    assert parity_checks.check_sync_protocol(GpuBackendDoc)
