@@ -316,7 +316,7 @@ class GpuBackendDoc:
     def apply_packed_flat(self, blob, offs, n, is_local=False, want_patch=True):
         pp, err = C.c_void_p(), _ErrStruct()
         if isinstance(blob, (bytes, bytearray)):
-            buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob)
+            buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(bytes(blob) if len(blob) else b'\0')   # (an empty list of changes is legal)
         elif isinstance(blob, np.ndarray):
             buf = blob.ctypes.data_as(C.c_void_p)
         else:

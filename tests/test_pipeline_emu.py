@@ -129,3 +129,14 @@ def test_history_after_load_emu(emu_doc, cfg, n, a):
 
 def test_history_after_load_late_cut_emu(emu_doc):
     parity_checks.check_history_after_load(emu_doc, 'C3', 1000, 4, frac=0.9)
+
+
+def test_empty_batch_emu(emu_doc):
+    from automerge_classic_b200 import tracegen
+    g = emu_doc()
+    p0 = g.apply_changes([])                       # an empty array of changes is legal (backend.js:27-32)
+    assert p0['diffs']['props'] == {} and p0['maxOp'] == 0
+    g.apply_changes(tracegen.generate('C2', 50, 0).changes())
+    before = g.save()
+    p1 = g.apply_changes([])
+    assert p1['diffs']['props'] == {} and g.save() == before
