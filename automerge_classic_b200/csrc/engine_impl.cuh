@@ -879,7 +879,6 @@ inline void Engine::computeHashGraph() {
   decodeCol(LC_UINT, 0x40, L, cDepsNum.p, tmpOff.p, tmpLen.p);
   decodeCol(LC_EXTRA_LEN, 0x56, L, cExtra.p, extraOff.p, extraLen.p);
   foreach(ctx, L, HistI64ToU32Kernel{cDepsNum.p, depsNum32.p});
-  foreach(ctx, L, HistI64ToU32Kernel{cDepsNum.p, tmpLen.p});   // (cDepsNum as the kernels read it: nulls -> 0)
   scan_exclusive(ctx, scanTmp, depsNum32.p, depBase.p, L);
   const size_t D = readU32(depBase.p + L);
   depIdxV.ensure(ctx, D + 1); depIdx.ensure(ctx, D + 2);
