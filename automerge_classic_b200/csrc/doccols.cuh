@@ -119,7 +119,6 @@ struct PcDeltaToI64Kernel { const long long* v; const u64* excl; long long* out;
 struct PcLenBytesKernel { const long long* v; u32* bytes; u32* bad; HD void operator()(size_t i) const { const long long x = v[i]; u64 b = x == NULLV ? 0 : ((u64)x >> 4); if (b > 0x7fffffffULL) { *bad = 1; b = 0; } bytes[i] = (u32)b; } };
 struct PcCountKernel { const long long* v; u32* cnt; u32* bad; HD void operator()(size_t i) const { const long long x = v[i]; u64 c = x == NULLV ? 0 : (u64)x; if (c > 0x7fffffffULL) { *bad = 1; c = 0; } cnt[i] = (u32)c; } };
 struct PcAddBaseKernel { u32* a; u32 base; HD void operator()(size_t i) const { a[i] += base; } };
-struct PcNullToZeroKernel { u32* a; HD void operator()(size_t i) const { if (a[i] == NULL32) a[i] = 0; } };
 struct PcCopyI64Kernel { const long long* in; long long* out; HD void operator()(size_t i) const { out[i] = in[i]; } };
 
 // ---- boolean columns: the tokens are run lengths, values alternate starting with false
