@@ -853,6 +853,8 @@ inline void Engine::computeHashGraph() {
   if (L == 0) { haveHashGraph = true; return; }
   if (L >= (1u << 29) || N + S >= (1u << 30)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: document too large for history reconstruction");
   DocRows d = doc.view();
+  HostClock hclk; const bool htrace = getenv("AMG_PAR_DOC_TRACE") != nullptr;
+  auto hmark = [&](const char* what) { if (htrace) { sync(ctx); fprintf(stderr, "amgpu history: %-26s %9.2f ms\n", what, hclk.ms()); } };
   dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull;
   // ---- 1. change metadata columns (the same decoders as save() after load())
   auto loadedCol = [&](u32 id) -> const HostChange& { static const u32 IDS[9] = {0x01, 0x03, 0x13, 0x23, 0x35, 0x40, 0x43, 0x56, 0x57}; for (int k = 0; k < 9; k++) if (IDS[k] == id) return loadedCols[k]; return loadedCols[0]; };
@@ -893,6 +895,7 @@ inline void Engine::computeHashGraph() {
   for (DBuf<u32>* b : {&rankD, &actorOfRank, &repOff, &repLen}) b->ensure(ctx, A + 1);
   h2d(ctx, rankD.p, rankH.data(), A * 4); h2d(ctx, actorOfRank.p, order.data(), A * 4); h2d(ctx, repOff.p, repOffH.data(), A * 4); h2d(ctx, repLen.p, repLenH.data(), A * 4);
   const int ctrBits = bits_for(maxOp + 1), idBits = std::min(64, ctrBits + 16);
+  hmark("change columns decoded");
   // ---- 3. (successor, predecessor) pairs -> pred lists and deletions
   DBuf<u64> predKey, succKey, keyA, keyB, groupId, opId; DBuf<u32> pairRow, valA, pairRowSorted, head, groupIdx, groupStart, groupRow, isDel, delSlot, idRows;
   DBuf<u64> idSorted; idSorted.ensure(ctx, N + 1); idRows.ensure(ctx, N + 1);
@@ -925,6 +928,7 @@ inline void Engine::computeHashGraph() {
   opPredBase.ensure(ctx, M + 3);
   if (N) foreach(ctx, N, HistRowOpKernel{d, opId.p, opSrc.p, opPredStart.p, opPredNum.p});
   if (G) foreach(ctx, G, HistGroupOpKernel{groupStart.p, groupId.p, groupRow.p, isDel.p, delSlot.p, pairRowSorted.p, (u32)G, (u32)S, (u32)N, opId.p, opSrc.p, opPredStart.p, opPredNum.p});
+  hmark("preds and deletions");
   // ---- 4. ops by (actor, counter); changes by (actor, seq); every op finds its change
   DBuf<u64> opKey, chKey; opKey.ensure(ctx, M + 1); chKey.ensure(ctx, L + 1);
   DBuf<u32> changeOrder, actorStart, chOpStart, chNOps; changeOrder.ensure(ctx, L + 1); actorStart.ensure(ctx, A + 2); chOpStart.ensure(ctx, L + 2); chNOps.ensure(ctx, L + 2);
@@ -943,6 +947,7 @@ inline void Engine::computeHashGraph() {
   } else dev_memset(ctx, opPredBase.p, 0, 8);
   const size_t P = M ? readU32(opPredBase.p + M) : 0;
   checkErr(actorIds);
+  hmark("ops assigned to changes");
   // ---- 5. the other actors of every change
   HistOpView view{d, opId.p, opSrc.p, opPredStart.p, opPredNum.p, opOrder.p, pairRowSorted.p, (u32)N};
   DBuf<u32> slotCnt, slotBase, uniq, uniqSlot, otherStart; DBuf<u64> slotKey, other; DBuf<u32> slotVal;
@@ -961,6 +966,7 @@ inline void Engine::computeHashGraph() {
   other.ensure(ctx, U + 1);
   if (U) foreach(ctx, Q, HistOtherFillKernel{slotKey.p, uniq.p, uniqSlot.p, other.p});
   foreach(ctx, L + 1, HistLowerBoundKernel{other.p, (u32)U, 16, otherStart.p});
+  hmark("actor tables");
   // ---- 6. local actor indexes and delta values, then the bytes (two passes)
   DBuf<u32> objA, keyAi, predA, outLen, outOff, depsAt, bodyAt, chOffD; DBuf<long long> keyDelta, predDelta;
   objA.ensure(ctx, M + 1); keyAi.ensure(ctx, M + 1); keyDelta.ensure(ctx, M + 1); predA.ensure(ctx, P + 1); predDelta.ensure(ctx, P + 1);
@@ -981,6 +987,7 @@ inline void Engine::computeHashGraph() {
   foreach(ctx, L, enc);
   foreach(ctx, L, HistChOffKernel{outOff.p, (u32)arenaLen, chOffD.p});
   checkErr(actorIds);
+  hmark("changes encoded");
   // ---- 7. dependency levels (host: one pass over the dependency indexes), hashes level by level
   std::vector<u32> depsNumH(L), depBaseH(L + 1), depIdxH(D), level(L), list(L);
   d2h(ctx, depsNumH.data(), depsNum32.p, L * 4); d2h(ctx, depBaseH.data(), depBase.p, (L + 1) * 4); if (D) d2h(ctx, depIdxH.data(), depIdx.p, D * 4); sync(ctx);
@@ -996,11 +1003,26 @@ inline void Engine::computeHashGraph() {
   { std::vector<u32> at(levelStart.begin(), levelStart.end() - 1); for (size_t k = 0; k < L; k++) list[at[level[k]]++] = (u32)k; }
   DBuf<u32> listD; listD.ensure(ctx, L + 1); h2d(ctx, listD.p, list.data(), L * 4);
   DBuf<u8> newHashes; newHashes.ensure(ctx, L * 32 + 64); d2d(ctx, newHashes.p, hashes.p, L * 32);   // scratch copy: committed only after the heads check
-  for (u32 l = 0; l <= maxLevel; l++) {
-    const size_t cnt = levelStart[l + 1] - levelStart[l];
-    if (cnt) foreach(ctx, cnt, HistHashKernel{listD.p + levelStart[l], arena.p, chOffD.p, outLen.p, depsAt.p, bodyAt.p, cDepsNum.p, depBase.p, depIdx.p, (u32)L, newHashes.p, errWord.p});
+  {
+    const HistHashKernel hk{listD.p, arena.p, chOffD.p, outLen.p, depsAt.p, bodyAt.p, cDepsNum.p, depBase.p, depIdx.p, (u32)L, newHashes.p, errWord.p};
+    auto wide = [&](u32 l) { HistHashKernel k = hk; k.list = listD.p + levelStart[l]; const size_t cnt = levelStart[l + 1] - levelStart[l]; if (cnt) foreach(ctx, cnt, k); };
+#ifdef AMG_EMU
+    for (u32 l = 0; l <= maxLevel; l++) wide(l);
+#else
+    DBuf<u32> levelStartD; levelStartD.ensure(ctx, levelStart.size() + 1); h2d(ctx, levelStartD.p, levelStart.data(), levelStart.size() * 4);
+    const u32 kNarrow = 1024;   // levels up to this many changes are walked by one CTA (k_hist_hash_chain); wider ones get their own launch
+    for (u32 l = 0; l <= maxLevel;) {
+      if (levelStart[l + 1] - levelStart[l] > kNarrow) { wide(l); l++; continue; }
+      u32 r = l; while (r <= maxLevel && levelStart[r + 1] - levelStart[r] <= kNarrow) r++;
+      k_hist_hash_chain<<<1, 256, 0, ctx.stream>>>(hk, levelStartD.p, l, r - l);
+      CUDA_CHECK(cudaGetLastError()); ctx.launches++;
+      l = r;
+    }
+    sync(ctx);   // levelStartD is a local
+#endif
   }
   checkErr(actorIds);
+  hmark("hashes (all levels)");
   // ---- 8. heads: the changes nobody depends on must be exactly the document's heads (columnar.js:968-980)
   {
     size_t nHeads = 0; for (size_t k = 0; k < L; k++) if (!isDep[k]) nHeads++;
@@ -1013,6 +1035,7 @@ inline void Engine::computeHashGraph() {
     }
     if (!ok) throw Error(AMG_ERR_RANGE, "Mismatched heads hashes: the document's heads are not the hashes of its reconstructed changes");
   }
+  hmark("heads checked");
   // ---- 9. commit: bytes into the arena and its host mirror, hashes, change table
   hostArena.resize(arenaLen + T);
   if (T) d2h(ctx, hostArena.data() + arenaLen, arena.p + arenaLen, T);
@@ -1020,6 +1043,7 @@ inline void Engine::computeHashGraph() {
   std::vector<u32> offH(L), lenH(L); d2h(ctx, offH.data(), chOffD.p, L * 4); d2h(ctx, lenH.data(), outLen.p, L * 4); sync(ctx);
   for (size_t k = 0; k < L; k++) changes[k] = HostChange{offH[k], lenH[k]};
   arenaLen += T; haveHashGraph = true; historyRebuilt = L;
+  hmark("committed");
 }
 
 // Parity hook: one document column through the parallel or the serial decoder (include/amgpu.h)

@@ -327,4 +327,18 @@ struct HistHashKernel {
   }
 };
 
+#ifndef AMG_EMU
+// Deep, narrow dependency graphs (one change per actor and level: editing traces) would cost one launch per level. One CTA
+// walks a run of consecutive narrow levels instead: the changes of a level in parallel, a barrier between levels (the
+// hashes a level reads were written by the same CTA before the barrier).
+__global__ void __launch_bounds__(256) k_hist_hash_chain(HistHashKernel hk, const u32* __restrict__ levelStart, u32 firstLevel, u32 numLevels) {
+  for (u32 l = 0; l < numLevels; l++) {
+    const u32 s = levelStart[firstLevel + l], e = levelStart[firstLevel + l + 1];
+    for (u32 t = s + threadIdx.x; t < e; t += 256) hk(t);
+    __threadfence();
+    __syncthreads();
+  }
+}
+#endif
+
 }  // namespace amg
