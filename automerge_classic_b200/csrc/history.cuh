@@ -299,12 +299,16 @@ HD void hist_sha256(const u8* m, u32 mlen, u8 out[32]) {
   const u32 nBlocks = (mlen + 9 + 63) / 64; u32 w[16];
   for (u32 blk = 0; blk < nBlocks; blk++) {
     const u32 done = blk * 64;
-    for (int i = 0; i < 16; i++) {
-      u32 x = 0;
-      for (int b = 0; b < 4; b++) { const u32 ix = done + 4 * i + b; u32 byte = 0; if (ix < mlen) byte = m[ix]; else if (ix == mlen) byte = 0x80; x = (x << 8) | byte; }
-      w[i] = x;
+    if (done + 64 <= mlen) {   // full block: 16 independent word loads (as ShaKernel does), not 64 dependent byte loads
+      for (int i = 0; i < 16; i++) w[i] = load_be32(m + done + 4 * i);
+    } else {
+      for (int i = 0; i < 16; i++) {
+        u32 x = 0;
+        for (int b = 0; b < 4; b++) { const u32 ix = done + 4 * i + b; u32 byte = 0; if (ix < mlen) byte = m[ix]; else if (ix == mlen) byte = 0x80; x = (x << 8) | byte; }
+        w[i] = x;
+      }
+      if (blk == nBlocks - 1) { w[14] = (u32)(((u64)mlen * 8) >> 32); w[15] = (u32)((u64)mlen * 8); }
     }
-    if (blk == nBlocks - 1) { w[14] = (u32)(((u64)mlen * 8) >> 32); w[15] = (u32)((u64)mlen * 8); }
     sha256_compress(h, w, K);
   }
   for (int i = 0; i < 8; i++) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }
