@@ -545,3 +545,49 @@ def check_sync_protocol(Doc):
     full, _ = B.applyChanges(full, ch[:700])
     assert B.save(p2) == B.save(full)
     return True
+
+
+def check_sync_random(Doc, seed, steps=40):
+    """Three replicas; random local changes, pairwise sync exchanges (with lost messages and replicas restored from a saved
+    document in between); in the end one full round of exchanges makes all three the same document."""
+    import random
+    rnd = random.Random(seed)
+    B = _sync_facade(Doc)
+    actors = ['%02x' % (i + 1) * 16 for i in range(3)]
+    peers = [B.init() for _ in range(3)]
+    seqs = [0, 0, 0]
+    states = {}                                    # (i, j): what i believes about j
+    def st(i, j):
+        return states.setdefault((i, j), B.initSyncState())
+    def exchange(i, j, lossy=False):
+        for _ in range(12):
+            states[(i, j)], mi = B.generateSyncMessage(peers[i], st(i, j))
+            states[(j, i)], mj = B.generateSyncMessage(peers[j], st(j, i))
+            if mi is None and mj is None:
+                return
+            if mi is not None and not (lossy and rnd.random() < 0.3):
+                peers[j], states[(j, i)], _ = B.receiveSyncMessage(peers[j], st(j, i), mi)
+            if mj is not None and not (lossy and rnd.random() < 0.3):
+                peers[i], states[(i, j)], _ = B.receiveSyncMessage(peers[i], st(i, j), mj)
+            if lossy and rnd.random() < 0.2:
+                return                              # connection dropped mid-way
+    for _ in range(steps):
+        op = rnd.random()
+        i = rnd.randrange(3)
+        if op < 0.55:
+            seqs[i] += 1
+            peers[i], _ = _local_change(B, peers[i], actors[i], seqs[i], rnd.choice('abcdef'), rnd.randrange(1000))
+        elif op < 0.9:
+            j = rnd.choice([x for x in range(3) if x != i])
+            exchange(i, j, lossy=rnd.random() < 0.4)
+        else:
+            peers[i] = B.load(B.save(peers[i]))     # restart: persisted document + persisted sync states
+            for j in range(3):
+                if (i, j) in states:
+                    states[(i, j)] = B.decodeSyncState(B.encodeSyncState(states[(i, j)]))
+    for _ in range(2):
+        for i, j in ((0, 1), (1, 2), (0, 2)):
+            exchange(i, j)
+    assert _same_document(B, peers[0], peers[1]) and _same_document(B, peers[1], peers[2])
+    assert len(B.getAllChanges(peers[0])) == sum(seqs)
+    return sum(seqs)

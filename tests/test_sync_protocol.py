@@ -18,6 +18,13 @@ def test_sync_protocol_emu():
     assert parity_checks.check_sync_protocol(doc_class_for(os.path.join(HERE, '_emu', 'libamgpu_emu.so')))
 
 
+@pytest.mark.parametrize('seed', [1, 2, 3, 4, 5, 6])
+def test_sync_random_emu(seed):
+    from automerge_classic_b200.engine import doc_class_for
+    subprocess.check_call([os.path.join(HERE, '_emu', 'build.sh')])
+    assert parity_checks.check_sync_random(doc_class_for(os.path.join(HERE, '_emu', 'libamgpu_emu.so')), seed) > 0
+
+
 @pytest.mark.gpu
 def test_sync_protocol_gpu():
     import torch
@@ -27,3 +34,13 @@ def test_sync_protocol_gpu():
     build.build_all()
     from automerge_classic_b200.engine import GpuBackendDoc
     assert parity_checks.check_sync_protocol(GpuBackendDoc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('seed', [1, 2, 3])
+def test_sync_random_gpu(seed):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from automerge_classic_b200.engine import GpuBackendDoc
+    assert parity_checks.check_sync_random(GpuBackendDoc, seed) > 0
