@@ -10,19 +10,22 @@ import parity_checks
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def test_sync_protocol_emu():
+@pytest.fixture(scope='module')
+def emu_doc():
     subprocess.check_call([os.path.join(HERE, '_emu', 'build.sh')])
     from automerge_classic_b200 import build
     build.build_tracegen()
     from automerge_classic_b200.engine import doc_class_for
-    assert parity_checks.check_sync_protocol(doc_class_for(os.path.join(HERE, '_emu', 'libamgpu_emu.so')))
+    return doc_class_for(os.path.join(HERE, '_emu', 'libamgpu_emu.so'))
+
+
+def test_sync_protocol_emu(emu_doc):
+    assert parity_checks.check_sync_protocol(emu_doc)
 
 
 @pytest.mark.parametrize('seed', [1, 2, 3, 4, 5, 6])
-def test_sync_random_emu(seed):
-    from automerge_classic_b200.engine import doc_class_for
-    subprocess.check_call([os.path.join(HERE, '_emu', 'build.sh')])
-    assert parity_checks.check_sync_random(doc_class_for(os.path.join(HERE, '_emu', 'libamgpu_emu.so')), seed) > 0
+def test_sync_random_emu(emu_doc, seed):
+    assert parity_checks.check_sync_random(emu_doc, seed) > 0
 
 
 @pytest.mark.gpu
