@@ -670,7 +670,8 @@ struct BackendDoc {
       if (q.empty()) break;
       if (applied.empty()) {
         if (haveHashGraph) break;
-        throw RangeError("oracle: computeHashGraph (new.js:1887-1912) is not restated");
+        computeHashGraph();   // new.js:1837-1839
+        cibh = changeIndexByHash;
       }
     }
     setupPatches(patches, objectIds, ds);
@@ -728,7 +729,126 @@ struct BackendDoc {
     return binaryDoc;
   }
 
-  void requireHashGraph() const { if (!haveHashGraph) throw RangeError("oracle: computeHashGraph (new.js:1887-1912) is not restated"); }
+  // new.js:1887-1912 computeHashGraph. The reference saves the document, decodes it again (decodeChanges -> decodeDocument,
+  // columnar.js:1040-1047, 876-981) and re-encodes every change (encodeChange, columnar.js:710-738). What decodeDocument
+  // would read back is exactly the change metadata and the document ops held here, so this starts from those.
+  void computeHashGraph() {
+    struct HOp {
+      int64_t idCtr = 0, idActor = 0, objActor = NUL, objCtr = NUL, keyActor = NUL, keyCtr = NUL; bool hasKeyStr = false; std::string keyStr;
+      bool insert = false; int64_t action = 0, valLen = 0; std::string valRaw; std::vector<std::pair<int64_t, int64_t>> pred; bool del = false;
+    };
+    const size_t numChanges = changeMetas.size();
+    // ---- groupChangeOps (columnar.js:876-944)
+    std::map<int64_t, std::vector<size_t>> changesByActor;
+    for (size_t i = 0; i < numChanges; i++) {
+      auto& list = changesByActor[changeMetas[i].actor];
+      if (changeMetas[i].seq != (int64_t)list.size() + 1) throw RangeError("Expected seq = " + std::to_string(list.size() + 1) + ", got " + std::to_string(changeMetas[i].seq));
+      if (changeMetas[i].seq > 1 && changeMetas[list.back()].maxOp > changeMetas[i].maxOp) throw RangeError("maxOp must increase monotonically per actor");
+      list.push_back(i);
+    }
+    typedef std::pair<int64_t, int64_t> Id;   // (counter, actor index)
+    std::map<Id, size_t> opsById; std::vector<HOp> ops;
+    for (auto& b : blocks) for (auto& op : b->ops) {
+      if (op.action == 3) throw RangeError("document should not contain del operations");
+      HOp h; h.idCtr = op.idCtr; h.idActor = op.idActor; h.objActor = op.objActor; h.objCtr = op.objCtr; h.keyActor = op.keyActor; h.keyCtr = op.keyCtr;
+      h.hasKeyStr = op.hasKeyStr; h.keyStr = op.keyStr; h.insert = op.insert; h.action = op.action; h.valLen = op.valLen == NUL ? 0 : op.valLen; h.valRaw = op.valRaw;
+      const Id id(op.idCtr, op.idActor);
+      auto it = opsById.find(id);
+      if (it != opsById.end()) { h.pred = ops[it->second].pred; ops[it->second] = h; }   // a successor list mentioned it before it appeared
+      else { opsById[id] = ops.size(); ops.push_back(h); }
+      for (size_t k = 0; k < op.succCtr.size(); k++) {
+        const Id sid(op.succCtr[k], op.succActor[k]);
+        auto st = opsById.find(sid);
+        if (st == opsById.end()) {
+          HOp d; d.del = true; d.action = 3; d.idCtr = sid.first; d.idActor = sid.second; d.objActor = op.objActor; d.objCtr = op.objCtr;
+          if (!op.hasKeyStr) { if (op.insert) { d.keyActor = op.idActor; d.keyCtr = op.idCtr; } else { d.keyActor = op.keyActor; d.keyCtr = op.keyCtr; } }
+          else { d.hasKeyStr = true; d.keyStr = op.keyStr; }
+          opsById[sid] = ops.size(); ops.push_back(d); st = opsById.find(sid);
+        }
+        ops[st->second].pred.push_back(id);
+      }
+    }
+    std::vector<std::vector<size_t>> changeOps(numChanges);
+    for (size_t o = 0; o < ops.size(); o++) {
+      auto ca = changesByActor.find(ops[o].idActor);
+      const std::string opIdText = std::to_string(ops[o].idCtr) + "@" + (ops[o].idActor >= 0 && (size_t)ops[o].idActor < actorIds.size() ? actorIds[ops[o].idActor] : std::string("?"));
+      if (ca == changesByActor.end()) throw RangeError("Operation ID " + opIdText + " outside of allowed range");
+      auto& list = ca->second; size_t left = 0, right = list.size();
+      while (left < right) { const size_t mid = (left + right) / 2; if (changeMetas[list[mid]].maxOp < ops[o].idCtr) left = mid + 1; else right = mid; }
+      if (left >= list.size()) throw RangeError("Operation ID " + opIdText + " outside of allowed range");
+      changeOps[list[left]].push_back(o);
+    }
+    auto idLess = [&](const Id& a, const Id& b) { return a.first != b.first ? a.first < b.first : actorIds[a.second] < actorIds[b.second]; };
+    // ---- decodeDocumentChanges (columnar.js:946-981) with encodeChange per change
+    std::vector<std::string> newChanges(numChanges), newHashes(numChanges);
+    std::set<std::string> headSet;
+    for (size_t i = 0; i < numChanges; i++) {
+      const ChangeMeta& m = changeMetas[i]; auto& mine = changeOps[i];
+      std::sort(mine.begin(), mine.end(), [&](size_t a, size_t b) { return idLess(Id(ops[a].idCtr, ops[a].idActor), Id(ops[b].idCtr, ops[b].idActor)); });
+      const int64_t startOp = m.maxOp - (int64_t)mine.size() + 1;
+      for (size_t k = 0; k < mine.size(); k++) if (ops[mine[k]].idCtr != startOp + (int64_t)k || ops[mine[k]].idActor != m.actor)
+        throw RangeError("Expected opId " + std::to_string(startOp + (int64_t)k) + "@" + actorIds[m.actor] + ", got " + std::to_string(ops[mine[k]].idCtr) + "@" + actorIds[ops[mine[k]].idActor]);
+      std::vector<std::string> deps;
+      for (int64_t index : m.depsIndex) {
+        if (index < 0 || (size_t)index >= i || newHashes[index].empty()) throw RangeError("No hash for index " + std::to_string(index) + " while processing index " + std::to_string(i));
+        deps.push_back(newHashes[index]); headSet.erase(newHashes[index]);
+      }
+      std::sort(deps.begin(), deps.end());
+      // encodeChange (columnar.js:710-738) with parseAllOpIds (:132-170) and encodeOps (:370-436)
+      std::set<std::string> actorSet;
+      for (size_t o : mine) {
+        const HOp& op = ops[o];
+        if (op.objCtr != NUL) actorSet.insert(actorIds[op.objActor]);
+        if (!op.hasKeyStr && op.keyActor != NUL) actorSet.insert(actorIds[op.keyActor]);
+        for (auto& pr : op.pred) actorSet.insert(actorIds[pr.second]);
+      }
+      std::vector<std::string> localActors{actorIds[m.actor]};
+      for (auto& a : actorSet) if (a != actorIds[m.actor]) localActors.push_back(a);
+      auto localNum = [&](int64_t docActor) -> int64_t { for (size_t k = 0; k < localActors.size(); k++) if (localActors[k] == actorIds[docActor]) return (int64_t)k; throw RangeError("missing actorId"); };
+      RLEEncoder objActorE(T_UINT), objCtrE(T_UINT), keyActorE(T_UINT), keyStrE(T_UTF8), actionE(T_UINT), valLenE(T_UINT), predNumE(T_UINT), predActorE(T_UINT);
+      DeltaEncoder keyCtrE, predCtrE; BooleanEncoder insertE; std::string valRaw;
+      for (size_t o : mine) {
+        HOp& op = ops[o];
+        if (op.objCtr == NUL) { objActorE.appendValue(RV()); objCtrE.appendValue(RV()); } else { objActorE.appendValue(RV::Num(localNum(op.objActor))); objCtrE.appendValue(RV::Num(op.objCtr)); }
+        if (op.hasKeyStr) { keyActorE.appendValue(RV()); keyCtrE.appendValue(RV()); keyStrE.appendValue(RV::Str(op.keyStr)); }
+        else if (op.keyActor == NUL) { keyActorE.appendValue(RV()); keyCtrE.appendValue(RV::Num(0)); keyStrE.appendValue(RV()); }   // _head
+        else { keyActorE.appendValue(RV::Num(localNum(op.keyActor))); keyCtrE.appendValue(RV::Num(op.keyCtr)); keyStrE.appendValue(RV()); }
+        insertE.appendValue(op.insert); actionE.appendValue(RV::Num(op.action));
+        valLenE.appendValue(RV::Num(op.del ? 0 : op.valLen)); if (!op.del) valRaw += op.valRaw;   // (values travel as tag + bytes: canonical input re-encodes to itself)
+        predNumE.appendValue(RV::Num((int64_t)op.pred.size()));
+        std::sort(op.pred.begin(), op.pred.end(), idLess);
+        for (auto& pr : op.pred) { predActorE.appendValue(RV::Num(localNum(pr.second))); predCtrE.appendValue(RV::Num(pr.first)); }
+      }
+      std::vector<Column> cols = {{COL_OBJ_ACTOR, objActorE.finish()}, {COL_OBJ_CTR, objCtrE.finish()}, {COL_KEY_ACTOR, keyActorE.finish()}, {COL_KEY_CTR, keyCtrE.finish()},
+                                  {COL_KEY_STR, keyStrE.finish()}, {COL_INSERT, insertE.finish()}, {COL_ACTION, actionE.finish()}, {COL_VAL_LEN, valLenE.finish()},
+                                  {COL_VAL_RAW, valRaw}, {0x70, predNumE.finish()}, {0x71, predActorE.finish()}, {0x73, predCtrE.finish()}};
+      Encoder body; body.appendUint53((int64_t)deps.size()); for (auto& dep : deps) body.appendRaw(fromHex(dep));
+      body.appendHexString(actorIds[m.actor]); body.appendUint53(m.seq); body.appendUint53(startOp); body.appendInt53(m.time); body.appendPrefixed(m.message);
+      body.appendUint53((int64_t)localActors.size() - 1); for (size_t k = 1; k < localActors.size(); k++) body.appendHexString(localActors[k]);
+      encodeColumnInfo(body, cols); for (auto& c : cols) body.appendRaw(c.buffer);
+      body.appendRaw(m.extra);
+      std::string hash; std::string bytes = encodeContainer(CHUNK_TYPE_CHANGE, body.buf, &hash);
+      newHashes[i] = hash; newChanges[i] = bytes.size() >= DEFLATE_MIN_SIZE ? deflateChange(bytes) : bytes;
+      headSet.insert(hash);
+    }
+    std::vector<std::string> actualHeads(headSet.begin(), headSet.end());
+    if (actualHeads != heads) { std::string a, b; for (auto& h : heads) a += (a.empty() ? "" : ", ") + h; for (auto& h : actualHeads) b += (b.empty() ? "" : ", ") + h; throw RangeError("Mismatched heads hashes: expected " + a + ", got " + b); }
+    // ---- new.js:1889-1911: the graph tables
+    changes = newChanges; changePresent.assign(numChanges, true); changeIndexByHash.clear(); dependenciesByHash.clear(); dependentsByHash.clear(); hashesByActor.clear();
+    std::map<std::string, int64_t> clk;
+    for (size_t i = 0; i < numChanges; i++) {
+      DecodedChange dc = decodeChangeColumns(changes[i]);
+      changeIndexByHash[dc.hash] = (int64_t)i; dependenciesByHash[dc.hash] = dc.deps; dependentsByHash[dc.hash];
+      for (auto& dep : dc.deps) dependentsByHash[dep].push_back(dc.hash);
+      if (dc.seq == 1) hashesByActor[dc.actor].clear();
+      hashesByActor[dc.actor].push_back(dc.hash);
+      const int64_t expectedSeq = clk[dc.actor] + 1;
+      if (dc.seq != expectedSeq) throw RangeError("Expected seq " + std::to_string(expectedSeq) + ", got seq " + std::to_string(dc.seq) + " from actor " + dc.actor);
+      clk[dc.actor] = dc.seq;
+    }
+    haveHashGraph = true;
+  }
+  void requireHashGraph() { if (!haveHashGraph) computeHashGraph(); }
 
   // new.js:1921-1973
   std::vector<std::string> getChanges(const std::vector<std::string>& haveDeps) {
