@@ -166,15 +166,17 @@ int amg_get_changes(amg_backend* b, const uint8_t* have_deps, size_t n, amg_buff
       auto it = g.dependents.find(h); if (it == g.dependents.end() || !g.indexByHash.count(h)) throw amg::Error(AMG_RANGE_ERROR, "hash not found: " + hashHex(h));
       stack.insert(stack.end(), it->second.begin(), it->second.end());
     }
-    bool aborted = false;
+    // Reference quirk reproduced on purpose (new.js:1938-1955): the traversal stops at a change with an unseen dependency, but
+    // the test below only looks at the stack and the heads - when that change was the last one on the stack and the heads
+    // have all been seen, the fast path still answers, without the changes that are concurrent to `haveDeps`.
     while (!stack.empty()) {
       Hash h = stack.back(); stack.pop_back(); seen[h] = true; toReturn.push_back(h);
       bool all = true; for (auto& d : g.deps[g.indexByHash[h]]) if (!seen.count(d)) all = false;
-      if (!all) { aborted = true; break; }
+      if (!all) break;
       auto& ds = g.dependents[h]; stack.insert(stack.end(), ds.begin(), ds.end());
     }
     bool headsSeen = true; for (auto& h : b->eng.heads) if (!seen.count(h)) headsSeen = false;
-    if (!aborted && stack.empty() && headsSeen) { for (auto& h : toReturn) l->items.push_back(b->changeBytes(g.indexByHash[h])); *out = guard.release(); return 0; }
+    if (stack.empty() && headsSeen) { for (auto& h : toReturn) l->items.push_back(b->changeBytes(g.indexByHash[h])); *out = guard.release(); return 0; }
     stack.clear(); for (size_t i = 0; i < n; i++) stack.push_back(toHash(have_deps + 32 * i)); seen.clear();
     while (!stack.empty()) {
       Hash h = stack.back(); stack.pop_back();

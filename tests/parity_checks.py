@@ -547,7 +547,7 @@ def check_sync_protocol(Doc):
     return True
 
 
-def check_sync_random(Doc, seed, steps=40):
+def check_sync_random(Doc, seed, steps=40, transcript=None):
     """Three replicas; random local changes, pairwise sync exchanges (with lost messages and replicas restored from a saved
     document in between); in the end one full round of exchanges makes all three the same document."""
     import random
@@ -563,6 +563,8 @@ def check_sync_random(Doc, seed, steps=40):
         for _ in range(12):
             states[(i, j)], mi = B.generateSyncMessage(peers[i], st(i, j))
             states[(j, i)], mj = B.generateSyncMessage(peers[j], st(j, i))
+            if transcript is not None:
+                transcript.append((i, j, mi, mj))
             if mi is None and mj is None:
                 return
             if mi is not None and not (lossy and rnd.random() < 0.3):
@@ -621,3 +623,36 @@ def check_history_against_oracle(Doc, oracle_mod, cfg, n, a, frac=0.5):
     assert [bytes(c) for c in g3.get_changes([])] == [bytes(c) for c in o3.get_changes([])]
     assert g3.get_missing_deps() == o3.get_missing_deps()
     return po['pendingChanges']
+
+
+def check_sync_transcripts_equal(Doc, oracle_mod, seed):
+    """The same scripted session of three replicas on the engine and on the oracle: every sync message (heads, need, Bloom
+    filter, the changes chosen and their order) is byte-identical."""
+    mine, theirs = [], []
+    check_sync_random(Doc, seed, transcript=mine)
+    check_sync_random(oracle_mod.OracleDoc, seed, transcript=theirs)
+    assert len(mine) == len(theirs)
+    for k, (a, b) in enumerate(zip(mine, theirs)):
+        assert a == b, 'sync message %d differs (peers %d -> %d)' % (k, a[0], a[1])
+    return len(mine)
+
+
+def check_get_changes_differential(Doc, oracle_mod, seed=3, queries=150):
+    """getChanges(haveDeps) for random sets of known hashes: the same changes in the same order as the oracle, which restates
+    the reference's traversal including its fast path (new.js:1921-1973)."""
+    import random
+    from automerge_classic_b200 import tracegen, columnar
+    rnd = random.Random(seed)
+    total = 0
+    for cfg, n, a in [('C3', 300, 3), ('C3', 500, 5), ('C6', 200, 3), ('C4', 1500, 6), ('C8', 300, 4)]:
+        ch = tracegen.generate(cfg, n, a).changes()
+        hashes = [columnar.decode_change(c)['hash'] for c in ch]
+        o, g = oracle_mod.OracleDoc(), Doc()
+        o.apply_changes(ch)
+        g.apply_changes(ch)
+        for _ in range(queries):
+            have = sorted(rnd.sample(hashes, min(len(hashes), rnd.choice([1, 1, 2, 3]))))
+            assert [bytes(c) for c in g.get_changes(have)] == [bytes(c) for c in o.get_changes(have)], (cfg, [hashes.index(h) for h in have])
+            total += 1
+        assert g.get_missing_deps(have) == o.get_missing_deps(have)
+    return total

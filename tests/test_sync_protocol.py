@@ -28,6 +28,15 @@ def test_sync_random_emu(emu_doc, seed):
     assert parity_checks.check_sync_random(emu_doc, seed) > 0
 
 
+@pytest.mark.parametrize('seed', [1, 2, 3, 4, 5, 6, 10, 11])
+def test_sync_transcripts_equal_emu(emu_doc, oracle_mod, seed):
+    assert parity_checks.check_sync_transcripts_equal(emu_doc, oracle_mod, seed) > 0
+
+
+def test_get_changes_differential_emu(emu_doc, oracle_mod):
+    assert parity_checks.check_get_changes_differential(emu_doc, oracle_mod) > 0
+
+
 @pytest.mark.gpu
 def test_sync_protocol_gpu():
     import torch
@@ -47,3 +56,14 @@ def test_sync_random_gpu(seed):
         pytest.skip('no CUDA device')
     from automerge_classic_b200.engine import GpuBackendDoc
     assert parity_checks.check_sync_random(GpuBackendDoc, seed) > 0
+
+
+@pytest.mark.gpu
+def test_get_changes_and_transcripts_gpu(oracle_mod):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from automerge_classic_b200.engine import GpuBackendDoc
+    assert parity_checks.check_get_changes_differential(GpuBackendDoc, oracle_mod, queries=60) > 0
+    for seed in (5, 10):
+        assert parity_checks.check_sync_transcripts_equal(GpuBackendDoc, oracle_mod, seed) > 0
