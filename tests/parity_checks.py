@@ -656,3 +656,32 @@ def check_get_changes_differential(Doc, oracle_mod, seed=3, queries=150):
             total += 1
         assert g.get_missing_deps(have) == o.get_missing_deps(have)
     return total
+
+
+def check_graph_queries_differential(Doc, oracle_mod, seed=9, rounds=12):
+    """getChangesAdded / getMissingDeps / getChangeByHash on pairs of replicas at random points of a trace, and with a batch
+    delivered out of order (queued changes), against the oracle (new.js:1979-2028)."""
+    import random
+    from automerge_classic_b200 import tracegen, columnar
+    rnd = random.Random(seed)
+    total = 0
+    for cfg, n, a in [('C3', 400, 4), ('C6', 200, 3), ('C8', 300, 4)]:
+        ch = tracegen.generate(cfg, n, a).changes()
+        hashes = [columnar.decode_change(c)['hash'] for c in ch]
+        for _ in range(rounds):
+            c1, c2 = sorted([rnd.randrange(len(ch) + 1), rnd.randrange(len(ch) + 1)])
+            o1, o2, g1, g2 = oracle_mod.OracleDoc(), oracle_mod.OracleDoc(), Doc(), Doc()
+            for d in (o1, g1):
+                d.apply_changes(ch[:c1])
+            late = ch[c2:c2 + 4]                     # a few changes whose dependencies are (mostly) missing: they wait in the queue
+            for d in (o2, g2):
+                d.apply_changes(ch[:max(c2 - 3, 0)] + late)
+            assert [bytes(c) for c in g2.get_changes_added(g1)] == [bytes(c) for c in o2.get_changes_added(o1)]
+            q = sorted(rnd.sample(hashes, min(3, len(hashes))))
+            assert g1.get_missing_deps(q) == o1.get_missing_deps(q) and g2.get_missing_deps(q) == o2.get_missing_deps(q)
+            assert g2.get_missing_deps() == o2.get_missing_deps()
+            for h in rnd.sample(hashes, 3):
+                x, y = o2.get_change_by_hash(h), g2.get_change_by_hash(h)
+                assert (None if x is None else bytes(x)) == (None if y is None else bytes(y))
+            total += 1
+    return total

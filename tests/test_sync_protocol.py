@@ -35,6 +35,7 @@ def test_sync_transcripts_equal_emu(emu_doc, oracle_mod, seed):
 
 def test_get_changes_differential_emu(emu_doc, oracle_mod):
     assert parity_checks.check_get_changes_differential(emu_doc, oracle_mod) > 0
+    assert parity_checks.check_graph_queries_differential(emu_doc, oracle_mod) > 0
 
 
 @pytest.mark.gpu
@@ -65,5 +66,6 @@ def test_get_changes_and_transcripts_gpu(oracle_mod):
         pytest.skip('no CUDA device')
     from automerge_classic_b200.engine import GpuBackendDoc
     assert parity_checks.check_get_changes_differential(GpuBackendDoc, oracle_mod, queries=60) > 0
+    assert parity_checks.check_graph_queries_differential(GpuBackendDoc, oracle_mod, rounds=6) > 0
     for seed in (5, 10):
         assert parity_checks.check_sync_transcripts_equal(GpuBackendDoc, oracle_mod, seed) > 0
