@@ -111,12 +111,13 @@ static inline PObjP emptyObjectPatch(const std::string& objectId, const std::str
 static inline void bloomFilterAdd(uint8_t* bloom, int64_t elemIdActor, int64_t elemIdCtr) {
   const int64_t modulo = 8 * BLOOM_FILTER_SIZE; int64_t x = elemIdCtr % modulo, y = elemIdActor % modulo;
   int64_t z = (int64_t)((uint32_t)((uint64_t)(uint32_t)((int32_t)elemIdCtr ^ (int32_t)elemIdActor) * 16777619ULL)) % modulo;
-  for (int i = 0; i < BLOOM_NUM_PROBES; i++) { bloom[x >> 3] |= 1 << (x & 7); x = (x + y) % modulo; y = (y + z) % modulo; }
+  // (ids decoded from a corrupt document can be negative; a Uint8Array ignores a store at a negative index, new.js:329-345)
+  for (int i = 0; i < BLOOM_NUM_PROBES; i++) { if (x >= 0) bloom[x >> 3] |= 1 << (x & 7); x = (x + y) % modulo; y = (y + z) % modulo; }
 }
 static inline bool bloomFilterContains(const uint8_t* bloom, int64_t elemIdActor, int64_t elemIdCtr) {
   const int64_t modulo = 8 * BLOOM_FILTER_SIZE; int64_t x = elemIdCtr % modulo, y = elemIdActor % modulo;
   int64_t z = (int64_t)((uint32_t)((uint64_t)(uint32_t)((int32_t)elemIdCtr ^ (int32_t)elemIdActor) * 16777619ULL)) % modulo;
-  for (int i = 0; i < BLOOM_NUM_PROBES; i++) { if ((bloom[x >> 3] & (1 << (x & 7))) == 0) return false; x = (x + y) % modulo; y = (y + z) % modulo; }
+  for (int i = 0; i < BLOOM_NUM_PROBES; i++) { if (x < 0 || (bloom[x >> 3] & (1 << (x & 7))) == 0) return false; x = (x + y) % modulo; y = (y + z) % modulo; }   // (a load at a negative index is undefined -> 0)
   return true;
 }
 

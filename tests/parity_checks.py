@@ -685,3 +685,52 @@ def check_graph_queries_differential(Doc, oracle_mod, seed=9, rounds=12):
                 assert (None if x is None else bytes(x)) == (None if y is None else bytes(y))
             total += 1
     return total
+
+
+def check_corrupt_documents(Doc, seed=1, per_doc=60):
+    """Documents with a valid checksum but damaged contents (bytes changed, removed, inserted; checksum recomputed): the
+    engine either loads them or refuses with an error - it must not crash, hang or corrupt memory (run under ASan by
+    tests/_emu/build_asan.sh). Both column decoders are exercised."""
+    import hashlib
+    import os
+    import random
+    from automerge_classic_b200 import tracegen
+    from automerge_classic_b200.engine import AmgError
+    rnd = random.Random(seed)
+    stats = {'loaded': 0, 'refused': 0}
+    old = os.environ.get('AMG_PAR_DOC_MIN')
+    try:
+        for par in ('1', '100000'):
+            os.environ['AMG_PAR_DOC_MIN'] = par
+            for cfg, n, a in [('C6', 40, 2), ('C3', 60, 3), ('C7', 40, 2), ('C4', 300, 3), ('C8', 60, 2)]:
+                g = Doc()
+                g.apply_changes(tracegen.generate(cfg, n, a).changes())
+                doc = g.save()
+                for _ in range(per_doc):
+                    b = bytearray(doc)
+                    for _ in range(rnd.choice([1, 1, 2, 4])):
+                        p, op = rnd.randrange(10, len(b)), rnd.random()
+                        if op < 0.5:
+                            b[p] = rnd.randrange(256)
+                        elif op < 0.7:
+                            b[p] ^= 1 << rnd.randrange(8)
+                        elif op < 0.85:
+                            del b[p]
+                        else:
+                            b.insert(p, rnd.randrange(256))
+                    b[4:8] = hashlib.sha256(bytes(b[8:])).digest()[:4]
+                    try:
+                        d = Doc(bytes(b))
+                        d.get_patch()
+                        d.save()
+                        d.get_changes([])
+                        stats['loaded'] += 1
+                    except (AmgError, ValueError):
+                        stats['refused'] += 1
+    finally:
+        if old is None:
+            os.environ.pop('AMG_PAR_DOC_MIN', None)
+        else:
+            os.environ['AMG_PAR_DOC_MIN'] = old
+    assert stats['refused'] > stats['loaded']
+    return stats

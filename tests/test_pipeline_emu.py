@@ -145,3 +145,8 @@ def test_empty_batch_emu(emu_doc):
 @pytest.mark.parametrize('cfg,n,a', [('C2', 300, 0), ('C3', 600, 3), ('C3', 2000, 4), ('C4', 1500, 4), ('C6', 300, 3), ('C7', 300, 3), ('C8', 300, 3)])
 def test_history_against_oracle_emu(emu_doc, oracle_mod, cfg, n, a):
     parity_checks.check_history_against_oracle(emu_doc, oracle_mod, cfg, n, a)
+
+
+def test_corrupt_documents_emu(emu_doc):
+    stats = parity_checks.check_corrupt_documents(emu_doc)
+    assert stats['loaded'] + stats['refused'] == 600
