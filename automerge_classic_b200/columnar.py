@@ -4,7 +4,7 @@ The reference keeps `encodeChange` in host JavaScript even with a native backend
 `Backend.applyLocalChange` (backend/backend.js:54-91) encodes the frontend's change request on the
 host and then calls `applyChanges` with the binary change.  This module is that host-side encoder
 for the Python mirror of the Backend facade (automerge_classic_b200/backend.py); it is also what the
-fixture extractor (tools/jsfixtures/extract.py) uses to turn the reference tests' JSON changes into
+fixture extractor (tests/jsfixtures/extract.py) uses to turn the reference tests' JSON changes into
 bytes.  It is pinned byte-for-byte by the annotated golden change of test/columnar_test.js:8-37.
 
 Follows (paths relative to /root/reference):

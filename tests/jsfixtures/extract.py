@@ -13,7 +13,7 @@ While extracting, the steps are executed against the oracle so that values the t
 (e.g. `backend.heads` used as deps of the next change) are available; any assertion the oracle
 fails is reported at the end (non-zero exit) — that is the pinning signal during development.
 
-usage: python tools/jsfixtures/extract.py [--ref /root/reference] [--out tests/golden]
+usage: python tests/jsfixtures/extract.py [--ref /root/reference] [--out tests/golden]
 """
 import argparse
 import hashlib
@@ -642,7 +642,7 @@ def main():
         skipped = [t for t in tests if 'skipped' in t]
         out = os.path.join(args.out, f.replace('.js', '.json'))
         with open(out, 'w') as fh:
-            json.dump({'source': 'test/' + f, 'generator': 'tools/jsfixtures/extract.py', 'tests': tests}, fh, separators=(',', ':'))
+            json.dump({'source': 'test/' + f, 'generator': 'tests/jsfixtures/extract.py', 'tests': tests}, fh, separators=(',', ':'))
         print('%s: %d tests, %d skipped -> %s' % (f, len(tests), len(skipped), out))
         for t in skipped:
             print('   skipped: %s  [%s]' % (t['name'], t['skipped'][:120]))

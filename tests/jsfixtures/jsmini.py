@@ -2,7 +2,7 @@
 
 Purpose: extract golden fixtures (binary changes, expected patches, expected column bytes) from the
 reference's own tests in this container, where no JS engine exists.  It is a fixture-generation tool
-only: tools/jsfixtures/extract.py drives it, the JSON it writes lives under tests/golden/.
+only: tests/jsfixtures/extract.py drives it, the JSON it writes lives under tests/golden/.
 
 Supported: const/let/var (with array/object destructuring), functions and arrow functions, object /
 array literals (shorthand, computed keys, spread), template strings, regex literals (opaque), calls,

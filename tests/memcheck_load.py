@@ -1,4 +1,4 @@
-"""Small load / save / column-decoder workload for `compute-sanitizer --tool memcheck python tools/memcheck_load.py`
+"""Small load / save / column-decoder workload for `compute-sanitizer --tool memcheck python tests/memcheck_load.py`
 (the pytest GPU suite is too long under the sanitizer). Every document takes the parallel column decoders."""
 import os, sys
 os.environ['AMG_PAR_DOC_MIN'] = '1'

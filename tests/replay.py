@@ -1,5 +1,5 @@
 """Replays the golden fixtures extracted from the reference's mocha tests (tests/golden/*.json, made
-by tools/jsfixtures/extract.py) against a document engine.
+by tests/jsfixtures/extract.py) against a document engine.
 
 `doc_class` is any class with the BackendDoc surface (oracle.OracleDoc, or the CUDA engine's
 GpuBackendDoc).  Steps that inspect the reference's internal block structure (`blocks`,

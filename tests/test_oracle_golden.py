@@ -1,7 +1,7 @@
 """Pins the CPU oracle on the reference's own tests: every assertion of test/new_backend_test.js
 (byte-exact doc columns, block metadata, Bloom bits, patches, error messages) and of
 test/backend_test.js (patches through the Backend facade, save/load, hash-graph queries), replayed
-from the fixtures that tools/jsfixtures/extract.py wrote to tests/golden/."""
+from the fixtures that tests/jsfixtures/extract.py wrote to tests/golden/."""
 import pytest
 
 import replay
