@@ -734,3 +734,67 @@ def check_corrupt_documents(Doc, seed=1, per_doc=60):
             os.environ['AMG_PAR_DOC_MIN'] = old
     assert stats['refused'] > stats['loaded']
     return stats
+
+
+# ---------------------------------------------------------------------------------------------
+# The two places where the engine deliberately does not follow the reference's 600-op block structure
+def _list_rows(doc):
+    """(idCtr, idActorHex, keyCtr, keyActorHex or None, insert, succNum) of every list row, in document order."""
+    dumped = doc.dump_ops()
+    if len(dumped) == 3:       # oracle: objCtr,objActor,keyCtr,keyActor,idCtr,idActor,insert,...,succNum[9]
+        rows, _, actors = dumped
+        out = []
+        for r in rows.astype(np.int64):
+            if r[2] == -1 and r[3] == -1:
+                continue       # map row
+            out.append((int(r[4]), actors[int(r[5])], int(r[2]), actors[int(r[3])] if r[3] >= 0 else None, bool(r[6]), int(r[9])))
+        return out
+    rows, _ = dumped           # engine: objCtr,objActor,idCtr,idActor,keyCtr,keyActor,flags,succNum
+    actors = doc._state().actors
+    none = np.uint64(0xffffffffffffffff)
+    out = []
+    for r in rows:
+        if r[4] == none:
+            continue
+        out.append((int(r[2]), actors[int(r[3])], int(r[4]), actors[int(r[5])] if r[5] != none else None, bool(int(r[6]) & 1), int(r[7])))
+    return out
+
+
+def _rga_violations(rows):
+    """Elements of lower id standing between an element and the element it was inserted after: the skip rule of
+    new.js:143-162 never leaves such a pair (single list object assumed)."""
+    pos = {(r[0], r[1]): i for i, r in enumerate(rows) if r[4]}
+    bad = 0
+    for i, r in enumerate(rows):
+        if not r[4] or r[3] is None:
+            continue
+        p = pos.get((r[2], r[3]))
+        if p is None:
+            continue
+        for q in rows[p + 1:i]:
+            if q[4] and (q[0], q[1]) < (r[0], r[1]):
+                bad += 1
+                break
+    return bad
+
+
+def check_block_boundary_cases(Doc, oracle_mod):
+    from automerge_classic_b200 import tracegen
+    # 1. an insertion whose skip run crosses a block boundary: the reference drops it at the block start
+    ch = tracegen.generate('C3', 1200, 6, seed=4246).changes()[:1115]
+    o, g = oracle_mod.OracleDoc(), Doc()
+    o.apply_changes(ch)
+    g.apply_changes(ch)
+    assert _rga_violations(_list_rows(g)) == 0
+    assert _rga_violations(_list_rows(o)) > 0, 'the oracle no longer reproduces the reference here: update DESIGN.md section 5'
+    # 2. a counter element deleted after an increment: counted by a recount of the block, not by the incremental bookkeeping
+    ch = tracegen.generate('C8', 2500, 1, seed=314489).changes()
+    o, g = oracle_mod.OracleDoc(), Doc()
+    for lo in range(0, 218, 2):
+        o.apply_changes(ch[lo:lo + 2])
+        g.apply_changes(ch[lo:lo + 2])
+    fresh = oracle_mod.OracleDoc(o.save())               # the same document, blocks recounted by load
+    p_live, p_fresh, p_eng = o.apply_changes(ch[218:220]), fresh.apply_changes(ch[218:220]), g.apply_changes(ch[218:220])
+    assert replay.deep_equal(replay.decode(p_eng), replay.decode(p_fresh)) is None
+    assert replay.deep_equal(replay.decode(p_eng), replay.decode(p_live)) is not None
+    return True

@@ -150,3 +150,7 @@ def test_history_against_oracle_emu(emu_doc, oracle_mod, cfg, n, a):
 def test_corrupt_documents_emu(emu_doc):
     stats = parity_checks.check_corrupt_documents(emu_doc)
     assert stats['loaded'] + stats['refused'] == 600
+
+
+def test_block_boundary_cases_emu(emu_doc, oracle_mod):
+    assert parity_checks.check_block_boundary_cases(emu_doc, oracle_mod)
