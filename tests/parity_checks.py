@@ -181,6 +181,13 @@ def check_full_size_properties(gpu_doc, n_ops=1000000, n_actors=10, calls=10):
     fp = bulk.apply_packed_flat(t.blob, t.offsets, t.n_changes)
     assert fp.pending == 0 and fp.max_op > 0
     s1 = bulk.save()
+    if (n_ops, n_actors) == (1000000, 10):   # the oracle's document at this size (tests/golden/full_size_c3.json)
+        import hashlib
+        import json
+        import os
+        gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'full_size_c3.json')))
+        assert len(s1) == gold['save_bytes'] and bulk.heads() == gold['heads']
+        assert hashlib.sha256(s1).hexdigest() == gold['save_sha256'], 'save() differs from the oracle\'s at full size'
     chunked = gpu_doc()
     step = (t.n_changes + calls - 1) // calls
     for lo in range(0, t.n_changes, step):

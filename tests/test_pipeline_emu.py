@@ -154,3 +154,8 @@ def test_corrupt_documents_emu(emu_doc):
 
 def test_block_boundary_cases_emu(emu_doc, oracle_mod):
     assert parity_checks.check_block_boundary_cases(emu_doc, oracle_mod)
+
+
+def test_full_size_oracle_fingerprint_emu(emu_doc):
+    # BASELINE.json's full size on the emulation build: bulk / chunked / loaded routes agree and save() has the oracle's digest
+    parity_checks.check_full_size_properties(emu_doc)
