@@ -1,0 +1,17 @@
+"""BASELINE.json's full size against the oracle: the document the CUDA engine reaches for the 1M-op C3 trace has the save()
+digest and heads the oracle produced (tests/golden/full_size_c3.json; the oracle needs 75 s for it, so its result is
+committed, not recomputed). Runs last: the file name sorts after the other test modules."""
+import pytest
+
+import parity_checks
+
+
+@pytest.mark.gpu
+def test_full_size_oracle_fingerprint():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from automerge_classic_b200 import build
+    build.build_all()
+    from automerge_classic_b200.engine import GpuBackendDoc
+    parity_checks.check_full_size_properties(GpuBackendDoc, golden=True)
