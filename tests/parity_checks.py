@@ -805,3 +805,48 @@ def check_block_boundary_cases(Doc, oracle_mod):
     assert replay.deep_equal(replay.decode(p_eng), replay.decode(p_fresh)) is None
     assert replay.deep_equal(replay.decode(p_eng), replay.decode(p_live)) is not None
     return True
+
+
+def check_out_of_order_random(Doc, oracle_mod, seed=7, sessions=20):
+    """Delivery shuffled inside windows and cut into random calls, with copies of already applied changes mixed in: every
+    call's patch (or error), the final save() and getMissingDeps equal the oracle's (queue order, passes, duplicates:
+    new.js:1550-1597, 1822-1841). Copies of a change that is still waiting are left out - see DESIGN.md section 5."""
+    import random
+    from automerge_classic_b200 import tracegen
+    rnd = random.Random(seed)
+    for _ in range(sessions):
+        cfg = rnd.choice(['C3', 'C6', 'C8', 'C7', 'C4'])
+        a = rnd.choice([2, 3, 5])
+        n = rnd.choice([60, 150, 300]) if cfg != 'C4' else rnd.choice([400, 900])
+        ch = tracegen.generate(cfg, n, a, seed=rnd.randrange(1, 10**6)).changes()
+        order = list(range(len(ch)))
+        w = rnd.choice([3, 8, 25])
+        for lo in range(0, len(order), w):
+            seg = order[lo:lo + w]
+            rnd.shuffle(seg)
+            order[lo:lo + w] = seg
+        o, g = oracle_mod.OracleDoc(), Doc()
+        pos = 0
+        while pos < len(order):
+            k = rnd.choice([1, 2, 5, 20])
+            batch = [ch[i] for i in order[pos:pos + k]]
+            pos += k
+            applied_before = len(o.get_changes([])) if rnd.random() < 0.3 else 0
+            if applied_before:                      # a few changes that were applied long ago, again
+                old = o.get_changes([])
+                batch[rnd.randrange(len(batch) + 1):0] = [bytes(old[rnd.randrange(applied_before)])]
+            eo = eg = None
+            try:
+                po = o.apply_changes(batch)
+            except Exception as e:
+                eo = str(e)
+            try:
+                pg = g.apply_changes(batch)
+            except Exception as e:
+                eg = str(e)
+            assert (eo is None) == (eg is None), (cfg, eo, eg)
+            if eo is None:
+                d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+                assert d is None, (cfg, d)
+        assert g.save() == o.save() and g.get_missing_deps() == o.get_missing_deps()
+    return sessions

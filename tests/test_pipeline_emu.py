@@ -159,3 +159,8 @@ def test_block_boundary_cases_emu(emu_doc, oracle_mod):
 def test_full_size_oracle_fingerprint_emu(emu_doc):
     # BASELINE.json's full size on the emulation build: bulk / chunked / loaded routes agree and save() has the oracle's digest
     parity_checks.check_full_size_properties(emu_doc)
+
+
+@pytest.mark.parametrize('seed', [7, 8])
+def test_out_of_order_random_emu(emu_doc, oracle_mod, seed):
+    assert parity_checks.check_out_of_order_random(emu_doc, oracle_mod, seed, sessions=12) > 0
