@@ -850,3 +850,75 @@ def check_out_of_order_random(Doc, oracle_mod, seed=7, sessions=20):
                 assert d is None, (cfg, d)
         assert g.save() == o.save() and g.get_missing_deps() == o.get_missing_deps()
     return sessions
+
+
+# ---------------------------------------------------------------------------------------------
+# applyLocalChange / merge sessions of two replicas through the facade, engine vs oracle
+def _local_session(BE, BO, seed):
+    import random
+    rnd = random.Random(seed)
+    actors = ['%02x' % (i + 1) * 16 for i in range(2)]
+    e = [BE.init(), BE.init()]; o = [BO.init(), BO.init()]; seqs = [0, 0]
+    lists = {}    # objectId -> list of elemIds (per model, approximate: we only need valid references)
+    model = {'list': None, 'elems': [], 'keys': {}, 'counter_keys': {}}
+    known = [set(), set()]; list_known = [False, False]
+    for step in range(40):
+        i = rnd.randrange(2)
+        if rnd.random() < 0.25:       # exchange everything
+            for (src, dst) in ((0, 1), (1, 0)):
+                chs = BE.getChanges(e[src], BE.getHeads(e[dst]) if False else [])
+                pe = BE.applyChanges(e[dst], chs); po = BO.applyChanges(o[dst], BO.getChanges(o[src], []))
+                e[dst], o[dst] = pe[0], po[0]
+                d = replay.deep_equal(pe[1], po[1]); assert d is None, ('merge patch', seed, step, d)
+            known[0] |= known[1]; known[1] |= known[0]; list_known = [any(list_known)] * 2
+            continue
+        st = e[i]['state']; max_op = st.max_op(); start = max_op + 1; ops = []
+        kind = rnd.random()
+        mine = [x for x in model['elems'] if x in known[i]]
+        if model['list'] is None or not list_known[i] or kind < 0.1:
+            if model['list'] is None and not any(list_known):
+                ops.append({'action': 'makeList', 'obj': '_root', 'key': 'items', 'pred': []}); model_list_pending = '%d@%s' % (start, actors[i])
+            else:
+                k = rnd.choice('abc'); ops.append({'action': 'set', 'obj': '_root', 'key': k, 'value': rnd.randrange(100), 'datatype': 'int', 'pred': model['keys'].get((i, k), [])})
+        elif kind < 0.6:
+            ref = rnd.choice(['_head'] + mine[-6:]) if mine else '_head'
+            ops.append({'action': 'set', 'obj': model['list'], 'elemId': ref, 'insert': True, 'value': rnd.choice('xyz'), 'pred': []})
+        elif kind < 0.8 and mine:
+            el = rnd.choice(mine); ops.append({'action': 'del', 'obj': model['list'], 'elemId': el, 'insert': False, 'pred': [el]})
+        else:
+            k = 'cnt'; pred = model['counter_keys'].get(i)
+            if pred is None: ops.append({'action': 'set', 'obj': '_root', 'key': k, 'value': 1, 'datatype': 'counter', 'pred': []})
+            else: ops.append({'action': 'inc', 'obj': '_root', 'key': k, 'value': rnd.randrange(1, 5), 'pred': [pred]})
+        seqs[i] += 1
+        ch = {'actor': actors[i], 'seq': seqs[i], 'startOp': start, 'time': 0, 'message': '', 'deps': list(BE.getHeads(e[i])), 'ops': ops}
+        try:
+            re_ = BE.applyLocalChange(e[i], dict(ch)); ee = None
+        except Exception as ex: ee = str(ex)[:80]
+        try:
+            ro_ = BO.applyLocalChange(o[i], dict(ch)); eo = None
+        except Exception as ex: eo = str(ex)[:80]
+        assert (ee is None) == (eo is None), ('error mismatch', seed, step, ee, eo, ops)
+        if ee is not None:
+            seqs[i] -= 1; continue
+        e[i], o[i] = re_[0], ro_[0]
+        d = replay.deep_equal(re_[1], ro_[1]); assert d is None, ('local patch', seed, step, d, ops)
+        assert bytes(re_[2]) == bytes(ro_[2]), ('binary change', seed, step)
+        op = ops[0]
+        if op['action'] == 'makeList': model['list'] = '%d@%s' % (start, actors[i]); list_known[i] = True
+        elif op.get('insert'): model['elems'].append('%d@%s' % (start, actors[i])); known[i].add('%d@%s' % (start, actors[i]))
+        elif op['action'] == 'set' and op.get('datatype') == 'counter': model['counter_keys'][i] = '%d@%s' % (start, actors[i])
+        elif op['action'] == 'set' and 'key' in op: model['keys'][(i, op['key'])] = ['%d@%s' % (start, actors[i])]
+    for i in range(2):
+        assert BE.save(e[i]) == BO.save(o[i]), ('save', seed, i)
+        d = replay.deep_equal(BE.getPatch(e[i]), BO.getPatch(o[i])); assert d is None, ('getPatch', seed, d)
+
+
+def check_local_changes_random(Doc, oracle_mod, seeds):
+    """Random sessions of two replicas making local changes (map keys, list insertions and deletions, counters) and merging:
+    every local patch, binary change and merge patch, the final save() and getPatch equal the oracle-backed facade's
+    (backend.js:54-91)."""
+    from automerge_classic_b200.backend import Backend as Facade
+    BE, BO = Facade(Doc), Facade(oracle_mod.OracleDoc)
+    for seed in seeds:
+        _local_session(BE, BO, seed)
+    return len(list(seeds))

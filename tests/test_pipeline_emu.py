@@ -164,3 +164,7 @@ def test_full_size_oracle_fingerprint_emu(emu_doc):
 @pytest.mark.parametrize('seed', [7, 8])
 def test_out_of_order_random_emu(emu_doc, oracle_mod, seed):
     assert parity_checks.check_out_of_order_random(emu_doc, oracle_mod, seed, sessions=12) > 0
+
+
+def test_local_changes_random_emu(emu_doc, oracle_mod):
+    assert parity_checks.check_local_changes_random(emu_doc, oracle_mod, range(25)) == 25
