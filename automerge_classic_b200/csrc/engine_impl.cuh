@@ -327,7 +327,22 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     changeActor.ensure(ctx, B); actorCnt.ensure(ctx, A + 1); actorBaseD.ensure(ctx, A + 1); seqSlot.ensure(ctx, numNew + 1);
     dev_memset(ctx, actorCnt.p, 0, (A + 1) * 4);
     foreach(ctx, B, ChangeActorKernel{amapBase.p, amap.p, applied.p, changeActor.p, actorCnt.p});
-    checkErr(actorsNow);
+    {
+      const u64 ew = fetchErr();
+      if ((ew & 0xff) == KE_UNKNOWN_ACTOR) {   // name the actor like the reference does (new.js:1446): re-read that change's actor table
+        const size_t b = (size_t)(ew >> 8); ChangeMeta m0; d2h(ctx, &m0, meta.p + b, sizeof(ChangeMeta)); sync(ctx);
+        std::vector<u8> bytes(m0.len); d2h(ctx, bytes.data(), arena.p + m0.off, m0.len); sync(ctx);
+        ByteReader r(bytes.data(), m0.otherOff - m0.off, m0.len); std::string culprit;
+        for (u32 k = 0; k <= m0.nOther && !r.err; k++) {
+          u32 off, len; if (k == 0) { off = m0.actorOff - m0.off; len = m0.actorLen; } else { len = (u32)r.uleb(); off = r.pos; r.skip(len); }
+          if (r.err) break;
+          const std::string id((const char*)bytes.data() + off, len);
+          if (std::find(actorsNow.begin(), actorsNow.end(), id) == actorsNow.end()) { culprit = id; break; }
+        }
+        if (!culprit.empty()) throw Error(AMG_ERR_RANGE, "actorId " + hex_of((const u8*)culprit.data(), culprit.size()) + " is not known to document");
+      }
+      if (ew) throwKernelError(ew, actorsNow);
+    }
     scan_exclusive(ctx, scanTmp, actorCnt.p, actorBaseD.p, A);
     DBuf<u64>& clockDev = pairKey;   // scratch reuse before the succ phase
     clockDev.ensure(ctx, A + 1); h2d(ctx, clockDev.p, clockNow.data(), A * 8);
