@@ -222,6 +222,7 @@ class Engine {
   void checkErr(const std::vector<std::string>& actorsNow) { u64 w = fetchErr(); if (w) throwKernelError(w, actorsNow); }
 
   // ---------------------------------------------------------------- helpers
+  DBuf<u64> gateBest;   // causal gate with several copies of a waiting change: best (pass, position) per hash
   bool domLocalReady = false;   // k_dom_local's dynamic shared memory size has been raised on this device
   std::vector<HostChange> batchStore;   // applyChanges: (offset, length) of the batch entries
   HBuf<u32> pinnedScratch; HBuf<u64> hostWord;   // pinned landing slots for the small device -> host reads that size the next stage

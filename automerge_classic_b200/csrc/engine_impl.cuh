@@ -231,13 +231,34 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   foreach(ctx, G, HashInsertKernel{hashes.p, hashTable.p, (u64)tcap - 1});
   foreach(ctx, B, ResolveDepsKernel{arena.p, hashes.p, hashTable.p, (u64)tcap - 1, meta.p, numApplied, depBase.p, depIdx.p, primary.p});
   fill32(pass.p, 1, B);
+  dev_memset(ctx, flagWord.p + 12, 0, 4);
+  foreach(ctx, B, GateDupFlagKernel{primary.p, numApplied, flagWord.p + 12});
+  bool copiesChecked = false, haveCopies = false;
   for (size_t iter = 0; iter <= B + 1; iter += 2) {   // two sweeps per host round trip: the common batch settles in the first
+    if (haveCopies) break;
     foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, meta.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
     dev_memset(ctx, flagWord.p, 0, 4);
     foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, meta.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
-    const u32 again = readU32(flagWord.p);
+    u32 again = 0, copies = 0; readU32x2(flagWord.p, flagWord.p + 12, &again, &copies);
     checkErr(actorIds);   // free: the error word came with the read
+    if (!copiesChecked) { copiesChecked = true; haveCopies = copies != 0; }
     if (!again) break;
+  }
+  if (haveCopies) {   // rare: a change that is waiting was delivered again (gate.cuh, GateBestKernel ...)
+    gateBest.ensure(ctx, B + 1); fill32(pass.p, 1, B);
+    for (size_t iter = 0; iter <= B + 1; iter++) {
+      dev_memset(ctx, gateBest.p, 0xff, B * 8); dev_memset(ctx, flagWord.p, 0, 4);
+      foreach(ctx, B, GateBestKernel{primary.p, pass.p, numApplied, gateBest.p});
+      foreach(ctx, B, RelaxCopiesKernel{depBase.p, depIdx.p, meta.p, primary.p, numApplied, gateBest.p, pass.p, flagWord.p, (u32)B + 1});
+      const u32 again = readU32(flagWord.p);
+      checkErr(actorIds);
+      if (!again) break;
+    }
+    dev_memset(ctx, gateBest.p, 0xff, B * 8);
+    foreach(ctx, B, GateBestKernel{primary.p, pass.p, numApplied, gateBest.p});
+    const size_t depTotal = readU32(depBase.p + B);
+    if (depTotal) foreach(ctx, depTotal, GateDepWinnerKernel{gateBest.p, numApplied, depIdx.p});
+    foreach(ctx, B, GateWinnerKernel{gateBest.p, numApplied, primary.p});
   }
   applied.ensure(ctx, B); appRank.ensure(ctx, B + 1); isRow.ensure(ctx, B + 1);
   dev_memset(ctx, flagWord.p, 0, 8);

@@ -89,6 +89,43 @@ struct RelaxKernel {
   }
 };
 
+// ---- the same change more than once among the entries that are not applied yet (a copy in the batch, another in the queue):
+// the reference walks the queue in order pass after pass and applies whichever copy is ready first; the others are then
+// duplicates (new.js:1556-1557). Every copy therefore takes part: best[group] = min over the copies of (pass, position),
+// a dependency is satisfied by the best copy of its hash. Only run when such copies exist (flag from GateDupFlagKernel).
+struct GateDupFlagKernel { const u32* primary; size_t numApplied; u32* flag; HD void operator()(size_t b) const { if (primary[b] >= numApplied && primary[b] != (u32)(numApplied + b)) *flag = 1; } };
+struct GateBestKernel {
+  const u32* primary; const u32* pass; size_t numApplied; u64* best;
+  HD void operator()(size_t b) const { if (primary[b] < numApplied) return; atomic_min(&best[primary[b] - numApplied], ((u64)pass[b] << 32) | (u64)b); }
+};
+struct RelaxCopiesKernel {
+  const u32* depBase; const u32* depIdx; const ChangeMeta* meta; const u32* primary; size_t numApplied; const u64* best; u32* pass; u32* changed; u32 maxPass;
+  HD void operator()(size_t b) const {
+    if (primary[b] < numApplied) return;   // a copy of an applied change
+    u32 p = 1; const u32 n = meta[b].nDeps, base = depBase[b];
+    for (u32 j = 0; j < n; j++) {
+      const u32 d = depIdx[base + j];
+      if (d == DEP_MISSING) { p = PASS_INF; break; }
+      if (d < numApplied) continue;
+      const u64 bd = best[d - (u32)numApplied]; const u32 pd = (u32)(bd >> 32), posd = (u32)bd;
+      if (pd >= PASS_INF) { p = PASS_INF; break; }
+      const u32 need = posd < b ? pd : pd + 1;
+      if (need > p) p = need;
+    }
+    if (p > maxPass) p = PASS_INF;
+    if (p != pass[b]) { pass[b] = p; *changed = 1; }
+  }
+};
+// the best copy of every hash becomes its primary; dependencies point at it
+struct GateWinnerKernel {
+  const u64* best; size_t numApplied; u32* primary;
+  HD void operator()(size_t b) const { if (primary[b] < numApplied) return; primary[b] = (u32)numApplied + (u32)best[primary[b] - numApplied]; }
+};
+struct GateDepWinnerKernel {
+  const u64* best; size_t numApplied; u32* depIdx;
+  HD void operator()(size_t j) const { const u32 d = depIdx[j]; if (d == DEP_MISSING || d < numApplied) return; depIdx[j] = (u32)numApplied + (u32)best[d - (u32)numApplied]; }
+};
+
 // ---------------------------------------------------------------- actor interning
 // Byte-string table: slot = {hash64 of the bytes, min(firstSeen<<32 | change)}; identity is the 64-bit
 // FNV-1a hash, verified byte-for-byte against the slot's representative in ActorVerify.
