@@ -807,10 +807,11 @@ def check_block_boundary_cases(Doc, oracle_mod):
     return True
 
 
-def check_out_of_order_random(Doc, oracle_mod, seed=7, sessions=20):
+def check_out_of_order_random(Doc, oracle_mod, seed=7, sessions=20, waiting_copies=False):
     """Delivery shuffled inside windows and cut into random calls, with copies of already applied changes mixed in: every
     call's patch (or error), the final save() and getMissingDeps equal the oracle's (queue order, passes, duplicates:
-    new.js:1550-1597, 1822-1841). Copies of a change that is still waiting are left out - see DESIGN.md section 5."""
+    new.js:1550-1597, 1822-1841). With waiting_copies a change may also be delivered again while it is still in the queue
+    (the copy that becomes ready first is the one the reference applies)."""
     import random
     from automerge_classic_b200 import tracegen
     rnd = random.Random(seed)
@@ -825,6 +826,13 @@ def check_out_of_order_random(Doc, oracle_mod, seed=7, sessions=20):
             seg = order[lo:lo + w]
             rnd.shuffle(seg)
             order[lo:lo + w] = seg
+        if waiting_copies:
+            again = []
+            for at, i in enumerate(order):
+                again.append(i)
+                if rnd.random() < 0.1:
+                    again.append(rnd.choice(order[:max(1, at)]))
+            order = again
         o, g = oracle_mod.OracleDoc(), Doc()
         pos = 0
         while pos < len(order):
