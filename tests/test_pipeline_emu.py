@@ -172,5 +172,5 @@ def test_local_changes_random_emu(emu_doc, oracle_mod):
 
 @pytest.mark.parametrize('seed', [31, 32, 33, 34, 36])
 def test_out_of_order_waiting_copies_emu(emu_doc, oracle_mod, seed):
-    # (seed 35 runs into the duplicated-successor case of DESIGN.md section 5)
+    # (seed 35 runs into the duplicated-successor quirk of the reference)
     assert parity_checks.check_out_of_order_random(emu_doc, oracle_mod, seed, sessions=15, waiting_copies=True) > 0
