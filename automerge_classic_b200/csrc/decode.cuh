@@ -66,21 +66,28 @@ struct ChangeMeta {
 };
 
 // ---------------------------------------------------------------- byte-level readers
-struct ByteReader {
-  const u8* base; u32 pos, end; u32 err;
-  HD ByteReader(const u8* b, u32 p, u32 e) : base(b), pos(p), end(e), err(0) {}
+// Where the bytes come from: a plain pointer (global memory, host memory in the emulation build) or a CTA's shared-memory
+// copy of its byte range (decode tile kernel). `pos` is always an absolute arena offset.
+struct PtrSrc { const u8* base; HD u32 ld(u32 pos) const { return base[pos]; } };
+#ifndef AMG_EMU
+struct SmemSrc { const u8* s; u32 shift; DEV u32 ld(u32 pos) const { return s[pos - shift]; } };   // s[0] holds arena byte `shift`
+#endif
+
+template <class S> struct ByteReaderT {
+  S src; u32 pos, end; u32 err;
+  HD ByteReaderT(S s, u32 p, u32 e) : src(s), pos(p), end(e), err(0) {}
   HD bool done() const { return pos >= end; }
   // encoding.js:416-441 readUint64 + :389-395 53-bit range check
   HD u64 uleb() {
     if (pos + 1 < end) {   // one- and two-byte values (nearly all of them) without the 64-bit loop
-      const u32 b0 = base[pos];
+      const u32 b0 = src.ld(pos);
       if (!(b0 & 0x80)) { pos++; return b0; }
-      const u32 b1 = base[pos + 1];
+      const u32 b1 = src.ld(pos + 1);
       if (!(b1 & 0x80)) { pos += 2; return (b0 & 0x7f) | (b1 << 7); }
     }
     u64 result = 0; int shift = 0;
     while (pos < end) {
-      u8 b = base[pos];
+      const u32 b = src.ld(pos);
       if (shift == 63 && (b & 0xfe)) { err = KE_NUM_RANGE; return 0; }
       result |= (u64)(b & 0x7f) << shift; shift += 7; pos++;
       if (!(b & 0x80)) { if (result > ((1ULL << 53) - 1)) err = KE_NUM_RANGE; return result; }
@@ -90,14 +97,14 @@ struct ByteReader {
   // encoding.js:450-488 readInt64 + :402-408
   HD long long sleb() {
     if (pos + 1 < end) {
-      const u32 b0 = base[pos];
+      const u32 b0 = src.ld(pos);
       if (!(b0 & 0x80)) { pos++; return (long long)((int)(b0 << 25) >> 25); }
-      const u32 b1 = base[pos + 1];
+      const u32 b1 = src.ld(pos + 1);
       if (!(b1 & 0x80)) { pos += 2; return (long long)((int)(((b0 & 0x7f) | (b1 << 7)) << 18) >> 18); }
     }
     u64 result = 0; int shift = 0;
     while (pos < end) {
-      u8 b = base[pos];
+      const u32 b = src.ld(pos);
       if (shift == 63 && b != 0 && b != 0x7f) { err = KE_NUM_RANGE; return 0; }
       result |= (u64)(b & 0x7f) << shift; shift += 7; pos++;
       if (!(b & 0x80)) {
@@ -111,17 +118,21 @@ struct ByteReader {
   }
   HD void skip(u64 n) { if ((u64)pos + n > end) { err = KE_TRUNCATED; pos = end; } else pos += (u32)n; }
 };
+struct ByteReader : ByteReaderT<PtrSrc> {
+  const u8* base;
+  HD ByteReader(const u8* b, u32 p, u32 e) : ByteReaderT<PtrSrc>(PtrSrc{b}, p, e), base(b) {}
+};
 
 // RLE record walker (encoding.js:789-920) over numeric (uint / int) or utf8 columns. One value at a time.
-struct RleReader {
-  ByteReader r; int type;   // 0 uint, 1 int, 2 utf8
+template <class S> struct RleReaderT {
+  ByteReaderT<S> r; int type;   // 0 uint, 1 int, 2 utf8
   long long count; int state;   // 0 none, 1 repetition, 2 literal, 3 nulls
   long long lastNum; u32 lastOff, lastLen; bool haveLast; bool lastNull;
-  HD RleReader(const u8* b, u32 p, u32 e, int t) : r(b, p, e), type(t), count(0), state(0), lastNum(0), lastOff(0), lastLen(0), haveLast(false), lastNull(false) {}
+  HD RleReaderT(S s, u32 p, u32 e, int t) : r(s, p, e), type(t), count(0), state(0), lastNum(0), lastOff(0), lastLen(0), haveLast(false), lastNull(false) {}
   HD bool done() const { return count == 0 && r.done(); }
   HD bool strEq(u32 offA, u32 lenA, u32 offB, u32 lenB) const {
     if (lenA != lenB) return false;
-    for (u32 i = 0; i < lenA; i++) if (r.base[offA + i] != r.base[offB + i]) return false;
+    for (u32 i = 0; i < lenA; i++) if (r.src.ld(offA + i) != r.src.ld(offB + i)) return false;
     return true;
   }
   HD void readRaw(long long& num, u32& off, u32& len) {
@@ -163,6 +174,7 @@ struct RleReader {
     num = lastNum; off = lastOff; len = lastLen; return true;
   }
 };
+struct RleReader : RleReaderT<PtrSrc> { HD RleReader(const u8* b, u32 p, u32 e, int t) : RleReaderT<PtrSrc>(PtrSrc{b}, p, e, t) {} };
 
 // ---------------------------------------------------------------- SHA-256 (FIPS 180-4), one thread per change
 struct ShaConsts { u32 k[64]; };
@@ -275,8 +287,8 @@ struct ShaKernel {
 };
 
 // number of values in an RLE column (record-level: runs are not expanded); *err receives a KErr
-HD u32 rle_count_values(const u8* arena, u32 off, u32 end, u32* err) {
-  RleReader a(arena, off, end, 0); u64 n = 0;
+template <class S> HD u32 rle_count_values_t(const S& src, u32 off, u32 end, u32* err) {
+  RleReaderT<S> a(src, off, end, 0); u64 n = 0;
   while (!a.done() && !a.r.err) {
     long long v; u32 o, l; a.next(v, o, l);
     u64 adv = 1;
@@ -287,8 +299,8 @@ HD u32 rle_count_values(const u8* arena, u32 off, u32 end, u32* err) {
   return (u32)n;
 }
 // sum of the first `limit` values of an RLE uint column (nulls count as 0)
-HD u64 rle_sum_values(const u8* arena, u32 off, u32 end, u32 limit, u32* err) {
-  RleReader pn(arena, off, end, 0); u32 seen = 0; u64 sum = 0;
+template <class S> HD u64 rle_sum_values_t(const S& src, u32 off, u32 end, u32 limit, u32* err) {
+  RleReaderT<S> pn(src, off, end, 0); u32 seen = 0; u64 sum = 0;
   while (!pn.done() && !pn.r.err && seen < limit) {
     long long n = 0; u32 o, l; const bool nn = pn.next(n, o, l);
     u64 adv = 1;
@@ -298,6 +310,8 @@ HD u64 rle_sum_values(const u8* arena, u32 off, u32 end, u32 limit, u32* err) {
   }
   *err = pn.r.err; return sum;
 }
+HD u32 rle_count_values(const u8* arena, u32 off, u32 end, u32* err) { return rle_count_values_t(PtrSrc{arena}, off, end, err); }
+HD u64 rle_sum_values(const u8* arena, u32 off, u32 end, u32 limit, u32* err) { return rle_sum_values_t(PtrSrc{arena}, off, end, limit, err); }
 
 // ---------------------------------------------------------------- header / column directory parse, one thread per change
 struct ParseKernel {
@@ -373,13 +387,13 @@ struct RawRows {   // SoA, one entry per op of the batch (raw change-local value
 };
 
 // Expands one column of one change into the raw rows. Returns a KErr code (0 = ok).
-HD u32 decode_one_column(const u8* arena, int col, u32 nOps, u32 base, u32 cOff, u32 cEnd, u32 valRawOff, u32 valRawLen, u32 predBase, u32 nPreds, const RawRows& rows) {
+template <class S> HD u32 decode_one_column_t(const S& arena, int col, u32 nOps, u32 base, u32 cOff, u32 cEnd, u32 valRawOff, u32 valRawLen, u32 predBase, u32 nPreds, const RawRows& rows) {
   u32 kerr = 0;
   switch (col) {
     case CX_OBJ_ACTOR: case CX_OBJ_CTR: case CX_KEY_ACTOR: case CX_ACTION: case CX_VAL_LEN: case CX_PRED_NUM: {
       u32* out = col == CX_OBJ_ACTOR ? rows.objActor : col == CX_OBJ_CTR ? rows.objCtr : col == CX_KEY_ACTOR ? rows.keyActor
                : col == CX_ACTION ? rows.action : col == CX_VAL_LEN ? rows.valLen : rows.predNum;
-      RleReader r(arena, cOff, cEnd, 0);
+      RleReaderT<S> r(arena, cOff, cEnd, 0);
       u32 running = 0;   // VAL_LEN: byte offset into valRaw; PRED_NUM: pred offset
       const u32 rawBase = col == CX_VAL_LEN ? valRawOff : (col == CX_PRED_NUM ? predBase : 0);
       for (u32 i = 0; i < nOps; i++) {
@@ -394,7 +408,7 @@ HD u32 decode_one_column(const u8* arena, int col, u32 nOps, u32 base, u32 cOff,
       break;
     }
     case CX_KEY_CTR: {
-      RleReader r(arena, cOff, cEnd, 1); long long acc = 0;
+      RleReaderT<S> r(arena, cOff, cEnd, 1); long long acc = 0;
       for (u32 i = 0; i < nOps; i++) {
         long long n = 0; u32 o, l; const bool nn = r.next(n, o, l);
         if (nn) { acc += n; if (acc < 0 || acc > 0xfffffffeLL) kerr = KE_TOO_LARGE; }
@@ -404,7 +418,7 @@ HD u32 decode_one_column(const u8* arena, int col, u32 nOps, u32 base, u32 cOff,
       break;
     }
     case CX_KEY_STR: {
-      RleReader r(arena, cOff, cEnd, 2);
+      RleReaderT<S> r(arena, cOff, cEnd, 2);
       for (u32 i = 0; i < nOps; i++) {
         long long n; u32 o = 0, l = 0; const bool nn = r.next(n, o, l);
         rows.keyStrOff[base + i] = nn ? o : 0; rows.keyStrLen[base + i] = nn ? l : NULL32;
@@ -413,7 +427,7 @@ HD u32 decode_one_column(const u8* arena, int col, u32 nOps, u32 base, u32 cOff,
       break;
     }
     case CX_INSERT: {   // BooleanDecoder encoding.js:1141-1207
-      ByteReader r(arena, cOff, cEnd); bool val = true, first = true; u64 count = 0;
+      ByteReaderT<S> r(arena, cOff, cEnd); bool val = true, first = true; u64 count = 0;
       for (u32 i = 0; i < nOps; i++) {
         bool v = false;
         if (!(count == 0 && r.done())) {
@@ -432,7 +446,7 @@ HD u32 decode_one_column(const u8* arena, int col, u32 nOps, u32 base, u32 cOff,
       break;
     }
     case CX_PRED_ACTOR: case CX_PRED_CTR: {
-      RleReader r(arena, cOff, cEnd, col == CX_PRED_CTR ? 1 : 0); long long acc = 0;
+      RleReaderT<S> r(arena, cOff, cEnd, col == CX_PRED_CTR ? 1 : 0); long long acc = 0;
       for (u32 j = 0; j < nPreds; j++) {
         long long n = 0; u32 o, l; const bool nn = r.next(n, o, l);
         if (col == CX_PRED_CTR) { if (nn) { acc += n; if (acc < 0 || acc > 0xfffffffeLL) kerr = KE_TOO_LARGE; } rows.predCtr[predBase + j] = nn ? (u32)acc : NULL32; }
@@ -444,6 +458,9 @@ HD u32 decode_one_column(const u8* arena, int col, u32 nOps, u32 base, u32 cOff,
     default: break;   // VAL_RAW is referenced in place; chld* columns are not needed by the op set
   }
   return kerr;
+}
+HD u32 decode_one_column(const u8* arena, int col, u32 nOps, u32 base, u32 cOff, u32 cEnd, u32 valRawOff, u32 valRawLen, u32 predBase, u32 nPreds, const RawRows& rows) {
+  return decode_one_column_t(PtrSrc{arena}, col, nOps, base, cOff, cEnd, valRawOff, valRawLen, predBase, nPreds, rows);
 }
 // default (column absent) values of the rows of one change
 HD void fill_absent_column(int col, u32 nOps, u32 base, u32 predBase, u32 nPreds, const RawRows& rows) {
@@ -462,98 +479,318 @@ HD void fill_absent_column(int col, u32 nOps, u32 base, u32 predBase, u32 nPreds
   if (col == CX_VAL_LEN) for (u32 i = 0; i < nOps; i++) rows.valOff[base + i] = 0;
 }
 
-// Small changes (<= SMALL_CHANGE_OPS ops): one thread per change walks the column directory and expands every
-// column of its few ops; consecutive threads write consecutive rows (coalesced). No directory round trip through HBM.
-struct DecodeSmallKernel {
-  const u8* arena; const ChangeMeta* meta; const u32* opBase; const u32* predBase; const u8* applied; RawRows rows; u64* errWord;
-  // A column that holds exactly one value is either the literal record [-1, v] or the null run [0, 1]. Handles those two
-  // byte patterns directly (v in one or two LEB bytes); anything else returns false and takes the general decoder,
-  // which also reports the malformed cases.
-  HD bool decode_single(const u8* arena, int ix, u32 pos, u32 l, u32 base, u32 rawOff, u32 rawLen, u32 pb, u32 nPreds) const {
-    const u8* p = arena + pos;
-    if (ix == CX_INSERT) {
-      if (l == 1 && p[0] == 1) { rows.insert[base] = 0; return true; }
-      if (l == 2 && p[0] == 0 && p[1] == 1) { rows.insert[base] = 1; return true; }
-      return false;
-    }
-    if (ix == CX_PRED_ACTOR || ix == CX_PRED_CTR) { if (nPreds != 1) return false; }
-    bool isNull = false; u32 v = 0, used = 0;
-    if (l == 2 && p[0] == 0 && p[1] == 1) { isNull = true; used = 2; }
-    else if (l >= 2 && p[0] == 0x7f) {
-      if (ix == CX_KEY_STR) { if (p[1] >= 0x80) return false; v = p[1]; used = 2 + v; }
-      else if (p[1] < 0x80) { v = p[1]; used = 2; }
-      else if (l >= 3 && p[2] < 0x80) { v = (p[1] & 0x7fu) | ((u32)p[2] << 7); used = 3; }
-      else return false;
-    } else return false;
-    if (used != l) return false;
-    const bool isDelta = ix == CX_KEY_CTR || ix == CX_PRED_CTR;
-    if (isDelta && !isNull) { const int sv = used == 2 ? ((int)(v << 25) >> 25) : ((int)(v << 18) >> 18); if (sv < 0) return false; v = (u32)sv; }
-    switch (ix) {
-      case CX_OBJ_ACTOR: rows.objActor[base] = isNull ? NULL32 : v; break;
-      case CX_OBJ_CTR: rows.objCtr[base] = isNull ? NULL32 : v; break;
-      case CX_KEY_ACTOR: rows.keyActor[base] = isNull ? NULL32 : v; break;
-      case CX_KEY_CTR: rows.keyCtr[base] = isNull ? NULL32 : v; break;
-      case CX_ACTION: rows.action[base] = isNull ? NULL32 : v; break;
-      case CX_KEY_STR: rows.keyStrOff[base] = isNull ? 0 : pos + 2; rows.keyStrLen[base] = isNull ? NULL32 : v; break;
-      case CX_VAL_LEN: { const u32 bytes = isNull ? 0 : (v >> 4); if (bytes > rawLen) return false; rows.valLen[base] = isNull ? NULL32 : v; rows.valOff[base] = rawOff; } break;
-      case CX_PRED_NUM: rows.predNum[base] = isNull ? 0 : v; rows.predOff[base] = pb; break;
-      case CX_PRED_ACTOR: rows.predActor[pb] = isNull ? NULL32 : v; break;
-      case CX_PRED_CTR: rows.predCtr[pb] = isNull ? NULL32 : v; break;
-      default: return false;
-    }
-    return true;
+// ---------------------------------------------------------------- fused decode: header parse + column expansion in one pass
+// What the rest of the apply pipeline needs of a change header: 48 bytes, written with three 128-bit stores (the counts
+// that feed prefix sums - ops, preds, deps, actors - are separate u32 arrays). time / message / extra bytes are only
+// needed by save(), which parses the headers again (ParseKernel above).
+struct alignas(16) ChangeHot {
+  u32 off, len, depsOff, actorOff;         // absolute arena offsets
+  u32 actorLen, otherOff, dirOff, dataOff; // otherOff: first other-actor entry; dirOff / dataOff: column directory / first column's bytes
+  u64 startOp, seq;
+};
+
+// One column that holds exactly one value: either the literal record [-1, v] or the null run [0, 1] (boolean: one run).
+// Returns false for anything else (the general decoder then handles - and validates - the column).
+struct SingleVals {   // the row of a single-op change, in registers until its row index is known
+  u32 objActor, objCtr, keyActor, keyCtr, keyStrOff, keyStrLen, insert, action, valLen, valOff, predNum, predActor, predCtr;
+};
+template <class S> HD bool single_value(const S& src, int ix, u32 pos, u32 l, u32& v, bool& isNull, u32& used) {
+  const u32 p0 = l > 0 ? src.ld(pos) : 0xffu, p1 = l > 1 ? src.ld(pos + 1) : 0xffu;
+  if (ix == CX_INSERT) {
+    if (l == 1 && p0 == 1) { v = 0; isNull = false; used = 1; return true; }
+    if (l == 2 && p0 == 0 && p1 == 1) { v = 1; isNull = false; used = 2; return true; }
+    return false;
   }
-  HD void operator()(size_t c) const { (*this)(c, this->arena); }
-  HD void operator()(size_t c, const u8* arena) const {
-    if (!applied[c]) return;
-    const u32 nOps = meta[c].nOps; if (nOps == 0 || nOps > SMALL_CHANGE_OPS) return;
-    decodeAt(c, arena, opBase[c], predBase[c], errWord);
+  isNull = false; v = 0; used = 0;
+  if (l == 2 && p0 == 0 && p1 == 1) { isNull = true; used = 2; }
+  else if (l >= 2 && p0 == 0x7f) {
+    if (ix == CX_KEY_STR) { if (p1 >= 0x80) return false; v = p1; used = 2 + v; }
+    else if (p1 < 0x80) { v = p1; used = 2; }
+    else if (l >= 3) { const u32 p2 = src.ld(pos + 2); if (p2 >= 0x80) return false; v = (p1 & 0x7fu) | (p2 << 7); used = 3; }
+    else return false;
+  } else return false;
+  if (used != l) return false;
+  if ((ix == CX_KEY_CTR || ix == CX_PRED_CTR) && !isNull) { const int sv = used == 2 ? ((int)(v << 25) >> 25) : ((int)(v << 18) >> 18); if (sv < 0) return false; v = (u32)sv; }
+  return true;
+}
+
+// Result of the first walk over a change: header fields, counts, and - when every column holds exactly one value - the row.
+struct ParsedChange {
+  ChangeHot h; u32 nDeps, nOther, nOps, nPreds; u32 err;   // err: KErr of the header / directory / count (raised for every change of a batch)
+  bool single; SingleVals sv;
+};
+// columnar.js:688-708 (container), :635-652 decodeChangeHeader, :609-624 decodeColumnInfo; op count = values of the action
+// column, pred count = sum of the predNum column (new.js:686-700 reads ops until the action column is exhausted)
+template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedChange& o) {
+  o.h.off = off; o.h.len = len; o.h.depsOff = o.h.actorOff = o.h.actorLen = o.h.otherOff = o.h.dirOff = o.h.dataOff = 0; o.h.startOp = 0; o.h.seq = 0;
+  o.nDeps = 0; o.nOther = 0; o.nOps = 0; o.nPreds = 0; o.err = 0; o.single = false;
+  ByteReaderT<S> r(src, off + 8, off + len);
+  const u32 chunkType = r.done() ? 0xffu : src.ld(r.pos); r.pos++;
+  const u64 chunkLen = r.uleb();
+  if (r.err) { o.err = r.err; return; }
+  if ((u64)r.pos + chunkLen > (u64)off + len) { o.err = KE_TRUNCATED; return; }
+  if ((u64)r.pos + chunkLen != (u64)off + len) { o.err = KE_TRAILING; return; }
+  if (chunkType != 1) { o.err = KE_CHUNK_TYPE; return; }
+  const u64 nDeps = r.uleb(); const u32 depsOff = r.pos; r.skip(nDeps * 32);
+  const u64 actorLen = r.uleb(); const u32 actorOff = r.pos; r.skip(actorLen);
+  const u64 seq = r.uleb(), startOp = r.uleb(); (void)r.sleb();
+  const u64 msgLen = r.uleb(); r.skip(msgLen);
+  const u64 nOther = r.uleb(); const u32 otherOff = r.pos;
+  for (u64 i = 0; i < nOther && !r.err; i++) { const u64 l = r.uleb(); r.skip(l); }
+  const u64 nCols = r.uleb();
+  if (r.err) { o.err = r.err; return; }
+  // column directory: ids ascending (ignoring the deflate bit, which a change must not carry); single-value columns are
+  // decoded on the way (their data position is the running sum of the lengths seen so far + the directory's end, which
+  // is not known yet: positions are kept relative to the data start and the bytes are read in a second, short loop)
+  const u32 dirPos = r.pos; long long lastId = -1; u64 total = 0;
+  u32 actOff = 0, actLen = 0, pnOff = 0, pnLen = 0; bool haveAct = false;
+  for (u64 i = 0; i < nCols && !r.err; i++) {
+    const u64 id = r.uleb(), l = r.uleb();
+    if (lastId >= 0 && ((u32)id & ~8u) <= ((u32)lastId & ~8u)) { o.err = KE_COL_ORDER; return; }
+    if (id & 8) { o.err = KE_COL_DEFLATE; return; }
+    if (id == 0x42) { actOff = (u32)total; actLen = (u32)l; haveAct = true; } else if (id == 0x70) { pnOff = (u32)total; pnLen = (u32)l; }
+    lastId = (long long)id; total += l;
   }
-  // expands the columns of change c into rows [base, base + nOps) and preds [pb, pb + nPreds)
-  HD void decodeAt(size_t c, const u8* arena, u32 base, u32 pb, u64* errWord) const {
-    const u32 nOps = meta[c].nOps, nPreds = meta[c].nPreds;
-    ByteReader d(arena, meta[c].dirOff, meta[c].dataOff); u32 pos = meta[c].dataOff; u32 seen = 0, kerr = 0;
-    while (!d.done()) {
+  if (r.err) { o.err = r.err; return; }
+  const u32 dataPos = r.pos;
+  if ((u64)dataPos + total > (u64)off + len) { o.err = KE_TRUNCATED; return; }
+  // single-op changes (the shape of editing traces): one pass over directory + data fills the row; anything that is not
+  // exactly one canonical value per column leaves `single` false
+  bool single = haveAct; SingleVals sv;
+  sv.objActor = sv.objCtr = sv.keyActor = sv.keyCtr = sv.action = sv.valLen = sv.keyStrLen = NULL32; sv.keyStrOff = 0; sv.insert = 0; sv.valOff = 0; sv.predNum = 0; sv.predActor = sv.predCtr = NULL32;
+  {
+    ByteReaderT<S> d(src, dirPos, dataPos); u32 pos = dataPos; bool afterValLen = false; u32 valBytes = 0, rawLen = 0; bool sawPredA = false, sawPredC = false;
+    for (u64 i = 0; i < nCols && single; i++) {
       const u32 id = (u32)d.uleb(), l = (u32)d.uleb(); const int ix = col_index_of(id);
+      if (afterValLen) { afterValLen = false; if (id == 0x57) { sv.valOff = pos; rawLen = l; } }
       if (ix >= 0 && ix != CX_VAL_RAW && ix != CX_CHLD_ACTOR && ix != CX_CHLD_CTR) {
-        u32 rawOff = 0, rawLen = 0;
-        if (ix == CX_VAL_LEN) {   // VALUE_RAW (0x57) directly follows VALUE_LEN (0x56) in the directory when present
-          ByteReader peek = d; if (!peek.done()) { const u32 nid = (u32)peek.uleb(), nl = (u32)peek.uleb(); if (nid == 0x57) { rawOff = pos + l; rawLen = nl; } }
+        u32 v = 0, used = 0; bool isNull = false;
+        if (!single_value(src, ix, pos, l, v, isNull, used)) { single = false; break; }
+        switch (ix) {
+          case CX_OBJ_ACTOR: sv.objActor = isNull ? NULL32 : v; break; case CX_OBJ_CTR: sv.objCtr = isNull ? NULL32 : v; break;
+          case CX_KEY_ACTOR: sv.keyActor = isNull ? NULL32 : v; break; case CX_KEY_CTR: sv.keyCtr = isNull ? NULL32 : v; break;
+          case CX_KEY_STR: sv.keyStrOff = isNull ? 0 : pos + 2; sv.keyStrLen = isNull ? NULL32 : v; break;
+          case CX_INSERT: sv.insert = v; break; case CX_ACTION: sv.action = isNull ? NULL32 : v; break;
+          case CX_VAL_LEN: sv.valLen = isNull ? NULL32 : v; valBytes = isNull ? 0 : (v >> 4); afterValLen = true; break;
+          case CX_PRED_NUM: sv.predNum = isNull ? 0 : v; if (sv.predNum > 1) single = false; break;
+          case CX_PRED_ACTOR: sv.predActor = isNull ? NULL32 : v; sawPredA = true; break;
+          case CX_PRED_CTR: sv.predCtr = isNull ? NULL32 : v; sawPredC = true; break;
+          default: break;
         }
-        if (!(nOps == 1 && decode_single(arena, ix, pos, l, base, rawOff, rawLen, pb, nPreds))) {
-          const u32 e = decode_one_column(arena, ix, nOps, base, pos, pos + l, rawOff, rawLen, pb, nPreds, rows);
-          if (e && !kerr) kerr = e;
-        }
-        seen |= 1u << ix;
       }
       pos += l;
     }
-    for (int k = 0; k < NCOLS; k++) if (!(seen & (1u << k))) fill_absent_column(k, nOps, base, pb, nPreds, rows);
-    if (kerr) raise(errWord, kerr, c);
+    if (single && valBytes > rawLen) single = false;   // the general decoder reports it
+    if (single && sv.predNum == 0 && (sawPredA || sawPredC)) single = false;   // values without a pred to belong to: general path ignores them
   }
-};
+  u32 kerr = 0; u32 nOps = 0; u64 nPreds = 0;
+  if (single) { nOps = 1; nPreds = sv.predNum; }
+  else {
+    nOps = rle_count_values_t(src, dataPos + actOff, dataPos + actOff + actLen, &kerr);
+    if (!kerr) nPreds = rle_sum_values_t(src, dataPos + pnOff, dataPos + pnOff + pnLen, nOps, &kerr);
+  }
+  if (kerr) { o.err = kerr; return; }
+  if (nPreds > 0x7fffffffULL || nOps > 0x7fffffffu) { o.err = KE_TOO_LARGE; return; }
+  o.h.depsOff = depsOff; o.h.actorOff = actorOff; o.h.actorLen = (u32)actorLen; o.h.otherOff = otherOff; o.h.dirOff = dirPos; o.h.dataOff = dataPos;
+  o.h.startOp = startOp; o.h.seq = seq;
+  o.nDeps = (u32)nDeps; o.nOther = (u32)nOther; o.nOps = nOps; o.nPreds = (u32)nPreds; o.single = single; o.sv = sv;
+}
+HD void store_single(const SingleVals& sv, u32 base, u32 pb, const RawRows& rows) {
+  rows.objActor[base] = sv.objActor; rows.objCtr[base] = sv.objCtr; rows.keyActor[base] = sv.keyActor; rows.keyCtr[base] = sv.keyCtr;
+  rows.keyStrOff[base] = sv.keyStrOff; rows.keyStrLen[base] = sv.keyStrLen; rows.insert[base] = sv.insert; rows.action[base] = sv.action;
+  rows.valLen[base] = sv.valLen; rows.valOff[base] = sv.valOff; rows.predNum[base] = sv.predNum; rows.predOff[base] = pb;
+  if (sv.predNum) { rows.predActor[pb] = sv.predActor; rows.predCtr[pb] = sv.predCtr; }
+}
+// general expansion of a small change (2 .. SMALL_CHANGE_OPS ops, or one op in a non-canonical encoding): walks the
+// directory again and expands every column into rows [base, base + nOps) / preds [pb, pb + nPreds). Returns a KErr.
+template <class S> HD u32 expand_change(const S& src, const ChangeHot& h, u32 nOps, u32 nPreds, u32 base, u32 pb, const RawRows& rows) {
+  ByteReaderT<S> d(src, h.dirOff, h.dataOff); u32 pos = h.dataOff; u32 seen = 0, kerr = 0;
+  while (!d.done()) {
+    const u32 id = (u32)d.uleb(), l = (u32)d.uleb(); const int ix = col_index_of(id);
+    if (ix >= 0 && ix != CX_VAL_RAW && ix != CX_CHLD_ACTOR && ix != CX_CHLD_CTR) {
+      u32 rawOff = 0, rawLen = 0;
+      if (ix == CX_VAL_LEN) {   // VALUE_RAW (0x57) directly follows VALUE_LEN (0x56) in the directory when present
+        ByteReaderT<S> peek = d; if (!peek.done()) { const u32 nid = (u32)peek.uleb(), nl = (u32)peek.uleb(); if (nid == 0x57) { rawOff = pos + l; rawLen = nl; } }
+      }
+      const u32 e = decode_one_column_t(src, ix, nOps, base, pos, pos + l, rawOff, rawLen, pb, nPreds, rows);
+      if (e && !kerr) kerr = e;
+      seen |= 1u << ix;
+    }
+    pos += l;
+  }
+  for (int k = 0; k < NCOLS; k++) if (!(seen & (1u << k))) fill_absent_column(k, nOps, base, pb, nPreds, rows);
+  return kerr;
+}
 
-// Large changes: one thread per (column, large change); `large` lists the change indices
+struct DecodeTilesArgs {
+  const u8* arena; const u32* chOff; const u32* chLen; u32 B;
+  ChangeHot* hot; u32* nOps; u32* nPreds; u32* nDeps; u32* nActors;
+  u32* rawBase /* [B+1] first raw row of each change (batch order, every change) */; u32* rawPredBase /* [B+1] */;
+  u32* decErr /* [B] KErr of the column contents: raised only if the change is applied (the reference decodes columns lazily) */;
+  RawRows rows; u32 rowCap, predCap;   // rows are written only inside the capacity; totals[2] tells the host to grow and run again
+  u64* tileState; u32* ticket; u32* totals /* [0] ops [1] preds [2] overflow [3] some change has > SMALL_CHANGE_OPS ops */; u64* errWord; u32 numTiles;
+};
+// what one thread does with its change once the row range is known
+template <class S> HD void finish_change(const DecodeTilesArgs& a, const S& src, u32 c, const ParsedChange& pc, u32 base, u32 pb) {
+  a.hot[c] = pc.h; a.nOps[c] = pc.nOps; a.nPreds[c] = pc.nPreds; a.nDeps[c] = pc.nDeps; a.nActors[c] = 1 + pc.nOther;
+  a.rawBase[c] = base; a.rawPredBase[c] = pb;
+  u32 kerr = 0;
+  if (pc.err) raise(a.errWord, pc.err, c);
+  else if (pc.nOps > SMALL_CHANGE_OPS) a.totals[3] = 1;   // expanded by DecodeColumnKernel once the gate has decided
+  else if (pc.nOps > 0) {
+    if ((u64)base + pc.nOps > a.rowCap || (u64)pb + pc.nPreds > a.predCap) a.totals[2] = 1;
+    else if (pc.single) store_single(pc.sv, base, pb, a.rows);
+    else kerr = expand_change(src, pc.h, pc.nOps, pc.nPreds, base, pb, a.rows);
+  }
+  a.decErr[c] = kerr;
+}
+
+#ifdef AMG_EMU
+inline void decode_tiles(Ctx& c, const DecodeTilesArgs& a) {
+  u64 ops = 0, preds = 0; a.totals[0] = a.totals[1] = a.totals[2] = a.totals[3] = 0;
+  for (u32 i = 0; i < a.B; i++) {
+    ParsedChange pc; parse_change(PtrSrc{a.arena}, a.chOff[i], a.chLen[i], pc);
+    finish_change(a, PtrSrc{a.arena}, i, pc, (u32)std::min<u64>(ops, 0x7fffffffu), (u32)std::min<u64>(preds, 0x7fffffffu));
+    ops += pc.nOps; preds += pc.nPreds;
+  }
+  a.rawBase[a.B] = a.totals[0] = (u32)std::min<u64>(ops, 0x7fffffffu); a.rawPredBase[a.B] = a.totals[1] = (u32)std::min<u64>(preds, 0x7fffffffu);
+  if (ops > a.rowCap || preds > a.predCap) a.totals[2] = 1;   // rows that larger changes reserved must fit as well
+  c.launches++;
+}
+#else
+// ---- the tile kernel. One CTA = DT_THREADS consecutive changes of the batch, one thread per change.
+//  1. the tile's byte range [lo, hi) of the arena is copied into shared memory by ONE bulk asynchronous copy
+//     (cp.async.bulk global -> shared, completion on an mbarrier): every byte of a change crosses HBM -> SM once, in full
+//     lines, and the byte-serial parsers below then read shared memory. 8 CTAs are resident per SM, so the copies of some
+//     tiles are in flight while others parse. Tiles whose range does not fit (big changes, changes that are not stored
+//     back to back: queue entries, inflated changes) read global memory directly.
+//  2. every thread parses its change (header, directory, counts; single-op changes keep their row in registers);
+//  3. block scan of (ops, preds) + decoupled look-back across tiles (tickets in launch order) -> first raw row of every change;
+//  4. rows are written (single-op: straight from registers, consecutive threads -> consecutive rows; 2..16 ops: second
+//     walk over the shared-memory copy); larger changes only reserve their rows.
+static const int DT_THREADS = 128;
+static const u32 DT_STAGE = 24u << 10;
+DEV u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+DEV u32 sat31(u64 v) { return v > 0x7fffffffULL ? 0x7fffffffu : (u32)v; }
+__global__ void __launch_bounds__(DT_THREADS, 8) k_decode_tiles(const DecodeTilesArgs a) {
+  __shared__ __align__(128) u8 stage[DT_STAGE];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ u32 sTile, sLo, sHi; __shared__ u64 sWarp[2][DT_THREADS / 32]; __shared__ u64 sBase[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    sTile = atomicAdd(a.ticket, 1u); sLo = 0xffffffffu; sHi = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const u32 tile = sTile; const u32 c = tile * DT_THREADS + tid; const bool live = c < a.B;
+  const u32 off = live ? a.chOff[c] : 0xffffffffu, len = live ? a.chLen[c] : 0;
+  {
+    const u32 lo = __reduce_min_sync(0xffffffffu, off), hi = __reduce_max_sync(0xffffffffu, live ? off + len : 0u);
+    if (lane == 0) { atomicMin(&sLo, lo); atomicMax(&sHi, hi); }
+  }
+  __syncthreads();
+  const u32 lo16 = sLo & ~15u, hi16 = (sHi + 15u) & ~15u;
+  const bool staged = sHi > sLo && hi16 - lo16 <= DT_STAGE;
+  if (staged) {
+    if (tid == 0) {
+      const u32 bytes = hi16 - lo16;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(&bar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(smem_addr(stage)), "l"(a.arena + lo16), "r"(bytes), "r"(smem_addr(&bar)) : "memory");
+    }
+    u32 ok = 0;
+    while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_addr(&bar)) : "memory");
+  }
+  ParsedChange pc; pc.nOps = pc.nPreds = 0;
+  const SmemSrc ssrc{stage, lo16}; const PtrSrc gsrc{a.arena};
+  if (live) { if (staged) parse_change(ssrc, off, len, pc); else parse_change(gsrc, off, len, pc); }
+  // (ops, preds) of the tile: exclusive scan inside the CTA, 64-bit each (a run-length encoded change can hold 2^31 ops)
+  u64 vo = live ? pc.nOps : 0, vp = live ? pc.nPreds : 0; u64 io = vo, ip = vp;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const u64 to = __shfl_up_sync(0xffffffffu, io, d), tp = __shfl_up_sync(0xffffffffu, ip, d); if (lane >= d) { io += to; ip += tp; } }
+  if (lane == 31) { sWarp[0][warp] = io; sWarp[1][warp] = ip; }
+  __syncthreads();
+  u64 wo = 0, wp = 0, to = 0, tp = 0;
+#pragma unroll
+  for (int w = 0; w < DT_THREADS / 32; w++) { const u64 xo = sWarp[0][w], xp = sWarp[1][w]; if (w < warp) { wo += xo; wp += xp; } to += xo; tp += xp; }
+  if (warp == 0) {   // publish the tile aggregate, look back over the predecessors (32 per step), publish the inclusive prefix
+    volatile u64* st = a.tileState; u64 exo = 0, exp_ = 0;
+    const u64 agg = ((u64)sat31(tp) << 31) | sat31(to);
+    if (lane == 0) st[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | agg;
+    if (tile > 0) {
+      long long p = (long long)tile;
+      while (true) {
+        const long long idx = p - 1 - lane; u32 status = 2; u64 val = 0;
+        if (idx >= 0) { u64 w; do { w = st[idx]; } while ((w >> 62) == 0); status = (u32)(w >> 62); val = w & ((1ull << 62) - 1); }
+        const unsigned inclMask = __ballot_sync(0xffffffffu, status == 2);
+        const int first = inclMask ? __ffs(inclMask) - 1 : 32;
+        u64 co = lane <= first ? (val & 0x7fffffffULL) : 0, cp = lane <= first ? (val >> 31) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { co += __shfl_xor_sync(0xffffffffu, co, d); cp += __shfl_xor_sync(0xffffffffu, cp, d); }
+        exo += co; exp_ += cp;
+        if (inclMask) break;
+        p -= 32;
+      }
+      if (lane == 0) st[tile] = (2ull << 62) | ((u64)sat31(exp_ + tp) << 31) | sat31(exo + to);
+    }
+    if (lane == 0) {
+      sBase[0] = exo; sBase[1] = exp_;
+      if (tile == a.numTiles - 1) {
+        a.totals[0] = a.rawBase[a.B] = sat31(exo + to); a.totals[1] = a.rawPredBase[a.B] = sat31(exp_ + tp); *a.ticket = 0;
+        if (exo + to > a.rowCap || exp_ + tp > a.predCap) a.totals[2] = 1;   // rows that larger changes reserved must fit as well
+      }
+    }
+  }
+  __syncthreads();
+  if (live) {
+    const u32 base = sat31(sBase[0] + wo + io - vo), pb = sat31(sBase[1] + wp + ip - vp);
+    if (staged) finish_change(a, ssrc, c, pc, base, pb); else finish_change(a, gsrc, c, pc, base, pb);
+  }
+}
+inline void decode_tiles(Ctx& c, const DecodeTilesArgs& a) {
+  CUDA_CHECK(cudaMemsetAsync(a.tileState, 0, (size_t)a.numTiles * 8, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(a.totals, 0, 16, c.stream));
+  k_decode_tiles<<<a.numTiles, DT_THREADS, 0, c.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  c.launches++;
+}
+#endif
+inline u32 decode_num_tiles(size_t B) {
+#ifdef AMG_EMU
+  return 1;
+#else
+  return (u32)((B + DT_THREADS - 1) / DT_THREADS);
+#endif
+}
+
+// Changes with more than SMALL_CHANGE_OPS ops: one thread per (column, large change); `large` lists the change indices.
+// The column is found by walking the change's directory (at most a few entries).
 struct DecodeColumnKernel {
-  const u8* arena; size_t numChanges; const u32* large; size_t numLarge; const ChangeMeta* meta; const u32* colOff; const u32* colLen;
-  const u32* opBase /* exclusive scan of nOps */; const u32* predBase; const u8* applied /* per change: decode only if 1 */;
+  const u8* arena; const u32* large; size_t numLarge; const ChangeHot* hot; const u32* nOps; const u32* nPreds;
+  const u32* rawBase; const u32* rawPredBase; const u8* applied /* per change: decode only if 1 */;
   RawRows rows; u64* errWord;
   HD void operator()(size_t t) const {
     const int col = (int)(t / numLarge); const size_t c = large[t % numLarge];
     if (!applied[c]) return;
-    const u32 nOps = meta[c].nOps; if (nOps == 0) return;
-    const u32 cOff = colOff[(size_t)col * numChanges + c], cLen = colLen[(size_t)col * numChanges + c];
-    if (cLen == 0) { fill_absent_column(col, nOps, opBase[c], predBase[c], meta[c].nPreds, rows); return; }
-    const u32 e = decode_one_column(arena, col, nOps, opBase[c], cOff, cOff + cLen, colOff[(size_t)CX_VAL_RAW * numChanges + c], colLen[(size_t)CX_VAL_RAW * numChanges + c],
-                                    predBase[c], meta[c].nPreds, rows);
+    const u32 n = nOps[c]; if (n == 0 || col == CX_VAL_RAW || col == CX_CHLD_ACTOR || col == CX_CHLD_CTR) return;
+    const ChangeHot h = hot[c];
+    ByteReader d(arena, h.dirOff, h.dataOff); u32 pos = h.dataOff; u32 cOff = 0, cLen = 0, rawOff = 0, rawLen = 0; bool found = false;
+    while (!d.done()) {
+      const u32 id = (u32)d.uleb(), l = (u32)d.uleb(); const int ix = col_index_of(id);
+      if (ix == col) { cOff = pos; cLen = l; found = true; }
+      if (ix == CX_VAL_RAW) { rawOff = pos; rawLen = l; }
+      pos += l;
+    }
+    if (!found || cLen == 0) { fill_absent_column(col, n, rawBase[c], rawPredBase[c], nPreds[c], rows); return; }
+    const u32 e = decode_one_column(arena, col, n, rawBase[c], cOff, cOff + cLen, rawOff, rawLen, rawPredBase[c], nPreds[c], rows);
     if (e) raise(errWord, e, c);
   }
 };
 #ifndef AMG_PARSE_MINBLOCKS
-#define AMG_PARSE_MINBLOCKS 4   // measured on B200 (1M single-op changes): 1 -> 0.119 / 0.152 ms, 4 -> 0.101 / 0.126, 6 -> 0.120 / 0.140, 8 -> 0.131 / 0.161 (parse / expand)
+#define AMG_PARSE_MINBLOCKS 4
 #endif
 template <> struct LaunchTraits<ParseKernel> { static const int minBlocks = AMG_PARSE_MINBLOCKS; };
-template <> struct LaunchTraits<DecodeSmallKernel> { static const int minBlocks = AMG_PARSE_MINBLOCKS; };
-struct LargeFlagKernel { const ChangeMeta* meta; const u8* applied; u32* flag; HD void operator()(size_t c) const { flag[c] = (applied[c] && meta[c].nOps > SMALL_CHANGE_OPS) ? 1u : 0u; } };
+struct LargeFlagKernel { const u32* nOps; const u8* applied; u32* flag; HD void operator()(size_t c) const { flag[c] = (applied[c] && nOps[c] > SMALL_CHANGE_OPS) ? 1u : 0u; } };
 
 }  // namespace amg

@@ -216,10 +216,9 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   }
   side_join(ctx);
   timer.mark(); hostMark();
-  meta.ensure(ctx, B); colOff.ensure(ctx, (size_t)NCOLS * B); colLen.ensure(ctx, (size_t)NCOLS * B);
-  nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
-  dev_memset(ctx, flagWord.p + 8, 0, 4);
-  foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p, flagWord.p + 8});
+  // header parse + column expansion of every change of the batch in one pass over the bytes (decode.cuh). Rows land in
+  // batch order; which changes are applied is decided by the gate below, FinalizeOpsKernel then picks their rows.
+  runDecodeTiles(arena.p, B, cur - arenaLen0);
   // (parse errors surface with the first host round trip of the gate: the error word travels with every small read, and a
   //  change that failed to parse has zero deps / ops so the kernels in between have nothing to walk)
   // ------------------------------------------------------------ 2. causal gate
@@ -229,18 +228,26 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   const size_t G = numApplied + B; const size_t tcap = pow2_at_least(2 * G + 2);
   hashTable.ensure(ctx, tcap); dev_memset(ctx, hashTable.p, 0xff, tcap * 4);
   foreach(ctx, G, HashInsertKernel{hashes.p, hashTable.p, (u64)tcap - 1});
-  foreach(ctx, B, ResolveDepsKernel{arena.p, hashes.p, hashTable.p, (u64)tcap - 1, meta.p, numApplied, depBase.p, depIdx.p, primary.p});
+  foreach(ctx, B, ResolveDepsKernel{arena.p, hashes.p, hashTable.p, (u64)tcap - 1, hot.p, nDeps.p, numApplied, depBase.p, depIdx.p, primary.p});
   fill32(pass.p, 1, B);
   dev_memset(ctx, flagWord.p + 12, 0, 4);
   foreach(ctx, B, GateDupFlagKernel{primary.p, numApplied, flagWord.p + 12});
-  bool copiesChecked = false, haveCopies = false;
+  bool copiesChecked = false, haveCopies = false; u32 decTot[4] = {0, 0, 0, 0};
   for (size_t iter = 0; iter <= B + 1; iter += 2) {   // two sweeps per host round trip: the common batch settles in the first
     if (haveCopies) break;
-    foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, meta.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
+    foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, nDeps.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
     dev_memset(ctx, flagWord.p, 0, 4);
-    foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, meta.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
-    u32 again = 0, copies = 0; readU32x2(flagWord.p, flagWord.p + 12, &again, &copies);
+    foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, nDeps.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
+    u32 again = 0, copies = 0;
+    { void* dst[6] = {&again, &copies, &decTot[0], &decTot[1], &decTot[2], &decTot[3]};
+      readWords({{flagWord.p, 4}, {flagWord.p + 12, 4}, {decTotals.p, 4}, {decTotals.p + 1, 4}, {decTotals.p + 2, 4}, {decTotals.p + 3, 4}}, dst); }
     checkErr(actorIds);   // free: the error word came with the read
+    if (iter == 0 && decodeOverflowed(decTot)) {   // the raw row tables were too small for this batch: grown, decoded again (same results otherwise)
+      runDecodeTiles(arena.p, B, cur - arenaLen0);
+      void* d2[4] = {&decTot[0], &decTot[1], &decTot[2], &decTot[3]};
+      readWords({{decTotals.p, 4}, {decTotals.p + 1, 4}, {decTotals.p + 2, 4}, {decTotals.p + 3, 4}}, d2);
+      if (decTot[2]) throw Error(AMG_ERR_INTERNAL, "amgpu: decode row tables overflowed twice");
+    }
     if (!copiesChecked) { copiesChecked = true; haveCopies = copies != 0; }
     if (!again) break;
   }
@@ -249,7 +256,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     for (size_t iter = 0; iter <= B + 1; iter++) {
       dev_memset(ctx, gateBest.p, 0xff, B * 8); dev_memset(ctx, flagWord.p, 0, 4);
       foreach(ctx, B, GateBestKernel{primary.p, pass.p, numApplied, gateBest.p});
-      foreach(ctx, B, RelaxCopiesKernel{depBase.p, depIdx.p, meta.p, primary.p, numApplied, gateBest.p, pass.p, flagWord.p, (u32)B + 1});
+      foreach(ctx, B, RelaxCopiesKernel{depBase.p, depIdx.p, nDeps.p, primary.p, numApplied, gateBest.p, pass.p, flagWord.p, (u32)B + 1});
       const u32 again = readU32(flagWord.p);
       checkErr(actorIds);
       if (!again) break;
@@ -296,8 +303,8 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     authorSlot.ensure(ctx, B); newSlots.ensure(ctx, B + 1); u32 fresh = 0;
     while (true) {   // grow the table until the distinct authors fit at load factor <= 1/2
       dev_memset(ctx, flagWord.p, 0, 8);
-      foreach(ctx, B, ActorInternKernel{arena.p, meta.p, applied.p, appRank.p, actorSlots.p, (u64)actorCap - 1, authorSlot.p});
-      foreach(ctx, B, NewActorKernel{meta.p, applied.p, authorSlot.p, actorSlots.p, newSlots.p, flagWord.p});
+      foreach(ctx, B, ActorInternKernel{arena.p, hot.p, applied.p, appRank.p, actorSlots.p, (u64)actorCap - 1, authorSlot.p});
+      foreach(ctx, B, NewActorKernel{hot.p, applied.p, authorSlot.p, actorSlots.p, newSlots.p, flagWord.p});
       fresh = readU32(flagWord.p);
       if ((actorIds.size() + fresh) * 2 <= actorCap) break;
       actorCap *= 4; actorSlots.ensure(ctx, actorCap); rebuildActorTable();
@@ -342,7 +349,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     foreach(ctx, B, MaskedCountKernel{nActors.p, applied.p, rowSlot.p});
     scan_exclusive(ctx, scanTmp, rowSlot.p, amapBase.p, B);
     amap.ensure(ctx, B + (cur - arenaLen0) / 2 + 2);   // author + one entry per other-actor table entry (>= 2 bytes each): bound instead of a round trip
-    foreach(ctx, B, ActorMapKernel{arena.p, meta.p, applied.p, appRank.p, actorSlots.p, (u64)actorCap - 1, amapBase.p, amap.p, errWord.p});
+    foreach(ctx, B, ActorMapKernel{arena.p, hot.p, nActors.p, applied.p, appRank.p, actorSlots.p, (u64)actorCap - 1, amapBase.p, amap.p, errWord.p});
     dbgMark("actors:mapped");
     // ---------------------------------------------------------- 4. sequence numbers
     changeActor.ensure(ctx, B); actorCnt.ensure(ctx, A + 1); actorBaseD.ensure(ctx, A + 1); seqSlot.ensure(ctx, numNew + 1);
@@ -351,10 +358,10 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     {
       const u64 ew = fetchErr();
       if ((ew & 0xff) == KE_UNKNOWN_ACTOR) {   // name the actor like the reference does (new.js:1446): re-read that change's actor table
-        const size_t b = (size_t)(ew >> 8); ChangeMeta m0; d2h(ctx, &m0, meta.p + b, sizeof(ChangeMeta)); sync(ctx);
+        const size_t b = (size_t)(ew >> 8); ChangeHot m0; u32 na0 = 1; d2h(ctx, &m0, hot.p + b, sizeof(ChangeHot)); d2h(ctx, &na0, nActors.p + b, 4); sync(ctx);
         std::vector<u8> bytes(m0.len); d2h(ctx, bytes.data(), arena.p + m0.off, m0.len); sync(ctx);
         ByteReader r(bytes.data(), m0.otherOff - m0.off, m0.len); std::string culprit;
-        for (u32 k = 0; k <= m0.nOther && !r.err; k++) {
+        for (u32 k = 0; k < na0 && !r.err; k++) {
           u32 off, len; if (k == 0) { off = m0.actorOff - m0.off; len = m0.actorLen; } else { len = (u32)r.uleb(); off = r.pos; r.skip(len); }
           if (r.err) break;
           const std::string id((const char*)bytes.data() + off, len);
@@ -368,13 +375,13 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     DBuf<u64>& clockDev = pairKey;   // scratch reuse before the succ phase
     clockDev.ensure(ctx, A + 1); h2d(ctx, clockDev.p, clockNow.data(), A * 8);
     dev_memset(ctx, seqSlot.p, 0xff, (numNew + 1) * 4); dev_memset(ctx, flagWord.p, 0, 4);
-    foreach(ctx, B, SeqScatterKernel{meta.p, applied.p, changeActor.p, appRank.p, actorBaseD.p, actorCnt.p, clockDev.p, seqSlot.p, flagWord.p});
-    foreach(ctx, B, SeqMonoKernel{meta.p, applied.p, changeActor.p, actorBaseD.p, clockDev.p, seqSlot.p, flagWord.p});
+    foreach(ctx, B, SeqScatterKernel{hot.p, applied.p, changeActor.p, appRank.p, actorBaseD.p, actorCnt.p, clockDev.p, seqSlot.p, flagWord.p});
+    foreach(ctx, B, SeqMonoKernel{hot.p, applied.p, changeActor.p, actorBaseD.p, clockDev.p, seqSlot.p, flagWord.p});
     actorCntH.resize(A); d2h(ctx, actorCntH.data(), actorCnt.p, A * 4);
     if (readU32(flagWord.p)) {
       // error path: replay the sequence check in application order on the host to produce the reference's message
-      std::vector<ChangeMeta> mh(B); std::vector<u32> ca(B), ar(B); std::vector<u8> ap(B);
-      d2h(ctx, mh.data(), meta.p, B * sizeof(ChangeMeta)); d2h(ctx, ca.data(), changeActor.p, B * 4); d2h(ctx, ar.data(), appRank.p, B * 4); d2h(ctx, ap.data(), applied.p, B); sync(ctx);
+      std::vector<ChangeHot> mh(B); std::vector<u32> ca(B), ar(B); std::vector<u8> ap(B);
+      d2h(ctx, mh.data(), hot.p, B * sizeof(ChangeHot)); d2h(ctx, ca.data(), changeActor.p, B * 4); d2h(ctx, ar.data(), appRank.p, B * 4); d2h(ctx, ap.data(), applied.p, B); sync(ctx);
       std::vector<u32> byRank(numNew, 0); for (size_t b = 0; b < B; b++) if (ap[b]) byRank[ar[b]] = (u32)b;
       std::vector<u64> clk = clockNow;
       for (size_t k = 0; k < numNew; k++) {
@@ -387,42 +394,48 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     }
     for (size_t a = 0; a < A; a++) clockNow[a] += actorCntH[a];
     dbgMark("seq:checked");
-    // ---------------------------------------------------------- 5. decode ops
-    opBase.ensure(ctx, B + 1); predBase.ensure(ctx, B + 1); timeBase.ensure(ctx, B + 1);
-    foreach(ctx, B, MaskedCountKernel{nOps.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, opBase.p, B);
-    foreach(ctx, B, MaskedCountKernel{nPreds.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, predBase.p, B);
-    u32 anyLarge = 0;
-    { u32 m32 = 0, p32 = 0; void* dst[3] = {&m32, &p32, &anyLarge}; readWords({{opBase.p + B, 4}, {predBase.p + B, 4}, {flagWord.p + 8, 4}}, dst); M = m32; P = p32; }
+    // ---------------------------------------------------------- 5. ops of the applied changes
+    // The rows were decoded with the headers (step 1), in batch order. When every change of the batch is applied the
+    // op / pred ranges of the changes are the raw ones; otherwise they are the scans over the applied changes only.
+    timeBase.ensure(ctx, B + 1);
+    const bool allApplied = numNew == B;
+    u32* opBaseP = rawBase.p; u32* predBaseP = rawPredBase.p;
+    const u32 anyLarge = decTot[3];
+    if (allApplied) { M = decTot[0]; P = decTot[1]; }
+    else {
+      opBase.ensure(ctx, B + 1); predBase.ensure(ctx, B + 1); opBaseP = opBase.p; predBaseP = predBase.p;
+      foreach(ctx, B, MaskedCountKernel{nOps.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, opBase.p, B);
+      foreach(ctx, B, MaskedCountKernel{nPreds.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, predBase.p, B);
+      u32 m32 = 0, p32 = 0; void* dst[2] = {&m32, &p32}; readWords({{opBase.p + B, 4}, {predBase.p + B, 4}}, dst); M = m32; P = p32;
+    }
+    if (decTot[0] >= 0x7fffffffu || decTot[1] >= 0x7fffffffu) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 2^31 operations in one call");
     dbgMark("decode:counts");
     if (!inOrder) {
       perm.ensure(ctx, B + 1); dev_memset(ctx, perm.p, 0, (B + 1) * 4);
       foreach(ctx, B, OpsInOrderKernel{nOps.p, applied.p, appRank.p, perm.p});
       scan_exclusive(ctx, scanTmp, perm.p, perm.p, numNew);
     }
-    foreach(ctx, B, TimeBaseKernel{perm.p, applied.p, appRank.p, opBase.p, inOrder ? 1 : 0, timeBase.p});
+    foreach(ctx, B, TimeBaseKernel{perm.p, applied.p, appRank.p, opBaseP, inOrder ? 1 : 0, timeBase.p});
     DBuf<u64>& maxOpD = pairSucc; maxOpD.ensure(ctx, 1); h2d(ctx, maxOpD.p, &maxOpNow, 8);
-    foreach(ctx, B, MaxOpKernel{meta.p, applied.p, maxOpD.p});
+    foreach(ctx, B, MaxOpKernel{hot.p, nOps.p, applied.p, decErr.p, maxOpD.p, errWord.p});
     d2h(ctx, &maxOpNow, maxOpD.p, 8);
-    for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, M + 1);
-    r_predActor.ensure(ctx, P + 1); r_predCtr.ensure(ctx, P + 1);
-    RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
-    foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+    RawRows raw = rawRows();
     lastNumLarge = 0;
-    if (anyLarge) {   // changes with more than SMALL_CHANGE_OPS ops: (column, change)-parallel expansion
+    if (anyLarge) {   // changes with more than SMALL_CHANGE_OPS ops: (column, change)-parallel expansion into their reserved rows
       largeFlag.ensure(ctx, B + 1); largeSlot.ensure(ctx, B + 2); largeList.ensure(ctx, B + 1);
-      foreach(ctx, B, LargeFlagKernel{meta.p, applied.p, largeFlag.p});
+      foreach(ctx, B, LargeFlagKernel{nOps.p, applied.p, largeFlag.p});
       scan_exclusive(ctx, scanTmp, largeFlag.p, largeSlot.p, B);
       lastNumLarge = readU32(largeSlot.p + B);
       if (lastNumLarge > 0) {
         foreach(ctx, B, CompactKernel{largeFlag.p, largeSlot.p, largeList.p});
-        foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{arena.p, B, largeList.p, lastNumLarge, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+        foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{arena.p, largeList.p, lastNumLarge, hot.p, nOps.p, nPreds.p, rawBase.p, rawPredBase.p, applied.p, raw, errWord.p});
       }
     }
     for (DBuf<u64>* b : {&o_id, &o_obj, &o_key}) b->ensure(ctx, M + 1);
     o_predId.ensure(ctx, P + 1);
     for (DBuf<u32>* b : {&o_keyStrOff, &o_keyStrLen, &o_flags, &o_valLen, &o_valOff, &o_predOff, &o_predNum, &o_change, &o_time}) b->ensure(ctx, M + 1);
     OpRows ops{o_id.p, o_obj.p, o_key.p, o_keyStrOff.p, o_keyStrLen.p, o_flags.p, o_valLen.p, o_valOff.p, o_predOff.p, o_predNum.p, o_change.p, o_time.p, o_predId.p};
-    foreach(ctx, M, FinalizeOpsKernel{B, meta.p, opBase.p, timeBase.p, amapBase.p, amap.p, applied.p, raw, ops, errWord.p});
+    foreach(ctx, M, FinalizeOpsKernel{B, hot.p, nActors.p, opBaseP, predBaseP, rawBase.p, rawPredBase.p, timeBase.p, amapBase.p, amap.p, applied.p, raw, ops, errWord.p});
     checkErr(actorsNow);
     dbgMark("decode:finalized");
     timer.mark(); hostMark();
@@ -547,7 +560,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     dbgMark("commit:begin");
     {
       DBuf<u32>& isDep = groupLinked; isDep.ensure(ctx, G + 1); dev_memset(ctx, isDep.p, 0, (G + 1) * 4);
-      foreach(ctx, B, MarkDepsKernel{applied.p, meta.p, depBase.p, depIdx.p, isDep.p});
+      foreach(ctx, B, MarkDepsKernel{applied.p, nDeps.p, depBase.p, depIdx.p, isDep.p});
       emit.ensure(ctx, B + 1); slot.ensure(ctx, B + 2); objStart.ensure(ctx, B + 1);
       foreach(ctx, B, HeadFlag2Kernel{applied.p, isDep.p, numApplied, emit.p});
       scan_exclusive(ctx, scanTmp, emit.p, slot.p, B);
@@ -610,7 +623,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   timer.mark(); hostMark();
   fillPatchHeader(out);
   if (isLocal && n == 1) {   // new.js:1874-1877
-    std::vector<ChangeMeta> m0(1); d2h(ctx, m0.data(), meta.p, sizeof(ChangeMeta)); sync(ctx);
+    std::vector<ChangeHot> m0(1); d2h(ctx, m0.data(), hot.p, sizeof(ChangeHot)); sync(ctx);
     mirror_wait(ctx);
     out.hasActorSeq = true; out.actor.assign((const char*)hostArena.data() + m0[0].actorOff, m0[0].actorLen); out.seq = m0[0].seq;
   }
@@ -852,28 +865,56 @@ inline void Engine::getPatch(PatchOut& out) {
 
 namespace amg {
 
+inline RawRows Engine::rawRows() {
+  return RawRows{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
+}
+// Fused header parse + column expansion of B changes (chOff / chLen are on the device). The raw row tables are sized from
+// what earlier calls needed (else from the batch size); the kernel never writes outside them and reports an overflow.
+inline void Engine::runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes) {
+  hot.ensure(ctx, B + 1); nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
+  rawBase.ensure(ctx, B + 2); rawPredBase.ensure(ctx, B + 2); decErr.ensure(ctx, B + 1); decTotals.ensure(ctx, 4);
+  if (!tileTicket.p) { tileTicket.ensure(ctx, 4); dev_memset(ctx, tileTicket.p, 0, 16); }
+  const u32 numTiles = decode_num_tiles(B); tileState.ensure(ctx, (size_t)numTiles + 1);
+  const size_t wantRows = std::max(decWantRows, B + B / 4 + batchBytes / 256 + 1024), wantPreds = std::max(decWantPreds, B + B / 4 + batchBytes / 256 + 1024);
+  for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, wantRows + 1);
+  r_predActor.ensure(ctx, wantPreds + 1); r_predCtr.ensure(ctx, wantPreds + 1);
+  decRowCap = wantRows; decPredCap = wantPreds;
+  DecodeTilesArgs a{arenaP, chOff.p, chLen.p, (u32)B, hot.p, nOps.p, nPreds.p, nDeps.p, nActors.p, rawBase.p, rawPredBase.p, decErr.p, rawRows(), (u32)wantRows, (u32)wantPreds,
+                    tileState.p, tileTicket.p, decTotals.p, errWord.p, numTiles};
+  decode_tiles(ctx, a);
+}
+inline bool Engine::decodeOverflowed(const u32 totals[4]) {
+  if (!totals[2]) return false;
+  if (totals[0] >= (1u << 29)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 2^29 operations in one call");
+  if (totals[1] >= (1u << 30)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 2^30 predecessors in one call");
+  decWantRows = (size_t)totals[0] + 1024; decWantPreds = (size_t)totals[1] + 1024;
+  return true;
+}
+
 // Re-runs the decode kernels over the last applied batch (bytes resident in HBM) and times them with CUDA events.
+// msParse = the fused decode (k_decode_tiles: header parse + expansion of every change of up to SMALL_CHANGE_OPS ops),
+// msDec = DecodeColumnKernel over the larger changes (0 when the batch has none).
 inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes) {
   if (lastB == 0 || iters <= 0) throw Error(AMG_ERR_RANGE, "amg_bench_decode: no batch has been applied yet");
   const size_t B = lastB;
   hashTmp.ensure(ctx, B * 32 + 64);
-  RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
+  RawRows raw = rawRows();
   *algoBytes = (u64)lastBytes + 48ull * lastM + 8ull * lastP + 96ull * B;
 #ifndef AMG_EMU
   cudaEvent_t e[4]; for (auto& x : e) cudaEventCreate(&x);
+  const u8* batchArena = arena.p;
   cudaEventRecord(e[0], ctx.stream);
-  for (int i = 0; i < iters; i++) foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
+  for (int i = 0; i < iters; i++) foreach(ctx, B, ShaKernel{batchArena, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
   cudaEventRecord(e[1], ctx.stream);
-  for (int i = 0; i < iters; i++) foreach(ctx, B, ParseKernel{arena.p, chOff.p, chLen.p, B, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p, flagWord.p + 8});
+  for (int i = 0; i < iters; i++) runDecodeTiles(batchArena, B, lastBytes);
   cudaEventRecord(e[2], ctx.stream);
   for (int i = 0; i < iters; i++) {
-    foreach(ctx, B, DecodeSmallKernel{arena.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
-    if (lastNumLarge > 0) foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{arena.p, B, largeList.p, lastNumLarge, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+    if (lastNumLarge > 0) foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{batchArena, largeList.p, lastNumLarge, hot.p, nOps.p, nPreds.p, rawBase.p, rawPredBase.p, applied.p, raw, errWord.p});
   }
   cudaEventRecord(e[3], ctx.stream);
   CUDA_CHECK(cudaEventSynchronize(e[3]));
   float a, b, c; cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[2], e[3]);
-  *msSha = a / iters; *msParse = b / iters; *msDec = c / iters;
+  *msSha = a / iters; *msParse = b / iters; *msDec = lastNumLarge > 0 ? c / iters : 0.f;
   for (auto& x : e) cudaEventDestroy(x);
 #else
   *msSha = *msParse = *msDec = 0;
@@ -1118,26 +1159,26 @@ inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* 
   chOff.ensure(ctx, n); chLen.ensure(ctx, n); h2d(ctx, chOff.p, off.data(), n * 4); h2d(ctx, chLen.p, len.data(), n * 4);
   dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull; hashTmp.ensure(ctx, n * 32 + 64);
   foreach(ctx, n, ShaKernel{ar.p, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
-  meta.ensure(ctx, n); colOff.ensure(ctx, (size_t)NCOLS * n); colLen.ensure(ctx, (size_t)NCOLS * n);
-  nOps.ensure(ctx, n + 1); nPreds.ensure(ctx, n + 1); nDeps.ensure(ctx, n + 1); nActors.ensure(ctx, n + 1);
-  foreach(ctx, n, ParseKernel{ar.p, chOff.p, chLen.p, n, meta.p, colOff.p, colLen.p, nOps.p, nPreds.p, nDeps.p, nActors.p, errWord.p, flagWord.p + 8});
+  applied.ensure(ctx, n); dev_memset(ctx, applied.p, 1, n);
+  u32 tot[4] = {0, 0, 0, 0}; void* dst[4] = {&tot[0], &tot[1], &tot[2], &tot[3]};
+  runDecodeTiles(ar.p, n, staged.size());
+  readWords({{decTotals.p, 4}, {decTotals.p + 1, 4}, {decTotals.p + 2, 4}, {decTotals.p + 3, 4}}, dst);
+  if (decodeOverflowed(tot)) { runDecodeTiles(ar.p, n, staged.size()); readWords({{decTotals.p, 4}, {decTotals.p + 1, 4}, {decTotals.p + 2, 4}, {decTotals.p + 3, 4}}, dst); }
   checkErr(actorIds);
-  opBase.ensure(ctx, n + 1); predBase.ensure(ctx, n + 1); applied.ensure(ctx, n); dev_memset(ctx, applied.p, 1, n);
-  scan_exclusive(ctx, scanTmp, nOps.p, opBase.p, n); scan_exclusive(ctx, scanTmp, nPreds.p, predBase.p, n);
-  const size_t M = readU32(opBase.p + n), P = readU32(predBase.p + n);
+  const size_t M = tot[0];
   DBuf<u32>* cols[12] = {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff};
-  for (auto* b : cols) b->ensure(ctx, M + 1);
-  r_predActor.ensure(ctx, P + 1); r_predCtr.ensure(ctx, P + 1);
-  RawRows raw{r_objActor.p, r_objCtr.p, r_keyActor.p, r_keyCtr.p, r_keyStrOff.p, r_keyStrLen.p, r_insert.p, r_action.p, r_valLen.p, r_valOff.p, r_predNum.p, r_predOff.p, r_predActor.p, r_predCtr.p};
-  foreach(ctx, n, DecodeSmallKernel{ar.p, meta.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
-  largeFlag.ensure(ctx, n + 1); largeSlot.ensure(ctx, n + 2); largeList.ensure(ctx, n + 1);
-  foreach(ctx, n, LargeFlagKernel{meta.p, applied.p, largeFlag.p});
-  scan_exclusive(ctx, scanTmp, largeFlag.p, largeSlot.p, n);
-  const size_t nl = readU32(largeSlot.p + n);
-  if (nl > 0) {
-    foreach(ctx, n, CompactKernel{largeFlag.p, largeSlot.p, largeList.p});
-    foreach(ctx, (size_t)NCOLS * nl, DecodeColumnKernel{ar.p, n, largeList.p, nl, meta.p, colOff.p, colLen.p, opBase.p, predBase.p, applied.p, raw, errWord.p});
+  RawRows raw = rawRows();
+  if (tot[3]) {
+    largeFlag.ensure(ctx, n + 1); largeSlot.ensure(ctx, n + 2); largeList.ensure(ctx, n + 1);
+    foreach(ctx, n, LargeFlagKernel{nOps.p, applied.p, largeFlag.p});
+    scan_exclusive(ctx, scanTmp, largeFlag.p, largeSlot.p, n);
+    const size_t nl = readU32(largeSlot.p + n);
+    if (nl > 0) {
+      foreach(ctx, n, CompactKernel{largeFlag.p, largeSlot.p, largeList.p});
+      foreach(ctx, (size_t)NCOLS * nl, DecodeColumnKernel{ar.p, largeList.p, nl, hot.p, nOps.p, nPreds.p, rawBase.p, rawPredBase.p, applied.p, raw, errWord.p});
+    }
   }
+  foreach(ctx, n, RaiseDecErrKernel{decErr.p, errWord.p});
   checkErr(actorIds);
   d2h(ctx, hashesOut, hashTmp.p, n * 32); d2h(ctx, nOpsOut, nOps.p, n * 4);
   u32* rows = (u32*)malloc(sizeof(u32) * 12 * (M + 1));
@@ -1197,7 +1238,7 @@ inline void Engine::saveDocument(std::string& result) {
       const size_t tcap = pow2_at_least(2 * C + 2);
       hashTable.ensure(ctx, tcap); dev_memset(ctx, hashTable.p, 0xff, tcap * 4);
       foreach(ctx, C, HashInsertKernel{hashes.p, hashTable.p, (u64)tcap - 1});
-      foreach(ctx, K, ResolveDepsKernel{arena.p, hashes.p, hashTable.p, (u64)tcap - 1, meta.p, L, depBase.p, depIdx.p, primary.p});
+      foreach(ctx, K, ResolveDepsKernelT<ChangeMeta>{arena.p, hashes.p, hashTable.p, (u64)tcap - 1, meta.p, nDeps.p, L, depBase.p, depIdx.p, primary.p});
     }
     auto loadedCol = [&](u32 id) -> const HostChange& { static const u32 IDS[9] = {0x01, 0x03, 0x13, 0x23, 0x35, 0x40, 0x43, 0x56, 0x57}; for (int k = 0; k < 9; k++) if (IDS[k] == id) return loadedCols[k]; return loadedCols[0]; };
     if (L > 0) {   // number of dependency indexes the loaded changes carry

@@ -53,13 +53,13 @@ HD u32 hash_lookup(const u8* hashes, const u32* table, u64 mask, const u8* h32 /
 }
 
 // per batch change: primary[b] = smallest global index with the same hash; resolves dependency hashes
-struct ResolveDepsKernel {
-  const u8* arena; const u8* hashes; const u32* table; u64 mask; const ChangeMeta* meta; size_t numApplied;
+template <class Meta> struct ResolveDepsKernelT {   // Meta: ChangeHot (apply) or ChangeMeta (save)
+  const u8* arena; const u8* hashes; const u32* table; u64 mask; const Meta* meta; const u32* nDeps; size_t numApplied;
   const u32* depBase; u32* depIdx; u32* primary;
   HD void operator()(size_t b) const {
     const size_t g = numApplied + b;
     primary[b] = hash_lookup(hashes, table, mask, hashes + g * 32);
-    const u32 n = meta[b].nDeps, base = depBase[b];
+    const u32 n = nDeps[b], base = depBase[b];
     for (u32 j = 0; j < n; j++) {
       u64 tmp[4]; const u8* src = arena + meta[b].depsOff + 32 * j;
       for (int k = 0; k < 4; k++) tmp[k] = load_u64_unaligned(src + 8 * k);
@@ -68,13 +68,15 @@ struct ResolveDepsKernel {
   }
 };
 
+typedef ResolveDepsKernelT<ChangeHot> ResolveDepsKernel;
+
 // one relaxation sweep; pass[b] starts at 1 for candidates, PASS_INF for changes that can never apply
 struct RelaxKernel {
-  const u32* depBase; const u32* depIdx; const ChangeMeta* meta; const u32* primary; size_t numApplied; u32* pass; u32* changed; u32 maxPass;
+  const u32* depBase; const u32* depIdx; const u32* nDeps; const u32* primary; size_t numApplied; u32* pass; u32* changed; u32 maxPass;
   HD void operator()(size_t b) const {
     const size_t g = numApplied + b;
     if (primary[b] != (u32)g) return;   // duplicate of an applied change or of an earlier batch entry
-    u32 p = 1; const u32 n = meta[b].nDeps, base = depBase[b];
+    u32 p = 1; const u32 n = nDeps[b], base = depBase[b];
     for (u32 j = 0; j < n; j++) {
       const u32 d = depIdx[base + j];
       if (d == DEP_MISSING) { p = PASS_INF; break; }
@@ -99,10 +101,10 @@ struct GateBestKernel {
   HD void operator()(size_t b) const { if (primary[b] < numApplied) return; atomic_min(&best[primary[b] - numApplied], ((u64)pass[b] << 32) | (u64)b); }
 };
 struct RelaxCopiesKernel {
-  const u32* depBase; const u32* depIdx; const ChangeMeta* meta; const u32* primary; size_t numApplied; const u64* best; u32* pass; u32* changed; u32 maxPass;
+  const u32* depBase; const u32* depIdx; const u32* nDeps; const u32* primary; size_t numApplied; const u64* best; u32* pass; u32* changed; u32 maxPass;
   HD void operator()(size_t b) const {
     if (primary[b] < numApplied) return;   // a copy of an applied change
-    u32 p = 1; const u32 n = meta[b].nDeps, base = depBase[b];
+    u32 p = 1; const u32 n = nDeps[b], base = depBase[b];
     for (u32 j = 0; j < n; j++) {
       const u32 d = depIdx[base + j];
       if (d == DEP_MISSING) { p = PASS_INF; break; }
@@ -148,7 +150,7 @@ HD u32 actor_find(const ActorSlot* slots, u64 mask, u64 h) {
 }
 // authors of applied changes claim slots; first (smallest application rank) appearance is recorded
 struct ActorInternKernel {
-  const u8* arena; const ChangeMeta* meta; const u8* applied; const u32* appRank; ActorSlot* slots; u64 mask; u32* authorSlot;
+  const u8* arena; const ChangeHot* meta; const u8* applied; const u32* appRank; ActorSlot* slots; u64 mask; u32* authorSlot;
   HD void operator()(size_t b) const {
     if (!applied[b]) { authorSlot[b] = EMPTY32; return; }
     const u64 h = fnv1a64(arena + meta[b].actorOff, meta[b].actorLen);
@@ -160,7 +162,7 @@ struct ActorInternKernel {
 };
 // resolves every (change, local actor index) to a slot; verifies bytes against the representative
 struct ActorMapKernel {
-  const u8* arena; const ChangeMeta* meta; const u8* applied; const u32* appRank; const ActorSlot* slots; u64 mask;
+  const u8* arena; const ChangeHot* meta; const u32* nActors; const u8* applied; const u32* appRank; const ActorSlot* slots; u64 mask;
   const u32* amapBase; u32* amap /* actorNum per (change, local index) */; u64* errWord;
   HD bool bytesEq(const u8* a, u32 la, const ActorSlot& s) const {
     if (la != s.repLen) return false;
@@ -171,7 +173,7 @@ struct ActorMapKernel {
     if (!applied[b]) return;
     const u32 base = amapBase[b];
     ByteReader r(arena, meta[b].otherOff, meta[b].off + meta[b].len);
-    for (u32 k = 0; k <= meta[b].nOther; k++) {
+    for (u32 k = 0; k < nActors[b]; k++) {
       u32 off, len;
       if (k == 0) { off = meta[b].actorOff; len = meta[b].actorLen; }
       else { len = (u32)r.uleb(); off = r.pos; r.skip(len); }
@@ -200,41 +202,46 @@ static const u32 F_INSERT = 1u;
 HD u32 flags_action(u32 f) { return (f >> 8) & 0xffffu; }
 
 struct FinalizeOpsKernel {
-  size_t numChanges; const ChangeMeta* meta; const u32* opBase; const u32* timeBase /* per change: first op's application time */;
+  size_t numChanges; const ChangeHot* meta; const u32* nActors; const u32* opBase /* first op of each applied change (masked scan) */;
+  const u32* predBase; const u32* rawBase /* first raw row of each change (every change of the batch) */; const u32* rawPredBase;
+  const u32* timeBase /* per change: first op's application time */;
   const u32* amapBase; const u32* amap; const u8* applied; RawRows raw; OpRows rows; u64* errWord;
   // binary search: change of op i
   HD size_t changeOf(u32 i) const {
-    size_t lo = 0, hi = numChanges;   // largest c with opBase[c] <= i and meta[c].nOps > 0 covering i
+    size_t lo = 0, hi = numChanges;   // largest c with opBase[c] <= i (changes without ops share their successor's base)
     while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (opBase[mid] <= i) lo = mid; else hi = mid; }
     return lo;
   }
   HD u32 actorOf(size_t c, u32 local, bool& bad) const {
-    if (local > meta[c].nOther) { bad = true; return 0; }
+    if (local >= nActors[c]) { bad = true; return 0; }
     return amap[amapBase[c] + local];
   }
   HD void operator()(size_t i) const {
     const size_t c = changeOf((u32)i);
     const u32 k = (u32)i - opBase[c]; bool bad = false;
+    const u32 r = rawBase[c] + k;   // raw rows are in batch order for every change; ops in application-masked order
     const u32 author = amap[amapBase[c]];
-    rows.id[i] = pack_id(meta[c].startOp + k, author);
+    const u64 startOp = meta[c].startOp;
+    rows.id[i] = pack_id(startOp + k, author);
     rows.change[i] = (u32)c; rows.time[i] = timeBase[c] + k;
-    const u32 oa = raw.objActor[i], oc = raw.objCtr[i];
+    const u32 oa = raw.objActor[r], oc = raw.objCtr[r];
     if ((oc == NULL32) != (oa == NULL32)) raise(errWord, KE_OBJ_MISMATCH, c);
     rows.obj[i] = oc == NULL32 ? 0 : pack_id(oc, actorOf(c, oa == NULL32 ? 0 : oa, bad));
-    const u32 ka = raw.keyActor[i], kc = raw.keyCtr[i];
+    const u32 ka = raw.keyActor[r], kc = raw.keyCtr[r];
     if ((kc == NULL32 && ka != NULL32) || (kc == 0 && ka != NULL32) || (kc != NULL32 && kc > 0 && ka == NULL32)) raise(errWord, KE_KEY_MISMATCH, c);
     rows.key[i] = (kc == NULL32 || kc == 0 || ka == NULL32) ? 0 : pack_id(kc, actorOf(c, ka, bad));
-    rows.keyStrOff[i] = raw.keyStrOff[i]; rows.keyStrLen[i] = raw.keyStrLen[i];
-    const u32 act = raw.action[i];
-    rows.flags[i] = (raw.insert[i] ? F_INSERT : 0) | ((act == NULL32 ? 0xffffu : (act > 0xfffe ? 0xfffeu : act)) << 8);
-    rows.valLen[i] = raw.valLen[i] == NULL32 ? 0 : raw.valLen[i]; rows.valOff[i] = raw.valOff[i];
-    rows.predOff[i] = raw.predOff[i]; rows.predNum[i] = raw.predNum[i];
-    for (u32 j = 0; j < raw.predNum[i]; j++) {
-      const u32 p = raw.predOff[i] + j; const u32 pa = raw.predActor[p], pc = raw.predCtr[p];
-      rows.predId[p] = (pa == NULL32 || pc == NULL32) ? 0 : pack_id(pc, actorOf(c, pa, bad));
+    rows.keyStrOff[i] = raw.keyStrOff[r]; rows.keyStrLen[i] = raw.keyStrLen[r];
+    const u32 act = raw.action[r];
+    rows.flags[i] = (raw.insert[r] ? F_INSERT : 0) | ((act == NULL32 ? 0xffffu : (act > 0xfffe ? 0xfffeu : act)) << 8);
+    rows.valLen[i] = raw.valLen[r] == NULL32 ? 0 : raw.valLen[r]; rows.valOff[i] = raw.valOff[r];
+    const u32 pn = raw.predNum[r], pr = raw.predOff[r], po = pr - rawPredBase[c] + predBase[c];
+    rows.predOff[i] = po; rows.predNum[i] = pn;
+    for (u32 j = 0; j < pn; j++) {
+      const u32 pa = raw.predActor[pr + j], pc = raw.predCtr[pr + j];
+      rows.predId[po + j] = (pa == NULL32 || pc == NULL32) ? 0 : pack_id(pc, actorOf(c, pa, bad));
     }
     if (bad) raise(errWord, KE_ACTOR_INDEX, c);
-    if (meta[c].startOp + k >= (1ULL << 47)) raise(errWord, KE_TOO_LARGE, c);
+    if (startOp + k >= (1ULL << 47)) raise(errWord, KE_TOO_LARGE, c);
   }
 };
 

@@ -20,11 +20,14 @@ struct MaskedCountKernel { const u32* v; const u8* applied; u32* out; HD void op
 // general (multi-pass) order: ops of change b start at time 1 + (ops of changes applied before b)
 struct OpsInOrderKernel { const u32* nOps; const u8* applied; const u32* appRank; u32* tmp; HD void operator()(size_t b) const { if (applied[b]) tmp[appRank[b]] = nOps[b]; } };
 struct TimeBaseKernel { const u32* scanned; const u8* applied; const u32* appRank; const u32* opBase; int inOrder; u32* timeBase; HD void operator()(size_t b) const { timeBase[b] = applied[b] ? (inOrder ? opBase[b] : scanned[appRank[b]]) + 1 : 0; } };
-struct MaxOpKernel { const ChangeMeta* meta; const u8* applied; u64* maxOp; HD void operator()(size_t b) const { u64 v = 0; if (applied[b] && meta[b].nOps > 0) v = meta[b].startOp + meta[b].nOps - 1; warp_agg_max(maxOp, v); } };   // one atomic per warp
+// also raises what the decode kernel found wrong inside the columns of a change that is applied (the reference decodes the
+// columns of a change when it applies it, new.js:686-700; a change that stays in the queue is not looked into)
+struct MaxOpKernel { const ChangeHot* meta; const u32* nOps; const u8* applied; const u32* decErr; u64* maxOp; u64* errWord; HD void operator()(size_t b) const { u64 v = 0; if (applied[b] && nOps[b] > 0) v = meta[b].startOp + nOps[b] - 1; if (applied[b] && decErr[b]) raise(errWord, decErr[b], b); warp_agg_max(maxOp, v); } };   // one atomic per warp
 
+struct RaiseDecErrKernel { const u32* decErr; u64* errWord; HD void operator()(size_t b) const { if (decErr[b]) raise(errWord, decErr[b], b); } };
 // new actors: the applied change with the smallest application rank per fresh slot registers the representative bytes
 struct NewActorKernel {
-  const ChangeMeta* meta; const u8* applied; const u32* authorSlot; ActorSlot* slots; u32* newSlots; u32* newCount;
+  const ChangeHot* meta; const u8* applied; const u32* authorSlot; ActorSlot* slots; u32* newSlots; u32* newCount;
   HD void operator()(size_t b) const {
     if (!applied[b]) return;
     ActorSlot& s = slots[authorSlot[b]];
@@ -45,7 +48,7 @@ struct ChangeActorKernel { const u32* amapBase; const u32* amap; const u8* appli
 // seq == clock + 1 in application order (new.js:1559, 1571-1579): the seqs of an actor's applied changes must be
 // exactly clock+1 .. clock+count, in increasing application order
 struct SeqScatterKernel {
-  const ChangeMeta* meta; const u8* applied; const u32* changeActor; const u32* appRank; const u32* actorBase; const u32* actorCnt; const u64* clock; u32* seqSlot; u32* bad;
+  const ChangeHot* meta; const u8* applied; const u32* changeActor; const u32* appRank; const u32* actorBase; const u32* actorCnt; const u64* clock; u32* seqSlot; u32* bad;
   HD void operator()(size_t b) const {
     if (!applied[b]) return;
     const u32 a = changeActor[b]; const u64 seq = meta[b].seq, c0 = clock[a];
@@ -54,7 +57,7 @@ struct SeqScatterKernel {
   }
 };
 struct SeqMonoKernel {
-  const ChangeMeta* meta; const u8* applied; const u32* changeActor; const u32* actorBase; const u64* clock; const u32* seqSlot; u32* bad;
+  const ChangeHot* meta; const u8* applied; const u32* changeActor; const u32* actorBase; const u64* clock; const u32* seqSlot; u32* bad;
   HD void operator()(size_t b) const {
     if (!applied[b]) return;
     const u32 a = changeActor[b]; const u64 idx = meta[b].seq - clock[a] - 1;
@@ -62,7 +65,7 @@ struct SeqMonoKernel {
   }
 };
 // heads (new.js:1582-1583): every dependency of an applied change stops being a head
-struct MarkDepsKernel { const u8* applied; const ChangeMeta* meta; const u32* depBase; const u32* depIdx; u32* isDep; HD void operator()(size_t b) const { if (!applied[b]) return; for (u32 j = 0; j < meta[b].nDeps; j++) { const u32 d = depIdx[depBase[b] + j]; if (d != DEP_MISSING) isDep[d] = 1; } } };
+struct MarkDepsKernel { const u8* applied; const u32* nDeps; const u32* depBase; const u32* depIdx; u32* isDep; HD void operator()(size_t b) const { if (!applied[b]) return; for (u32 j = 0; j < nDeps[b]; j++) { const u32 d = depIdx[depBase[b] + j]; if (d != DEP_MISSING) isDep[d] = 1; } } };
 struct HeadFlag2Kernel { const u8* applied; const u32* isDep; size_t numApplied; u32* flag; HD void operator()(size_t b) const { flag[b] = (applied[b] && !isDep[numApplied + b]) ? 1u : 0u; } };
 struct CompactKernel { const u32* flag; const u32* slot; u32* out; HD void operator()(size_t i) const { if (flag[i]) out[slot[i]] = (u32)i; } };
 struct HashGatherKernel { const u8* src; const u8* applied; const u32* appRank; u8* dst; HD void operator()(size_t b) const { if (!applied[b]) return; const u64* s = reinterpret_cast<const u64*>(src + b * 32); u64* d = reinterpret_cast<u64*>(dst + (size_t)appRank[b] * 32); d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; } };

@@ -216,7 +216,7 @@ def main():
             # the HBM-bound part of the decode: header parse + column expansion. SHA-256 over the same bytes is
             # ALU-bound (64 rounds per 64-byte block) and is reported next to it, not folded into the HBM figure.
             t_dec = (ms_parse.value + ms_dec.value) / 1e3
-            kernel_name = 'column decode = ParseKernel + DecodeSmallKernel (+ DecodeColumnKernel for large changes)'
+            kernel_name = 'column decode = k_decode_tiles (fused header parse + column expansion, bulk-staged through shared memory) + DecodeColumnKernel for changes of more than 16 ops'
             ach = algo.value / t_dec / 1e9
             n_blocks = (trace.blob.size + 64 * trace.n_changes) / 64.0          # ~ message blocks incl. padding
             roofline = {'bound': 'hbm', 'kernel': kernel_name,
