@@ -258,8 +258,8 @@ int amg_debug_dump_ops(amg_backend* b, uint64_t** rows_out, size_t* n, uint64_t*
     *rows_out = (uint64_t*)r; *n = N; *succ_out = (uint64_t*)s; *m = S; return 0;)
 }
 
-int amg_debug_decode(amg_backend* b, const uint8_t* blob, const uint64_t* offsets, size_t n, uint8_t* hashes_out, uint32_t* n_ops_out, uint32_t** rows_out, size_t* total_ops, amg_error* err) {
-  AMG_GUARD(b->eng.decodeRaw(blob, (const u64*)offsets, n, hashes_out, n_ops_out, rows_out, total_ops); return 0;)
+int amg_debug_decode(amg_backend* b, const uint8_t* blob, const uint64_t* offsets, size_t n, uint8_t* hashes_out, uint32_t* n_ops_out, uint32_t** rows_out, size_t* total_ops, size_t* total_preds, amg_error* err) {
+  AMG_GUARD(b->eng.decodeRaw(blob, (const u64*)offsets, n, hashes_out, n_ops_out, rows_out, total_ops, total_preds); return 0;)
 }
 int amg_debug_decode_column(amg_backend* b, const uint8_t* bytes, size_t len, int kind, size_t n, int parallel, int64_t* out, amg_error* err) {
   AMG_GUARD(return b->eng.debugDecodeColumn(bytes, len, kind, n, parallel != 0, (long long*)out);)

@@ -70,7 +70,10 @@ struct ChangeMeta {
 // copy of its byte range (decode tile kernel). `pos` is always an absolute arena offset.
 struct PtrSrc { const u8* base; HD u32 ld(u32 pos) const { return base[pos]; } };
 #ifndef AMG_EMU
-struct SmemSrc { const u8* s; u32 shift; DEV u32 ld(u32 pos) const { return s[pos - shift]; } };   // s[0] holds arena byte `shift`
+// sbase = 32-bit shared-memory address that holds arena byte 0 of this view (stage address - first staged arena offset); an
+// explicit ld.shared: through a pointer the compiler lost the address space in most of the parser and emitted generic loads
+// (L1TEX path, long scoreboard) for what is a shared-memory read
+struct SmemSrc { u32 sbase; DEV u32 ld(u32 pos) const { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sbase + pos)); return v; } };
 #endif
 
 template <class S> struct ByteReaderT {
@@ -79,11 +82,15 @@ template <class S> struct ByteReaderT {
   HD bool done() const { return pos >= end; }
   // encoding.js:416-441 readUint64 + :389-395 53-bit range check
   HD u64 uleb() {
-    if (pos + 1 < end) {   // one- and two-byte values (nearly all of them) without the 64-bit loop
+    if (pos + 3 < end) {   // values of up to four bytes (28 bits: nearly all of them) in 32-bit arithmetic, without the 64-bit loop
       const u32 b0 = src.ld(pos);
       if (!(b0 & 0x80)) { pos++; return b0; }
-      const u32 b1 = src.ld(pos + 1);
-      if (!(b1 & 0x80)) { pos += 2; return (b0 & 0x7f) | (b1 << 7); }
+      const u32 b1 = src.ld(pos + 1); u32 v = (b0 & 0x7f) | ((b1 & 0x7f) << 7);
+      if (!(b1 & 0x80)) { pos += 2; return v; }
+      const u32 b2 = src.ld(pos + 2); v |= (b2 & 0x7f) << 14;
+      if (!(b2 & 0x80)) { pos += 3; return v; }
+      const u32 b3 = src.ld(pos + 3); v |= (b3 & 0x7f) << 21;
+      if (!(b3 & 0x80)) { pos += 4; return v; }
     }
     u64 result = 0; int shift = 0;
     while (pos < end) {
@@ -524,12 +531,13 @@ struct ParsedChange {
 template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedChange& o) {
   o.h.off = off; o.h.len = len; o.h.depsOff = o.h.actorOff = o.h.actorLen = o.h.otherOff = o.h.dirOff = o.h.dataOff = 0; o.h.startOp = 0; o.h.seq = 0;
   o.nDeps = 0; o.nOther = 0; o.nOps = 0; o.nPreds = 0; o.err = 0; o.single = false;
-  ByteReaderT<S> r(src, off + 8, off + len);
+  const u32 end = off + len;
+  ByteReaderT<S> r(src, off + 8, end);
   const u32 chunkType = r.done() ? 0xffu : src.ld(r.pos); r.pos++;
   const u64 chunkLen = r.uleb();
   if (r.err) { o.err = r.err; return; }
-  if ((u64)r.pos + chunkLen > (u64)off + len) { o.err = KE_TRUNCATED; return; }
-  if ((u64)r.pos + chunkLen != (u64)off + len) { o.err = KE_TRAILING; return; }
+  if ((u64)r.pos + chunkLen > (u64)end) { o.err = KE_TRUNCATED; return; }
+  if ((u64)r.pos + chunkLen != (u64)end) { o.err = KE_TRAILING; return; }
   if (chunkType != 1) { o.err = KE_CHUNK_TYPE; return; }
   const u64 nDeps = r.uleb(); const u32 depsOff = r.pos; r.skip(nDeps * 32);
   const u64 actorLen = r.uleb(); const u32 actorOff = r.pos; r.skip(actorLen);
@@ -539,50 +547,56 @@ template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedCh
   for (u64 i = 0; i < nOther && !r.err; i++) { const u64 l = r.uleb(); r.skip(l); }
   const u64 nCols = r.uleb();
   if (r.err) { o.err = r.err; return; }
-  // column directory: ids ascending (ignoring the deflate bit, which a change must not carry); single-value columns are
-  // decoded on the way (their data position is the running sum of the lengths seen so far + the directory's end, which
-  // is not known yet: positions are kept relative to the data start and the bytes are read in a second, short loop)
-  const u32 dirPos = r.pos; long long lastId = -1; u64 total = 0;
-  u32 actOff = 0, actLen = 0, pnOff = 0, pnLen = 0; bool haveAct = false;
-  for (u64 i = 0; i < nCols && !r.err; i++) {
-    const u64 id = r.uleb(), l = r.uleb();
-    if (lastId >= 0 && ((u32)id & ~8u) <= ((u32)lastId & ~8u)) { o.err = KE_COL_ORDER; return; }
-    if (id & 8) { o.err = KE_COL_DEFLATE; return; }
-    if (id == 0x42) { actOff = (u32)total; actLen = (u32)l; haveAct = true; } else if (id == 0x70) { pnOff = (u32)total; pnLen = (u32)l; }
-    lastId = (long long)id; total += l;
-  }
-  if (r.err) { o.err = r.err; return; }
-  const u32 dataPos = r.pos;
-  if ((u64)dataPos + total > (u64)off + len) { o.err = KE_TRUNCATED; return; }
-  // single-op changes (the shape of editing traces): one pass over directory + data fills the row; anything that is not
-  // exactly one canonical value per column leaves `single` false
-  bool single = haveAct; SingleVals sv;
-  sv.objActor = sv.objCtr = sv.keyActor = sv.keyCtr = sv.action = sv.valLen = sv.keyStrLen = NULL32; sv.keyStrOff = 0; sv.insert = 0; sv.valOff = 0; sv.predNum = 0; sv.predActor = sv.predCtr = NULL32;
-  {
-    ByteReaderT<S> d(src, dirPos, dataPos); u32 pos = dataPos; bool afterValLen = false; u32 valBytes = 0, rawLen = 0; bool sawPredA = false, sawPredC = false;
-    for (u64 i = 0; i < nCols && single; i++) {
-      const u32 id = (u32)d.uleb(), l = (u32)d.uleb(); const int ix = col_index_of(id);
+  // Column directory and - for single-op changes, the shape of editing traces - the row itself in ONE walk. The data of
+  // column k starts at (end of the directory) + (lengths of the columns before it); the end of the directory is guessed
+  // as 2 bytes per entry (ids and lengths below 128) and the walk is repeated with the real value if the guess was wrong.
+  // Checks in the reference's order: column ids ascending over the whole directory (decodeColumnInfo), then per column
+  // "no deflated columns" and "bytes present" (decodeChangeColumns).
+  const u32 dirPos = r.pos; u32 dataPos = nCols < len ? dirPos + 2 * (u32)nCols : end;
+  u32 actOff = 0, actLen = 0, pnOff = 0, pnLen = 0; bool haveAct = false, single = false; SingleVals sv; u32 dirErr = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    ByteReaderT<S> d(src, dirPos, end); long long lastId = -1; u64 total = 0; u32 colErr = 0; bool orderBad = false;
+    single = true; haveAct = false; actLen = pnLen = 0;
+    sv.objActor = sv.objCtr = sv.keyActor = sv.keyCtr = sv.action = sv.valLen = sv.keyStrLen = NULL32; sv.keyStrOff = 0; sv.insert = 0; sv.valOff = 0; sv.predNum = 0; sv.predActor = sv.predCtr = NULL32;
+    bool afterValLen = false, sawPred = false; u32 valBytes = 0, rawLen = 0;
+    for (u64 i = 0; i < nCols; i++) {
+      const u64 id64 = d.uleb(), l64 = d.uleb();
+      if (d.err) break;
+      if (lastId >= 0 && ((u32)id64 & ~8u) <= ((u32)lastId & ~8u)) orderBad = true;
+      lastId = (long long)id64;
+      if (!colErr) { if (id64 & 8) colErr = KE_COL_DEFLATE; else if ((u64)dataPos + total + l64 > (u64)end) colErr = KE_TRUNCATED; }
+      const u32 id = id64 > 0xffffffffULL ? 0xffffffffu : (u32)id64, l = (u32)l64, pos = dataPos + (u32)total;
+      if (id == 0x42) { actOff = (u32)total; actLen = l; haveAct = true; } else if (id == 0x70) { pnOff = (u32)total; pnLen = l; }
       if (afterValLen) { afterValLen = false; if (id == 0x57) { sv.valOff = pos; rawLen = l; } }
-      if (ix >= 0 && ix != CX_VAL_RAW && ix != CX_CHLD_ACTOR && ix != CX_CHLD_CTR) {
-        u32 v = 0, used = 0; bool isNull = false;
-        if (!single_value(src, ix, pos, l, v, isNull, used)) { single = false; break; }
-        switch (ix) {
-          case CX_OBJ_ACTOR: sv.objActor = isNull ? NULL32 : v; break; case CX_OBJ_CTR: sv.objCtr = isNull ? NULL32 : v; break;
-          case CX_KEY_ACTOR: sv.keyActor = isNull ? NULL32 : v; break; case CX_KEY_CTR: sv.keyCtr = isNull ? NULL32 : v; break;
-          case CX_KEY_STR: sv.keyStrOff = isNull ? 0 : pos + 2; sv.keyStrLen = isNull ? NULL32 : v; break;
-          case CX_INSERT: sv.insert = v; break; case CX_ACTION: sv.action = isNull ? NULL32 : v; break;
-          case CX_VAL_LEN: sv.valLen = isNull ? NULL32 : v; valBytes = isNull ? 0 : (v >> 4); afterValLen = true; break;
-          case CX_PRED_NUM: sv.predNum = isNull ? 0 : v; if (sv.predNum > 1) single = false; break;
-          case CX_PRED_ACTOR: sv.predActor = isNull ? NULL32 : v; sawPredA = true; break;
-          case CX_PRED_CTR: sv.predCtr = isNull ? NULL32 : v; sawPredC = true; break;
-          default: break;
+      if (single && !colErr) {
+        const int ix = col_index_of(id);
+        if (ix >= 0 && ix != CX_VAL_RAW && ix != CX_CHLD_ACTOR && ix != CX_CHLD_CTR) {
+          u32 v = 0, used = 0; bool isNull = false;
+          if (!single_value(src, ix, pos, l, v, isNull, used)) single = false;
+          else switch (ix) {
+            case CX_OBJ_ACTOR: sv.objActor = isNull ? NULL32 : v; break; case CX_OBJ_CTR: sv.objCtr = isNull ? NULL32 : v; break;
+            case CX_KEY_ACTOR: sv.keyActor = isNull ? NULL32 : v; break; case CX_KEY_CTR: sv.keyCtr = isNull ? NULL32 : v; break;
+            case CX_KEY_STR: sv.keyStrOff = isNull ? 0 : pos + 2; sv.keyStrLen = isNull ? NULL32 : v; break;
+            case CX_INSERT: sv.insert = v; break; case CX_ACTION: sv.action = isNull ? NULL32 : v; break;
+            case CX_VAL_LEN: sv.valLen = isNull ? NULL32 : v; valBytes = isNull ? 0 : (v >> 4); afterValLen = true; break;
+            case CX_PRED_NUM: sv.predNum = isNull ? 0 : v; if (sv.predNum > 1) single = false; break;
+            case CX_PRED_ACTOR: sv.predActor = isNull ? NULL32 : v; sawPred = true; break;
+            case CX_PRED_CTR: sv.predCtr = isNull ? NULL32 : v; sawPred = true; break;
+            default: break;
+          }
         }
       }
-      pos += l;
+      total += l64;
     }
-    if (single && valBytes > rawLen) single = false;   // the general decoder reports it
-    if (single && sv.predNum == 0 && (sawPredA || sawPredC)) single = false;   // values without a pred to belong to: general path ignores them
+    if (d.err) { dirErr = d.err; break; }
+    if (d.pos != dataPos) { dataPos = d.pos; if (attempt == 0) continue; }   // directory longer than guessed: once more, with its real end
+    if (orderBad) dirErr = KE_COL_ORDER; else if (colErr) dirErr = colErr;
+    if (valBytes > rawLen) single = false;                 // the general decoder reports it
+    if (sv.predNum == 0 && sawPred) single = false;        // pred values without a pred: the general decoder skips them
+    if (!haveAct) single = false;
+    break;
   }
+  if (dirErr) { o.err = dirErr; return; }
   u32 kerr = 0; u32 nOps = 0; u64 nPreds = 0;
   if (single) { nOps = 1; nPreds = sv.predNum; }
   else {
@@ -625,10 +639,12 @@ template <class S> HD u32 expand_change(const S& src, const ChangeHot& h, u32 nO
 struct DecodeTilesArgs {
   const u8* arena; const u32* chOff; const u32* chLen; u32 B;
   ChangeHot* hot; u32* nOps; u32* nPreds; u32* nDeps; u32* nActors;
-  u32* rawBase /* [B+1] first raw row of each change (batch order, every change) */; u32* rawPredBase /* [B+1] */;
+  u32* rawBase /* [B] first raw row of each change (every change of the batch) */; u32* rawPredBase /* [B] */;
   u32* decErr /* [B] KErr of the column contents: raised only if the change is applied (the reference decodes columns lazily) */;
   RawRows rows; u32 rowCap, predCap;   // rows are written only inside the capacity; totals[2] tells the host to grow and run again
-  u64* tileState; u32* ticket; u32* totals /* [0] ops [1] preds [2] overflow [3] some change has > SMALL_CHANGE_OPS ops */; u64* errWord; u32 numTiles;
+  unsigned long long* cursor /* [0] ops, [1] preds handed out so far */;
+  u32* totals /* [2] overflow [3] some change has > SMALL_CHANGE_OPS ops; [0] ops and [1] preds are filled from the cursor by k_decode_totals */; u64* errWord; u32 numTiles;
+  u32* directList /* [B] changes the staged kernel could not take (outside their tile's staged window) */; u32* directCount;
 };
 // what one thread does with its change once the row range is known
 template <class S> HD void finish_change(const DecodeTilesArgs& a, const S& src, u32 c, const ParsedChange& pc, u32 base, u32 pb) {
@@ -647,13 +663,16 @@ template <class S> HD void finish_change(const DecodeTilesArgs& a, const S& src,
 
 #ifdef AMG_EMU
 inline void decode_tiles(Ctx& c, const DecodeTilesArgs& a) {
+  // tiles of 4 changes, last tile first: raw rows are NOT in batch order on the device either (tiles take their row range
+  // from a cursor in arrival order), so the emulation makes sure nothing downstream relies on it
   u64 ops = 0, preds = 0; a.totals[0] = a.totals[1] = a.totals[2] = a.totals[3] = 0;
-  for (u32 i = 0; i < a.B; i++) {
+  const u32 T = 4, numTiles = (a.B + T - 1) / T;
+  for (u32 t = numTiles; t-- > 0;) for (u32 i = t * T; i < a.B && i < (t + 1) * T; i++) {
     ParsedChange pc; parse_change(PtrSrc{a.arena}, a.chOff[i], a.chLen[i], pc);
     finish_change(a, PtrSrc{a.arena}, i, pc, (u32)std::min<u64>(ops, 0x7fffffffu), (u32)std::min<u64>(preds, 0x7fffffffu));
     ops += pc.nOps; preds += pc.nPreds;
   }
-  a.rawBase[a.B] = a.totals[0] = (u32)std::min<u64>(ops, 0x7fffffffu); a.rawPredBase[a.B] = a.totals[1] = (u32)std::min<u64>(preds, 0x7fffffffu);
+  a.totals[0] = (u32)std::min<u64>(ops, 0x7fffffffu); a.totals[1] = (u32)std::min<u64>(preds, 0x7fffffffu);
   if (ops > a.rowCap || preds > a.predCap) a.totals[2] = 1;   // rows that larger changes reserved must fit as well
   c.launches++;
 }
@@ -662,49 +681,31 @@ inline void decode_tiles(Ctx& c, const DecodeTilesArgs& a) {
 //  1. the tile's byte range [lo, hi) of the arena is copied into shared memory by ONE bulk asynchronous copy
 //     (cp.async.bulk global -> shared, completion on an mbarrier): every byte of a change crosses HBM -> SM once, in full
 //     lines, and the byte-serial parsers below then read shared memory. 8 CTAs are resident per SM, so the copies of some
-//     tiles are in flight while others parse. Tiles whose range does not fit (big changes, changes that are not stored
-//     back to back: queue entries, inflated changes) read global memory directly.
+//     tiles are in flight while others parse. Changes outside their tile's window (inflated changes, which live behind the
+//     batch; queue entries; changes too big for the window) are handed to k_decode_direct, which reads global memory.
 //  2. every thread parses its change (header, directory, counts; single-op changes keep their row in registers);
-//  3. block scan of (ops, preds) + decoupled look-back across tiles (tickets in launch order) -> first raw row of every change;
+//  3. block scan of (ops, preds); the tile takes its raw row range from a global cursor with one atomic (no tile waits for
+//     another: a decoupled look-back across 7800 tiles advanced at most 32 tiles per L2 round trip and took 0.5 ms);
 //  4. rows are written (single-op: straight from registers, consecutive threads -> consecutive rows; 2..16 ops: second
 //     walk over the shared-memory copy); larger changes only reserve their rows.
-static const int DT_THREADS = 128;
-static const u32 DT_STAGE = 24u << 10;
+#ifndef AMG_DT_THREADS
+#define AMG_DT_THREADS 128
+#endif
+#ifndef AMG_DT_STAGE_KB
+#define AMG_DT_STAGE_KB 24
+#endif
+#ifndef AMG_DT_MINBLOCKS
+#define AMG_DT_MINBLOCKS 8
+#endif
+static const int DT_THREADS = AMG_DT_THREADS;
+static const u32 DT_STAGE = (u32)AMG_DT_STAGE_KB << 10;
 DEV u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 DEV u32 sat31(u64 v) { return v > 0x7fffffffULL ? 0x7fffffffu : (u32)v; }
-__global__ void __launch_bounds__(DT_THREADS, 8) k_decode_tiles(const DecodeTilesArgs a) {
-  __shared__ __align__(128) u8 stage[DT_STAGE];
-  __shared__ __align__(8) unsigned long long bar;
-  __shared__ u32 sTile, sLo, sHi; __shared__ u64 sWarp[2][DT_THREADS / 32]; __shared__ u64 sBase[2];
+// steps 2-4 for the change of this thread; S = where its bytes are read from
+template <class S> DEV void decode_tile_body(const DecodeTilesArgs& a, const S& src, u32 c, bool live, u32 off, u32 len, u64 (*sWarp)[DT_THREADS / 32], u64* sBase) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    sTile = atomicAdd(a.ticket, 1u); sLo = 0xffffffffu; sHi = 0;
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&bar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const u32 tile = sTile; const u32 c = tile * DT_THREADS + tid; const bool live = c < a.B;
-  const u32 off = live ? a.chOff[c] : 0xffffffffu, len = live ? a.chLen[c] : 0;
-  {
-    const u32 lo = __reduce_min_sync(0xffffffffu, off), hi = __reduce_max_sync(0xffffffffu, live ? off + len : 0u);
-    if (lane == 0) { atomicMin(&sLo, lo); atomicMax(&sHi, hi); }
-  }
-  __syncthreads();
-  const u32 lo16 = sLo & ~15u, hi16 = (sHi + 15u) & ~15u;
-  const bool staged = sHi > sLo && hi16 - lo16 <= DT_STAGE;
-  if (staged) {
-    if (tid == 0) {
-      const u32 bytes = hi16 - lo16;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(&bar)), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   :: "r"(smem_addr(stage)), "l"(a.arena + lo16), "r"(bytes), "r"(smem_addr(&bar)) : "memory");
-    }
-    u32 ok = 0;
-    while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_addr(&bar)) : "memory");
-  }
   ParsedChange pc; pc.nOps = pc.nPreds = 0;
-  const SmemSrc ssrc{stage, lo16}; const PtrSrc gsrc{a.arena};
-  if (live) { if (staged) parse_change(ssrc, off, len, pc); else parse_change(gsrc, off, len, pc); }
+  if (live) parse_change(src, off, len, pc);
   // (ops, preds) of the tile: exclusive scan inside the CTA, 64-bit each (a run-length encoded change can hold 2^31 ops)
   u64 vo = live ? pc.nOps : 0, vp = live ? pc.nPreds : 0; u64 io = vo, ip = vp;
 #pragma unroll
@@ -714,46 +715,81 @@ __global__ void __launch_bounds__(DT_THREADS, 8) k_decode_tiles(const DecodeTile
   u64 wo = 0, wp = 0, to = 0, tp = 0;
 #pragma unroll
   for (int w = 0; w < DT_THREADS / 32; w++) { const u64 xo = sWarp[0][w], xp = sWarp[1][w]; if (w < warp) { wo += xo; wp += xp; } to += xo; tp += xp; }
-  if (warp == 0) {   // publish the tile aggregate, look back over the predecessors (32 per step), publish the inclusive prefix
-    volatile u64* st = a.tileState; u64 exo = 0, exp_ = 0;
-    const u64 agg = ((u64)sat31(tp) << 31) | sat31(to);
-    if (lane == 0) st[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | agg;
-    if (tile > 0) {
-      long long p = (long long)tile;
-      while (true) {
-        const long long idx = p - 1 - lane; u32 status = 2; u64 val = 0;
-        if (idx >= 0) { u64 w; do { w = st[idx]; } while ((w >> 62) == 0); status = (u32)(w >> 62); val = w & ((1ull << 62) - 1); }
-        const unsigned inclMask = __ballot_sync(0xffffffffu, status == 2);
-        const int first = inclMask ? __ffs(inclMask) - 1 : 32;
-        u64 co = lane <= first ? (val & 0x7fffffffULL) : 0, cp = lane <= first ? (val >> 31) : 0;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) { co += __shfl_xor_sync(0xffffffffu, co, d); cp += __shfl_xor_sync(0xffffffffu, cp, d); }
-        exo += co; exp_ += cp;
-        if (inclMask) break;
-        p -= 32;
-      }
-      if (lane == 0) st[tile] = (2ull << 62) | ((u64)sat31(exp_ + tp) << 31) | sat31(exo + to);
-    }
-    if (lane == 0) {
-      sBase[0] = exo; sBase[1] = exp_;
-      if (tile == a.numTiles - 1) {
-        a.totals[0] = a.rawBase[a.B] = sat31(exo + to); a.totals[1] = a.rawPredBase[a.B] = sat31(exp_ + tp); *a.ticket = 0;
-        if (exo + to > a.rowCap || exp_ + tp > a.predCap) a.totals[2] = 1;   // rows that larger changes reserved must fit as well
-      }
-    }
+  if (tid == 0) {
+    // The tile takes its raw row range from a global cursor (one atomic per tile; no tile waits for another). Raw rows are
+    // therefore stored in the order in which tiles arrive; FinalizeOpsKernel reads them through rawBase[change], the op
+    // order of the batch comes from the scans over the applied changes.
+    sBase[0] = atomicAdd(&a.cursor[0], (unsigned long long)to); sBase[1] = tp ? atomicAdd(&a.cursor[1], (unsigned long long)tp) : 0;
   }
   __syncthreads();
-  if (live) {
-    const u32 base = sat31(sBase[0] + wo + io - vo), pb = sat31(sBase[1] + wp + ip - vp);
-    if (staged) finish_change(a, ssrc, c, pc, base, pb); else finish_change(a, gsrc, c, pc, base, pb);
+  if (live) finish_change(a, src, c, pc, sat31(sBase[0] + wo + io - vo), sat31(sBase[1] + wp + ip - vp));
+}
+__global__ void __launch_bounds__(DT_THREADS, AMG_DT_MINBLOCKS) k_decode_tiles(const DecodeTilesArgs a) {
+  __shared__ __align__(128) u8 stage[DT_STAGE];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ u32 sLo, sHi; __shared__ u64 sWarp[2][DT_THREADS / 32]; __shared__ u64 sBase[2];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    sLo = 0xffffffffu; sHi = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const u32 c = blockIdx.x * DT_THREADS + tid; bool live = c < a.B;
+  const u32 off = live ? a.chOff[c] : 0xffffffffu, len = live ? a.chLen[c] : 0;
+  // the staged window starts at the tile's lowest offset; changes that do not lie inside it (inflated changes live behind
+  // the batch, a big change may not fit) are passed on to k_decode_direct one by one
+  { const u32 lo = __reduce_min_sync(0xffffffffu, off); if (lane == 0) atomicMin(&sLo, lo); }
+  __syncthreads();
+  const u32 lo16 = sLo & ~15u;
+  const bool inWindow = live && (u64)off + len <= (u64)lo16 + DT_STAGE;
+  { const u32 hi = __reduce_max_sync(0xffffffffu, inWindow ? off + len : 0u); if (lane == 0 && hi) atomicMax(&sHi, hi); }
+  if (live && !inWindow) {
+    const unsigned peers = __activemask(); const int leader = __ffs(peers) - 1; u32 base = 0;
+    if (lane == leader) base = atomicAdd(a.directCount, (u32)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    a.directList[base + __popc(peers & ((1u << lane) - 1))] = c;
+  }
+  __syncthreads();
+  live = inWindow;
+  if (sHi > lo16) {
+    if (tid == 0) {
+      const u32 bytes = ((sHi + 15u) & ~15u) - lo16;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(&bar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(smem_addr(stage)), "l"(a.arena + lo16), "r"(bytes), "r"(smem_addr(&bar)) : "memory");
+    }
+    u32 ok = 0;
+    while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_addr(&bar)) : "memory");
+  }
+  decode_tile_body(a, SmemSrc{smem_addr(stage) - lo16}, c, live, off, len, sWarp, sBase);
+}
+// the changes the staged kernel passed on: same steps, one thread per listed change, bytes read from global memory
+__global__ void __launch_bounds__(DT_THREADS) k_decode_direct(const DecodeTilesArgs a) {
+  __shared__ u64 sWarp[2][DT_THREADS / 32]; __shared__ u64 sBase[2];
+  const u32 n = *a.directCount;
+  for (u32 t = blockIdx.x; t * DT_THREADS < n; t += gridDim.x) {
+    const u32 i = t * DT_THREADS + threadIdx.x; const bool live = i < n; const u32 c = live ? a.directList[i] : 0u;
+    decode_tile_body(a, PtrSrc{a.arena}, c, live, live ? a.chOff[c] : 0u, live ? a.chLen[c] : 0u, sWarp, sBase);
+    __syncthreads();
   }
 }
+static __global__ void k_decode_totals(const DecodeTilesArgs a) {   // cursor -> totals (+ overflow when the reserved rows of larger changes do not fit)
+  if (threadIdx.x) return;
+  const u64 ops = a.cursor[0], preds = a.cursor[1];
+  a.totals[0] = sat31(ops); a.totals[1] = sat31(preds);
+  if (ops > a.rowCap || preds > a.predCap) a.totals[2] = 1;
+}
 inline void decode_tiles(Ctx& c, const DecodeTilesArgs& a) {
-  CUDA_CHECK(cudaMemsetAsync(a.tileState, 0, (size_t)a.numTiles * 8, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(a.cursor, 0, 16, c.stream));
   CUDA_CHECK(cudaMemsetAsync(a.totals, 0, 16, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(a.directCount, 0, 4, c.stream));
   k_decode_tiles<<<a.numTiles, DT_THREADS, 0, c.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
-  c.launches++;
+  k_decode_direct<<<(unsigned)std::min<size_t>(a.numTiles, (size_t)c.numSMs * 8), DT_THREADS, 0, c.stream>>>(a);
+  k_decode_totals<<<1, 32, 0, c.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  c.launches += 3;
 }
 #endif
 inline u32 decode_num_tiles(size_t B) {
@@ -791,6 +827,9 @@ struct DecodeColumnKernel {
 #define AMG_PARSE_MINBLOCKS 4
 #endif
 template <> struct LaunchTraits<ParseKernel> { static const int minBlocks = AMG_PARSE_MINBLOCKS; };
+#ifdef AMG_SHA_MINBLOCKS
+template <> struct LaunchTraits<ShaKernel> { static const int minBlocks = AMG_SHA_MINBLOCKS; };
+#endif
 struct LargeFlagKernel { const u32* nOps; const u8* applied; u32* flag; HD void operator()(size_t c) const { flag[c] = (applied[c] && nOps[c] > SMALL_CHANGE_OPS) ? 1u : 0u; } };
 
 }  // namespace amg

@@ -95,7 +95,7 @@ class Engine {
   // ---- scratch (grow-only)
   DBuf<u32> chOff, chLen, nOps, nPreds, nDeps, nActors, colOff, colLen, depBase, depIdx, primary, pass, flagWord, appRank, opBase, predBase, timeBase, amapBase, amap, authorSlot, newSlots;
   DBuf<u8> applied; DBuf<ChangeHot> hot; DBuf<ChangeMeta> meta /* save(): full headers */; DBuf<u64> errWord; DBuf<u32> hashTable;
-  DBuf<u32> rawBase, rawPredBase, decErr, decTotals; DBuf<u64> tileState; DBuf<u32> tileTicket;   // fused decode (decode.cuh k_decode_tiles)
+  DBuf<u32> rawBase, rawPredBase, decErr, decTotals, decDirect; DBuf<u64> decCursor;   // fused decode (decode.cuh k_decode_tiles)
   DBuf<u32> r_objActor, r_objCtr, r_keyActor, r_keyCtr, r_keyStrOff, r_keyStrLen, r_insert, r_action, r_valLen, r_valOff, r_predNum, r_predOff, r_predActor, r_predCtr;
   DBuf<u64> o_id, o_obj, o_key, o_predId; DBuf<u32> o_keyStrOff, o_keyStrLen, o_flags, o_valLen, o_valOff, o_predOff, o_predNum, o_change, o_time;
   DBuf<u32> isRow, rowSlot, rowOfOp; DocBufs work, sorted;
@@ -279,7 +279,7 @@ class Engine {
   bool decodeOverflowed(const u32 totals[4]);
   void computeHashGraph();   // change history of a loaded document (history.cuh)
   int debugDecodeColumn(const u8* bytes, size_t len, int kind, size_t n, bool parallel, long long* out);
-  void decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* hashesOut, u32* nOpsOut, u32** rowsOut, size_t* totalOps);
+  void decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* hashesOut, u32* nOpsOut, u32** rowsOut, size_t* totalOps, size_t* totalPreds);
   size_t lastB = 0, lastM = 0, lastP = 0, lastBytes = 0;
   size_t decWantRows = 0, decWantPreds = 0, decRowCap = 0, decPredCap = 0;
 };

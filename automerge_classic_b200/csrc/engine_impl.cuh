@@ -399,11 +399,11 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     // op / pred ranges of the changes are the raw ones; otherwise they are the scans over the applied changes only.
     timeBase.ensure(ctx, B + 1);
     const bool allApplied = numNew == B;
-    u32* opBaseP = rawBase.p; u32* predBaseP = rawPredBase.p;
+    opBase.ensure(ctx, B + 1); predBase.ensure(ctx, B + 1); u32* opBaseP = opBase.p; u32* predBaseP = predBase.p;
     const u32 anyLarge = decTot[3];
-    if (allApplied) { M = decTot[0]; P = decTot[1]; }
+    // first op / pred of every applied change in batch order (the raw rows themselves lie in tile arrival order, rawBase)
+    if (allApplied) { scan_exclusive(ctx, scanTmp, nOps.p, opBase.p, B); scan_exclusive(ctx, scanTmp, nPreds.p, predBase.p, B); M = decTot[0]; P = decTot[1]; }
     else {
-      opBase.ensure(ctx, B + 1); predBase.ensure(ctx, B + 1); opBaseP = opBase.p; predBaseP = predBase.p;
       foreach(ctx, B, MaskedCountKernel{nOps.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, opBase.p, B);
       foreach(ctx, B, MaskedCountKernel{nPreds.p, applied.p, rowSlot.p}); scan_exclusive(ctx, scanTmp, rowSlot.p, predBase.p, B);
       u32 m32 = 0, p32 = 0; void* dst[2] = {&m32, &p32}; readWords({{opBase.p + B, 4}, {predBase.p + B, 4}}, dst); M = m32; P = p32;
@@ -873,14 +873,13 @@ inline RawRows Engine::rawRows() {
 inline void Engine::runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes) {
   hot.ensure(ctx, B + 1); nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
   rawBase.ensure(ctx, B + 2); rawPredBase.ensure(ctx, B + 2); decErr.ensure(ctx, B + 1); decTotals.ensure(ctx, 4);
-  if (!tileTicket.p) { tileTicket.ensure(ctx, 4); dev_memset(ctx, tileTicket.p, 0, 16); }
-  const u32 numTiles = decode_num_tiles(B); tileState.ensure(ctx, (size_t)numTiles + 1);
+  decCursor.ensure(ctx, 2); const u32 numTiles = decode_num_tiles(B); decDirect.ensure(ctx, B + 2);
   const size_t wantRows = std::max(decWantRows, B + B / 4 + batchBytes / 256 + 1024), wantPreds = std::max(decWantPreds, B + B / 4 + batchBytes / 256 + 1024);
   for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, wantRows + 1);
   r_predActor.ensure(ctx, wantPreds + 1); r_predCtr.ensure(ctx, wantPreds + 1);
   decRowCap = wantRows; decPredCap = wantPreds;
   DecodeTilesArgs a{arenaP, chOff.p, chLen.p, (u32)B, hot.p, nOps.p, nPreds.p, nDeps.p, nActors.p, rawBase.p, rawPredBase.p, decErr.p, rawRows(), (u32)wantRows, (u32)wantPreds,
-                    tileState.p, tileTicket.p, decTotals.p, errWord.p, numTiles};
+                    (unsigned long long*)decCursor.p, decTotals.p, errWord.p, numTiles, decDirect.p + 1, decDirect.p};
   decode_tiles(ctx, a);
 }
 inline bool Engine::decodeOverflowed(const u32 totals[4]) {
@@ -1147,7 +1146,7 @@ inline int Engine::debugDecodeColumn(const u8* bytes, size_t len, int kind, size
 }
 
 // Parity hook: hashes, op counts and the raw decoded columns (change-local values) of a batch, without touching the document.
-inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* hashesOut, u32* nOpsOut, u32** rowsOut, size_t* totalOps) {
+inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* hashesOut, u32* nOpsOut, u32** rowsOut, size_t* totalOps, size_t* totalPreds) {
   std::vector<u32> off(n), len(n); std::string staged;
   for (size_t i = 0; i < n; i++) {
     const u8* p = blob + offsets[i]; const size_t l = offsets[i + 1] - offsets[i];
@@ -1181,8 +1180,14 @@ inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* 
   foreach(ctx, n, RaiseDecErrKernel{decErr.p, errWord.p});
   checkErr(actorIds);
   d2h(ctx, hashesOut, hashTmp.p, n * 32); d2h(ctx, nOpsOut, nOps.p, n * 4);
-  u32* rows = (u32*)malloc(sizeof(u32) * 12 * (M + 1));
-  for (int k = 0; k < 12; k++) d2h(ctx, rows + (size_t)k * M, cols[k]->p, M * 4);
+  const size_t P = tot[1];
+  opBase.ensure(ctx, n + 1); predBase.ensure(ctx, n + 1);
+  scan_exclusive(ctx, scanTmp, nOps.p, opBase.p, n); scan_exclusive(ctx, scanTmp, nPreds.p, predBase.p, n);
+  DBuf<u32> gathered; gathered.ensure(ctx, 12 * (M + 1) + 2 * (P + 1));
+  if (M) foreach(ctx, M, GatherRawKernel{n, opBase.p, predBase.p, rawBase.p, rawPredBase.p, raw, gathered.p, M, gathered.p + 12 * M, P});
+  u32* rows = (u32*)malloc(sizeof(u32) * (12 * (M + 1) + 2 * (P + 1)));
+  d2h(ctx, rows, gathered.p, (12 * M + 2 * P) * 4);
+  if (totalPreds) *totalPreds = P;
   sync(ctx); *rowsOut = rows; *totalOps = M; lastB = 0;
 }
 

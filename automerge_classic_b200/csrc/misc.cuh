@@ -24,6 +24,18 @@ struct TimeBaseKernel { const u32* scanned; const u8* applied; const u32* appRan
 // columns of a change when it applies it, new.js:686-700; a change that stays in the queue is not looked into)
 struct MaxOpKernel { const ChangeHot* meta; const u32* nOps; const u8* applied; const u32* decErr; u64* maxOp; u64* errWord; HD void operator()(size_t b) const { u64 v = 0; if (applied[b] && nOps[b] > 0) v = meta[b].startOp + nOps[b] - 1; if (applied[b] && decErr[b]) raise(errWord, decErr[b], b); warp_agg_max(maxOp, v); } };   // one atomic per warp
 
+// amg_debug_decode: raw rows of every change gathered into batch order (predOff re-based to the batch-order pred index)
+struct GatherRawKernel {
+  size_t numChanges; const u32* opBase; const u32* predBase; const u32* rawBase; const u32* rawPredBase; RawRows raw; u32* out /* [12][M] */; size_t M; u32* predOut /* [2][P] */; size_t P;
+  HD void operator()(size_t i) const {
+    size_t lo = 0, hi = numChanges; while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (opBase[mid] <= (u32)i) lo = mid; else hi = mid; }
+    const size_t c = lo; const u32 r = rawBase[c] + ((u32)i - opBase[c]);
+    const u32* cols[12] = {raw.objActor, raw.objCtr, raw.keyActor, raw.keyCtr, raw.keyStrOff, raw.keyStrLen, raw.insert, raw.action, raw.valLen, raw.valOff, raw.predNum, raw.predOff};
+    for (int k = 0; k < 12; k++) out[(size_t)k * M + i] = cols[k][r];
+    const u32 po = raw.predOff[r] - rawPredBase[c] + predBase[c]; out[(size_t)11 * M + i] = po;
+    for (u32 j = 0; j < raw.predNum[r]; j++) { predOut[po + j] = raw.predActor[raw.predOff[r] + j]; predOut[P + po + j] = raw.predCtr[raw.predOff[r] + j]; }
+  }
+};
 struct RaiseDecErrKernel { const u32* decErr; u64* errWord; HD void operator()(size_t b) const { if (decErr[b]) raise(errWord, decErr[b], b); } };
 // new actors: the applied change with the smallest application rank per fresh slot registers the representative bytes
 struct NewActorKernel {

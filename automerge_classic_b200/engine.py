@@ -415,6 +415,29 @@ class GpuBackendDoc:
         self._lib.L.amg_free_mem(succ)
         return r, s
 
+    def debug_decode(self, changes):
+        """Decoded rows of a batch of binary changes straight from the decode kernels (amg_debug_decode): the document is
+        not touched. Returns (hashes [n] bytes, n_ops [n], rows {column: uint32 array in batch order}, preds {'predActor',
+        'predCtr'}, staged bytes that keyStrOff / valOff index: the changes back to back, DEFLATEd ones inflated)."""
+        n = len(changes)
+        blob = b''.join(bytes(c) for c in changes)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum([len(c) for c in changes], out=offs[1:])
+        buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob if blob else b'\0')
+        hashes = (C.c_uint8 * (32 * max(n, 1)))()
+        n_ops = np.zeros(max(n, 1), dtype=np.uint32)
+        rows, total, total_preds, err = C.c_void_p(), C.c_size_t(), C.c_size_t(), _ErrStruct()
+        self._lib.check(self._lib.L.amg_debug_decode(self.h, buf, offs.ctypes.data_as(C.c_void_p), C.c_size_t(n), hashes, n_ops.ctypes.data_as(C.c_void_p),
+                                                     C.byref(rows), C.byref(total), C.byref(total_preds), C.byref(err)), err)
+        M, P = total.value, total_preds.value
+        flat = np.frombuffer(C.string_at(rows, 4 * (12 * M + 2 * P)), dtype=np.uint32).copy()
+        self._lib.L.amg_free_mem(rows)
+        names = ['objActor', 'objCtr', 'keyActor', 'keyCtr', 'keyStrOff', 'keyStrLen', 'insert', 'action', 'valLen', 'valOff', 'predNum', 'predOff']
+        cols = {name: flat[k * M:(k + 1) * M] for k, name in enumerate(names)}
+        preds = {'predActor': flat[12 * M:12 * M + P], 'predCtr': flat[12 * M + P:12 * M + 2 * P]}
+        hs = bytes(hashes)
+        return [hs[32 * i:32 * i + 32] for i in range(n)], n_ops[:n].copy(), cols, preds
+
     def debug_decode_column(self, buf, kind, n, parallel):
         """One document column through the parallel (True) or serial decoder; (rc, values, message), rc 1 = declined."""
         out = np.zeros(max(n, 1), dtype=np.int64)

@@ -43,8 +43,8 @@ int amg_reset(amg_backend* b, amg_error* err);
 int amg_reserve(amg_backend* b, size_t arena_bytes, amg_error* err);
 
 /* Backend.applyChanges(state, changes) — backend/backend.js:27-32 -> BackendDoc.applyChanges, new.js:1797-1879.
- * `bufs[i]` / `lens[i]`: the binary changes (chunk type 1, or 2 = DEFLATE, inflated on the host with zlib as
- * columnar.js:813-823 does with pako). is_local != 0 mirrors the `isLocal` argument used by applyLocalChange
+ * `bufs[i]` / `lens[i]`: the binary changes (chunk type 1, or 2 = DEFLATE, inflated on the device by an RFC 1951 decoder,
+ * csrc/inflate.cuh, where columnar.js:813-823 uses pako). is_local != 0 mirrors the `isLocal` argument used by applyLocalChange
  * (backend.js:84): the patch then carries actor and seq of the single change. want_patch == 0 is
  * Backend.loadChanges (backend.js:116-121): same state transition, no patch computed; *out is set to NULL. */
 int amg_apply_changes(amg_backend* b, const uint8_t* const* bufs, const size_t* lens, size_t n, int is_local, int want_patch,
@@ -107,9 +107,13 @@ void amg_patch_free(amg_patch* p);
 const uint8_t* amg_arena(amg_backend* b, size_t* len);
 
 /* ---- parity / measurement hooks (not part of the reference surface) ---- */
-/* decoded rows of a batch of changes (SoA dump of the decode kernels' output), for parity tests */
+/* decoded rows of a batch of changes (SoA dump of the decode kernels' output, gathered into batch order), for parity tests
+ * (SURVEY.md 8c "parity definition" items 1-2: per-change hash, decoded rows). rows_out (malloc'ed, amg_free_mem) holds 12
+ * columns x total_ops {objActor,objCtr,keyActor,keyCtr,keyStrOff,keyStrLen,insert,action,valLen,valOff,predNum,predOff}
+ * (change-local actor indexes, 0xffffffff = null, offsets relative to the staged copy of the batch) followed by
+ * 2 columns x total_preds {predActor, predCtr}. The document is not touched. */
 int amg_debug_decode(amg_backend* b, const uint8_t* blob, const uint64_t* offsets, size_t n, uint8_t* hashes_out /* n*32 */,
-                     uint32_t* n_ops_out /* n */, uint32_t** rows_out /* 12 columns x total ops, malloc'ed */, size_t* total_ops, amg_error* err);
+                     uint32_t* n_ops_out /* n */, uint32_t** rows_out, size_t* total_ops, size_t* total_preds, amg_error* err);
 /* document-ordered op table: rows[n][8] = {objCtr,objActor,idCtr,idActor,keyCtr,keyActor,flags,succNum}; succ[m][2] = {ctr, actor} */
 int amg_debug_dump_ops(amg_backend* b, uint64_t** rows_out, size_t* n, uint64_t** succ_out, size_t* m, amg_error* err);
 /* timings of the last applyChanges call: [0..11] CUDA-event phases in ms (stage+upload, sha256, parse+gate, actors+decode, op set,

@@ -312,7 +312,7 @@ static int64_t mergeDocChangeOps(Patches& patches, Block& newBlock, std::vector<
         } else if (!insert && !lastOp && !nextOp.hasKeyStr && hasDocOp && docOp.insert && !docOp.hasKeyStr &&
                    docOp.idActor == nextOp.keyActor && docOp.idCtr == nextOp.keyCtr) {
           // updating several consecutive list elements
-        } else if (!insert && !lastOp && nextOp.hasKeyStr && hasLastChangeKey && lastChangeKey < nextOp.keyStr) {
+        } else if (!insert && !lastOp && nextOp.hasKeyStr && hasLastChangeKey && js_less(lastChangeKey, nextOp.keyStr)) {
           // several keys in ascending order
         } else break;
         firstIteration = false;
@@ -337,7 +337,7 @@ static int64_t mergeDocChangeOps(Patches& patches, Block& newBlock, std::vector<
 
     bool takeDocOp = false; size_t takeChangeOps = 0;
     if (insert || !inCorrectObject || (!docOp.hasKeyStr && changeOp.hasKeyStr) ||
-        (docOp.hasKeyStr && changeOp.hasKeyStr && changeOp.keyStr < docOp.keyStr)) {
+        (docOp.hasKeyStr && changeOp.hasKeyStr && js_less(changeOp.keyStr, docOp.keyStr))) {
       takeChangeOps = changeOps.size();
       if (!inCorrectObject && !foundListElem && !changeOp.hasKeyStr && !changeOp.insert)
         throw RangeError("could not find list element with ID: " + opIdStr(changeOp.keyCtr, ds.actorOf(changeOp.keyActor)));

@@ -20,6 +20,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 namespace orc {
 
@@ -356,5 +357,26 @@ struct BooleanEncoder {
   }
   std::string finish() { if (count > 0) { e.appendUint53(count); count = 0; } return e.buf; }
 };
+
+// JavaScript's `<` on strings compares UTF-16 code units (new.js:84, 250, 1159 compare map keys this way). Keys are held
+// as UTF-8 here; byte order equals code point order, which differs from code unit order exactly when a supplementary-plane
+// character (surrogate pair, units 0xD800-0xDFFF) meets one of U+E000..U+FFFF. Compared unit by unit after decoding.
+inline void utf16_units(const std::string& s, std::vector<uint16_t>& out) {
+  out.clear(); size_t i = 0; const size_t n = s.size();
+  while (i < n) {
+    const unsigned char c = (unsigned char)s[i]; uint32_t cp; size_t len;
+    if (c < 0x80) { cp = c; len = 1; } else if ((c >> 5) == 6) { cp = c & 0x1f; len = 2; } else if ((c >> 4) == 14) { cp = c & 0x0f; len = 3; } else if ((c >> 3) == 30) { cp = c & 0x07; len = 4; } else { cp = 0xfffd; len = 1; }
+    for (size_t k = 1; k < len; k++) cp = (i + k < n) ? ((cp << 6) | ((unsigned char)s[i + k] & 0x3f)) : 0xfffd;
+    i += len;
+    if (cp >= 0x10000) { cp -= 0x10000; out.push_back((uint16_t)(0xd800 | (cp >> 10))); out.push_back((uint16_t)(0xdc00 | (cp & 0x3ff))); } else out.push_back((uint16_t)cp);
+  }
+}
+inline bool js_less(const std::string& a, const std::string& b) {
+  bool ascii = true; for (unsigned char c : a) if (c >= 0xe0) { ascii = false; break; }
+  if (ascii) for (unsigned char c : b) if (c >= 0xe0) { ascii = false; break; }
+  if (ascii) return a < b;   // no three- or four-byte sequences: byte order is code unit order
+  std::vector<uint16_t> x, y; utf16_units(a, x); utf16_units(b, y);
+  return std::lexicographical_compare(x.begin(), x.end(), y.begin(), y.end());
+}
 
 }  // namespace orc

@@ -192,7 +192,7 @@ static SeekResult seekWithinBlock(const SeekOps& ops, const Block& blk, const Do
       } else { nObjActor.kind = 0; nObjCtrNull = true; }
       ocur++;
       const Op& r = rows[kcur]; kcur++;
-      if (r.hasKeyStr && r.keyStr < ops.keyStr && objEq()) skipCount += 1; else break;
+      if (r.hasKeyStr && js_less(r.keyStr, ops.keyStr) && objEq()) skipCount += 1; else break;
     }
     return {true, skipCount, visibleCount};
   }
@@ -280,7 +280,7 @@ static SeekPos seekToOp(const DocState& ds, const SeekOps& ops) {
     // String key is used. First skip any blocks that contain only lower keys
     while (blockIndex < nb - 1) {
       const Block& b = *ds.blocks[blockIndex];
-      if (ops.objCtr == b.lastObjectCtr && ops.objActorNum == b.lastObjectActor && b.hasLastKey && b.lastKey < ops.keyStr) blockIndex++; else break;
+      if (ops.objCtr == b.lastObjectCtr && ops.objActorNum == b.lastObjectActor && b.hasLastKey && js_less(b.lastKey, ops.keyStr)) blockIndex++; else break;
     }
     SeekResult r = seekWithinBlock(ops, *ds.blocks[blockIndex], ds, false);
     return {blockIndex, r.skipCount, 0};
@@ -343,7 +343,7 @@ static void updateBlockMetadata(Block& block) {
 // new.js:426-459
 static void addBlockOperation(Block& block, const Op& op, const DocState& ds, bool isChangeOp) {
   if (op.hasKeyStr) {
-    if (block.lastObjectCtr == op.objCtr && block.lastObjectActor == op.objActor && (!block.hasLastKey || block.lastKey < op.keyStr)) {
+    if (block.lastObjectCtr == op.objCtr && block.lastObjectActor == op.objActor && (!block.hasLastKey || js_less(block.lastKey, op.keyStr))) {
       block.hasLastKey = true; block.lastKey = op.keyStr;
     }
   } else {

@@ -41,6 +41,158 @@ def check_trace_parity(gpu_doc, oracle_mod, cfg, n, a):
     _dump_equal(g, orc)
 
 
+def _inflated(change):
+    """the change as the engine stages it: DEFLATEd changes (chunk type 2) with their body inflated (columnar.js:813-823)"""
+    import zlib
+    change = bytes(change)
+    if change[8] != 2:
+        return change
+    pos, n, shift = 9, 0, 0
+    while True:
+        b = change[pos]; pos += 1; n |= (b & 0x7f) << shift; shift += 7
+        if not b & 0x80:
+            break
+    body = zlib.decompress(change[pos:pos + n], -15)
+    ln, v = bytearray(), len(body)
+    while True:
+        b = v & 0x7f; v >>= 7
+        ln.append(b | (0x80 if v else 0))
+        if not v:
+            break
+    return change[:8] + b'\x01' + bytes(ln) + body
+
+
+def check_decoded_rows(gpu_doc, oracle_mod, changes):
+    """SURVEY.md 8c parity items 1-2: per-change hash and the decoded rows (every op column, change-local actor indexes, keys
+    and value bytes, preds) of the decode kernels against the oracle's decodeChangeColumns / readOperation restatement."""
+    NULL = 0xffffffff
+    g = gpu_doc()
+    hashes, n_ops, cols, preds = g.debug_decode(changes)
+    staged = b''.join(_inflated(c) for c in changes)
+    i = 0
+    for ci, c in enumerate(changes):
+        d = oracle_mod.decode_change(c)
+        assert hashes[ci].hex() == d['hash'], ('hash', ci)
+        assert int(n_ops[ci]) == len(d['ops']), ('nOps', ci)
+        acc_key = None
+        for op in d['ops']:
+            def col(name):
+                v = int(cols[name][i]); return None if v == NULL else v
+            assert col('objActor') == op['objActor'] and col('objCtr') == op['objCtr'], ('obj', ci, i)
+            assert col('keyActor') == op['keyActor'], ('keyActor', ci, i)
+            assert col('keyCtr') == op['keyCtr'], ('keyCtr', ci, i, col('keyCtr'), op['keyCtr'])
+            if op['keyStr'] is None:
+                assert int(cols['keyStrLen'][i]) == NULL, ('keyStr null', ci, i)
+            else:
+                o, l = int(cols['keyStrOff'][i]), int(cols['keyStrLen'][i])
+                assert staged[o:o + l].decode('utf-8') == op['keyStr'], ('keyStr', ci, i)
+            assert bool(cols['insert'][i]) == op['insert'], ('insert', ci, i)
+            assert col('action') == op['action'], ('action', ci, i)
+            vl = op['valLen']
+            assert (0 if col('valLen') is None else col('valLen')) == (0 if vl is None else vl), ('valLen', ci, i)
+            nbytes = 0 if vl is None else vl >> 4
+            o = int(cols['valOff'][i])
+            assert staged[o:o + nbytes].hex() == op['valRaw'], ('valRaw', ci, i)
+            pn, po = int(cols['predNum'][i]), int(cols['predOff'][i])
+            assert pn == len(op['pred']), ('predNum', ci, i)
+            for j, (pc, pa) in enumerate(op['pred']):
+                ga, gc = int(preds['predActor'][po + j]), int(preds['predCtr'][po + j])
+                assert (None if ga == NULL else ga) == pa and (None if gc == NULL else gc) == pc, ('pred', ci, i, j)
+            i += 1
+    assert i == len(cols['action'])
+    return i
+
+
+def check_decoded_rows_trace(gpu_doc, oracle_mod, cfg, n, a):
+    from automerge_classic_b200 import tracegen
+    return check_decoded_rows(gpu_doc, oracle_mod, tracegen.generate(cfg, n, a).changes())
+
+
+def check_decode_corrupted(gpu_doc, oracle_mod, seed=11, cases=150):
+    """Changes with a valid checksum but damaged contents: the decode kernels and the oracle's decoder either both refuse the
+    batch or produce the same rows (the kernels validate every column in full, the reference only as far as it reads: a
+    change the oracle decodes must decode identically; one it refuses may be refused for a different reason)."""
+    import random
+    from automerge_classic_b200 import tracegen, columnar
+    from automerge_classic_b200.engine import AmgError
+    rnd = random.Random(seed)
+    base = tracegen.generate('C6', 300, 3, seed=seed).changes() + tracegen.generate('C4', 600, 3, seed=seed).changes()[:3]
+    same = refused = 0
+    for _ in range(cases):
+        c = bytearray(_inflated(rnd.choice(base)))
+        for _ in range(rnd.choice((1, 1, 2))):
+            pos = rnd.randrange(12, len(c))
+            how = rnd.random()
+            if how < 0.6:
+                c[pos] = rnd.randrange(256)
+            elif how < 0.8 and len(c) > 20:
+                del c[pos]
+            else:
+                c.insert(pos, rnd.randrange(256))
+        body = bytes(c[8:])
+        # a consistent container: chunk length and checksum recomputed (a plain corruption would stop at the checksum)
+        hdr_end, ln, sh = 9, 0, 0
+        while True:
+            b = c[hdr_end]; hdr_end += 1; ln |= (b & 0x7f) << sh; sh += 7
+            if not b & 0x80:
+                break
+        payload = bytes(c[hdr_end:])
+        lnb, v = bytearray(), len(payload)
+        while True:
+            b = v & 0x7f; v >>= 7
+            lnb.append(b | (0x80 if v else 0))
+            if not v:
+                break
+        framed = b'\x01' + bytes(lnb) + payload
+        fixed = bytes(c[:4]) + oracle_mod.sha256(framed)[:4] + framed
+        try:
+            oracle_mod.decode_change(fixed)
+            ok_o = True
+        except oracle_mod.OracleError:
+            ok_o = False
+        try:
+            check_decoded_rows(gpu_doc, oracle_mod, [fixed]) if ok_o else gpu_doc().debug_decode([fixed])
+            ok_g = True
+        except AmgError:
+            ok_g = False
+        if ok_o:
+            assert ok_g, 'the engine refuses a change the oracle decodes: %s' % fixed.hex()
+            same += 1
+        else:
+            refused += 1
+    assert same >= cases // 10, (same, refused)
+    return same, refused
+
+
+def check_utf16_keys(gpu_doc, oracle_mod):
+    """Map keys are ordered by UTF-16 code units (JavaScript `<`, new.js:84, 250, 1159), not by code points / UTF-8 bytes:
+    the two differ when a supplementary-plane character meets U+E000..U+FFFF. Batch apply, incremental apply, save and load."""
+    from automerge_classic_b200 import columnar
+    keys = ['\U0001F600', '\ue000z', '\uffff', 'a', '\u00e9', '\U00010000', '\ud7ff', '\U0001F600b', '\ue000', 'zz', '\uff5e\U00020000']
+    actors = ['aa' * 16, 'bb' * 16]
+    changes, deps, start = [], [], 1
+    for rnd_ in range(3):
+        for ai, actor in enumerate(actors):
+            ops = [{'action': 'set', 'obj': '_root', 'key': k, 'value': '%s/%d/%d' % (k, rnd_, ai), 'pred': []} for k in (keys if ai == 0 else keys[::-1])[rnd_::2]]
+            change = {'actor': actor, 'seq': rnd_ + 1, 'startOp': start, 'time': 0, 'message': '', 'deps': sorted(deps), 'ops': ops}
+            raw, h = columnar.encode_change_raw(change, False, 6)
+            changes.append(raw); deps = [h]; start += len(ops)
+    for chunk in (len(changes), 1, 2):
+        orc, g = oracle_mod.OracleDoc(), gpu_doc()
+        for lo in range(0, len(changes), chunk):
+            po, pg = orc.apply_changes(changes[lo:lo + chunk]), g.apply_changes(changes[lo:lo + chunk])
+            d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+            assert d is None, (chunk, lo, d)
+        _dump_equal(g, orc)
+        saved = g.save()
+        assert saved == orc.save(), 'save() differs from the oracle for keys outside the BMP'
+        g2 = gpu_doc(saved)
+        d = replay.deep_equal(replay.decode(g2.get_patch()), replay.decode(orc.get_patch()))
+        assert d is None, d
+        _dump_equal(g2, orc)
+    check_decoded_rows(gpu_doc, oracle_mod, changes)
+
+
 def check_rich_list(gpu_doc, oracle_mod, seed, n, a, chunk, cfg='C6'):
     """Config C6 / C8 (C8 adds counter elements: inserted counters, increments, overwrites and deletes of them)
     Config C6 (list of scalars and map objects; element updates, conflicts, deletes, re-insertions, nested keys),

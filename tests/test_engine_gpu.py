@@ -48,9 +48,6 @@ def test_reference_fixture(gpu_doc, test):
     from automerge_classic_b200.engine import AmgError
     r = replay.Replayer(gpu_doc, (AmgError, ValueError, TypeError, RuntimeError, FacadeRangeError), structural=False)
     fails = r.run_test(test)
-    unsupported = [f for f in fails if 'amgpu:' in f]
-    if unsupported:
-        pytest.xfail('outside the engine\'s current subset: ' + unsupported[0][:160])
     assert not fails, '\n'.join(fails[:5])
 
 
@@ -67,6 +64,20 @@ def test_rich_list_parity(gpu_doc, oracle_mod, n, a, chunk):
     """C6: element updates / conflicts / deletes / re-insertions and objects nested in list elements."""
     compared = sum(parity_checks.check_rich_list(gpu_doc, oracle_mod, seed, n, a, chunk) for seed in range(1, 9))
     assert compared >= 3
+
+
+@pytest.mark.parametrize('cfg,n,a', [('C1', 0, 0), ('C2', 2000, 0), ('C2b', 3000, 0), ('C3', 20000, 10), ('C4', 4000, 4), ('C6', 600, 3), ('C7', 400, 3), ('C8', 400, 3)])
+def test_decoded_rows(gpu_doc, oracle_mod, cfg, n, a):
+    """SURVEY.md 8c parity items 1-2: per-change hashes and decoded rows of the decode kernels vs the oracle."""
+    assert parity_checks.check_decoded_rows_trace(gpu_doc, oracle_mod, cfg, n, a) > 0
+
+
+def test_decoded_rows_corrupted(gpu_doc, oracle_mod):
+    parity_checks.check_decode_corrupted(gpu_doc, oracle_mod)
+
+
+def test_utf16_key_order(gpu_doc, oracle_mod):
+    parity_checks.check_utf16_keys(gpu_doc, oracle_mod)
 
 
 def test_deflate_variants(gpu_doc, oracle_mod):

@@ -38,9 +38,6 @@ def test_reference_fixture_emu(emu_doc, test):
     from automerge_classic_b200.engine import AmgError
     r = replay.Replayer(emu_doc, (AmgError, ValueError, TypeError, RuntimeError, FacadeRangeError), structural=False)
     fails = r.run_test(test)
-    unsupported = [f for f in fails if 'amgpu:' in f]
-    if unsupported:
-        pytest.xfail('outside the engine\'s current subset: ' + unsupported[0][:160])
     assert not fails, '\n'.join(fails[:5])
 
 
@@ -53,6 +50,19 @@ def test_trace_parity_emu(emu_doc, oracle_mod, cfg, n, a):
 def test_rich_list_emu(emu_doc, oracle_mod, n, a, chunk):
     compared = sum(parity_checks.check_rich_list(emu_doc, oracle_mod, seed, n, a, chunk) for seed in range(1, 7))
     assert compared >= 4
+
+
+@pytest.mark.parametrize('cfg,n,a', [('C1', 0, 0), ('C2', 300, 0), ('C2b', 500, 0), ('C3', 1500, 5), ('C4', 1200, 4), ('C6', 300, 3), ('C7', 300, 3)])
+def test_decoded_rows_emu(emu_doc, oracle_mod, cfg, n, a):
+    assert parity_checks.check_decoded_rows_trace(emu_doc, oracle_mod, cfg, n, a) > 0
+
+
+def test_decoded_rows_corrupted_emu(emu_doc, oracle_mod):
+    parity_checks.check_decode_corrupted(emu_doc, oracle_mod, cases=80)
+
+
+def test_utf16_key_order_emu(emu_doc, oracle_mod):
+    parity_checks.check_utf16_keys(emu_doc, oracle_mod)
 
 
 def test_deflate_variants_emu(emu_doc, oracle_mod):
