@@ -31,6 +31,7 @@ struct amg_backend {
     if (!e.haveHashGraph) e.computeHashGraph();   // new.js:1922, 1980, 2000, 2015
     if (g.known == e.numApplied) return;
     const size_t from = g.known, to = e.numApplied;
+    e.ensureHostMirror();   // the change headers are read from the host copy of the arena (fetched now if the batch came from pinned / device memory)
     std::vector<u8> hs((to - from) * 32); d2h(e.ctx, hs.data(), e.hashes.p + from * 32, hs.size()); sync(e.ctx);
     for (size_t i = from; i < to; i++) {
       Hash h; memcpy(h.data(), hs.data() + (i - from) * 32, 32);
@@ -62,6 +63,7 @@ struct amg_backend {
     return out + comp;
   }
   std::string changeBytes(u32 idx) {
+    eng.ensureHostMirror();
     if (const HostChange* o = eng.originalOf(idx)) return std::string((const char*)eng.hostArena.data() + o->off, o->len);
     const HostChange& c = eng.changes[idx];
     std::string plain((const char*)eng.hostArena.data() + c.off, c.len);
@@ -105,7 +107,7 @@ amg_backend* amg_clone(amg_backend* src, amg_error* err) {
   try {
     auto* b = new amg_backend(src->eng.ctx.device);
     Engine& d = b->eng; Engine& s = src->eng; Ctx& c = d.ctx;
-    sync(s.ctx);
+    sync(s.ctx); s.ensureHostMirror();
     d.hostArena.assign(s.hostArena); d.arenaLen = s.arenaLen; d.arena.ensure(c, s.arenaLen + 64); d2d(c, d.arena.p, s.arena.p, s.arenaLen);
     d.numApplied = s.numApplied; d.hashes.ensure(c, s.numApplied * 32 + 64); d2d(c, d.hashes.p, s.hashes.p, s.numApplied * 32);
     d.numRows = s.numRows; d.doc.ensure(c, s.numRows + 1);
@@ -139,7 +141,10 @@ int amg_get_state(amg_backend* b, amg_patch** out, amg_error* err) {
 }
 const uint8_t* amg_patch_bytes(const amg_patch* p, size_t* len) { *len = p->len; return p->p; }
 void amg_patch_free(amg_patch* p) { delete p; }
-const uint8_t* amg_arena(amg_backend* b, size_t* len) { *len = b->eng.hostArena.size(); return b->eng.hostArena.data(); }
+const uint8_t* amg_arena(amg_backend* b, size_t* len) {
+  try { b->eng.ensureHostMirror(); } catch (...) { amg::drop_pending_peeks(); *len = 0; return nullptr; }
+  *len = b->eng.hostArena.size(); return b->eng.hostArena.data();
+}
 
 size_t amg_buffers_count(const amg_buffers* l) { return l->items.size(); }
 const uint8_t* amg_buffers_get(const amg_buffers* l, size_t i, size_t* len) { *len = l->items[i].size(); return (const uint8_t*)l->items[i].data(); }
@@ -209,6 +214,7 @@ int amg_get_missing_deps(amg_backend* b, const uint8_t* heads, size_t n, amg_buf
   AMG_GUARD(
     b->ensureGraph(); std::map<Hash, bool> allDeps, inQueue; Engine& e = b->eng;
     for (size_t i = 0; i < n; i++) allDeps[toHash(heads + 32 * i)] = true;
+    e.ensureHostMirror();
     for (auto& q : e.queue) {
       Hash h;
       // hash of the queued change: SHA-256 over bytes [8..) — computed on the host for the (short) queue

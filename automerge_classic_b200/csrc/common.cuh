@@ -51,7 +51,7 @@ struct Ctx {
   cudaStream_t side = nullptr;        // second stream: work that may overlap the main pipeline (joined through events)
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaStream_t copy = nullptr;        // third stream: device -> host copy of the uploaded change bytes into the host mirror
-  cudaEvent_t evUp = nullptr, evMirror = nullptr; bool mirrorPending = false;
+  cudaEvent_t evUp = nullptr, evMirror = nullptr; bool copyPending = false; std::vector<cudaEvent_t> pieceEv; size_t pieceNext = 0;
   cudaEvent_t phaseEv[13]; bool phaseEvReady = false;   // phase timing of the last call (PhaseTimer)
   // small device -> host reads go through a kernel that stores into pinned (device-visible) host memory, not through the
   // copy engine: a read of 4 bytes must not queue behind a 100 MB transfer (see d2h / sync)
@@ -301,25 +301,41 @@ inline void side_join(Ctx& c) {
 #endif
 }
 
-// Host mirror of freshly uploaded bytes: copied back from the device by the copy engine (no CPU time, and the caller's
-// buffer is not touched after the upload), ordered after everything queued on the main stream so far. mirror_wait() is
-// the host-side join; nothing else on the device waits for it.
-inline void mirror_start(Ctx& c, void* dstPinnedHost, const void* srcDev, size_t bytes) {
-#ifdef AMG_EMU
-  memcpy(dstPinnedHost, srcDev, bytes);
-#else
-  CUDA_CHECK(cudaEventRecord(c.evUp, c.stream)); CUDA_CHECK(cudaStreamWaitEvent(c.copy, c.evUp, 0));
-  // (the small device -> host reads that size the pipeline stages do not use the copy engine, see d2h: behind this
-  // transfer each of them waited for all that was left of it, in one piece or in many)
-  CUDA_CHECK(cudaMemcpyAsync(dstPinnedHost, srcDev, bytes, cudaMemcpyDeviceToHost, c.copy));
-  CUDA_CHECK(cudaEventRecord(c.evMirror, c.copy)); c.mirrorPending = true;
-#endif
-}
-inline void mirror_wait(Ctx& c) noexcept {
+// Copy stream: uploads of a call's change bytes, piece by piece. copy_fork(): the copy stream starts behind what the main
+// stream has queued so far. copy_piece_done(): main and side stream wait for everything queued on the copy stream so far
+// (one event per piece, taken from a pool). copy_join(): host-side join at the end of the call (also on error paths).
+inline void copy_fork(Ctx& c) {
 #ifndef AMG_EMU
-  if (c.mirrorPending) { cudaEventSynchronize(c.evMirror); c.mirrorPending = false; }
+  CUDA_CHECK(cudaEventRecord(c.evUp, c.stream)); CUDA_CHECK(cudaStreamWaitEvent(c.copy, c.evUp, 0)); c.pieceNext = 0;
 #endif
 }
+inline void h2d_copy(Ctx& c, void* dst, const void* src, size_t bytes) {
+#ifdef AMG_EMU
+  memcpy(dst, src, bytes);
+#else
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.copy)); c.copyPending = true;
+#endif
+}
+inline void d2d_copy(Ctx& c, void* dst, const void* src, size_t bytes) {
+#ifdef AMG_EMU
+  memmove(dst, src, bytes);
+#else
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c.copy)); c.copyPending = true;
+#endif
+}
+inline void copy_piece_done(Ctx& c) {
+#ifndef AMG_EMU
+  if (c.pieceNext >= c.pieceEv.size()) { cudaEvent_t e; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.pieceEv.push_back(e); }
+  cudaEvent_t e = c.pieceEv[c.pieceNext++];
+  CUDA_CHECK(cudaEventRecord(e, c.copy)); CUDA_CHECK(cudaStreamWaitEvent(c.stream, e, 0)); CUDA_CHECK(cudaStreamWaitEvent(c.side, e, 0));
+#endif
+}
+inline void copy_join(Ctx& c) noexcept {
+#ifndef AMG_EMU
+  if (c.copyPending) { cudaStreamSynchronize(c.copy); c.copyPending = false; }
+#endif
+}
+inline void mirror_wait(Ctx&) noexcept {}
 
 // ---------------------------------------------------------------- atomics (serial in EMU)
 #ifdef AMG_EMU

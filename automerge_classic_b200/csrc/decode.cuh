@@ -247,9 +247,10 @@ struct DeflateScanKernel {
 };
 // hashes arena[off+8 .. off+len) of every change; writes 32-byte digests; checks magic + checksum
 struct ShaKernel {
-  const u8* arena; const u32* chOff; const u32* chLen; u8* hashOut /* [n][32] */; u64* errWord; const u32* subset /* optional: only these changes */; u32* deflList;
+  const u8* arena; const u32* chOff; const u32* chLen; u8* hashOut /* [n][32] */; u64* errWord; const u32* subset /* optional: only these changes */; u32* deflList /* non-null: DEFLATEd changes are skipped (hashed once inflated) */;
+  size_t first = 0;   // items are changes first, first + 1, ...
   HD void operator()(size_t ci) const {
-    const size_t c = subset ? subset[ci] : ci;
+    const size_t c = subset ? subset[ci] : first + ci;
     const u8* p = arena + chOff[c]; const u32 len = chLen[c];
     if (len > 8 && p[8] == 2 && p[0] == 0x85) {   // DEFLATEd change (columnar.js:742): listed for the host, which inflates it and re-points this entry
       if (!deflList) raise(errWord, KE_CHUNK_TYPE, c);   // with a list: skipped here, hashed again once the host has inflated it
@@ -637,7 +638,7 @@ template <class S> HD u32 expand_change(const S& src, const ChangeHot& h, u32 nO
 }
 
 struct DecodeTilesArgs {
-  const u8* arena; const u32* chOff; const u32* chLen; u32 B;
+  const u8* arena; const u32* chOff; const u32* chLen; u32 B /* end of the change range of this launch */; u32 first /* its first change */;
   ChangeHot* hot; u32* nOps; u32* nPreds; u32* nDeps; u32* nActors;
   u32* rawBase /* [B] first raw row of each change (every change of the batch) */; u32* rawPredBase /* [B] */;
   u32* decErr /* [B] KErr of the column contents: raised only if the change is applied (the reference decodes columns lazily) */;
@@ -662,16 +663,29 @@ template <class S> HD void finish_change(const DecodeTilesArgs& a, const S& src,
 }
 
 #ifdef AMG_EMU
-inline void decode_tiles(Ctx& c, const DecodeTilesArgs& a) {
+inline void decode_tiles_begin(Ctx&, const DecodeTilesArgs& a) { a.cursor[0] = a.cursor[1] = 0; a.totals[0] = a.totals[1] = a.totals[2] = a.totals[3] = 0; *a.directCount = 0; }
+inline void decode_tiles_range(Ctx& c, DecodeTilesArgs a, u32 first, u32 end) {
   // tiles of 4 changes, last tile first: raw rows are NOT in batch order on the device either (tiles take their row range
-  // from a cursor in arrival order), so the emulation makes sure nothing downstream relies on it
-  u64 ops = 0, preds = 0; a.totals[0] = a.totals[1] = a.totals[2] = a.totals[3] = 0;
-  const u32 T = 4, numTiles = (a.B + T - 1) / T;
-  for (u32 t = numTiles; t-- > 0;) for (u32 i = t * T; i < a.B && i < (t + 1) * T; i++) {
+  // from a cursor in arrival order), so the emulation makes sure nothing downstream relies on it. DEFLATEd changes wait
+  // for the inflate step like on the device (decode_tiles_finish).
+  const u32 T = 4, numTiles = (end - first + T - 1) / T;
+  for (u32 t = numTiles; t-- > 0;) for (u32 i = first + t * T; i < end && i < first + (t + 1) * T; i++) {
+    const u8* p = a.arena + a.chOff[i];
+    if (a.chLen[i] > 8 && p[8] == 2 && p[0] == 0x85) { a.directList[(*a.directCount)++] = i; continue; }
     ParsedChange pc; parse_change(PtrSrc{a.arena}, a.chOff[i], a.chLen[i], pc);
-    finish_change(a, PtrSrc{a.arena}, i, pc, (u32)std::min<u64>(ops, 0x7fffffffu), (u32)std::min<u64>(preds, 0x7fffffffu));
-    ops += pc.nOps; preds += pc.nPreds;
+    finish_change(a, PtrSrc{a.arena}, i, pc, (u32)std::min<u64>(a.cursor[0], 0x7fffffffu), (u32)std::min<u64>(a.cursor[1], 0x7fffffffu));
+    a.cursor[0] += pc.nOps; a.cursor[1] += pc.nPreds;
   }
+  c.launches++;
+}
+inline void decode_tiles_finish(Ctx& c, const DecodeTilesArgs& a, size_t) {
+  for (u32 k = 0; k < *a.directCount; k++) {
+    const u32 i = a.directList[k];
+    ParsedChange pc; parse_change(PtrSrc{a.arena}, a.chOff[i], a.chLen[i], pc);
+    finish_change(a, PtrSrc{a.arena}, i, pc, (u32)std::min<u64>(a.cursor[0], 0x7fffffffu), (u32)std::min<u64>(a.cursor[1], 0x7fffffffu));
+    a.cursor[0] += pc.nOps; a.cursor[1] += pc.nPreds;
+  }
+  const u64 ops = a.cursor[0], preds = a.cursor[1];
   a.totals[0] = (u32)std::min<u64>(ops, 0x7fffffffu); a.totals[1] = (u32)std::min<u64>(preds, 0x7fffffffu);
   if (ops > a.rowCap || preds > a.predCap) a.totals[2] = 1;   // rows that larger changes reserved must fit as well
   c.launches++;
@@ -735,7 +749,7 @@ __global__ void __launch_bounds__(DT_THREADS, AMG_DT_MINBLOCKS) k_decode_tiles(c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const u32 c = blockIdx.x * DT_THREADS + tid; bool live = c < a.B;
+  const u32 c = a.first + blockIdx.x * DT_THREADS + tid; bool live = c < a.B;
   const u32 off = live ? a.chOff[c] : 0xffffffffu, len = live ? a.chLen[c] : 0;
   // the staged window starts at the tile's lowest offset; changes that do not lie inside it (inflated changes live behind
   // the batch, a big change may not fit) are passed on to k_decode_direct one by one
@@ -744,12 +758,6 @@ __global__ void __launch_bounds__(DT_THREADS, AMG_DT_MINBLOCKS) k_decode_tiles(c
   const u32 lo16 = sLo & ~15u;
   const bool inWindow = live && (u64)off + len <= (u64)lo16 + DT_STAGE;
   { const u32 hi = __reduce_max_sync(0xffffffffu, inWindow ? off + len : 0u); if (lane == 0 && hi) atomicMax(&sHi, hi); }
-  if (live && !inWindow) {
-    const unsigned peers = __activemask(); const int leader = __ffs(peers) - 1; u32 base = 0;
-    if (lane == leader) base = atomicAdd(a.directCount, (u32)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    a.directList[base + __popc(peers & ((1u << lane) - 1))] = c;
-  }
   __syncthreads();
   live = inWindow;
   if (sHi > lo16) {
@@ -762,7 +770,18 @@ __global__ void __launch_bounds__(DT_THREADS, AMG_DT_MINBLOCKS) k_decode_tiles(c
     u32 ok = 0;
     while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_addr(&bar)) : "memory");
   }
-  decode_tile_body(a, SmemSrc{smem_addr(stage) - lo16}, c, live, off, len, sWarp, sBase);
+  const SmemSrc ssrc{smem_addr(stage) - lo16};
+  // DEFLATEd changes (chunk type 2, columnar.js:742) are inflated later in the call: decoded by k_decode_direct then
+  const bool deflated = live && len > 8 && ssrc.ld(off + 8) == 2 && ssrc.ld(off) == 0x85;
+  const bool defer = (c < a.B && !inWindow) || deflated;
+  if (defer) {
+    const unsigned peers = __activemask(); const int leader = __ffs(peers) - 1; u32 base = 0;
+    if (lane == leader) base = atomicAdd(a.directCount, (u32)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    a.directList[base + __popc(peers & ((1u << lane) - 1))] = c;
+  }
+  live = live && !deflated;
+  decode_tile_body(a, ssrc, c, live, off, len, sWarp, sBase);
 }
 // the changes the staged kernel passed on: same steps, one thread per listed change, bytes read from global memory
 __global__ void __launch_bounds__(DT_THREADS) k_decode_direct(const DecodeTilesArgs a) {
@@ -780,25 +799,27 @@ static __global__ void k_decode_totals(const DecodeTilesArgs a) {   // cursor ->
   a.totals[0] = sat31(ops); a.totals[1] = sat31(preds);
   if (ops > a.rowCap || preds > a.predCap) a.totals[2] = 1;
 }
-inline void decode_tiles(Ctx& c, const DecodeTilesArgs& a) {
+// begin (clears cursor / counters) -> any number of ranges (each as soon as its bytes are on the device) -> finish
+inline void decode_tiles_begin(Ctx& c, const DecodeTilesArgs& a) {
   CUDA_CHECK(cudaMemsetAsync(a.cursor, 0, 16, c.stream));
   CUDA_CHECK(cudaMemsetAsync(a.totals, 0, 16, c.stream));
   CUDA_CHECK(cudaMemsetAsync(a.directCount, 0, 4, c.stream));
-  k_decode_tiles<<<a.numTiles, DT_THREADS, 0, c.stream>>>(a);
+}
+inline void decode_tiles_range(Ctx& c, DecodeTilesArgs a, u32 first, u32 end) {
+  if (end <= first) return;
+  a.first = first; a.B = end;
+  k_decode_tiles<<<(end - first + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, c.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
-  k_decode_direct<<<(unsigned)std::min<size_t>(a.numTiles, (size_t)c.numSMs * 8), DT_THREADS, 0, c.stream>>>(a);
+  c.launches++;
+}
+inline void decode_tiles_finish(Ctx& c, const DecodeTilesArgs& a, size_t numChanges) {
+  const size_t tiles = (numChanges + DT_THREADS - 1) / DT_THREADS;
+  k_decode_direct<<<(unsigned)std::max<size_t>(1, std::min<size_t>(tiles, (size_t)c.numSMs * 8)), DT_THREADS, 0, c.stream>>>(a);
   k_decode_totals<<<1, 32, 0, c.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
-  c.launches += 3;
+  c.launches += 2;
 }
 #endif
-inline u32 decode_num_tiles(size_t B) {
-#ifdef AMG_EMU
-  return 1;
-#else
-  return (u32)((B + DT_THREADS - 1) / DT_THREADS);
-#endif
-}
 
 // Changes with more than SMALL_CHANGE_OPS ops: one thread per (column, large change); `large` lists the change indices.
 // The column is found by walking the change's directory (at most a few entries).

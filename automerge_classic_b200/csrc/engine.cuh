@@ -45,7 +45,7 @@ struct DocBufs {
 struct PatchOut {   // flat patch, written straight into the engine's pinned output buffer (layout: include/amgpu.h)
   u64 maxOp = 0, pendingChanges = 0; bool hasActorSeq = false; std::string actor; u64 seq = 0;
   std::vector<std::pair<u32, u64>> clock; std::vector<std::array<u8, 32>> deps; std::vector<std::string> actors;
-  size_t propsOff = 0, numProps = 0, editsOff = 0, numEdits = 0, elemOff = 0, bigEnd = 0;   // byte offsets into Engine::patchBuf
+  size_t propsOff = 0, numProps = 0, editsOff = 0, numEdits = 0, elemOff = 0, valBytesOff = 0, valBytesLen = 0, bigEnd = 0;   // byte offsets into Engine::patchBuf
   const u8* bytes = nullptr; size_t bytesLen = 0;   // final serialised patch (valid until the next call on the same engine)
 };
 
@@ -95,7 +95,8 @@ class Engine {
   // ---- scratch (grow-only)
   DBuf<u32> chOff, chLen, nOps, nPreds, nDeps, nActors, colOff, colLen, depBase, depIdx, primary, pass, flagWord, appRank, opBase, predBase, timeBase, amapBase, amap, authorSlot, newSlots;
   DBuf<u8> applied; DBuf<ChangeHot> hot; DBuf<ChangeMeta> meta /* save(): full headers */; DBuf<u64> errWord; DBuf<u32> hashTable;
-  DBuf<u32> rawBase, rawPredBase, decErr, decTotals, decDirect; DBuf<u64> decCursor;   // fused decode (decode.cuh k_decode_tiles)
+  DBuf<u32> rawBase, rawPredBase, decErr, decTotals, decDirect; DBuf<u64> decCursor;
+  DBuf<u32> patchByteLen, patchByteOff; DBuf<u8> patchBytesD;   // key / value bytes shipped inside the patch   // fused decode (decode.cuh k_decode_tiles)
   DBuf<u32> r_objActor, r_objCtr, r_keyActor, r_keyCtr, r_keyStrOff, r_keyStrLen, r_insert, r_action, r_valLen, r_valOff, r_predNum, r_predOff, r_predActor, r_predCtr;
   DBuf<u64> o_id, o_obj, o_key, o_predId; DBuf<u32> o_keyStrOff, o_keyStrLen, o_flags, o_valLen, o_valOff, o_predOff, o_predNum, o_change, o_time;
   DBuf<u32> isRow, rowSlot, rowOfOp; DocBufs work, sorted;
@@ -275,7 +276,15 @@ class Engine {
   bool haveHashGraph = true;   // false after Backend.load: change history (hashes, bytes) is not reconstructed (new.js:1887-1912)
   void benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes);
   RawRows rawRows();
-  void runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes);   // sizes the raw row tables and launches the fused decode
+  void runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes);
+  DecodeTilesArgs decodeArgs(const u8* arenaP, size_t B, size_t batchBytes);
+  // Host mirror of the arena, filled on demand: hostArena holds arena[0, hostArena.size()); whatever is missing is fetched
+  // from the device when a reader (getChanges, amg_arena, clone ...) asks for it.
+  void ensureHostMirror() {
+    if (hostArena.size() >= arenaLen) return;
+    const size_t from = hostArena.size(); hostArena.resize(arenaLen);
+    d2h(ctx, hostArena.data() + from, arena.p + from, arenaLen - from); sync(ctx);
+  }   // sizes the raw row tables and launches the fused decode
   bool decodeOverflowed(const u32 totals[4]);
   void computeHashGraph();   // change history of a loaded document (history.cuh)
   int debugDecodeColumn(const u8* bytes, size_t len, int kind, size_t n, bool parallel, long long* out);

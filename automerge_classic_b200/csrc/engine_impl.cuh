@@ -6,6 +6,7 @@
 
 namespace amg {
 
+static const size_t PATCH_HDR_WORDS = 20;
 struct HostClock {
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   float ms() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
@@ -31,6 +32,20 @@ inline void parallel_copy(u8* dst, const u8* src, size_t n) {
   for (auto& t : ts) t.join();
 }
 
+// changes [c0, c1) of a pointer array, back to back into dst (the shape Backend.applyChanges(state, Uint8Array[]) hands over)
+inline void parallel_gather(u8* dst, const u8* const* bufs, const size_t* lens, size_t c0, size_t c1) {
+  size_t bytes = 0; for (size_t i = c0; i < c1; i++) bytes += lens[i];
+  unsigned nt = bytes < (4u << 20) ? 1u : std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+  if (nt == 1) { for (size_t i = c0; i < c1; i++) { memcpy(dst, bufs[i], lens[i]); dst += lens[i]; } return; }
+  std::vector<std::thread> ts; const size_t per = (c1 - c0 + nt - 1) / nt; size_t at = 0;
+  for (unsigned t = 0; t < nt; t++) {
+    const size_t a = c0 + t * per, b = std::min(c1, a + per); if (a >= b) break;
+    u8* d = dst + at; for (size_t i = a; i < b; i++) at += lens[i];
+    ts.emplace_back([=] { u8* q = d; for (size_t i = a; i < b; i++) { memcpy(q, bufs[i], lens[i]); q += lens[i]; } });
+  }
+  for (auto& t : ts) t.join();
+}
+
 inline void Engine::fillPatchHeader(PatchOut& out) {
   out.maxOp = maxOp; out.pendingChanges = queue.size();
   out.clock.clear(); for (size_t a = 0; a < clock.size(); a++) if (clock[a] > 0) out.clock.emplace_back((u32)a, clock[a]);
@@ -39,19 +54,19 @@ inline void Engine::fillPatchHeader(PatchOut& out) {
 
 // writes the header and the small sections (actor, actors, clock, deps) after the big record sections
 inline void Engine::finishPatch(PatchOut& out) {
-  if (out.bigEnd == 0) { out.propsOff = out.editsOff = 18 * 8; out.elemOff = 0; out.bigEnd = 18 * 8; }
+  if (out.bigEnd == 0) { out.propsOff = out.editsOff = PATCH_HDR_WORDS * 8; out.elemOff = 0; out.valBytesOff = out.valBytesLen = 0; out.bigEnd = PATCH_HDR_WORDS * 8; }
   size_t small = 64 + out.actor.size(); for (auto& a : out.actors) small += 8 + a.size(); small += out.clock.size() * 16 + out.deps.size() * 32 + 64;
   patchBuf.ensure(out.bigEnd + small);   // growth preserves what is already there
   u8* b = patchBuf.p; size_t at = out.bigEnd;
   auto pad8 = [&]() { while (at % 8) b[at++] = 0; };
-  u64 hdr[18] = {0}; hdr[0] = 0x31504747414d41ULL; hdr[1] = out.maxOp; hdr[2] = out.pendingChanges; hdr[3] = out.hasActorSeq ? 1 : 0; hdr[4] = out.seq;
+  u64 hdr[PATCH_HDR_WORDS] = {0}; hdr[0] = 0x31504747414d41ULL; hdr[1] = out.maxOp; hdr[2] = out.pendingChanges; hdr[3] = out.hasActorSeq ? 1 : 0; hdr[4] = out.seq;
   pad8(); hdr[5] = at; hdr[6] = out.actor.size(); memcpy(b + at, out.actor.data(), out.actor.size()); at += out.actor.size(); pad8();
   hdr[7] = at; hdr[8] = out.actors.size();
   for (auto& a : out.actors) { const u32 l = (u32)a.size(); memcpy(b + at, &l, 4); at += 4; memcpy(b + at, a.data(), l); at += l; while (at % 4) b[at++] = 0; }
   pad8(); hdr[9] = at; hdr[10] = out.clock.size();
   for (auto& c : out.clock) { const u64 a = c.first, s = c.second; memcpy(b + at, &a, 8); memcpy(b + at + 8, &s, 8); at += 16; }
   hdr[11] = at; hdr[12] = out.deps.size(); for (auto& d : out.deps) { memcpy(b + at, d.data(), 32); at += 32; }
-  hdr[13] = out.propsOff; hdr[14] = out.numProps; hdr[15] = out.editsOff; hdr[16] = out.numEdits; hdr[17] = out.elemOff;
+  hdr[13] = out.propsOff; hdr[14] = out.numProps; hdr[15] = out.editsOff; hdr[16] = out.numEdits; hdr[17] = out.elemOff; hdr[18] = out.valBytesOff; hdr[19] = out.valBytesLen;
   memcpy(b, hdr, sizeof(hdr));
   out.bytes = b; out.bytesLen = at;
 }
@@ -88,14 +103,20 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   dbgMarks.clear(); dbgMark = [this, &hclk](const char* l) { dbgMarks.emplace_back(l, hclk.ms()); };
   struct SideJoinAll { Ctx& c; ~SideJoinAll() { side_join(c); } } sideJoinAll{ctx};   // whatever this call put on the side stream is ordered before the next call
   struct ClearTimer { Engine* e; ~ClearTimer() { e->curTimer = nullptr; e->curHostMark = nullptr; e->dbgMark = [](const char*) {}; } } clearTimer{this};
-  // ------------------------------------------------------------ 0. stage the batch in the arena (pinned host mirror + device)
+  // ------------------------------------------------------------ 0. stage the batch in the arena; hash and decode it piece by piece
+  // The change bytes go to the device in pieces on the copy stream; as soon as a piece has landed, its changes are hashed
+  // (side stream) and decoded (main stream) while the next piece is still crossing PCIe - both kernels read the piece
+  // while it is hot in L2. The host keeps NO copy of bytes that came from a pinned or device buffer of the caller: the
+  // mirror (hostArena) is filled lazily when something asks for it (getChanges, amg_arena ...; ensureHostMirror). Bytes
+  // that have to be staged through pinned memory anyway (pageable caller buffers, pointer arrays) are staged through the
+  // mirror itself, which then stays complete for free.
   const size_t arenaLen0 = arenaLen; const size_t hostLen0 = hostArena.size();
   std::vector<HostChange>& batch = batchStore; batch.clear();   // member: the 8 MB of a 1M-change batch keep their pages across calls
   std::vector<HostChange> batchOriginal, inflOrig;   // originals of DEFLATEd changes: batchOriginal (dense, queue entries) / inflOrig (sparse, parallel to deflIdx)
   std::vector<u32> deflIdx;
   size_t inflNd = 0, inflExtraStart = 0, inflExtra = 0; bool inflPending = false;
-  // Host side of the device inflate: which batch entries moved where, and the inflated bytes for the host mirror. Not on
-  // the critical path: runs when the information is first needed (queue hand-over, commit); by then the mirror copy is done.
+  // Host side of the device inflate: which batch entries moved where. Not on the critical path: runs when the information
+  // is first needed (queue hand-over, commit).
   auto finishInflate = [&]() {
     if (!inflPending) return;
     inflPending = false; const size_t nd = inflNd;
@@ -103,9 +124,10 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     pinnedScratch.ensure(5 * nd + 16); u32* ps = pinnedScratch.p;   // pinned: the five small copies queue up and complete with one sync
     d2h(ctx, ps, deflList.p, nd * 4); d2h(ctx, ps + nd, inflLen.p, nd * 4); d2h(ctx, ps + 2 * nd, inflOff.p, nd * 4);
     d2h(ctx, ps + 3 * nd, origOff, nd * 4); d2h(ctx, ps + 4 * nd, origLen, nd * 4);
-    mirror_wait(ctx);   // the mirror has to grow
-    hostArena.resize(inflExtraStart + inflExtra);
-    d2h(ctx, hostArena.data() + inflExtraStart, arena.p + inflExtraStart, inflExtra);
+    if (hostArena.size() == inflExtraStart) {   // the mirror is complete up to here: keep it complete
+      hostArena.resize(inflExtraStart + inflExtra);
+      d2h(ctx, hostArena.data() + inflExtraStart, arena.p + inflExtraStart, inflExtra);
+    }
     sync(ctx);
     deflIdx.assign(ps, ps + nd); inflOrig.resize(nd);   // deflIdx is ascending: (batch index, original range), looked up by binary search
     for (size_t k = 0; k < nd; k++) { const u32 bi = ps[k]; inflOrig[k] = HostChange{ps[3 * nd + k], ps[4 * nd + k]}; batch[bi] = HostChange{(u32)inflExtraStart + ps[2 * nd + k], ps[nd + k]}; }
@@ -115,85 +137,103 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     auto it = std::lower_bound(deflIdx.begin(), deflIdx.end(), (u32)b);
     return it != deflIdx.end() && *it == (u32)b ? inflOrig[it - deflIdx.begin()] : HostChange{0, 0};
   };
-  struct Rollback { Engine* e; size_t len; bool armed = true; ~Rollback() { if (armed) { e->hostArena.resize(len); e->rebuildActorTable(); } } };
+  struct Rollback { Engine* e; size_t len; bool armed = true; ~Rollback() { if (armed) { if (e->hostArena.size() > len) e->hostArena.resize(len); e->rebuildActorTable(); } } };
   size_t total = 0;
   if (blob && n > 0) total = offsets[n] - offsets[0]; else for (size_t i = 0; i < n; i++) total += lens[i];
   if ((u64)arenaLen0 + total + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
   Rollback rb{this, hostLen0};
-  struct MirrorJoin { Engine* e; ~MirrorJoin() { mirror_wait(e->ctx); } } mirrorJoin{this};   // declared after rb: joins first
-  size_t cur = arenaLen0; bool uploaded = false;
-  const size_t Bq = queue.size();
-  if (blob && n > 0 && !hostScan) {
-    // bulk path: no per-change host work beyond one (offset, length) pair; DEFLATEd changes are detected on the device
-    const size_t base = offsets[0]; const size_t tot = offsets[n] - base;
-    hostArena.resize(cur + tot); arena.ensure(ctx, cur + tot + 64, arenaLen0);
-    bool callerPinned = false;
+  struct CopyJoin { Engine* e; ~CopyJoin() { copy_join(e->ctx); } } copyJoin{this};   // nothing of this call is left on the copy stream, also on the error paths
+  size_t cur = arenaLen0;
+  const size_t Bq = queue.size(); const size_t B = n + Bq;
+  if (B == 0) { rb.armed = false; fillPatchHeader(out); finishPatch(out); return; }
+  enum { SRC_PINNED, SRC_DEVICE, SRC_PAGEABLE } srcKind = SRC_PAGEABLE;
 #ifndef AMG_EMU
-    { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, blob) == cudaSuccess && at.type == cudaMemoryTypeHost) callerPinned = true; else cudaGetLastError(); }
+  if (blob && n > 0) { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, blob) == cudaSuccess) { if (at.type == cudaMemoryTypeHost) srcKind = SRC_PINNED; else if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) srcKind = SRC_DEVICE; } else cudaGetLastError(); }
 #endif
-    dbgMark("stage:attrs");
-    if (callerPinned) {
-      // the caller's buffer is pinned: DMA straight from it; the host mirror is filled from the device copy by the copy
-      // engine while the kernels run (a CPU copy of the same bytes took longer than the whole device pipeline)
-      // in pieces, so that the copy back of piece k (device -> host, the other PCIe direction) overlaps the upload of piece k + 1
-      // (splitting the upload itself over two streams / copy engines was measured: no gain)
-      const size_t kPiece = 16u << 20;
-      for (size_t o = 0; o < tot; o += kPiece) {
-        const size_t m = std::min(kPiece, tot - o);
-        h2d(ctx, arena.p + cur + o, blob + base + o, m);
-        mirror_start(ctx, hostArena.data() + cur + o, arena.p + cur + o, m);
-      }
-      dbgMark("stage:h2d-enqueued");
-    } else {
-      const size_t kChunk = 32u << 20;   // copy into the pinned mirror and upload chunk by chunk (H2D overlaps the next host copy)
-      for (size_t o = 0; o < tot; o += kChunk) {
-        const size_t m = std::min(kChunk, tot - o);
-        parallel_copy(hostArena.data() + cur + o, blob + base + o, m);
-        h2d(ctx, arena.p + cur + o, hostArena.data() + cur + o, m);
-      }
-    }
-    const u32 shift = (u32)(cur - base);
-    batch.resize(n + Bq);   // after the DMA is under way: everything the host does from here to the next device read is in its shadow
+  const bool throughMirror = srcKind == SRC_PAGEABLE && total > 0;
+  if (throughMirror) { ensureHostMirror(); hostArena.resize(arenaLen0 + total); }
+  arena.ensure(ctx, arenaLen0 + total + 64, arenaLen0);
+  dbgMark("stage:begin");
+  // (offset, length) of every change: the host's list, the device's chOff / chLen. Pieces end on change boundaries.
+  batch.resize(B);
+  const size_t kPiece = 16u << 20;
+  struct Piece { size_t byteEnd, changeEnd; };
+  std::vector<Piece> pieces;
+  if (blob && n > 0) {
+    const size_t base = offsets[0]; const u32 shift = (u32)(arenaLen0 - base);
     for (size_t i = 0; i < n; i++) { batch[i].off = (u32)offsets[i] + shift; batch[i].len = (u32)(offsets[i + 1] - offsets[i]); }
-    uploaded = true; cur += tot; dbgMark("stage:batch-filled");
-  } else {
-    batch.resize(n + Bq);
-    for (size_t i = 0; i < n; i++) {
-      const u8* p = blob ? blob + offsets[i] : bufs[i]; const size_t l = blob ? (size_t)(offsets[i + 1] - offsets[i]) : lens[i];
-      hostArena.append(p, l); batch[i] = HostChange{(u32)cur, (u32)l}; cur += l;
+    for (size_t o = kPiece;; o += kPiece) {
+      if (o >= total) { pieces.push_back({total, n}); break; }
+      const size_t ce = (size_t)(std::upper_bound(offsets, offsets + n + 1, (u64)(base + o)) - offsets) - 1;   // changes that end inside the first o bytes
+      pieces.push_back({(size_t)(offsets[ce] - base), ce});
     }
+  } else {
+    size_t at = 0, nextCut = kPiece;
+    for (size_t i = 0; i < n; i++) {
+      batch[i] = HostChange{(u32)(arenaLen0 + at), (u32)lens[i]}; at += lens[i];
+      if (at >= nextCut && i + 1 < n) { pieces.push_back({at, i + 1}); nextCut = at + kPiece; }
+    }
+    pieces.push_back({at, n});
   }
+  cur = arenaLen0 + total;
   if (Bq > 0) {
-    if (batchOriginal.empty()) batchOriginal.assign(n + Bq, HostChange{0, 0});
+    batchOriginal.assign(B, HostChange{0, 0});
     for (size_t i = 0; i < Bq; i++) { batch[n + i] = queue[i]; batchOriginal[n + i] = queueOriginal[i]; }
   }
-  const size_t B = batch.size();
-  if (B == 0) { rb.armed = false; fillPatchHeader(out); finishPatch(out); return; }
-  arena.ensure(ctx, cur + 64, arenaLen0);
-  if (!uploaded) h2d(ctx, arena.p + arenaLen0, hostArena.data() + arenaLen0, cur - arenaLen0);
-  dev_memset(ctx, arena.p + cur, 0, 64);
   chPairs.ensure(ctx, B); chOff.ensure(ctx, B); chLen.ensure(ctx, B);
   h2d(ctx, chPairs.p, batch.data(), B * sizeof(HostChange));
-  dbgMark("stage:pairs-h2d");
   foreach(ctx, B, SplitPairsKernel{chPairs.p, chOff.p, chLen.p});
-  dbgMark("stage:done");
-  timer.mark(); hostMark();
-  // ------------------------------------------------------------ 1. hash + header parse
+  dev_memset(ctx, arena.p + cur, 0, 64);
   dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull;
   hashes.ensure(ctx, (numApplied + B) * 32 + 64, numApplied * 32);
+  deflList.ensure(ctx, B + 1);
+  u8* hashOut = hashes.p + numApplied * 32;
+  const DecodeTilesArgs dargs = decodeArgs(arena.p, B, cur - arenaLen0);
+  decode_tiles_begin(ctx, dargs);
+  copy_fork(ctx);   // the copy stream starts behind what is queued on the main stream so far (arena growth, tables)
+  struct SideJoin { Ctx& c; ~SideJoin() { side_join(c); } } sideJoin{ctx};   // also on the error paths: nothing of this call outlives it on the side stream
+  dbgMark("stage:tables");
+  // changes [c0, c1) are on the device once the copy stream has passed `ev`: hash on the side stream, decode on the main one
+  auto processRange = [&](size_t c0, size_t c1, bool waitCopy) {
+    if (c1 <= c0) return;
+    if (waitCopy) copy_piece_done(ctx);   // both streams wait for the piece
+    else side_fork(ctx);
+    ShaKernel sk{arena.p, chOff.p, chLen.p, hashOut, errWord.p, nullptr, deflList.p}; sk.first = c0;
+    foreach(ctx, c1 - c0, sk, true);
+    decode_tiles_range(ctx, dargs, (u32)c0, (u32)c1);
+  };
+  if (Bq > 0) processRange(n, B, false);   // queue entries: their bytes are on the device already
   {
-    // Which changes of the bulk batch are DEFLATEd (columnar.js:742)? Those are inflated on the device, behind the batch:
+    size_t byte0 = 0, ch0 = 0;
+    for (const Piece& pc : pieces) {
+      const size_t m = pc.byteEnd - byte0;
+      if (m > 0) {
+        u8* dst = arena.p + arenaLen0 + byte0;
+        if (srcKind == SRC_PINNED) h2d_copy(ctx, dst, blob + offsets[0] + byte0, m);
+        else if (srcKind == SRC_DEVICE) d2d_copy(ctx, dst, blob + offsets[0] + byte0, m);
+        else {
+          u8* stage = hostArena.data() + arenaLen0 + byte0;
+          if (blob) parallel_copy(stage, blob + offsets[0] + byte0, m);
+          else parallel_gather(stage, bufs, lens, ch0, pc.changeEnd);
+          h2d_copy(ctx, dst, stage, m);
+        }
+      }
+      processRange(ch0, pc.changeEnd, true);
+      byte0 = pc.byteEnd; ch0 = pc.changeEnd;
+    }
+  }
+  dbgMark("stage:enqueued");
+  timer.mark(); hostMark();
+  // ------------------------------------------------------------ 1. DEFLATEd changes
+  {
+    // Which changes of the batch are DEFLATEd (columnar.js:742)? Those are inflated on the device, behind the batch:
     // flag -> scan -> ordered list -> InflateKernel pass 0 (sizes) -> scan -> pass 1 (bytes); the originals stay in place.
-    emit.ensure(ctx, B + 1); slot.ensure(ctx, B + 2); deflList.ensure(ctx, B + 1);
+    // The hash / decode kernels above skipped them; they are hashed and decoded here, from the inflated bytes.
+    emit.ensure(ctx, B + 1); slot.ensure(ctx, B + 2);
     foreach(ctx, B, DeflateFlagKernel{arena.p, chOff.p, chLen.p, emit.p});
     scan_exclusive(ctx, scanTmp, emit.p, slot.p, B);
     const size_t nd = readU32(slot.p + B);
     dbgMark("sha:deflate-scanned");
-    // the SHA-256 of the whole batch (ALU-bound, ~0.5 ms at 1M changes) runs on the side stream while the few
-    // DEFLATEd changes are inflated, laid out and hashed on the main one; joined before the header parse
-    side_fork(ctx);
-    struct SideJoin { Ctx& c; ~SideJoin() { side_join(c); } } sideJoin{ctx};   // also on the error paths: nothing of this call outlives it on the side stream
-    foreach(ctx, B, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, nullptr, nd ? deflList.p : nullptr}, true);
     if (nd > 0) {
       foreach(ctx, B, CompactKernel{emit.p, slot.p, deflList.p});
       inflLen.ensure(ctx, nd + 1); inflOff.ensure(ctx, nd + 2); patchTriples.ensure(ctx, 2 * nd + 2);
@@ -204,21 +244,20 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       { u64 ew0 = 0; d2h(ctx, &ew0, errWord.p, 8); sync(ctx); if (ew0) throwKernelError(ew0, actorIds); }
       if ((u64)cur + extra + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
       const size_t extraStart = cur; cur += extra;
+      side_join(ctx);   // the arena may move: nothing may still be reading it
       arena.ensure(ctx, cur + 64, extraStart);
       foreach_warp(ctx, nd, InflateKernel{1, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, inflOff.p, (u32)extraStart, origOff, origLen, errWord.p});
       dev_memset(ctx, arena.p + cur, 0, 64);
-      side_join(ctx);
       foreach(ctx, nd, InflatePatchKernel{deflList.p, inflLen.p, inflOff.p, (u32)extraStart, chOff.p, chLen.p});
-      foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashes.p + numApplied * 32, errWord.p, deflList.p, nullptr});
+      foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashOut, errWord.p, deflList.p, nullptr});
       inflNd = nd; inflExtraStart = extraStart; inflExtra = extra; inflPending = true;   // host bookkeeping happens in finishInflate()
       dbgMark("sha:inflated");
     }
   }
+  // changes the tile kernel passed on (inflated ones, changes outside their tile's window), then the totals
+  { DecodeTilesArgs fin = dargs; fin.arena = arena.p; decode_tiles_finish(ctx, fin, B); }
   side_join(ctx);
   timer.mark(); hostMark();
-  // header parse + column expansion of every change of the batch in one pass over the bytes (decode.cuh). Rows land in
-  // batch order; which changes are applied is decided by the gate below, FinalizeOpsKernel then picks their rows.
-  runDecodeTiles(arena.p, B, cur - arenaLen0);
   // (parse errors surface with the first host round trip of the gate: the error word travels with every small read, and a
   //  change that failed to parse has zero deps / ops so the kernels in between have nothing to walk)
   // ------------------------------------------------------------ 2. causal gate
@@ -243,7 +282,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       readWords({{flagWord.p, 4}, {flagWord.p + 12, 4}, {decTotals.p, 4}, {decTotals.p + 1, 4}, {decTotals.p + 2, 4}, {decTotals.p + 3, 4}}, dst); }
     checkErr(actorIds);   // free: the error word came with the read
     if (iter == 0 && decodeOverflowed(decTot)) {   // the raw row tables were too small for this batch: grown, decoded again (same results otherwise)
-      runDecodeTiles(arena.p, B, cur - arenaLen0);
+      runDecodeTiles(arena.p, B, cur - arenaLen0);   // the whole batch is resident by now (inflated changes re-pointed)
       void* d2[4] = {&decTot[0], &decTot[1], &decTot[2], &decTot[3]};
       readWords({{decTotals.p, 4}, {decTotals.p + 1, 4}, {decTotals.p + 2, 4}, {decTotals.p + 3, 4}}, d2);
       if (decTot[2]) throw Error(AMG_ERR_INTERNAL, "amgpu: decode row tables overflowed twice");
@@ -624,11 +663,10 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   fillPatchHeader(out);
   if (isLocal && n == 1) {   // new.js:1874-1877
     std::vector<ChangeHot> m0(1); d2h(ctx, m0.data(), hot.p, sizeof(ChangeHot)); sync(ctx);
-    mirror_wait(ctx);
-    out.hasActorSeq = true; out.actor.assign((const char*)hostArena.data() + m0[0].actorOff, m0[0].actorLen); out.seq = m0[0].seq;
+    out.hasActorSeq = true; out.actor.assign(m0[0].actorLen, '\0'); out.seq = m0[0].seq;
+    if (m0[0].actorLen) { d2h(ctx, &out.actor[0], arena.p + m0[0].actorOff, m0[0].actorLen); sync(ctx); }
   }
   dbgMark("commit:end");
-  mirror_wait(ctx); dbgMark("commit:mirror-done");
   lastB = B; lastM = M; lastP = P; lastBytes = cur - arenaLen0; for (auto& c : queue) lastBytes += 0 * c.len;
   finishPatch(out); dbgMark("call:patch-finished");
   timer.collect(lastPhaseMs, 12); dbgMark("call:timers-collected");
@@ -839,14 +877,29 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   }
   if (wholeDoc && numEdits > 0) foreach(ctx, numEdits, RunFlagKernel{editOut.p, editElem.p, numEdits});
   out.numProps = numProps; out.numEdits = numEdits;
-  out.propsOff = 18 * 8; out.editsOff = out.propsOff + numProps * sizeof(PropRec);
-  if (shipElem) { out.elemOff = out.editsOff + numEdits * sizeof(EditRec); out.bigEnd = out.elemOff + numEdits * 8; }
-  else { out.elemOff = 0; out.bigEnd = out.editsOff + numEdits * sizeof(EditRec); }   // elemOff 0: every insert's elemId is its opId
+  out.propsOff = PATCH_HDR_WORDS * 8; out.editsOff = out.propsOff + numProps * sizeof(PropRec);
+  size_t end;
+  if (shipElem) { out.elemOff = out.editsOff + numEdits * sizeof(EditRec); end = out.elemOff + numEdits * 8; }
+  else { out.elemOff = 0; end = out.editsOff + numEdits * sizeof(EditRec); }   // elemOff 0: every insert's elemId is its opId
+  // key and value bytes of the records: gathered behind them, offsets rewritten to positions inside the patch
+  const size_t nRec = numProps + numEdits; size_t nBytes = 0;
+  out.valBytesOff = end;
+  if (nRec > 0) {
+    patchByteLen.ensure(ctx, nRec + 1); patchByteOff.ensure(ctx, nRec + 2);
+    foreach(ctx, nRec, PatchBytesCountKernel{propOut.p, numProps, editOut.p, patchByteLen.p});
+    scan_exclusive(ctx, scanTmp, patchByteLen.p, patchByteOff.p, nRec);
+    nBytes = readU32(patchByteOff.p + nRec);
+    if ((u64)end + nBytes >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: patch larger than 4 GiB");
+    patchBytesD.ensure(ctx, nBytes + 8);
+    foreach(ctx, nRec, PatchBytesGatherKernel{arena.p, propOut.p, numProps, editOut.p, patchByteOff.p, (u32)out.valBytesOff, patchBytesD.p});
+  }
+  out.valBytesLen = nBytes; out.bigEnd = (out.valBytesOff + nBytes + 7) & ~(size_t)7;
   patchBuf.ensure(out.bigEnd + 4096);
   // the copy-out runs on the side stream: the caller joins it before reading the patch, later kernels overlap it
   side_fork(ctx);
   d2h_side(ctx, patchBuf.p + out.propsOff, propOut.p, numProps * sizeof(PropRec));
   if (numEdits > 0) { d2h_side(ctx, patchBuf.p + out.editsOff, editOut.p, numEdits * sizeof(EditRec)); if (shipElem) d2h_side(ctx, patchBuf.p + out.elemOff, editElem.p, numEdits * 8); }
+  if (nBytes > 0) d2h_side(ctx, patchBuf.p + out.valBytesOff, patchBytesD.p, nBytes);
 }
 
 inline void Engine::getPatch(PatchOut& out) {
@@ -870,17 +923,20 @@ inline RawRows Engine::rawRows() {
 }
 // Fused header parse + column expansion of B changes (chOff / chLen are on the device). The raw row tables are sized from
 // what earlier calls needed (else from the batch size); the kernel never writes outside them and reports an overflow.
-inline void Engine::runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes) {
+inline DecodeTilesArgs Engine::decodeArgs(const u8* arenaP, size_t B, size_t batchBytes) {
   hot.ensure(ctx, B + 1); nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
   rawBase.ensure(ctx, B + 2); rawPredBase.ensure(ctx, B + 2); decErr.ensure(ctx, B + 1); decTotals.ensure(ctx, 4);
-  decCursor.ensure(ctx, 2); const u32 numTiles = decode_num_tiles(B); decDirect.ensure(ctx, B + 2);
+  decCursor.ensure(ctx, 2); decDirect.ensure(ctx, B + 2);
   const size_t wantRows = std::max(decWantRows, B + B / 4 + batchBytes / 256 + 1024), wantPreds = std::max(decWantPreds, B + B / 4 + batchBytes / 256 + 1024);
   for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, wantRows + 1);
   r_predActor.ensure(ctx, wantPreds + 1); r_predCtr.ensure(ctx, wantPreds + 1);
   decRowCap = wantRows; decPredCap = wantPreds;
-  DecodeTilesArgs a{arenaP, chOff.p, chLen.p, (u32)B, hot.p, nOps.p, nPreds.p, nDeps.p, nActors.p, rawBase.p, rawPredBase.p, decErr.p, rawRows(), (u32)wantRows, (u32)wantPreds,
-                    (unsigned long long*)decCursor.p, decTotals.p, errWord.p, numTiles, decDirect.p + 1, decDirect.p};
-  decode_tiles(ctx, a);
+  return DecodeTilesArgs{arenaP, chOff.p, chLen.p, (u32)B, 0u, hot.p, nOps.p, nPreds.p, nDeps.p, nActors.p, rawBase.p, rawPredBase.p, decErr.p, rawRows(), (u32)wantRows, (u32)wantPreds,
+                         (unsigned long long*)decCursor.p, decTotals.p, errWord.p, 0u, decDirect.p + 1, decDirect.p};
+}
+inline void Engine::runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes) {
+  const DecodeTilesArgs a = decodeArgs(arenaP, B, batchBytes);
+  decode_tiles_begin(ctx, a); decode_tiles_range(ctx, a, 0, (u32)B); decode_tiles_finish(ctx, a, B);
 }
 inline bool Engine::decodeOverflowed(const u32 totals[4]) {
   if (!totals[2]) return false;
@@ -1113,8 +1169,10 @@ inline void Engine::computeHashGraph() {
   }
   hmark("heads checked");
   // ---- 9. commit: bytes into the arena and its host mirror, hashes, change table
-  hostArena.resize(arenaLen + T);
-  if (T) d2h(ctx, hostArena.data() + arenaLen, arena.p + arenaLen, T);
+  if (hostArena.size() == arenaLen) {   // the mirror is complete: keep it complete (otherwise it is fetched when asked for)
+    hostArena.resize(arenaLen + T);
+    if (T) d2h(ctx, hostArena.data() + arenaLen, arena.p + arenaLen, T);
+  }
   d2d(ctx, hashes.p, newHashes.p, L * 32);
   std::vector<u32> offH(L), lenH(L); d2h(ctx, offH.data(), chOffD.p, L * 4); d2h(ctx, lenH.data(), outLen.p, L * 4); sync(ctx);
   for (size_t k = 0; k < L; k++) changes[k] = HostChange{offH[k], lenH[k]};

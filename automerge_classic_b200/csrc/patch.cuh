@@ -26,6 +26,31 @@ struct EditRec { u64 obj, opId; u32 index, kind /* 0 insert 1 remove 2 update | 
 enum { EK_INSERT = 0, EK_REMOVE = 1, EK_UPDATE = 2 };
 enum { EF_POP = 0x400, EF_GROUP_FIRST = 0x800, EF_START = 0x100, EF_MULTI = 0x200, EF_COUNTER = 0x1000 /* value = int64 (valOff:valLen), not arena bytes */ };
 
+// The bytes the patch records point at (map keys, value payloads) travel inside the patch: counted per record, laid out by
+// a prefix sum, copied from the arena; the records' offsets are rewritten to positions in the patch buffer. (The host no
+// longer needs a mirror of the arena to read a patch.)
+struct PatchBytesCountKernel {
+  const PropRec* props; size_t numProps; const EditRec* edits; u32* len;
+  HD void operator()(size_t i) const {
+    if (i < numProps) { const PropRec& r = props[i]; len[i] = (r.keyLen == 0xffffffffu ? 0u : r.keyLen) + ((r.flags & 2u) ? 0u : (r.valLen >> 4)); }
+    else { const EditRec& r = edits[i - numProps]; len[i] = (r.kind & EF_COUNTER) ? 0u : (r.valLen >> 4); }
+  }
+};
+struct PatchBytesGatherKernel {
+  const u8* arena; PropRec* props; size_t numProps; EditRec* edits; const u32* off; u32 bytesOff /* of the section inside the patch */; u8* out;
+  HD void operator()(size_t i) const {
+    u32 at = off[i];
+    if (i < numProps) {
+      PropRec& r = props[i];
+      if (r.keyLen != 0xffffffffu) { for (u32 k = 0; k < r.keyLen; k++) out[at + k] = arena[r.keyOff + k]; r.keyOff = bytesOff + at; at += r.keyLen; }
+      if (!(r.flags & 2u)) { const u32 n = r.valLen >> 4; for (u32 k = 0; k < n; k++) out[at + k] = arena[r.valOff + k]; r.valOff = bytesOff + at; }
+    } else {
+      EditRec& r = edits[i - numProps];
+      if (!(r.kind & EF_COUNTER)) { const u32 n = r.valLen >> 4; for (u32 k = 0; k < n; k++) out[at + k] = arena[r.valOff + k]; r.valOff = bytesOff + at; }
+    }
+  }
+};
+
 // ---------------------------------------------------------------- per-position state in document order
 struct GroupHeadKernel {   // group = rows of one map key / one list element (insert row + its update rows), adjacent in document order
   const u8* arena; DocRows d; u32* head;

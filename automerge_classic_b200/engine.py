@@ -128,9 +128,9 @@ def empty_object_patch(object_id, action):
 class FlatPatch:
     """Zero-copy view of the flat patch table (layout in include/amgpu.h)."""
 
-    def __init__(self, raw, arena):
-        self.raw, self.arena = raw, arena
-        h = self.hdr = np.frombuffer(raw, dtype='<u8', count=18)
+    def __init__(self, raw):
+        self.raw = self.arena = raw   # keyOff / valOff of the records index the patch buffer itself (its bytes section)
+        h = self.hdr = np.frombuffer(raw, dtype='<u8', count=20)
         assert int(h[0]) == 0x31504747414d41, 'bad patch magic'
         self.max_op, self.pending = int(h[1]), int(h[2])
         self.actor_seq = None
@@ -286,7 +286,7 @@ class GpuBackendDoc:
         p = self._lib.L.amg_patch_bytes(pp, C.byref(n))
         raw = bytes((C.c_uint8 * n.value).from_address(p))
         self._lib.L.amg_patch_free(pp)
-        return FlatPatch(raw, self._arena())
+        return FlatPatch(raw)
 
     def _buffers(self, bl):
         L = self._lib.L
