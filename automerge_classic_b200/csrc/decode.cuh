@@ -215,25 +215,28 @@ HD u32 load_be32(const u8* p) {
   return (u32)p[0] << 24 | (u32)p[1] << 16 | (u32)p[2] << 8 | p[3];
 #endif
 }
-// One compression. The 64 rounds run as 4 iterations of a 16-round body: inside the body every w[] index is a
-// compile-time constant (the schedule stays in registers) while the code stays small enough for the instruction
-// cache (a fully unrolled 64-round body made ShaKernel stall on instruction fetch: ncu "no_instruction").
+// One compression: 16 rounds on the message words as they are, then 3 x 16 rounds with the message schedule. Inside a
+// 16-round body every w[] index is a compile-time constant (the schedule stays in registers) while the code stays small
+// enough for the instruction cache (a fully unrolled 64-round body made ShaKernel stall on instruction fetch: ncu
+// "no_instruction"); the first 16 rounds are peeled so that no round carries a "schedule or not" test.
+template <bool SCHEDULE> HD void sha256_rounds16(u32& a, u32& b, u32& c, u32& d, u32& e, u32& f, u32& g, u32& hh, u32* w, const u32* K) {
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    if (SCHEDULE) {
+      const u32 w15 = w[(j + 1) & 15], w2 = w[(j + 14) & 15];
+      const u32 s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3), s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+      w[j] = w[j] + s0 + w[(j + 9) & 15] + s1;
+    }
+    const u32 t1 = hh + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + K[j] + w[j];
+    const u32 t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+  }
+}
 HD void sha256_compress(u32* h, u32* w, const u32* K) {
   u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+  sha256_rounds16<false>(a, b, c, d, e, f, g, hh, w, K);
 #pragma unroll 1
-  for (int r = 0; r < 64; r += 16) {
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-      if (r > 0) {
-        const u32 w15 = w[(j + 1) & 15], w2 = w[(j + 14) & 15];
-        const u32 s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3), s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
-        w[j] = w[j] + s0 + w[(j + 9) & 15] + s1;
-      }
-      const u32 t1 = hh + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + K[r + j] + w[j];
-      const u32 t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
-      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
-    }
-  }
+  for (int r = 16; r < 64; r += 16) sha256_rounds16<true>(a, b, c, d, e, f, g, hh, w, K + r);
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
 
@@ -264,27 +267,36 @@ struct ShaKernel {
 #endif
     u32 h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
     const u8* m = p + 8; const u32 mlen = len - 8;
-    // blocks: all full 64-byte blocks, then one or two padded blocks (0x80, zeros, 64-bit bit length); one call site
+    // blocks: all full 64-byte blocks, then one or two padded blocks (0x80, zeros, 64-bit bit length); one call site.
+    // Message word i of a block = 4 bytes at an arbitrary address: two aligned 32-bit loads (the second is the next word's
+    // first), funnel shift, byte swap; words that reach past the message end are masked, never loaded past it.
     const u32 nBlocks = (mlen + 9 + 63) / 64; u32 w[16];
+#if defined(__CUDA_ARCH__)
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
+    const u32* aw = reinterpret_cast<const u32*>(m - (addr & 3)); const u32 sh = (u32)(addr & 3) * 8;   // (pointer arithmetic on m: the loads stay global loads)
+    const u32 lastAligned = (mlen + (u32)(addr & 3) + 3) / 4;   // aligned words [0, lastAligned) hold message bytes
+#endif
     for (u32 blk = 0; blk < nBlocks; blk++) {
       const u32 done = blk * 64;
-      if (done + 64 <= mlen) {
+#if defined(__CUDA_ARCH__)
+      const u32 k0 = done / 4;
+      u32 lo = k0 < lastAligned ? aw[k0] : 0u;
 #pragma unroll
-        for (int i = 0; i < 16; i++) w[i] = load_be32(m + done + 4 * i);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          u32 v = 0;
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            const u32 ix = done + 4 * i + b; u32 byte = 0;
-            if (ix < mlen) byte = m[ix]; else if (ix == mlen) byte = 0x80;
-            v = (v << 8) | byte;
-          }
-          w[i] = v;
-        }
-        if (blk == nBlocks - 1) { w[14] = (u32)(((u64)mlen * 8) >> 32); w[15] = (u32)((u64)mlen * 8); }
+      for (int i = 0; i < 16; i++) {
+        const u32 hi = (k0 + i + 1 < lastAligned) ? aw[k0 + i + 1] : 0u;
+        u32 v = __byte_perm(__funnelshift_r(lo, hi, sh), 0, 0x0123);
+        const int rem = (int)mlen - (int)(done + 4 * i);   // message bytes from this word on
+        if (rem < 4) v = rem <= 0 ? (rem == 0 ? 0x80000000u : 0u) : ((v & (0xffffffffu << (32 - 8 * rem))) | (0x80u << (24 - 8 * rem)));
+        w[i] = v; lo = hi;
       }
+#else
+      for (int i = 0; i < 16; i++) {
+        u32 v = 0;
+        for (int b = 0; b < 4; b++) { const u32 ix = done + 4 * i + b; u32 byte = 0; if (ix < mlen) byte = m[ix]; else if (ix == mlen) byte = 0x80; v = (v << 8) | byte; }
+        w[i] = v;
+      }
+#endif
+      if (blk == nBlocks - 1) { w[14] = (u32)(((u64)mlen * 8) >> 32); w[15] = (u32)((u64)mlen * 8); }
       sha256_compress(h, w, K);
     }
     u8* out = hashOut + c * 32;
@@ -848,9 +860,10 @@ struct DecodeColumnKernel {
 #define AMG_PARSE_MINBLOCKS 4
 #endif
 template <> struct LaunchTraits<ParseKernel> { static const int minBlocks = AMG_PARSE_MINBLOCKS; };
-#ifdef AMG_SHA_MINBLOCKS
-template <> struct LaunchTraits<ShaKernel> { static const int minBlocks = AMG_SHA_MINBLOCKS; };
+#ifndef AMG_SHA_MINBLOCKS
+#define AMG_SHA_MINBLOCKS 3
 #endif
+template <> struct LaunchTraits<ShaKernel> { static const int minBlocks = AMG_SHA_MINBLOCKS; };
 struct LargeFlagKernel { const u32* nOps; const u8* applied; u32* flag; HD void operator()(size_t c) const { flag[c] = (applied[c] && nOps[c] > SMALL_CHANGE_OPS) ? 1u : 0u; } };
 
 }  // namespace amg

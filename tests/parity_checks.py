@@ -5,6 +5,28 @@ import numpy as np
 import replay
 
 
+def patch_digest(patch):
+    """SHA-256 of a patch in canonical form: JSON with sorted object keys (assert.deepStrictEqual ignores key order), arrays
+    (edits, deps) in order, bytes as hex. The same function digests the oracle's patch (tests/golden/make_full_size.py)
+    and the engine's (GPU tests), so equal digests mean deep-equal patches."""
+    import hashlib
+    import json
+
+    def canon(v):
+        if isinstance(v, dict):
+            if set(v.keys()) == {'$bytes'}:
+                return {'$bytes': v['$bytes']}
+            return {k: canon(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return [canon(x) for x in v]
+        if isinstance(v, (bytes, bytearray, memoryview)):
+            return {'$bytes': bytes(v).hex()}
+        if type(v).__name__ in ('_Undefined', 'Undef'):
+            return {'$undefined': True}
+        return v
+    return hashlib.sha256(json.dumps(canon(patch), sort_keys=True, separators=(',', ':'), ensure_ascii=True).encode()).hexdigest()
+
+
 def _dump_equal(gpu, orc):
     """document-ordered op table + succ lists (SURVEY.md §8c parity item 3)"""
     gr, gs = gpu.dump_ops()
@@ -360,6 +382,28 @@ def check_full_size_properties(gpu_doc, n_ops=1000000, n_actors=10, calls=10, go
     # the incremental patch of the bulk call inserts / removes exactly what the final document shows
     kinds = fp.edits['kind'] & 0xff
     assert int((kinds == 0).sum()) - int((kinds == 1).sum()) == len(a.edits)
+
+
+def check_full_size_fingerprint(gpu_doc, cfg):
+    """BASELINE.json's full size of config `cfg` against the ORACLE's committed fingerprint (tests/golden/full_size.json,
+    generated by tests/golden/make_full_size.py): the incremental patch of applyChanges(init(), all changes), getPatch(),
+    save() bytes, heads and maxOp of the CUDA engine digest to what the oracle produced."""
+    import hashlib
+    import json
+    import os
+    from automerge_classic_b200 import tracegen
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'full_size.json')))[cfg]
+    t = tracegen.generate(cfg, {'C3': 1000000, 'C4': 1000000, 'C2': 100000, 'C2b': 100000}[cfg], gold['n_actors'])
+    assert t.n_ops == gold['n_ops'] and t.n_changes == gold['n_changes'] and int(t.offsets[-1]) == gold['change_bytes']
+    g = gpu_doc()
+    fp = g.apply_packed_flat(t.blob, t.offsets, t.n_changes)
+    assert fp.pending == 0 and fp.max_op == gold['max_op']
+    assert patch_digest(fp.to_patch(False)) == gold['patch_sha256'], 'incremental patch differs from the oracle\'s at full size (%s)' % cfg
+    del fp
+    assert g.heads() == gold['heads']
+    s = g.save()
+    assert len(s) == gold['save_bytes'] and hashlib.sha256(s).hexdigest() == gold['save_sha256'], 'save() differs from the oracle\'s at full size (%s)' % cfg
+    assert patch_digest(g.get_patch()) == gold['get_patch_sha256'], 'getPatch() differs from the oracle\'s at full size (%s)' % cfg
 
 
 def check_pointer_array_entry(gpu_doc, oracle_mod):

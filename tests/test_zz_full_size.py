@@ -15,3 +15,17 @@ def test_full_size_oracle_fingerprint():
     build.build_all()
     from automerge_classic_b200.engine import GpuBackendDoc
     parity_checks.check_full_size_properties(GpuBackendDoc, golden=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('cfg', ['C2', 'C2b', 'C4', 'C3'])
+def test_full_size_patch_and_document(cfg):
+    """Incremental patch, getPatch, save() and heads at BASELINE.json's full size of every workload against
+    the oracle's committed digests (tests/golden/full_size.json)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from automerge_classic_b200 import build
+    build.build_all()
+    from automerge_classic_b200.engine import GpuBackendDoc
+    parity_checks.check_full_size_fingerprint(GpuBackendDoc, cfg)
