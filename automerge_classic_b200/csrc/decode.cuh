@@ -37,7 +37,8 @@ enum KErr {
   KE_NONE = 0, KE_MAGIC, KE_CHECKSUM, KE_TRAILING, KE_CHUNK_TYPE, KE_TRUNCATED, KE_NUM_RANGE, KE_COL_ORDER, KE_COL_DEFLATE,
   KE_RLE_REP1, KE_RLE_SUCC_REP, KE_RLE_SUCC_LIT, KE_RLE_SUCC_NULL, KE_RLE_ZERO_NULL, KE_RLE_LIT_REP, KE_BOOL_ZERO,
   KE_OBJ_MISMATCH, KE_KEY_MISMATCH, KE_ACTOR_INDEX, KE_TOO_LARGE, KE_UNKNOWN_ACTOR, KE_PRED_MISSING, KE_REF_ELEM, KE_DUP_OPID,
-  KE_UNSUPPORTED_OP, KE_LAMPORT, KE_HASH_COLLISION, KE_LIST_ELEM, KE_PRED_ORDER, KE_DEFLATE, KE_UNKNOWN_COUNTER, KE_HIST_RANGE, KE_HIST_OPID, KE_HIST_DEP
+  KE_UNSUPPORTED_OP, KE_LAMPORT, KE_HASH_COLLISION, KE_LIST_ELEM, KE_PRED_ORDER, KE_DEFLATE, KE_UNKNOWN_COUNTER, KE_HIST_RANGE, KE_HIST_OPID, KE_HIST_DEP,
+  KE_SUBARRAY   // raw bytes (a string, a hash, a column, a chunk body) reach past the end: encoding.js:497, where a number that runs out is KE_TRUNCATED (:353)
 };
 // error word: (code << 32 | item index); the smallest item index wins so that the error reported is
 // the one the sequential reference would hit first within a phase.
@@ -123,7 +124,7 @@ template <class S> struct ByteReaderT {
     }
     err = KE_TRUNCATED; return 0;
   }
-  HD void skip(u64 n) { if ((u64)pos + n > end) { err = KE_TRUNCATED; pos = end; } else pos += (u32)n; }
+  HD void skip(u64 n) { if ((u64)pos + n > end) { err = KE_SUBARRAY; pos = end; } else pos += (u32)n; }   // readRawBytes: encoding.js:494-500
 };
 struct ByteReader : ByteReaderT<PtrSrc> {
   const u8* base;
@@ -423,7 +424,7 @@ template <class S> HD u32 decode_one_column_t(const S& arena, int col, u32 nOps,
         if (col == CX_VAL_LEN) { rows.valOff[base + i] = rawBase + running; running += nn ? (u32)((u64)n >> 4) : 0; }
         if (col == CX_PRED_NUM) { rows.predOff[base + i] = rawBase + running; running += nn ? (u32)n : 0; if (!nn) out[base + i] = 0; }
       }
-      if (col == CX_VAL_LEN && running > valRawLen) kerr = KE_TRUNCATED;
+      if (col == CX_VAL_LEN && running > valRawLen) kerr = KE_SUBARRAY;
       if (!kerr) kerr = r.r.err;
       break;
     }
@@ -549,7 +550,7 @@ template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedCh
   const u32 chunkType = r.done() ? 0xffu : src.ld(r.pos); r.pos++;
   const u64 chunkLen = r.uleb();
   if (r.err) { o.err = r.err; return; }
-  if ((u64)r.pos + chunkLen > (u64)end) { o.err = KE_TRUNCATED; return; }
+  if ((u64)r.pos + chunkLen > (u64)end) { o.err = KE_SUBARRAY; return; }
   if ((u64)r.pos + chunkLen != (u64)end) { o.err = KE_TRAILING; return; }
   if (chunkType != 1) { o.err = KE_CHUNK_TYPE; return; }
   const u64 nDeps = r.uleb(); const u32 depsOff = r.pos; r.skip(nDeps * 32);
@@ -577,7 +578,7 @@ template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedCh
       if (d.err) break;
       if (lastId >= 0 && ((u32)id64 & ~8u) <= ((u32)lastId & ~8u)) orderBad = true;
       lastId = (long long)id64;
-      if (!colErr) { if (id64 & 8) colErr = KE_COL_DEFLATE; else if ((u64)dataPos + total + l64 > (u64)end) colErr = KE_TRUNCATED; }
+      if (!colErr) { if (id64 & 8) colErr = KE_COL_DEFLATE; else if ((u64)dataPos + total + l64 > (u64)end) colErr = KE_SUBARRAY; }
       const u32 id = id64 > 0xffffffffULL ? 0xffffffffu : (u32)id64, l = (u32)l64, pos = dataPos + (u32)total;
       if (id == 0x42) { actOff = (u32)total; actLen = l; haveAct = true; } else if (id == 0x70) { pnOff = (u32)total; pnLen = l; }
       if (afterValLen) { afterValLen = false; if (id == 0x57) { sv.valOff = pos; rawLen = l; } }

@@ -196,6 +196,7 @@ class Engine {
       case KE_HIST_OPID: throw Error(AMG_ERR_RANGE, "Expected opId does not match the operation found");   // columnar.js:936
       case KE_HIST_DEP: throw Error(AMG_ERR_RANGE, "No hash for dependency index");                      // columnar.js:952
       case KE_TRUNCATED: throw Error(AMG_ERR_RANGE, "buffer ended with incomplete number");
+      case KE_SUBARRAY: throw Error(AMG_ERR_RANGE, "subarray exceeds buffer size");
       case KE_NUM_RANGE: throw Error(AMG_ERR_RANGE, "number out of range");
       case KE_COL_ORDER: throw Error(AMG_ERR_RANGE, "Columns must be in ascending order");
       case KE_COL_DEFLATE: throw Error(AMG_ERR_RANGE, "change must not contain deflated columns");
@@ -273,6 +274,7 @@ class Engine {
   void loadDocument(const u8* buf, size_t len);
   size_t historyRebuilt = 0;   // changes [0, historyRebuilt) were rebuilt by computeHashGraph (getChanges DEFLATEs the large ones like encodeChange does)
   DBuf<u64> excl64;
+  bool headIndexesUnknown = false;   // Backend.load of a document with several heads and no head indexes, until computeHashGraph has matched them
   bool haveHashGraph = true;   // false after Backend.load: change history (hashes, bytes) is not reconstructed (new.js:1887-1912)
   void benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes);
   RawRows rawRows();

@@ -73,7 +73,7 @@ inline void Engine::finishPatch(PatchOut& out) {
 
 // forgets the document but keeps every allocation (steady-state serving / benchmarking)
 inline void Engine::reset() {
-  sync(ctx);
+  sync(ctx); headIndexesUnknown = false;
   arenaLen = 0; hostArena.len = 0; numApplied = 0; numRows = 0; numSucc = 0; dev_memset(ctx, succOff.p, 0, 4);
   actorIds.clear(); actorRep.clear(); clock.clear(); heads.clear(); headIdx.clear(); changes.clear(); changeHashes.clear(); deflatedOriginal.clear(); loadedDoc.clear(); numLoaded = 0; historyRebuilt = 0; haveHashGraph = true;
   queue.clear(); queueOriginal.clear(); maxOp = 0; rebuildActorTable();
@@ -1160,7 +1160,18 @@ inline void Engine::computeHashGraph() {
     size_t nHeads = 0; for (size_t k = 0; k < L; k++) if (!isDep[k]) nHeads++;
     bool ok = numApplied != L || nHeads == heads.size();   // (changes applied after the load have moved the heads)
     std::vector<std::array<u8, 32>> got(heads.size());
-    if (numApplied == L) {
+    if (headIndexesUnknown) {   // loaded without head indexes: the heads are the changes nobody depends on, matched by hash
+      if (numApplied != L) throw Error(AMG_ERR_INTERNAL, "amgpu: head indexes must be resolved right after the load");
+      std::vector<u32> cand; for (size_t k = 0; k < L; k++) if (!isDep[k]) cand.push_back((u32)k);
+      ok = cand.size() == heads.size();
+      std::vector<std::array<u8, 32>> ch(cand.size());
+      if (ok) { for (size_t i = 0; i < cand.size(); i++) d2h(ctx, ch[i].data(), newHashes.p + (size_t)cand[i] * 32, 32); sync(ctx); }
+      for (size_t i = 0; i < heads.size() && ok; i++) {
+        size_t j = 0; while (j < cand.size() && ch[j] != heads[i]) j++;
+        if (j == cand.size()) ok = false; else headIdx[i] = cand[j];
+      }
+      if (ok) headIndexesUnknown = false;
+    } else if (numApplied == L) {
       for (size_t i = 0; i < heads.size(); i++) d2h(ctx, got[i].data(), newHashes.p + (size_t)headIdx[i] * 32, 32);
       sync(ctx);
       for (size_t i = 0; i < heads.size() && ok; i++) if (isDep[headIdx[i]] || got[i] != heads[i]) ok = false;
@@ -1423,9 +1434,9 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   lmark("container checksum");
   // columnar.js:1006-1038 decodeDocumentHeader
   std::vector<std::string> actors; const u64 numActors = r.uleb();
-  for (u64 i = 0; i < numActors && !r.err; i++) { const u64 l = r.uleb(); if ((u64)r.pos + l > len) { r.err = KE_TRUNCATED; break; } actors.emplace_back((const char*)buf + r.pos, l); r.skip(l); }
+  for (u64 i = 0; i < numActors && !r.err; i++) { const u64 l = r.uleb(); if ((u64)r.pos + l > len) { r.err = KE_SUBARRAY; break; } actors.emplace_back((const char*)buf + r.pos, l); r.skip(l); }
   std::vector<std::array<u8, 32>> hs; const u64 numHeads = r.uleb();
-  for (u64 i = 0; i < numHeads && !r.err; i++) { if ((u64)r.pos + 32 > len) { r.err = KE_TRUNCATED; break; } std::array<u8, 32> h; memcpy(h.data(), buf + r.pos, 32); hs.push_back(h); r.skip(32); }
+  for (u64 i = 0; i < numHeads && !r.err; i++) { if ((u64)r.pos + 32 > len) { r.err = KE_SUBARRAY; break; } std::array<u8, 32> h; memcpy(h.data(), buf + r.pos, 32); hs.push_back(h); r.skip(32); }
   struct ColInfo { u32 id; u64 len; std::string data; };
   auto readInfo = [&](std::vector<ColInfo>& cols) {
     const u64 n = r.uleb(); long long last = -1;
@@ -1507,7 +1518,10 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   }
   lmark("clock");
   if (!headsIndexes.empty() && headsIndexes.size() != hs.size()) headsIndexes.clear();
-  if (headsIndexes.empty()) { if (hs.size() == 1) headsIndexes.push_back((u32)(numChanges ? numChanges - 1 : 0)); else if (!hs.empty()) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: document without head indexes and several heads (needs decodeDocument, not built)"); }
+  // several heads without indexes (new.js:1734-1737: the hashes are known, their change indexes are not): the indexes are
+  // found by reconstructing the change history right after the load (computeHashGraph below)
+  bool headIdxUnknown = false;
+  if (headsIndexes.empty()) { if (hs.size() == 1) headsIndexes.push_back((u32)(numChanges ? numChanges - 1 : 0)); else if (!hs.empty()) { headIdxUnknown = true; headsIndexes.assign(hs.size(), 0xffffffffu); } }
   dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull; dev_memset(ctx, flagWord.p, 0, 16);
   // Number of rows = values of the action column, number of succ entries = sum of succNum. Long columns take the parallel
   // decoder (doccols.cuh); short, malformed or non-canonical ones the serial walkers, which also report the errors.
@@ -1589,16 +1603,17 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   lmark("rows finalized");
   // ---- change history placeholders: only the head hashes are known (new.js:1727-1739)
   hashes.ensure(ctx, numChanges * 32 + 64); dev_memset(ctx, hashes.p, 0, numChanges * 32 + 64);
-  for (size_t i = 0; i < hs.size(); i++) { if (headsIndexes[i] >= numChanges) throw Error(AMG_ERR_RANGE, "head index out of range"); h2d(ctx, hashes.p + (size_t)headsIndexes[i] * 32, hs[i].data(), 32); }
+  if (!headIdxUnknown) for (size_t i = 0; i < hs.size(); i++) { if (headsIndexes[i] >= numChanges) throw Error(AMG_ERR_RANGE, "head index out of range"); h2d(ctx, hashes.p + (size_t)headsIndexes[i] * 32, hs[i].data(), 32); }
   sync(ctx);
   numRows = N; numSucc = S; numApplied = numChanges; arenaLen = cur; maxOp = mx; actorIds = actors; actorRep = reps; clock = clk;
   heads = hs; headIdx = headsIndexes;
   { std::vector<size_t> o(heads.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i; std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return hs[a] < hs[b]; });
     for (size_t i = 0; i < o.size(); i++) { heads[i] = hs[o[i]]; headIdx[i] = headsIndexes[o[i]]; } }
-  changes.assign(numChanges, HostChange{0, 0}); haveHashGraph = false; loadedDoc.assign((const char*)buf, len); numLoaded = numChanges;
+  changes.assign(numChanges, HostChange{0, 0}); haveHashGraph = false; loadedDoc.assign((const char*)buf, len); numLoaded = numChanges; headIndexesUnknown = headIdxUnknown;
   lmark("host state");
   while (actorCap < 2 * (actorIds.size() + 16)) actorCap *= 2;
   actorSlots.ensure(ctx, actorCap); rebuildActorTable();
+  if (headIndexesUnknown) computeHashGraph();   // finds the heads' change indexes (and leaves the history rebuilt)
 }
 
 }  // namespace amg

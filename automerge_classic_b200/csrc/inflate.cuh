@@ -140,7 +140,7 @@ struct InflateKernel {
   HD void operator()(size_t k) const {
     const u32 c = list[k]; const u32 off = pass == 0 ? chOff[c] : origOff[k], len = pass == 0 ? chLen[c] : origLen[k];
     ByteReader r(arena, off + 9, off + len); const u64 clen = r.uleb();
-    if (r.err || (u64)r.pos + clen > (u64)off + len) { raise(errWord, KE_TRUNCATED, c); if (pass == 0) outLen[k] = 0; return; }
+    if (r.err || (u64)r.pos + clen > (u64)off + len) { raise(errWord, r.err ? r.err : (u32)KE_SUBARRAY, c); if (pass == 0) outLen[k] = 0; return; }
     if (pass == 0) {
       u32 n = 0; const u32 e = inflate_raw(arena, r.pos, r.pos + (u32)clen, nullptr, 0, &n);
       if (e) { raise(errWord, e, c); outLen[k] = 0; return; }

@@ -406,6 +406,67 @@ def check_full_size_fingerprint(gpu_doc, cfg):
     assert patch_digest(g.get_patch()) == gold['get_patch_sha256'], 'getPatch() differs from the oracle\'s at full size (%s)' % cfg
 
 
+def strip_heads_indexes(doc, oracle_mod):
+    """A saved document without the optional headsIndexes trailer (columnar.js:1031-1036 reads them only if bytes remain):
+    body re-framed, chunk length and checksum recomputed."""
+    def uleb(buf, pos):
+        v, sh = 0, 0
+        while True:
+            b = buf[pos]; pos += 1; v |= (b & 0x7f) << sh; sh += 7
+            if not b & 0x80:
+                return v, pos
+    doc = bytes(doc)
+    assert doc[8] == 0
+    _, pos = uleb(doc, 9)
+    body0 = pos
+    n, pos = uleb(doc, pos)
+    for _ in range(n):
+        l, pos = uleb(doc, pos); pos += l
+    nheads, pos = uleb(doc, pos); pos += 32 * nheads
+    total = 0
+    for _ in range(2):
+        ncols, pos = uleb(doc, pos)
+        for _ in range(ncols):
+            _, pos = uleb(doc, pos); l, pos = uleb(doc, pos); total += l
+    pos += total
+    assert pos < len(doc), 'the document has no headsIndexes trailer'
+    body = doc[body0:pos]
+    ln, v = bytearray(), len(body)
+    while True:
+        b = v & 0x7f; v >>= 7
+        ln.append(b | (0x80 if v else 0))
+        if not v:
+            break
+    framed = b'\x00' + bytes(ln) + body
+    return doc[:4] + oracle_mod.sha256(framed)[:4] + framed, nheads
+
+
+def check_load_without_head_indexes(gpu_doc, oracle_mod):
+    """Backend.load of a document with several heads and no headsIndexes (new.js:1734-1737 keeps the head hashes with
+    unknown indexes): the engine finds the indexes by reconstructing the change history; the loaded document gives the
+    oracle's getPatch and accepts changes that build on those heads like the oracle does."""
+    from automerge_classic_b200 import tracegen
+    all_changes = tracegen.generate('C3', 2400, 3).changes()
+    first = all_changes[:1201]
+    orc = oracle_mod.OracleDoc(); orc.apply_changes(first)
+    stripped, nheads = strip_heads_indexes(orc.save(), oracle_mod)
+    assert nheads > 1
+    o2, g2 = oracle_mod.OracleDoc(stripped), gpu_doc(stripped)
+    assert g2.heads() == o2.heads() and g2.clock() == o2.clock() and g2.max_op() == o2.max_op()
+    d = replay.deep_equal(replay.decode(g2.get_patch()), replay.decode(o2.get_patch()))
+    assert d is None, d
+    _dump_equal(g2, o2)
+    assert g2.save() == stripped                      # unchanged since the load: the same bytes (new.js:2034)
+    assert g2.get_changes([]) == first                # the history was reconstructed: byte-identical changes
+    rest = all_changes[1201:]
+    po, pg = o2.apply_changes(rest), g2.apply_changes(rest)
+    d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+    assert d is None, d
+    _dump_equal(g2, o2)
+    full = gpu_doc(); full.apply_changes(all_changes)
+    assert g2.save() == full.save()                   # as if the whole history had been applied to an empty document
+
+
 def check_pointer_array_entry(gpu_doc, oracle_mod):
     """amg_apply_changes (array of pointers, the N-API shape) gives the same result as the packed entry point and the oracle,
     including DEFLATEd changes and several calls."""

@@ -136,6 +136,10 @@ def test_load_saved_document(gpu_doc, oracle_mod, cfg, n, a):
     parity_checks.check_load(gpu_doc, oracle_mod, cfg, n, a)
 
 
+def test_load_without_head_indexes(gpu_doc, oracle_mod):
+    parity_checks.check_load_without_head_indexes(gpu_doc, oracle_mod)
+
+
 def test_load_rust_document(gpu_doc):
     parity_checks.check_rust_document(gpu_doc)
 

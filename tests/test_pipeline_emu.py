@@ -184,3 +184,7 @@ def test_local_changes_random_emu(emu_doc, oracle_mod):
 def test_out_of_order_waiting_copies_emu(emu_doc, oracle_mod, seed):
     # (seed 35 runs into the duplicated-successor quirk of the reference)
     assert parity_checks.check_out_of_order_random(emu_doc, oracle_mod, seed, sessions=15, waiting_copies=True) > 0
+
+
+def test_load_without_head_indexes_emu(emu_doc, oracle_mod):
+    parity_checks.check_load_without_head_indexes(emu_doc, oracle_mod)
