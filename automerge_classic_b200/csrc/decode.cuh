@@ -37,7 +37,7 @@ enum KErr {
   KE_NONE = 0, KE_MAGIC, KE_CHECKSUM, KE_TRAILING, KE_CHUNK_TYPE, KE_TRUNCATED, KE_NUM_RANGE, KE_COL_ORDER, KE_COL_DEFLATE,
   KE_RLE_REP1, KE_RLE_SUCC_REP, KE_RLE_SUCC_LIT, KE_RLE_SUCC_NULL, KE_RLE_ZERO_NULL, KE_RLE_LIT_REP, KE_BOOL_ZERO,
   KE_OBJ_MISMATCH, KE_KEY_MISMATCH, KE_ACTOR_INDEX, KE_TOO_LARGE, KE_UNKNOWN_ACTOR, KE_PRED_MISSING, KE_REF_ELEM, KE_DUP_OPID,
-  KE_UNSUPPORTED_OP, KE_LAMPORT, KE_HASH_COLLISION, KE_LIST_ELEM, KE_PRED_ORDER, KE_DEFLATE, KE_UNKNOWN_COUNTER, KE_HIST_RANGE, KE_HIST_OPID, KE_HIST_DEP,
+  KE_UNSUPPORTED_OP, KE_LAMPORT, KE_HASH_COLLISION, KE_LIST_ELEM, KE_PRED_ORDER, KE_DEFLATE, KE_UNKNOWN_COUNTER, KE_HIST_RANGE, KE_HIST_OPID, KE_HIST_DEP, KE_FLOAT_LEN /* columnar.js:316 */,
   KE_SUBARRAY   // raw bytes (a string, a hash, a column, a chunk body) reach past the end: encoding.js:497, where a number that runs out is KE_TRUNCATED (:353)
 };
 // error word: (code << 32 | item index); the smallest item index wins so that the error reported is

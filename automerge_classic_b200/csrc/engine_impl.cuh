@@ -891,7 +891,12 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
     nBytes = readU32(patchByteOff.p + nRec);
     if ((u64)end + nBytes >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: patch larger than 4 GiB");
     patchBytesD.ensure(ctx, nBytes + 8);
-    foreach(ctx, nRec, PatchBytesGatherKernel{arena.p, propOut.p, numProps, editOut.p, patchByteOff.p, (u32)out.valBytesOff, patchBytesD.p});
+    foreach(ctx, nRec, PatchBytesGatherKernel{arena.p, propOut.p, numProps, editOut.p, patchByteOff.p, (u32)out.valBytesOff, patchBytesD.p, errWord.p});
+    {   // a value that the reference's decodeValue refuses (it decodes every value that reaches a patch, columnar.js:300-329)
+      const u64 ew = fetchErr();
+      if ((ew & 0xff) == KE_FLOAT_LEN) { u32 l = 0; d2h(ctx, &l, patchByteLen.p + (ew >> 8), 4); sync(ctx); const size_t i = (size_t)(ew >> 8); u32 keyLen = 0; if (i < numProps) { PropRec r; d2h(ctx, &r, propOut.p + i, sizeof(PropRec)); sync(ctx); keyLen = r.keyLen == 0xffffffffu ? 0 : r.keyLen; } throw Error(AMG_ERR_RANGE, "Invalid length for floating point number: " + std::to_string(l - keyLen)); }
+      if (ew) throwKernelError(ew, actorsNow);
+    }
   }
   out.valBytesLen = nBytes; out.bigEnd = (out.valBytesOff + nBytes + 7) & ~(size_t)7;
   patchBuf.ensure(out.bigEnd + 4096);

@@ -37,16 +37,26 @@ struct PatchBytesCountKernel {
   }
 };
 struct PatchBytesGatherKernel {
-  const u8* arena; PropRec* props; size_t numProps; EditRec* edits; const u32* off; u32 bytesOff /* of the section inside the patch */; u8* out;
+  const u8* arena; PropRec* props; size_t numProps; EditRec* edits; const u32* off; u32 bytesOff /* of the section inside the patch */; u8* out; u64* errWord;
+  // decodeValue (columnar.js:300-329) runs in the reference whenever a value reaches a patch: numbers must be complete
+  // LEB128 values within 53 bits, floating point payloads must be 8 bytes
+  HD void validate(u32 valLen, u32 valOff, size_t i) const {
+    const u32 tag = valLen & 15, n = valLen >> 4;
+    if (tag == 3 || tag == 4 || tag == 8 || tag == 9) {
+      ByteReader r(arena, valOff, valOff + n);
+      if (tag == 3) r.uleb(); else r.sleb();
+      if (r.err) raise(errWord, r.err, i);
+    } else if (tag == 5 && n != 8) raise(errWord, KE_FLOAT_LEN, i);
+  }
   HD void operator()(size_t i) const {
     u32 at = off[i];
     if (i < numProps) {
       PropRec& r = props[i];
       if (r.keyLen != 0xffffffffu) { for (u32 k = 0; k < r.keyLen; k++) out[at + k] = arena[r.keyOff + k]; r.keyOff = bytesOff + at; at += r.keyLen; }
-      if (!(r.flags & 2u)) { const u32 n = r.valLen >> 4; for (u32 k = 0; k < n; k++) out[at + k] = arena[r.valOff + k]; r.valOff = bytesOff + at; }
+      if (!(r.flags & 2u)) { const u32 n = r.valLen >> 4; if (!(r.flags & 1u) && (r.flags >> 8) == 1) validate(r.valLen, r.valOff, i); for (u32 k = 0; k < n; k++) out[at + k] = arena[r.valOff + k]; r.valOff = bytesOff + at; }
     } else {
       EditRec& r = edits[i - numProps];
-      if (!(r.kind & EF_COUNTER)) { const u32 n = r.valLen >> 4; for (u32 k = 0; k < n; k++) out[at + k] = arena[r.valOff + k]; r.valOff = bytesOff + at; }
+      if (!(r.kind & EF_COUNTER)) { const u32 n = r.valLen >> 4; if ((r.kind & 0xff) != EK_REMOVE && (r.kind >> 16) == 1) validate(r.valLen, r.valOff, i); for (u32 k = 0; k < n; k++) out[at + k] = arena[r.valOff + k]; r.valOff = bytesOff + at; }
     }
   }
 };

@@ -536,6 +536,50 @@ def check_errors_atomic(gpu_doc):
     g.apply_changes(ch[10:])
 
 
+def check_value_validation(gpu_doc, oracle_mod):
+    """Values are decoded when they reach a patch (decodeValue, columnar.js:300-329): an incomplete or oversized LEB128
+    number, or a float64 that is not 8 bytes long, makes applyChanges throw - with the reference's message - and leaves the
+    document untouched; the same bytes in a value that no patch shows (overwritten in the same call) are not looked at."""
+    from automerge_classic_b200 import columnar
+    from automerge_classic_b200.engine import AmgError
+    actor = 'ab' * 16
+
+    def craft(seq, start, deps, ops, find, repl):
+        raw, _ = columnar.encode_change_raw({'actor': actor, 'seq': seq, 'startOp': start, 'time': 0, 'message': '', 'deps': deps, 'ops': ops}, False, 6)
+        raw = bytearray(raw)
+        at = bytes(raw).rfind(find)
+        assert at > 12, 'pattern not found'
+        raw[at:at + len(find)] = repl
+        raw[4:8] = oracle_mod.sha256(bytes(raw[8:]))[:4]
+        return bytes(raw), oracle_mod.sha256(bytes(raw[8:])).hex()
+
+    base, h0 = columnar.encode_change_raw({'actor': actor, 'seq': 1, 'startOp': 1, 'time': 0, 'message': '', 'deps': [], 'ops': [
+        {'action': 'makeList', 'obj': '_root', 'key': 'l', 'pred': []}, {'action': 'set', 'obj': '_root', 'key': 'k', 'value': 1, 'datatype': 'uint', 'pred': []}]}, False, 6)
+    cases = [
+        ([{'action': 'set', 'obj': '_root', 'key': 'n', 'value': 200, 'datatype': 'uint', 'pred': []}], bytes([0xc8, 0x01]), bytes([0xc8, 0x81])),          # incomplete number
+        ([{'action': 'set', 'obj': '1@' + actor, 'elemId': '_head', 'insert': True, 'value': 300, 'datatype': 'int', 'pred': []}], bytes([0xac, 0x02]), bytes([0xac, 0x82])),
+        ([{'action': 'set', 'obj': '_root', 'key': 'c', 'value': 70000, 'datatype': 'counter', 'pred': []}], bytes([0xf0, 0xa2, 0x04]), bytes([0xf0, 0xa2, 0x84])),
+    ]
+    for ops, find, repl in cases:
+        bad, _ = craft(2, 3, [h0], ops, find, repl)
+        orc, g = oracle_mod.OracleDoc(), gpu_doc()
+        orc.apply_changes([base]); g.apply_changes([base])
+        before = g.get_patch()
+        try:
+            orc.apply_changes([bad])
+            want = None
+        except oracle_mod.OracleError as e:
+            want = str(e)
+        assert want is not None, 'the oracle accepts %s' % bad.hex()
+        try:
+            g.apply_changes([bad])
+            got = None
+        except AmgError as e:
+            got = str(e)
+        assert got is not None and want.endswith(got), (got, want)   # the oracle prefixes the JS error class
+        assert g.get_patch() == before and g.heads() == orc.heads()
+
+
 def check_large_text(gpu_doc, oracle_mod, n):
     """C3 at 100k ops: full parity against the oracle (the oracle finishes this size in seconds)."""
     from automerge_classic_b200 import tracegen

@@ -173,3 +173,7 @@ def test_history_after_load_late_cut(gpu_doc):
 @pytest.mark.parametrize('cfg,n,a', [('C2', 300, 0), ('C3', 600, 3), ('C3', 2000, 4), ('C4', 1500, 4), ('C6', 300, 3), ('C7', 300, 3), ('C8', 300, 3)])
 def test_history_against_oracle(gpu_doc, oracle_mod, cfg, n, a):
     parity_checks.check_history_against_oracle(gpu_doc, oracle_mod, cfg, n, a)
+
+
+def test_value_validation(gpu_doc, oracle_mod):
+    parity_checks.check_value_validation(gpu_doc, oracle_mod)

@@ -188,3 +188,7 @@ def test_out_of_order_waiting_copies_emu(emu_doc, oracle_mod, seed):
 
 def test_load_without_head_indexes_emu(emu_doc, oracle_mod):
     parity_checks.check_load_without_head_indexes(emu_doc, oracle_mod)
+
+
+def test_value_validation_emu(emu_doc, oracle_mod):
+    parity_checks.check_value_validation(emu_doc, oracle_mod)
