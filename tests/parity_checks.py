@@ -580,6 +580,40 @@ def check_value_validation(gpu_doc, oracle_mod):
         assert g.get_patch() == before and g.heads() == orc.heads()
 
 
+def check_duplicated_successor_pin(gpu_doc, oracle_mod):
+    """PINS A KNOWN DIFFERENCE: mergeDocChangeOps adds an overwriting op to the succ list of the current
+    document op at the top of every loop iteration, for every op still in the group (new.js:1172-1187, no predSeen check).
+    When group ops with smaller ids are emitted before that document op, it is visited again and the successor is entered
+    again. Here: doc op 24@c on key c02; author b's changes [20, 21] and [25, 26] on the same key in ONE call, 21 overwrites
+    20, 25 overwrites 24@c: the reference (oracle) records succ(24@c) = [25@b, 25@b], the engine [25@b]. Patches are
+    identical; applied in separate calls both record it once. If this test fails because the engine now reproduces the
+    duplicate, update the pin (and DESIGN.md)."""
+    from automerge_classic_b200 import columnar
+    b, c = 'bb' * 16, 'cc' * 16
+
+    def ch(actor, seq, start, deps, ops):
+        return columnar.encode_change_raw({'actor': actor, 'seq': seq, 'startOp': start, 'time': 0, 'message': '', 'deps': sorted(deps), 'ops': ops}, False, 6)
+    c1, hc = ch(c, 1, 24, [], [{'action': 'set', 'obj': '_root', 'key': 'c02', 'value': 'c', 'pred': []}])
+    a1, ha = ch(b, 1, 20, [], [{'action': 'set', 'obj': '_root', 'key': 'c02', 'value': 'b20', 'pred': []},
+                               {'action': 'set', 'obj': '_root', 'key': 'c02', 'value': 'b21', 'pred': ['20@' + b]}])
+    a2, _ = ch(b, 2, 25, [ha, hc], [{'action': 'set', 'obj': '_root', 'key': 'c02', 'value': 'b25', 'pred': ['24@' + c]},
+                                    {'action': 'set', 'obj': '_root', 'key': 'c02', 'value': 'b26', 'pred': []}])
+    for one_call, want_oracle in ((True, [1, 0, 2, 0, 0]), (False, [1, 0, 1, 0, 0])):
+        o, g = oracle_mod.OracleDoc(), gpu_doc()
+        o.apply_changes([c1]); g.apply_changes([c1])
+        if one_call:
+            po, pg = o.apply_changes([a1, a2]), g.apply_changes([a1, a2])
+        else:
+            o.apply_changes([a1]); g.apply_changes([a1])
+            po, pg = o.apply_changes([a2]), g.apply_changes([a2])
+        assert replay.deep_equal(replay.decode(pg), replay.decode(po)) is None
+        assert replay.deep_equal(replay.decode(g.get_patch()), replay.decode(o.get_patch())) is None
+        rows, _, _ = o.dump_ops(); gr, _ = g.dump_ops()
+        assert rows[:, 9].tolist() == want_oracle, rows[:, 9].tolist()
+        assert gr[:, 7].tolist() == [1, 0, 1, 0, 0], gr[:, 7].tolist()
+        assert (o.save() == g.save()) == (not one_call)
+
+
 def check_large_text(gpu_doc, oracle_mod, n):
     """C3 at 100k ops: full parity against the oracle (the oracle finishes this size in seconds)."""
     from automerge_classic_b200 import tracegen

@@ -177,3 +177,7 @@ def test_history_against_oracle(gpu_doc, oracle_mod, cfg, n, a):
 
 def test_value_validation(gpu_doc, oracle_mod):
     parity_checks.check_value_validation(gpu_doc, oracle_mod)
+
+
+def test_duplicated_successor_pinned(gpu_doc, oracle_mod):
+    parity_checks.check_duplicated_successor_pin(gpu_doc, oracle_mod)

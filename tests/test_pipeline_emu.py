@@ -192,3 +192,7 @@ def test_load_without_head_indexes_emu(emu_doc, oracle_mod):
 
 def test_value_validation_emu(emu_doc, oracle_mod):
     parity_checks.check_value_validation(emu_doc, oracle_mod)
+
+
+def test_duplicated_successor_pinned_emu(emu_doc, oracle_mod):
+    parity_checks.check_duplicated_successor_pin(emu_doc, oracle_mod)
