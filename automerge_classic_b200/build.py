@@ -19,7 +19,7 @@ def build_engine(force=False, verbose=False):
     out = os.path.join(HERE, 'libamgpu.so')
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', 'hostsha.cc'))] + [os.path.join(HERE, '..', 'include', 'amgpu.h')]
     if force or _stale(out, srcs):
-        cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + [os.path.join(CSRC, 'capi.cu'), os.path.join(CSRC, 'hostsha.cc'), '-o', out, '-lz']
+        cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + [os.path.join(CSRC, 'capi.cu'), os.path.join(CSRC, 'hostsha.cc'), '-o', out, '-lz', '-ldl']
         subprocess.check_call(cmd)
     return out
 
@@ -28,7 +28,7 @@ def build_tracegen(force=False):
     out = os.path.join(HERE, 'libamgtrace.so')
     src = os.path.join(CSRC, 'tracegen.cc')
     if force or _stale(out, [src]):
-        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', src, '-o', out, '-lz'])
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', src, '-o', out, '-lz', '-ldl'])
     return out
 
 

@@ -1,12 +1,25 @@
 // amgpu — Engine::applyChanges / getPatch pipeline (see engine.cuh for the state layout).
 #pragma once
 #include <chrono>
+#ifndef AMG_EMU
+#include <nvtx3/nvToolsExt.h>
+#endif
 #include "engine.cuh"
 #include "misc.cuh"
 
 namespace amg {
 
 static const size_t PATCH_HDR_WORDS = 20;
+// NVTX range per pipeline phase: next() closes the running range and opens the named one (nullptr: just closes)
+struct NvtxPhases {
+#ifndef AMG_EMU
+  bool open = false;
+  void next(const char* name) { if (open) nvtxRangePop(); open = name != nullptr; if (name) nvtxRangePushA(name); }
+  ~NvtxPhases() { if (open) nvtxRangePop(); }
+#else
+  void next(const char*) {}
+#endif
+};
 struct HostClock {
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   float ms() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
@@ -97,6 +110,7 @@ inline void Engine::applyChanges(const u8* const* bufs, const size_t* lens, size
 }
 inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, size_t n, const u8* blob, const u64* offsets, bool isLocal, bool wantPatch, PatchOut& out, bool hostScan) {
   PhaseTimer timer(ctx); HostClock hclk; int hmark = 12;
+  NvtxPhases nvtx; nvtx.next("upload+hash+decode");   // NVTX ranges per pipeline phase (nsys / ncu timelines)
   for (auto& x : lastPhaseMs) x = 0;
   auto hostMark = [&]() { if (hmark < 24) lastPhaseMs[hmark++] = hclk.ms(); };
   curTimer = &timer; curHostMark = hostMark;
@@ -223,7 +237,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     }
   }
   dbgMark("stage:enqueued");
-  timer.mark(); hostMark();
+  timer.mark(); hostMark(); nvtx.next("inflate+decode-finish");
   // ------------------------------------------------------------ 1. DEFLATEd changes
   {
     // Which changes of the batch are DEFLATEd (columnar.js:742)? Those are inflated on the device, behind the batch:
@@ -257,7 +271,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   // changes the tile kernel passed on (inflated ones, changes outside their tile's window), then the totals
   { DecodeTilesArgs fin = dargs; fin.arena = arena.p; decode_tiles_finish(ctx, fin, B); }
   side_join(ctx);
-  timer.mark(); hostMark();
+  timer.mark(); hostMark(); nvtx.next("gate");
   // (parse errors surface with the first host round trip of the gate: the error word travels with every small read, and a
   //  change that failed to parse has zero deps / ops so the kernels in between have nothing to walk)
   // ------------------------------------------------------------ 2. causal gate
@@ -332,7 +346,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     const bool hashApplied = pr < numApplied || appliedH[pr - numApplied];
     if (!hashApplied) { newQueue.push_back(batch[b]); newQueueOriginal.push_back(originalOf(b)); }
   }
-  timer.mark(); hostMark();
+  timer.mark(); hostMark(); nvtx.next("actors+seq+finalize");
   std::vector<std::string> actorsNow = actorIds; std::vector<u64> clockNow = clock; std::vector<u32> actorCntH; std::vector<std::pair<u32, u32>> actorRepNow = actorRep;
   size_t M = 0, P = 0, N = numRows, numPairs = numSucc; u64 maxOpNow = maxOp;
   IdTable idt{nullptr, nullptr, 0};
@@ -477,7 +491,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     foreach(ctx, M, FinalizeOpsKernel{B, hot.p, nActors.p, opBaseP, predBaseP, rawBase.p, rawPredBase.p, timeBase.p, amapBase.p, amap.p, applied.p, raw, ops, errWord.p});
     checkErr(actorsNow);
     dbgMark("decode:finalized");
-    timer.mark(); hostMark();
+    timer.mark(); hostMark(); nvtx.next("opset");
     // ---------------------------------------------------------- 6. op set
     if (maxOpNow >= (1ULL << 40)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: op counters above 2^40");
     const int ordBits = bits_for(maxOpNow) + rb;
@@ -585,7 +599,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     sorted.ensure(ctx, N + 1);
     foreach(ctx, N, GatherRowsKernel{w, sorted.view(), perm.p});
     dbgMark("opset:succ+gather(enqueued)");
-    timer.mark(); hostMark();
+    timer.mark(); hostMark(); nvtx.next("patch");
     // ---------------------------------------------------------- 7. incremental patch
     if (wantPatch) {
       objPos.ensure(ctx, N + 1);
@@ -594,7 +608,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       buildPatch(sorted.view(), N, false, &ops, M, &idt, rowOfOp.p, pos.p, actorsNow, out, newSuccOff.p, newSucc.p);
     }
     checkErr(actorsNow);
-    timer.mark(); hostMark();
+    timer.mark(); hostMark(); nvtx.next("heads+commit");
     // heads
     dbgMark("commit:begin");
     {
@@ -659,7 +673,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   }
   arenaLen = cur; queue = newQueue; queueOriginal = newQueueOriginal; rb.armed = false;
   side_join(ctx); sync(ctx);
-  timer.mark(); hostMark();
+  timer.mark(); hostMark(); nvtx.next(nullptr);
   fillPatchHeader(out);
   if (isLocal && n == 1) {   // new.js:1874-1877
     std::vector<ChangeHot> m0(1); d2h(ctx, m0.data(), hot.p, sizeof(ChangeHot)); sync(ctx);
@@ -765,6 +779,7 @@ inline void Engine::buildPatch(DocRows d, size_t N, bool wholeDoc, const OpRows*
   propOut.ensure(ctx, numProps + 1);
   foreach(ctx, N, PropEmitKernel{d, emit.p, marker.p, slot.p, propOut.p, counterLast.p, counterTotal.p});
   if (curTimer) { curTimer->mark(); curHostMark(); }
+  NvtxPhases nvtxPatch; nvtxPatch.next("patch:list-edits");
   // ---- list edits
   size_t numEdits = 0; bool shipElem = true;
   if (wholeDoc) {
