@@ -57,6 +57,7 @@ struct Ctx {
   // copy engine: a read of 4 bytes must not queue behind a 100 MB transfer (see d2h / sync)
   struct Peek { void* dst; size_t off, bytes; };
   unsigned char* peekBuf = nullptr; size_t peekCap = 0, peekUsed = 0; std::vector<Peek> peeks;
+  volatile unsigned long long* peekFlag = nullptr; unsigned long long peekSeq = 0; bool peekFlagArmed = false;   // completion flag of the last k_peek_words (pinned)
 #endif
   int device = 0;
   int numSMs = 148;
@@ -134,9 +135,13 @@ static __global__ void k_peek_bytes(unsigned char* dstPinned, const unsigned cha
 #endif
 #ifndef AMG_EMU
 struct PeekWords { const void* src[8]; unsigned bytes[8]; unsigned off[8]; int n; };
-static __global__ void k_peek_words(PeekWords w, unsigned char* dstPinned) {   // a handful of 4- or 8-byte words in one launch
+static __global__ void k_peek_words(PeekWords w, unsigned char* dstPinned, volatile unsigned long long* flag, unsigned long long seq) {   // a handful of 4- or 8-byte words in one launch
   const int k = threadIdx.x >> 3, b = threadIdx.x & 7;
   if (k < w.n && (unsigned)b < w.bytes[k]) dstPinned[w.off[k] + b] = ((const unsigned char*)w.src[k])[b];
+  // completion flag in pinned host memory: the host spins on it instead of going through cudaStreamSynchronize (whose
+  // wake-up costs more than the kernel); everything queued on the stream before this kernel has completed by then
+  __threadfence_system(); __syncthreads();
+  if (threadIdx.x == 0) { *flag = seq; __threadfence_system(); }
 }
 #endif
 // dst is valid after the next sync(c). Up to 16 KB: read by a kernel into the pinned staging buffer (sync() moves it to
@@ -182,9 +187,9 @@ inline void d2h_words(Ctx& c, int n, const void* const* srcs, const size_t* size
   if (!small) { for (int k = 0; k < n; k++) d2h(c, dsts[k], srcs[k], sizes[k]); return; }
   PeekWords w; w.n = n;
   for (int k = 0; k < n; k++) { w.src[k] = srcs[k]; w.bytes[k] = (unsigned)sizes[k]; w.off[k] = (unsigned)(c.peekUsed + 16 * (size_t)k); c.peeks.push_back(Ctx::Peek{dsts[k], c.peekUsed + 16 * (size_t)k, sizes[k]}); }
-  k_peek_words<<<1, 64, 0, c.stream>>>(w, c.peekBuf);
+  k_peek_words<<<1, 64, 0, c.stream>>>(w, c.peekBuf, c.peekFlag, ++c.peekSeq);
   CUDA_CHECK(cudaGetLastError());
-  c.peekUsed += 16 * (size_t)n; last_peek_ctx() = &c; c.launches++;
+  c.peekUsed += 16 * (size_t)n; last_peek_ctx() = &c; c.launches++; c.peekFlagArmed = true;
 #endif
 }
 inline void drop_peeks(Ctx& c) {   // after an aborted call: whatever was pending must not be delivered into dead stack frames
@@ -193,9 +198,19 @@ inline void drop_peeks(Ctx& c) {   // after an aborted call: whatever was pendin
 #endif
 }
 inline void drop_pending_peeks() { if (last_peek_ctx()) drop_peeks(*last_peek_ctx()); }
-inline void sync(Ctx& c) {
+inline void sync(Ctx& c, bool spinOnPeekFlag = false) {
 #ifndef AMG_EMU
-  cudaError_t e = cudaStreamSynchronize(c.stream);
+  cudaError_t e = cudaSuccess;
+  if (spinOnPeekFlag && c.peekFlagArmed) {   // the LAST thing queued is a k_peek_words (readWords): spin on its flag (a failed launch / device error shows up in the stream query)
+    c.peekFlagArmed = false; unsigned spins = 0;
+    while (*c.peekFlag != c.peekSeq) {
+      if ((++spins & 0xfff) == 0) { e = cudaStreamQuery(c.stream); if (e == cudaSuccess) continue; if (e != cudaErrorNotReady) break; e = cudaSuccess; }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    if (e == cudaSuccess && *c.peekFlag != c.peekSeq) e = cudaStreamSynchronize(c.stream);
+  } else { c.peekFlagArmed = false; e = cudaStreamSynchronize(c.stream); }
   if (e != cudaSuccess) { drop_peeks(c); CUDA_CHECK(e); }
   for (const Ctx::Peek& p : c.peeks) memcpy(p.dst, c.peekBuf + p.off, p.bytes);
   c.peeks.clear(); c.peekUsed = 0;

@@ -122,7 +122,8 @@ class Engine {
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.side, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.copy, cudaStreamNonBlocking));
-    ctx.peekCap = 1u << 20; CUDA_CHECK(cudaMallocHost((void**)&ctx.peekBuf, ctx.peekCap));
+    ctx.peekCap = 1u << 20; CUDA_CHECK(cudaMallocHost((void**)&ctx.peekBuf, ctx.peekCap + 64));
+    ctx.peekFlag = reinterpret_cast<volatile unsigned long long*>(ctx.peekBuf + ctx.peekCap); *ctx.peekFlag = 0;
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evUp, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evMirror, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evFork, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&ctx.evJoin, cudaEventDisableTiming));
     ShaConsts k; memcpy(k.k, SHA_K, sizeof(SHA_K)); CUDA_CHECK(cudaMemcpyToSymbol(c_sha, &k, sizeof(k)));
@@ -173,9 +174,10 @@ class Engine {
     if (srcs.size() > 8) throw Error(AMG_ERR_INTERNAL, "readWords: too many words");
     for (auto& s : srcs) { w[k] = 0; from[k] = s.first; sizes[k] = s.second; to[k] = &w[k]; k++; }
     from[k] = errWord.p; sizes[k] = 8; to[k] = &w[k];
+    ctx.peekFlagArmed = false;
     if (k + 1 <= 8) d2h_words(ctx, (int)k + 1, from, sizes, to); else for (size_t i = 0; i <= k; i++) d2h(ctx, to[i], from[i], sizes[i]);
     const uint64_t launchesNow = ctx.launches;
-    sync(ctx);
+    sync(ctx, true);   // the words' kernel is the last thing on the stream: wait on its completion flag
     k = 0; for (auto& s : srcs) { memcpy(dsts[k], &w[k], s.second); k++; }
     errSnapshot = w[k]; errSnapLaunches = launchesNow;
   }
