@@ -199,6 +199,7 @@ inline void drop_peeks(Ctx& c) {   // after an aborted call: whatever was pendin
 }
 inline void drop_pending_peeks() { if (last_peek_ctx()) drop_peeks(*last_peek_ctx()); }
 inline void sync(Ctx& c, bool spinOnPeekFlag = false) {
+  (void)spinOnPeekFlag;
 #ifndef AMG_EMU
   cudaError_t e = cudaSuccess;
   if (spinOnPeekFlag && c.peekFlagArmed) {   // the LAST thing queued is a k_peek_words (readWords): spin on its flag (a failed launch / device error shows up in the stream query)

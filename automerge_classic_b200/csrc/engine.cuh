@@ -174,7 +174,9 @@ class Engine {
     if (srcs.size() > 8) throw Error(AMG_ERR_INTERNAL, "readWords: too many words");
     for (auto& s : srcs) { w[k] = 0; from[k] = s.first; sizes[k] = s.second; to[k] = &w[k]; k++; }
     from[k] = errWord.p; sizes[k] = 8; to[k] = &w[k];
+#ifndef AMG_EMU
     ctx.peekFlagArmed = false;
+#endif
     if (k + 1 <= 8) d2h_words(ctx, (int)k + 1, from, sizes, to); else for (size_t i = 0; i <= k; i++) d2h(ctx, to[i], from[i], sizes[i]);
     const uint64_t launchesNow = ctx.launches;
     sync(ctx, true);   // the words' kernel is the last thing on the stream: wait on its completion flag
