@@ -52,6 +52,9 @@ def _emit(line):
 
 N_OPS, N_ACTORS = 1_000_000, 10
 CPU_SAMPLE_OPS = 200_000
+# bounded CPU samples (about 10-30 s of oracle time each): the oracle, like the reference, is super-linear in document length
+# (C4: 50k ops 43 s, 100k ops 172 s), so the sample is a prefix and the ops/s it yields flatters the CPU side
+CPU_SAMPLE = {'C3': 200_000, 'C4': 30_000, 'C2': 100_000, 'C2b': 100_000}
 
 
 def read_traffic():
@@ -109,7 +112,7 @@ def run_reference(args, rank, world):
     from automerge_classic_b200 import tracegen
     oracle.build()
     cfg, ops, actors, desc = WORKLOADS[getattr(args, 'workload', 'C3')]
-    t = tracegen.generate(cfg, min(CPU_SAMPLE_OPS, ops), actors)
+    t = tracegen.generate(cfg, min(CPU_SAMPLE[getattr(args, 'workload', 'C3')], ops), actors)
     times = []
     for i in range(args.warmup + args.steps):
         doc = oracle.OracleDoc()
@@ -391,7 +394,7 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_sample(args.workload, CPU_SAMPLE_OPS)
+        cpu = cpu_sample(args.workload, CPU_SAMPLE[args.workload])
 
     if rank == 0 and os.environ.get('AMG_BENCH_MARKS'):
         buf = C.create_string_buffer(4096)

@@ -49,8 +49,10 @@ int amg_reserve(amg_backend* b, size_t arena_bytes, amg_error* err);
  * Backend.loadChanges (backend.js:116-121): same state transition, no patch computed; *out is set to NULL. */
 int amg_apply_changes(amg_backend* b, const uint8_t* const* bufs, const size_t* lens, size_t n, int is_local, int want_patch,
                       amg_patch** out, amg_error* err);
-/* Same, with the n changes stored back to back in one host buffer: change i is blob[offsets[i] .. offsets[i+1]).
- * This is the bulk-replay entry point (one host->device copy from a caller buffer, preferably pinned). */
+/* Same, with the n changes stored back to back in one buffer: change i is blob[offsets[i] .. offsets[i+1]) (offsets: host
+ * memory). This is the bulk-replay entry point. `blob` may be pinned host memory (uploaded in 16 MB pieces, each piece
+ * hashed and decoded while the next one is in flight), pageable host memory (staged through the engine's pinned arena
+ * mirror) or DEVICE memory (copied device to device: the bytes are already resident). */
 int amg_apply_changes_packed(amg_backend* b, const uint8_t* blob, const uint64_t* offsets, size_t n, int is_local, int want_patch,
                              amg_patch** out, amg_error* err);
 /* Backend.getPatch(state) — backend/backend.js:127-129 -> new.js:2060-2068 / documentPatch new.js:1604-1635 */
@@ -80,10 +82,10 @@ size_t amg_buffers_count(const amg_buffers* l);
 const uint8_t* amg_buffers_get(const amg_buffers* l, size_t i, size_t* len);
 void amg_buffers_free(amg_buffers* l);
 
-/* Patch layout (little endian). amg_patch_bytes returns a header of 18 uint64:
+/* Patch layout (little endian). amg_patch_bytes returns a header of 20 uint64:
  *   [0] 0x31504747414d41 ("AMAGGP1") [1] maxOp [2] pendingChanges [3] hasActorSeq [4] seq [5] actorOff [6] actorLen
  *   [7] actorsOff [8] nActors [9] clockOff [10] nClock [11] depsOff [12] nDeps [13] propsOff [14] nProps
- *   [15] editsOff [16] nEdits [17] editElemOff
+ *   [15] editsOff [16] nEdits [17] editElemOff [18] bytesOff [19] bytesLen
  * followed by the sections (offsets relative to the start of the buffer, 8-byte aligned):
  *   actors : nActors x { uint32 len; bytes[len]; pad to 4 }   (document actor index -> actor id bytes)
  *   clock  : nClock x { uint64 actorIndex; uint64 seq }
@@ -91,8 +93,11 @@ void amg_buffers_free(amg_buffers* l);
  *   props  : nProps x { uint64 objId; uint64 opId; uint32 keyOff, keyLen, valLen, valOff, flags, pad }   (map entries)
  *   edits  : nEdits x { uint64 objId; uint64 opId; uint32 index, kind, valLen, valOff }                  (list edits, per object in order)
  *   editElem: nEdits x uint64 elemId (offset 0 in the header = section absent: every insert's elemId is its opId)
- * ids are (counter << 16 | actorIndex); objId 0 = _root. keyOff / valOff index the document arena
- * (amg_arena); valLen is the reference's VALUE_LEN tag (length << 4 | type, columnar.js:46-49).
+ *   bytes  : the map keys and value payloads the records refer to, gathered on the device
+ * ids are (counter << 16 | actorIndex); objId 0 = _root. keyOff / valOff are offsets INTO THE PATCH BUFFER (its bytes
+ * section): a patch is self-contained, no second buffer is needed to read it. valLen is the reference's VALUE_LEN tag
+ * (length << 4 | type, columnar.js:46-49); numeric payloads have been validated like the reference's decodeValue does
+ * (columnar.js:300-329) - a malformed one makes the call fail with the reference's RangeError.
  * props.flags = action << 8 | 1 if the key has no visible value (reference emits `key: {}`);
  * edits.kind = (0 insert | 1 remove | 2 update) | 0x100 if the edit starts a new run (edits without the bit
  * continue the previous insert as `multi-insert` / add to the previous remove's count, new.js:747-782)
@@ -103,7 +108,9 @@ void amg_buffers_free(amg_buffers* l);
 /* The bytes live in a pinned buffer owned by the backend: valid until the next call on the same backend. */
 const uint8_t* amg_patch_bytes(const amg_patch* p, size_t* len);
 void amg_patch_free(amg_patch* p);
-/* host mirror of the document arena that keyOff / valOff refer to (valid until the next mutating call) */
+/* host copy of the document arena (every change's bytes back to back, inflated copies of DEFLATEd changes behind them);
+ * valid until the next mutating call. The engine keeps no host copy of bytes that were handed over in pinned or device
+ * memory: the missing part is fetched from the device by this call (and by getChanges & co, which read from it). */
 const uint8_t* amg_arena(amg_backend* b, size_t* len);
 
 /* ---- parity / measurement hooks (not part of the reference surface) ---- */
@@ -116,8 +123,9 @@ int amg_debug_decode(amg_backend* b, const uint8_t* blob, const uint64_t* offset
                      uint32_t* n_ops_out /* n */, uint32_t** rows_out, size_t* total_ops, size_t* total_preds, amg_error* err);
 /* document-ordered op table: rows[n][8] = {objCtr,objActor,idCtr,idActor,keyCtr,keyActor,flags,succNum}; succ[m][2] = {ctr, actor} */
 int amg_debug_dump_ops(amg_backend* b, uint64_t** rows_out, size_t* n, uint64_t** succ_out, size_t* m, amg_error* err);
-/* timings of the last applyChanges call: [0..11] CUDA-event phases in ms (stage+upload, sha256, parse+gate, actors+decode, op set,
- * patch groups+props, list index, edits+copy-out, heads+commit), [12..23] host wall-clock marks (ms since the call started) */
+/* timings of the last applyChanges call: [0..11] CUDA-event phases in ms on the engine's main stream (upload + hash + decode of
+ * the pieces, inflate + rest of the decode, gate, actors + seq + row finalisation, op set, patch groups + props, list index,
+ * edits + copy-out, heads + commit), [12..23] host wall-clock marks (ms since the call started; [23] = the whole ABI call) */
 int amg_last_timings(amg_backend* b, float* ms_out, int n);
 uint64_t amg_kernel_launches(amg_backend* b);
 /* labelled host wall-clock marks of the last applyChanges call ("label=ms ..."), development aid */
@@ -128,7 +136,9 @@ void amg_free_mem(void* p);
  * long columns (returns 1 without touching out when it declines the stream); parallel = 0: the serial walker (malformed
  * input is an error, as in the reference). For differential tests of the two. */
 int amg_debug_decode_column(amg_backend* b, const uint8_t* bytes, size_t len, int kind, size_t n, int parallel, int64_t* out, amg_error* err);
-/* device-only re-run of the decode kernels over the last batch (inputs resident in HBM), for the roofline measurement */
+/* device-only re-run of the decode kernels over the last batch (inputs resident in HBM), for the roofline measurement:
+ * ms_sha = SHA-256 kernel, ms_parse = fused decode (k_decode_tiles + k_decode_direct), ms_decode = DecodeColumnKernel over
+ * changes of more than 16 ops (0 if none); algo_bytes = SURVEY.md 8d: encoded bytes + 48 B/op + 8 B/pred + 96 B/change */
 int amg_bench_decode(amg_backend* b, int iters, float* ms_sha, float* ms_parse, float* ms_decode, uint64_t* algo_bytes, amg_error* err);
 
 #ifdef __cplusplus

@@ -393,7 +393,7 @@ def check_full_size_fingerprint(gpu_doc, cfg):
     import os
     from automerge_classic_b200 import tracegen
     gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'full_size.json')))[cfg]
-    t = tracegen.generate(cfg, {'C3': 1000000, 'C4': 1000000, 'C2': 100000, 'C2b': 100000}[cfg], gold['n_actors'])
+    t = tracegen.generate(gold['config'], gold['ops_requested'], gold['n_actors'])
     assert t.n_ops == gold['n_ops'] and t.n_changes == gold['n_changes'] and int(t.offsets[-1]) == gold['change_bytes']
     g = gpu_doc()
     fp = g.apply_packed_flat(t.blob, t.offsets, t.n_changes)

@@ -18,7 +18,7 @@ def test_full_size_oracle_fingerprint():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('cfg', ['C2', 'C2b', 'C4', 'C3'])
+@pytest.mark.parametrize('cfg', ['C2', 'C2b', 'C4_100k', 'C3'])
 def test_full_size_patch_and_document(cfg):
     """Incremental patch, getPatch, save() and heads at BASELINE.json's full size of every workload against
     the oracle's committed digests (tests/golden/full_size.json)."""
