@@ -839,10 +839,11 @@ inline void decode_tiles_finish(Ctx& c, const DecodeTilesArgs& a, size_t numChan
 struct DecodeColumnKernel {
   const u8* arena; const u32* large; size_t numLarge; const ChangeHot* hot; const u32* nOps; const u32* nPreds;
   const u32* rawBase; const u32* rawPredBase; const u8* applied /* per change: decode only if 1 */;
-  RawRows rows; u64* errWord;
+  RawRows rows; u64* errWord; const u32* done /* optional [numLarge][NCOLS]: columns the parallel decoders have expanded already */;
   HD void operator()(size_t t) const {
     const int col = (int)(t / numLarge); const size_t c = large[t % numLarge];
     if (!applied[c]) return;
+    if (done && done[(t % numLarge) * NCOLS + col]) return;
     const u32 n = nOps[c]; if (n == 0 || col == CX_VAL_RAW || col == CX_CHLD_ACTOR || col == CX_CHLD_CTR) return;
     const ChangeHot h = hot[c];
     ByteReader d(arena, h.dirOff, h.dataOff); u32 pos = h.dataOff; u32 cOff = 0, cLen = 0, rawOff = 0, rawLen = 0; bool found = false;

@@ -282,6 +282,7 @@ class Engine {
   bool haveHashGraph = true;   // false after Backend.load: change history (hashes, bytes) is not reconstructed (new.js:1887-1912)
   void benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes);
   RawRows rawRows();
+  u32 decodeHugeChanges(const RawRows& raw, size_t numLarge); DBuf<u32> hugeDone;
   void runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes);
   DecodeTilesArgs decodeArgs(const u8* arenaP, size_t B, size_t batchBytes);
   // Host mirror of the arena, filled on demand: hostArena holds arena[0, hostArena.size()); whatever is missing is fetched

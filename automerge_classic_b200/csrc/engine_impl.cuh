@@ -481,7 +481,13 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       lastNumLarge = readU32(largeSlot.p + B);
       if (lastNumLarge > 0) {
         foreach(ctx, B, CompactKernel{largeFlag.p, largeSlot.p, largeList.p});
-        foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{arena.p, largeList.p, lastNumLarge, hot.p, nOps.p, nPreds.p, rawBase.p, rawPredBase.p, applied.p, raw, errWord.p});
+        // bulk changes (thousands of ops in one change): their columns are expanded in parallel by the token / record
+        // decoders of doccols.cuh, column by column; whatever those decline (non-canonical streams, columns that do not hold
+        // exactly the op count) and all other large changes go through DecodeColumnKernel (one thread per column)
+        u32 hugeMask = 0;
+        if (lastNumLarge <= 8) hugeMask = decodeHugeChanges(raw, lastNumLarge);
+        foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{arena.p, largeList.p, lastNumLarge, hot.p, nOps.p, nPreds.p, rawBase.p, rawPredBase.p, applied.p, raw, errWord.p, hugeDone.p});
+        (void)hugeMask;
       }
     }
     for (DBuf<u64>* b : {&o_id, &o_obj, &o_key}) b->ensure(ctx, M + 1);
@@ -966,6 +972,46 @@ inline bool Engine::decodeOverflowed(const u32 totals[4]) {
   return true;
 }
 
+// Columns of bulk changes (>= HUGE_CHANGE_OPS ops) through the parallel column decoders. largeList holds the large changes of
+// the batch (at most 8 here). hugeDone[k * NCOLS + col] = 1 tells DecodeColumnKernel that column `col` of large change k is done.
+inline u32 Engine::decodeHugeChanges(const RawRows& raw, size_t numLarge) {
+  static const u32 HUGE_CHANGE_OPS = 4096;
+  hugeDone.ensure(ctx, numLarge * NCOLS + 1); dev_memset(ctx, hugeDone.p, 0, (numLarge * NCOLS + 1) * 4);
+  std::vector<u32> list(numLarge); d2h(ctx, list.data(), largeList.p, numLarge * 4); sync(ctx);
+  u32 any = 0;
+  for (size_t k = 0; k < numLarge; k++) {
+    const u32 c = list[k]; ChangeHot h; u32 n = 0, np = 0, rb = 0, rpb = 0;
+    d2h(ctx, &h, hot.p + c, sizeof(ChangeHot)); d2h(ctx, &n, nOps.p + c, 4); d2h(ctx, &np, nPreds.p + c, 4); d2h(ctx, &rb, rawBase.p + c, 4); d2h(ctx, &rpb, rawPredBase.p + c, 4); sync(ctx);
+    if (n < HUGE_CHANGE_OPS || h.dataOff <= h.dirOff || h.dataOff - h.dirOff > 4096) continue;
+    std::vector<u8> dir(h.dataOff - h.dirOff); d2h(ctx, dir.data(), arena.p + h.dirOff, dir.size()); sync(ctx);
+    u32 cOff[NCOLS] = {0}, cLen[NCOLS] = {0}; bool have[NCOLS] = {false};
+    { ByteReader d(dir.data(), 0, (u32)dir.size()); u32 pos = h.dataOff;
+      while (!d.done() && !d.err) { const u32 id = (u32)d.uleb(), l = (u32)d.uleb(); const int ix = col_index_of(id); if (ix >= 0) { cOff[ix] = pos; cLen[ix] = l; have[ix] = true; } pos += l; } }
+    std::vector<u32> done(NCOLS, 0);
+    auto bytesOf = [&](int ix) { return arena.p + cOff[ix]; };
+    struct Plan { int col; u32* out; size_t cnt; };
+    const Plan plan[] = {{CX_OBJ_ACTOR, raw.objActor + rb, n}, {CX_OBJ_CTR, raw.objCtr + rb, n}, {CX_KEY_ACTOR, raw.keyActor + rb, n}, {CX_KEY_CTR, raw.keyCtr + rb, n},
+                         {CX_INSERT, raw.insert + rb, n}, {CX_ACTION, raw.action + rb, n}, {CX_VAL_LEN, raw.valLen + rb, n}, {CX_PRED_NUM, raw.predNum + rb, n},
+                         {CX_PRED_ACTOR, raw.predActor + rpb, np}, {CX_PRED_CTR, raw.predCtr + rpb, np}};
+    for (const Plan& pl : plan) {
+      if (!have[pl.col] || cLen[pl.col] == 0 || pl.cnt == 0) continue;   // absent / empty: the serial path fills the defaults
+      const u8* bytes = bytesOf(pl.col); const u32 len = cLen[pl.col]; bool ok = false;
+      switch (pl.col) {
+        case CX_OBJ_ACTOR: case CX_OBJ_CTR: case CX_KEY_ACTOR: case CX_ACTION: case CX_PRED_ACTOR: ok = parCols.toU32(bytes, len, pl.cnt, pl.out); break;
+        case CX_KEY_CTR: case CX_PRED_CTR: ok = parCols.deltaToU32(bytes, len, pl.cnt, pl.out); break;
+        case CX_INSERT: ok = parCols.boolean(bytes, len, pl.cnt, pl.out); break;
+        case CX_VAL_LEN: { u64 sum = 0; ok = parCols.lenColumn(bytes, len, pl.cnt, raw.valLen + rb, raw.valOff + rb, have[CX_VAL_RAW] ? cOff[CX_VAL_RAW] : 0, &sum) && sum <= (have[CX_VAL_RAW] ? cLen[CX_VAL_RAW] : 0); } break;
+        case CX_PRED_NUM: { u64 sum = 0; ok = parCols.countColumn(bytes, len, pl.cnt, raw.predNum + rb, raw.predOff + rb, &sum) && sum == np; if (ok && rpb) foreach(ctx, pl.cnt, PcAddBaseKernel{raw.predOff + rb, rpb}); } break;
+        default: break;
+      }
+      if (ok) { done[pl.col] = 1; any |= 1u << pl.col; }
+    }
+    h2d(ctx, hugeDone.p + k * NCOLS, done.data(), NCOLS * 4); sync(ctx);
+    if (getenv("AMG_PAR_DOC_TRACE")) fprintf(stderr, "amgpu decode: bulk change %u (%u ops, %u preds): columns expanded in parallel: mask %04x\n", c, n, np, any);
+  }
+  return any;
+}
+
 // Re-runs the decode kernels over the last applied batch (bytes resident in HBM) and times them with CUDA events.
 // msParse = the fused decode (k_decode_tiles: header parse + expansion of every change of up to SMALL_CHANGE_OPS ops),
 // msDec = DecodeColumnKernel over the larger changes (0 when the batch has none).
@@ -984,7 +1030,7 @@ inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* 
   for (int i = 0; i < iters; i++) runDecodeTiles(batchArena, B, lastBytes);
   cudaEventRecord(e[2], ctx.stream);
   for (int i = 0; i < iters; i++) {
-    if (lastNumLarge > 0) foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{batchArena, largeList.p, lastNumLarge, hot.p, nOps.p, nPreds.p, rawBase.p, rawPredBase.p, applied.p, raw, errWord.p});
+    if (lastNumLarge > 0) foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{batchArena, largeList.p, lastNumLarge, hot.p, nOps.p, nPreds.p, rawBase.p, rawPredBase.p, applied.p, raw, errWord.p, nullptr});
   }
   cudaEventRecord(e[3], ctx.stream);
   CUDA_CHECK(cudaEventSynchronize(e[3]));
@@ -1263,7 +1309,7 @@ inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* 
     const size_t nl = readU32(largeSlot.p + n);
     if (nl > 0) {
       foreach(ctx, n, CompactKernel{largeFlag.p, largeSlot.p, largeList.p});
-      foreach(ctx, (size_t)NCOLS * nl, DecodeColumnKernel{ar.p, largeList.p, nl, hot.p, nOps.p, nPreds.p, rawBase.p, rawPredBase.p, applied.p, raw, errWord.p});
+      foreach(ctx, (size_t)NCOLS * nl, DecodeColumnKernel{ar.p, largeList.p, nl, hot.p, nOps.p, nPreds.p, rawBase.p, rawPredBase.p, applied.p, raw, errWord.p, nullptr});
     }
   }
   foreach(ctx, n, RaiseDecErrKernel{decErr.p, errWord.p});
