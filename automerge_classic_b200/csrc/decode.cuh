@@ -523,28 +523,34 @@ template <class S> HD bool single_value(const S& src, int ix, u32 pos, u32 l, u3
     return false;
   }
   isNull = false; v = 0; used = 0;
-  if (l == 2 && p0 == 0 && p1 == 1) { isNull = true; used = 2; }
-  else if (l >= 2 && p0 == 0x7f) {
-    if (ix == CX_KEY_STR) { if (p1 >= 0x80) return false; v = p1; used = 2 + v; }
-    else if (p1 < 0x80) { v = p1; used = 2; }
-    else if (l >= 3) { const u32 p2 = src.ld(pos + 2); if (p2 >= 0x80) return false; v = (p1 & 0x7fu) | (p2 << 7); used = 3; }
-    else return false;
-  } else return false;
-  if (used != l) return false;
-  if ((ix == CX_KEY_CTR || ix == CX_PRED_CTR) && !isNull) { const int sv = used == 2 ? ((int)(v << 25) >> 25) : ((int)(v << 18) >> 18); if (sv < 0) return false; v = (u32)sv; }
+  if (l == 2 && p0 == 0 && p1 == 1) { isNull = true; used = 2; return true; }
+  if (l < 2 || p0 != 0x7f) return false;
+  if (ix == CX_KEY_STR) { if (p1 >= 0x80) return false; v = p1; used = 2 + v; return used == l; }
+  // the literal's value: a LEB128 number of 1 .. 5 bytes that ends exactly at the column's end (counters of a long
+  // document need three and four bytes)
+  if (l > 6) return false;
+  u64 val = p1 & 0x7fu; u32 last = p1; u32 nb = 1;
+#pragma unroll
+  for (u32 k = 1; k < 5; k++) if ((last & 0x80u) && nb < l - 1) { last = src.ld(pos + 1 + k); val |= (u64)(last & 0x7fu) << (7 * k); nb = k + 1; }
+  if ((last & 0x80u) || nb != l - 1) return false;
+  used = l;
+  if (ix == CX_KEY_CTR || ix == CX_PRED_CTR) {   // signed (delta from 0): negative values go to the general decoder, which reports them
+    if (last & 0x40u) return false;
+  }
+  if (val > 0xfffffffeULL) return false;
+  v = (u32)val;
   return true;
 }
 
-// Result of the first walk over a change: header fields, counts, and - when every column holds exactly one value - the row.
 struct ParsedChange {
   ChangeHot h; u32 nDeps, nOther, nOps, nPreds; u32 err;   // err: KErr of the header / directory / count (raised for every change of a batch)
-  bool single; SingleVals sv;
+  bool single; bool unknownCols /* a column id this version does not know: the host carries its values (unknowncols.hpp) */; SingleVals sv;
 };
 // columnar.js:688-708 (container), :635-652 decodeChangeHeader, :609-624 decodeColumnInfo; op count = values of the action
 // column, pred count = sum of the predNum column (new.js:686-700 reads ops until the action column is exhausted)
 template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedChange& o) {
   o.h.off = off; o.h.len = len; o.h.depsOff = o.h.actorOff = o.h.actorLen = o.h.otherOff = o.h.dirOff = o.h.dataOff = 0; o.h.startOp = 0; o.h.seq = 0;
-  o.nDeps = 0; o.nOther = 0; o.nOps = 0; o.nPreds = 0; o.err = 0; o.single = false;
+  o.nDeps = 0; o.nOther = 0; o.nOps = 0; o.nPreds = 0; o.err = 0; o.single = false; o.unknownCols = false;
   const u32 end = off + len;
   ByteReaderT<S> r(src, off + 8, end);
   const u32 chunkType = r.done() ? 0xffu : src.ld(r.pos); r.pos++;
@@ -582,6 +588,7 @@ template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedCh
       const u32 id = id64 > 0xffffffffULL ? 0xffffffffu : (u32)id64, l = (u32)l64, pos = dataPos + (u32)total;
       if (id == 0x42) { actOff = (u32)total; actLen = l; haveAct = true; } else if (id == 0x70) { pnOff = (u32)total; pnLen = l; }
       if (afterValLen) { afterValLen = false; if (id == 0x57) { sv.valOff = pos; rawLen = l; } }
+      if (col_index_of(id) < 0) o.unknownCols = true;
       if (single && !colErr) {
         const int ix = col_index_of(id);
         if (ix >= 0 && ix != CX_VAL_RAW && ix != CX_CHLD_ACTOR && ix != CX_CHLD_CTR) {
@@ -657,7 +664,7 @@ struct DecodeTilesArgs {
   u32* decErr /* [B] KErr of the column contents: raised only if the change is applied (the reference decodes columns lazily) */;
   RawRows rows; u32 rowCap, predCap;   // rows are written only inside the capacity; totals[2] tells the host to grow and run again
   unsigned long long* cursor /* [0] ops, [1] preds handed out so far */;
-  u32* totals /* [2] overflow [3] some change has > SMALL_CHANGE_OPS ops; [0] ops and [1] preds are filled from the cursor by k_decode_totals */; u64* errWord; u32 numTiles;
+  u32* totals /* [2] overflow [3] bit 0: some change has > SMALL_CHANGE_OPS ops, bit 1: some change has a column with an unknown id; [0] ops and [1] preds are filled from the cursor by k_decode_totals */; u64* errWord; u32 numTiles;
   u32* directList /* [B] changes the staged kernel could not take (outside their tile's staged window) */; u32* directCount;
 };
 // what one thread does with its change once the row range is known
@@ -666,12 +673,13 @@ template <class S> HD void finish_change(const DecodeTilesArgs& a, const S& src,
   a.rawBase[c] = base; a.rawPredBase[c] = pb;
   u32 kerr = 0;
   if (pc.err) raise(a.errWord, pc.err, c);
-  else if (pc.nOps > SMALL_CHANGE_OPS) a.totals[3] = 1;   // expanded by DecodeColumnKernel once the gate has decided
+  else if (pc.nOps > SMALL_CHANGE_OPS) atomic_or(&a.totals[3], 1u);   // expanded by DecodeColumnKernel once the gate has decided
   else if (pc.nOps > 0) {
     if ((u64)base + pc.nOps > a.rowCap || (u64)pb + pc.nPreds > a.predCap) a.totals[2] = 1;
     else if (pc.single) store_single(pc.sv, base, pb, a.rows);
     else kerr = expand_change(src, pc.h, pc.nOps, pc.nPreds, base, pb, a.rows);
   }
+  if (!pc.err && pc.unknownCols) atomic_or(&a.totals[3], 2u);
   a.decErr[c] = kerr;
 }
 
@@ -686,6 +694,7 @@ inline void decode_tiles_range(Ctx& c, DecodeTilesArgs a, u32 first, u32 end) {
     const u8* p = a.arena + a.chOff[i];
     if (a.chLen[i] > 8 && p[8] == 2 && p[0] == 0x85) { a.directList[(*a.directCount)++] = i; continue; }
     ParsedChange pc; parse_change(PtrSrc{a.arena}, a.chOff[i], a.chLen[i], pc);
+    if (getenv("AMG_EMU_DECODE_STATS")) { static size_t tot = 0, nonSingle = 0, shown = 0; tot++; if (!pc.single) { nonSingle++; if (shown < 6 && pc.nOps == 1) { shown++; fprintf(stderr, "non-single 1-op change %u:", i); for (u32 k = pc.h.dirOff; k < a.chOff[i] + a.chLen[i]; k++) fprintf(stderr, " %02x", a.arena[k]); fprintf(stderr, "\n"); } } if (tot % 100000 == 0) fprintf(stderr, "decode stats: %zu changes, %zu not single\n", tot, nonSingle); }
     finish_change(a, PtrSrc{a.arena}, i, pc, (u32)std::min<u64>(a.cursor[0], 0x7fffffffu), (u32)std::min<u64>(a.cursor[1], 0x7fffffffu));
     a.cursor[0] += pc.nOps; a.cursor[1] += pc.nPreds;
   }

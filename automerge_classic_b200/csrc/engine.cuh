@@ -24,6 +24,7 @@
 #include "domlocal.cuh"
 #include "doccols.cuh"
 #include "history.cuh"
+#include "unknowncols.hpp"
 
 namespace amg {
 
@@ -281,6 +282,9 @@ class Engine {
   bool headIndexesUnknown = false;   // Backend.load of a document with several heads and no head indexes, until computeHashGraph has matched them
   bool haveHashGraph = true;   // false after Backend.load: change history (hashes, bytes) is not reconstructed (new.js:1887-1912)
   void benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes);
+  UnknownStore unknownCols;   // values of columns with ids this version does not know, per op (unknowncols.hpp)
+  void collectUnknownColumns(size_t B, std::vector<std::pair<u64, UnknownRow>>& out, std::set<u32>& ids);
+  void appendUnknownDocColumns(std::vector<std::pair<u32, std::string>>& cols);   // save(): their document columns
   RawRows rawRows();
   u32 decodeHugeChanges(const RawRows& raw, size_t numLarge); DBuf<u32> hugeDone;
   void runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes);

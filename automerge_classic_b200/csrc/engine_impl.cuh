@@ -348,7 +348,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   }
   timer.mark(); hostMark(); nvtx.next("actors+seq+finalize");
   std::vector<std::string> actorsNow = actorIds; std::vector<u64> clockNow = clock; std::vector<u32> actorCntH; std::vector<std::pair<u32, u32>> actorRepNow = actorRep;
-  size_t M = 0, P = 0, N = numRows, numPairs = numSucc; u64 maxOpNow = maxOp;
+  size_t M = 0, P = 0, N = numRows, numPairs = numSucc; u64 maxOpNow = maxOp; bool hasUnknownColsCall = false;
   IdTable idt{nullptr, nullptr, 0};
   std::vector<std::array<u8, 32>> headsNow = heads; std::vector<u32> headIdxNow;
   if (numNew > 0) {
@@ -453,7 +453,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     timeBase.ensure(ctx, B + 1);
     const bool allApplied = numNew == B;
     opBase.ensure(ctx, B + 1); predBase.ensure(ctx, B + 1); u32* opBaseP = opBase.p; u32* predBaseP = predBase.p;
-    const u32 anyLarge = decTot[3];
+    const u32 anyLarge = decTot[3] & 1u; hasUnknownColsCall = (decTot[3] & 2u) != 0;
     // first op / pred of every applied change in batch order (the raw rows themselves lie in tile arrival order, rawBase)
     if (allApplied) { scan_exclusive(ctx, scanTmp, nOps.p, opBase.p, B); scan_exclusive(ctx, scanTmp, nPreds.p, predBase.p, B); M = decTot[0]; P = decTot[1]; }
     else {
@@ -643,6 +643,8 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     headIdxNow = headIdx;
   }
   dbgMark("commit:heads-done");
+  std::vector<std::pair<u64, UnknownRow>> unknownNow; std::set<u32> unknownIdsNow;
+  if (numNew > 0 && hasUnknownColsCall) collectUnknownColumns(B, unknownNow, unknownIdsNow);   // rare: columns written by a future version (unknowncols.hpp)
   // ------------------------------------------------------------ 8. commit (nothing above mutated persistent state)
   sync(ctx);
   dbgMark("commit:synced");
@@ -672,6 +674,8 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     doc.swap(sorted); numRows = N;
     std::swap(succOff.p, newSuccOff.p); std::swap(succOff.cap, newSuccOff.cap); std::swap(succ.p, newSucc.p); std::swap(succ.cap, newSucc.cap); numSucc = numPairs;
     fill32(doc.time.p, 0, N);
+    for (auto& kv : unknownNow) unknownCols.byOp[kv.first] = std::move(kv.second);
+    unknownCols.colIds.insert(unknownIdsNow.begin(), unknownIdsNow.end());
     loadedDoc.clear(); numApplied += numNew; actorRep = actorRepNow; actorIds = actorsNow; clock = clockNow; maxOp = maxOpNow; heads = headsNow; headIdx = headIdxNow;
     dbgMark("commit:state-swapped");
     rebuildActorTable();   // slots of actors registered in this call become permanent (first = 0)
@@ -970,6 +974,36 @@ inline bool Engine::decodeOverflowed(const u32 totals[4]) {
   if (totals[1] >= (1u << 30)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: more than 2^30 predecessors in one call");
   decWantRows = (size_t)totals[0] + 1024; decWantPreds = (size_t)totals[1] + 1024;
   return true;
+}
+
+// Values of columns with unknown ids in the changes this call applies (reference new.js:1406-1424 keeps them in the document).
+// Host work on a rare path: headers, op counts and actor maps come back from the device, the change bytes from the arena.
+inline void Engine::collectUnknownColumns(size_t B, std::vector<std::pair<u64, UnknownRow>>& out, std::set<u32>& ids) {
+  std::vector<ChangeHot> hh(B); std::vector<u32> nops(B), amb(B + 1), nact(B); std::vector<u8> ap(B);
+  d2h(ctx, hh.data(), hot.p, B * sizeof(ChangeHot)); d2h(ctx, nops.data(), nOps.p, B * 4); d2h(ctx, amb.data(), amapBase.p, (B + 1) * 4); d2h(ctx, nact.data(), nActors.p, B * 4); d2h(ctx, ap.data(), applied.p, B); sync(ctx);
+  std::vector<u32> am(amb[B] + 1); if (amb[B]) { d2h(ctx, am.data(), amap.p, (size_t)amb[B] * 4); sync(ctx); }
+  for (size_t b = 0; b < B; b++) {
+    if (!ap[b] || nops[b] == 0 || hh[b].dataOff <= hh[b].dirOff) continue;
+    const ChangeHot& h = hh[b];
+    std::vector<u8> bytes(h.len); d2h(ctx, bytes.data(), arena.p + h.off, h.len); sync(ctx);
+    std::vector<std::array<u32, 3>> cols; bool any = false;
+    { ByteReader d(bytes.data(), h.dirOff - h.off, h.dataOff - h.off); u32 pos = h.dataOff - h.off;
+      while (!d.done() && !d.err) { const u32 id = (u32)d.uleb(), l = (u32)d.uleb(); cols.push_back({id, pos, l}); if (!is_known_change_column(id)) any = true; pos += l; } }
+    if (!any) continue;
+    const u32 author = am[amb[b]];
+    const u32 e = read_unknown_columns(bytes.data(), cols, nops[b], is_known_change_column, [&](size_t i, UnknownRow& row) {
+      for (auto& kv : row) {
+        ids.insert(kv.first);
+        if ((kv.first & 7) == 1) for (auto& v : kv.second) if (!v.isNull) {   // ACTOR_ID: change-local index -> document actor index (new.js:586-588)
+          if ((u64)v.num >= nact[b]) throw Error(AMG_ERR_RANGE, "actor index out of range");
+          v.num = am[amb[b] + (u32)v.num];
+        }
+      }
+      out.emplace_back(pack_id(h.startOp + i, author), row);
+    });
+    if (e == KE_UNSUPPORTED_OP) throw Error(AMG_ERR_RANGE, "unexpected VALUE_RAW column");
+    if (e) throwKernelError(((u64)b << 8) | e, actorIds);
+  }
 }
 
 // Columns of bulk changes (>= HUGE_CHANGE_OPS ops) through the parallel column decoders. largeList holds the large changes of
@@ -1302,7 +1336,7 @@ inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* 
   const size_t M = tot[0];
   DBuf<u32>* cols[12] = {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff};
   RawRows raw = rawRows();
-  if (tot[3]) {
+  if (tot[3] & 1u) {
     largeFlag.ensure(ctx, n + 1); largeSlot.ensure(ctx, n + 2); largeList.ensure(ctx, n + 1);
     foreach(ctx, n, LargeFlagKernel{nOps.p, applied.p, largeFlag.p});
     scan_exclusive(ctx, scanTmp, largeFlag.p, largeSlot.p, n);

@@ -284,6 +284,10 @@ def cpu_sample(wl_name, sample_ops):
 
 
 def main():
+    import faulthandler
+    # a hung native call must not eat the GPU budget silently: after this many seconds the Python stacks go to stderr and the
+    # process exits
+    faulthandler.dump_traceback_later(int(os.environ.get('AMG_BENCH_WATCHDOG_S', '900')), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)

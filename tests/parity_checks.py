@@ -136,10 +136,10 @@ def check_decode_corrupted(gpu_doc, oracle_mod, seed=11, cases=150):
     change the oracle decodes must decode identically; one it refuses may be refused for a different reason)."""
     import random
     from automerge_classic_b200 import tracegen, columnar
-    from automerge_classic_b200.engine import AmgError
+    from automerge_classic_b200.engine import AmgError, Unsupported
     rnd = random.Random(seed)
     base = tracegen.generate('C6', 300, 3, seed=seed).changes() + tracegen.generate('C4', 600, 3, seed=seed).changes()[:3]
-    same = refused = 0
+    same = refused = limits = 0
     for _ in range(cases):
         c = bytearray(_inflated(rnd.choice(base)))
         for _ in range(rnd.choice((1, 1, 2))):
@@ -175,6 +175,9 @@ def check_decode_corrupted(gpu_doc, oracle_mod, seed=11, cases=150):
         try:
             check_decoded_rows(gpu_doc, oracle_mod, [fixed]) if ok_o else gpu_doc().debug_decode([fixed])
             ok_g = True
+        except Unsupported:   # a documented limit of the engine (32-bit counters / offsets), reported as such: not a parity question
+            limits += 1
+            continue
         except AmgError:
             ok_g = False
         if ok_o:
@@ -182,7 +185,7 @@ def check_decode_corrupted(gpu_doc, oracle_mod, seed=11, cases=150):
             same += 1
         else:
             refused += 1
-    assert same >= cases // 10, (same, refused)
+    assert same >= cases // 10 and limits <= cases // 10, (same, refused, limits)
     return same, refused
 
 
