@@ -114,7 +114,8 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   for (auto& x : lastPhaseMs) x = 0;
   auto hostMark = [&]() { if (hmark < 24) lastPhaseMs[hmark++] = hclk.ms(); };
   curTimer = &timer; curHostMark = hostMark;
-  dbgMarks.clear(); dbgMark = [this, &hclk](const char* l) { dbgMarks.emplace_back(l, hclk.ms()); };
+  static const bool liveMarks = getenv("AMG_DEBUG_LIVE") != nullptr;   // development aid: marks go to stderr as they happen (to see where a call is stuck)
+  dbgMarks.clear(); dbgMark = [this, &hclk](const char* l) { dbgMarks.emplace_back(l, hclk.ms()); if (liveMarks) { fprintf(stderr, "amgpu mark %-28s %9.3f ms\n", l, hclk.ms()); fflush(stderr); } };
   struct SideJoinAll { Ctx& c; ~SideJoinAll() { side_join(c); } } sideJoinAll{ctx};   // whatever this call put on the side stream is ordered before the next call
   struct ClearTimer { Engine* e; ~ClearTimer() { e->curTimer = nullptr; e->curHostMark = nullptr; e->dbgMark = [](const char*) {}; } } clearTimer{this};
   // ------------------------------------------------------------ 0. stage the batch in the arena; hash and decode it piece by piece
