@@ -271,6 +271,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   }
   // changes the tile kernel passed on (inflated ones, changes outside their tile's window), then the totals
   { DecodeTilesArgs fin = dargs; fin.arena = arena.p; decode_tiles_finish(ctx, fin, B); }
+  dbgMark("decode:finish-enqueued");
   side_join(ctx);
   timer.mark(); hostMark(); nvtx.next("gate");
   // (parse errors surface with the first host round trip of the gate: the error word travels with every small read, and a
@@ -321,6 +322,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     if (depTotal) foreach(ctx, depTotal, GateDepWinnerKernel{gateBest.p, numApplied, depIdx.p});
     foreach(ctx, B, GateWinnerKernel{gateBest.p, numApplied, primary.p});
   }
+  dbgMark("gate:settled");
   applied.ensure(ctx, B); appRank.ensure(ctx, B + 1); isRow.ensure(ctx, B + 1);
   dev_memset(ctx, flagWord.p, 0, 8);
   foreach(ctx, B, AppliedFlagKernel{primary.p, pass.p, numApplied, applied.p, isRow.p, flagWord.p});
@@ -357,10 +359,10 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     authorSlot.ensure(ctx, B); newSlots.ensure(ctx, B + 1); u32 fresh = 0;
     while (true) {   // grow the table until the distinct authors fit at load factor <= 1/2
       dev_memset(ctx, flagWord.p, 0, 8);
-      foreach(ctx, B, ActorInternKernel{arena.p, hot.p, applied.p, appRank.p, actorSlots.p, (u64)actorCap - 1, authorSlot.p});
+      foreach(ctx, B, ActorInternKernel{arena.p, hot.p, applied.p, appRank.p, actorSlots.p, (u64)actorCap - 1, authorSlot.p, flagWord.p + 1});
       foreach(ctx, B, NewActorKernel{hot.p, applied.p, authorSlot.p, actorSlots.p, newSlots.p, flagWord.p});
-      fresh = readU32(flagWord.p);
-      if ((actorIds.size() + fresh) * 2 <= actorCap) break;
+      u32 full = 0; readU32x2(flagWord.p, flagWord.p + 1, &fresh, &full);
+      if (!full && (actorIds.size() + fresh) * 2 <= actorCap) break;
       actorCap *= 4; actorSlots.ensure(ctx, actorCap); rebuildActorTable();
     }
     if (fresh > 0) {

@@ -135,26 +135,29 @@ HD u64 fnv1a64(const u8* p, u32 len) { u64 h = 0xcbf29ce484222325ULL; for (u32 i
 
 struct ActorSlot { u64 hash; u64 first; /* (appRank << 32 | batch change), min wins */ u32 actorNum; u32 repOff; u32 repLen; u32 pad; };
 
-HD u32 actor_find_or_insert(ActorSlot* slots, u64 mask, u64 h) {
+HD u32 actor_find_or_insert(ActorSlot* slots, u64 mask, u64 h) {   // EMPTY32: the table is full (the host grows it and runs the kernel again)
   u64 s = mix64(h) & mask;
-  while (true) {
+  for (u64 probes = 0; probes <= mask; probes++) {
     u64 cur = slots[s].hash;   // read first: after the first few inserts every lookup hits without an atomic
     if (cur == h) return (u32)s;
     if (cur == 0) { cur = atomic_cas(&slots[s].hash, (u64)0, h); if (cur == 0 || cur == h) return (u32)s; }
     s = (s + 1) & mask;
   }
+  return EMPTY32;
 }
 HD u32 actor_find(const ActorSlot* slots, u64 mask, u64 h) {
   u64 s = mix64(h) & mask;
-  while (true) { const u64 cur = slots[s].hash; if (cur == h) return (u32)s; if (cur == 0) return EMPTY32; s = (s + 1) & mask; }
+  for (u64 probes = 0; probes <= mask; probes++) { const u64 cur = slots[s].hash; if (cur == h) return (u32)s; if (cur == 0) return EMPTY32; s = (s + 1) & mask; }
+  return EMPTY32;
 }
 // authors of applied changes claim slots; first (smallest application rank) appearance is recorded
 struct ActorInternKernel {
-  const u8* arena; const ChangeHot* meta; const u8* applied; const u32* appRank; ActorSlot* slots; u64 mask; u32* authorSlot;
+  const u8* arena; const ChangeHot* meta; const u8* applied; const u32* appRank; ActorSlot* slots; u64 mask; u32* authorSlot; u32* full /* set when the table has no room: grown by the host, kernel run again */;
   HD void operator()(size_t b) const {
     if (!applied[b]) { authorSlot[b] = EMPTY32; return; }
     const u64 h = fnv1a64(arena + meta[b].actorOff, meta[b].actorLen);
     const u32 s = actor_find_or_insert(slots, mask, h);
+    if (s == EMPTY32) { *full = 1; authorSlot[b] = EMPTY32; return; }
     const u64 cand = ((u64)appRank[b] << 32) | (u64)b;
     if (cand < slots[s].first) atomic_min(&slots[s].first, cand);
     authorSlot[b] = s;

@@ -41,7 +41,7 @@ struct RaiseDecErrKernel { const u32* decErr; u64* errWord; HD void operator()(s
 struct NewActorKernel {
   const ChangeHot* meta; const u8* applied; const u32* authorSlot; ActorSlot* slots; u32* newSlots; u32* newCount;
   HD void operator()(size_t b) const {
-    if (!applied[b]) return;
+    if (!applied[b] || authorSlot[b] == EMPTY32) return;
     ActorSlot& s = slots[authorSlot[b]];
     if (s.actorNum != EMPTY32 || (u32)(s.first & 0xffffffffu) != (u32)b) return;
     s.repOff = meta[b].actorOff; s.repLen = meta[b].actorLen;

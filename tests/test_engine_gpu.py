@@ -51,7 +51,7 @@ def test_reference_fixture(gpu_doc, test):
     assert not fails, '\n'.join(fails[:5])
 
 
-TRACES = [('C1', 0, 0), ('C2', 3000, 0), ('C2b', 5000, 0), ('C3', 20000, 10), ('C3', 3000, 3), ('C4', 4000, 4)]
+TRACES = [('C1', 0, 0), ('C2', 3000, 0), ('C2b', 5000, 0), ('C3', 20000, 10), ('C3', 3000, 3), ('C4', 4000, 4), ('C4', 20000, 100)]   # the last one: 100 new actors in one call (actor table growth)
 
 
 @pytest.mark.parametrize('cfg,n,a', TRACES)

@@ -41,7 +41,7 @@ def test_reference_fixture_emu(emu_doc, test):
     assert not fails, '\n'.join(fails[:5])
 
 
-@pytest.mark.parametrize('cfg,n,a', [('C1', 0, 0), ('C2', 400, 0), ('C2b', 700, 0), ('C2b', 6000, 0), ('C3', 3000, 10), ('C3', 900, 3), ('C4', 2000, 4)])
+@pytest.mark.parametrize('cfg,n,a', [('C1', 0, 0), ('C2', 400, 0), ('C2b', 700, 0), ('C2b', 6000, 0), ('C3', 3000, 10), ('C3', 900, 3), ('C4', 2000, 4), ('C4', 10000, 100)])
 def test_trace_parity_emu(emu_doc, oracle_mod, cfg, n, a):
     parity_checks.check_trace_parity(emu_doc, oracle_mod, cfg, n, a)
 
