@@ -73,10 +73,21 @@ struct Ctx {
 // driver when an allocation fails.
 struct DevPool {
   typedef std::pair<int, size_t> Key;   // (device, block bytes)
-  std::mutex m; std::multimap<Key, void*> parked; std::unordered_map<void*, Key> blocks; size_t parkedBytes = 0;
+  struct Block { Key key; bool fromSlab; };
+  struct Slab { char* base; size_t used, size; };
+  std::mutex m; std::multimap<Key, void*> parked; std::unordered_map<void*, Block> blocks; size_t parkedBytes = 0;
+  std::map<int, Slab> slab;   // per device: the slab new blocks are carved from
   static const size_t kMaxParked = 32ull << 30;
+  static const size_t kSlabBytes = 256ull << 20;   // a fresh document needs ~200 tables: carved from a few slabs instead of ~200 cudaMallocs (0.1 - 1 ms each)
   static DevPool& get() { static DevPool* p = new DevPool(); return *p; }   // never destroyed: must outlive every engine and the runtime's own teardown
-  void trim() { for (auto& kv : parked) { blocks.erase(kv.second); cudaFree(kv.second); } parked.clear(); parkedBytes = 0; }
+  // gives parked blocks that own their allocation back to the driver (blocks carved from a slab stay parked: a slab is never freed)
+  void trim() {
+    for (auto it = parked.begin(); it != parked.end();) {
+      auto b = blocks.find(it->second);
+      if (b != blocks.end() && b->second.fromSlab) { ++it; continue; }
+      parkedBytes -= it->first.second; if (b != blocks.end()) blocks.erase(b); cudaFree(it->second); it = parked.erase(it);
+    }
+  }
 };
 #endif
 inline void* dev_alloc(size_t bytes) {
@@ -90,10 +101,29 @@ inline void* dev_alloc(size_t bytes) {
   if (it != pool.parked.end() && it->first.first == dev && it->first.second <= want + want / 2 + 4096) {
     void* p = it->second; pool.parkedBytes -= it->first.second; pool.parked.erase(it); return p;
   }
+  if (want <= DevPool::kSlabBytes / 4) {   // small and medium tables: carved from the device's current slab
+    DevPool::Slab& sl = pool.slab[dev];
+    if (!sl.base || sl.used + want > sl.size) {
+      void* base = nullptr; cudaError_t e = cudaMalloc(&base, DevPool::kSlabBytes);
+      if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); pool.trim(); e = cudaMalloc(&base, DevPool::kSlabBytes); }
+      if (e == cudaSuccess) {
+        if (sl.base && sl.size - sl.used >= 4096) {   // what is left of the old slab stays usable
+          void* rest = sl.base + sl.used; const size_t restBytes = (sl.size - sl.used) & ~(size_t)255;
+          pool.blocks[rest] = DevPool::Block{DevPool::Key(dev, restBytes), true}; pool.parked.emplace(DevPool::Key(dev, restBytes), rest); pool.parkedBytes += restBytes;
+        }
+        sl.base = (char*)base; sl.used = 0; sl.size = DevPool::kSlabBytes;
+      } else cudaGetLastError();   // no room for a slab: fall through to a plain allocation
+    }
+    if (sl.base && sl.used + want <= sl.size) {
+      void* p = sl.base + sl.used; sl.used += want;
+      pool.blocks[p] = DevPool::Block{DevPool::Key(dev, want), true};
+      return p;
+    }
+  }
   void* p = nullptr; cudaError_t e = cudaMalloc(&p, want);
   if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); pool.trim(); e = cudaMalloc(&p, want); }
   CUDA_CHECK(e);
-  pool.blocks[p] = DevPool::Key(dev, want);
+  pool.blocks[p] = DevPool::Block{DevPool::Key(dev, want), false};
   return p;
 #endif
 }
@@ -106,8 +136,8 @@ inline void dev_free(void* p) {
   DevPool& pool = DevPool::get(); std::lock_guard<std::mutex> lock(pool.m);
   auto it = pool.blocks.find(p);
   if (it == pool.blocks.end()) { cudaFree(p); return; }
-  if (pool.parkedBytes + it->second.second > DevPool::kMaxParked) { pool.blocks.erase(it); cudaFree(p); return; }
-  pool.parked.emplace(it->second, p); pool.parkedBytes += it->second.second;
+  if (!it->second.fromSlab && pool.parkedBytes + it->second.key.second > DevPool::kMaxParked) { pool.blocks.erase(it); cudaFree(p); return; }
+  pool.parked.emplace(it->second.key, p); pool.parkedBytes += it->second.key.second;
 #endif
 }
 inline void dev_memset(Ctx& c, void* p, int v, size_t bytes) {
@@ -339,11 +369,20 @@ inline void d2d_copy(Ctx& c, void* dst, const void* src, size_t bytes) {
   CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c.copy)); c.copyPending = true;
 #endif
 }
-inline void copy_piece_done(Ctx& c) {
+inline size_t copy_piece_record(Ctx& c) {   // marks "everything queued on the copy stream so far"; returns the mark's number
 #ifndef AMG_EMU
   if (c.pieceNext >= c.pieceEv.size()) { cudaEvent_t e; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.pieceEv.push_back(e); }
-  cudaEvent_t e = c.pieceEv[c.pieceNext++];
-  CUDA_CHECK(cudaEventRecord(e, c.copy)); CUDA_CHECK(cudaStreamWaitEvent(c.stream, e, 0)); CUDA_CHECK(cudaStreamWaitEvent(c.side, e, 0));
+  CUDA_CHECK(cudaEventRecord(c.pieceEv[c.pieceNext], c.copy));
+  return c.pieceNext++;
+#else
+  return 0;
+#endif
+}
+inline void copy_piece_wait(Ctx& c, size_t mark) {   // main and side stream wait for that mark
+#ifndef AMG_EMU
+  CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.pieceEv[mark], 0)); CUDA_CHECK(cudaStreamWaitEvent(c.side, c.pieceEv[mark], 0));
+#else
+  (void)mark;
 #endif
 }
 inline void copy_join(Ctx& c) noexcept {

@@ -48,7 +48,7 @@ inline void parallel_copy(u8* dst, const u8* src, size_t n) {
 // changes [c0, c1) of a pointer array, back to back into dst (the shape Backend.applyChanges(state, Uint8Array[]) hands over)
 inline void parallel_gather(u8* dst, const u8* const* bufs, const size_t* lens, size_t c0, size_t c1) {
   size_t bytes = 0; for (size_t i = c0; i < c1; i++) bytes += lens[i];
-  unsigned nt = bytes < (4u << 20) ? 1u : std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+  unsigned nt = bytes < (4u << 20) ? 1u : std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency() / 2));   // small scattered buffers: bound by cache misses, not by bandwidth
   if (nt == 1) { for (size_t i = c0; i < c1; i++) { memcpy(dst, bufs[i], lens[i]); dst += lens[i]; } return; }
   std::vector<std::thread> ts; const size_t per = (c1 - c0 + nt - 1) / nt; size_t at = 0;
   for (unsigned t = 0; t < nt; t++) {
@@ -169,34 +169,59 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   if (throughMirror) { ensureHostMirror(); hostArena.resize(arenaLen0 + total); }
   arena.ensure(ctx, arenaLen0 + total + 64, arenaLen0);
   dbgMark("stage:begin");
-  // (offset, length) of every change: the host's list, the device's chOff / chLen. Pieces end on change boundaries.
-  batch.resize(B);
+  batch.clear();
+  // Pieces end on change boundaries. The copies of a pinned / device buffer are queued first (they need nothing but byte
+  // ranges); the (offset, length) table of the changes is built and uploaded while they run; then every piece's kernels
+  // are queued behind its copy. Pageable input is staged piece by piece, each piece's kernels right behind it.
   const size_t kPiece = 16u << 20;
-  struct Piece { size_t byteEnd, changeEnd; };
+  struct Piece { size_t byteEnd, changeEnd, mark; };
   std::vector<Piece> pieces;
+  pairStage.ensure(B + 1); HostChange* pairs = pairStage.p;   // pinned: the table goes up by DMA while the host carries on
   if (blob && n > 0) {
-    const size_t base = offsets[0]; const u32 shift = (u32)(arenaLen0 - base);
-    for (size_t i = 0; i < n; i++) { batch[i].off = (u32)offsets[i] + shift; batch[i].len = (u32)(offsets[i + 1] - offsets[i]); }
+    const size_t base = offsets[0];
     for (size_t o = kPiece;; o += kPiece) {
-      if (o >= total) { pieces.push_back({total, n}); break; }
+      if (o >= total) { pieces.push_back({total, n, 0}); break; }
       const size_t ce = (size_t)(std::upper_bound(offsets, offsets + n + 1, (u64)(base + o)) - offsets) - 1;   // changes that end inside the first o bytes
-      pieces.push_back({(size_t)(offsets[ce] - base), ce});
+      pieces.push_back({(size_t)(offsets[ce] - base), ce, 0});
     }
   } else {
     size_t at = 0, nextCut = kPiece;
     for (size_t i = 0; i < n; i++) {
-      batch[i] = HostChange{(u32)(arenaLen0 + at), (u32)lens[i]}; at += lens[i];
-      if (at >= nextCut && i + 1 < n) { pieces.push_back({at, i + 1}); nextCut = at + kPiece; }
+      pairs[i] = HostChange{(u32)(arenaLen0 + at), (u32)lens[i]}; at += lens[i];
+      if (at >= nextCut && i + 1 < n) { pieces.push_back({at, i + 1, 0}); nextCut = at + kPiece; }
     }
-    pieces.push_back({at, n});
+    pieces.push_back({at, n, 0});
   }
   cur = arenaLen0 + total;
-  if (Bq > 0) {
-    batchOriginal.assign(B, HostChange{0, 0});
-    for (size_t i = 0; i < Bq; i++) { batch[n + i] = queue[i]; batchOriginal[n + i] = queueOriginal[i]; }
+  copy_fork(ctx);   // the copy stream starts behind what is queued on the main stream so far (arena growth)
+  const bool copiesFirst = srcKind != SRC_PAGEABLE;
+  auto queueCopy = [&](Piece& pc, size_t byte0, size_t ch0) {
+    const size_t m = pc.byteEnd - byte0;
+    if (m > 0) {
+      u8* dst = arena.p + arenaLen0 + byte0;
+      if (srcKind == SRC_PINNED) h2d_copy(ctx, dst, blob + offsets[0] + byte0, m);
+      else if (srcKind == SRC_DEVICE) d2d_copy(ctx, dst, blob + offsets[0] + byte0, m);
+      else {
+        u8* stage = hostArena.data() + arenaLen0 + byte0;
+        if (blob) parallel_copy(stage, blob + offsets[0] + byte0, m);
+        else parallel_gather(stage, bufs, lens, ch0, pc.changeEnd);
+        h2d_copy(ctx, dst, stage, m);
+      }
+    }
+    pc.mark = copy_piece_record(ctx);
+  };
+  if (copiesFirst) { size_t byte0 = 0, ch0 = 0; for (Piece& pc : pieces) { queueCopy(pc, byte0, ch0); byte0 = pc.byteEnd; ch0 = pc.changeEnd; } }
+  dbgMark("stage:copies-queued");
+  if (blob && n > 0) {   // the table of a packed batch: filled by a few threads (1M entries), in the shadow of the copies
+    const size_t base = offsets[0]; const u32 shift = (u32)(arenaLen0 - base);
+    auto fill = [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) { pairs[i].off = (u32)offsets[i] + shift; pairs[i].len = (u32)(offsets[i + 1] - offsets[i]); } };
+    const unsigned nt = n < (1u << 16) ? 1u : std::min<unsigned>(4, std::max(1u, std::thread::hardware_concurrency()));
+    if (nt == 1) fill(0, n);
+    else { std::vector<std::thread> ts; const size_t per = (n + nt - 1) / nt; for (unsigned t = 0; t < nt; t++) { const size_t a = t * per, b = std::min(n, a + per); if (a < b) ts.emplace_back(fill, a, b); } for (auto& t : ts) t.join(); }
   }
+  for (size_t i = 0; i < Bq; i++) pairs[n + i] = queue[i];
   chPairs.ensure(ctx, B); chOff.ensure(ctx, B); chLen.ensure(ctx, B);
-  h2d(ctx, chPairs.p, batch.data(), B * sizeof(HostChange));
+  h2d(ctx, chPairs.p, pairs, B * sizeof(HostChange));
   foreach(ctx, B, SplitPairsKernel{chPairs.p, chOff.p, chLen.p});
   dev_memset(ctx, arena.p + cur, 0, 64);
   dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull;
@@ -205,38 +230,30 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   u8* hashOut = hashes.p + numApplied * 32;
   const DecodeTilesArgs dargs = decodeArgs(arena.p, B, cur - arenaLen0);
   decode_tiles_begin(ctx, dargs);
-  copy_fork(ctx);   // the copy stream starts behind what is queued on the main stream so far (arena growth, tables)
   struct SideJoin { Ctx& c; ~SideJoin() { side_join(c); } } sideJoin{ctx};   // also on the error paths: nothing of this call outlives it on the side stream
   dbgMark("stage:tables");
-  // changes [c0, c1) are on the device once the copy stream has passed `ev`: hash on the side stream, decode on the main one
-  auto processRange = [&](size_t c0, size_t c1, bool waitCopy) {
+  // changes [c0, c1) are on the device once the copy stream has passed the piece's mark: hash on the side stream, decode on the main one
+  auto processRange = [&](size_t c0, size_t c1, bool waitCopy, size_t mark) {
     if (c1 <= c0) return;
-    if (waitCopy) copy_piece_done(ctx);   // both streams wait for the piece
+    if (waitCopy) copy_piece_wait(ctx, mark);   // both streams wait for the piece
     else side_fork(ctx);
     ShaKernel sk{arena.p, chOff.p, chLen.p, hashOut, errWord.p, nullptr, deflList.p}; sk.first = c0;
     foreach(ctx, c1 - c0, sk, true);
     decode_tiles_range(ctx, dargs, (u32)c0, (u32)c1);
   };
-  if (Bq > 0) processRange(n, B, false);   // queue entries: their bytes are on the device already
+  side_fork(ctx);   // the side stream is ordered behind the tables
+  if (Bq > 0) processRange(n, B, false, 0);   // queue entries: their bytes are on the device already
   {
     size_t byte0 = 0, ch0 = 0;
-    for (const Piece& pc : pieces) {
-      const size_t m = pc.byteEnd - byte0;
-      if (m > 0) {
-        u8* dst = arena.p + arenaLen0 + byte0;
-        if (srcKind == SRC_PINNED) h2d_copy(ctx, dst, blob + offsets[0] + byte0, m);
-        else if (srcKind == SRC_DEVICE) d2d_copy(ctx, dst, blob + offsets[0] + byte0, m);
-        else {
-          u8* stage = hostArena.data() + arenaLen0 + byte0;
-          if (blob) parallel_copy(stage, blob + offsets[0] + byte0, m);
-          else parallel_gather(stage, bufs, lens, ch0, pc.changeEnd);
-          h2d_copy(ctx, dst, stage, m);
-        }
-      }
-      processRange(ch0, pc.changeEnd, true);
+    for (Piece& pc : pieces) {
+      if (!copiesFirst) queueCopy(pc, byte0, ch0);
+      processRange(ch0, pc.changeEnd, true, pc.mark);
       byte0 = pc.byteEnd; ch0 = pc.changeEnd;
     }
   }
+  // the host's own list of the batch entries (bookkeeping at commit, queue hand-over): copied in the shadow of the device work
+  batch.assign(pairs, pairs + B);
+  if (Bq > 0) { batchOriginal.assign(B, HostChange{0, 0}); for (size_t i = 0; i < Bq; i++) batchOriginal[n + i] = queueOriginal[i]; }
   dbgMark("stage:enqueued");
   timer.mark(); hostMark(); nvtx.next("inflate+decode-finish");
   // ------------------------------------------------------------ 1. DEFLATEd changes
