@@ -74,7 +74,13 @@ struct PtrSrc { const u8* base; HD u32 ld(u32 pos) const { return base[pos]; } }
 // sbase = 32-bit shared-memory address that holds arena byte 0 of this view (stage address - first staged arena offset); an
 // explicit ld.shared: through a pointer the compiler lost the address space in most of the parser and emitted generic loads
 // (L1TEX path, long scoreboard) for what is a shared-memory read
-struct SmemSrc { u32 sbase; DEV u32 ld(u32 pos) const { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sbase + pos)); return v; } };
+#ifndef AMG_DT_THREADS
+#define AMG_DT_THREADS 128
+#endif
+struct SmemSrc {
+  u32 sbase; u32 lutBase /* shared address of the 128-byte column-id -> column-index table */; u32 slotBase /* shared address of this thread's first value slot */;
+  DEV u32 ld(u32 pos) const { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sbase + pos)); return v; }
+};
 #endif
 
 template <class S> struct ByteReaderT {
@@ -541,6 +547,28 @@ template <class S> HD bool single_value(const S& src, int ix, u32 pos, u32 l, u3
   v = (u32)val;
   return true;
 }
+// Per-thread scratch for the column values of a single-op change while its directory is walked: indexed by column
+// index with an index that is not known at compile time. In registers that costs a divergent switch per column; the tile
+// kernel keeps the 14 slots of a thread in shared memory (slot k of thread t at [k][t]: conflict-free) and looks the
+// column index up in a 128-byte shared table; elsewhere (direct kernel, emulation) a local array and the switch do.
+template <class S> struct ColSlots;
+template <> struct ColSlots<PtrSrc> {
+  u32 v[16];
+  HD ColSlots(const PtrSrc&) {}
+  HD void put(int ix, u32 x) { v[ix] = x; }
+  HD u32 get(int ix) const { return v[ix]; }
+  HD int index(u32 id) const { return col_index_of(id); }
+};
+#ifndef AMG_EMU
+template <> struct ColSlots<SmemSrc> {
+  u32 lutBase, slotBase;
+  DEV ColSlots(const SmemSrc& s) : lutBase(s.lutBase), slotBase(s.slotBase) {}
+  DEV void put(int ix, u32 x) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(slotBase + (u32)ix * (4u * AMG_DT_THREADS)), "r"(x) : "memory"); }
+  DEV u32 get(int ix) const { u32 x; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(slotBase + (u32)ix * (4u * AMG_DT_THREADS)) : "memory"); return x; }
+  DEV int index(u32 id) const { int x; asm volatile("ld.shared.s8 %0, [%1];" : "=r"(x) : "r"(lutBase + (id & 127u))); return x; }   // callers pass id < 128
+};
+#endif
+
 
 struct ParsedChange {
   ChangeHot h; u32 nDeps, nOther, nOps, nPreds; u32 err;   // err: KErr of the header / directory / count (raised for every change of a batch)
@@ -574,7 +602,50 @@ template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedCh
   // "no deflated columns" and "bytes present" (decodeChangeColumns).
   const u32 dirPos = r.pos; u32 dataPos = nCols < len ? dirPos + 2 * (u32)nCols : end;
   u32 actOff = 0, actLen = 0, pnOff = 0, pnLen = 0; bool haveAct = false, single = false; SingleVals sv; u32 dirErr = 0;
-  for (int attempt = 0; attempt < 2; attempt++) {
+  // Fast walk: every id and length of the directory is a single byte (ids below 128, columns shorter than 128 bytes: what
+  // small changes look like). Same checks and results as the general walk below, in 32-bit arithmetic and without the
+  // per-column switch (ColSlots); anything else falls through to the general walk.
+  bool fastWalk = false;
+  if (nCols <= 32 && (u64)dirPos + 2 * nCols <= (u64)end) {
+    ColSlots<S> slots(src);
+    const u32 nc = (u32)nCols; u32 total = 0, colErr = 0, lastId = 0xffffffffu, seen = 0, rawLen = 0, keyStrPos = 0; bool orderBad = false, afterValLen = false; fastWalk = true;
+    single = true; haveAct = false; actLen = pnLen = 0; sv.valOff = 0;
+    for (u32 i = 0; i < nc; i++) {
+      const u32 id = src.ld(dirPos + 2 * i), l = src.ld(dirPos + 2 * i + 1);
+      if ((id | l) & 0x80u) { fastWalk = false; break; }
+      if (lastId != 0xffffffffu && (id & ~8u) <= (lastId & ~8u)) orderBad = true;
+      lastId = id;
+      const u32 pos = dataPos + total;
+      if (!colErr) { if (id & 8u) colErr = KE_COL_DEFLATE; else if (pos + l > end) colErr = KE_SUBARRAY; }
+      const int ix = slots.index(id);
+      if (ix < 0) o.unknownCols = true;
+      else {
+        if (ix == CX_ACTION) { actOff = total; actLen = l; haveAct = true; } else if (ix == CX_PRED_NUM) { pnOff = total; pnLen = l; }
+        if (ix == CX_VAL_RAW) { if (afterValLen) { sv.valOff = pos; rawLen = l; } }
+        else if (single && !colErr && ix != CX_CHLD_ACTOR && ix != CX_CHLD_CTR) {
+          u32 v = 0, used = 0; bool isNull = false;
+          if (!single_value(src, ix, pos, l, v, isNull, used)) single = false;
+          else { slots.put(ix, isNull ? NULL32 : v); seen |= 1u << ix; if (ix == CX_KEY_STR) keyStrPos = pos + 2; }
+        }
+      }
+      afterValLen = ix == CX_VAL_LEN;
+      total += l;
+    }
+    if (fastWalk) {
+      if (orderBad) dirErr = KE_COL_ORDER; else if (colErr) dirErr = colErr;
+      auto val = [&](int ix) -> u32 { return (seen >> ix) & 1u ? slots.get(ix) : NULL32; };
+      sv.objActor = val(CX_OBJ_ACTOR); sv.objCtr = val(CX_OBJ_CTR); sv.keyActor = val(CX_KEY_ACTOR); sv.keyCtr = val(CX_KEY_CTR); sv.action = val(CX_ACTION);
+      sv.valLen = val(CX_VAL_LEN); sv.keyStrLen = val(CX_KEY_STR); sv.keyStrOff = sv.keyStrLen == NULL32 ? 0 : keyStrPos;
+      sv.insert = (seen >> CX_INSERT) & 1u ? slots.get(CX_INSERT) : 0u;
+      { const u32 pn = val(CX_PRED_NUM); sv.predNum = pn == NULL32 ? 0 : pn; }
+      sv.predActor = val(CX_PRED_ACTOR); sv.predCtr = val(CX_PRED_CTR);
+      if (sv.predNum > 1) single = false;
+      if ((sv.valLen == NULL32 ? 0u : (sv.valLen >> 4)) > rawLen) single = false;                           // the general decoder reports it
+      if (sv.predNum == 0 && (seen & ((1u << CX_PRED_ACTOR) | (1u << CX_PRED_CTR)))) single = false;        // pred values without a pred
+      if (!haveAct) single = false;
+    }
+  }
+  if (!fastWalk) for (int attempt = 0; attempt < 2; attempt++) {
     ByteReaderT<S> d(src, dirPos, end); long long lastId = -1; u64 total = 0; u32 colErr = 0; bool orderBad = false;
     single = true; haveAct = false; actLen = pnLen = 0;
     sv.objActor = sv.objCtr = sv.keyActor = sv.keyCtr = sv.action = sv.valLen = sv.keyStrLen = NULL32; sv.keyStrOff = 0; sv.insert = 0; sv.valOff = 0; sv.predNum = 0; sv.predActor = sv.predCtr = NULL32;
@@ -724,11 +795,8 @@ inline void decode_tiles_finish(Ctx& c, const DecodeTilesArgs& a, size_t) {
 //     another: a decoupled look-back across 7800 tiles advanced at most 32 tiles per L2 round trip and took 0.5 ms);
 //  4. rows are written (single-op: straight from registers, consecutive threads -> consecutive rows; 2..16 ops: second
 //     walk over the shared-memory copy); larger changes only reserve their rows.
-#ifndef AMG_DT_THREADS
-#define AMG_DT_THREADS 128
-#endif
 #ifndef AMG_DT_STAGE_KB
-#define AMG_DT_STAGE_KB 24
+#define AMG_DT_STAGE_KB 19
 #endif
 #ifndef AMG_DT_MINBLOCKS
 #define AMG_DT_MINBLOCKS 8
@@ -764,7 +832,9 @@ __global__ void __launch_bounds__(DT_THREADS, AMG_DT_MINBLOCKS) k_decode_tiles(c
   __shared__ __align__(128) u8 stage[DT_STAGE];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ u32 sLo, sHi; __shared__ u64 sWarp[2][DT_THREADS / 32]; __shared__ u64 sBase[2];
+  __shared__ u32 sSlots[NCOLS][DT_THREADS]; __shared__ signed char sLut[128];   // ColSlots<SmemSrc>
   const int tid = threadIdx.x, lane = tid & 31;
+  for (int k = tid; k < 128; k += DT_THREADS) sLut[k] = (signed char)col_index_of((u32)k);
   if (tid == 0) {
     sLo = 0xffffffffu; sHi = 0;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&bar)));
@@ -792,7 +862,7 @@ __global__ void __launch_bounds__(DT_THREADS, AMG_DT_MINBLOCKS) k_decode_tiles(c
     u32 ok = 0;
     while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_addr(&bar)) : "memory");
   }
-  const SmemSrc ssrc{smem_addr(stage) - lo16};
+  const SmemSrc ssrc{smem_addr(stage) - lo16, smem_addr(sLut), smem_addr(&sSlots[0][tid])};
   // DEFLATEd changes (chunk type 2, columnar.js:742) are inflated later in the call: decoded by k_decode_direct then
   const bool deflated = live && len > 8 && ssrc.ld(off + 8) == 2 && ssrc.ld(off) == 0x85;
   const bool defer = (c < a.B && !inWindow) || deflated;
