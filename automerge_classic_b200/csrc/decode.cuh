@@ -131,6 +131,17 @@ template <class S> struct ByteReaderT {
     err = KE_TRUNCATED; return 0;
   }
   HD void skip(u64 n) { if ((u64)pos + n > end) { err = KE_SUBARRAY; pos = end; } else pos += (u32)n; }   // readRawBytes: encoding.js:494-500
+  // the same number, clamped to 32 bits: for lengths and counts, where anything that large is an error a few lines later
+  HD u32 ulebc() {
+    if (pos + 3 < end) {
+      const u32 b0 = src.ld(pos);
+      if (!(b0 & 0x80)) { pos++; return b0; }
+      const u32 b1 = src.ld(pos + 1); u32 v = (b0 & 0x7f) | ((b1 & 0x7f) << 7);
+      if (!(b1 & 0x80)) { pos += 2; return v; }
+    }
+    const u64 v = uleb(); return v > 0xffffffffULL ? 0xffffffffu : (u32)v;
+  }
+  HD void skip32(u32 n) { if (pos > end || n > end - pos) { err = KE_SUBARRAY; pos = end; } else pos += n; }
 };
 struct ByteReader : ByteReaderT<PtrSrc> {
   const u8* base;
@@ -518,9 +529,6 @@ struct alignas(16) ChangeHot {
 
 // One column that holds exactly one value: either the literal record [-1, v] or the null run [0, 1] (boolean: one run).
 // Returns false for anything else (the general decoder then handles - and validates - the column).
-struct SingleVals {   // the row of a single-op change, in registers until its row index is known
-  u32 objActor, objCtr, keyActor, keyCtr, keyStrOff, keyStrLen, insert, action, valLen, valOff, predNum, predActor, predCtr;
-};
 template <class S> HD bool single_value(const S& src, int ix, u32 pos, u32 l, u32& v, bool& isNull, u32& used) {
   const u32 p0 = l > 0 ? src.ld(pos) : 0xffu, p1 = l > 1 ? src.ld(pos + 1) : 0xffu;
   if (ix == CX_INSERT) {
@@ -536,8 +544,10 @@ template <class S> HD bool single_value(const S& src, int ix, u32 pos, u32 l, u3
   // document need three and four bytes)
   if (l > 6) return false;
   u64 val = p1 & 0x7fu; u32 last = p1; u32 nb = 1;
+  if (l > 2) {   // more than one value byte
 #pragma unroll
-  for (u32 k = 1; k < 5; k++) if ((last & 0x80u) && nb < l - 1) { last = src.ld(pos + 1 + k); val |= (u64)(last & 0x7fu) << (7 * k); nb = k + 1; }
+    for (u32 k = 1; k < 5; k++) if ((last & 0x80u) && nb < l - 1) { last = src.ld(pos + 1 + k); val |= (u64)(last & 0x7fu) << (7 * k); nb = k + 1; }
+  }
   if ((last & 0x80u) || nb != l - 1) return false;
   used = l;
   if (ix == CX_KEY_CTR || ix == CX_PRED_CTR) {   // signed (delta from 0): negative values go to the general decoder, which reports them
@@ -569,16 +579,18 @@ template <> struct ColSlots<SmemSrc> {
 };
 #endif
 
-
+// Result of the first walk over a change: header fields, counts, and - when every column holds exactly one value - the row,
+// which stays in the thread's ColSlots (slot ix valid iff bit ix of `seen`) until its row index is known.
 struct ParsedChange {
   ChangeHot h; u32 nDeps, nOther, nOps, nPreds; u32 err;   // err: KErr of the header / directory / count (raised for every change of a batch)
-  bool single; bool unknownCols /* a column id this version does not know: the host carries its values (unknowncols.hpp) */; SingleVals sv;
+  bool single; bool unknownCols /* a column id this version does not know: the host carries its values (unknowncols.hpp) */;
+  u32 seen, keyStrPos, valOff;
 };
 // columnar.js:688-708 (container), :635-652 decodeChangeHeader, :609-624 decodeColumnInfo; op count = values of the action
 // column, pred count = sum of the predNum column (new.js:686-700 reads ops until the action column is exhausted)
-template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedChange& o) {
+template <class S> HD void parse_change(const S& src, ColSlots<S>& slots, u32 off, u32 len, ParsedChange& o) {
   o.h.off = off; o.h.len = len; o.h.depsOff = o.h.actorOff = o.h.actorLen = o.h.otherOff = o.h.dirOff = o.h.dataOff = 0; o.h.startOp = 0; o.h.seq = 0;
-  o.nDeps = 0; o.nOther = 0; o.nOps = 0; o.nPreds = 0; o.err = 0; o.single = false; o.unknownCols = false;
+  o.nDeps = 0; o.nOther = 0; o.nOps = 0; o.nPreds = 0; o.err = 0; o.single = false; o.unknownCols = false; o.seen = 0; o.keyStrPos = 0; o.valOff = 0;
   const u32 end = off + len;
   ByteReaderT<S> r(src, off + 8, end);
   const u32 chunkType = r.done() ? 0xffu : src.ld(r.pos); r.pos++;
@@ -587,30 +599,28 @@ template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedCh
   if ((u64)r.pos + chunkLen > (u64)end) { o.err = KE_SUBARRAY; return; }
   if ((u64)r.pos + chunkLen != (u64)end) { o.err = KE_TRAILING; return; }
   if (chunkType != 1) { o.err = KE_CHUNK_TYPE; return; }
-  const u64 nDeps = r.uleb(); const u32 depsOff = r.pos; r.skip(nDeps * 32);
-  const u64 actorLen = r.uleb(); const u32 actorOff = r.pos; r.skip(actorLen);
+  // lengths and counts in 32-bit arithmetic (clamped: anything that does not fit is longer than the change)
+  const u32 nDeps = r.ulebc(); const u32 depsOff = r.pos; if (nDeps > 0x07ffffffu) { r.err = KE_SUBARRAY; r.pos = end; } else r.skip32(nDeps * 32);
+  const u32 actorLen = r.ulebc(); const u32 actorOff = r.pos; r.skip32(actorLen);
   const u64 seq = r.uleb(), startOp = r.uleb(); (void)r.sleb();
-  const u64 msgLen = r.uleb(); r.skip(msgLen);
-  const u64 nOther = r.uleb(); const u32 otherOff = r.pos;
-  for (u64 i = 0; i < nOther && !r.err; i++) { const u64 l = r.uleb(); r.skip(l); }
-  const u64 nCols = r.uleb();
+  const u32 msgLen = r.ulebc(); r.skip32(msgLen);
+  const u32 nOther = r.ulebc(); const u32 otherOff = r.pos;
+  for (u32 i = 0; i < nOther && !r.err; i++) { const u32 l = r.ulebc(); r.skip32(l); }
+  const u32 nCols = r.ulebc();
   if (r.err) { o.err = r.err; return; }
   // Column directory and - for single-op changes, the shape of editing traces - the row itself in ONE walk. The data of
-  // column k starts at (end of the directory) + (lengths of the columns before it); the end of the directory is guessed
-  // as 2 bytes per entry (ids and lengths below 128) and the walk is repeated with the real value if the guess was wrong.
-  // Checks in the reference's order: column ids ascending over the whole directory (decodeColumnInfo), then per column
-  // "no deflated columns" and "bytes present" (decodeChangeColumns).
-  const u32 dirPos = r.pos; u32 dataPos = nCols < len ? dirPos + 2 * (u32)nCols : end;
-  u32 actOff = 0, actLen = 0, pnOff = 0, pnLen = 0; bool haveAct = false, single = false; SingleVals sv; u32 dirErr = 0;
+  // column k starts at (end of the directory) + (lengths of the columns before it). Checks in the reference's order: column
+  // ids ascending over the whole directory (decodeColumnInfo), then per column "no deflated columns" and "bytes present"
+  // (decodeChangeColumns).
+  const u32 dirPos = r.pos; u32 dataPos = nCols < len ? dirPos + 2 * nCols : end;
+  u32 actOff = 0, actLen = 0, pnOff = 0, pnLen = 0, seen = 0, rawLen = 0, keyStrPos = 0, valOff = 0, dirErr = 0; bool haveAct = false, single = false;
   // Fast walk: every id and length of the directory is a single byte (ids below 128, columns shorter than 128 bytes: what
-  // small changes look like). Same checks and results as the general walk below, in 32-bit arithmetic and without the
-  // per-column switch (ColSlots); anything else falls through to the general walk.
+  // small changes look like). Same checks and results as the general walk below, in 32-bit arithmetic; anything else
+  // falls through to the general walk.
   bool fastWalk = false;
-  if (nCols <= 32 && (u64)dirPos + 2 * nCols <= (u64)end) {
-    ColSlots<S> slots(src);
-    const u32 nc = (u32)nCols; u32 total = 0, colErr = 0, lastId = 0xffffffffu, seen = 0, rawLen = 0, keyStrPos = 0; bool orderBad = false, afterValLen = false; fastWalk = true;
-    single = true; haveAct = false; actLen = pnLen = 0; sv.valOff = 0;
-    for (u32 i = 0; i < nc; i++) {
+  if (nCols <= 32 && dirPos + 2 * nCols <= end) {
+    u32 total = 0, colErr = 0, lastId = 0xffffffffu; bool orderBad = false, afterValLen = false; fastWalk = true; single = true;
+    for (u32 i = 0; i < nCols; i++) {
       const u32 id = src.ld(dirPos + 2 * i), l = src.ld(dirPos + 2 * i + 1);
       if ((id | l) & 0x80u) { fastWalk = false; break; }
       if (lastId != 0xffffffffu && (id & ~8u) <= (lastId & ~8u)) orderBad = true;
@@ -621,7 +631,7 @@ template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedCh
       if (ix < 0) o.unknownCols = true;
       else {
         if (ix == CX_ACTION) { actOff = total; actLen = l; haveAct = true; } else if (ix == CX_PRED_NUM) { pnOff = total; pnLen = l; }
-        if (ix == CX_VAL_RAW) { if (afterValLen) { sv.valOff = pos; rawLen = l; } }
+        if (ix == CX_VAL_RAW) { if (afterValLen) { valOff = pos; rawLen = l; } }
         else if (single && !colErr && ix != CX_CHLD_ACTOR && ix != CX_CHLD_CTR) {
           u32 v = 0, used = 0; bool isNull = false;
           if (!single_value(src, ix, pos, l, v, isNull, used)) single = false;
@@ -631,81 +641,70 @@ template <class S> HD void parse_change(const S& src, u32 off, u32 len, ParsedCh
       afterValLen = ix == CX_VAL_LEN;
       total += l;
     }
-    if (fastWalk) {
-      if (orderBad) dirErr = KE_COL_ORDER; else if (colErr) dirErr = colErr;
-      auto val = [&](int ix) -> u32 { return (seen >> ix) & 1u ? slots.get(ix) : NULL32; };
-      sv.objActor = val(CX_OBJ_ACTOR); sv.objCtr = val(CX_OBJ_CTR); sv.keyActor = val(CX_KEY_ACTOR); sv.keyCtr = val(CX_KEY_CTR); sv.action = val(CX_ACTION);
-      sv.valLen = val(CX_VAL_LEN); sv.keyStrLen = val(CX_KEY_STR); sv.keyStrOff = sv.keyStrLen == NULL32 ? 0 : keyStrPos;
-      sv.insert = (seen >> CX_INSERT) & 1u ? slots.get(CX_INSERT) : 0u;
-      { const u32 pn = val(CX_PRED_NUM); sv.predNum = pn == NULL32 ? 0 : pn; }
-      sv.predActor = val(CX_PRED_ACTOR); sv.predCtr = val(CX_PRED_CTR);
-      if (sv.predNum > 1) single = false;
-      if ((sv.valLen == NULL32 ? 0u : (sv.valLen >> 4)) > rawLen) single = false;                           // the general decoder reports it
-      if (sv.predNum == 0 && (seen & ((1u << CX_PRED_ACTOR) | (1u << CX_PRED_CTR)))) single = false;        // pred values without a pred
-      if (!haveAct) single = false;
-    }
+    if (fastWalk) { if (orderBad) dirErr = KE_COL_ORDER; else if (colErr) dirErr = colErr; }
   }
-  if (!fastWalk) for (int attempt = 0; attempt < 2; attempt++) {
-    ByteReaderT<S> d(src, dirPos, end); long long lastId = -1; u64 total = 0; u32 colErr = 0; bool orderBad = false;
-    single = true; haveAct = false; actLen = pnLen = 0;
-    sv.objActor = sv.objCtr = sv.keyActor = sv.keyCtr = sv.action = sv.valLen = sv.keyStrLen = NULL32; sv.keyStrOff = 0; sv.insert = 0; sv.valOff = 0; sv.predNum = 0; sv.predActor = sv.predCtr = NULL32;
-    bool afterValLen = false, sawPred = false; u32 valBytes = 0, rawLen = 0;
-    for (u64 i = 0; i < nCols; i++) {
-      const u64 id64 = d.uleb(), l64 = d.uleb();
-      if (d.err) break;
-      if (lastId >= 0 && ((u32)id64 & ~8u) <= ((u32)lastId & ~8u)) orderBad = true;
-      lastId = (long long)id64;
-      if (!colErr) { if (id64 & 8) colErr = KE_COL_DEFLATE; else if ((u64)dataPos + total + l64 > (u64)end) colErr = KE_SUBARRAY; }
-      const u32 id = id64 > 0xffffffffULL ? 0xffffffffu : (u32)id64, l = (u32)l64, pos = dataPos + (u32)total;
-      if (id == 0x42) { actOff = (u32)total; actLen = l; haveAct = true; } else if (id == 0x70) { pnOff = (u32)total; pnLen = l; }
-      if (afterValLen) { afterValLen = false; if (id == 0x57) { sv.valOff = pos; rawLen = l; } }
-      if (col_index_of(id) < 0) o.unknownCols = true;
-      if (single && !colErr) {
+  if (!fastWalk) {   // general walk: ids / lengths of any size; the end of the directory is guessed (2 bytes per entry) and the walk repeated once with the real one
+    o.unknownCols = false;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      ByteReaderT<S> d(src, dirPos, end); long long lastId = -1; u64 total = 0; u32 colErr = 0; bool orderBad = false, afterValLen = false;
+      single = true; haveAct = false; actLen = pnLen = 0; seen = 0; rawLen = 0; valOff = 0; keyStrPos = 0;
+      for (u32 i = 0; i < nCols; i++) {
+        const u64 id64 = d.uleb(), l64 = d.uleb();
+        if (d.err) break;
+        if (lastId >= 0 && ((u32)id64 & ~8u) <= ((u32)lastId & ~8u)) orderBad = true;
+        lastId = (long long)id64;
+        if (!colErr) { if (id64 & 8) colErr = KE_COL_DEFLATE; else if ((u64)dataPos + total + l64 > (u64)end) colErr = KE_SUBARRAY; }
+        const u32 id = id64 > 0xffffffffULL ? 0xffffffffu : (u32)id64, l = (u32)l64, pos = dataPos + (u32)total;
         const int ix = col_index_of(id);
-        if (ix >= 0 && ix != CX_VAL_RAW && ix != CX_CHLD_ACTOR && ix != CX_CHLD_CTR) {
-          u32 v = 0, used = 0; bool isNull = false;
-          if (!single_value(src, ix, pos, l, v, isNull, used)) single = false;
-          else switch (ix) {
-            case CX_OBJ_ACTOR: sv.objActor = isNull ? NULL32 : v; break; case CX_OBJ_CTR: sv.objCtr = isNull ? NULL32 : v; break;
-            case CX_KEY_ACTOR: sv.keyActor = isNull ? NULL32 : v; break; case CX_KEY_CTR: sv.keyCtr = isNull ? NULL32 : v; break;
-            case CX_KEY_STR: sv.keyStrOff = isNull ? 0 : pos + 2; sv.keyStrLen = isNull ? NULL32 : v; break;
-            case CX_INSERT: sv.insert = v; break; case CX_ACTION: sv.action = isNull ? NULL32 : v; break;
-            case CX_VAL_LEN: sv.valLen = isNull ? NULL32 : v; valBytes = isNull ? 0 : (v >> 4); afterValLen = true; break;
-            case CX_PRED_NUM: sv.predNum = isNull ? 0 : v; if (sv.predNum > 1) single = false; break;
-            case CX_PRED_ACTOR: sv.predActor = isNull ? NULL32 : v; sawPred = true; break;
-            case CX_PRED_CTR: sv.predCtr = isNull ? NULL32 : v; sawPred = true; break;
-            default: break;
+        if (ix < 0) o.unknownCols = true;
+        else {
+          if (ix == CX_ACTION) { actOff = (u32)total; actLen = l; haveAct = true; } else if (ix == CX_PRED_NUM) { pnOff = (u32)total; pnLen = l; }
+          if (ix == CX_VAL_RAW) { if (afterValLen) { valOff = pos; rawLen = l; } }
+          else if (single && !colErr && ix != CX_CHLD_ACTOR && ix != CX_CHLD_CTR) {
+            u32 v = 0, used = 0; bool isNull = false;
+            if (!single_value(src, ix, pos, l, v, isNull, used)) single = false;
+            else { slots.put(ix, isNull ? NULL32 : v); seen |= 1u << ix; if (ix == CX_KEY_STR) keyStrPos = pos + 2; }
           }
         }
+        afterValLen = ix == CX_VAL_LEN;
+        total += l64;
       }
-      total += l64;
+      if (d.err) { dirErr = d.err; break; }
+      if (d.pos != dataPos) { dataPos = d.pos; if (attempt == 0) continue; }   // directory longer than guessed: once more, with its real end
+      if (orderBad) dirErr = KE_COL_ORDER; else if (colErr) dirErr = colErr;
+      break;
     }
-    if (d.err) { dirErr = d.err; break; }
-    if (d.pos != dataPos) { dataPos = d.pos; if (attempt == 0) continue; }   // directory longer than guessed: once more, with its real end
-    if (orderBad) dirErr = KE_COL_ORDER; else if (colErr) dirErr = colErr;
-    if (valBytes > rawLen) single = false;                 // the general decoder reports it
-    if (sv.predNum == 0 && sawPred) single = false;        // pred values without a pred: the general decoder skips them
-    if (!haveAct) single = false;
-    break;
   }
   if (dirErr) { o.err = dirErr; return; }
+  u32 predNum = 0;
+  if (single) {
+    const u32 pn = (seen >> CX_PRED_NUM) & 1u ? slots.get(CX_PRED_NUM) : NULL32; predNum = pn == NULL32 ? 0 : pn;
+    const u32 vl = (seen >> CX_VAL_LEN) & 1u ? slots.get(CX_VAL_LEN) : NULL32;
+    if (predNum > 1) single = false;
+    if ((vl == NULL32 ? 0u : (vl >> 4)) > rawLen) single = false;                                       // the general decoder reports it
+    if (predNum == 0 && (seen & ((1u << CX_PRED_ACTOR) | (1u << CX_PRED_CTR)))) single = false;    // pred values without a pred: the general decoder skips them
+    if (!haveAct) single = false;
+  }
   u32 kerr = 0; u32 nOps = 0; u64 nPreds = 0;
-  if (single) { nOps = 1; nPreds = sv.predNum; }
+  if (single) { nOps = 1; nPreds = predNum; }
   else {
     nOps = rle_count_values_t(src, dataPos + actOff, dataPos + actOff + actLen, &kerr);
     if (!kerr) nPreds = rle_sum_values_t(src, dataPos + pnOff, dataPos + pnOff + pnLen, nOps, &kerr);
   }
   if (kerr) { o.err = kerr; return; }
   if (nPreds > 0x7fffffffULL || nOps > 0x7fffffffu) { o.err = KE_TOO_LARGE; return; }
-  o.h.depsOff = depsOff; o.h.actorOff = actorOff; o.h.actorLen = (u32)actorLen; o.h.otherOff = otherOff; o.h.dirOff = dirPos; o.h.dataOff = dataPos;
+  o.h.depsOff = depsOff; o.h.actorOff = actorOff; o.h.actorLen = actorLen; o.h.otherOff = otherOff; o.h.dirOff = dirPos; o.h.dataOff = dataPos;
   o.h.startOp = startOp; o.h.seq = seq;
-  o.nDeps = (u32)nDeps; o.nOther = (u32)nOther; o.nOps = nOps; o.nPreds = (u32)nPreds; o.single = single; o.sv = sv;
+  o.nDeps = nDeps; o.nOther = nOther; o.nOps = nOps; o.nPreds = (u32)nPreds; o.single = single; o.seen = seen; o.keyStrPos = keyStrPos; o.valOff = valOff;
 }
-HD void store_single(const SingleVals& sv, u32 base, u32 pb, const RawRows& rows) {
-  rows.objActor[base] = sv.objActor; rows.objCtr[base] = sv.objCtr; rows.keyActor[base] = sv.keyActor; rows.keyCtr[base] = sv.keyCtr;
-  rows.keyStrOff[base] = sv.keyStrOff; rows.keyStrLen[base] = sv.keyStrLen; rows.insert[base] = sv.insert; rows.action[base] = sv.action;
-  rows.valLen[base] = sv.valLen; rows.valOff[base] = sv.valOff; rows.predNum[base] = sv.predNum; rows.predOff[base] = pb;
-  if (sv.predNum) { rows.predActor[pb] = sv.predActor; rows.predCtr[pb] = sv.predCtr; }
+// the row of a single-op change: from the thread's slots to the raw row tables
+template <class S> HD void store_single(const ColSlots<S>& slots, const ParsedChange& pc, u32 base, u32 pb, const RawRows& rows) {
+  auto val = [&](int ix) -> u32 { return (pc.seen >> ix) & 1u ? slots.get(ix) : NULL32; };
+  rows.objActor[base] = val(CX_OBJ_ACTOR); rows.objCtr[base] = val(CX_OBJ_CTR); rows.keyActor[base] = val(CX_KEY_ACTOR); rows.keyCtr[base] = val(CX_KEY_CTR);
+  const u32 ksl = val(CX_KEY_STR); rows.keyStrLen[base] = ksl; rows.keyStrOff[base] = ksl == NULL32 ? 0 : pc.keyStrPos;
+  rows.insert[base] = (pc.seen >> CX_INSERT) & 1u ? slots.get(CX_INSERT) : 0u; rows.action[base] = val(CX_ACTION);
+  rows.valLen[base] = val(CX_VAL_LEN); rows.valOff[base] = pc.valOff; rows.predNum[base] = pc.nPreds; rows.predOff[base] = pb;
+  if (pc.nPreds) { rows.predActor[pb] = val(CX_PRED_ACTOR); rows.predCtr[pb] = val(CX_PRED_CTR); }
 }
 // general expansion of a small change (2 .. SMALL_CHANGE_OPS ops, or one op in a non-canonical encoding): walks the
 // directory again and expands every column into rows [base, base + nOps) / preds [pb, pb + nPreds). Returns a KErr.
@@ -739,7 +738,7 @@ struct DecodeTilesArgs {
   u32* directList /* [B] changes the staged kernel could not take (outside their tile's staged window) */; u32* directCount;
 };
 // what one thread does with its change once the row range is known
-template <class S> HD void finish_change(const DecodeTilesArgs& a, const S& src, u32 c, const ParsedChange& pc, u32 base, u32 pb) {
+template <class S> HD void finish_change(const DecodeTilesArgs& a, const S& src, const ColSlots<S>& slots, u32 c, const ParsedChange& pc, u32 base, u32 pb) {
   a.hot[c] = pc.h; a.nOps[c] = pc.nOps; a.nPreds[c] = pc.nPreds; a.nDeps[c] = pc.nDeps; a.nActors[c] = 1 + pc.nOther;
   a.rawBase[c] = base; a.rawPredBase[c] = pb;
   u32 kerr = 0;
@@ -747,7 +746,7 @@ template <class S> HD void finish_change(const DecodeTilesArgs& a, const S& src,
   else if (pc.nOps > SMALL_CHANGE_OPS) atomic_or(&a.totals[3], 1u);   // expanded by DecodeColumnKernel once the gate has decided
   else if (pc.nOps > 0) {
     if ((u64)base + pc.nOps > a.rowCap || (u64)pb + pc.nPreds > a.predCap) a.totals[2] = 1;
-    else if (pc.single) store_single(pc.sv, base, pb, a.rows);
+    else if (pc.single) store_single(slots, pc, base, pb, a.rows);
     else kerr = expand_change(src, pc.h, pc.nOps, pc.nPreds, base, pb, a.rows);
   }
   if (!pc.err && pc.unknownCols) atomic_or(&a.totals[3], 2u);
@@ -764,9 +763,9 @@ inline void decode_tiles_range(Ctx& c, DecodeTilesArgs a, u32 first, u32 end) {
   for (u32 t = numTiles; t-- > 0;) for (u32 i = first + t * T; i < end && i < first + (t + 1) * T; i++) {
     const u8* p = a.arena + a.chOff[i];
     if (a.chLen[i] > 8 && p[8] == 2 && p[0] == 0x85) { a.directList[(*a.directCount)++] = i; continue; }
-    ParsedChange pc; parse_change(PtrSrc{a.arena}, a.chOff[i], a.chLen[i], pc);
+    ColSlots<PtrSrc> slots(PtrSrc{a.arena}); ParsedChange pc; parse_change(PtrSrc{a.arena}, slots, a.chOff[i], a.chLen[i], pc);
     if (getenv("AMG_EMU_DECODE_STATS")) { static size_t tot = 0, nonSingle = 0, shown = 0; tot++; if (!pc.single) { nonSingle++; if (shown < 6 && pc.nOps == 1) { shown++; fprintf(stderr, "non-single 1-op change %u:", i); for (u32 k = pc.h.dirOff; k < a.chOff[i] + a.chLen[i]; k++) fprintf(stderr, " %02x", a.arena[k]); fprintf(stderr, "\n"); } } if (tot % 100000 == 0) fprintf(stderr, "decode stats: %zu changes, %zu not single\n", tot, nonSingle); }
-    finish_change(a, PtrSrc{a.arena}, i, pc, (u32)std::min<u64>(a.cursor[0], 0x7fffffffu), (u32)std::min<u64>(a.cursor[1], 0x7fffffffu));
+    finish_change(a, PtrSrc{a.arena}, slots, i, pc, (u32)std::min<u64>(a.cursor[0], 0x7fffffffu), (u32)std::min<u64>(a.cursor[1], 0x7fffffffu));
     a.cursor[0] += pc.nOps; a.cursor[1] += pc.nPreds;
   }
   c.launches++;
@@ -774,8 +773,8 @@ inline void decode_tiles_range(Ctx& c, DecodeTilesArgs a, u32 first, u32 end) {
 inline void decode_tiles_finish(Ctx& c, const DecodeTilesArgs& a, size_t) {
   for (u32 k = 0; k < *a.directCount; k++) {
     const u32 i = a.directList[k];
-    ParsedChange pc; parse_change(PtrSrc{a.arena}, a.chOff[i], a.chLen[i], pc);
-    finish_change(a, PtrSrc{a.arena}, i, pc, (u32)std::min<u64>(a.cursor[0], 0x7fffffffu), (u32)std::min<u64>(a.cursor[1], 0x7fffffffu));
+    ColSlots<PtrSrc> slots(PtrSrc{a.arena}); ParsedChange pc; parse_change(PtrSrc{a.arena}, slots, a.chOff[i], a.chLen[i], pc);
+    finish_change(a, PtrSrc{a.arena}, slots, i, pc, (u32)std::min<u64>(a.cursor[0], 0x7fffffffu), (u32)std::min<u64>(a.cursor[1], 0x7fffffffu));
     a.cursor[0] += pc.nOps; a.cursor[1] += pc.nPreds;
   }
   const u64 ops = a.cursor[0], preds = a.cursor[1];
@@ -808,12 +807,18 @@ DEV u32 sat31(u64 v) { return v > 0x7fffffffULL ? 0x7fffffffu : (u32)v; }
 // steps 2-4 for the change of this thread; S = where its bytes are read from
 template <class S> DEV void decode_tile_body(const DecodeTilesArgs& a, const S& src, u32 c, bool live, u32 off, u32 len, u64 (*sWarp)[DT_THREADS / 32], u64* sBase) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  ParsedChange pc; pc.nOps = pc.nPreds = 0;
-  if (live) parse_change(src, off, len, pc);
-  // (ops, preds) of the tile: exclusive scan inside the CTA, 64-bit each (a run-length encoded change can hold 2^31 ops)
+  ColSlots<S> slots(src); ParsedChange pc; pc.nOps = pc.nPreds = 0;
+  if (live) parse_change(src, slots, off, len, pc);
+  // (ops, preds) of the tile: exclusive scan inside the CTA, 64-bit each (a run-length encoded change can hold 2^31 ops).
+  // A warp of single-op changes (the common case) gets its prefixes from two ballots instead of ten shuffles.
   u64 vo = live ? pc.nOps : 0, vp = live ? pc.nPreds : 0; u64 io = vo, ip = vp;
+  if (__all_sync(0xffffffffu, vo <= 1 && vp <= 1)) {
+    const unsigned le = 0xffffffffu >> (31 - lane);
+    io = __popc(__ballot_sync(0xffffffffu, vo == 1) & le); ip = __popc(__ballot_sync(0xffffffffu, vp == 1) & le);
+  } else {
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { const u64 to = __shfl_up_sync(0xffffffffu, io, d), tp = __shfl_up_sync(0xffffffffu, ip, d); if (lane >= d) { io += to; ip += tp; } }
+    for (int d = 1; d < 32; d <<= 1) { const u64 to = __shfl_up_sync(0xffffffffu, io, d), tp = __shfl_up_sync(0xffffffffu, ip, d); if (lane >= d) { io += to; ip += tp; } }
+  }
   if (lane == 31) { sWarp[0][warp] = io; sWarp[1][warp] = ip; }
   __syncthreads();
   u64 wo = 0, wp = 0, to = 0, tp = 0;
@@ -826,7 +831,7 @@ template <class S> DEV void decode_tile_body(const DecodeTilesArgs& a, const S& 
     sBase[0] = atomicAdd(&a.cursor[0], (unsigned long long)to); sBase[1] = tp ? atomicAdd(&a.cursor[1], (unsigned long long)tp) : 0;
   }
   __syncthreads();
-  if (live) finish_change(a, src, c, pc, sat31(sBase[0] + wo + io - vo), sat31(sBase[1] + wp + ip - vp));
+  if (live) finish_change(a, src, slots, c, pc, sat31(sBase[0] + wo + io - vo), sat31(sBase[1] + wp + ip - vp));
 }
 __global__ void __launch_bounds__(DT_THREADS, AMG_DT_MINBLOCKS) k_decode_tiles(const DecodeTilesArgs a) {
   __shared__ __align__(128) u8 stage[DT_STAGE];
