@@ -279,7 +279,7 @@ class Engine {
   void reset();
   void loadDocument(const u8* buf, size_t len);
   size_t historyRebuilt = 0;   // changes [0, historyRebuilt) were rebuilt by computeHashGraph (getChanges DEFLATEs the large ones like encodeChange does)
-  DBuf<u64> excl64;
+  DBuf<u64> excl64, offsDev;
   bool headIndexesUnknown = false;   // Backend.load of a document with several heads and no head indexes, until computeHashGraph has matched them
   bool haveHashGraph = true;   // false after Backend.load: change history (hashes, bytes) is not reconstructed (new.js:1887-1912)
   void benchDecode(int iters, float* msSha, float* msParse, float* msDec, u64* algoBytes);

@@ -9,6 +9,11 @@
 
 namespace amg {
 
+#ifdef AMG_EMU
+#define CUDA_CHECK_EMU(x) do {} while (0)
+#else
+#define CUDA_CHECK_EMU(x) CUDA_CHECK(x)
+#endif
 static const size_t PATCH_HDR_WORDS = 20;
 // NVTX range per pipeline phase: next() closes the running range and opens the named one (nullptr: just closes)
 struct NvtxPhases {
@@ -212,17 +217,33 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   };
   if (copiesFirst) { size_t byte0 = 0, ch0 = 0; for (Piece& pc : pieces) { queueCopy(pc, byte0, ch0); byte0 = pc.byteEnd; ch0 = pc.changeEnd; } }
   dbgMark("stage:copies-queued");
-  if (blob && n > 0) {   // the table of a packed batch: filled by a few threads (1M entries), in the shadow of the copies
+  // The (offset, length) table of the changes. Packed batch whose offsets array is pinned or device memory: the array goes
+  // up by DMA and a kernel derives the table (the host's own copy is filled later, in the shadow of the device work).
+  // Otherwise the host fills a pinned table (a few threads for 1M entries) and uploads that.
+  auto fillPairs = [&]() {
+    if (!(blob && n > 0)) return;
     const size_t base = offsets[0]; const u32 shift = (u32)(arenaLen0 - base);
     auto fill = [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) { pairs[i].off = (u32)offsets[i] + shift; pairs[i].len = (u32)(offsets[i + 1] - offsets[i]); } };
     const unsigned nt = n < (1u << 16) ? 1u : std::min<unsigned>(4, std::max(1u, std::thread::hardware_concurrency()));
     if (nt == 1) fill(0, n);
     else { std::vector<std::thread> ts; const size_t per = (n + nt - 1) / nt; for (unsigned t = 0; t < nt; t++) { const size_t a = t * per, b = std::min(n, a + per); if (a < b) ts.emplace_back(fill, a, b); } for (auto& t : ts) t.join(); }
-  }
+  };
+  bool offsetsByDma = false;
+#ifndef AMG_EMU
+  if (blob && n >= 4096) { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, offsets) == cudaSuccess) offsetsByDma = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged; else cudaGetLastError(); }
+#endif
   for (size_t i = 0; i < Bq; i++) pairs[n + i] = queue[i];
   chPairs.ensure(ctx, B); chOff.ensure(ctx, B); chLen.ensure(ctx, B);
-  h2d(ctx, chPairs.p, pairs, B * sizeof(HostChange));
-  foreach(ctx, B, SplitPairsKernel{chPairs.p, chOff.p, chLen.p});
+  if (offsetsByDma) {
+    DBuf<u64>& offsD = offsDev; offsD.ensure(ctx, n + 2);
+    CUDA_CHECK_EMU(cudaMemcpyAsync(offsD.p, offsets, (n + 1) * 8, cudaMemcpyDefault, ctx.stream));
+    foreach(ctx, n, OffsetsToRangesKernel{offsD.p, (u32)(arenaLen0 - offsets[0]), chOff.p, chLen.p});
+    if (Bq > 0) { h2d(ctx, chPairs.p + n, pairs + n, Bq * sizeof(HostChange)); foreach(ctx, Bq, SplitPairsKernel{chPairs.p + n, chOff.p + n, chLen.p + n}); }
+  } else {
+    fillPairs();
+    h2d(ctx, chPairs.p, pairs, B * sizeof(HostChange));
+    foreach(ctx, B, SplitPairsKernel{chPairs.p, chOff.p, chLen.p});
+  }
   dev_memset(ctx, arena.p + cur, 0, 64);
   dev_memset(ctx, errWord.p, 0, 16); errSnapLaunches = ~0ull;
   hashes.ensure(ctx, (numApplied + B) * 32 + 64, numApplied * 32);
@@ -251,7 +272,8 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       byte0 = pc.byteEnd; ch0 = pc.changeEnd;
     }
   }
-  // the host's own list of the batch entries (bookkeeping at commit, queue hand-over): copied in the shadow of the device work
+  // the host's own list of the batch entries (bookkeeping at commit, queue hand-over): filled in the shadow of the device work
+  if (offsetsByDma) fillPairs();
   batch.assign(pairs, pairs + B);
   if (Bq > 0) { batchOriginal.assign(B, HostChange{0, 0}); for (size_t i = 0; i < Bq; i++) batchOriginal[n + i] = queueOriginal[i]; }
   dbgMark("stage:enqueued");

@@ -74,32 +74,52 @@ def read_peaks():
         return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
-class ClockSampler(threading.Thread):
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+class ClockSampler:
+    """One `nvidia-smi -lms 50` process for the length of the measurement (a fresh nvidia-smi per sample takes longer to
+    start than a timed region of ten 8 ms steps lasts)."""
 
-    def run(self):
+    def __init__(self, index):
         q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(',')])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        self.samples, self.marks = [], []
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '50'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.strip().split(',')]
+            if parts and parts[0].isdigit():
+                self.samples.append((time.perf_counter(), parts))
+
+    def start(self):
+        pass
+
+    def mark(self):
+        """start / end of a timed region"""
+        self.marks.append(time.perf_counter())
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)   # one more sample after the last timed step
+            self.proc.terminate()
+    stop_flag = property(lambda self: False, lambda self, v: self.stop() if v else None)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        lo, hi = (self.marks[0], self.marks[-1]) if len(self.marks) >= 2 else (0, float('inf'))
+        inside = [p for t, p in self.samples if lo - 0.11 <= t <= hi + 0.16] or [p for _, p in self.samples]
+        sm = sorted(int(p[0]) for p in inside)
         reasons = set()
-        for s in self.samples:
-            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], s[2:6]):
+        for p in inside:
+            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], p[2:6]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons), 'samples': len(sm)}
+        mx = [int(p[1]) for p in inside if len(p) > 1 and p[1].isdigit()]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons), 'samples': len(sm),
+                'how': 'nvidia-smi -lms 50 running from before the warm-up to after the last timed step; samples inside (or within 0.1 s of) the timed regions'}
 
 
 def run_reference(args, rank, world):
@@ -180,7 +200,8 @@ def measure(args, wl_name, rank, world, local, lib, torch, dist, full):
     pinned[:nbytes].copy_(torch.from_numpy(trace.blob))
     resident = pinned.to('cuda:%d' % local)
     offs = np.ascontiguousarray(trace.offsets)
-    offs_p = offs.ctypes.data_as(C.c_void_p)
+    offs_pinned = torch.from_numpy(offs.astype(np.int64)).pin_memory()   # the offsets array travels by DMA as well (pinned like the bytes)
+    offs_p = C.c_void_p(offs_pinned.data_ptr())
     doc = GpuBackendDoc(device=local)
     err = _ErrStruct()
     L.amg_reserve(doc.h, C.c_size_t(nbytes + (1 << 20)), C.byref(err))
@@ -209,14 +230,14 @@ def measure(args, wl_name, rank, world, local, lib, torch, dist, full):
             dev.append(sum(ph[0:12]) / 1e3)   # CUDA events on the engine's stream, first to last kernel of the call
         return wall, dev, ph, pb
 
+    sampler = ClockSampler(local)
     for _ in range(args.warmup):
         step(resident.data_ptr())
         step(pinned.data_ptr())
-    sampler = ClockSampler(local)
-    sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark()
     # value: K steps on the device-resident bytes (the call copies them device -> device into the document's arena: that
     # copy, SHA-256, decode, gate, op-set ordering, patch kernels and the patch copy-out are all inside the figure)
     _, dev_res, ph_res, _ = timed(resident.data_ptr(), args.steps)
@@ -226,9 +247,10 @@ def measure(args, wl_name, rank, world, local, lib, torch, dist, full):
     launches0 = doc.launches()
     wall, dev_e2e, last_ph, patch_bytes = timed(pinned.data_ptr(), args.steps)
     torch.cuda.synchronize()
+    sampler.mark()
     if world > 1:
         dist.barrier()
-    sampler.stop_flag = True
+    sampler.stop()
     launches = (doc.launches() - launches0) // max(args.steps, 1)
     t_wall, t_dev = sum(wall) / len(wall), sum(dev_res) / len(dev_res)
     if world > 1:   # a step ends when the slowest rank is done
@@ -236,7 +258,7 @@ def measure(args, wl_name, rank, world, local, lib, torch, dist, full):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_wall, t_dev = float(tt[0]), float(tt[1])
     res = {'trace': trace, 'nbytes': nbytes, 'desc': desc, 't_wall': t_wall, 't_dev': t_dev, 'wall_steps': wall, 'dev_steps': dev_res, 'last_ph': last_ph, 'ph_res': ph_res,
-           'patch_bytes': patch_bytes, 'launches': int(launches), 'call_ms': state['call_ms'], 'clocks': sampler.summary(), 'doc': doc, 'pinned': pinned, 'offs': offs}
+           'patch_bytes': patch_bytes, 'launches': int(launches), 'call_ms': state['call_ms'], 'clocks': sampler.summary(), 'doc': doc, 'pinned': pinned, 'offs': offs, 'offs_pinned': offs_pinned}
     if not full:
         del doc
     return res
