@@ -116,7 +116,7 @@ amg_backend* amg_clone(amg_backend* src, amg_error* err) {
     d2d(c, d.doc.valLen.p, s.doc.valLen.p, s.numRows * 4); d2d(c, d.doc.valOff.p, s.doc.valOff.p, s.numRows * 4); d2d(c, d.doc.time.p, s.doc.time.p, s.numRows * 4);
     d.numSucc = s.numSucc; d.succOff.ensure(c, s.numRows + 2); d2d(c, d.succOff.p, s.succOff.p, (s.numRows + 1) * 4); d.succ.ensure(c, s.numSucc + 1); d2d(c, d.succ.p, s.succ.p, s.numSucc * 8);
     d.actorIds = s.actorIds; d.actorRep = s.actorRep; d.clock = s.clock; d.heads = s.heads; d.headIdx = s.headIdx; d.changes = s.changes; d.deflatedOriginal = s.deflatedOriginal; d.loadedDoc = s.loadedDoc; d.numLoaded = s.numLoaded; for (int k = 0; k < 9; k++) d.loadedCols[k] = s.loadedCols[k];
-    d.queue = s.queue; d.queueOriginal = s.queueOriginal; d.maxOp = s.maxOp; d.haveHashGraph = s.haveHashGraph; d.historyRebuilt = s.historyRebuilt;
+    d.unknownCols = s.unknownCols; d.queue = s.queue; d.queueOriginal = s.queueOriginal; d.maxOp = s.maxOp; d.haveHashGraph = s.haveHashGraph; d.historyRebuilt = s.historyRebuilt;
     while (d.actorCap < 2 * (d.actorIds.size() + 16)) d.actorCap *= 2;
     d.actorSlots.ensure(c, d.actorCap); d.rebuildActorTable();
     sync(c);

@@ -91,7 +91,7 @@ inline void Engine::finishPatch(PatchOut& out) {
 
 // forgets the document but keeps every allocation (steady-state serving / benchmarking)
 inline void Engine::reset() {
-  sync(ctx); headIndexesUnknown = false;
+  sync(ctx); headIndexesUnknown = false; unknownCols.clear();
   arenaLen = 0; hostArena.len = 0; numApplied = 0; numRows = 0; numSucc = 0; dev_memset(ctx, succOff.p, 0, 4);
   actorIds.clear(); actorRep.clear(); clock.clear(); heads.clear(); headIdx.clear(); changes.clear(); changeHashes.clear(); deflatedOriginal.clear(); loadedDoc.clear(); numLoaded = 0; historyRebuilt = 0; haveHashGraph = true;
   queue.clear(); queueOriginal.clear(); maxOp = 0; rebuildActorTable();
@@ -272,12 +272,12 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       byte0 = pc.byteEnd; ch0 = pc.changeEnd;
     }
   }
+  dbgMark("stage:enqueued");
+  timer.mark(); hostMark();
   // the host's own list of the batch entries (bookkeeping at commit, queue hand-over): filled in the shadow of the device work
   if (offsetsByDma) fillPairs();
   batch.assign(pairs, pairs + B);
-  if (Bq > 0) { batchOriginal.assign(B, HostChange{0, 0}); for (size_t i = 0; i < Bq; i++) batchOriginal[n + i] = queueOriginal[i]; }
-  dbgMark("stage:enqueued");
-  timer.mark(); hostMark(); nvtx.next("inflate+decode-finish");
+  if (Bq > 0) { batchOriginal.assign(B, HostChange{0, 0}); for (size_t i = 0; i < Bq; i++) batchOriginal[n + i] = queueOriginal[i]; } nvtx.next("inflate+decode-finish");
   // ------------------------------------------------------------ 1. DEFLATEd changes
   {
     // Which changes of the batch are DEFLATEd (columnar.js:742)? Those are inflated on the device, behind the batch:
@@ -1048,6 +1048,26 @@ inline void Engine::collectUnknownColumns(size_t B, std::vector<std::pair<u64, U
   }
 }
 
+// save(): document columns of the unknown ids, rows in document order; a row without a value in a column contributes null
+// (a group cardinality of 0 for grouped columns), as the reference's decoders yield for columns a block never had
+// (new.js:1418-1420 makeDecoders over the widened column list).
+inline void Engine::appendUnknownDocColumns(std::vector<std::pair<u32, std::string>>& cols) {
+  const size_t N = numRows; std::vector<u64> ids(N); d2h(ctx, ids.data(), doc.id.p, N * 8); sync(ctx);
+  for (u32 id : unknownCols.colIds) {
+    std::vector<UnknownValue> vals; vals.reserve(N);
+    const bool grouped = (id & 7) != 0 && (unknownCols.colIds.count((id & ~15u)) != 0 || (id >> 4) == 7 || (id >> 4) == 8);   // a member of a group with a GROUP_CARD column: a row without values has cardinality 0
+    for (size_t i = 0; i < N; i++) {
+      auto it = unknownCols.byOp.find(ids[i]);
+      const std::vector<UnknownValue>* v = nullptr;
+      if (it != unknownCols.byOp.end()) { auto c = it->second.find(id); if (c != it->second.end()) v = &c->second; }
+      if (v) vals.insert(vals.end(), v->begin(), v->end());
+      else if ((id & 7) == 0) { UnknownValue z; z.isNull = false; z.num = 0; vals.push_back(z); }   // GROUP_CARD: `readValue() || 0` (new.js:581)
+      else if (!grouped && (id & 7) != 7) vals.push_back(UnknownValue());   // null (raw bytes: nothing)
+    }
+    cols.emplace_back(id, encode_unknown_column(id, vals));
+  }
+}
+
 // Columns of bulk changes (>= HUGE_CHANGE_OPS ops) through the parallel column decoders. largeList holds the large changes of
 // the batch (at most 8 here). hugeDone[k * NCOLS + col] = 1 tells DecodeColumnKernel that column `col` of large change k is done.
 inline u32 Engine::decodeHugeChanges(const RawRows& raw, size_t numLarge) {
@@ -1123,6 +1143,7 @@ inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* 
 // column bytes - and its hash. Kernels: history.cuh. Nothing persistent is touched until the heads check has passed.
 inline void Engine::computeHashGraph() {
   if (haveHashGraph) return;
+  if (!unknownCols.empty()) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: the change history of a loaded document that holds columns with unknown ids cannot be reconstructed");
   const size_t L = numLoaded, N = numRows, S = numSucc, A = actorIds.size();
   if (L == 0) { haveHashGraph = true; return; }
   if (L >= (1u << 29) || N + S >= (1u << 30)) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: document too large for history reconstruction");
@@ -1527,6 +1548,11 @@ inline void Engine::saveDocument(std::string& result) {
   std::vector<Packed> packed; std::vector<size_t> firstOp;
   auto pack = [&](const std::vector<Col>& cols) { for (auto& c : cols) if (c.len > 0) packed.push_back({c.id, std::string((const char*)raw.data() + c.off, c.len)}); };
   pack(changeCols); const size_t numChangeCols = packed.size(); pack(opCols);
+  if (!unknownCols.empty() && N > 0) {   // columns with ids this version does not know: host-encoded from the values kept per op (unknowncols.hpp)
+    std::vector<std::pair<u32, std::string>> extra; appendUnknownDocColumns(extra);
+    for (auto& e : extra) if (!e.second.empty()) packed.push_back({e.first, e.second});
+    std::stable_sort(packed.begin() + numChangeCols, packed.end(), [](const Packed& a, const Packed& b) { return (a.id & ~8u) < (b.id & ~8u); });
+  }
   {
     std::vector<std::thread> ts; std::vector<std::string> errs(packed.size());
     for (size_t k = 0; k < packed.size(); k++) if (packed[k].data.size() >= 256) ts.emplace_back([&, k] {
@@ -1743,6 +1769,22 @@ inline void Engine::loadDocument(const u8* buf, size_t len) {
   { const u32 s32 = (u32)S; h2d(ctx, succOff.p + N, &s32, 4); }
   u64 mx = 0; d2h(ctx, &mx, maxOpD.p, 8); sync(ctx); checkErr(actors);
   lmark("rows finalized");
+  {   // op columns with unknown ids: their values are kept per op (host; unknowncols.hpp) so that save() writes them again
+    bool anyUnknown = false; for (auto& c : opCols) if (!is_known_doc_column(c.id)) anyUnknown = true;
+    unknownCols.clear();
+    if (anyUnknown && N > 0) {
+      std::string all; std::vector<std::array<u32, 3>> cols;
+      for (auto& c : opCols) { cols.push_back({c.id, (u32)all.size(), (u32)c.data.size()}); all += c.data; }
+      std::vector<u64> ids(N); d2h(ctx, ids.data(), doc.id.p, N * 8); sync(ctx);
+      const u32 e = read_unknown_columns((const u8*)all.data(), cols, N, is_known_doc_column, [&](size_t i, UnknownRow& row) {
+        if (row.empty()) return;
+        for (auto& kv : row) unknownCols.colIds.insert(kv.first);
+        unknownCols.byOp[ids[i]] = row;
+      });
+      if (e == KE_UNSUPPORTED_OP) throw Error(AMG_ERR_RANGE, "unexpected VALUE_RAW column");
+      if (e) throwKernelError((u64)e, actors);
+    }
+  }
   // ---- change history placeholders: only the head hashes are known (new.js:1727-1739)
   hashes.ensure(ctx, numChanges * 32 + 64); dev_memset(ctx, hashes.p, 0, numChanges * 32 + 64);
   if (!headIdxUnknown) for (size_t i = 0; i < hs.size(); i++) { if (headsIndexes[i] >= numChanges) throw Error(AMG_ERR_RANGE, "head index out of range"); h2d(ctx, hashes.p + (size_t)headsIndexes[i] * 32, hs[i].data(), 32); }

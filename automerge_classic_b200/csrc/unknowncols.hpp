@@ -68,7 +68,9 @@ template <class Known, class Sink> inline u32 read_unknown_columns(const u8* bas
         if ((long long)r.id != valueColumn) return KE_UNSUPPORTED_OP;  // "unexpected VALUE_RAW column"
         e = r.readRaw(valueBytes, v); vals.push_back(v);
       } else if (r.type == 0) {                                        // GROUP_CARD
-        lastGroup = r.id >> 4; e = r.read(v); card = v.isNull ? 0 : (u64)v.num; vals.push_back(v);
+        lastGroup = r.id >> 4; e = r.read(v); card = v.isNull ? 0 : (u64)v.num;
+        if (v.isNull) { v.isNull = false; v.num = 0; }   // `readValue() || 0` (new.js:581): a missing cardinality is written back as 0
+        vals.push_back(v);
       } else if ((long long)(r.id >> 4) == lastGroup) {
         if (r.type == 6) { valueColumn = r.id + 1; valueBytes = 0; }
         for (u64 k = 0; k < card && !e; k++) { e = r.read(v); if (r.type == 6 && !v.isNull) valueBytes += (u64)v.num >> 4; vals.push_back(v); }

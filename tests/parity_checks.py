@@ -617,6 +617,44 @@ def check_duplicated_successor_pin(gpu_doc, oracle_mod):
         assert (o.save() == g.save()) == (not one_call)
 
 
+UNKNOWN_COLUMNS_CHANGE = bytes([   # test/new_backend_test.js:1858-1876: unknown column group 0xf0 / 0xf1 / 0xf3, action 17, datatype 14
+    0x85, 0x6f, 0x4a, 0x83, 0xad, 0xfb, 0x1a, 0x69, 1, 51, 0, 2, 0x12, 0x34, 1, 1, 0, 0, 0, 9,
+    0x15, 3, 0x34, 1, 0x42, 2, 0x56, 2, 0x57, 4, 0x70, 2, 0xf0, 1, 2, 0xf1, 1, 2, 0xf3, 1, 2,
+    0x7f, 1, 0x78, 1, 0x7f, 17, 0x7f, 0x4e, 1, 2, 3, 4, 0x7f, 0, 0x7f, 2, 2, 0, 2, 1])
+
+
+def check_unknown_columns(gpu_doc, oracle_mod):
+    """Columns with ids a future version would write are carried through apply, save and load (new.js:1406-1424; fixture
+    test/new_backend_test.js:1857-1905, whose expected document columns 240 / 241 / 243 the oracle reproduces): save() is
+    byte-identical to the oracle's - right after the change, after later changes without those columns (their rows hold
+    nulls there), after a change by another actor that sorts in front, and after load()."""
+    from automerge_classic_b200 import columnar
+    actor2, actor3 = '0001', 'ffee'
+    c1 = UNKNOWN_COLUMNS_CHANGE
+    h1 = oracle_mod.decode_change(c1)['hash']
+    c2, h2 = columnar.encode_change_raw({'actor': '1234', 'seq': 2, 'startOp': 2, 'time': 0, 'message': '', 'deps': [h1], 'ops': [
+        {'action': 'set', 'obj': '_root', 'key': 'a', 'value': 1, 'datatype': 'uint', 'pred': []}, {'action': 'set', 'obj': '_root', 'key': 'z', 'value': 'zz', 'pred': []}]}, False, 6)
+    c3, h3 = columnar.encode_change_raw({'actor': actor2, 'seq': 1, 'startOp': 5, 'time': 0, 'message': '', 'deps': [h2], 'ops': [
+        {'action': 'set', 'obj': '_root', 'key': 'b', 'value': 2, 'datatype': 'uint', 'pred': []}]}, False, 6)
+    orc, g = oracle_mod.OracleDoc(), gpu_doc()
+    for batch in ([c1], [c2], [c3]):
+        po, pg = orc.apply_changes(batch), g.apply_changes(batch)
+        d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+        assert d is None, d
+        so, sg = orc.save(), g.save()
+        assert sg == so, 'save() differs from the oracle with unknown columns:\n %s\n %s' % (sg.hex(), so.hex())
+        g2, o2 = gpu_doc(sg), oracle_mod.OracleDoc(so)
+        assert replay.deep_equal(replay.decode(g2.get_patch()), replay.decode(o2.get_patch())) is None
+        assert g2.save() == sg
+        # a loaded document keeps them through further changes too
+        c4, _ = columnar.encode_change_raw({'actor': actor3, 'seq': 1, 'startOp': 9, 'time': 0, 'message': '', 'deps': sorted(g2.heads()), 'ops': [
+            {'action': 'set', 'obj': '_root', 'key': 'm', 'value': 3, 'datatype': 'uint', 'pred': []}]}, False, 6)
+        o2.apply_changes([c4]); g2.apply_changes([c4])
+        assert g2.save() == o2.save(), 'save() after load + change differs with unknown columns'
+    one = gpu_doc(); one.apply_changes([c1, c2, c3])
+    assert one.save() == orc.save()
+
+
 def check_large_text(gpu_doc, oracle_mod, n):
     """C3 at 100k ops: full parity against the oracle (the oracle finishes this size in seconds)."""
     from automerge_classic_b200 import tracegen

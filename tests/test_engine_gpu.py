@@ -181,3 +181,7 @@ def test_value_validation(gpu_doc, oracle_mod):
 
 def test_duplicated_successor_pinned(gpu_doc, oracle_mod):
     parity_checks.check_duplicated_successor_pin(gpu_doc, oracle_mod)
+
+
+def test_unknown_columns(gpu_doc, oracle_mod):
+    parity_checks.check_unknown_columns(gpu_doc, oracle_mod)

@@ -196,3 +196,7 @@ def test_value_validation_emu(emu_doc, oracle_mod):
 
 def test_duplicated_successor_pinned_emu(emu_doc, oracle_mod):
     parity_checks.check_duplicated_successor_pin(emu_doc, oracle_mod)
+
+
+def test_unknown_columns_emu(emu_doc, oracle_mod):
+    parity_checks.check_unknown_columns(emu_doc, oracle_mod)

@@ -14,7 +14,8 @@ def short(n):
     m = re.search(r'(k_\w+)', n)
     return m.group(1) if m else n[:40]
 names = [short(n) for n, _ in rows]
-starts = [i for i, n in enumerate(names) if n == 'SplitPairsKernel']
+starts = [i for i, n in enumerate(names) if n in ('OffsetsToRangesKernel', 'SplitPairsKernel') and (i == 0 or names[i - 1] not in ('OffsetsToRangesKernel',))]
+starts = [i for k, i in enumerate(starts) if k == 0 or i - starts[k - 1] > 20]   # one per call
 a = starts[1] if len(starts) > 1 else starts[0]
 b = min(len(rows), a + (starts[1] - starts[0])) if len(starts) > 1 else len(rows)   # same number of launches as the call before it (what follows in bench.py is the decode re-run)
 seg = list(zip(names[a:b], [v for _, v in rows[a:b]]))
