@@ -274,10 +274,17 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   }
   dbgMark("stage:enqueued");
   timer.mark(); hostMark();
-  // the host's own list of the batch entries (bookkeeping at commit, queue hand-over): filled in the shadow of the device work
-  if (offsetsByDma) fillPairs();
-  batch.assign(pairs, pairs + B);
-  if (Bq > 0) { batchOriginal.assign(B, HostChange{0, 0}); for (size_t i = 0; i < Bq; i++) batchOriginal[n + i] = queueOriginal[i]; } nvtx.next("inflate+decode-finish");
+  // The host's own list of the batch entries (bookkeeping at commit, queue hand-over) is filled by a helper thread while
+  // this one keeps the device fed; needBatch() joins it before the list is first read.
+  struct BatchFill { std::thread t; void join() { if (t.joinable()) t.join(); } ~BatchFill() { join(); } } batchFill;
+  auto fillBatch = [&, pairs, B, n, Bq]() {
+    if (offsetsByDma) fillPairs();
+    batch.assign(pairs, pairs + B);
+    if (Bq > 0) { batchOriginal.assign(B, HostChange{0, 0}); for (size_t i = 0; i < Bq; i++) batchOriginal[n + i] = queueOriginal[i]; }
+  };
+  if (B >= (1u << 15)) batchFill.t = std::thread(fillBatch); else fillBatch();
+  auto needBatch = [&]() { batchFill.join(); };
+  nvtx.next("inflate+decode-finish");
   // ------------------------------------------------------------ 1. DEFLATEd changes
   {
     // Which changes of the batch are DEFLATEd (columnar.js:742)? Those are inflated on the device, behind the batch:
@@ -382,7 +389,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   if (!haveHashGraph && numNew < B) throw NeedHistory{};   // a change waits for (or repeats) something older than the loaded heads
   // the queue after this call: every batch entry whose hash is still not applied (new.js:1569-1570, 1832)
   std::vector<HostChange> newQueue, newQueueOriginal;
-  if (numNew < B) finishInflate();
+  if (numNew < B) { needBatch(); finishInflate(); }
   if (numNew < B) for (size_t b = 0; b < B; b++) {
     const u32 pr = primaryH[b];
     const bool hashApplied = pr < numApplied || appliedH[pr - numApplied];
@@ -690,7 +697,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   // ------------------------------------------------------------ 8. commit (nothing above mutated persistent state)
   sync(ctx);
   dbgMark("commit:synced");
-  finishInflate();
+  needBatch(); finishInflate();
   if (numNew > 0) {
     if (!(inOrder && numNew == B)) {   // hashes of applied changes must be contiguous in application order
       DBuf<u8>& tmp = hashTmp; tmp.ensure(ctx, numNew * 32 + 64);

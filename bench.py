@@ -60,8 +60,8 @@ CPU_SAMPLE = {'C3': 200_000, 'C4': 30_000, 'C2': 100_000, 'C2b': 100_000}
 def read_traffic():
     """DRAM bytes per launch of the decode kernels from the committed ncu capture (None if the file is missing)."""
     try:
-        with open(os.path.join(ROOT, 'profiles', 'traffic_r01.json')) as fh:
-            return int(json.load(fh)['decode_total_bytes']), 'profiles/traffic_r01.json (ncu --set full, see profiles/README_r01.md)'
+        with open(os.path.join(ROOT, 'profiles', 'traffic_r02.json')) as fh:
+            return int(json.load(fh)['decode_total_bytes']), 'profiles/traffic_r02.json (ncu --set full of k_decode_tiles, dram__bytes_read.sum + dram__bytes_write.sum, see profiles/README_r02.md)'
     except Exception:
         return None, None
 
