@@ -299,7 +299,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       foreach(ctx, B, CompactKernel{emit.p, slot.p, deflList.p});
       inflLen.ensure(ctx, nd + 1); inflOff.ensure(ctx, nd + 2); patchTriples.ensure(ctx, 2 * nd + 2);
       u32* origOff = patchTriples.p; u32* origLen = patchTriples.p + nd;
-      foreach_warp(ctx, nd, InflateKernel{0, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, nullptr, 0, origOff, origLen, errWord.p});
+      inflate_changes(ctx, 0, arena.p, chOff.p, chLen.p, deflList.p, nd, inflLen.p, nullptr, 0, origOff, origLen, errWord.p);
       scan_exclusive(ctx, scanTmp, inflLen.p, inflOff.p, nd);
       const size_t extra = readU32(inflOff.p + nd);
       { u64 ew0 = 0; d2h(ctx, &ew0, errWord.p, 8); sync(ctx); if (ew0) throwKernelError(ew0, actorIds); }
@@ -307,7 +307,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       const size_t extraStart = cur; cur += extra;
       side_join(ctx);   // the arena may move: nothing may still be reading it
       arena.ensure(ctx, cur + 64, extraStart);
-      foreach_warp(ctx, nd, InflateKernel{1, arena.p, chOff.p, chLen.p, deflList.p, inflLen.p, inflOff.p, (u32)extraStart, origOff, origLen, errWord.p});
+      inflate_changes(ctx, 1, arena.p, chOff.p, chLen.p, deflList.p, nd, inflLen.p, inflOff.p, (u32)extraStart, origOff, origLen, errWord.p);
       dev_memset(ctx, arena.p + cur, 0, 64);
       foreach(ctx, nd, InflatePatchKernel{deflList.p, inflLen.p, inflOff.p, (u32)extraStart, chOff.p, chLen.p});
       foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashOut, errWord.p, deflList.p, nullptr});
