@@ -158,24 +158,33 @@ struct InflateKernel {
     if (e || produced != n) { raise(errWord, e ? e : (u32)KE_DEFLATE, c); return; }
   }
 };
-#ifndef AMG_EMU
-// ---- warp-per-stream decoder with lookup tables in shared memory (the product path on the device; InflateKernel above is
-// the serial restatement the emulation build runs). Lane 0 walks the stream; all lanes build the Huffman lookup tables of a
-// block: 10 bits for literal / length codes, 8 bits for distance codes (entry = symbol << 4 | code length; 0 = code longer
-// than the table: decoded bit by bit from the canonical counts like the serial decoder). Configs whose changes are all
-// DEFLATEd (C4: 10 000 changes of 8 KB) spent 80 % of a call in the bit-by-bit decoder.
+// ---- decoder with lookup tables (the product path on the device: one warp per stream, tables in shared memory; the
+// emulation build runs the same code with a "warp" of one lane). Lane 0 walks the stream; all lanes build the Huffman lookup
+// tables of a block: 10 bits for literal / length codes, 8 bits for distance codes (entry = symbol << 4 | code length;
+// 0 = code longer than the table: decoded bit by bit from the canonical counts like inflate_raw above). Configs whose
+// changes are all DEFLATEd (C4: 10 000 changes of 8 KB) spent 80 % of a call in the bit-by-bit decoder.
 static const int INFL_LBITS = 10, INFL_DBITS = 8, INFL_WARPS = 8;
 struct InflWarpTables { uint16_t lit[1 << INFL_LBITS]; uint16_t dist[1 << INFL_DBITS]; uint16_t lcount[16], lsym[288], dcount[16], dsym[32]; u8 lengths[320]; };
+#if defined(__CUDA_ARCH__)
+#define INFL_SYNC() __syncwarp()
+#define INFL_BCAST(x) __shfl_sync(0xffffffffu, (x), 0)
+#define INFL_BREV(x) __brev(x)
+#else
+#define INFL_SYNC() do {} while (0)
+#define INFL_BCAST(x) (x)
+HD u32 infl_brev_host(u32 v) { u32 r = 0; for (int i = 0; i < 32; i++) { r = (r << 1) | (v & 1u); v >>= 1; } return r; }
+#define INFL_BREV(x) infl_brev_host(x)
+#endif
 struct WarpBits {   // LSB-first bit buffer over src[pos, end)
   const u8* src; u32 pos, end; u64 bb; int bc; bool err;
-  DEV WarpBits(const u8* s, u32 b, u32 e) : src(s), pos(b), end(e), bb(0), bc(0), err(false) {}
-  DEV void refill() { while (bc <= 56 && pos < end) { bb |= (u64)src[pos++] << bc; bc += 8; } }
-  DEV u32 peek(int n) const { return (u32)(bb & ((1ull << n) - 1ull)); }
-  DEV void drop(int n) { if (n > bc) { err = true; bc = 0; bb = 0; } else { bb >>= n; bc -= n; } }
-  DEV u32 bits(int n) { if (bc < n) refill(); const u32 v = peek(n); drop(n); return v; }   // n <= 16
-  DEV void alignByte() { const int r = bc & 7; bb >>= r; bc -= r; }
+  HD WarpBits(const u8* s, u32 b, u32 e) : src(s), pos(b), end(e), bb(0), bc(0), err(false) {}
+  HD void refill() { while (bc <= 56 && pos < end) { bb |= (u64)src[pos++] << bc; bc += 8; } }
+  HD u32 peek(int n) const { return (u32)(bb & ((1ull << n) - 1ull)); }
+  HD void drop(int n) { if (n > bc) { err = true; bc = 0; bb = 0; } else { bb >>= n; bc -= n; } }
+  HD u32 bits(int n) { if (bc < n) refill(); const u32 v = peek(n); drop(n); return v; }   // n <= 16
+  HD void alignByte() { const int r = bc & 7; bb >>= r; bc -= r; }
 };
-DEV int infl_decode_slow(WarpBits& b, const uint16_t* count, const uint16_t* symbol) {   // canonical decode, bit by bit (codes longer than the table)
+HD int infl_decode_slow(WarpBits& b, const uint16_t* count, const uint16_t* symbol) {   // canonical decode, bit by bit (codes longer than the table)
   int code = 0, first = 0, index = 0;
   for (int len = 1; len < 16; len++) {
     code |= (int)b.bits(1); if (b.err) return -1;
@@ -185,185 +194,196 @@ DEV int infl_decode_slow(WarpBits& b, const uint16_t* count, const uint16_t* sym
   }
   return -1;
 }
-// lane-parallel: canonical code of n symbols -> count / symbol arrays (lane 0) and the TBITS lookup table (all lanes)
-DEV bool infl_build(const u8* lengths, int n, uint16_t* count, uint16_t* symbol, uint16_t* table, int tbits, int lane) {
-  bool ok = true;
+// canonical code of n symbols -> count / symbol arrays (lane 0) and the tbits lookup table (all lanes)
+HD bool infl_build(const u8* lengths, int n, uint16_t* count, uint16_t* symbol, uint16_t* table, int tbits, int lane, int nlanes, bool mustBeComplete) {
+  int ok = 1;
   if (lane == 0) {
     for (int i = 0; i < 16; i++) count[i] = 0;
     for (int i = 0; i < n; i++) count[lengths[i]]++;
     if (count[0] != n) {
       int left = 1;
-      for (int len = 1; len < 16; len++) { left <<= 1; left -= count[len]; if (left < 0) { ok = false; break; } }
+      for (int len = 1; len < 16; len++) { left <<= 1; left -= count[len]; if (left < 0) { ok = 0; break; } }
       if (ok) {
         uint16_t offs[16]; offs[1] = 0;
         for (int len = 1; len < 15; len++) offs[len + 1] = (uint16_t)(offs[len] + count[len]);
         for (int i = 0; i < n; i++) if (lengths[i]) symbol[offs[lengths[i]]++] = (uint16_t)i;
-        ok = left == 0 || (n - count[0]) == 1;
+        ok = (!mustBeComplete || left == 0 || (n - count[0]) == 1) ? 1 : 0;   // (the fixed distance code of RFC 1951 3.2.6 uses 30 of 32 codes)
       }
     }
   }
-  ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-  __syncwarp();
-  for (int k = lane; k < (1 << tbits); k += 32) table[k] = 0;
-  __syncwarp();
+  ok = INFL_BCAST(ok);
+  INFL_SYNC();
+  for (int k = lane; k < (1 << tbits); k += nlanes) table[k] = 0;
+  INFL_SYNC();
   if (!ok) return false;
-  // first canonical code of every length
-  // (RFC 1951 3.2.2; count[0] is the number of unused symbols, not a code length: the recurrence starts at length 1 with code 0)
+  // first canonical code of every length (RFC 1951 3.2.2; count[0] is the number of unused symbols, not a code length)
   u32 next[16]; { u32 code = 0; u32 prev = 0; for (int len = 1; len < 16; len++) { code = (code + prev) << 1; next[len] = code; prev = count[len]; } }
-  // symbols of one length are numbered in symbol order: symbol[] is sorted by (length, symbol), so the j-th entry of length L has code next[L] + j
+  // symbol[] is sorted by (length, symbol): the j-th symbol of length L has code next[L] + j; codes are sent MSB first into an LSB-first stream
   int base = 0;
   for (int len = 1; len <= tbits; len++) {
     const int c = count[len];
-    for (int j = lane; j < c; j += 32) {
-      const u32 code = next[len] + (u32)j; const u32 rev = __brev(code) >> (32 - len);
+    for (int j = lane; j < c; j += nlanes) {
+      const u32 code = next[len] + (u32)j; const u32 rev = INFL_BREV(code) >> (32 - len);
       const uint16_t entry = (uint16_t)((symbol[base + j] << 4) | len);
       for (u32 k = rev; k < (1u << tbits); k += (1u << len)) table[k] = entry;
     }
     base += c;
   }
-  __syncwarp();
+  INFL_SYNC();
   return true;
 }
-__global__ void __launch_bounds__(INFL_WARPS * 32) k_inflate(int pass, u8* arena, u32* chOff, u32* chLen, const u32* list, size_t nd, u32* outLen, const u32* outOff, u32 extraStart, u32* origOff, u32* origLen, u64* errWord) {
-  __shared__ InflWarpTables tabs[INFL_WARPS];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  InflWarpTables& T = tabs[warp];
+// Decodes src[begin, end) into dst (nullptr = only count) with the tables T of this warp. Every lane calls it; lane 0
+// returns the KErr and *produced.
+HD u32 inflate_tabled(InflWarpTables& T, const u8* src, u32 begin, u32 end, u8* dst, u32 dstCap, u32* produced, int lane, int nlanes) {
   const uint16_t lenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
   const u8 lenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
   const uint16_t distBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
   const u8 distExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
   const u8 clOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-  for (size_t k = (size_t)blockIdx.x * INFL_WARPS + warp; k < nd; k += (size_t)gridDim.x * INFL_WARPS) {
-    const u32 c = list[k]; const u32 off = pass == 0 ? chOff[c] : origOff[k], len = pass == 0 ? chLen[c] : origLen[k];
-    u32 kerr = 0, streamBegin = 0, clen = 0;
-    if (lane == 0) { ByteReader r(arena, off + 9, off + len); const u64 cl = r.uleb(); if (r.err || (u64)r.pos + cl > (u64)off + len) kerr = r.err ? r.err : (u32)KE_SUBARRAY; streamBegin = r.pos; clen = (u32)cl; }
-    kerr = __shfl_sync(0xffffffffu, kerr, 0); streamBegin = __shfl_sync(0xffffffffu, streamBegin, 0); clen = __shfl_sync(0xffffffffu, clen, 0);
-    if (kerr) { if (lane == 0) { raise(errWord, kerr, c); if (pass == 0) outLen[k] = 0; } continue; }
-    u8* dst = nullptr; u32 dstCap = 0, hl = 9;
-    if (pass == 1) {
-      const u32 total = outLen[k]; if (total == 0) continue;
-      u8* d0 = arena + extraStart + outOff[k]; u32 n = 0;
-      for (u32 w = 1; w <= 5; w++) { n = total - 9 - w; if (uleb_len(n) == w) break; }
-      if (lane == 0) { for (int i = 0; i < 8; i++) d0[i] = arena[off + i]; d0[8] = 1; u64 v = n; do { u8 x = v & 0x7f; v >>= 7; if (v) x |= 0x80; d0[hl++] = x; } while (v); }
-      hl = __shfl_sync(0xffffffffu, hl, 0);
-      dst = d0 + hl; dstCap = n;
-    }
-    WarpBits b(arena, streamBegin, streamBegin + clen); u32 out = 0; u32 e = 0; bool done = false;
-    while (!done && !e) {
-      u32 last = 0, type = 0; int nlen = 0, ndist = 0;
-      if (lane == 0) {
-        last = b.bits(1); type = b.bits(2); if (b.err) e = KE_DEFLATE;
-        if (!e && type == 0) {            // stored
-          b.alignByte();
-          // the bit buffer holds whole bytes now: give them back to the byte position
-          b.pos -= (u32)(b.bc >> 3); b.bb = 0; b.bc = 0;
-          if (b.pos + 4 > b.end) e = KE_DEFLATE;
-          else {
-            const u32 ln = arena[b.pos] | ((u32)arena[b.pos + 1] << 8), nln = arena[b.pos + 2] | ((u32)arena[b.pos + 3] << 8);
-            if ((ln ^ 0xffffu) != nln) e = KE_DEFLATE;
-            else { b.pos += 4; if (b.pos + ln > b.end) e = KE_DEFLATE; else { if (dst) { if (out + ln > dstCap) e = KE_DEFLATE; else for (u32 i = 0; i < ln; i++) dst[out + i] = arena[b.pos + i]; } out += ln; b.pos += ln; } }
-          }
-        } else if (!e && type == 1) {     // fixed code (RFC 1951 3.2.6)
-          for (int i = 0; i < 144; i++) T.lengths[i] = 8;
-          for (int i = 144; i < 256; i++) T.lengths[i] = 9;
-          for (int i = 256; i < 280; i++) T.lengths[i] = 7;
-          for (int i = 280; i < 288; i++) T.lengths[i] = 8;
-          for (int i = 0; i < 30; i++) T.lengths[288 + i] = 5;
-          nlen = 288; ndist = 30;
-        } else if (!e && type == 2) {     // dynamic code (RFC 1951 3.2.7): code lengths decoded by lane 0 with the bit-by-bit decoder
-          nlen = (int)b.bits(5) + 257; ndist = (int)b.bits(5) + 1; const int ncode = (int)b.bits(4) + 4;
-          if (b.err || nlen > 286 || ndist > 30) e = KE_DEFLATE;
-          else {
-            u8 cl[19]; for (int i = 0; i < 19; i++) cl[i] = 0;
-            for (int i = 0; i < ncode; i++) cl[clOrder[i]] = (u8)b.bits(3);
-            if (b.err) e = KE_DEFLATE;
-            // canonical code of the 19 code-length symbols in the distance count / symbol arrays (free at this point)
-            uint16_t* cnt = T.dcount; uint16_t* sym = T.dsym;
-            for (int i = 0; i < 16; i++) cnt[i] = 0;
-            for (int i = 0; i < 19; i++) cnt[cl[i]]++;
-            if (!e && cnt[0] != 19) {
+  WarpBits b(src, begin, end); u32 out = 0; u32 e = 0; bool done = false; *produced = 0;
+  while (!done && !e) {
+    u32 last = 0, type = 0; int nlen = 0, ndist = 0;
+    if (lane == 0) {
+      last = b.bits(1); type = b.bits(2); if (b.err) e = KE_DEFLATE;
+      if (!e && type == 0) {            // stored
+        b.alignByte();
+        b.pos -= (u32)(b.bc >> 3); b.bb = 0; b.bc = 0;   // the bit buffer holds whole bytes now: given back to the byte position
+        if (b.pos + 4 > b.end) e = KE_DEFLATE;
+        else {
+          const u32 ln = src[b.pos] | ((u32)src[b.pos + 1] << 8), nln = src[b.pos + 2] | ((u32)src[b.pos + 3] << 8);
+          if ((ln ^ 0xffffu) != nln) e = KE_DEFLATE;
+          else { b.pos += 4; if (b.pos + ln > b.end) e = KE_DEFLATE; else { if (dst) { if (out + ln > dstCap) e = KE_DEFLATE; else for (u32 i = 0; i < ln; i++) dst[out + i] = src[b.pos + i]; } out += ln; b.pos += ln; } }
+        }
+      } else if (!e && type == 1) {     // fixed code (RFC 1951 3.2.6)
+        for (int i = 0; i < 144; i++) T.lengths[i] = 8;
+        for (int i = 144; i < 256; i++) T.lengths[i] = 9;
+        for (int i = 256; i < 280; i++) T.lengths[i] = 7;
+        for (int i = 280; i < 288; i++) T.lengths[i] = 8;
+        for (int i = 0; i < 30; i++) T.lengths[288 + i] = 5;
+        nlen = 288; ndist = 30;
+      } else if (!e && type == 2) {     // dynamic code (RFC 1951 3.2.7): the code lengths are decoded by lane 0, bit by bit
+        nlen = (int)b.bits(5) + 257; ndist = (int)b.bits(5) + 1; const int ncode = (int)b.bits(4) + 4;
+        if (b.err || nlen > 286 || ndist > 30) e = KE_DEFLATE;
+        else {
+          u8 cl[19]; for (int i = 0; i < 19; i++) cl[i] = 0;
+          for (int i = 0; i < ncode; i++) cl[clOrder[i]] = (u8)b.bits(3);
+          if (b.err) e = KE_DEFLATE;
+          uint16_t* cnt = T.dcount; uint16_t* sym = T.dsym;   // the code-length code (19 symbols) borrows the distance arrays
+          for (int i = 0; i < 16; i++) cnt[i] = 0;
+          for (int i = 0; i < 19; i++) cnt[cl[i]]++;
+          if (!e) {
+            if (cnt[0] == 19) { /* no codes: decode fails below */ }
+            else {
               int left = 1; for (int l2 = 1; l2 < 16; l2++) { left <<= 1; left -= cnt[l2]; if (left < 0) { e = KE_DEFLATE; break; } }
               if (!e) { uint16_t offs[16]; offs[1] = 0; for (int l2 = 1; l2 < 15; l2++) offs[l2 + 1] = (uint16_t)(offs[l2] + cnt[l2]); for (int i = 0; i < 19; i++) if (cl[i]) sym[offs[cl[i]]++] = (uint16_t)i; if (!(left == 0 || (19 - cnt[0]) == 1)) e = KE_DEFLATE; }
             }
-            int idx = 0;
-            while (!e && idx < nlen + ndist) {
-              const int s2 = infl_decode_slow(b, cnt, sym);
-              if (s2 < 0) { e = KE_DEFLATE; break; }
-              if (s2 < 16) T.lengths[idx++] = (u8)s2;
-              else {
-                int rep; u8 val = 0;
-                if (s2 == 16) { if (idx == 0) { e = KE_DEFLATE; break; } val = T.lengths[idx - 1]; rep = 3 + (int)b.bits(2); }
-                else if (s2 == 17) rep = 3 + (int)b.bits(3);
-                else rep = 11 + (int)b.bits(7);
-                if (b.err || idx + rep > nlen + ndist) { e = KE_DEFLATE; break; }
-                while (rep--) T.lengths[idx++] = val;
-              }
-            }
-            if (!e && T.lengths[256] == 0) e = KE_DEFLATE;   // no end-of-block code
-            if (!e) { for (int i = ndist - 1; i >= 0; i--) T.lengths[288 + i] = T.lengths[nlen + i]; }   // distance lengths at a fixed place (nlen <= 286 < 288: moved from the back)
           }
-        } else if (!e) e = KE_DEFLATE;
-      }
-      e = __shfl_sync(0xffffffffu, e, 0); type = __shfl_sync(0xffffffffu, type, 0); last = __shfl_sync(0xffffffffu, last, 0);
-      nlen = __shfl_sync(0xffffffffu, nlen, 0); ndist = __shfl_sync(0xffffffffu, ndist, 0);
-      __syncwarp();
-      if (e) break;
-      if (type != 0) {
-        const bool okL = infl_build(T.lengths, nlen, T.lcount, T.lsym, T.lit, INFL_LBITS, lane);
-        const bool okD = infl_build(T.lengths + 288, ndist, T.dcount, T.dsym, T.dist, INFL_DBITS, lane);
-        if (!okL || !okD) { e = KE_DEFLATE; break; }
-        if (lane == 0) {
-          while (true) {
-            b.refill();
-            int sym; { const u32 t = T.lit[b.peek(INFL_LBITS)]; if (t) { b.drop((int)(t & 15)); sym = (int)(t >> 4); } else sym = infl_decode_slow(b, T.lcount, T.lsym); }
-            if (sym < 0 || b.err) { e = KE_DEFLATE; break; }
-            if (sym < 256) { if (dst) { if (out >= dstCap) { e = KE_DEFLATE; break; } dst[out] = (u8)sym; } out++; }
-            else if (sym == 256) break;
+          int idx = 0;
+          while (!e && idx < nlen + ndist) {
+            const int s2 = infl_decode_slow(b, cnt, sym);
+            if (s2 < 0) { e = KE_DEFLATE; break; }
+            if (s2 < 16) T.lengths[idx++] = (u8)s2;
             else {
-              sym -= 257; if (sym >= 29) { e = KE_DEFLATE; break; }
-              const u32 ln = lenBase[sym] + b.bits(lenExtra[sym]);
-              b.refill();
-              int ds; { const u32 t = T.dist[b.peek(INFL_DBITS)]; if (t) { b.drop((int)(t & 15)); ds = (int)(t >> 4); } else ds = infl_decode_slow(b, T.dcount, T.dsym); }
-              if (ds < 0 || ds >= 30) { e = KE_DEFLATE; break; }
-              const u32 d = distBase[ds] + b.bits(distExtra[ds]);
-              if (b.err || d > out) { e = KE_DEFLATE; break; }
-              if (dst) { if (out + ln > dstCap) { e = KE_DEFLATE; break; } for (u32 i = 0; i < ln; i++) dst[out + i] = dst[out + i - d]; }
-              out += ln;
+              int rep; u8 val = 0;
+              if (s2 == 16) { if (idx == 0) { e = KE_DEFLATE; break; } val = T.lengths[idx - 1]; rep = 3 + (int)b.bits(2); }
+              else if (s2 == 17) rep = 3 + (int)b.bits(3);
+              else rep = 11 + (int)b.bits(7);
+              if (b.err || idx + rep > nlen + ndist) { e = KE_DEFLATE; break; }
+              while (rep--) T.lengths[idx++] = val;
             }
-            if (out > 0x7fffffffu) { e = KE_TOO_LARGE; break; }
           }
+          if (!e && T.lengths[256] == 0) e = KE_DEFLATE;   // no end-of-block code
+          if (!e) { u8 dl[30]; for (int i = 0; i < ndist; i++) dl[i] = T.lengths[nlen + i]; for (int i = 0; i < ndist; i++) T.lengths[288 + i] = dl[i]; }   // distance lengths at a fixed place
         }
-        e = __shfl_sync(0xffffffffu, e, 0);
-        __syncwarp();
+      } else if (!e) e = KE_DEFLATE;
+    }
+    e = INFL_BCAST(e); type = INFL_BCAST(type); last = INFL_BCAST(last); nlen = INFL_BCAST(nlen); ndist = INFL_BCAST(ndist);
+    INFL_SYNC();
+    if (e) break;
+    if (type != 0) {
+      const bool okL = infl_build(T.lengths, nlen, T.lcount, T.lsym, T.lit, INFL_LBITS, lane, nlanes, type == 2);
+      const bool okD = infl_build(T.lengths + 288, ndist, T.dcount, T.dsym, T.dist, INFL_DBITS, lane, nlanes, type == 2);
+      if (!okL || !okD) { e = KE_DEFLATE; break; }
+      if (lane == 0) {
+        while (true) {
+          b.refill();
+          int sym; { const u32 t = T.lit[b.peek(INFL_LBITS)]; if (t) { b.drop((int)(t & 15)); sym = (int)(t >> 4); } else sym = infl_decode_slow(b, T.lcount, T.lsym); }
+          if (sym < 0 || b.err) { e = KE_DEFLATE; break; }
+          if (sym < 256) { if (dst) { if (out >= dstCap) { e = KE_DEFLATE; break; } dst[out] = (u8)sym; } out++; }
+          else if (sym == 256) break;
+          else {
+            sym -= 257; if (sym >= 29) { e = KE_DEFLATE; break; }
+            const u32 ln = lenBase[sym] + b.bits(lenExtra[sym]);
+            b.refill();
+            int ds; { const u32 t = T.dist[b.peek(INFL_DBITS)]; if (t) { b.drop((int)(t & 15)); ds = (int)(t >> 4); } else ds = infl_decode_slow(b, T.dcount, T.dsym); }
+            if (ds < 0 || ds >= 30) { e = KE_DEFLATE; break; }
+            const u32 d = distBase[ds] + b.bits(distExtra[ds]);
+            if (b.err || d > out) { e = KE_DEFLATE; break; }
+            if (dst) { if (out + ln > dstCap) { e = KE_DEFLATE; break; } for (u32 i = 0; i < ln; i++) dst[out + i] = dst[out + i - d]; }
+            out += ln;
+          }
+          if (out > 0x7fffffffu) { e = KE_TOO_LARGE; break; }
+        }
       }
-      if (last) done = true;
+      e = INFL_BCAST(e);
+      INFL_SYNC();
     }
-    if (lane == 0) {
-      if (pass == 0) { if (e) { raise(errWord, e, c); outLen[k] = 0; } else { outLen[k] = 9 + uleb_len(out) + out; origOff[k] = off; origLen[k] = len; } }
-      else if (e || out != dstCap) raise(errWord, e ? e : (u32)KE_DEFLATE, c);
-    }
-    __syncwarp();
+    if (last) done = true;
   }
+  *produced = out;
+  return e;
 }
+// One stream k of the list with `nlanes` cooperating lanes (32 on the device, 1 in the emulation). pass 0: outLen[k] = size of
+// the inflated change (8 bytes magic + checksum, chunk type 1, LEB128 length, body), original range kept; pass 1: bytes
+// written at arena[extraStart + outOff[k]).
+HD void inflate_one(InflWarpTables& T, size_t k, int pass, u8* arena, u32* chOff, u32* chLen, const u32* list, u32* outLen, const u32* outOff, u32 extraStart, u32* origOff, u32* origLen, u64* errWord, int lane, int nlanes) {
+  const u32 c = list[k]; const u32 off = pass == 0 ? chOff[c] : origOff[k], len = pass == 0 ? chLen[c] : origLen[k];
+  u32 kerr = 0, streamBegin = 0, clen = 0;
+  if (lane == 0) { ByteReader r(arena, off + 9, off + len); const u64 cl = r.uleb(); if (r.err || (u64)r.pos + cl > (u64)off + len) kerr = r.err ? r.err : (u32)KE_SUBARRAY; streamBegin = r.pos; clen = (u32)cl; }
+  kerr = INFL_BCAST(kerr); streamBegin = INFL_BCAST(streamBegin); clen = INFL_BCAST(clen);
+  if (kerr) { if (lane == 0) { raise(errWord, kerr, c); if (pass == 0) outLen[k] = 0; } return; }
+  u8* dst = nullptr; u32 dstCap = 0, hl = 9;
+  if (pass == 1) {
+    const u32 total = outLen[k]; if (total == 0) return;
+    u8* d0 = arena + extraStart + outOff[k]; u32 n = 0;
+    for (u32 w = 1; w <= 5; w++) { n = total - 9 - w; if (uleb_len(n) == w) break; }
+    if (lane == 0) { for (int i = 0; i < 8; i++) d0[i] = arena[off + i]; d0[8] = 1; u64 v = n; do { u8 x = v & 0x7f; v >>= 7; if (v) x |= 0x80; d0[hl++] = x; } while (v); }
+    hl = INFL_BCAST(hl);
+    dst = d0 + hl; dstCap = n;
+  }
+  u32 out = 0; const u32 e = inflate_tabled(T, arena, streamBegin, streamBegin + clen, dst, dstCap, &out, lane, nlanes);
+  if (lane == 0) {
+    if (pass == 0) { if (e) { raise(errWord, e, c); outLen[k] = 0; } else { outLen[k] = 9 + uleb_len(out) + out; origOff[k] = off; origLen[k] = len; } }
+    else if (e || out != dstCap) raise(errWord, e ? e : (u32)KE_DEFLATE, c);
+  }
+  INFL_SYNC();
+}
+#ifndef AMG_EMU
+__global__ void __launch_bounds__(INFL_WARPS * 32) k_inflate(int pass, u8* arena, u32* chOff, u32* chLen, const u32* list, size_t nd, u32* outLen, const u32* outOff, u32 extraStart, u32* origOff, u32* origLen, u64* errWord) {
+  __shared__ InflWarpTables tabs[INFL_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (size_t k = (size_t)blockIdx.x * INFL_WARPS + warp; k < nd; k += (size_t)gridDim.x * INFL_WARPS)
+    inflate_one(tabs[warp], k, pass, arena, chOff, chLen, list, outLen, outOff, extraStart, origOff, origLen, errWord, lane, 32);
+}
+#endif
 inline void inflate_changes(Ctx& c, int pass, u8* arena, u32* chOff, u32* chLen, const u32* list, size_t nd, u32* outLen, const u32* outOff, u32 extraStart, u32* origOff, u32* origLen, u64* errWord) {
   if (nd == 0) return;
+#ifdef AMG_EMU
+  InflWarpTables* T = new InflWarpTables();
+  for (size_t k = 0; k < nd; k++) inflate_one(*T, k, pass, arena, chOff, chLen, list, outLen, outOff, extraStart, origOff, origLen, errWord, 0, 1);
+  delete T;
+#else
   const size_t want = (nd + INFL_WARPS - 1) / INFL_WARPS, maxGrid = (size_t)c.numSMs * 4;
   k_inflate<<<(unsigned)std::min(want, maxGrid), INFL_WARPS * 32, 0, c.stream>>>(pass, arena, chOff, chLen, list, nd, outLen, outOff, extraStart, origOff, origLen, errWord);
-  CUDA_CHECK(cudaGetLastError()); c.launches++;
-}
-#else
-inline void inflate_changes(Ctx& c, int pass, u8* arena, u32* chOff, u32* chLen, const u32* list, size_t nd, u32* outLen, const u32* outOff, u32 extraStart, u32* origOff, u32* origLen, u64* errWord);
+  CUDA_CHECK(cudaGetLastError());
 #endif
+  c.launches++;
+}
 // re-points the inflated changes (separate from pass 1: the batch-wide SHA kernel may still be reading the old entries)
 struct InflatePatchKernel {
   const u32* list; const u32* outLen; const u32* outOff; u32 extraStart; u32* chOff; u32* chLen;
   HD void operator()(size_t k) const { if (outLen[k] == 0) return; const u32 c = list[k]; chOff[c] = extraStart + outOff[k]; chLen[c] = outLen[k]; }
 };
-#ifdef AMG_EMU
-inline void inflate_changes(Ctx& c, int pass, u8* arena, u32* chOff, u32* chLen, const u32* list, size_t nd, u32* outLen, const u32* outOff, u32 extraStart, u32* origOff, u32* origLen, u64* errWord) {
-  foreach_warp(c, nd, InflateKernel{pass, arena, chOff, chLen, list, outLen, outOff, extraStart, origOff, origLen, errWord});
-}
-#endif
 struct DeflateFlagKernel {   // 1 for chunks of type 2 (columnar.js:742)
   const u8* arena; const u32* chOff; const u32* chLen; u32* flag;
   HD void operator()(size_t c) const { const u8* p = arena + chOff[c]; flag[c] = (chLen[c] > 8 && p[8] == 2 && p[0] == 0x85) ? 1u : 0u; }
