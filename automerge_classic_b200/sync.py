@@ -102,11 +102,13 @@ class BloomFilter:
         return out
 
     def add_hash(self, hash_hex):
+        if len(self.bits) == 0:   # a peer's filter with entries but no bits: the reference computes NaN probes and stores nothing
+            return
         for p in self.probes(hash_hex):
             self.bits[p >> 3] |= 1 << (p & 7)
 
     def contains_hash(self, hash_hex):
-        if self.num_entries == 0:
+        if self.num_entries == 0 or len(self.bits) == 0:   # (sync.js:84-98 with modulo 0: NaN probes, containsHash false: the changes are sent)
             return False
         return all(self.bits[p >> 3] & (1 << (p & 7)) for p in self.probes(hash_hex))
 
