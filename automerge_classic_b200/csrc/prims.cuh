@@ -4,7 +4,7 @@
 //                  nothing is cleared between scans; warp 0 inspects 32 predecessor tiles per step). Measured against the
 //                  three-kernel form (reduce / scan of tile sums / apply) on the 1M-op trace: 0.1 ms less per call.
 // scan_exclusive64: the packed 64-bit scan of the list-index levels keeps the three-kernel form (single pass: no gain).
-// radix_sort_pairs: 8-bit digits; per pass: tile histogram (shared-memory atomics) -> scan of the
+// radix_sort_pairs: digits of up to 11 bits (balanced over the key width); per pass: tile histogram (shared-memory atomics) -> scan of the
 //                  digit-major histogram -> stable scatter. The stable in-tile rank uses
 //                  __match_any_sync warp multisplit (one leader lane per digit value per round bumps
 //                  a per-warp shared-memory counter), so no sorting network and no second key read.
@@ -204,28 +204,31 @@ template <class F> inline void scan_exclusive64(Ctx& c, ScanTemp& t, const F& in
 
 // ---------------------------------------------------------------- radix sort
 #ifndef AMG_EMU
-static const int RS_THREADS = 256, RS_ITEMS = 16, RS_TILE = RS_THREADS * RS_ITEMS, RS_WARPS = RS_THREADS / 32, RS_STRIP = 32 * RS_ITEMS;
+// Digits of up to RS_MAX_BITS bits: a 51-bit sibling key takes 5 passes of 11 bits instead of 7 of 8, a 20-bit field 2 instead
+// of 3 (every pass is three launches and a full read + write of the pairs). The digit width of a sort is chosen so that
+// its passes are balanced (radix_sort_pairs).
+static const int RS_THREADS = 256, RS_ITEMS = 16, RS_TILE = RS_THREADS * RS_ITEMS, RS_WARPS = RS_THREADS / 32, RS_STRIP = 32 * RS_ITEMS, RS_MAX_BITS = 11, RS_MAX_BINS = 1 << RS_MAX_BITS;
 
-__global__ void __launch_bounds__(256) k_rs_hist(const u64* __restrict__ keys, u32* __restrict__ histG, size_t n, int shift, unsigned numTiles) {
-  __shared__ u32 hist[256];
-  hist[threadIdx.x] = 0;
+__global__ void __launch_bounds__(256) k_rs_hist(const u64* __restrict__ keys, u32* __restrict__ histG, size_t n, int shift, u32 mask, unsigned numTiles) {
+  __shared__ u32 hist[RS_MAX_BINS];
+  for (u32 k = threadIdx.x; k <= mask; k += RS_THREADS) hist[k] = 0;
   __syncthreads();
   const size_t base = (size_t)blockIdx.x * RS_TILE;
 #pragma unroll 4
   for (int j = 0; j < RS_ITEMS; j++) {
     size_t i = base + (size_t)j * RS_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&hist[(u32)(keys[i] >> shift) & 255u], 1u);
+    if (i < n) atomicAdd(&hist[(u32)(keys[i] >> shift) & mask], 1u);
   }
   __syncthreads();
-  histG[(size_t)threadIdx.x * numTiles + blockIdx.x] = hist[threadIdx.x];
+  for (u32 k = threadIdx.x; k <= mask; k += RS_THREADS) histG[(size_t)k * numTiles + blockIdx.x] = hist[k];
 }
 
 __global__ void __launch_bounds__(256) k_rs_scatter(const u64* __restrict__ keysIn, const u32* __restrict__ valsIn, u64* __restrict__ keysOut,
-                                                     u32* __restrict__ valsOut, const u32* __restrict__ histScan, size_t n, int shift, unsigned numTiles) {
-  __shared__ u32 warpHist[RS_WARPS][256];
-  __shared__ u32 digitBase[256];
+                                                     u32* __restrict__ valsOut, const u32* __restrict__ histScan, size_t n, int shift, u32 mask, unsigned numTiles) {
+  __shared__ uint16_t warpHist[RS_WARPS][RS_MAX_BINS];   // a warp's strip holds 512 items: 16-bit counters
+  __shared__ u32 digitBase[RS_MAX_BINS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&warpHist[0][0])[k] = 0;
+  for (u32 k = threadIdx.x; k < RS_WARPS * (mask + 1); k += RS_THREADS) warpHist[k / (mask + 1)][k % (mask + 1)] = 0;
   __syncthreads();
   const size_t stripBase = (size_t)blockIdx.x * RS_TILE + (size_t)warp * RS_STRIP;
   u64 key[RS_ITEMS]; u32 val[RS_ITEMS]; u32 rank[RS_ITEMS];
@@ -235,20 +238,20 @@ __global__ void __launch_bounds__(256) k_rs_scatter(const u64* __restrict__ keys
     const size_t i = stripBase + (size_t)j * 32 + lane;
     const bool active = i < n;
     key[j] = active ? keysIn[i] : 0; val[j] = active ? valsIn[i] : 0;
-    const u32 d = active ? ((u32)(key[j] >> shift) & 255u) : 0xffffffffu;
+    const u32 d = active ? ((u32)(key[j] >> shift) & mask) : 0xffffffffu;
     const u32 peers = __match_any_sync(0xffffffffu, d);
     const int leader = __ffs(peers) - 1;
     u32 base = 0;
-    if (active && lane == leader) { base = warpHist[warp][d]; warpHist[warp][d] = base + __popc(peers); }
+    if (active && lane == leader) { base = warpHist[warp][d]; warpHist[warp][d] = (uint16_t)(base + __popc(peers)); }
     base = __shfl_sync(0xffffffffu, base, leader);
     rank[j] = base + __popc(peers & ltMask);
     __syncwarp();
   }
   __syncthreads();
-  {   // thread d: turn per-warp counts of digit d into exclusive prefixes, add the global base
-    const int d = threadIdx.x; u32 acc = 0;
+  for (u32 d = threadIdx.x; d <= mask; d += RS_THREADS) {   // per-warp counts of digit d -> exclusive prefixes; + the global base of (digit, tile)
+    u32 acc = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; w++) { u32 cnt = warpHist[w][d]; warpHist[w][d] = acc; acc += cnt; }
+    for (int w = 0; w < RS_WARPS; w++) { const u32 cnt = warpHist[w][d]; warpHist[w][d] = (uint16_t)acc; acc += cnt; }
     digitBase[d] = histScan[(size_t)d * numTiles + blockIdx.x];
   }
   __syncthreads();
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(256) k_rs_scatter(const u64* __restrict__ keys
   for (int j = 0; j < RS_ITEMS; j++) {
     const size_t i = stripBase + (size_t)j * 32 + lane;
     if (i < n) {
-      const u32 d = (u32)(key[j] >> shift) & 255u;
+      const u32 d = (u32)(key[j] >> shift) & mask;
       const size_t dst = (size_t)digitBase[d] + warpHist[warp][d] + rank[j];
       keysOut[dst] = key[j]; valsOut[dst] = val[j];
     }
@@ -280,13 +283,15 @@ inline void radix_sort_pairs(Ctx& c, SortTemp& t, DBuf<u64>& keys, DBuf<u32>& va
   c.launches += 5 * ((endBit - beginBit + 7) / 8);
 #else
   const unsigned numTiles = (unsigned)((n + RS_TILE - 1) / RS_TILE);
-  t.hist.ensure(c, (size_t)256 * numTiles + 1);
+  const int bits = endBit - beginBit, passes = (bits + RS_MAX_BITS - 1) / RS_MAX_BITS, width = (bits + passes - 1) / passes;   // balanced digit widths
+  t.hist.ensure(c, ((size_t)1 << width) * numTiles + 1);
   t.keysAlt.ensure(c, n); t.valsAlt.ensure(c, n);
-  for (int shift = beginBit; shift < endBit; shift += 8) {
-    k_rs_hist<<<numTiles, RS_THREADS, 0, c.stream>>>(keys.p, t.hist.p, n, shift, numTiles);
+  for (int shift = beginBit; shift < endBit; shift += width) {
+    const int w = std::min(width, endBit - shift); const u32 mask = (1u << w) - 1u;
+    k_rs_hist<<<numTiles, RS_THREADS, 0, c.stream>>>(keys.p, t.hist.p, n, shift, mask, numTiles);
     c.launches++;
-    scan_exclusive(c, t.scan, t.hist.p, t.hist.p, (size_t)256 * numTiles);
-    k_rs_scatter<<<numTiles, RS_THREADS, 0, c.stream>>>(keys.p, vals.p, t.keysAlt.p, t.valsAlt.p, t.hist.p, n, shift, numTiles);
+    scan_exclusive(c, t.scan, t.hist.p, t.hist.p, ((size_t)mask + 1) * numTiles);
+    k_rs_scatter<<<numTiles, RS_THREADS, 0, c.stream>>>(keys.p, vals.p, t.keysAlt.p, t.valsAlt.p, t.hist.p, n, shift, mask, numTiles);
     CUDA_CHECK(cudaGetLastError());
     c.launches++;
     std::swap(keys.p, t.keysAlt.p); std::swap(keys.cap, t.keysAlt.cap);
