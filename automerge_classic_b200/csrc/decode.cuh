@@ -557,6 +557,38 @@ template <class S> HD bool single_value(const S& src, int ix, u32 pos, u32 l, u3
   v = (u32)val;
   return true;
 }
+// The same test with the column index known at compile time (second phase of the fast walk in parse_change): the two
+// common shapes - one literal byte, one null - are decided from (length, first byte, second byte) alone. Reads one byte past
+// a column of length 0 or 1; the caller's bytes have that much slack (shared-memory window, zeroed arena tail).
+template <int IX, class S> HD bool fast_value(const S& src, u32 pos, u32 l, u32& v) {
+  const u32 p0 = src.ld(pos), p1 = src.ld(pos + 1);
+  if (IX == CX_INSERT) {
+    if (l == 1 && p0 == 1) { v = 0; return true; }
+    if (l == 2 && p0 == 0 && p1 == 1) { v = 1; return true; }
+    return false;
+  }
+  if (l == 2) {
+    if (p0 == 0x7f && p1 < 0x80) {
+      if ((IX == CX_KEY_CTR || IX == CX_PRED_CTR) && (p1 & 0x40u)) return false;   // negative delta: the general decoder reports it
+      if (IX == CX_KEY_STR && p1 != 0) return false;
+      v = p1; return true;
+    }
+    if (p0 == 0 && p1 == 1) { v = NULL32; return true; }
+    return false;
+  }
+  if (l < 2 || p0 != 0x7f) return false;
+  if (IX == CX_KEY_STR) { if (p1 >= 0x80) return false; v = p1; return 2 + v == l; }
+  // longer numbers (2 .. 5 bytes of LEB128 that end exactly at the column's end): only for the columns that hold counters
+  // and lengths; an actor index or an action that long is left to the general walk
+  if (!(IX == CX_OBJ_CTR || IX == CX_KEY_CTR || IX == CX_VAL_LEN || IX == CX_PRED_CTR) || l > 6) return false;
+  u64 val = p1 & 0x7fu; u32 last = p1; u32 nb = 1;
+#pragma unroll
+  for (u32 k = 1; k < 5; k++) if ((last & 0x80u) && nb < l - 1) { last = src.ld(pos + 1 + k); val |= (u64)(last & 0x7fu) << (7 * k); nb = k + 1; }
+  if ((last & 0x80u) || nb != l - 1) return false;
+  if ((IX == CX_KEY_CTR || IX == CX_PRED_CTR) && (last & 0x40u)) return false;
+  if (val > 0xfffffffeULL) return false;
+  v = (u32)val; return true;
+}
 // Per-thread scratch for the column values of a single-op change while its directory is walked: indexed by column
 // index with an index that is not known at compile time. In registers that costs a divergent switch per column; the tile
 // kernel keeps the 14 slots of a thread in shared memory (slot k of thread t at [k][t]: conflict-free) and looks the
@@ -614,34 +646,49 @@ template <class S> HD void parse_change(const S& src, ColSlots<S>& slots, u32 of
   // (decodeChangeColumns).
   const u32 dirPos = r.pos; u32 dataPos = nCols < len ? dirPos + 2 * nCols : end;
   u32 actOff = 0, actLen = 0, pnOff = 0, pnLen = 0, seen = 0, rawLen = 0, keyStrPos = 0, valOff = 0, dirErr = 0; bool haveAct = false, single = false;
-  // Fast walk: every id and length of the directory is a single byte (ids below 128, columns shorter than 128 bytes: what
-  // small changes look like). Same checks and results as the general walk below, in 32-bit arithmetic; anything else
-  // falls through to the general walk.
+  // Fast walk, for what editing traces consist of: a well-formed single-op change whose directory entries are single bytes.
+  //  phase A: one pass over the directory; (position, length) of every known column goes to the thread's slot of that
+  //           column; anything unusual (multi-byte id / length, deflate bit, ids not ascending, bytes missing) leaves the
+  //           fast walk, and the general walk below - the one that knows the reference's error order - starts over;
+  //  phase B: the value columns in a fixed order, each decoded by code specialised for it (fast_value); the value
+  //           replaces (position, length) in the slot.
+  // The fast walk either produces the whole single-op result or nothing.
   bool fastWalk = false;
-  if (nCols <= 32 && dirPos + 2 * nCols <= end) {
-    u32 total = 0, colErr = 0, lastId = 0xffffffffu; bool orderBad = false, afterValLen = false; fastWalk = true; single = true;
+  if (nCols <= 32 && dirPos + 2 * nCols <= end && len < (1u << 24)) {
+    u32 total = 0, bad = 0, nextKey = 0, seenA = 0; bool unk = false;
     for (u32 i = 0; i < nCols; i++) {
       const u32 id = src.ld(dirPos + 2 * i), l = src.ld(dirPos + 2 * i + 1);
-      if ((id | l) & 0x80u) { fastWalk = false; break; }
-      if (lastId != 0xffffffffu && (id & ~8u) <= (lastId & ~8u)) orderBad = true;
-      lastId = id;
-      const u32 pos = dataPos + total;
-      if (!colErr) { if (id & 8u) colErr = KE_COL_DEFLATE; else if (pos + l > end) colErr = KE_SUBARRAY; }
-      const int ix = slots.index(id);
-      if (ix < 0) o.unknownCols = true;
-      else {
-        if (ix == CX_ACTION) { actOff = total; actLen = l; haveAct = true; } else if (ix == CX_PRED_NUM) { pnOff = total; pnLen = l; }
-        if (ix == CX_VAL_RAW) { if (afterValLen) { valOff = pos; rawLen = l; } }
-        else if (single && !colErr && ix != CX_CHLD_ACTOR && ix != CX_CHLD_CTR) {
-          u32 v = 0, used = 0; bool isNull = false;
-          if (!single_value(src, ix, pos, l, v, isNull, used)) single = false;
-          else { slots.put(ix, isNull ? NULL32 : v); seen |= 1u << ix; if (ix == CX_KEY_STR) keyStrPos = pos + 2; }
-        }
-      }
-      afterValLen = ix == CX_VAL_LEN;
+      bad |= (id | l) & 0x80u; bad |= id & 8u;
+      if (id < nextKey) bad = 1;   // (no deflate bits among accepted ids: the plain compare is the reference's)
+      nextKey = id + 1;
+      const int ix = slots.index(id & 127u);
+      if (ix < 0) unk = true; else { slots.put(ix, ((dataPos + total - off) << 8) | l); seenA |= 1u << ix; }
       total += l;
     }
-    if (fastWalk) { if (orderBad) dirErr = KE_COL_ORDER; else if (colErr) dirErr = colErr; }
+    if (!bad && dataPos + total <= end) {
+      bool ok = (seenA >> CX_ACTION) & 1u; u32 v = 0;
+#define AMG_FAST_COL(IX) if (ok && ((seenA >> IX) & 1u)) { const u32 w = slots.get(IX); if (fast_value<IX>(src, off + (w >> 8), w & 0xffu, v)) slots.put(IX, v); else ok = false; }
+      AMG_FAST_COL(CX_ACTION)
+      AMG_FAST_COL(CX_OBJ_ACTOR) AMG_FAST_COL(CX_OBJ_CTR) AMG_FAST_COL(CX_KEY_ACTOR) AMG_FAST_COL(CX_KEY_CTR)
+      if (ok && ((seenA >> CX_KEY_STR) & 1u)) { const u32 w = slots.get(CX_KEY_STR); keyStrPos = off + (w >> 8) + 2; if (fast_value<CX_KEY_STR>(src, off + (w >> 8), w & 0xffu, v)) slots.put(CX_KEY_STR, v); else ok = false; }
+      AMG_FAST_COL(CX_INSERT) AMG_FAST_COL(CX_VAL_LEN) AMG_FAST_COL(CX_PRED_NUM) AMG_FAST_COL(CX_PRED_ACTOR) AMG_FAST_COL(CX_PRED_CTR)
+#undef AMG_FAST_COL
+      if (ok) {
+        if (((seenA >> CX_VAL_RAW) & 1u) && ((seenA >> CX_VAL_LEN) & 1u)) { const u32 w = slots.get(CX_VAL_RAW); valOff = off + (w >> 8); rawLen = w & 0xffu; }
+        const u32 pn = (seenA >> CX_PRED_NUM) & 1u ? slots.get(CX_PRED_NUM) : NULL32, predNum = pn == NULL32 ? 0 : pn;
+        const u32 vl = (seenA >> CX_VAL_LEN) & 1u ? slots.get(CX_VAL_LEN) : NULL32;
+        if (predNum > 1 || (vl == NULL32 ? 0u : (vl >> 4)) > rawLen) ok = false;
+        if (predNum == 0 && (seenA & ((1u << CX_PRED_ACTOR) | (1u << CX_PRED_CTR)))) ok = false;
+        if (ok) {
+          o.h.depsOff = depsOff; o.h.actorOff = actorOff; o.h.actorLen = actorLen; o.h.otherOff = otherOff; o.h.dirOff = dirPos; o.h.dataOff = dataPos;
+          o.h.startOp = startOp; o.h.seq = seq;
+          o.nDeps = nDeps; o.nOther = nOther; o.nOps = 1; o.nPreds = predNum; o.single = true; o.unknownCols = unk;
+          o.seen = seenA & ~((1u << CX_VAL_RAW) | (1u << CX_CHLD_ACTOR) | (1u << CX_CHLD_CTR)); o.keyStrPos = (seenA >> CX_KEY_STR) & 1u ? keyStrPos : 0; o.valOff = valOff;
+          return;
+        }
+      }
+      keyStrPos = 0; valOff = 0; rawLen = 0;
+    }
   }
   if (!fastWalk) {   // general walk: ids / lengths of any size; the end of the directory is guessed (2 bytes per entry) and the walk repeated once with the real one
     o.unknownCols = false;
@@ -834,7 +881,7 @@ template <class S> DEV void decode_tile_body(const DecodeTilesArgs& a, const S& 
   if (live) finish_change(a, src, slots, c, pc, sat31(sBase[0] + wo + io - vo), sat31(sBase[1] + wp + ip - vp));
 }
 __global__ void __launch_bounds__(DT_THREADS, AMG_DT_MINBLOCKS) k_decode_tiles(const DecodeTilesArgs a) {
-  __shared__ __align__(128) u8 stage[DT_STAGE];
+  __shared__ __align__(128) u8 stage[DT_STAGE + 16];   // (+16: fast_value may read one byte past a change that ends at the window's end)
   __shared__ __align__(8) unsigned long long bar;
   __shared__ u32 sLo, sHi; __shared__ u64 sWarp[2][DT_THREADS / 32]; __shared__ u64 sBase[2];
   __shared__ u32 sSlots[NCOLS][DT_THREADS]; __shared__ signed char sLut[128];   // ColSlots<SmemSrc>

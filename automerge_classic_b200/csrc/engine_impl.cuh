@@ -302,7 +302,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       inflate_changes(ctx, 0, arena.p, chOff.p, chLen.p, deflList.p, nd, inflLen.p, nullptr, 0, origOff, origLen, errWord.p);
       scan_exclusive(ctx, scanTmp, inflLen.p, inflOff.p, nd);
       const size_t extra = readU32(inflOff.p + nd);
-      { u64 ew0 = 0; d2h(ctx, &ew0, errWord.p, 8); sync(ctx); if (ew0) throwKernelError(ew0, actorIds); }
+      if (errSnapshot) throwKernelError(errSnapshot, actorIds);   // (the error word travels with every small read)
       if ((u64)cur + extra + 64 >= 0xfff00000ULL) throw Error(AMG_ERR_UNSUPPORTED, "amgpu: change arena limited to 4 GiB per document");
       const size_t extraStart = cur; cur += extra;
       side_join(ctx);   // the arena may move: nothing may still be reading it
@@ -672,18 +672,23 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       emit.ensure(ctx, B + 1); slot.ensure(ctx, B + 2); objStart.ensure(ctx, B + 1);
       foreach(ctx, B, HeadFlag2Kernel{applied.p, isDep.p, numApplied, emit.p});
       scan_exclusive(ctx, scanTmp, emit.p, slot.p, B);
-      const u32 nh = readU32(slot.p + B);
       foreach(ctx, B, CompactKernel{emit.p, slot.p, objStart.p});
-      std::vector<u32> hb(nh); d2h(ctx, hb.data(), objStart.p, nh * 4);
-      std::vector<u32> oldDep(headIdx.size());
-      for (size_t i = 0; i < headIdx.size(); i++) d2h(ctx, &oldDep[i], isDep.p + headIdx[i], 4);
-      sync(ctx);
+      // one round trip for the whole answer (HeadsPackKernel); a second one only if the call leaves more heads than the block holds
+      const u32 nOld = (u32)headIdx.size(); u32 cap = 64, nh = 0; std::vector<u32> pack;
+      headsPack.ensure(ctx, nOld + 1);
+      if (nOld) h2d(ctx, headsPack.p, headIdx.data(), nOld * 4);
+      for (;;) {
+        const size_t words = 1 + (size_t)nOld + 9 * (size_t)cap;
+        headsOut.ensure(ctx, words + 1); pack.resize(words);
+        foreach(ctx, std::max<size_t>(std::max<size_t>(nOld, cap), 1), HeadsPackKernel{slot.p + B, objStart.p, hashes.p + numApplied * 32, appRank.p, isDep.p, headsPack.p, nOld, cap, headsOut.p});
+        d2h(ctx, pack.data(), headsOut.p, words * 4); sync(ctx);
+        nh = pack[0];
+        if (nh <= cap) break;
+        cap = nh;
+      }
       std::vector<std::array<u8, 32>> hs; std::vector<u32> hi;
-      for (size_t i = 0; i < headIdx.size(); i++) if (!oldDep[i]) { hs.push_back(heads[i]); hi.push_back(headIdx[i]); }
-      std::vector<u32> rankOfB(nh); std::vector<std::array<u8, 32>> newHeads(nh);
-      for (u32 k = 0; k < nh; k++) { d2h(ctx, newHeads[k].data(), hashes.p + (numApplied + hb[k]) * 32, 32); d2h(ctx, &rankOfB[k], appRank.p + hb[k], 4); }
-      if (nh) sync(ctx);   // one round trip for all of them
-      for (u32 k = 0; k < nh; k++) { hs.push_back(newHeads[k]); hi.push_back((u32)(numApplied + rankOfB[k])); }
+      for (u32 i = 0; i < nOld; i++) if (!pack[1 + i]) { hs.push_back(heads[i]); hi.push_back(headIdx[i]); }
+      for (u32 k = 0; k < nh; k++) { const u32* e = pack.data() + 1 + nOld + 9 * (size_t)k; std::array<u8, 32> h; memcpy(h.data(), e, 32); hs.push_back(h); hi.push_back((u32)(numApplied + e[8])); }
       std::vector<size_t> o(hs.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i;
       std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return hs[a] < hs[b]; });
       headsNow.clear(); headIdxNow.clear(); for (size_t i : o) { headsNow.push_back(hs[i]); headIdxNow.push_back(hi[i]); }

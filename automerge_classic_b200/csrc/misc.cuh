@@ -79,6 +79,21 @@ struct SeqMonoKernel {
 // heads (new.js:1582-1583): every dependency of an applied change stops being a head
 struct MarkDepsKernel { const u8* applied; const u32* nDeps; const u32* depBase; const u32* depIdx; u32* isDep; HD void operator()(size_t b) const { if (!applied[b]) return; for (u32 j = 0; j < nDeps[b]; j++) { const u32 d = depIdx[depBase[b] + j]; if (d != DEP_MISSING) isDep[d] = 1; } } };
 struct HeadFlag2Kernel { const u8* applied; const u32* isDep; size_t numApplied; u32* flag; HD void operator()(size_t b) const { flag[b] = (applied[b] && !isDep[numApplied + b]) ? 1u : 0u; } };
+// The heads of a call travel back in one block of 32-bit words: [0] = number of new heads, [1 .. nOld] = "became a dependency"
+// per old head, then per new head (the first `cap` of them) its 32 hash bytes and its rank among the applied changes.
+struct HeadsPackKernel {
+  const u32* count /* number of new heads */; const u32* list /* their batch indexes */; const u8* batchHashes; const u32* appRank; const u32* isDep; const u32* oldIdx; u32 nOld, cap; u32* out;
+  HD void operator()(size_t k) const {
+    const u32 nh = *count;
+    if (k == 0) out[0] = nh;
+    if (k < nOld) out[1 + k] = isDep[oldIdx[k]];
+    if (k < cap && k < nh) {
+      const u32 b = list[k]; const u32* h = reinterpret_cast<const u32*>(batchHashes + (size_t)b * 32); u32* o = out + 1 + nOld + 9 * k;
+      for (int j = 0; j < 8; j++) o[j] = h[j];
+      o[8] = appRank[b];
+    }
+  }
+};
 struct CompactKernel { const u32* flag; const u32* slot; u32* out; HD void operator()(size_t i) const { if (flag[i]) out[slot[i]] = (u32)i; } };
 struct HashGatherKernel { const u8* src; const u8* applied; const u32* appRank; u8* dst; HD void operator()(size_t b) const { if (!applied[b]) return; const u64* s = reinterpret_cast<const u64*>(src + b * 32); u64* d = reinterpret_cast<u64*>(dst + (size_t)appRank[b] * 32); d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; } };
 // (offset, length) of the changes of a packed batch straight from the caller's offsets array (device copy)
