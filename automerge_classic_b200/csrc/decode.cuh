@@ -782,7 +782,11 @@ struct DecodeTilesArgs {
   RawRows rows; u32 rowCap, predCap;   // rows are written only inside the capacity; totals[2] tells the host to grow and run again
   unsigned long long* cursor /* [0] ops, [1] preds handed out so far */;
   u32* totals /* [2] overflow [3] bit 0: some change has > SMALL_CHANGE_OPS ops, bit 1: some change has a column with an unknown id; [0] ops and [1] preds are filled from the cursor by k_decode_totals */; u64* errWord; u32 numTiles;
-  u32* directList /* [B] changes the staged kernel could not take (outside their tile's staged window) */; u32* directCount;
+  u32* directList /* [B] changes the staged kernel could not take (outside their tile's staged window) */; u32* directCount /* [1] = CTAs of k_decode_direct that are done */;
+  // A launch walks changes first .. B-1 of the batch, perTile per CTA - or, with a list, the changes list[first .. B-1] (the
+  // DEFLATEd changes once they are inflated: their bytes lie behind the batch, in list order). A launch without a list leaves
+  // out the changes at or behind skipFrom (arena offset): those belong to the list launch.
+  const u32* list = nullptr; u32 perTile = 0; u32 skipFrom = 0xffffffffu;
 };
 // what one thread does with its change once the row range is known
 template <class S> HD void finish_change(const DecodeTilesArgs& a, const S& src, const ColSlots<S>& slots, u32 c, const ParsedChange& pc, u32 base, u32 pb) {
@@ -817,6 +821,7 @@ inline void decode_tiles_range(Ctx& c, DecodeTilesArgs a, u32 first, u32 end) {
   }
   c.launches++;
 }
+inline void decode_tiles_list(Ctx&, DecodeTilesArgs, const u32*, u32, u32 = 32) {}   // (the emulation's range walk lists DEFLATEd changes for the finish step)
 inline void decode_tiles_finish(Ctx& c, const DecodeTilesArgs& a, size_t) {
   for (u32 k = 0; k < *a.directCount; k++) {
     const u32 i = a.directList[k];
@@ -893,16 +898,21 @@ __global__ void __launch_bounds__(DT_THREADS, AMG_DT_MINBLOCKS) k_decode_tiles(c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const u32 c = a.first + blockIdx.x * DT_THREADS + tid; bool live = c < a.B;
-  const u32 off = live ? a.chOff[c] : 0xffffffffu, len = live ? a.chLen[c] : 0;
-  // the staged window starts at the tile's lowest offset; changes that do not lie inside it (inflated changes live behind
-  // the batch, a big change may not fit) are passed on to k_decode_direct one by one
+  const u32 i = a.first + blockIdx.x * a.perTile + tid; const bool valid = (u32)tid < a.perTile && i < a.B;
+  const u32 c = valid ? (a.list ? a.list[i] : i) : 0u;
+  u32 off = valid ? a.chOff[c] : 0xffffffffu; const u32 len = valid ? a.chLen[c] : 0;
+  bool live = valid && (a.list || off < a.skipFrom);   // (else: a change of the list launch)
+  if (!live) off = 0xffffffffu;
+  // the staged window starts at the tile's lowest offset; changes that do not lie inside it (a big change may not fit, queue
+  // entries may lie anywhere) are passed on to k_decode_direct one by one
   { const u32 lo = __reduce_min_sync(0xffffffffu, off); if (lane == 0) atomicMin(&sLo, lo); }
   __syncthreads();
   const u32 lo16 = sLo & ~15u;
   const bool inWindow = live && (u64)off + len <= (u64)lo16 + DT_STAGE;
   { const u32 hi = __reduce_max_sync(0xffffffffu, inWindow ? off + len : 0u); if (lane == 0 && hi) atomicMax(&sHi, hi); }
   __syncthreads();
+  bool defer = live && !inWindow;
+  if (defer && !a.list && len > 8 && a.arena[off + 8] == 2 && a.arena[off] == 0x85) defer = false;   // DEFLATEd and outside the window: the list launch takes it, like every DEFLATEd change
   live = inWindow;
   if (sHi > lo16) {
     if (tid == 0) {
@@ -915,9 +925,8 @@ __global__ void __launch_bounds__(DT_THREADS, AMG_DT_MINBLOCKS) k_decode_tiles(c
     while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_addr(&bar)) : "memory");
   }
   const SmemSrc ssrc{smem_addr(stage) - lo16, smem_addr(sLut), smem_addr(&sSlots[0][tid])};
-  // DEFLATEd changes (chunk type 2, columnar.js:742) are inflated later in the call: decoded by k_decode_direct then
+  // DEFLATEd changes (chunk type 2, columnar.js:742) are inflated later in the call and decoded by the list launch then
   const bool deflated = live && len > 8 && ssrc.ld(off + 8) == 2 && ssrc.ld(off) == 0x85;
-  const bool defer = (c < a.B && !inWindow) || deflated;
   if (defer) {
     const unsigned peers = __activemask(); const int leader = __ffs(peers) - 1; u32 base = 0;
     if (lane == leader) base = atomicAdd(a.directCount, (u32)__popc(peers));
@@ -927,7 +936,8 @@ __global__ void __launch_bounds__(DT_THREADS, AMG_DT_MINBLOCKS) k_decode_tiles(c
   live = live && !deflated;
   decode_tile_body(a, ssrc, c, live, off, len, sWarp, sBase);
 }
-// the changes the staged kernel passed on: same steps, one thread per listed change, bytes read from global memory
+// the changes the staged kernel passed on: same steps, one thread per listed change, bytes read from global memory. The last
+// CTA to finish turns the cursor into the totals (+ overflow when the reserved rows of larger changes do not fit).
 __global__ void __launch_bounds__(DT_THREADS) k_decode_direct(const DecodeTilesArgs a) {
   __shared__ u64 sWarp[2][DT_THREADS / 32]; __shared__ u64 sBase[2];
   const u32 n = *a.directCount;
@@ -936,32 +946,39 @@ __global__ void __launch_bounds__(DT_THREADS) k_decode_direct(const DecodeTilesA
     decode_tile_body(a, PtrSrc{a.arena}, c, live, live ? a.chOff[c] : 0u, live ? a.chLen[c] : 0u, sWarp, sBase);
     __syncthreads();
   }
-}
-static __global__ void k_decode_totals(const DecodeTilesArgs a) {   // cursor -> totals (+ overflow when the reserved rows of larger changes do not fit)
-  if (threadIdx.x) return;
-  const u64 ops = a.cursor[0], preds = a.cursor[1];
-  a.totals[0] = sat31(ops); a.totals[1] = sat31(preds);
-  if (ops > a.rowCap || preds > a.predCap) a.totals[2] = 1;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.directCount + 1, 1u) == gridDim.x - 1) {
+      const u64 ops = atomicAdd(&a.cursor[0], 0ULL), preds = atomicAdd(&a.cursor[1], 0ULL);
+      a.totals[0] = sat31(ops); a.totals[1] = sat31(preds);
+      if (ops > a.rowCap || preds > a.predCap) a.totals[2] = 1;
+    }
+  }
 }
 // begin (clears cursor / counters) -> any number of ranges (each as soon as its bytes are on the device) -> finish
 inline void decode_tiles_begin(Ctx& c, const DecodeTilesArgs& a) {
-  CUDA_CHECK(cudaMemsetAsync(a.cursor, 0, 16, c.stream));
-  CUDA_CHECK(cudaMemsetAsync(a.totals, 0, 16, c.stream));
-  CUDA_CHECK(cudaMemsetAsync(a.directCount, 0, 4, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(a.cursor, 0, 64, c.stream));   // cursor, totals, direct count, done count: one block (Engine::decodeArgs)
 }
 inline void decode_tiles_range(Ctx& c, DecodeTilesArgs a, u32 first, u32 end) {
   if (end <= first) return;
-  a.first = first; a.B = end;
+  a.first = first; a.B = end; a.list = nullptr; a.perTile = DT_THREADS;
   k_decode_tiles<<<(end - first + DT_THREADS - 1) / DT_THREADS, DT_THREADS, 0, c.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  c.launches++;
+}
+// the inflated changes list[0 .. n): larger than the rest (only changes of 256 bytes and more are compressed), so fewer per tile
+inline void decode_tiles_list(Ctx& c, DecodeTilesArgs a, const u32* list, u32 n, u32 perTile = 32) {
+  if (n == 0) return;
+  a.first = 0; a.B = n; a.list = list; a.perTile = perTile;
+  k_decode_tiles<<<(n + perTile - 1) / perTile, DT_THREADS, 0, c.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   c.launches++;
 }
 inline void decode_tiles_finish(Ctx& c, const DecodeTilesArgs& a, size_t numChanges) {
   const size_t tiles = (numChanges + DT_THREADS - 1) / DT_THREADS;
-  k_decode_direct<<<(unsigned)std::max<size_t>(1, std::min<size_t>(tiles, (size_t)c.numSMs * 8)), DT_THREADS, 0, c.stream>>>(a);
-  k_decode_totals<<<1, 32, 0, c.stream>>>(a);
+  k_decode_direct<<<(unsigned)std::max<size_t>(1, std::min<size_t>(tiles, (size_t)c.numSMs * 2)), DT_THREADS, 0, c.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
-  c.launches += 2;
+  c.launches++;
 }
 #endif
 

@@ -96,7 +96,8 @@ class Engine {
   // ---- scratch (grow-only)
   DBuf<u32> chOff, chLen, nOps, nPreds, nDeps, nActors, colOff, colLen, depBase, depIdx, primary, pass, flagWord, appRank, opBase, predBase, timeBase, amapBase, amap, authorSlot, newSlots;
   DBuf<u8> applied; DBuf<ChangeHot> hot; DBuf<ChangeMeta> meta /* save(): full headers */; DBuf<u64> errWord; DBuf<u32> hashTable;
-  DBuf<u32> rawBase, rawPredBase, decErr, decTotals, decDirect; DBuf<u64> decCursor;
+  DBuf<u32> rawBase, rawPredBase, decErr, decDirect; DBuf<u64> decCursor; size_t lastDeflCount = 0, lastDeflStart = 0;
+  u32* decTotalsPtr() { return reinterpret_cast<u32*>(decCursor.p + 2); }
   DBuf<u32> patchByteLen, patchByteOff; DBuf<u8> patchBytesD;   // key / value bytes shipped inside the patch   // fused decode (decode.cuh k_decode_tiles)
   DBuf<u32> r_objActor, r_objCtr, r_keyActor, r_keyCtr, r_keyStrOff, r_keyStrLen, r_insert, r_action, r_valLen, r_valOff, r_predNum, r_predOff, r_predActor, r_predCtr;
   DBuf<u64> o_id, o_obj, o_key, o_predId; DBuf<u32> o_keyStrOff, o_keyStrLen, o_flags, o_valLen, o_valOff, o_predOff, o_predNum, o_change, o_time;
@@ -288,7 +289,7 @@ class Engine {
   void appendUnknownDocColumns(std::vector<std::pair<u32, std::string>>& cols);   // save(): their document columns
   RawRows rawRows();
   u32 decodeHugeChanges(const RawRows& raw, size_t numLarge); DBuf<u32> hugeDone;
-  void runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes);
+  void runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes, const u32* deflListP = nullptr, size_t numDefl = 0, size_t deflStart = 0);
   DecodeTilesArgs decodeArgs(const u8* arenaP, size_t B, size_t batchBytes);
   // Host mirror of the arena, filled on demand: hostArena holds arena[0, hostArena.size()); whatever is missing is fetched
   // from the device when a reader (getChanges, amg_arena, clone ...) asks for it.

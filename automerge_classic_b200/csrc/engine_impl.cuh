@@ -316,7 +316,8 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     }
   }
   // changes the tile kernel passed on (inflated ones, changes outside their tile's window), then the totals
-  { DecodeTilesArgs fin = dargs; fin.arena = arena.p; decode_tiles_finish(ctx, fin, B); }
+  { DecodeTilesArgs fin = dargs; fin.arena = arena.p; decode_tiles_list(ctx, fin, deflList.p, (u32)inflNd); decode_tiles_finish(ctx, fin, B); }
+  lastDeflCount = inflNd; lastDeflStart = inflExtraStart;
   dbgMark("decode:finish-enqueued");
   side_join(ctx);
   timer.mark(); hostMark(); nvtx.next("gate");
@@ -341,12 +342,12 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     foreach(ctx, B, RelaxKernel{depBase.p, depIdx.p, nDeps.p, primary.p, numApplied, pass.p, flagWord.p, (u32)B + 1});
     u32 again = 0, copies = 0;
     { void* dst[6] = {&again, &copies, &decTot[0], &decTot[1], &decTot[2], &decTot[3]};
-      readWords({{flagWord.p, 4}, {flagWord.p + 12, 4}, {decTotals.p, 4}, {decTotals.p + 1, 4}, {decTotals.p + 2, 4}, {decTotals.p + 3, 4}}, dst); }
+      readWords({{flagWord.p, 4}, {flagWord.p + 12, 4}, {decTotalsPtr(), 4}, {decTotalsPtr() + 1, 4}, {decTotalsPtr() + 2, 4}, {decTotalsPtr() + 3, 4}}, dst); }
     checkErr(actorIds);   // free: the error word came with the read
     if (iter == 0 && decodeOverflowed(decTot)) {   // the raw row tables were too small for this batch: grown, decoded again (same results otherwise)
-      runDecodeTiles(arena.p, B, cur - arenaLen0);   // the whole batch is resident by now (inflated changes re-pointed)
+      runDecodeTiles(arena.p, B, cur - arenaLen0, deflList.p, inflNd, inflExtraStart);   // the whole batch is resident by now (inflated changes re-pointed)
       void* d2[4] = {&decTot[0], &decTot[1], &decTot[2], &decTot[3]};
-      readWords({{decTotals.p, 4}, {decTotals.p + 1, 4}, {decTotals.p + 2, 4}, {decTotals.p + 3, 4}}, d2);
+      readWords({{decTotalsPtr(), 4}, {decTotalsPtr() + 1, 4}, {decTotalsPtr() + 2, 4}, {decTotalsPtr() + 3, 4}}, d2);
       if (decTot[2]) throw Error(AMG_ERR_INTERNAL, "amgpu: decode row tables overflowed twice");
     }
     if (!copiesChecked) { copiesChecked = true; haveCopies = copies != 0; }
@@ -1009,18 +1010,23 @@ inline RawRows Engine::rawRows() {
 // what earlier calls needed (else from the batch size); the kernel never writes outside them and reports an overflow.
 inline DecodeTilesArgs Engine::decodeArgs(const u8* arenaP, size_t B, size_t batchBytes) {
   hot.ensure(ctx, B + 1); nOps.ensure(ctx, B + 1); nPreds.ensure(ctx, B + 1); nDeps.ensure(ctx, B + 1); nActors.ensure(ctx, B + 1);
-  rawBase.ensure(ctx, B + 2); rawPredBase.ensure(ctx, B + 2); decErr.ensure(ctx, B + 1); decTotals.ensure(ctx, 4);
-  decCursor.ensure(ctx, 2); decDirect.ensure(ctx, B + 2);
+  rawBase.ensure(ctx, B + 2); rawPredBase.ensure(ctx, B + 2); decErr.ensure(ctx, B + 1);
+  decCursor.ensure(ctx, 8); decDirect.ensure(ctx, B + 2);   // decCursor: one 64-byte block = cursor (2 x u64), totals (4 x u32), direct count, done count
   const size_t wantRows = std::max(decWantRows, B + B / 4 + batchBytes / 256 + 1024), wantPreds = std::max(decWantPreds, B + B / 4 + batchBytes / 256 + 1024);
   for (DBuf<u32>* b : {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff}) b->ensure(ctx, wantRows + 1);
   r_predActor.ensure(ctx, wantPreds + 1); r_predCtr.ensure(ctx, wantPreds + 1);
   decRowCap = wantRows; decPredCap = wantPreds;
   return DecodeTilesArgs{arenaP, chOff.p, chLen.p, (u32)B, 0u, hot.p, nOps.p, nPreds.p, nDeps.p, nActors.p, rawBase.p, rawPredBase.p, decErr.p, rawRows(), (u32)wantRows, (u32)wantPreds,
-                         (unsigned long long*)decCursor.p, decTotals.p, errWord.p, 0u, decDirect.p + 1, decDirect.p};
+                         (unsigned long long*)decCursor.p, decTotalsPtr(), errWord.p, 0u, decDirect.p, decTotalsPtr() + 4};
 }
-inline void Engine::runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes) {
-  const DecodeTilesArgs a = decodeArgs(arenaP, B, batchBytes);
-  decode_tiles_begin(ctx, a); decode_tiles_range(ctx, a, 0, (u32)B); decode_tiles_finish(ctx, a, B);
+// the whole batch in one go (bytes resident): the range launch, the list launch over the inflated changes (numDefl of them,
+// bytes from arena offset deflStart on), then the changes outside their tile's window
+inline void Engine::runDecodeTiles(const u8* arenaP, size_t B, size_t batchBytes, const u32* deflListP, size_t numDefl, size_t deflStart) {
+  DecodeTilesArgs a = decodeArgs(arenaP, B, batchBytes);
+  if (numDefl > 0) a.skipFrom = (u32)deflStart;
+  decode_tiles_begin(ctx, a); decode_tiles_range(ctx, a, 0, (u32)B);
+  if (numDefl > 0) decode_tiles_list(ctx, a, deflListP, (u32)numDefl);
+  decode_tiles_finish(ctx, a, B);
 }
 inline bool Engine::decodeOverflowed(const u32 totals[4]) {
   if (!totals[2]) return false;
@@ -1135,7 +1141,7 @@ inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* 
   cudaEventRecord(e[0], ctx.stream);
   for (int i = 0; i < iters; i++) foreach(ctx, B, ShaKernel{batchArena, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
   cudaEventRecord(e[1], ctx.stream);
-  for (int i = 0; i < iters; i++) runDecodeTiles(batchArena, B, lastBytes);
+  for (int i = 0; i < iters; i++) runDecodeTiles(batchArena, B, lastBytes, deflList.p, lastDeflCount, lastDeflStart);
   cudaEventRecord(e[2], ctx.stream);
   for (int i = 0; i < iters; i++) {
     if (lastNumLarge > 0) foreach(ctx, (size_t)NCOLS * lastNumLarge, DecodeColumnKernel{batchArena, largeList.p, lastNumLarge, hot.p, nOps.p, nPreds.p, rawBase.p, rawPredBase.p, applied.p, raw, errWord.p, nullptr});
@@ -1405,8 +1411,8 @@ inline void Engine::decodeRaw(const u8* blob, const u64* offsets, size_t n, u8* 
   applied.ensure(ctx, n); dev_memset(ctx, applied.p, 1, n);
   u32 tot[4] = {0, 0, 0, 0}; void* dst[4] = {&tot[0], &tot[1], &tot[2], &tot[3]};
   runDecodeTiles(ar.p, n, staged.size());
-  readWords({{decTotals.p, 4}, {decTotals.p + 1, 4}, {decTotals.p + 2, 4}, {decTotals.p + 3, 4}}, dst);
-  if (decodeOverflowed(tot)) { runDecodeTiles(ar.p, n, staged.size()); readWords({{decTotals.p, 4}, {decTotals.p + 1, 4}, {decTotals.p + 2, 4}, {decTotals.p + 3, 4}}, dst); }
+  readWords({{decTotalsPtr(), 4}, {decTotalsPtr() + 1, 4}, {decTotalsPtr() + 2, 4}, {decTotalsPtr() + 3, 4}}, dst);
+  if (decodeOverflowed(tot)) { runDecodeTiles(ar.p, n, staged.size()); readWords({{decTotalsPtr(), 4}, {decTotalsPtr() + 1, 4}, {decTotalsPtr() + 2, 4}, {decTotalsPtr() + 3, 4}}, dst); }
   checkErr(actorIds);
   const size_t M = tot[0];
   DBuf<u32>* cols[12] = {&r_objActor, &r_objCtr, &r_keyActor, &r_keyCtr, &r_keyStrOff, &r_keyStrLen, &r_insert, &r_action, &r_valLen, &r_valOff, &r_predNum, &r_predOff};
