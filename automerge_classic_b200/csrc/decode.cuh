@@ -221,6 +221,10 @@ HD u32 rotr32(u32 x, int n) {
   return (x >> n) | (x << (32 - n));
 #endif
 }
+// rotr(x,a) ^ rotr(x,b) ^ (SHIFT ? x >> c : rotr(x,c)): three funnel shifts and one LOP3. (Measured and dropped: the rotations
+// as halves of 64-bit products on the FMA pipe - IMAD.WIDE with multipliers from constant memory - to relieve the ALU pipe:
+// 0.59 ms instead of 0.42 ms for the 1M changes of C3.)
+template <int A, int B, int C, bool SHIFT> HD u32 sha_sigma(u32 x) { return rotr32(x, A) ^ rotr32(x, B) ^ (SHIFT ? (x >> C) : rotr32(x, C)); }
 // big-endian 32-bit load at an arbitrary byte address (two aligned loads + funnel shift on device)
 HD u32 load_be32(const u8* p) {
 #if defined(__CUDA_ARCH__)
@@ -242,11 +246,11 @@ template <bool SCHEDULE> HD void sha256_rounds16(u32& a, u32& b, u32& c, u32& d,
   for (int j = 0; j < 16; j++) {
     if (SCHEDULE) {
       const u32 w15 = w[(j + 1) & 15], w2 = w[(j + 14) & 15];
-      const u32 s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3), s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+      const u32 s0 = sha_sigma<7, 18, 3, true>(w15), s1 = sha_sigma<17, 19, 10, true>(w2);
       w[j] = w[j] + s0 + w[(j + 9) & 15] + s1;
     }
-    const u32 t1 = hh + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + K[j] + w[j];
-    const u32 t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+    const u32 t1 = hh + sha_sigma<6, 11, 25, false>(e) + ((e & f) ^ (~e & g)) + K[j] + w[j];
+    const u32 t2 = sha_sigma<2, 13, 22, false>(a) + ((a & b) ^ (a & c) ^ (b & c));
     hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
   }
 }
@@ -266,63 +270,103 @@ struct DeflateScanKernel {
     if (chLen[c] > 8 && p[8] == 2 && p[0] == 0x85) list[atomic_add(counter, (u64)1)] = (u32)c;
   }
 };
-// hashes arena[off+8 .. off+len) of every change; writes 32-byte digests; checks magic + checksum
+// Where the bytes of ONE change are read from when it is hashed: global (host, in the emulation) memory. byte(i) = byte i of the change; on the device word(k) = aligned 32-bit word k counted from
+// the aligned word that holds the first message byte (the message = bytes 8 ..), mis() = the message's misalignment.
+struct GlobalBytes {
+  const u8* p;
+  HD u32 byte(u32 i) const { return p[i]; }
+#if defined(__CUDA_ARCH__)
+  DEV u32 mis() const { return (u32)(reinterpret_cast<uintptr_t>(p + 8) & 3); }
+  DEV u32 word(u32 k) const { return reinterpret_cast<const u32*>(p + 8 - mis())[k]; }   // (pointer arithmetic on p: the loads stay global loads)
+#endif
+};
+// SHA-256 of bytes 8 .. len of change c (columnar.js:688-708: the hash covers everything behind the checksum); writes the
+// 32-byte digest, checks magic and checksum. DEFLATEd changes (chunk type 2, columnar.js:742) are left out when the caller
+// hashes them later, once they are inflated.
+template <class BS> HD void sha_change(const BS& bs, size_t c, u32 len, u8* hashOut, u64* errWord, bool deflatedLater) {
+  if (len > 8 && bs.byte(8) == 2 && bs.byte(0) == 0x85) {
+    if (!deflatedLater) raise(errWord, KE_CHUNK_TYPE, c);
+    return;
+  }
+  if (len < 10 || bs.byte(0) != 0x85 || bs.byte(1) != 0x6f || bs.byte(2) != 0x4a || bs.byte(3) != 0x83) { raise(errWord, KE_MAGIC, c); return; }
+#if defined(__CUDA_ARCH__)
+  const u32* K = c_sha.k;
+#else
+  const u32* K = SHA_K;
+#endif
+  u32 h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  const u32 mlen = len - 8;
+  // blocks: all full 64-byte blocks, then one or two padded blocks (0x80, zeros, 64-bit bit length). Message word i of a
+  // block = 4 bytes at an arbitrary address: two aligned 32-bit loads (the second is the next word's first), funnel shift,
+  // byte swap. Full blocks take the words as they are; in the padded blocks every word is masked by how many message bytes
+  // it still holds (branch-free), and no load reaches more than one word past the message.
+  const u32 nBlocks = (mlen + 9 + 63) / 64; u32 w[16];
+#if defined(__CUDA_ARCH__)
+  const u32 sh = bs.mis() * 8, lastAligned = (mlen + bs.mis() + 3) / 4;   // aligned words [0, lastAligned) hold message bytes
+#endif
+  for (u32 blk = 0; blk < nBlocks; blk++) {
+    const u32 done = blk * 64;
+#if defined(__CUDA_ARCH__)
+    const u32 k0 = done / 4;
+    if (done + 64 <= mlen) {
+      u32 lo = bs.word(k0);
+#pragma unroll
+      for (int i = 0; i < 16; i++) { const u32 hi = bs.word(k0 + i + 1); w[i] = __byte_perm(__funnelshift_r(lo, hi, sh), 0, 0x0123); lo = hi; }
+    } else {
+      u32 lo = bs.word(k0 < lastAligned ? k0 : lastAligned);
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const u32 k = k0 + i + 1, hi = bs.word(k < lastAligned ? k : lastAligned);
+        const u32 v = __byte_perm(__funnelshift_r(lo, hi, sh), 0, 0x0123);
+        const int rem = (int)mlen - (int)(done + 4 * i);   // message bytes from this word on
+        const u32 r8 = 8u * (u32)(rem < 0 ? 0 : (rem > 4 ? 4 : rem));
+        const u32 keep = ~__funnelshift_rc(0xffffffffu, 0u, r8), pad = rem < 0 ? 0u : __funnelshift_rc(0x80000000u, 0u, r8);
+        w[i] = (v & keep) | pad; lo = hi;
+      }
+    }
+#else
+    for (int i = 0; i < 16; i++) {
+      u32 v = 0;
+      for (int b = 0; b < 4; b++) { const u32 ix = done + 4 * i + b; u32 byte = 0; if (ix < mlen) byte = bs.byte(8 + ix); else if (ix == mlen) byte = 0x80; v = (v << 8) | byte; }
+      w[i] = v;
+    }
+#endif
+    if (blk == nBlocks - 1) { w[14] = (u32)(((u64)mlen * 8) >> 32); w[15] = (u32)((u64)mlen * 8); }
+    sha256_compress(h, w, K);
+  }
+  u8* out = hashOut + c * 32;
+#if defined(__CUDA_ARCH__)
+  uint4* o4 = reinterpret_cast<uint4*>(out);   // digests are 32-byte aligned
+  o4[0] = make_uint4(__byte_perm(h[0], 0, 0x0123), __byte_perm(h[1], 0, 0x0123), __byte_perm(h[2], 0, 0x0123), __byte_perm(h[3], 0, 0x0123));
+  o4[1] = make_uint4(__byte_perm(h[4], 0, 0x0123), __byte_perm(h[5], 0, 0x0123), __byte_perm(h[6], 0, 0x0123), __byte_perm(h[7], 0, 0x0123));
+#else
+  for (int i = 0; i < 8; i++) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }
+#endif
+  if (h[0] != ((bs.byte(4) << 24) | (bs.byte(5) << 16) | (bs.byte(6) << 8) | bs.byte(7))) raise(errWord, KE_CHECKSUM, c);
+}
+// one change per thread, bytes read where they lie
 struct ShaKernel {
   const u8* arena; const u32* chOff; const u32* chLen; u8* hashOut /* [n][32] */; u64* errWord; const u32* subset /* optional: only these changes */; u32* deflList /* non-null: DEFLATEd changes are skipped (hashed once inflated) */;
   size_t first = 0;   // items are changes first, first + 1, ...
   HD void operator()(size_t ci) const {
     const size_t c = subset ? subset[ci] : first + ci;
-    const u8* p = arena + chOff[c]; const u32 len = chLen[c];
-    if (len > 8 && p[8] == 2 && p[0] == 0x85) {   // DEFLATEd change (columnar.js:742): listed for the host, which inflates it and re-points this entry
-      if (!deflList) raise(errWord, KE_CHUNK_TYPE, c);   // with a list: skipped here, hashed again once the host has inflated it
-      return;
-    }
-    if (len < 10 || p[0] != 0x85 || p[1] != 0x6f || p[2] != 0x4a || p[3] != 0x83) { raise(errWord, KE_MAGIC, c); return; }
-#if defined(__CUDA_ARCH__)
-    const u32* K = c_sha.k;
-#else
-    const u32* K = SHA_K;
-#endif
-    u32 h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
-    const u8* m = p + 8; const u32 mlen = len - 8;
-    // blocks: all full 64-byte blocks, then one or two padded blocks (0x80, zeros, 64-bit bit length); one call site.
-    // Message word i of a block = 4 bytes at an arbitrary address: two aligned 32-bit loads (the second is the next word's
-    // first), funnel shift, byte swap; words that reach past the message end are masked, never loaded past it.
-    const u32 nBlocks = (mlen + 9 + 63) / 64; u32 w[16];
-#if defined(__CUDA_ARCH__)
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
-    const u32* aw = reinterpret_cast<const u32*>(m - (addr & 3)); const u32 sh = (u32)(addr & 3) * 8;   // (pointer arithmetic on m: the loads stay global loads)
-    const u32 lastAligned = (mlen + (u32)(addr & 3) + 3) / 4;   // aligned words [0, lastAligned) hold message bytes
-#endif
-    for (u32 blk = 0; blk < nBlocks; blk++) {
-      const u32 done = blk * 64;
-#if defined(__CUDA_ARCH__)
-      const u32 k0 = done / 4;
-      u32 lo = k0 < lastAligned ? aw[k0] : 0u;
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const u32 hi = (k0 + i + 1 < lastAligned) ? aw[k0 + i + 1] : 0u;
-        u32 v = __byte_perm(__funnelshift_r(lo, hi, sh), 0, 0x0123);
-        const int rem = (int)mlen - (int)(done + 4 * i);   // message bytes from this word on
-        if (rem < 4) v = rem <= 0 ? (rem == 0 ? 0x80000000u : 0u) : ((v & (0xffffffffu << (32 - 8 * rem))) | (0x80u << (24 - 8 * rem)));
-        w[i] = v; lo = hi;
-      }
-#else
-      for (int i = 0; i < 16; i++) {
-        u32 v = 0;
-        for (int b = 0; b < 4; b++) { const u32 ix = done + 4 * i + b; u32 byte = 0; if (ix < mlen) byte = m[ix]; else if (ix == mlen) byte = 0x80; v = (v << 8) | byte; }
-        w[i] = v;
-      }
-#endif
-      if (blk == nBlocks - 1) { w[14] = (u32)(((u64)mlen * 8) >> 32); w[15] = (u32)((u64)mlen * 8); }
-      sha256_compress(h, w, K);
-    }
-    u8* out = hashOut + c * 32;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }
-    if (out[0] != p[4] || out[1] != p[5] || out[2] != p[6] || out[3] != p[7]) raise(errWord, KE_CHECKSUM, c);
+    sha_change(GlobalBytes{arena + chOff[c]}, c, chLen[c], hashOut, errWord, deflList != nullptr);
   }
 };
+
+#ifndef AMG_SHA_MINBLOCKS
+#define AMG_SHA_MINBLOCKS 3
+#endif
+template <> struct LaunchTraits<ShaKernel> { static const int minBlocks = AMG_SHA_MINBLOCKS; };
+// ---- SHA-256 of the changes first .. end-1 of a batch: one thread per change, bytes read where they lie (ShaKernel). (Measured
+// and dropped: staging a tile's bytes in shared memory like the decode does - 0.52 ms instead of 0.42 ms on C3: the kernel is
+// bound by the rounds on the ALU pipe, not by its loads.)
+struct ShaTilesArgs { const u8* arena; const u32* chOff; const u32* chLen; u8* hashOut; u64* errWord; u32* deflList /* non-null: DEFLATEd changes are hashed later */; u32 first, end; };
+inline void sha_range(Ctx& c, const ShaTilesArgs& a, bool onSide) {
+  if (a.end <= a.first) return;
+  ShaKernel sk{a.arena, a.chOff, a.chLen, a.hashOut, a.errWord, nullptr, a.deflList}; sk.first = a.first;
+  foreach(c, a.end - a.first, sk, onSide);
+}
 
 // number of values in an RLE column (record-level: runs are not expanded); *err receives a KErr
 template <class S> HD u32 rle_count_values_t(const S& src, u32 off, u32 end, u32* err) {
@@ -1010,10 +1054,6 @@ struct DecodeColumnKernel {
 #define AMG_PARSE_MINBLOCKS 4
 #endif
 template <> struct LaunchTraits<ParseKernel> { static const int minBlocks = AMG_PARSE_MINBLOCKS; };
-#ifndef AMG_SHA_MINBLOCKS
-#define AMG_SHA_MINBLOCKS 3
-#endif
-template <> struct LaunchTraits<ShaKernel> { static const int minBlocks = AMG_SHA_MINBLOCKS; };
 struct LargeFlagKernel { const u32* nOps; const u8* applied; u32* flag; HD void operator()(size_t c) const { flag[c] = (applied[c] && nOps[c] > SMALL_CHANGE_OPS) ? 1u : 0u; } };
 
 }  // namespace amg

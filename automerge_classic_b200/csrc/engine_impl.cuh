@@ -184,11 +184,18 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   pairStage.ensure(B + 1); HostChange* pairs = pairStage.p;   // pinned: the table goes up by DMA while the host carries on
   if (blob && n > 0) {
     const size_t base = offsets[0];
-    for (size_t o = kPiece;; o += kPiece) {
-      if (o >= total) { pieces.push_back({total, n, 0}); break; }
-      const size_t ce = (size_t)(std::upper_bound(offsets, offsets + n + 1, (u64)(base + o)) - offsets) - 1;   // changes that end inside the first o bytes
-      pieces.push_back({(size_t)(offsets[ce] - base), ce, 0});
+    // cut points: every kPiece bytes, the tail halved three more times - what is left to hash and decode once the last byte
+    // has arrived is a piece of a few MB, not a whole one
+    std::vector<size_t> cuts; size_t o = kPiece;
+    for (; o < total && total - o > kPiece; o += kPiece) cuts.push_back(o);
+    if (total > 0) { const size_t from = o - kPiece; size_t rest = total - from; for (int k = 0; k < 3 && rest > (2u << 20); k++) { rest /= 2; cuts.push_back(total - rest); } }
+    size_t lastCe = 0;
+    for (size_t c : cuts) {
+      const size_t ce = (size_t)(std::upper_bound(offsets, offsets + n + 1, (u64)(base + c)) - offsets) - 1;   // changes that end inside the first c bytes
+      if (ce <= lastCe || ce >= n) continue;
+      pieces.push_back({(size_t)(offsets[ce] - base), ce, 0}); lastCe = ce;
     }
+    pieces.push_back({total, n, 0});
   } else {
     size_t at = 0, nextCut = kPiece;
     for (size_t i = 0; i < n; i++) {
@@ -258,8 +265,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     if (c1 <= c0) return;
     if (waitCopy) copy_piece_wait(ctx, mark);   // both streams wait for the piece
     else side_fork(ctx);
-    ShaKernel sk{arena.p, chOff.p, chLen.p, hashOut, errWord.p, nullptr, deflList.p}; sk.first = c0;
-    foreach(ctx, c1 - c0, sk, true);
+    sha_range(ctx, ShaTilesArgs{arena.p, chOff.p, chLen.p, hashOut, errWord.p, deflList.p, (u32)c0, (u32)c1}, true);
     decode_tiles_range(ctx, dargs, (u32)c0, (u32)c1);
   };
   side_fork(ctx);   // the side stream is ordered behind the tables
@@ -1139,7 +1145,7 @@ inline void Engine::benchDecode(int iters, float* msSha, float* msParse, float* 
   cudaEvent_t e[4]; for (auto& x : e) cudaEventCreate(&x);
   const u8* batchArena = arena.p;
   cudaEventRecord(e[0], ctx.stream);
-  for (int i = 0; i < iters; i++) foreach(ctx, B, ShaKernel{batchArena, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, nullptr});
+  for (int i = 0; i < iters; i++) sha_range(ctx, ShaTilesArgs{batchArena, chOff.p, chLen.p, hashTmp.p, errWord.p, nullptr, 0u, (u32)B}, false);
   cudaEventRecord(e[1], ctx.stream);
   for (int i = 0; i < iters; i++) runDecodeTiles(batchArena, B, lastBytes, deflList.p, lastDeflCount, lastDeflStart);
   cudaEventRecord(e[2], ctx.stream);
