@@ -608,14 +608,16 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       foreach(ctx, I, ItemIndexKernel{sortVals.p, itemIdx.p});
       foreach(ctx, N, ListObjFlagKernel{w, emit.p}); scan_exclusive(ctx, scanTmp, emit.p, objSlot.p, N);
       const size_t Lo = readU32(objSlot.p + N);
-      const size_t S = 2 * I + 2 * Lo; eNext.ensure(ctx, S + 1); eNext2.ensure(ctx, S + 1); eRank.ensure(ctx, S + 1); eRank2.ensure(ctx, S + 1);
+      const size_t S = 2 * I + 2 * Lo; eNext.ensure(ctx, S + 1); eRank.ensure(ctx, S + 1); ePacked.ensure(ctx, S + 1); ePacked2.ensure(ctx, S + 1);
       foreach(ctx, S, EulerInitKernel{eNext.p, eRank.p});
       foreach(ctx, I, EulerLinkKernel{sortKeys.p, ordBits, itemIdx.p, objSlot.p, eNext.p, eRank.p, I});
+      foreach(ctx, S, ListRankPackKernel{eNext.p, eRank.p, ePacked.p});
       const int rounds = bits_for(S);
       for (int k = 0; k < rounds; k++) {
-        foreach(ctx, S, ListRankKernel{eNext.p, eRank.p, eNext2.p, eRank2.p});
-        std::swap(eNext.p, eNext2.p); std::swap(eNext.cap, eNext2.cap); std::swap(eRank.p, eRank2.p); std::swap(eRank.cap, eRank2.cap);
+        foreach(ctx, S, ListRankPackedKernel{ePacked.p, ePacked2.p});
+        std::swap(ePacked.p, ePacked2.p); std::swap(ePacked.cap, ePacked2.cap);
       }
+      foreach(ctx, S, ListRankUnpackKernel{ePacked.p, eRank.p});
       foreach(ctx, N, ListPosKernel{eRank.p, elemRow.p, objRow.p, itemIdx.p, objSlot.p, (u32)I, listPos.p});
     } else dev_memset(ctx, listPos.p, 0, (N + 1) * 4);
     checkErr(actorsNow);

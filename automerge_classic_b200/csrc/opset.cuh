@@ -9,7 +9,7 @@
 // RGA order equals the pre-order of the insertion tree with siblings in descending opId order,
 // provided every insert has a greater counter than its reference element (Lamport property; checked
 // in ResolveRowsKernel, KE_LAMPORT otherwise). The pre-order is computed with an Euler tour over
-// 4 slots per row and Wyllie pointer jumping (ListRankKernel), log2(n) passes.
+// 4 slots per row and Wyllie pointer jumping (ListRankPackedKernel), log2(n) passes.
 #pragma once
 #include "gate.cuh"
 
@@ -180,15 +180,20 @@ struct EulerInitKernel {   // default links: enter -> own exit, exit -> self (te
   u32* next; u32* weight;
   HD void operator()(size_t s) const { next[s] = (s & 1) ? (u32)s : (u32)s + 1; weight[s] = 0; }
 };
-// Wyllie pointer jumping: rank[s] = sum of weights from s (inclusive) to the end of its list
-struct ListRankKernel {
-  const u32* nextIn; const u32* rankIn; u32* nextOut; u32* rankOut;
+// Wyllie pointer jumping: rank[s] = sum of weights from s (inclusive) to the end of its list, on (next | rank << 32) packed
+// into one word: a jump reads ONE random 8-byte word (one sector) instead of two
+// 4-byte words in two arrays (two sectors) - the random reads are what a round costs.
+struct ListRankPackKernel { const u32* next; const u32* rank; u64* packed; HD void operator()(size_t s) const { packed[s] = (u64)next[s] | ((u64)rank[s] << 32); } };
+struct ListRankPackedKernel {
+  const u64* in; u64* out;
   HD void operator()(size_t s) const {
-    const u32 n = nextIn[s];
-    if (n == (u32)s) { nextOut[s] = n; rankOut[s] = rankIn[s]; return; }
-    rankOut[s] = rankIn[s] + rankIn[n]; nextOut[s] = nextIn[n];
+    const u64 me = in[s]; const u32 n = (u32)me;
+    if (n == (u32)s) { out[s] = me; return; }
+    const u64 nb = in[n];
+    out[s] = (u64)(u32)nb | ((u64)((u32)(me >> 32) + (u32)(nb >> 32)) << 32);
   }
 };
+struct ListRankUnpackKernel { const u64* packed; u32* rank; HD void operator()(size_t s) const { rank[s] = (u32)(packed[s] >> 32); } };
 // list position of every list row = number of elements before its element in its object
 struct ListPosKernel {
   const u32* rank; const u32* elemRow; const u32* objRow; const u32* itemIdx; const u32* objSlot; u32 numItems; u32* listPos;
