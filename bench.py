@@ -361,7 +361,7 @@ def main():
             # the HBM-bound part of the decode: header parse + column expansion (one fused kernel). SHA-256 over the same
             # bytes is ALU-bound (64 rounds per 64-byte block) and is reported next to it, not folded into the HBM figure.
             t_dec = (ms_parse.value + ms_dec.value) / 1e3
-            kernel_name = 'column decode = k_decode_tiles (fused header parse + column expansion, bulk-staged through shared memory) + k_decode_direct (changes outside their tile) + DecodeColumnKernel (changes of more than 16 ops)'
+            kernel_name = 'column decode = k_decode_tiles (fused header parse + column expansion, bulk-staged through shared memory; one launch over the batch, one over the inflated changes) + k_decode_direct (changes outside their tile, totals) + DecodeColumnKernel (changes of more than 16 ops)'
             ach = algo.value / t_dec / 1e9
             n_blocks = (trace.blob.size + 64 * trace.n_changes) / 64.0          # ~ message blocks incl. padding
             roofline = {'bound': 'hbm', 'kernel': kernel_name,
