@@ -294,18 +294,28 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
   // ------------------------------------------------------------ 1. DEFLATEd changes
   {
     // Which changes of the batch are DEFLATEd (columnar.js:742)? Those are inflated on the device, behind the batch:
-    // flag -> scan -> ordered list -> InflateKernel pass 0 (sizes) -> scan -> pass 1 (bytes); the originals stay in place.
+    // flag -> scan -> ordered list -> k_inflate (decode into scratch, sizes) -> scan -> k_inflate (assemble in place); the originals stay.
     // The hash / decode kernels above skipped them; they are hashed and decoded here, from the inflated bytes.
     emit.ensure(ctx, B + 1); slot.ensure(ctx, B + 2);
-    foreach(ctx, B, DeflateFlagKernel{arena.p, chOff.p, chLen.p, emit.p});
+    dev_memset(ctx, flagWord.p + 8, 0, 4);
+    foreach(ctx, B, DeflateFlagKernel{arena.p, chOff.p, chLen.p, emit.p, flagWord.p + 8});
     scan_exclusive(ctx, scanTmp, emit.p, slot.p, B);
-    const size_t nd = readU32(slot.p + B);
+    u32 nd32 = 0, deflBytes = 0; readU32x2(slot.p + B, flagWord.p + 8, &nd32, &deflBytes);
+    const size_t nd = nd32;
     dbgMark("sha:deflate-scanned");
     if (nd > 0) {
+      // every stream is decoded once, into scratch (capacity: a few times its compressed size); the sizes give the places
+      // behind the batch, a second kernel assembles the changes there (copy; the rare stream that did not fit is decoded again)
       foreach(ctx, B, CompactKernel{emit.p, slot.p, deflList.p});
-      inflLen.ensure(ctx, nd + 1); inflOff.ensure(ctx, nd + 2); patchTriples.ensure(ctx, 2 * nd + 2);
+      inflLen.ensure(ctx, nd + 1); inflOff.ensure(ctx, nd + 2); patchTriples.ensure(ctx, 2 * nd + 2); inflCap.ensure(ctx, nd + 2); inflCapOff.ensure(ctx, nd + 2); inflOvf.ensure(ctx, nd + 1);
       u32* origOff = patchTriples.p; u32* origLen = patchTriples.p + nd;
-      inflate_changes(ctx, 0, arena.p, chOff.p, chLen.p, deflList.p, nd, inflLen.p, nullptr, 0, origOff, origLen, errWord.p);
+      u32 factor = 4; while (factor > 1 && (u64)factor * deflBytes + 1024ull * nd >= 0xf0000000ULL) factor--;
+      const size_t scratchBytes = (size_t)factor * deflBytes + 1024 * nd + 64;
+      inflScratch.ensure(ctx, scratchBytes);
+      foreach(ctx, nd, InflateCapKernel{deflList.p, chLen.p, factor, inflCap.p});
+      scan_exclusive(ctx, scanTmp, inflCap.p, inflCapOff.p, nd);
+      InflateArgs ia{arena.p, chOff.p, chLen.p, deflList.p, nd, inflLen.p, nullptr, 0u, origOff, origLen, inflScratch.p, inflCapOff.p, inflOvf.p, errWord.p};
+      inflate_changes(ctx, INFL_SPECULATE, ia);
       scan_exclusive(ctx, scanTmp, inflLen.p, inflOff.p, nd);
       const size_t extra = readU32(inflOff.p + nd);
       if (errSnapshot) throwKernelError(errSnapshot, actorIds);   // (the error word travels with every small read)
@@ -313,7 +323,8 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
       const size_t extraStart = cur; cur += extra;
       side_join(ctx);   // the arena may move: nothing may still be reading it
       arena.ensure(ctx, cur + 64, extraStart);
-      inflate_changes(ctx, 1, arena.p, chOff.p, chLen.p, deflList.p, nd, inflLen.p, inflOff.p, (u32)extraStart, origOff, origLen, errWord.p);
+      ia.arena = arena.p; ia.outOff = inflOff.p; ia.extraStart = (u32)extraStart;
+      inflate_changes(ctx, INFL_PLACE, ia);
       dev_memset(ctx, arena.p + cur, 0, 64);
       foreach(ctx, nd, InflatePatchKernel{deflList.p, inflLen.p, inflOff.p, (u32)extraStart, chOff.p, chLen.p});
       foreach(ctx, nd, ShaKernel{arena.p, chOff.p, chLen.p, hashOut, errWord.p, deflList.p, nullptr});

@@ -234,7 +234,7 @@ HD bool infl_build(const u8* lengths, int n, uint16_t* count, uint16_t* symbol, 
 }
 // Decodes src[begin, end) into dst (nullptr = only count) with the tables T of this warp. Every lane calls it; lane 0
 // returns the KErr and *produced.
-HD u32 inflate_tabled(InflWarpTables& T, const u8* src, u32 begin, u32 end, u8* dst, u32 dstCap, u32* produced, int lane, int nlanes) {
+HD u32 inflate_tabled(InflWarpTables& T, const u8* src, u32 begin, u32 end, u8* dst, u32 dstCap, u32* produced, int lane, int nlanes, u32* softOverflow = nullptr) {
   const uint16_t lenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
   const u8 lenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
   const uint16_t distBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
@@ -252,7 +252,7 @@ HD u32 inflate_tabled(InflWarpTables& T, const u8* src, u32 begin, u32 end, u8* 
         else {
           const u32 ln = src[b.pos] | ((u32)src[b.pos + 1] << 8), nln = src[b.pos + 2] | ((u32)src[b.pos + 3] << 8);
           if ((ln ^ 0xffffu) != nln) e = KE_DEFLATE;
-          else { b.pos += 4; if (b.pos + ln > b.end) e = KE_DEFLATE; else { if (dst) { if (out + ln > dstCap) e = KE_DEFLATE; else for (u32 i = 0; i < ln; i++) dst[out + i] = src[b.pos + i]; } out += ln; b.pos += ln; } }
+          else { b.pos += 4; if (b.pos + ln > b.end) e = KE_DEFLATE; else { if (dst && out + ln > dstCap) { if (softOverflow) { *softOverflow = 1; dst = nullptr; } else e = KE_DEFLATE; } if (dst && !e) for (u32 i = 0; i < ln; i++) dst[out + i] = src[b.pos + i]; if (!e) { out += ln; b.pos += ln; } } }
         }
       } else if (!e && type == 1) {     // fixed code (RFC 1951 3.2.6)
         for (int i = 0; i < 144; i++) T.lengths[i] = 8;
@@ -309,7 +309,7 @@ HD u32 inflate_tabled(InflWarpTables& T, const u8* src, u32 begin, u32 end, u8* 
           b.refill();
           int sym; { const u32 t = T.lit[b.peek(INFL_LBITS)]; if (t) { b.drop((int)(t & 15)); sym = (int)(t >> 4); } else sym = infl_decode_slow(b, T.lcount, T.lsym); }
           if (sym < 0 || b.err) { e = KE_DEFLATE; break; }
-          if (sym < 256) { if (dst) { if (out >= dstCap) { e = KE_DEFLATE; break; } dst[out] = (u8)sym; } out++; }
+          if (sym < 256) { if (dst && out >= dstCap) { if (softOverflow) { *softOverflow = 1; dst = nullptr; } else { e = KE_DEFLATE; break; } } if (dst) dst[out] = (u8)sym; out++; }
           else if (sym == 256) break;
           else {
             sym -= 257; if (sym >= 29) { e = KE_DEFLATE; break; }
@@ -319,7 +319,7 @@ HD u32 inflate_tabled(InflWarpTables& T, const u8* src, u32 begin, u32 end, u8* 
             if (ds < 0 || ds >= 30) { e = KE_DEFLATE; break; }
             const u32 d = distBase[ds] + b.bits(distExtra[ds]);
             if (b.err || d > out) { e = KE_DEFLATE; break; }
-            if (dst) { if (out + ln > dstCap) { e = KE_DEFLATE; break; } for (u32 i = 0; i < ln; i++) dst[out + i] = dst[out + i - d]; }
+            if (dst && out + ln > dstCap) { if (softOverflow) { *softOverflow = 1; dst = nullptr; } else { e = KE_DEFLATE; break; } } if (dst) for (u32 i = 0; i < ln; i++) dst[out + i] = dst[out + i - d];
             out += ln;
           }
           if (out > 0x7fffffffu) { e = KE_TOO_LARGE; break; }
@@ -333,60 +333,79 @@ HD u32 inflate_tabled(InflWarpTables& T, const u8* src, u32 begin, u32 end, u8* 
   *produced = out;
   return e;
 }
-// One stream k of the list with `nlanes` cooperating lanes (32 on the device, 1 in the emulation). pass 0: outLen[k] = size of
-// the inflated change (8 bytes magic + checksum, chunk type 1, LEB128 length, body), original range kept; pass 1: bytes
-// written at arena[extraStart + outOff[k]).
-HD void inflate_one(InflWarpTables& T, size_t k, int pass, u8* arena, u32* chOff, u32* chLen, const u32* list, u32* outLen, const u32* outOff, u32 extraStart, u32* origOff, u32* origLen, u64* errWord, int lane, int nlanes) {
-  const u32 c = list[k]; const u32 off = pass == 0 ? chOff[c] : origOff[k], len = pass == 0 ? chLen[c] : origLen[k];
+// One stream k of the list with `nlanes` cooperating lanes (32 on the device, 1 in the emulation). A stream is decoded ONCE:
+//   INFL_SPECULATE: the body goes to scratch[capOff[k] ..) (capacity capOff[k+1] - capOff[k]: a few times the compressed size);
+//                   outLen[k] = size of the inflated change (8 bytes magic + checksum, chunk type 1, LEB128 length, body), the
+//                   original range is kept in origOff / origLen; a body that does not fit is only counted (ovf[k] = 1);
+//   INFL_PLACE:     (after the prefix sum over outLen) the change is assembled at arena[extraStart + outOff[k]): header, then
+//                   the body copied from scratch - or, for the few that did not fit, decoded a second time, straight to its place.
+enum { INFL_SPECULATE = 0, INFL_PLACE = 1 };
+struct InflateArgs {
+  u8* arena; u32* chOff; u32* chLen; const u32* list; size_t nd; u32* outLen; const u32* outOff; u32 extraStart; u32* origOff; u32* origLen;
+  u8* scratch; const u32* capOff; u32* ovf; u64* errWord;
+};
+HD void inflate_one(InflWarpTables& T, size_t k, int pass, const InflateArgs& a, int lane, int nlanes) {
+  const u32 c = a.list[k]; const u32 off = pass == INFL_SPECULATE ? a.chOff[c] : a.origOff[k], len = pass == INFL_SPECULATE ? a.chLen[c] : a.origLen[k];
+  if (pass == INFL_PLACE && a.outLen[k] == 0) return;
   u32 kerr = 0, streamBegin = 0, clen = 0;
-  if (lane == 0) { ByteReader r(arena, off + 9, off + len); const u64 cl = r.uleb(); if (r.err || (u64)r.pos + cl > (u64)off + len) kerr = r.err ? r.err : (u32)KE_SUBARRAY; streamBegin = r.pos; clen = (u32)cl; }
+  if (lane == 0) { ByteReader r(a.arena, off + 9, off + len); const u64 cl = r.uleb(); if (r.err || (u64)r.pos + cl > (u64)off + len) kerr = r.err ? r.err : (u32)KE_SUBARRAY; streamBegin = r.pos; clen = (u32)cl; }
   kerr = INFL_BCAST(kerr); streamBegin = INFL_BCAST(streamBegin); clen = INFL_BCAST(clen);
-  if (kerr) { if (lane == 0) { raise(errWord, kerr, c); if (pass == 0) outLen[k] = 0; } return; }
-  u8* dst = nullptr; u32 dstCap = 0, hl = 9;
-  if (pass == 1) {
-    const u32 total = outLen[k]; if (total == 0) return;
-    u8* d0 = arena + extraStart + outOff[k]; u32 n = 0;
-    for (u32 w = 1; w <= 5; w++) { n = total - 9 - w; if (uleb_len(n) == w) break; }
-    if (lane == 0) { for (int i = 0; i < 8; i++) d0[i] = arena[off + i]; d0[8] = 1; u64 v = n; do { u8 x = v & 0x7f; v >>= 7; if (v) x |= 0x80; d0[hl++] = x; } while (v); }
-    hl = INFL_BCAST(hl);
-    dst = d0 + hl; dstCap = n;
+  if (kerr) { if (lane == 0) { raise(a.errWord, kerr, c); if (pass == INFL_SPECULATE) a.outLen[k] = 0; } return; }
+  if (pass == INFL_SPECULATE) {
+    u8* dst = a.scratch + a.capOff[k]; const u32 cap = a.capOff[k + 1] - a.capOff[k]; u32 out = 0, over = 0;
+    const u32 e = inflate_tabled(T, a.arena, streamBegin, streamBegin + clen, dst, cap, &out, lane, nlanes, &over);
+    if (lane == 0) {
+      if (e) { raise(a.errWord, e, c); a.outLen[k] = 0; }
+      else { a.outLen[k] = 9 + uleb_len(out) + out; a.origOff[k] = off; a.origLen[k] = len; a.ovf[k] = over; }
+    }
+    INFL_SYNC();
+    return;
   }
-  u32 out = 0; const u32 e = inflate_tabled(T, arena, streamBegin, streamBegin + clen, dst, dstCap, &out, lane, nlanes);
-  if (lane == 0) {
-    if (pass == 0) { if (e) { raise(errWord, e, c); outLen[k] = 0; } else { outLen[k] = 9 + uleb_len(out) + out; origOff[k] = off; origLen[k] = len; } }
-    else if (e || out != dstCap) raise(errWord, e ? e : (u32)KE_DEFLATE, c);
+  const u32 total = a.outLen[k];
+  u8* d0 = a.arena + a.extraStart + a.outOff[k]; u32 n = 0, hl = 9;
+  for (u32 w = 1; w <= 5; w++) { n = total - 9 - w; if (uleb_len(n) == w) break; }
+  if (lane == 0) { for (int i = 0; i < 8; i++) d0[i] = a.arena[off + i]; d0[8] = 1; u64 v = n; do { u8 x = v & 0x7f; v >>= 7; if (v) x |= 0x80; d0[hl++] = x; } while (v); }
+  hl = INFL_BCAST(hl);
+  if (!a.ovf[k]) {
+    const u8* body = a.scratch + a.capOff[k];
+    for (u32 i = (u32)lane; i < n; i += (u32)nlanes) d0[hl + i] = body[i];
+  } else {
+    u32 out = 0; const u32 e = inflate_tabled(T, a.arena, streamBegin, streamBegin + clen, d0 + hl, n, &out, lane, nlanes);
+    if (lane == 0 && (e || out != n)) raise(a.errWord, e ? e : (u32)KE_DEFLATE, c);
   }
   INFL_SYNC();
 }
 #ifndef AMG_EMU
-__global__ void __launch_bounds__(INFL_WARPS * 32) k_inflate(int pass, u8* arena, u32* chOff, u32* chLen, const u32* list, size_t nd, u32* outLen, const u32* outOff, u32 extraStart, u32* origOff, u32* origLen, u64* errWord) {
+__global__ void __launch_bounds__(INFL_WARPS * 32) k_inflate(int pass, const InflateArgs a) {
   __shared__ InflWarpTables tabs[INFL_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (size_t k = (size_t)blockIdx.x * INFL_WARPS + warp; k < nd; k += (size_t)gridDim.x * INFL_WARPS)
-    inflate_one(tabs[warp], k, pass, arena, chOff, chLen, list, outLen, outOff, extraStart, origOff, origLen, errWord, lane, 32);
+  for (size_t k = (size_t)blockIdx.x * INFL_WARPS + warp; k < a.nd; k += (size_t)gridDim.x * INFL_WARPS) inflate_one(tabs[warp], k, pass, a, lane, 32);
 }
 #endif
-inline void inflate_changes(Ctx& c, int pass, u8* arena, u32* chOff, u32* chLen, const u32* list, size_t nd, u32* outLen, const u32* outOff, u32 extraStart, u32* origOff, u32* origLen, u64* errWord) {
-  if (nd == 0) return;
+inline void inflate_changes(Ctx& c, int pass, const InflateArgs& a) {
+  if (a.nd == 0) return;
 #ifdef AMG_EMU
   InflWarpTables* T = new InflWarpTables();
-  for (size_t k = 0; k < nd; k++) inflate_one(*T, k, pass, arena, chOff, chLen, list, outLen, outOff, extraStart, origOff, origLen, errWord, 0, 1);
+  for (size_t k = 0; k < a.nd; k++) inflate_one(*T, k, pass, a, 0, 1);
   delete T;
 #else
-  const size_t want = (nd + INFL_WARPS - 1) / INFL_WARPS, maxGrid = (size_t)c.numSMs * 4;
-  k_inflate<<<(unsigned)std::min(want, maxGrid), INFL_WARPS * 32, 0, c.stream>>>(pass, arena, chOff, chLen, list, nd, outLen, outOff, extraStart, origOff, origLen, errWord);
+  const size_t want = (a.nd + INFL_WARPS - 1) / INFL_WARPS, maxGrid = (size_t)c.numSMs * 4;
+  k_inflate<<<(unsigned)std::min(want, maxGrid), INFL_WARPS * 32, 0, c.stream>>>(pass, a);
   CUDA_CHECK(cudaGetLastError());
 #endif
   c.launches++;
 }
+// scratch capacity of a stream: `factor` (four, unless the batch is huge) times its compressed size; a stream that inflates to
+// more is decoded a second time, straight into place
+struct InflateCapKernel { const u32* list; const u32* chLen; u32 factor; u32* cap; HD void operator()(size_t k) const { cap[k] = factor * chLen[list[k]] + 1024u; } };
 // re-points the inflated changes (separate from pass 1: the batch-wide SHA kernel may still be reading the old entries)
 struct InflatePatchKernel {
   const u32* list; const u32* outLen; const u32* outOff; u32 extraStart; u32* chOff; u32* chLen;
   HD void operator()(size_t k) const { if (outLen[k] == 0) return; const u32 c = list[k]; chOff[c] = extraStart + outOff[k]; chLen[c] = outLen[k]; }
 };
-struct DeflateFlagKernel {   // 1 for chunks of type 2 (columnar.js:742)
-  const u8* arena; const u32* chOff; const u32* chLen; u32* flag;
-  HD void operator()(size_t c) const { const u8* p = arena + chOff[c]; flag[c] = (chLen[c] > 8 && p[8] == 2 && p[0] == 0x85) ? 1u : 0u; }
+struct DeflateFlagKernel {   // 1 for chunks of type 2 (columnar.js:742); their compressed bytes are summed (scratch sizing)
+  const u8* arena; const u32* chOff; const u32* chLen; u32* flag; u32* bytes;
+  HD void operator()(size_t c) const { const u8* p = arena + chOff[c]; const bool d = chLen[c] > 8 && p[8] == 2 && p[0] == 0x85; flag[c] = d ? 1u : 0u; warp_agg_add(bytes, d ? chLen[c] : 0u); }
 };
 
 }  // namespace amg
