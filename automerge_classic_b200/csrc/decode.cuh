@@ -1,18 +1,18 @@
 // amgpu — kernels #1: columnar change decode.
 //
 // Replaces (reference paths relative to /root/reference):
-//   backend/columnar.js:688-708  decodeContainerHeader (magic, SHA-256 over [type|len|body], checksum)   -> ShaKernel
-//   backend/columnar.js:635-652  decodeChangeHeader, :609-624 decodeColumnInfo, :741-765 decodeChangeColumns -> ParseKernel
+//   backend/columnar.js:688-708  decodeContainerHeader (magic, SHA-256 over [type|len|body], checksum)   -> ShaKernel / sha_change
+//   backend/columnar.js:635-652  decodeChangeHeader, :609-624 decodeColumnInfo, :741-765 decodeChangeColumns -> parse_change
 //   backend/encoding.js:341-488  LEB128 readers, :789-920 RLEDecoder, :1004-1051 DeltaDecoder,
-//   backend/encoding.js:1141-1207 BooleanDecoder, backend/new.js:570-610 readOperation               -> DecodeColumnKernel
-//   backend/new.js:678-724       readNextChangeOp (opId assignment, reference validation)             -> FinalizeOpsKernel
+//   backend/encoding.js:1141-1207 BooleanDecoder, backend/new.js:570-610 readOperation               -> fast_value / decode_one_column_t
+//   backend/new.js:678-724       readNextChangeOp (opId assignment, reference validation)             -> FinalizeOpsKernel (gate.cuh)
 //
-// Layout: all change bytes of a call sit back to back in one device arena (u8). ParseKernel writes a
-// ChangeMeta per change plus a column directory in structure-of-arrays form ([column][change]);
-// DecodeColumnKernel runs one thread per (column, change) — adjacent threads handle adjacent changes
-// of the same column, so directory reads and row writes are coalesced for the many-small-changes
-// regime, and large changes get 14-way column parallelism. Rows are raw u32 columns (SoA); the
-// finalize kernel packs them into 64-bit ids with document-global actor numbers.
+// Layout: all change bytes of a call sit back to back in one device arena (u8). The apply path decodes with ONE fused kernel,
+// k_decode_tiles (below: one CTA = 128 consecutive changes staged in shared memory by a bulk copy, one thread per change:
+// header -> 48-byte ChangeHot + counts, columns -> raw u32 rows in structure-of-arrays form, row ranges from a global cursor);
+// changes of more than SMALL_CHANGE_OPS ops only reserve rows there and are expanded by DecodeColumnKernel (one thread per
+// (column, change)) or the parallel decoders of doccols.cuh. save() re-parses headers with ParseKernel (ChangeMeta: the fields
+// only it needs). The finalize kernel packs raw rows into 64-bit ids with document-global actor numbers.
 #pragma once
 #include "common.cuh"
 
@@ -20,7 +20,7 @@ namespace amg {
 
 static const u32 NULL32 = 0xffffffffu;
 static const int NCOLS = 14;   // known change columns, in this order:
-static const u32 SMALL_CHANGE_OPS = 16;   // changes with at most this many ops are decoded by one thread (DecodeSmallKernel)
+static const u32 SMALL_CHANGE_OPS = 16;   // changes with at most this many ops are decoded by one thread inside k_decode_tiles
 enum ColIx { CX_OBJ_ACTOR = 0, CX_OBJ_CTR, CX_KEY_ACTOR, CX_KEY_CTR, CX_KEY_STR, CX_INSERT, CX_ACTION, CX_VAL_LEN, CX_VAL_RAW,
              CX_CHLD_ACTOR, CX_CHLD_CTR, CX_PRED_NUM, CX_PRED_ACTOR, CX_PRED_CTR };
 HD int col_index_of(u32 columnId) {
@@ -262,14 +262,6 @@ HD void sha256_compress(u32* h, u32* w, const u32* K) {
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
 
-// lists the DEFLATEd changes (chunk type 2, columnar.js:742) of a bulk batch so that the host can inflate just those
-struct DeflateScanKernel {
-  const u8* arena; const u32* chOff; const u32* chLen; u64* counter; u32* list;
-  HD void operator()(size_t c) const {
-    const u8* p = arena + chOff[c];
-    if (chLen[c] > 8 && p[8] == 2 && p[0] == 0x85) list[atomic_add(counter, (u64)1)] = (u32)c;
-  }
-};
 // Where the bytes of ONE change are read from when it is hashed: global (host, in the emulation) memory. byte(i) = byte i of the change; on the device word(k) = aligned 32-bit word k counted from
 // the aligned word that holds the first message byte (the message = bytes 8 ..), mis() = the message's misalignment.
 struct GlobalBytes {
