@@ -16,7 +16,6 @@
 #include <map>
 #include <memory>
 #include <thread>
-#include <atomic>
 #include <zlib.h>
 #include "patch.cuh"
 #include "inflate.cuh"
@@ -237,7 +236,6 @@ class Engine {
   bool domLocalReady = false;   // k_dom_local's dynamic shared memory size has been raised on this device
   std::vector<HostChange> batchStore;   // applyChanges: (offset, length) of the batch entries
   HBuf<HostChange> pairStage;           // the same table in pinned memory: uploaded by DMA
-  HBuf<uint16_t> lenStage; DBuf<u32> offsLen16;   // 16-bit lengths of a packed batch (pinned / device): what goes up instead of 64-bit offsets
   HBuf<u32> pinnedScratch; HBuf<u64> hostWord;   // pinned landing slots for the small device -> host reads that size the next stage
   u32 readU32(const u32* dptr) { u32 v = 0; void* d[1] = {&v}; readWords({{dptr, 4}}, d); return v; }
   void readU32x2(const u32* a, const u32* b, u32* va, u32* vb) { void* d[2] = {va, vb}; readWords({{a, 4}, {b, 4}}, d); }

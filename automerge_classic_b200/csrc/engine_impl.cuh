@@ -236,40 +236,15 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     else { std::vector<std::thread> ts; const size_t per = (n + nt - 1) / nt; for (unsigned t = 0; t < nt; t++) { const size_t a = t * per, b = std::min(n, a + per); if (a < b) ts.emplace_back(fill, a, b); } for (auto& t : ts) t.join(); }
   };
   bool offsetsByDma = false;
-#ifdef AMG_EMU
-  offsetsByDma = blob && n >= 4096;   // (the emulation takes the 16-bit-lengths route below: same kernels as on the device)
-#else
+#ifndef AMG_EMU
   if (blob && n >= 4096) { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, offsets) == cudaSuccess) offsetsByDma = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged; else cudaGetLastError(); }
 #endif
   for (size_t i = 0; i < Bq; i++) pairs[n + i] = queue[i];
-  chPairs.ensure(ctx, B); chOff.ensure(ctx, B + 1); chLen.ensure(ctx, B + 1);
+  chPairs.ensure(ctx, B); chOff.ensure(ctx, B); chLen.ensure(ctx, B);
   if (offsetsByDma) {
-    // The table crosses PCIe next to the change bytes. Host-resident offsets of a batch of small changes go up as 16-bit
-    // LENGTHS (2 bytes per change instead of 8; a few host threads write them into a pinned table while the first piece is
-    // already on its way) and the device rebuilds the offsets with a prefix sum; anything else goes up as it is.
-    bool asLengths = true;
-#ifndef AMG_EMU
-    { cudaPointerAttributes at; asLengths = cudaPointerGetAttributes(&at, offsets) == cudaSuccess && at.type == cudaMemoryTypeHost; cudaGetLastError(); }
-#endif
-    if (asLengths) {
-      lenStage.ensure(n + 1); uint16_t* l16 = lenStage.p;
-      std::atomic<int> big{0};
-      auto fill = [&](size_t a, size_t b) { int any = 0; for (size_t i = a; i < b; i++) { const u64 l = offsets[i + 1] - offsets[i]; if (l >= 0xffffu) any = 1; l16[i] = (uint16_t)l; } if (any) big = 1; };
-      const unsigned nt = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
-      { std::vector<std::thread> ts; const size_t per = (n + nt - 1) / nt; for (unsigned t = 0; t < nt; t++) { const size_t a = t * per, b = std::min(n, a + per); if (a < b) ts.emplace_back(fill, a, b); } for (auto& t : ts) t.join(); }
-      asLengths = !big;
-    }
-    if (asLengths) {
-      DBuf<u32>& lenD = offsLen16; lenD.ensure(ctx, n / 2 + 2);
-      h2d(ctx, lenD.p, lenStage.p, n * 2);
-      foreach(ctx, n, WidenLengthsKernel{reinterpret_cast<const uint16_t*>(lenD.p), chLen.p});
-      scan_exclusive(ctx, scanTmp, chLen.p, chOff.p, n);
-      foreach(ctx, n, AddU32Kernel{chOff.p, (u32)arenaLen0});
-    } else {
-      DBuf<u64>& offsD = offsDev; offsD.ensure(ctx, n + 2);
-      CUDA_CHECK_EMU(cudaMemcpyAsync(offsD.p, offsets, (n + 1) * 8, cudaMemcpyDefault, ctx.stream));
-      foreach(ctx, n, OffsetsToRangesKernel{offsD.p, (u32)(arenaLen0 - offsets[0]), chOff.p, chLen.p});
-    }
+    DBuf<u64>& offsD = offsDev; offsD.ensure(ctx, n + 2);
+    CUDA_CHECK_EMU(cudaMemcpyAsync(offsD.p, offsets, (n + 1) * 8, cudaMemcpyDefault, ctx.stream));
+    foreach(ctx, n, OffsetsToRangesKernel{offsD.p, (u32)(arenaLen0 - offsets[0]), chOff.p, chLen.p});
     if (Bq > 0) { h2d(ctx, chPairs.p + n, pairs + n, Bq * sizeof(HostChange)); foreach(ctx, Bq, SplitPairsKernel{chPairs.p + n, chOff.p + n, chLen.p + n}); }
   } else {
     fillPairs();

@@ -98,8 +98,6 @@ struct CompactKernel { const u32* flag; const u32* slot; u32* out; HD void opera
 struct HashGatherKernel { const u8* src; const u8* applied; const u32* appRank; u8* dst; HD void operator()(size_t b) const { if (!applied[b]) return; const u64* s = reinterpret_cast<const u64*>(src + b * 32); u64* d = reinterpret_cast<u64*>(dst + (size_t)appRank[b] * 32); d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; } };
 // (offset, length) of the changes of a packed batch straight from the caller's offsets array (device copy)
 struct OffsetsToRangesKernel { const u64* offsets; u32 shift; u32* off; u32* len; HD void operator()(size_t b) const { off[b] = (u32)offsets[b] + shift; len[b] = (u32)(offsets[b + 1] - offsets[b]); } };
-struct WidenLengthsKernel { const uint16_t* l16; u32* len; HD void operator()(size_t b) const { len[b] = l16[b]; } };
-struct AddU32Kernel { u32* v; u32 add; HD void operator()(size_t b) const { v[b] += add; } };
 struct SplitPairsKernel { const HostChange* pairs; u32* off; u32* len; HD void operator()(size_t b) const { off[b] = pairs[b].off; len[b] = pairs[b].len; } };
 struct PatchPairsKernel { const u32* triples; u32* off; u32* len; HD void operator()(size_t i) const { const u32 c = triples[3 * i]; off[c] = triples[3 * i + 1]; len[c] = triples[3 * i + 2]; } };
 // ---------------------------------------------------------------- Backend.load: document chunk -> document table (new.js:1709-1750)

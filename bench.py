@@ -347,11 +347,6 @@ def main():
     trace, doc, nbytes = m['trace'], m['doc'], m['nbytes']
     t_wall, t_dev, last_ph = m['t_wall'], m['t_dev'], m['last_ph']
     total_ops = trace.n_ops * world
-    # what the engine moves across PCIe for the (offset, length) table of a packed batch: 16-bit lengths when every change is
-    # shorter than 64 KB and the batch has at least 4096 changes (engine_impl.cuh), the caller's 64-bit offsets otherwise
-    import numpy as _np
-    _lens = _np.diff(trace.offsets.astype(_np.int64))
-    table_bytes = 2 * trace.n_changes if (trace.n_changes >= 4096 and int(_lens.max()) < 0xffff) else 8 * (trace.n_changes + 1)
     blob_ptr, offs = C.c_void_p(m['pinned'].data_ptr()), m['offs']
     extras = rank == 0 and not args.no_extras
 
@@ -444,7 +439,7 @@ def main():
                        'phase_ms_last_step_e2e': dict(zip(names, [round(x, 3) for x in last_ph[:9]])),
                        'phase_ms_last_step_resident': dict(zip(names, [round(x, 3) for x in m['ph_res'][:9]])),
                        'host_marks_ms': [round(x, 3) for x in last_ph[12:22]], 'other_paths': other, 'other_workloads': others},
-            'e2e': {'value': total_ops / t_wall, 'unit': 'ops/s', 'h2d_bytes_per_step': nbytes + table_bytes, 'd2h_bytes_per_step': m['patch_bytes']},
+            'e2e': {'value': total_ops / t_wall, 'unit': 'ops/s', 'h2d_bytes_per_step': nbytes + 8 * (trace.n_changes + 1), 'd2h_bytes_per_step': m['patch_bytes']},
             'e2e_ptr_array': e2e_ptr,
             'gpu_launches': m['launches'], 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': m['clocks']}))
     if world > 1:
