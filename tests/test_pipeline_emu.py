@@ -200,3 +200,12 @@ def test_duplicated_successor_pinned_emu(emu_doc, oracle_mod):
 
 def test_unknown_columns_emu(emu_doc, oracle_mod):
     parity_checks.check_unknown_columns(emu_doc, oracle_mod)
+
+
+def test_random_sweep_small_emu(emu_doc):
+    """tools/sweep_emu.py, 60 random small trace configurations (C3 - C8): every patch, getPatch, op table, decoded rows and
+    save() identical to the oracle's."""
+    import sys
+    root = os.path.dirname(HERE)
+    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'sweep_emu.py'), '60', '99'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and 'sweep: 60 cases identical' in out.stdout and ' 0 mismatches' in out.stdout, out.stdout[-600:] + out.stderr[-300:]
