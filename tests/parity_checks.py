@@ -291,6 +291,43 @@ def check_deflate_variants(gpu_doc, oracle_mod):
     assert g.apply_changes([bytes(raw)])['pendingChanges'] == 0
 
 
+def check_deflate_fuzz(gpu_doc, oracle_mod, cases, seed=3):
+    """Corrupted DEFLATE streams (bit flips, truncation) inside otherwise well-formed compressed changes: the engine accepts
+    exactly what the oracle accepts (columnar.js:813-823 inflateChange + the checks behind it), with the same patch."""
+    import random
+    from automerge_classic_b200 import columnar
+    rnd = random.Random(seed)
+    actor = '0123456789abcdef0123456789abcdef'
+    texts = ['a' * 3000, ''.join(rnd.choice('abcdefghij klmnop') for _ in range(2500)),
+             'xyz' * 900 + ''.join(chr(rnd.randrange(0x20, 0x7f)) for _ in range(700))]
+    accepted = 0
+    for case in range(cases):
+        text, level = rnd.choice(texts), rnd.choice([1, 6, 9])
+        change = {'actor': actor, 'seq': 1, 'startOp': 1, 'time': 0, 'message': '', 'deps': [], 'ops': [
+            {'action': 'set', 'obj': '_root', 'key': 'k', 'value': text, 'pred': []}]}
+        raw = bytearray(columnar.encode_change(change, True, level))
+        assert raw[8] == 2
+        for _ in range(rnd.choice([1, 1, 2, 3])):
+            raw[rnd.randrange(9, len(raw))] ^= 1 << rnd.randrange(8)
+        if rnd.random() < 0.15:
+            raw = raw[:rnd.randrange(12, len(raw))]
+        eo = eg = None
+        try:
+            po = oracle_mod.OracleDoc().apply_changes([bytes(raw)])
+        except Exception as e:
+            eo = str(e)
+        try:
+            pg = gpu_doc().apply_changes([bytes(raw)])
+        except Exception as e:
+            eg = str(e)
+        assert (eo is None) == (eg is None), (case, eo, eg)
+        if eo is None:
+            d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+            assert d is None, (case, d)
+            accepted += 1
+    return accepted
+
+
 def check_counters(gpu_doc, oracle_mod, seed, n, a, chunk):
     """Config C7: counters in map keys (create, concurrent increments, overwrite, delete), applied in calls of `chunk`
     changes: incremental patches, getPatch and the op table equal the oracle's."""

@@ -209,3 +209,7 @@ def test_random_sweep_small_emu(emu_doc):
     root = os.path.dirname(HERE)
     out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'sweep_emu.py'), '60', '99'], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and 'sweep: 60 cases identical' in out.stdout and ' 0 mismatches' in out.stdout, out.stdout[-600:] + out.stderr[-300:]
+
+
+def test_deflate_fuzz_emu(emu_doc, oracle_mod):
+    parity_checks.check_deflate_fuzz(emu_doc, oracle_mod, 400)
