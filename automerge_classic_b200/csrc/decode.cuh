@@ -23,6 +23,10 @@ static const int NCOLS = 14;   // known change columns, in this order:
 static const u32 SMALL_CHANGE_OPS = 16;   // changes with at most this many ops are decoded by one thread inside k_decode_tiles
 enum ColIx { CX_OBJ_ACTOR = 0, CX_OBJ_CTR, CX_KEY_ACTOR, CX_KEY_CTR, CX_KEY_STR, CX_INSERT, CX_ACTION, CX_VAL_LEN, CX_VAL_RAW,
              CX_CHLD_ACTOR, CX_CHLD_CTR, CX_PRED_NUM, CX_PRED_ACTOR, CX_PRED_CTR };
+// A column id this version does not know is carried along (unknowncols.hpp) - except a GROUP_CARD column (type 0) whose group
+// (id >> 4) is one of the groups the known scalar columns live in (obj 0, key 1, insert 3, action 4, value 5, child 6): the
+// reference's readOperation would then read those known columns as arrays (new.js:576-597). No encoder writes that; refused.
+HD bool groups_known_columns(u32 columnId) { return (columnId & 7u) == 0 && (columnId >> 4) < 7u && (columnId >> 4) != 2u; }
 HD int col_index_of(u32 columnId) {
   switch (columnId) {
     case 0x01: return CX_OBJ_ACTOR; case 0x02: return CX_OBJ_CTR; case 0x11: return CX_KEY_ACTOR; case 0x13: return CX_KEY_CTR;
@@ -38,7 +42,8 @@ enum KErr {
   KE_RLE_REP1, KE_RLE_SUCC_REP, KE_RLE_SUCC_LIT, KE_RLE_SUCC_NULL, KE_RLE_ZERO_NULL, KE_RLE_LIT_REP, KE_BOOL_ZERO,
   KE_OBJ_MISMATCH, KE_KEY_MISMATCH, KE_ACTOR_INDEX, KE_TOO_LARGE, KE_UNKNOWN_ACTOR, KE_PRED_MISSING, KE_REF_ELEM, KE_DUP_OPID,
   KE_UNSUPPORTED_OP, KE_LAMPORT, KE_HASH_COLLISION, KE_LIST_ELEM, KE_PRED_ORDER, KE_DEFLATE, KE_UNKNOWN_COUNTER, KE_HIST_RANGE, KE_HIST_OPID, KE_HIST_DEP, KE_FLOAT_LEN /* columnar.js:316 */,
-  KE_SUBARRAY   // raw bytes (a string, a hash, a column, a chunk body) reach past the end: encoding.js:497, where a number that runs out is KE_TRUNCATED (:353)
+  KE_SUBARRAY,  // raw bytes (a string, a hash, a column, a chunk body) reach past the end: encoding.js:497, where a number that runs out is KE_TRUNCATED (:353)
+  KE_GROUP_COLUMN   // an unknown GROUP_CARD column in the group of known scalar columns: readOperation (new.js:576-597) would read those as arrays
 };
 // error word: (code << 32 | item index); the smallest item index wins so that the error reported is
 // the one the sequential reference would hit first within a phase.
@@ -701,7 +706,7 @@ template <class S> HD void parse_change(const S& src, ColSlots<S>& slots, u32 of
       if (ix < 0) unk = true; else { slots.put(ix, ((dataPos + total - off) << 8) | l); seenA |= 1u << ix; }
       total += l;
     }
-    if (!bad && dataPos + total <= end) {
+    if (!bad && !unk && dataPos + total <= end) {   // (a column id this version does not know: the general walk looks at it)
       bool ok = (seenA >> CX_ACTION) & 1u; u32 v = 0;
 #define AMG_FAST_COL(IX) if (ok && ((seenA >> IX) & 1u)) { const u32 w = slots.get(IX); if (fast_value<IX>(src, off + (w >> 8), w & 0xffu, v)) slots.put(IX, v); else ok = false; }
       AMG_FAST_COL(CX_ACTION)
@@ -718,7 +723,7 @@ template <class S> HD void parse_change(const S& src, ColSlots<S>& slots, u32 of
         if (ok) {
           o.h.depsOff = depsOff; o.h.actorOff = actorOff; o.h.actorLen = actorLen; o.h.otherOff = otherOff; o.h.dirOff = dirPos; o.h.dataOff = dataPos;
           o.h.startOp = startOp; o.h.seq = seq;
-          o.nDeps = nDeps; o.nOther = nOther; o.nOps = 1; o.nPreds = predNum; o.single = true; o.unknownCols = unk;
+          o.nDeps = nDeps; o.nOther = nOther; o.nOps = 1; o.nPreds = predNum; o.single = true; o.unknownCols = false;
           o.seen = seenA & ~((1u << CX_VAL_RAW) | (1u << CX_CHLD_ACTOR) | (1u << CX_CHLD_CTR)); o.keyStrPos = (seenA >> CX_KEY_STR) & 1u ? keyStrPos : 0; o.valOff = valOff;
           return;
         }
@@ -729,7 +734,7 @@ template <class S> HD void parse_change(const S& src, ColSlots<S>& slots, u32 of
   if (!fastWalk) {   // general walk: ids / lengths of any size; the end of the directory is guessed (2 bytes per entry) and the walk repeated once with the real one
     o.unknownCols = false;
     for (int attempt = 0; attempt < 2; attempt++) {
-      ByteReaderT<S> d(src, dirPos, end); long long lastId = -1; u64 total = 0; u32 colErr = 0; bool orderBad = false, afterValLen = false;
+      ByteReaderT<S> d(src, dirPos, end); long long lastId = -1; u64 total = 0; u32 colErr = 0; bool orderBad = false, afterValLen = false, groupClash = false;
       single = true; haveAct = false; actLen = pnLen = 0; seen = 0; rawLen = 0; valOff = 0; keyStrPos = 0;
       for (u32 i = 0; i < nCols; i++) {
         const u64 id64 = d.uleb(), l64 = d.uleb();
@@ -739,7 +744,7 @@ template <class S> HD void parse_change(const S& src, ColSlots<S>& slots, u32 of
         if (!colErr) { if (id64 & 8) colErr = KE_COL_DEFLATE; else if ((u64)dataPos + total + l64 > (u64)end) colErr = KE_SUBARRAY; }
         const u32 id = id64 > 0xffffffffULL ? 0xffffffffu : (u32)id64, l = (u32)l64, pos = dataPos + (u32)total;
         const int ix = col_index_of(id);
-        if (ix < 0) o.unknownCols = true;
+        if (ix < 0) { o.unknownCols = true; if (id64 <= 0xffffffffULL && groups_known_columns(id)) groupClash = true; }
         else {
           if (ix == CX_ACTION) { actOff = (u32)total; actLen = l; haveAct = true; } else if (ix == CX_PRED_NUM) { pnOff = (u32)total; pnLen = l; }
           if (ix == CX_VAL_RAW) { if (afterValLen) { valOff = pos; rawLen = l; } }
@@ -754,7 +759,7 @@ template <class S> HD void parse_change(const S& src, ColSlots<S>& slots, u32 of
       }
       if (d.err) { dirErr = d.err; break; }
       if (d.pos != dataPos) { dataPos = d.pos; if (attempt == 0) continue; }   // directory longer than guessed: once more, with its real end
-      if (orderBad) dirErr = KE_COL_ORDER; else if (colErr) dirErr = colErr;
+      if (orderBad) dirErr = KE_COL_ORDER; else if (colErr) dirErr = colErr; else if (groupClash) dirErr = KE_GROUP_COLUMN;
       break;
     }
   }

@@ -56,7 +56,7 @@ def _check(rc, err):
 
 
 def _take_str(p):
-    s = C.string_at(p).decode('utf-8')
+    s = C.string_at(p).decode('utf-8', 'replace')   # (corrupted test inputs may carry bytes that are not UTF-8)
     lib().orc_free_mem(p)
     return s
 

@@ -57,8 +57,9 @@ def test_decoded_rows_emu(emu_doc, oracle_mod, cfg, n, a):
     assert parity_checks.check_decoded_rows_trace(emu_doc, oracle_mod, cfg, n, a) > 0
 
 
-def test_decoded_rows_corrupted_emu(emu_doc, oracle_mod):
-    parity_checks.check_decode_corrupted(emu_doc, oracle_mod, cases=80)
+@pytest.mark.parametrize('seed', [11, 10, 3, 101, 7])
+def test_decoded_rows_corrupted_emu(emu_doc, oracle_mod, seed):
+    parity_checks.check_decode_corrupted(emu_doc, oracle_mod, seed=seed, cases=200)   # seed 10: an unknown GROUP_CARD column in the key group
 
 
 def test_utf16_key_order_emu(emu_doc, oracle_mod):
