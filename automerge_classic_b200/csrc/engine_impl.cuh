@@ -658,7 +658,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     foreach(ctx, numRows, OldPairsKernel{succOff.p, succ.p, pos.p, ord, pairKey.p, pairIdx.p, pairSucc.p, pairPos.p, pairTime.p});
     foreach(ctx, M, PredPairsKernel{ops, idt, pos.p, rowOfOp.p, w, elemRow.p, keySlot.p, ord, pairKey.p, pairIdx.p, pairSucc.p, pairPos.p, pairTime.p, numSucc, errWord.p});
     foreach(ctx, M, DelKeyCheckKernel{arena.p, ops, idt, w, errWord.p});
-    foreach(ctx, M, IncCheckKernel{ops, idt, w, errWord.p});
+    foreach(ctx, M, IncCheckKernel{ops, idt, w, arena.p, errWord.p});
     {
       const u64 w2 = fetchErr();
       if (w2) {

@@ -235,7 +235,8 @@ struct PredPairsKernel {
       const size_t p = ops.predOff[i] + j; const size_t q = pairBase + p;
       const u32 target = id_lookup(t, ops.predId[p]);
       pairKey[q] = ord(ops.id[i]); pairIdx[q] = (u32)q; pairSucc[q] = ops.id[i]; pairTime[q] = ops.time[i];
-      if (target == ROW_NONE) { raise(errWord, KE_PRED_MISSING, p); pairPos[q] = 0; continue; }
+      // (an inserting op never meets its preds: the reference places it without looking at the document ops, new.js:1156-1160, 1254-1257)
+      if (target == ROW_NONE || (ops.flags[i] & F_INSERT)) { raise(errWord, KE_PRED_MISSING, p); pairPos[q] = 0; continue; }
       // the pred must be an op on the same key / list element of the same object, applied earlier (new.js:1173-1188, 1254-1257)
       bool ok = w.obj[target] == ops.obj[i] && w.time[target] < ops.time[i];
       if (ops.keyStrLen[i] != NULL32) {
@@ -251,10 +252,18 @@ struct PredPairsKernel {
   }
 };
 // an `inc` op needs a counter to add to: one of its preds must be a `set` of datatype counter (new.js:953-957)
+// (its number is decoded when the op is processed, whether or not the counter still shows: decodeValue, new.js:954,
+// columnar.js:300-329 - like that of a counter `set`, new.js:944)
 struct IncCheckKernel {
-  OpRows ops; IdTable t; DocRows w; u64* errWord;
+  OpRows ops; IdTable t; DocRows w; const u8* arena; u64* errWord;
   HD void operator()(size_t i) const {
-    if (flags_action(ops.flags[i]) != ACT_INC) return;
+    const u32 act = flags_action(ops.flags[i]), tag = ops.valLen[i] & 15;
+    if ((act == ACT_INC || (act == ACT_SET && tag == 8)) && (tag == 3 || tag == 4 || tag == 8 || tag == 9)) {
+      ByteReader r(arena, ops.valOff[i], ops.valOff[i] + (ops.valLen[i] >> 4));
+      if (tag == 3) r.uleb(); else r.sleb();
+      if (r.err) raise(errWord, r.err, i);
+    }
+    if (act != ACT_INC) return;
     bool ok = false;
     for (u32 j = 0; j < ops.predNum[i] && !ok; j++) {
       const u32 target = id_lookup(t, ops.predId[ops.predOff[i] + j]);
