@@ -264,6 +264,7 @@ struct IncCheckKernel {
       if (r.err) raise(errWord, r.err, i);
     }
     if (act != ACT_INC) return;
+    if (tag > 4 && tag != 8 && tag != 9) { raise(errWord, KE_UNSUPPORTED_OP, i); return; }   // += of a float / string / bytes value: JavaScript would concatenate or go floating point
     bool ok = false;
     for (u32 j = 0; j < ops.predNum[i] && !ok; j++) {
       const u32 target = id_lookup(t, ops.predId[ops.predOff[i] + j]);

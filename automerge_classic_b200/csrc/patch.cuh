@@ -208,15 +208,22 @@ struct GroupFinalKernel {   // pass 0: finalTime[g] = latest group on key group 
     for (size_t u = t0; u < t; u++) { const u32 i = c.opAt[u]; if (rowOfOp[i] != ROW_NONE) member[pos[rowOfOp[i]]] = 1; }
   }
 };
+// What `counterState.value += decodeValue(...).value` (new.js:944, 954) adds for a value of the given tag: the number; JavaScript
+// turns null / false into 0 and true into 1 (only invalid input carries those; anything else - float, string, bytes - is refused
+// by IncCheckKernel before it gets here).
+HD long long counter_operand(const u8* arena, u32 valLen, u32 valOff) {
+  const u32 tag = valLen & 15;
+  if (tag == 2) return 1;
+  if (tag < 2) return 0;
+  ByteReader br(arena, valOff, valOff + (valLen >> 4));
+  return tag == 3 ? (long long)br.uleb() : br.sleb();
+}
 // Counters (new.js:941-966): increments are successors of the `set` that created the counter. The counter shows with the
 // summed value once every successor turned out to be an `inc`; the reference emits it while processing the last of them.
 struct CounterKernel {
   const u8* arena; DocRows d; const u32* succOff; const u64* succ; const u32* groupOf; const u32* groupFirst; const u32* groupRows;
   u32* counterLast /* position of the last inc row, ROW_NONE = not a visible counter */; u64* counterTotal; u32* counterOwner /* per inc row that completes a counter: the counter's row */;
-  HD long long valueOf(u32 r) const {
-    ByteReader br(arena, d.valOff[r], d.valOff[r] + (d.valLen[r] >> 4));
-    return (d.valLen[r] & 15) == 3 ? (long long)br.uleb() : br.sleb();
-  }
+  HD long long valueOf(u32 r) const { return counter_operand(arena, d.valLen[r], d.valOff[r]); }
   HD void operator()(size_t p) const {
     counterLast[p] = ROW_NONE;
     if (flags_action(d.flags[p]) != ACT_SET || (d.valLen[p] & 15) != 8) return;
@@ -344,7 +351,7 @@ struct ListCtx {
   DocRows d; const u32* succCnt; const u32* newSuccCnt; const u32* firstNewSucc; const u32* groupOf; const u32* groupFirst; const u32* groupRows;
   const u8* arena; const u32* succOff; const u64* succ; const u32* succTime;   // successors of every row with their application times (0 = before this call)
   HD u32 minSucc(u32 p) const { return succCnt[p] > newSuccCnt[p] ? 0u : firstNewSucc[p]; }
-  HD long long valueOf(u32 r) const { ByteReader br(arena, d.valOff[r], d.valOff[r] + (d.valLen[r] >> 4)); return (d.valLen[r] & 15) == 3 ? (long long)br.uleb() : br.sleb(); }
+  HD long long valueOf(u32 r) const { return counter_operand(arena, d.valLen[r], d.valOff[r]); }
   HD bool isCounterRow(u32 r) const { return flags_action(d.flags[r]) == ACT_SET && (d.valLen[r] & 15) == 8; }
   // Counter row c of the element [e, e + rows) at time T: true if it has increments by then and nothing else overwrote it;
   // *total = summed value, *lastInc = position of the latest of those increments (new.js:941-966).
