@@ -503,7 +503,7 @@ inline void Engine::applyChangesOnce(const u8* const* bufs, const size_t* lens, 
     clockDev.ensure(ctx, A + 1); h2d(ctx, clockDev.p, clockNow.data(), A * 8);
     dev_memset(ctx, seqSlot.p, 0xff, (numNew + 1) * 4); dev_memset(ctx, flagWord.p, 0, 4);
     foreach(ctx, B, SeqScatterKernel{hot.p, applied.p, changeActor.p, appRank.p, actorBaseD.p, actorCnt.p, clockDev.p, seqSlot.p, flagWord.p});
-    foreach(ctx, B, SeqMonoKernel{hot.p, applied.p, changeActor.p, actorBaseD.p, clockDev.p, seqSlot.p, flagWord.p});
+    foreach(ctx, B, SeqMonoKernel{hot.p, applied.p, changeActor.p, actorBaseD.p, actorCnt.p, clockDev.p, seqSlot.p, flagWord.p});
     actorCntH.resize(A); d2h(ctx, actorCntH.data(), actorCnt.p, A * 4);
     if (readU32(flagWord.p)) {
       // error path: replay the sequence check in application order on the host to produce the reference's message

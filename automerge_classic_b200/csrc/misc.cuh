@@ -69,10 +69,12 @@ struct SeqScatterKernel {
   }
 };
 struct SeqMonoKernel {
-  const ChangeHot* meta; const u8* applied; const u32* changeActor; const u32* actorBase; const u64* clock; const u32* seqSlot; u32* bad;
+  const ChangeHot* meta; const u8* applied; const u32* changeActor; const u32* actorBase; const u32* actorCnt; const u64* clock; const u32* seqSlot; u32* bad;
   HD void operator()(size_t b) const {
     if (!applied[b]) return;
-    const u32 a = changeActor[b]; const u64 idx = meta[b].seq - clock[a] - 1;
+    const u32 a = changeActor[b]; const u64 seq = meta[b].seq, c0 = clock[a];
+    if (seq <= c0 || seq - c0 - 1 >= actorCnt[a]) return;   // out of range: SeqScatterKernel has reported it (and there is no slot to look at)
+    const u64 idx = seq - c0 - 1;
     if (idx > 0) { const u32 j = actorBase[a] + (u32)idx; if (seqSlot[j - 1] == EMPTY32 || seqSlot[j - 1] > seqSlot[j]) *bad = 1; }
   }
 };

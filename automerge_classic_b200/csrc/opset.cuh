@@ -70,7 +70,12 @@ struct ResolveRowsKernel {
   u64* errWord;
   HD void operator()(size_t r) const {
     const u64 obj = w.obj[r]; u32 orow = ROW_NONE;
-    if (obj != 0) { orow = id_lookup(t, obj); if (orow == ROW_NONE && r >= numOld) raise(errWord, KE_UNSUPPORTED_OP, r); }
+    if (obj != 0) {
+      orow = id_lookup(t, obj);
+      // the object of a new op must have been made by a make* op (only those are registered in objectMeta, new.js:904-927: an op in
+      // anything else makes the reference fail with a TypeError)
+      if (r >= numOld) { const u32 a = orow == ROW_NONE ? 1u : flags_action(w.flags[orow]); if (orow == ROW_NONE || !(a == ACT_MAKE_MAP || a == ACT_MAKE_LIST || a == ACT_MAKE_TEXT || a == ACT_MAKE_TABLE)) raise(errWord, KE_UNSUPPORTED_OP, r); }
+    }
     objRow[r] = orow;
     u32 er = ROW_NONE, pr = ROW_NONE;
     if (w.keyStrLen[r] == NULL32) {   // list / text row

@@ -189,6 +189,65 @@ def check_decode_corrupted(gpu_doc, oracle_mod, seed=11, cases=150):
     return same, refused
 
 
+def check_apply_corrupted(gpu_doc, oracle_mod, cases, seed=5):
+    """A damaged change (valid checksum) applied to a live document: whatever the oracle refuses the engine refuses too, and
+    what both accept gives the same patch. (The engine alone may refuse: it validates every column in full, the reference only
+    as far as it reads - DESIGN.md section 5.)"""
+    import random
+    from automerge_classic_b200 import tracegen
+    from automerge_classic_b200.engine import Unsupported
+    rnd = random.Random(seed)
+    both = refused = engine_only = 0
+    for case in range(cases):
+        cfg, a = rnd.choice(['C6', 'C7', 'C3', 'C8']), rnd.choice([1, 2, 3])
+        ch = tracegen.generate(cfg, 120, a, seed=rnd.randrange(1, 10**6)).changes()
+        k = rnd.randrange(5, len(ch) - 1)
+        c = bytearray(_inflated(ch[k]))
+        for _ in range(rnd.choice((1, 1, 2))):
+            pos, how = rnd.randrange(12, len(c)), rnd.random()
+            if how < 0.7:
+                c[pos] = rnd.randrange(256)
+            elif how < 0.85 and len(c) > 20:
+                del c[pos]
+            else:
+                c.insert(pos, rnd.randrange(256))
+        hdr_end = 9
+        while c[hdr_end] & 0x80:
+            hdr_end += 1
+        payload, lnb = bytes(c[hdr_end + 1:]), bytearray()
+        v = len(payload)
+        while True:
+            b = v & 0x7f; v >>= 7
+            lnb.append(b | (0x80 if v else 0))
+            if not v:
+                break
+        framed = b'\x01' + bytes(lnb) + payload
+        bad = bytes(c[:4]) + oracle_mod.sha256(framed)[:4] + framed
+        o, g = oracle_mod.OracleDoc(), gpu_doc()
+        o.apply_changes(ch[:k]); g.apply_changes(ch[:k])
+        eo = eg = None
+        try:
+            po = o.apply_changes([bad])
+        except Exception as e:
+            eo = str(e)
+        try:
+            pg = g.apply_changes([bad])
+        except Unsupported:
+            continue                      # a documented limit of the engine
+        except Exception as e:
+            eg = str(e)
+        if eo is not None:
+            assert eg is not None, ('accepted by the engine alone', cfg, case, eo, bad.hex())
+            refused += 1
+        elif eg is not None:
+            engine_only += 1
+        else:
+            d = replay.deep_equal(replay.decode(pg), replay.decode(po))
+            assert d is None, (cfg, case, d, bad.hex())
+            both += 1
+    return both, refused, engine_only
+
+
 def check_utf16_keys(gpu_doc, oracle_mod):
     """Map keys are ordered by UTF-16 code units (JavaScript `<`, new.js:84, 250, 1159), not by code points / UTF-8 bytes:
     the two differ when a supplementary-plane character meets U+E000..U+FFFF. Batch apply, incremental apply, save and load."""

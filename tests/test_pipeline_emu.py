@@ -214,3 +214,8 @@ def test_random_sweep_small_emu(emu_doc):
 
 def test_deflate_fuzz_emu(emu_doc, oracle_mod):
     parity_checks.check_deflate_fuzz(emu_doc, oracle_mod, 400)
+
+
+def test_apply_corrupted_emu(emu_doc, oracle_mod):
+    both, refused, engine_only = parity_checks.check_apply_corrupted(emu_doc, oracle_mod, 40)
+    assert both > 5 and refused > 5
