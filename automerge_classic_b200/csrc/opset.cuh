@@ -243,7 +243,9 @@ struct PredPairsKernel {
       // (an inserting op never meets its preds: the reference places it without looking at the document ops, new.js:1156-1160, 1254-1257)
       if (target == ROW_NONE || (ops.flags[i] & F_INSERT)) { raise(errWord, KE_PRED_MISSING, p); pairPos[q] = 0; continue; }
       // the pred must be an op on the same key / list element of the same object, applied earlier (new.js:1173-1188, 1254-1257)
-      bool ok = w.obj[target] == ops.obj[i] && w.time[target] < ops.time[i];
+      // ... and must have the smaller opId (every encoder's startOp exceeds what its author has seen): the reference only looks for
+      // a pred among the ops in front of the place the new op takes in opId order (new.js:1172-1187, 1254-1257)
+      bool ok = w.obj[target] == ops.obj[i] && w.time[target] < ops.time[i] && ord(ops.predId[p]) < ord(ops.id[i]);
       if (ops.keyStrLen[i] != NULL32) {
         ok = ok && w.keyStrLen[target] != NULL32;
         const u32 r = rowOfOp[i];
@@ -270,19 +272,22 @@ struct IncCheckKernel {
     }
     if (act != ACT_INC) return;
     if (tag > 4 && tag != 8 && tag != 9) { raise(errWord, KE_UNSUPPORTED_OP, i); return; }   // += of a float / string / bytes value: JavaScript would concatenate or go floating point
-    bool ok = false;
-    for (u32 j = 0; j < ops.predNum[i] && !ok; j++) {
+    bool ok = false, other = false;
+    for (u32 j = 0; j < ops.predNum[i]; j++) {
       const u32 target = id_lookup(t, ops.predId[ops.predOff[i] + j]);
-      ok = target != ROW_NONE && flags_action(w.flags[target]) == ACT_SET && (w.valLen[target] & 15) == 8;
+      if (target != ROW_NONE && flags_action(w.flags[target]) == ACT_SET && (w.valLen[target] & 15) == 8) ok = true; else other = true;
     }
     if (!ok) raise(errWord, KE_UNKNOWN_COUNTER, i);
+    else if (other) raise(errWord, KE_UNSUPPORTED_OP, i);   // an increment that also overwrites something that is no counter: no encoder writes one
   }
 };
 // list `del` ops have no row: their element must exist (seekToOp would throw first, new.js:293-301)
 struct DelElemCheckKernel {
   OpRows ops; IdTable t; DocRows w; u64* errWord;
   HD void operator()(size_t i) const {
-    if (flags_action(ops.flags[i]) != ACT_DEL || ops.keyStrLen[i] != NULL32) return;
+    if (flags_action(ops.flags[i]) != ACT_DEL) return;
+    if ((ops.flags[i] & F_INSERT) || ops.predNum[i] == 0) { raise(errWord, KE_UNSUPPORTED_OP, i); return; }   // an inserting `del` (the reference would make a list element of it), a `del` that deletes nothing: no encoder writes one
+    if (ops.keyStrLen[i] != NULL32) return;
     const u32 e = id_lookup(t, ops.key[i]);
     if (e == ROW_NONE || w.obj[e] != ops.obj[i] || !(w.flags[e] & F_INSERT) || w.keyStrLen[e] != NULL32) raise(errWord, KE_REF_ELEM, i);
   }
